@@ -1,0 +1,363 @@
+"""SeirmEngine — host driver of the sm_100a SEIRM step kernel (libat_seirm.so).
+
+Owns the device-resident working set of one shard (one process per GPU):
+  * the destination-sorted CSR contact graph (graph.ContactGraph),
+  * the packed SoA agent state (SeirmState: stage f32, timers i16, age u8),
+  * the double-buffered infectiousness arrays (1-byte code + 1-bit "is infectious" bitmap per
+    source agent) that one step writes for the next — the only per-step data another GPU needs,
+  * the reduction workspace and saved-for-backward buffers,
+and issues the launches on torch's current stream (so they can be captured into a CUDA graph).
+
+Replaces the reference's per-substep ATen op chains (new_transmission/transition.py:131-252,
+seirm_progression/transition.py:90-121) and its T-step autograd graph.
+"""
+import ctypes
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import _native as nat
+from .graph import ContactGraph
+
+
+# ----------------------------------------------------------------------------------------- model
+@dataclass
+class SeirmSpec:
+    """Constants of the SEIRM model (simulation_metadata + environment tables, config.yaml)."""
+    sfs: tuple = (0.35, 0.69, 1.03, 1.03, 1.03, 1.03, 1.27, 1.52, 1.52)
+    sfi: tuple = (0.0, 0.33, 0.72, 0.0, 0.0)
+    lam_gamma: tuple = ()
+    num_steps: int = 21
+    exposed_to_infected_time: int = 5
+    infected_to_recovered_time: int = 5
+    infinity_time: Optional[int] = None      # default num_steps + 20 (seirm_progression/transition.py:28-30)
+
+    def __post_init__(self):
+        if self.infinity_time is None:
+            self.infinity_time = self.num_steps + 20
+        if not self.lam_gamma:
+            self.lam_gamma = tuple(lam_gamma_integrals(5.5, 2.4, self.num_steps).tolist())
+        if not 1 <= len(self.lam_gamma) <= nat.MAX_LAMGAMMA:
+            raise ValueError(f"lam_gamma_integrals must have 1..{nat.MAX_LAMGAMMA} entries")
+        if len(self.sfs) > nat.MAX_SFS or len(self.sfi) > nat.MAX_SFI:
+            raise ValueError("SFSusceptibility / SFInfector table too long")
+
+    def to_struct(self, i_bar):
+        m = nat.SeirmModel()
+        m.n_sfs, m.n_sfi, m.n_lam_gamma = len(self.sfs), len(self.sfi), len(self.lam_gamma)
+        m.exposed_to_infected_time = int(self.exposed_to_infected_time)
+        m.infected_to_recovered_time = int(self.infected_to_recovered_time)
+        m.infinity_time = int(self.infinity_time)
+        m.i_bar = float(i_bar)
+        for i, v in enumerate(self.sfs):
+            m.sfs[i] = float(v)
+        for i, v in enumerate(self.sfi):
+            m.sfi[i] = float(v)
+        for i, v in enumerate(self.lam_gamma):
+            m.lam_gamma[i] = float(v)
+        return m
+
+
+def lam_gamma_integrals(scale, rate, t):
+    """Daily gamma-CDF differences, float32 (initialiser `get_lam_gamma_integrals`,
+    models/covid/substeps/utils.py:14-27; a = scale/b, b = rate^2/scale evaluated in float32)."""
+    from scipy.stats import gamma
+
+    scale_t = torch.tensor([float(scale)], dtype=torch.float32)
+    rate_t = torch.tensor([float(rate)], dtype=torch.float32)
+    b = rate_t * rate_t / scale_t
+    a = scale_t / b
+    a64, b64 = float(a), float(b)
+    vals = [gamma.cdf(i, a=a64, loc=0, scale=b64) - gamma.cdf(i - 1, a=a64, loc=0, scale=b64) for i in range(int(t))]
+    return torch.tensor(vals, dtype=torch.float64).float()
+
+
+# ----------------------------------------------------------------------------------------- state
+@dataclass
+class SeirmState:
+    """Packed SoA agent state of one shard + the (T,) daily series."""
+    stage: torch.Tensor             # (n,) float32 — integers, or k + (1-W) under soft isolation (Q4)
+    next_stage_time: torch.Tensor   # (n,) int16 (or float32 in the reference layout)
+    infected_time: torch.Tensor     # (n,) int16 (or float32)
+    age: torch.Tensor               # (n,) uint8 (or float32)
+    daily_infected: torch.Tensor    # (T,) float32
+    daily_deaths: torch.Tensor      # (T,) float32
+
+    @staticmethod
+    def from_initial(stage0, age, num_steps, device, packed=True):
+        """Initial timers as the reference's initialisers (utils.py:30-57): infected_time 500 / -1 / -3,
+        next_stage_time 500 / 3 / 5 for stage 0 / 1 / 2."""
+        stage = torch.as_tensor(stage0).reshape(-1).to(device=device, dtype=torch.float32).contiguous()
+        tdt = torch.int16 if packed else torch.float32
+        itime = torch.full_like(stage, 500, dtype=tdt)
+        nst = torch.full_like(stage, 500, dtype=tdt)
+        itime[stage == 1] = -1
+        itime[stage == 2] = -3
+        nst[stage == 1] = 3
+        nst[stage == 2] = 5
+        age_t = torch.as_tensor(age).reshape(-1).to(device=device)
+        age_t = age_t.to(torch.uint8 if packed else torch.float32).contiguous()
+        z = torch.zeros(num_steps, dtype=torch.float32, device=device)
+        return SeirmState(stage, nst, itime, age_t, z, z.clone())
+
+    def clone(self):
+        return SeirmState(*(getattr(self, f).clone() for f in
+                            ("stage", "next_stage_time", "infected_time", "age", "daily_infected", "daily_deaths")))
+
+
+@dataclass
+class NoiseSpec:
+    """Where the step's randomness comes from (stands in for torch.rand / torch.bernoulli)."""
+    seed: int = 0
+    isolation: str = "soft"          # 'soft' | 'hard' | 'none' | 'tensor'
+    p_isolate: float = 0.3
+    uniform: str = "hash"            # 'hash' | 'tensor'
+    isolation_tensor: Optional[torch.Tensor] = None   # (n,) or (T,n) float32
+    uniform_tensor: Optional[torch.Tensor] = None
+
+    def iso_mode(self):
+        return {"tensor": nat.ISO_TENSOR, "soft": nat.ISO_HASH_SOFT, "hard": nat.ISO_HASH_HARD,
+                "none": nat.ISO_NONE}[self.isolation]
+
+    def u_mode(self):
+        return {"tensor": nat.U_TENSOR, "hash": nat.U_HASH}[self.uniform]
+
+
+_TIMER_TAG = {torch.float32: nat.TIMER_F32, torch.int16: nat.TIMER_I16}
+_AGE_TAG = {torch.float32: nat.AGE_F32, torch.uint8: nat.AGE_U8}
+
+
+def _ptr(t, dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (agenttorch_b200 has no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+class SeirmEngine:
+    def __init__(self, graph: ContactGraph, spec: SeirmSpec, process_group=None, use_smem_bitmap=-1, grid=0):
+        if not graph.row_ptr.is_cuda:
+            raise RuntimeError("SeirmEngine needs the contact graph on a CUDA device; there is no CPU fallback")
+        self.lib = nat.lib()
+        self.graph = graph
+        self.spec = spec
+        self.device = graph.device
+        self.model = spec.to_struct(graph.i_bar)
+        self.pg = process_group
+        self.use_smem_bitmap = use_smem_bitmap
+        self.grid = grid
+        n_src = graph.n_sources
+        self.n_code = ((n_src + 1023) // 1024) * 1024
+        words = self.n_code // 32
+        self.code = [torch.zeros(self.n_code, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.bitmap = [torch.zeros(words + 4, dtype=torch.int32, device=self.device) for _ in range(2)]
+        self.cur = 0
+        self.workspace = torch.zeros(self.lib.at_seirm_workspace_bytes() // 8 + 8, dtype=torch.float64, device=self.device)
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.seed_buf = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.launch_count = 0
+        self._graphs = {}
+        self._saved = {}
+
+    # ------------------------------------------------------------------------------ raw launch
+    def launch(self, state: SeirmState, *, flags, t, t_encode=None, code_in=None, code_out=None,
+               noise: Optional[NoiseSpec] = None, isolation=None, uniform=None, r_value=None, r_index=0,
+               m_value=None, dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None,
+               seed_ptr=None):
+        g = self.graph
+        a = nat.SeirmLaunch()
+        a.abi_version = nat.ABI_VERSION
+        a.flags = int(flags)
+        a.t = int(t)
+        a.t_encode = int(t + 1 if t_encode is None else t_encode)
+        a.n_rows, a.n_sources, a.row_offset = g.n_rows, self.n_code, g.row_offset
+        a.row_ptr = _ptr(g.row_ptr, torch.int32, "row_ptr")
+        a.col_idx = _ptr(g.col_idx, torch.int32, "col_idx")
+        a.edge_weight = _ptr(g.edge_weight, torch.float32, "edge_weight")
+        if state.stage.shape[0] != g.n_rows:
+            raise RuntimeError("state size does not match the graph shard")
+        a.stage = _ptr(state.stage, torch.float32, "stage")
+        if state.next_stage_time.dtype not in _TIMER_TAG or state.infected_time.dtype != state.next_stage_time.dtype:
+            raise RuntimeError("timers must both be float32 or both int16")
+        a.next_stage_time = _ptr(state.next_stage_time, None, "next_stage_time")
+        a.infected_time = _ptr(state.infected_time, None, "infected_time")
+        a.timer_dtype = _TIMER_TAG[state.next_stage_time.dtype]
+        if state.age.dtype not in _AGE_TAG:
+            raise RuntimeError("age must be float32 or uint8")
+        a.age = _ptr(state.age, None, "age")
+        a.age_dtype = _AGE_TAG[state.age.dtype]
+        ci = self.cur if code_in is None else code_in
+        co = 1 - ci if code_out is None else code_out
+        a.code_in = _ptr(self.code[ci], torch.uint8)
+        a.bitmap_in = _ptr(self.bitmap[ci], torch.int32)
+        a.code_out = _ptr(self.code[co], torch.uint8)
+        a.bitmap_out = _ptr(self.bitmap[co], torch.int32)
+        noise = noise or NoiseSpec()
+        a.iso_mode, a.u_mode = noise.iso_mode(), noise.u_mode()
+        a.isolation = _ptr(isolation, torch.float32, "isolation")
+        a.uniform = _ptr(uniform, torch.float32, "uniform")
+        a.seed = int(noise.seed) & ((1 << 64) - 1)
+        a.seed_ptr = _ptr(seed_ptr, torch.int64, "seed_ptr")
+        a.p_isolate = float(noise.p_isolate)
+        a.r_value = _ptr(r_value, torch.float32, "r_value")
+        a.r_index = int(r_index)
+        a.m_value = _ptr(m_value, torch.float32, "m_value")
+        a.daily_infected = _ptr(state.daily_infected, torch.float32, "daily_infected")
+        a.daily_deaths = _ptr(state.daily_deaths, torch.float32, "daily_deaths")
+        a.dne_dr = _ptr(dne_dr, torch.float32, "dne_dr")
+        a.sum_dne_dr = _ptr(sum_dne_dr, torch.float32, "sum_dne_dr")
+        a.death_count = _ptr(death_count, torch.float32, "death_count")
+        a.recovered_step = _ptr(recovered_step, torch.uint8, "recovered_step")
+        a.partials = _ptr(self.workspace, torch.float64)
+        a.error_flag = _ptr(self.error_flag, torch.int32)
+        a.grid = int(self.grid)
+        a.use_smem_bitmap = int(self.use_smem_bitmap)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(self.lib.at_seirm_step(ctypes.byref(self.model), ctypes.byref(a), ctypes.c_void_p(stream)))
+        self.launch_count += 1
+
+    # ------------------------------------------------------------------------ halo exchange
+    def exchange(self, buf_index):
+        """Make every rank's freshly written slice of code/bitmap visible to all ranks (the per-step
+        halo exchange of boundary-agent infectiousness).  No-op on one GPU."""
+        if self.pg is None:
+            return
+        import torch.distributed as dist
+
+        world = dist.get_world_size(self.pg)
+        per = self.n_code // world
+        rank = dist.get_rank(self.pg)
+        code = self.code[buf_index]
+        dist.all_gather_into_tensor(code, code[rank * per:(rank + 1) * per], group=self.pg)
+        bm = self.bitmap[buf_index][: self.n_code // 32]
+        wper = per // 32
+        dist.all_gather_into_tensor(bm, bm[rank * wper:(rank + 1) * wper], group=self.pg)
+
+    # ----------------------------------------------------------------------------- substeps
+    def encode(self, state, t):
+        """Write the infectiousness code/bitmap of step `t` from the current state into the live buffer."""
+        self.launch(state, flags=nat.DO_ENCODE, t=0, t_encode=t, code_in=1 - self.cur, code_out=self.cur)
+        self.exchange(self.cur)
+
+    def step(self, state, t, noise, r_value, r_index, m_value, *, isolation=None, uniform=None, flags=None,
+             dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None, seed_ptr=None):
+        """One fused step: transmission + progression + encode of step t+1; flips the live buffer."""
+        flags = (nat.DO_TRANSMISSION | nat.DO_PROGRESSION | nat.DO_ENCODE) if flags is None else flags
+        self.launch(state, flags=flags, t=t, t_encode=t + 1, noise=noise, isolation=isolation, uniform=uniform,
+                    r_value=r_value, r_index=r_index, m_value=m_value, dne_dr=dne_dr, sum_dne_dr=sum_dne_dr,
+                    death_count=death_count, recovered_step=recovered_step, seed_ptr=seed_ptr)
+        if flags & nat.DO_ENCODE:
+            self.cur = 1 - self.cur
+            self.exchange(self.cur)
+
+    # ------------------------------------------------------------------------------ episode
+    def saved_buffers(self, num_steps, want_grad):
+        key = (num_steps, want_grad)
+        if key not in self._saved:
+            n, dev = self.graph.n_rows, self.device
+            ld = ((n + 31) // 32) * 32
+            self._saved[key] = {
+                "ld": ld,
+                "dne_dr": torch.zeros((num_steps, ld), dtype=torch.float32, device=dev) if want_grad else None,
+                "recovered_step": torch.full((n,), 255, dtype=torch.uint8, device=dev),
+                "sum_dne_dr": torch.zeros(num_steps, dtype=torch.float32, device=dev),
+                "death_count": torch.zeros(num_steps, dtype=torch.float32, device=dev),
+                "r_steps": torch.zeros(num_steps, dtype=torch.float32, device=dev),
+                "m_value": torch.zeros(1, dtype=torch.float32, device=dev),
+            }
+        return self._saved[key]
+
+    def _issue_episode(self, state, num_steps, noise, sv, want_grad, t0=0):
+        sv["recovered_step"].fill_(255)
+        self.encode(state, t0)
+        for k in range(num_steps):
+            t = t0 + k
+            iso = noise.isolation_tensor[k] if noise.isolation == "tensor" else None
+            uni = noise.uniform_tensor[k] if noise.uniform == "tensor" else None
+            self.step(state, t, noise, sv["r_steps"], k, sv["m_value"], isolation=iso, uniform=uni,
+                      dne_dr=sv["dne_dr"][k] if want_grad else None, sum_dne_dr=sv["sum_dne_dr"],
+                      death_count=sv["death_count"], recovered_step=sv["recovered_step"], seed_ptr=self.seed_buf)
+
+    def run_episode(self, state, r_steps, m_value, num_steps, noise: NoiseSpec, want_grad=False, cuda_graph=False):
+        """Advance `state` in place through `num_steps` steps (t = 0..num_steps-1, as Runner.step does).
+
+        r_steps: (num_steps,) float32 device tensor with the per-step R (transition.py:139-143);
+        m_value: (1,) float32.  Returns the saved-for-backward buffers (views owned by the engine).
+        With cuda_graph=True the launch sequence is captured once per (state buffers, shape) and
+        replayed; the seed, R and M are read from device memory so the graph is reusable."""
+        sv = self.saved_buffers(num_steps, want_grad)
+        sv["r_steps"].copy_(r_steps.detach().reshape(-1)[:num_steps])
+        sv["m_value"].copy_(m_value.detach().reshape(-1)[:1])
+        self.seed_buf.fill_(_as_i64(noise.seed))
+        if not cuda_graph or self.pg is not None:
+            self._issue_episode(state, num_steps, noise, sv, want_grad)
+            return sv
+        key = (num_steps, want_grad, noise.isolation, noise.uniform, float(noise.p_isolate),
+               state.stage.data_ptr(), state.next_stage_time.data_ptr(), state.infected_time.data_ptr(),
+               state.age.data_ptr(), state.daily_infected.data_ptr(), state.daily_deaths.data_ptr(),
+               None if noise.isolation_tensor is None else noise.isolation_tensor.data_ptr(),
+               None if noise.uniform_tensor is None else noise.uniform_tensor.data_ptr())
+        entry = self._graphs.get(key)
+        if entry is None:
+            cur0 = self.cur
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            # capture issues no work; the replay below is the execution
+            with torch.cuda.graph(g):
+                self._issue_episode(state, num_steps, noise, sv, want_grad)
+            entry = (g, cur0, self.cur)
+            self._graphs[key] = entry
+            self.cur = cur0
+        g, cur0, cur1 = entry
+        if self.cur != cur0:                 # the captured sequence starts from buffer cur0
+            self.cur = cur0
+        g.replay()
+        self.cur = cur1
+        return sv
+
+    def episode_backward(self, sv, num_steps, g_daily_infected, g_daily_deaths, m_value):
+        """grad wrt the per-step R (num_steps,) and M (1,) — at_seirm_episode_backward."""
+        dev = self.device
+        grad_r = torch.empty(num_steps, dtype=torch.float32, device=dev)
+        grad_m = torch.empty(1, dtype=torch.float32, device=dev)
+        gi = g_daily_infected.detach().reshape(-1)[:num_steps].to(torch.float32).contiguous()
+        gd = g_daily_deaths.detach().reshape(-1)[:num_steps].to(torch.float32).contiguous()
+        mv = m_value.detach().reshape(-1)[:1].to(torch.float32).contiguous()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        nat.check(self.lib.at_seirm_episode_backward(
+            int(num_steps), int(self.graph.n_rows), int(sv["ld"]), _ptr(sv["dne_dr"]), _ptr(sv["recovered_step"]),
+            _ptr(sv["sum_dne_dr"]), _ptr(sv["death_count"]), _ptr(gi), _ptr(gd), _ptr(mv), _ptr(grad_r), _ptr(grad_m),
+            _ptr(self.workspace), 0, ctypes.c_void_p(stream)))
+        self.launch_count += 1
+        if self.pg is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(grad_r, group=self.pg)
+            dist.all_reduce(grad_m, group=self.pg)
+        return grad_r, grad_m
+
+    def check_errors(self):
+        if int(self.error_flag.item()) != 0:
+            raise RuntimeError("lam_gamma_integrals index out of range during the episode (SURVEY.md A.2 Q10)")
+
+
+def _as_i64(v):
+    v = int(v) & ((1 << 64) - 1)
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def noise_fill(out, seed, step, what, p_isolate=0.3, id_offset=0):
+    """Fill `out` (float32 CUDA tensor) with the counter-hash noise of (seed, step): what =
+    'uniform' (exposure U), 'isolation' (uniform W) or 'isolation_hard'."""
+    code = {"uniform": 0, "isolation": 1, "isolation_hard": 2}[what]
+    stream = torch.cuda.current_stream(out.device).cuda_stream
+    nat.check(nat.lib().at_noise_fill(_ptr(out, torch.float32, "out"), out.numel(), int(id_offset),
+                                      int(seed) & ((1 << 64) - 1), int(step), code, float(p_isolate),
+                                      ctypes.c_void_p(stream)))
+    return out

@@ -1,0 +1,215 @@
+"""Contact graph in the layout the sm_100a step kernel reads: destination-sorted CSR.
+
+Replaces the `(edge_index, edge_attr)` COO pair that the reference hands to PyG
+(`network_from_file`, models/covid/substeps/utils.py:129-148; consumed by
+`NewTransmission.forward`, new_transmission/transition.py:165-218).
+
+* rows = destination agents (`edge_index[1]`), columns = source agents (`edge_index[0]`);
+* the sort is STABLE, so inside a row the edges keep the order of the original edge list —
+  the order in which the reference's scatter-add (index_add on CPU) accumulates them;
+* edges are used as written: directed, duplicates and self-loops kept;
+* `col_idx` is int32, padded by >= 4 entries and 16-byte aligned for 128-bit loads;
+* `i_bar` reproduces quirk Q1: the reference's `torch.gather(x_i[:,4], 0, edge_type)` with
+  edge_type == c for every edge reads ONE scalar, `mean_interactions[dst[c]]` (c = 1 in
+  `network_from_file`), indexed in the ORIGINAL edge order.
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+COL_PAD = 8
+
+
+@dataclass
+class ContactGraph:
+    n_rows: int                      # destination agents owned by this shard
+    n_sources: int                   # size of the source id space (code / bitmap arrays)
+    row_offset: int                  # global id of local row 0 (multiple of 32)
+    row_ptr: torch.Tensor            # (n_rows+1,) int32
+    col_idx: torch.Tensor            # (E + COL_PAD,) int32, source ids
+    num_edges: int
+    edge_weight: Optional[torch.Tensor] = None   # (E + COL_PAD,) float32 or None when all == 1
+    i_bar: float = 1.0
+    i_bar_agent: int = -1            # agent whose mean_interactions is I_bar (dst of original edge #c)
+
+    @property
+    def device(self):
+        return self.row_ptr.device
+
+    def to(self, device):
+        return ContactGraph(self.n_rows, self.n_sources, self.row_offset, self.row_ptr.to(device),
+                            self.col_idx.to(device), self.num_edges,
+                            None if self.edge_weight is None else self.edge_weight.to(device),
+                            self.i_bar, self.i_bar_agent)
+
+    def edge_index(self):
+        """COO view in CSR order: (2,E) int64 [src; dst] with global destination ids."""
+        deg = (self.row_ptr[1:] - self.row_ptr[:-1]).long()
+        dst = torch.repeat_interleave(torch.arange(self.n_rows, device=self.device), deg) + self.row_offset
+        return torch.stack((self.col_idx[: self.num_edges].long(), dst))
+
+    def avg_degree(self):
+        return self.num_edges / max(self.n_rows, 1)
+
+
+def _pad_cols(col, pad_value=0):
+    out = torch.full((col.numel() + COL_PAD,), pad_value, dtype=col.dtype, device=col.device)
+    out[: col.numel()] = col
+    return out
+
+
+def build_contact_graph(edge_index, num_agents, edge_attr=None, mean_interactions=None, device=None):
+    """COO (reference format) -> ContactGraph.
+
+    edge_index: (2,E) integer tensor [src; dst]; edge_attr: optional (2,E) [edge_type; weight]
+    (utils.py:143-145); mean_interactions: (N,) or (N,1) used for I_bar (Q1)."""
+    edge_index = torch.as_tensor(edge_index)
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError("edge_index must have shape (2, E)")
+    device = torch.device(device) if device is not None else edge_index.device
+    e = int(edge_index.shape[1])
+    if e >= 2**31 - COL_PAD:
+        raise ValueError("more than 2^31 edges in one shard: partition the graph first")
+    src = edge_index[0].to(device=device, dtype=torch.int64)
+    dst = edge_index[1].to(device=device, dtype=torch.int64)
+    if e and (int(src.min()) < 0 or int(src.max()) >= num_agents or int(dst.min()) < 0 or int(dst.max()) >= num_agents):
+        raise ValueError("edge endpoint out of range")
+
+    weight = None
+    i_bar, i_bar_agent = 1.0, -1
+    etype_const = 1
+    if edge_attr is not None:
+        edge_attr = torch.as_tensor(edge_attr)
+        etype = edge_attr[0].to(torch.int64)
+        if e:
+            etype_const = int(etype[0])
+            if not bool((etype == etype_const).all()):
+                raise NotImplementedError("per-edge edge_type (multi-layer networks) is not supported yet")
+        w = edge_attr[1].to(device=device, dtype=torch.float32)
+        if e and not bool((w == 1.0).all()):
+            weight = w
+    if e and mean_interactions is not None:
+        if not 0 <= etype_const < e:
+            raise IndexError("edge_type indexes past the edge list (the reference's gather would fail)")
+        i_bar_agent = int(dst[etype_const])
+        i_bar = float(torch.as_tensor(mean_interactions).reshape(-1)[i_bar_agent])
+
+    order = torch.sort(dst, stable=True).indices
+    col = src[order].to(torch.int32)
+    counts = torch.bincount(dst, minlength=num_agents)
+    row_ptr = torch.zeros(num_agents + 1, dtype=torch.int64, device=device)
+    row_ptr[1:] = torch.cumsum(counts, 0)
+    g = ContactGraph(num_agents, num_agents, 0, row_ptr.to(torch.int32), _pad_cols(col), e,
+                     None if weight is None else _pad_cols(weight[order]), i_bar, i_bar_agent)
+    return g
+
+
+# Astoria's age histogram (populations/astoria/age.pickle), used for synthetic populations
+ASTORIA_AGE_COUNTS = (6723, 11573, 5724, 4647, 3910, 4941)
+
+
+def synthetic_population(num_agents, seed, initial_exposed=0.01, device="cpu"):
+    """age (uint8, categorical with astoria's proportions) and initial stage (float32: 1 for a
+    fraction `initial_exposed`, else 0) — the inputs of BASELINE configs C2/C3/C5."""
+    gen = torch.Generator(device="cpu").manual_seed(int(seed))
+    probs = torch.tensor(ASTORIA_AGE_COUNTS, dtype=torch.float64)
+    age = torch.multinomial(probs / probs.sum(), num_agents, replacement=True, generator=gen).to(torch.uint8)
+    stage0 = (torch.rand(num_agents, generator=gen) < initial_exposed).to(torch.float32)
+    return age.to(device), stage0.to(device)
+
+
+def mean_interactions_from_age(age):
+    """2 / 3 / 4 contacts for children / adults / elderly (utils.py:88-109)."""
+    age = age.reshape(-1).to(torch.int64)
+    out = torch.full(age.shape, 3.0, dtype=torch.float32, device=age.device)
+    out[age < 1] = 2.0
+    out[age > 4] = 4.0
+    return out
+
+
+def synthetic_contact_graph(num_agents, avg_degree, seed, family="rand", degree_dist="poisson",
+                            block=65536, p_local=0.8, device="cpu", row_begin=0, row_end=None,
+                            mean_interactions=None):
+    """Seeded synthetic contact graph generated directly in CSR form (no sort needed).
+
+    In-degree ~ Poisson(avg_degree) or negative-binomial with the same mean (dispersion 4, as the
+    census generator data/census/generate/mobility_network.py:12-19 does per agent).  Sources:
+      family="rand": uniform over all agents (the reference generator's configuration model);
+      family="comm": with probability p_local uniform inside the destination's block of `block`
+                     consecutive ids, else uniform over all agents (community structure).
+    Only rows [row_begin, row_end) are generated (a rank's shard); every row has its own generator
+    stream, so shards of different world sizes describe the same global graph when generated in
+    chunks aligned to `gen_chunk`.
+    """
+    row_end = num_agents if row_end is None else row_end
+    gen_chunk = 1 << 20
+    dev = torch.device(device)
+    cols, degs = [], []
+    for c0 in range((row_begin // gen_chunk) * gen_chunk, row_end, gen_chunk):
+        c1 = min(c0 + gen_chunk, num_agents)
+        g = torch.Generator(device=dev).manual_seed(int(seed) * 1000003 + c0 // gen_chunk)
+        n = c1 - c0
+        if degree_dist == "poisson":
+            deg = torch.poisson(torch.full((n,), float(avg_degree), device=dev), generator=g)
+        elif degree_dist == "nb":
+            k = 4.0
+            u = torch.rand((n, int(k)), device=dev, generator=g).clamp_min(1e-12)
+            rate = -torch.log(u).sum(1) * (float(avg_degree) / k)          # Gamma(k, d/k)
+            deg = torch.poisson(rate, generator=g)
+        else:
+            raise ValueError(degree_dist)
+        deg = deg.to(torch.int64)
+        total = int(deg.sum())
+        dst_local = torch.repeat_interleave(torch.arange(n, device=dev), deg)
+        src = torch.randint(0, num_agents, (total,), device=dev, generator=g)
+        if family == "comm":
+            local = torch.rand(total, device=dev, generator=g) < p_local
+            blk0 = ((dst_local + c0) // block) * block
+            blk_n = torch.clamp(torch.full_like(blk0, block), max=num_agents - blk0)
+            src_local = blk0 + (torch.rand(total, device=dev, generator=g) * blk_n).long().clamp_max(blk_n - 1)
+            src = torch.where(local, src_local, src)
+        elif family != "rand":
+            raise ValueError(family)
+        # keep only the rows of this shard
+        lo, hi = max(row_begin, c0) - c0, min(row_end, c1) - c0
+        if lo > 0 or hi < n:
+            starts = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+            starts[1:] = torch.cumsum(deg, 0)
+            src = src[int(starts[lo]): int(starts[hi])]
+            deg = deg[lo:hi]
+        cols.append(src.to(torch.int32))
+        degs.append(deg)
+    deg = torch.cat(degs) if degs else torch.zeros(0, dtype=torch.int64, device=dev)
+    col = torch.cat(cols) if cols else torch.zeros(0, dtype=torch.int32, device=dev)
+    e = int(col.numel())
+    if e >= 2**31 - COL_PAD:
+        raise ValueError("more than 2^31 edges in one shard")
+    row_ptr = torch.zeros(row_end - row_begin + 1, dtype=torch.int64, device=dev)
+    row_ptr[1:] = torch.cumsum(deg, 0)
+    graph = ContactGraph(row_end - row_begin, num_agents, row_begin, row_ptr.to(torch.int32), _pad_cols(col), e)
+    if mean_interactions is not None and e > 1 and row_begin == 0:
+        # canonical edge list = CSR order; original edge #1 is the second CSR entry (Q1)
+        first_rows = torch.searchsorted(row_ptr, torch.tensor([1], device=dev), right=True) - 1
+        graph.i_bar_agent = int(first_rows[0])
+        graph.i_bar = float(mean_interactions.reshape(-1)[graph.i_bar_agent])
+    return graph
+
+
+def shard_bounds(num_agents, world_size, align=1024):
+    """Contiguous ownership ranges, boundaries aligned so that bitmap words never straddle ranks."""
+    per = -(-num_agents // world_size)
+    per = -(-per // align) * align
+    return [(min(r * per, num_agents), min((r + 1) * per, num_agents)) for r in range(world_size)]
+
+
+def shard_graph(graph, row_begin, row_end):
+    """Rows [row_begin,row_end) of a full (row_offset == 0) graph as a shard with global column ids."""
+    if graph.row_offset != 0:
+        raise ValueError("shard_graph expects the full graph")
+    rp = graph.row_ptr.long()
+    e0, e1 = int(rp[row_begin]), int(rp[row_end])
+    col = graph.col_idx[e0:e1].clone()
+    w = None if graph.edge_weight is None else _pad_cols(graph.edge_weight[e0:e1].clone())
+    return ContactGraph(row_end - row_begin, graph.n_sources, row_begin, (rp[row_begin: row_end + 1] - e0).to(torch.int32),
+                        _pad_cols(col), e1 - e0, w, graph.i_bar, graph.i_bar_agent)

@@ -1,0 +1,164 @@
+/*
+ * at_seirm.h — C ABI of libat_seirm.so: the B200 (sm_100a) implementation of AgentTorch's
+ * per-step SEIRM agent update.
+ *
+ * The reference has no native layer: its "FFI" for this path is the Python operator surface
+ *   - NewTransmission.forward           agent_torch/models/covid/substeps/new_transmission/transition.py:131-252
+ *       (PyG MessagePassing.propagate gather + scatter-add, _lam :52-85, StraightThroughBernoulli
+ *        core/distributions/distributions.py:8-24, update_stages/.._times :102-129)
+ *   - SEIRMProgression.forward          agent_torch/models/covid/substeps/seirm_progression/transition.py:90-121
+ *   - torch autograd over both          (loss.backward() through an episode)
+ * Each entry point below names the reference function(s) it replaces.  The library is called
+ * from Python through ctypes by torch.library custom ops (agenttorch_b200/ops.py); see
+ * INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (message via
+ * at_last_error()); nothing throws across the boundary.  The library is stateless: it allocates
+ * nothing and owns nothing — every buffer is caller-allocated DEVICE memory (all pointers are
+ * device pointers unless the comment says host) and every launch goes to the caller's stream,
+ * so launches are legal inside CUDA-graph capture.
+ */
+#ifndef AT_SEIRM_H
+#define AT_SEIRM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AT_SEIRM_ABI_VERSION 3
+#define AT_MAX_SFS 16        /* SFSusceptibility entries (config.yaml:206-223 has 9)   */
+#define AT_MAX_SFI 8         /* SFInfector entries (config.yaml:191-205 has 5)         */
+#define AT_MAX_LAMGAMMA 84   /* lam_gamma_integrals entries; 1 + 3*K codes fit a byte  */
+
+/* dtype tags for the timer / age arrays */
+#define AT_TIMER_F32 0       /* reference layout: float32 holding integers (Q3)        */
+#define AT_TIMER_I16 1       /* packed engine layout                                   */
+#define AT_AGE_F32 0
+#define AT_AGE_U8 1
+
+/* isolation decision W (MakeIsolationDecision.forward, new_transmission/action.py:51-67) */
+#define AT_ISO_TENSOR 0      /* W read from `isolation` (float32, any value in [0,1])   */
+#define AT_ISO_HASH_SOFT 1   /* W = uniform[0,1) from the counter hash (action.py:54)   */
+#define AT_ISO_HASH_HARD 2   /* W = 1 with probability p_isolate else 0                 */
+#define AT_ISO_NONE 3        /* W = 0                                                   */
+/* exposure uniform U (stands in for torch.bernoulli, distributions.py:16) */
+#define AT_U_TENSOR 0        /* U read from `uniform` (float32)                         */
+#define AT_U_HASH 1          /* U from the counter hash: top 24 bits of SplitMix64      */
+
+/* what one launch does */
+#define AT_DO_TRANSMISSION 1 /* substep '0' transition (NewTransmission.forward)        */
+#define AT_DO_PROGRESSION 2  /* substep '1' transition (SEIRMProgression.forward)       */
+#define AT_DO_ENCODE 4       /* write the infectiousness code/bitmap of step `t_encode` */
+
+/* Model constants (simulation_metadata + environment tables of config.yaml). Host struct. */
+typedef struct at_seirm_model {
+    int32_t n_sfs, n_sfi, n_lam_gamma;
+    int32_t exposed_to_infected_time;   /* EXPOSED_TO_INFECTED_TIME, transition.py:25-27      */
+    int32_t infected_to_recovered_time; /* INFECTED_TO_RECOVERED_TIME, progression :31-33      */
+    int32_t infinity_time;              /* num_steps_per_episode + 20, progression :28-30      */
+    float i_bar;                        /* mean_interactions[dst[edge_type]] — one scalar (Q1) */
+    float sfs[AT_MAX_SFS];
+    float sfi[AT_MAX_SFI];
+    float lam_gamma[AT_MAX_LAMGAMMA];
+} at_seirm_model;
+
+/* One launch of the step kernel.  Host struct, passed by pointer; pointers inside are device. */
+typedef struct at_seirm_launch {
+    int32_t abi_version;        /* = AT_SEIRM_ABI_VERSION */
+    int32_t flags;              /* AT_DO_* */
+    int32_t t;                  /* current_step */
+    int32_t t_encode;           /* step whose infectiousness is encoded (normally t+1) */
+    /* destination-sorted CSR of the rows this rank owns (stable: original edge order in a row) */
+    int64_t n_rows;             /* owned agents */
+    int64_t n_sources;          /* length of code_in / 32*words of bitmap_in (>= max col_idx+1) */
+    int64_t row_offset;         /* global id of local row 0: index of this rank's slice in code/bitmap,
+                                   and the agent id fed to the counter hash */
+    const int32_t* row_ptr;     /* n_rows+1 */
+    const int32_t* col_idx;     /* E (+ >= 4 ints of padding), source ids; 16-byte aligned */
+    const float* edge_weight;   /* E or NULL when all weights are 1 (utils.py:144) */
+    /* agent state, updated in place */
+    float* stage;               /* n_rows */
+    void* next_stage_time;      /* n_rows, dtype timer_dtype */
+    void* infected_time;        /* n_rows */
+    const void* age;            /* n_rows, dtype age_dtype */
+    int32_t timer_dtype, age_dtype;
+    /* infectiousness of step t (read) and of step t_encode (written for owned rows) */
+    const uint8_t* code_in;     /* n_sources */
+    const uint32_t* bitmap_in;  /* ceil(n_sources/32) */
+    uint8_t* code_out;          /* n_sources; written at [row_offset, row_offset+n_rows) */
+    uint32_t* bitmap_out;       /* row_offset must be a multiple of 32 */
+    /* noise */
+    int32_t iso_mode, u_mode;
+    const float* isolation;     /* n_rows or NULL */
+    const float* uniform;       /* n_rows or NULL */
+    uint64_t seed;
+    const uint64_t* seed_ptr;   /* optional device word overriding `seed` (keeps CUDA graphs seed-agnostic) */
+    float p_isolate;
+    int32_t _pad0;
+    /* parameters (device scalars so that no host sync is needed) */
+    const float* r_value;       /* R of this step = r_value[r_index] */
+    int64_t r_index;
+    const float* m_value;       /* M = m_value[0] */
+    /* outputs */
+    float* daily_infected;      /* [t] += sum(ne)              (transition.py:235) */
+    float* daily_deaths;        /* [t] += M * sum(stage*rd/2)  (progression :41-61) */
+    float* dne_dr;              /* n_rows or NULL: d ne_i / d R, saved for backward */
+    float* sum_dne_dr;          /* [t] = sum_i dne_dr, or NULL */
+    float* death_count;         /* [t] = sum(stage*rd/2), or NULL (d daily_deaths / d M) */
+    uint8_t* recovered_step;    /* n_rows or NULL: set to t where the I->R transition fires */
+    /* workspace: caller-zeroed once; 4 doubles per CTA + one ticket word at the end */
+    double* partials;           /* at_seirm_workspace_bytes() bytes */
+    int32_t* error_flag;        /* or NULL; set non-zero on a lam_gamma index out of range (Q10) */
+    /* launch geometry: 0 = library default */
+    int32_t grid, use_smem_bitmap; /* use_smem_bitmap: -1 auto, 0 off, 1 on */
+} at_seirm_launch;
+
+/* ---- queries (host only) ---- */
+int at_seirm_abi_version(void);
+const char* at_last_error(void);
+/* sizeof() of the two host structs, so that a foreign-language mirror can be checked at load time */
+int64_t at_seirm_sizeof_launch(void);
+int64_t at_seirm_sizeof_model(void);
+/* bytes of `partials` the step / backward kernels need (independent of N) */
+int64_t at_seirm_workspace_bytes(void);
+/* largest n_sources whose infectious bitmap the step kernel stages in shared memory */
+int64_t at_seirm_smem_bitmap_capacity(void);
+
+/*
+ * at_seirm_step — one launch of the fused agent update on `stream`.
+ * Replaces, per the flags: NewTransmission.forward (transition.py:131-252, including the PyG
+ * gather/scatter-add and the straight-through Bernoulli), SEIRMProgression.forward
+ * (seirm_progression/transition.py:90-121), and produces what their autograd graph would have
+ * saved (dne_dr, death_count, recovered_step) without any per-edge intermediate.
+ */
+int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, void* stream);
+
+/*
+ * at_seirm_episode_backward — reverse pass of an episode, replacing torch autograd over the
+ * T x (transmission, progression) graph (SURVEY.md 3.6, A.1 "reverse form"):
+ *   grad_r[t] = g_daily_infected[t] * sum_dne_dr[t]
+ *             + sum_i dne_dr[t,i] * g_daily_deaths[recovered_step[i]] * M / 2
+ *   grad_m[0] = sum_t g_daily_deaths[t] * death_count[t]
+ * dne_dr is (T, ld) row-major with the first n_rows entries of each row used.
+ */
+int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld,
+                              const float* dne_dr, const uint8_t* recovered_step,
+                              const float* sum_dne_dr, const float* death_count,
+                              const float* g_daily_infected, const float* g_daily_deaths,
+                              const float* m_value, float* grad_r, float* grad_m,
+                              double* partials, int32_t grid, void* stream);
+
+/*
+ * at_noise_fill — materialise the counter-hash noise (same values the step kernel generates in
+ * registers) for the tensor-mode API: what = 0 exposure uniform U, 1 isolation uniform,
+ * 2 hard isolation decision (uses p_isolate).  Stands in for torch.rand (action.py:54).
+ */
+int at_noise_fill(float* out, int64_t n, int64_t id_offset, uint64_t seed, int32_t step,
+                  int32_t what, float p_isolate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AT_SEIRM_H */

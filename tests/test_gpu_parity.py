@@ -1,0 +1,74 @@
+"""GPU parity: the CUDA step kernel (through the C ABI) vs the real reference's golden outputs and
+vs the CPU oracle on seeded synthetic inputs.  Integer state bit-exact; float series 1e-5; grads 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import GOLDEN_CASES, load_golden, make_noise, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _r_steps_and_grad(r2_np, T, num_weeks=3):
+    """per-step R exactly as the reference computes it (transition.py:136-143), with autograd"""
+    r2 = torch.tensor(r2_np, dtype=torch.float32, requires_grad=True)
+    eye = torch.eye(num_weeks)
+    r_steps = torch.stack([(r2 * eye[int(t / 7)]).sum() for t in range(T)])
+    return r2, r_steps
+
+
+def _run_engine(g, *, packed, smem, use_tensor_noise=False, cuda_graph=False, grid=0):
+    from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
+    from agenttorch_b200.graph import build_contact_graph, mean_interactions_from_age
+
+    dev = torch.device("cuda:0")
+    T = g["num_steps"]
+    n = len(g["age"])
+    age = torch.from_numpy(g["age"].astype(np.int64))
+    mi = mean_interactions_from_age(age)
+    edges = torch.from_numpy(g["edges"].astype(np.int64)).t().contiguous()
+    graph = build_contact_graph(edges, n, mean_interactions=mi).to(dev)
+    spec = SeirmSpec(num_steps=T)
+    eng = SeirmEngine(graph, spec, use_smem_bitmap=1 if smem else 0, grid=grid)
+    st = SeirmState.from_initial(g["stage0"].astype(np.float32), g["age"], T, dev, packed=packed)
+    if use_tensor_noise:
+        U, W = make_noise(g["seed"], g["mode"], n, T, float(g["p_isolate"]))
+        noise = NoiseSpec(seed=0, isolation="tensor", uniform="tensor",
+                          isolation_tensor=torch.from_numpy(W).to(dev), uniform_tensor=torch.from_numpy(U).to(dev))
+    else:
+        noise = NoiseSpec(seed=g["seed"], isolation=g["mode"], p_isolate=float(g["p_isolate"]))
+    r2, r_steps = _r_steps_and_grad(g["r2"], T)
+    m = torch.tensor(g["m"], dtype=torch.float32)
+    sv = eng.run_episode(st, r_steps.to(dev), m.to(dev), T, noise, want_grad=True, cuda_graph=cuda_graph)
+    gr, gm = eng.episode_backward(sv, T, torch.from_numpy(g["gI"]).to(dev), torch.from_numpy(g["gD"]).to(dev), m.to(dev))
+    eng.check_errors()
+    r_steps.backward(gr.cpu())
+    return st, r2.grad.numpy(), gm.cpu().numpy(), eng
+
+
+def _check(g, st, grad_r2, grad_m):
+    assert np.array_equal(st.stage.cpu().numpy().astype(np.float64), g["ref_stage"])
+    assert np.array_equal(st.next_stage_time.cpu().numpy().astype(np.int64), g["ref_next_stage_time"].astype(np.int64))
+    assert np.array_equal(st.infected_time.cpu().numpy().astype(np.int64), g["ref_infected_time"].astype(np.int64))
+    assert rel_err(g["ref_daily_infected"], st.daily_infected.cpu().numpy()) <= 1e-5   # north star: float state 1e-5 rel
+    assert rel_err(g["ref_daily_deaths"], st.daily_deaths.cpu().numpy()) <= 1e-5
+    assert rel_err(g["ref_grad_R2"], grad_r2) <= 1e-4                                  # north star: gradients 1e-4 rel
+    assert rel_err(g["ref_grad_M"], grad_m) <= 1e-4
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("packed,smem", [(True, True), (False, False)])
+def test_episode_matches_reference_golden(case, packed, smem):
+    g = load_golden(case)
+    st, gr2, gm, _ = _run_engine(g, packed=packed, smem=smem)
+    _check(g, st, gr2, gm)
+
+
+@pytest.mark.parametrize("case", ["synth3k_soft", "astoria_hard"])
+def test_tensor_noise_and_cuda_graph_paths(case):
+    g = load_golden(case)
+    st, gr2, gm, _ = _run_engine(g, packed=True, smem=True, use_tensor_noise=True)
+    _check(g, st, gr2, gm)
+    st, gr2, gm, eng = _run_engine(g, packed=True, smem=False, cuda_graph=True, grid=7)
+    _check(g, st, gr2, gm)
+    assert eng.launch_count > 0
