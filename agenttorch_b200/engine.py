@@ -88,7 +88,7 @@ class SeirmState:
     def from_initial(stage0, age, num_steps, device, packed=True):
         """Initial timers as the reference's initialisers (utils.py:30-57): infected_time 500 / -1 / -3,
         next_stage_time 500 / 3 / 5 for stage 0 / 1 / 2."""
-        stage = torch.as_tensor(stage0).reshape(-1).to(device=device, dtype=torch.float32).contiguous()
+        stage = torch.as_tensor(stage0).reshape(-1).to(device=device, dtype=torch.float32).clone().contiguous()
         tdt = torch.int16 if packed else torch.float32
         itime = torch.full_like(stage, 500, dtype=tdt)
         nst = torch.full_like(stage, 500, dtype=tdt)

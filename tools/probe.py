@@ -1,0 +1,59 @@
+"""Developer probe: per-launch timing of the step kernel on a synthetic population (not the bench)."""
+import argparse
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
+from agenttorch_b200.graph import synthetic_contact_graph, synthetic_population, mean_interactions_from_age
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=1_000_000)
+ap.add_argument("--d", type=float, default=20.0)
+ap.add_argument("--steps", type=int, default=21)
+ap.add_argument("--family", default="rand")
+ap.add_argument("--smem", type=int, default=-1)
+ap.add_argument("--grad", type=int, default=1)
+ap.add_argument("--r2", type=float, default=4.75)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--iso", default="soft")
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+T = args.steps
+age, stage0 = synthetic_population(args.n, 1234, device=dev)
+mi = mean_interactions_from_age(age)
+graph = synthetic_contact_graph(args.n, args.d, 99, family=args.family, device=dev, mean_interactions=mi)
+print("N", args.n, "E", graph.num_edges, "ibar", graph.i_bar, flush=True)
+eng = SeirmEngine(graph, SeirmSpec(num_steps=T), use_smem_bitmap=args.smem)
+r_steps = torch.full((T,), 3 * args.r2, device=dev)
+m = torch.tensor([0.12], device=dev)
+noise = NoiseSpec(seed=5, isolation=args.iso)
+for rep in range(args.reps):
+    st = SeirmState.from_initial(stage0, age, T, dev)
+    sv = eng.saved_buffers(T, bool(args.grad))
+    sv["r_steps"].copy_(r_steps); sv["m_value"].copy_(m); eng.seed_buf.fill_(5)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(T + 2)]
+    sv["recovered_step"].fill_(255)
+    evs[0].record()
+    eng.encode(st, 0)
+    evs[1].record()
+    for t in range(T):
+        eng.step(st, t, noise, sv["r_steps"], t, sv["m_value"], dne_dr=sv["dne_dr"][t] if args.grad else None,
+                 sum_dne_dr=sv["sum_dne_dr"], death_count=sv["death_count"], recovered_step=sv["recovered_step"], seed_ptr=eng.seed_buf)
+        evs[t + 2].record()
+    torch.cuda.synchronize()
+    times = [evs[i].elapsed_time(evs[i + 1]) * 1e3 for i in range(T + 1)]
+    if rep == args.reps - 1:
+        sus = None
+        print("encode us %.1f" % times[0])
+        di = st.daily_infected.tolist()
+        for t in range(T):
+            bytes_ = args.n * (4 * graph.num_edges / args.n + 41)
+            print("t=%2d  %8.1f us  %6.2f TB/s(alg)  new_inf=%d" % (t, times[t + 1], bytes_ / times[t + 1] / 1e6, di[t]))
+        tot = sum(times[1:])
+        print("episode fwd %.3f ms  -> %.2f G agent-steps/s" % (tot / 1e3, args.n * T / tot / 1e3))
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        if args.grad:
+            gi = torch.ones(T, device=dev); gd = torch.ones(T, device=dev)
+            e0.record(); gr, gm = eng.episode_backward(sv, T, gi, gd, m); e1.record(); torch.cuda.synchronize()
+            print("bwd %.1f us" % (e0.elapsed_time(e1) * 1e3), gr[:4].tolist(), gm.tolist())
+        print("stage hist", torch.bincount(st.stage.round().long().clamp(0, 3), minlength=4).tolist())
