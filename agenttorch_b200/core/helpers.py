@@ -1,0 +1,153 @@
+"""Path, copy and config helpers with the reference's names and behaviour
+(agent_torch/core/helpers/general.py:11-129), re-implemented without omegaconf."""
+import copy
+import re
+
+import torch
+import yaml
+from torch import nn
+
+
+def _walk(root, keys):
+    node = root
+    for k in keys:
+        node = node[k]
+    return node
+
+
+def get_by_path(root, items):
+    """Nested lookup; a plain nn.Module leaf is called, a ModuleDict is returned (general.py:11-21)."""
+    obj = _walk(root, items)
+    if isinstance(obj, nn.ModuleDict):
+        return obj
+    if isinstance(obj, nn.Module):
+        return obj()
+    return obj
+
+
+def get_var(state, var):
+    return get_by_path(state, re.split("/", var))
+
+
+def set_by_path(root, items, value):
+    parent = get_by_path(root, items[:-1])
+    if isinstance(parent, nn.ModuleDict):
+        parent[items[-1]].param.data.copy_(value)
+        parent[items[-1]].param.requires_grad = value.requires_grad
+        return None
+    parent[items[-1]] = value
+    return root
+
+
+def del_by_path(root, items):
+    del get_by_path(root, items[:-1])[items[-1]]
+
+
+def copy_module(tree):
+    """New dict tree with every tensor cloned (general.py:49-65).  Unlike the reference, tuples/lists of
+    tensors (the `(edge_index, edge_attr)` adjacency payload) are shared, not deep-copied: they are
+    immutable inputs and copying ~4 GB of edges per substep is the reference's quirk Q8."""
+    out = {}
+    for k, v in tree.items():
+        if torch.is_tensor(v):
+            out[k] = v.clone()
+        elif isinstance(v, dict):
+            out[k] = copy_module(v)
+        elif isinstance(v, (tuple, list)) and all(torch.is_tensor(x) for x in v):
+            out[k] = v
+        else:
+            out[k] = copy.deepcopy(v)
+    return out
+
+
+def to_cpu(tree):
+    out = {}
+    for k, v in tree.items():
+        if torch.is_tensor(v):
+            out[k] = v.clone().cpu()
+        elif isinstance(v, dict):
+            out[k] = to_cpu(v)
+        else:
+            out[k] = v
+    return out
+
+
+def process_shape(config, s):
+    return get_by_path(config, re.split("/", s)) if isinstance(s, str) else s
+
+
+# ------------------------------------------------------------------------------------------ config
+_RESOLVERS = {"sum": lambda x, y: x + y, "multiply": lambda x, y: x * y, "divide": lambda x, y: x // y}
+_INTERP = re.compile(r"\$\{([^${}]+)\}")
+
+
+def register_resolver(name, resolver):
+    _RESOLVERS[name] = resolver
+
+
+def _lookup_dotted(root, dotted):
+    node = root
+    for part in dotted.split("."):
+        node = node[int(part)] if isinstance(node, list) else node[part]
+    return node
+
+
+def _scalar(tok):
+    try:
+        return yaml.safe_load(tok)
+    except yaml.YAMLError:
+        return tok
+
+
+def _resolve(root, value):
+    """`${a.b.c}` interpolation and `${name:x,y}` resolvers, applied until a fixed point."""
+    for _ in range(64):
+        if not isinstance(value, str):
+            return value
+        m = _INTERP.search(value)
+        if m is None:
+            return value
+        expr = m.group(1).strip()
+        head = expr.split(":", 1)[0]
+        if ":" in expr and head in _RESOLVERS:
+            args = [_scalar(_resolve(root, a.strip())) if isinstance(a, str) else a for a in expr.split(":", 1)[1].split(",")]
+            args = [_scalar(a) if isinstance(a, str) else a for a in args]
+            sub = _RESOLVERS[head](*args)
+        else:
+            sub = _resolve(root, _lookup_dotted(root, expr))
+        if m.span() == (0, len(value)):
+            value = sub
+        else:
+            value = value[: m.start()] + str(sub) + value[m.end():]
+    raise ValueError("config interpolation did not converge")
+
+
+def _resolve_tree(root, node):
+    if isinstance(node, dict):
+        return {k: _resolve_tree(root, v) for k, v in node.items()}
+    if isinstance(node, list):
+        return [_resolve_tree(root, v) for v in node]
+    return _resolve(root, node)
+
+
+def resolve_config(raw):
+    """Plain-dict config with every interpolation resolved (OmegaConf.to_object equivalent)."""
+    return _resolve_tree(raw, raw)
+
+
+def read_config(config_file, register_resolvers=True):
+    """Load a YAML config and resolve interpolations (general.py:101-129)."""
+    if str(config_file)[-5:] != ".yaml":
+        raise ValueError("Config file type should be yaml")
+    try:
+        with open(config_file, "r", encoding="utf-8") as f:
+            raw = yaml.safe_load(f)
+        return resolve_config(raw)
+    except Exception as e:  # same error surface as the reference
+        raise ValueError(f"Could not load config file. Please check path and file type. Error message is {str(e)}")
+
+
+def memory_checkpoint(name):
+    allocated, reserved = torch.cuda.memory_allocated(), torch.cuda.memory_reserved()
+    print("Checkpoint: ", name, " Allocated: ", allocated, " Reserved: ", reserved)
+    return allocated, reserved

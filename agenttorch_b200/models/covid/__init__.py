@@ -1,0 +1,29 @@
+"""covid (SEIRM) model: registry wiring identical to the reference's (models/covid/__init__.py:4-50) —
+same names, same keys — with the B200 substep classes behind them."""
+from agenttorch_b200.core.registry import Registry
+
+
+def get_registry():
+    reg = Registry()
+    from .substeps.new_transmission.action import MakeIsolationDecision
+    from .substeps.new_transmission.transition import NewTransmission
+    from .substeps.seirm_progression.transition import SEIRMProgression
+    from .substeps import utils
+
+    reg.register(MakeIsolationDecision, "make_isolation_decision", key="policy")
+    reg.register(NewTransmission, "new_transmission", key="transition")
+    reg.register(SEIRMProgression, "seirm_progression", key="transition")
+    reg.register(utils.network_from_file, "network_from_file", key="network")
+    for name in ("read_from_file", "get_lam_gamma_integrals", "get_mean_agent_interactions", "get_infected_time",
+                 "get_next_stage_time", "load_population_attribute", "initialize_id"):
+        reg.register(getattr(utils, name), name, key="initialization")
+    return reg
+
+
+registry = get_registry()
+
+
+def get_runner(config, registry):
+    from agenttorch_b200.core.runner import Runner
+
+    return Runner(config, registry)

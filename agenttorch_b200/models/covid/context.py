@@ -1,0 +1,67 @@
+"""Per-simulation engine context shared by the covid substeps and the Runner's fused episode path."""
+import re
+
+import torch
+
+from agenttorch_b200 import ops
+from agenttorch_b200.core.helpers import get_by_path
+from agenttorch_b200.engine import SeirmEngine, SeirmSpec
+from agenttorch_b200.graph import build_contact_graph
+
+_CACHE = {}
+_MAX_CACHED = 4
+
+
+def _check_constants(meta):
+    want = {"SUSCEPTIBLE_VAR": 0, "EXPOSED_VAR": 1, "INFECTED_VAR": 2, "RECOVERED_VAR": 3}
+    for k, v in want.items():
+        if int(meta.get(k, v)) != v:
+            raise NotImplementedError(f"simulation_metadata.{k} must be {v} for the fused SEIRM kernels")
+
+
+def spec_from_state(config, state, input_variables):
+    meta = config["simulation_metadata"]
+    _check_constants(meta)
+
+    def env(name, default_path):
+        return get_by_path(state, re.split("/", input_variables.get(name, default_path)))
+
+    sfs = env("SFSusceptibility", "environment/SFSusceptibility").detach().reshape(-1).cpu().tolist()
+    sfi = env("SFInfector", "environment/SFInfector").detach().reshape(-1).cpu().tolist()
+    lg = env("lam_gamma_integrals", "environment/lam_gamma_integrals").detach().reshape(-1).cpu().tolist()
+    return SeirmSpec(sfs=tuple(sfs), sfi=tuple(sfi), lam_gamma=tuple(lg), num_steps=int(meta["num_steps_per_episode"]),
+                     exposed_to_infected_time=int(meta["EXPOSED_TO_INFECTED_TIME"]),
+                     infected_to_recovered_time=int(meta["INFECTED_TO_RECOVERED_TIME"]))
+
+
+class SeirmContext:
+    def __init__(self, engine):
+        self.engine = engine
+        self.handle = ops.register_engine(engine)
+
+
+def get_context(config, state, input_variables):
+    """Engine for the contact network this substep reads; built on first use and cached by the identity
+    of the adjacency payload.  Raises on CPU tensors: the kernels are the only implementation."""
+    adjacency = get_by_path(state, re.split("/", input_variables["adjacency_matrix"]))
+    edge_index, edge_attr = adjacency
+    if not edge_index.is_cuda:
+        raise RuntimeError("agenttorch_b200 SEIRM substeps need CUDA tensors (simulation_metadata.device: cuda); "
+                           "there is no CPU fallback")
+    key = (edge_index.data_ptr(), edge_index.shape[1], str(edge_index.device))
+    ctx = _CACHE.get(key)
+    if ctx is None:
+        mean_int = get_by_path(state, re.split("/", input_variables["mean_interactions"]))
+        n = int(config["simulation_metadata"]["num_agents"])
+        graph = build_contact_graph(edge_index, n, edge_attr=edge_attr, mean_interactions=mean_int, device=edge_index.device)
+        ctx = SeirmContext(SeirmEngine(graph, spec_from_state(config, state, input_variables)))
+        if len(_CACHE) >= _MAX_CACHED:
+            old = next(iter(_CACHE))
+            ops.release_engine(_CACHE.pop(old).handle)
+        _CACHE[key] = ctx
+    return ctx
+
+
+def as_kernel_f32(t):
+    """State tensors are float32 in this package; accept float64 inputs (the reference's CSV path) by value."""
+    return t if t.dtype == torch.float32 and t.is_contiguous() else t.to(torch.float32).contiguous()

@@ -1,0 +1,218 @@
+"""torch.library custom ops (namespace `agenttorch_b200`) over the C ABI, with registered autograd.
+
+Three operators replace the reference's ATen op chains and their autograd graph:
+  seirm_transmission  — NewTransmission.forward       (new_transmission/transition.py:131-252)
+  seirm_progression   — SEIRMProgression.forward      (seirm_progression/transition.py:90-121)
+  seirm_episode       — T x (transmission + progression) fused, state advanced in place, with a fused
+                        O(N) backward (at_seirm_episode_backward) instead of a T-step autograd tape.
+An engine (graph + buffers) is addressed by an integer handle because custom ops only take tensors
+and scalars.  Every op launches CUDA kernels from libat_seirm.so; there is no CPU implementation —
+calling them with CPU tensors raises.
+"""
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _native as nat
+from .engine import NoiseSpec, SeirmEngine, SeirmState
+
+_ENGINES = {}
+_NEXT_HANDLE = [1]
+
+
+def register_engine(engine: SeirmEngine) -> int:
+    h = _NEXT_HANDLE[0]
+    _NEXT_HANDLE[0] += 1
+    _ENGINES[h] = engine
+    return h
+
+
+def release_engine(handle: int):
+    _ENGINES.pop(handle, None)
+
+
+def get_engine(handle: int) -> SeirmEngine:
+    return _ENGINES[handle]
+
+
+def _noise(seed, iso_mode, p_isolate, isolation, uniform):
+    return NoiseSpec(seed=seed, isolation="tensor" if isolation is not None else iso_mode, p_isolate=p_isolate,
+                     uniform="tensor" if uniform is not None else "hash", isolation_tensor=isolation, uniform_tensor=uniform)
+
+
+def _flat_state(stage, nst, itime, age, di, dd):
+    return SeirmState(stage.view(-1), nst.view(-1), itime.view(-1), age.view(-1), di.view(-1), dd.view(-1))
+
+
+# ------------------------------------------------------------------------------------ transmission
+@torch.library.custom_op("agenttorch_b200::seirm_transmission", mutates_args=())
+def seirm_transmission(handle: int, stage: Tensor, next_stage_time: Tensor, infected_time: Tensor, age: Tensor,
+                       daily_infected: Tensor, r_value: Tensor, t: int, seed: int, iso_mode: str, p_isolate: float,
+                       isolation: Optional[Tensor], uniform: Optional[Tensor], want_grad: bool
+                       ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Substep '0'.  Returns (stage, next_stage_time, infected_time, daily_infected, dne_dr) as NEW tensors."""
+    eng = get_engine(handle)
+    st = _flat_state(stage.detach().clone(), next_stage_time.detach().clone(), infected_time.detach().clone(), age,
+                     daily_infected.detach().clone(), daily_infected.new_zeros(daily_infected.numel()))
+    dne = torch.zeros(st.stage.numel(), dtype=torch.float32, device=stage.device) if want_grad else None
+    eng.encode(st, t)   # the state may have been edited between calls: re-derive the infectiousness of step t
+    noise = _noise(seed, iso_mode, p_isolate, None if isolation is None else isolation.reshape(-1).contiguous(),
+                   None if uniform is None else uniform.reshape(-1).contiguous())
+    eng.launch(st, flags=nat.DO_TRANSMISSION, t=t, noise=noise, isolation=noise.isolation_tensor,
+               uniform=noise.uniform_tensor, r_value=r_value.detach().reshape(-1).to(torch.float32).contiguous(),
+               r_index=0, dne_dr=dne)
+    if dne is None:
+        dne = torch.zeros(0, dtype=torch.float32, device=stage.device)
+    return (st.stage.view_as(stage), st.next_stage_time.view_as(next_stage_time), st.infected_time.view_as(infected_time),
+            st.daily_infected.view_as(daily_infected), dne)
+
+
+@seirm_transmission.register_fake
+def _(handle, stage, next_stage_time, infected_time, age, daily_infected, r_value, t, seed, iso_mode, p_isolate,
+      isolation, uniform, want_grad):
+    n = stage.numel() if want_grad else 0
+    return (torch.empty_like(stage), torch.empty_like(next_stage_time), torch.empty_like(infected_time),
+            torch.empty_like(daily_infected), stage.new_empty(n, dtype=torch.float32))
+
+
+def _transmission_setup(ctx, inputs, output):
+    ctx.t = inputs[7]
+    ctx.r_shape = inputs[6].shape
+    ctx.save_for_backward(output[4])
+
+
+def _transmission_backward(ctx, g_stage, g_nst, g_itime, g_di, g_dne):
+    (dne,) = ctx.saved_tensors
+    g_r = None
+    if dne.numel():
+        # d ne_i / dR feeds stage_i (+= ne_i) and daily_infected[t] (+= sum ne)   (SURVEY.md A.1 reverse form)
+        w = torch.zeros_like(dne) if g_stage is None else g_stage.reshape(-1).to(torch.float32)
+        if g_di is not None:
+            w = w + g_di.reshape(-1)[ctx.t].to(torch.float32)
+        g_r = (dne * w).sum().reshape(ctx.r_shape)
+    return (None, g_stage, None, None, None, g_di, g_r, None, None, None, None, None, None, None)
+
+
+seirm_transmission.register_autograd(_transmission_backward, setup_context=_transmission_setup)
+
+
+# ------------------------------------------------------------------------------------- progression
+@torch.library.custom_op("agenttorch_b200::seirm_progression", mutates_args=())
+def seirm_progression(handle: int, stage: Tensor, next_stage_time: Tensor, daily_deaths: Tensor, m_value: Tensor,
+                      t: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Substep '1'.  Returns (stage, next_stage_time, daily_deaths, recovered_mask u8, death_count (1,))."""
+    eng = get_engine(handle)
+    dev = stage.device
+    nst = next_stage_time.detach().clone()
+    st = SeirmState(stage.detach().clone().view(-1), nst.view(-1), nst.view(-1), nst.view(-1),
+                    daily_deaths.new_zeros(daily_deaths.numel()), daily_deaths.detach().clone().view(-1))
+    st.age = torch.zeros(1, dtype=torch.uint8, device=dev)          # not read by the progression pass
+    rstep = torch.full((st.stage.numel(),), 255, dtype=torch.uint8, device=dev)
+    dcount = torch.zeros(max(daily_deaths.numel(), t + 1), dtype=torch.float32, device=dev)
+    eng.launch(st, flags=nat.DO_PROGRESSION, t=t, m_value=m_value.detach().reshape(-1).to(torch.float32).contiguous(),
+               death_count=dcount, recovered_step=rstep)
+    return (st.stage.view_as(stage), st.next_stage_time.view_as(next_stage_time), st.daily_deaths.view_as(daily_deaths),
+            (rstep == t).to(torch.uint8), dcount[t:t + 1].clone())
+
+
+@seirm_progression.register_fake
+def _(handle, stage, next_stage_time, daily_deaths, m_value, t):
+    return (torch.empty_like(stage), torch.empty_like(next_stage_time), torch.empty_like(daily_deaths),
+            stage.new_empty(stage.numel(), dtype=torch.uint8), stage.new_empty(1, dtype=torch.float32))
+
+
+def _progression_setup(ctx, inputs, output):
+    ctx.t = inputs[5]
+    ctx.m_shape = inputs[4].shape
+    ctx.stage_shape = inputs[1].shape
+    ctx.save_for_backward(output[3], output[4], inputs[4])
+
+
+def _progression_backward(ctx, g_stage, g_nst, g_dd, g_mask, g_cnt):
+    rd, dcount, m = ctx.saved_tensors
+    g_stage_in, g_m = g_stage, None
+    if g_dd is not None:
+        gt = g_dd.reshape(-1)[ctx.t]
+        # daily_deaths[t] += M * sum(stage * rd / 2): d/dstage_i = M*rd_i/2, d/dM = sum(stage*rd/2)
+        add = (gt * m.reshape(-1)[0] * 0.5) * rd.to(gt.dtype).view(ctx.stage_shape)
+        g_stage_in = add if g_stage is None else g_stage + add
+        g_m = (gt * dcount.reshape(-1)[0]).reshape(1).expand(m.numel()).reshape(ctx.m_shape).clone()
+    return (None, g_stage_in, None, g_dd, g_m, None)
+
+
+seirm_progression.register_autograd(_progression_backward, setup_context=_progression_setup)
+
+
+# ----------------------------------------------------------------------------------------- episode
+_BOUND = {}
+
+
+def bind_state(handle: int, stage: Tensor, next_stage_time: Tensor, infected_time: Tensor, age: Tensor):
+    """Attach the agent-state tensors the episode operator advances IN PLACE.  They are engine-side state
+    (like an optimizer's buffers), not operator arguments: torch.library only registers autograd formulas
+    for functional operators, and the state tensors are never differentiable inputs."""
+    _BOUND[handle] = (stage.view(-1), next_stage_time.view(-1), infected_time.view(-1), age.view(-1))
+
+
+@torch.library.custom_op("agenttorch_b200::seirm_episode", mutates_args=())
+def seirm_episode(handle: int, daily_infected: Tensor, daily_deaths: Tensor, r_steps: Tensor, m_value: Tensor,
+                  num_steps: int, seed: int, iso_mode: str, p_isolate: float, isolation: Optional[Tensor],
+                  uniform: Optional[Tensor], want_grad: bool, cuda_graph: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Advance the bound agent state through `num_steps` steps.  Returns the new (daily_infected,
+    daily_deaths) and the (T,) reductions saved for backward (sum_dne_dr, death_count); the (T,N) dne_dr and
+    recovered_step buffers stay inside the engine until the next episode."""
+    eng = get_engine(handle)
+    stage, nst, itime, age = _BOUND[handle]
+    di = daily_infected.detach().clone()
+    dd = daily_deaths.detach().clone()
+    st = SeirmState(stage, nst, itime, age, di.view(-1), dd.view(-1))
+    noise = _noise(seed, iso_mode, p_isolate, isolation, uniform)
+    sv = eng.run_episode(st, r_steps, m_value, num_steps, noise, want_grad=want_grad, cuda_graph=cuda_graph)
+    return di, dd, sv["sum_dne_dr"].clone(), sv["death_count"].clone()
+
+
+@seirm_episode.register_fake
+def _(handle, daily_infected, daily_deaths, r_steps, m_value, num_steps, seed, iso_mode, p_isolate, isolation,
+      uniform, want_grad, cuda_graph):
+    return (torch.empty_like(daily_infected), torch.empty_like(daily_deaths),
+            daily_infected.new_empty(num_steps), daily_infected.new_empty(num_steps))
+
+
+@torch.library.custom_op("agenttorch_b200::seirm_episode_backward", mutates_args=())
+def seirm_episode_backward(handle: int, num_steps: int, g_daily_infected: Tensor, g_daily_deaths: Tensor,
+                           m_value: Tensor) -> Tuple[Tensor, Tensor]:
+    eng = get_engine(handle)
+    sv = eng.saved_buffers(num_steps, True)
+    return eng.episode_backward(sv, num_steps, g_daily_infected, g_daily_deaths, m_value)
+
+
+@seirm_episode_backward.register_fake
+def _(handle, num_steps, g_daily_infected, g_daily_deaths, m_value):
+    return g_daily_infected.new_empty(num_steps), g_daily_infected.new_empty(1)
+
+
+def _episode_setup(ctx, inputs, output):
+    ctx.handle, ctx.num_steps = inputs[0], inputs[5]
+    ctx.want_grad = inputs[11]
+    ctx.r_shape, ctx.m_shape = inputs[3].shape, inputs[4].shape
+    ctx.save_for_backward(inputs[4])
+
+
+def _episode_backward(ctx, g_di, g_dd, g_sum, g_cnt):
+    (m_value,) = ctx.saved_tensors
+    g_r = g_m = None
+    if ctx.want_grad and (g_di is not None or g_dd is not None):
+        T = ctx.num_steps
+        zeros = torch.zeros(T, dtype=torch.float32, device=m_value.device)
+        gi = zeros if g_di is None else g_di.reshape(-1)[:T]
+        gd = zeros if g_dd is None else g_dd.reshape(-1)[:T]
+        gr, gm = seirm_episode_backward(ctx.handle, T, gi, gd, m_value)
+        g_r = torch.zeros(ctx.r_shape, dtype=gr.dtype, device=gr.device).reshape(-1)
+        g_r[:T] = gr
+        g_r = g_r.reshape(ctx.r_shape)
+        g_m = gm.expand(m_value.numel()).reshape(ctx.m_shape).clone()
+    return (None, g_di, g_dd, g_r, g_m, None, None, None, None, None, None, None, None)
+
+
+seirm_episode.register_autograd(_episode_backward, setup_context=_episode_setup)

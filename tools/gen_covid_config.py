@@ -1,0 +1,122 @@
+"""Emit agenttorch_b200/models/covid/yamls/config.yaml (same schema as the reference's covid config:
+simulation_metadata / state / substeps; property = {name, shape, dtype, learnable, value | initialization_function})."""
+import os
+import sys
+
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N = "${simulation_metadata.num_agents}"
+T = "${simulation_metadata.num_steps_per_episode}"
+
+
+def prop(name, shape, dtype, value=None, gen=None, args=None, learnable=False):
+    d = {"name": name, "shape": shape, "dtype": dtype, "learnable": learnable}
+    if gen is None:
+        d["initialization_function"] = None
+        d["value"] = value
+    else:
+        d["initialization_function"] = {"generator": gen, "arguments": args or {}}
+    return d
+
+
+def arg(name, value, shape=(1,), learnable=False, dtype=None):
+    d = {"name": name, "shape": list(shape) if shape is not None else None, "learnable": learnable,
+         "initialization_function": None, "value": value}
+    if dtype:
+        d["dtype"] = dtype
+    return d
+
+
+stage_file = {"file_path": arg("Disease Stage File", "${simulation_metadata.disease_stage_file}")}
+age_file = {"file_path": arg("Filepath for age group stage", "${simulation_metadata.age_group_file}")}
+cfg = {
+    "simulation_metadata": {
+        "EXECUTION_MODE": "heuristic", "EXPOSED_TO_INFECTED_TIME": 5, "EXPOSED_VAR": 1, "INFECTED_TO_RECOVERED_TIME": 5,
+        "INFECTED_VAR": 2, "INFINITY_TIME": 130, "MORTALITY_VAR": 4, "NUM_WEEKS": 3, "RECOVERED_VAR": 3,
+        "SUSCEPTIBLE_VAR": 0, "calibration": True, "device": "auto",
+        "cuda_params": {"fused_episode": True, "cuda_graph": True, "snapshot_pack_bools": True, "batch_size": 16384,
+                        "pool_limit_per_shape": 8, "inplace_progress": False},
+        "population_dir": "populations/astoria",
+        "age_group_file": "${simulation_metadata.population_dir}/age.pickle",
+        "disease_stage_file": "${simulation_metadata.population_dir}/disease_stages.csv",
+        "infection_network_file": "${simulation_metadata.population_dir}/mobility_networks/0.csv",
+        "num_agents": 37518, "num_episodes": 5, "num_steps_per_episode": 21, "num_substeps_per_step": 2,
+        "learning_params": {"lr": 5e-3, "betas": [0.5, 0.5], "lr_gamma": 0.9999, "model_path": "saved_model.pth"},
+    },
+    "state": {
+        "agents": {"citizens": {"number": N, "properties": {
+            "age": prop("Age", [N, 1], "int", gen="load_population_attribute",
+                        args={"attribute": arg("Age", "age", shape=None), **age_file}),
+            "disease_stage": prop("Disease Stage", [N, 1], "int", gen="read_from_file", args=stage_file),
+            "id": prop("id", [N, 1], "float", gen="initialize_id",
+                       args={"pop_size": arg("population size", "${simulation_metadata.num_agents}")}),
+            "infected_time": prop("Last Infected timestep", [N, 1], "int", gen="get_infected_time",
+                                  args={**stage_file, "num_steps": arg("Num steps per episode", T)}),
+            "next_stage_time": prop("Timestep for next transition", [N, 1], "int", gen="get_next_stage_time",
+                                    args={**stage_file, "num_steps": arg("Num steps per episode", T)}),
+        }}},
+        "environment": {
+            "SFInfector": prop("Infectiousness of Infector", [5], "float", value=[0.0, 0.33, 0.72, 0.0, 0.0]),
+            "SFSusceptibility": prop("Susceptibility by Age Group", [9], "float",
+                                     value=[0.35, 0.69, 1.03, 1.03, 1.03, 1.03, 1.27, 1.52, 1.52]),
+            "daily_deaths": prop("daily_deaths", [T], "float", value=0),
+            "daily_infected": prop("daily_infected", [T], "float", value=0),
+            "exposed_to_infected_time": prop("Time from Exposed to Infected", [1], "float", value=3),
+            "infected_to_recovered_time": prop("Infected to Recovered time", [1], "float", value=5),
+            "lam_gamma_integrals": prop("Lam Gamma Integrals", [10], "float", gen="get_lam_gamma_integrals", args={
+                "rate": arg("Lam Gamma Rate", 2.4, dtype="float"), "scale": arg("Lam Gamma Scale", 5.5, dtype="float"),
+                "t": arg("Num Steps", T, dtype="int")}),
+            "mean_interactions": prop("Mean agent interactions across networks", [N, 1], "int",
+                                      gen="get_mean_agent_interactions", args=age_file),
+            "mortality_rate": prop("Mortality Rate", [1], "float", value=0.2),
+        },
+        "network": {"agent_agent": {"infection_network": {
+            "type": "network_from_file", "arguments": {"file_path": "${simulation_metadata.infection_network_file}"}}}},
+        "objects": None,
+    },
+    "substeps": {
+        "0": {
+            "name": "Transmission", "description": "Transmission of new infections", "active_agents": ["citizens"],
+            "observation": {"citizens": None},
+            "policy": {"citizens": {"make_isolation_decision": {
+                "generator": "MakeIsolationDecision", "arguments": None,
+                "input_variables": {"age": "agents/citizens/age"}, "output_variables": ["isolation_decision"]}}},
+            "reward": None,
+            "transition": {"new_transmission": {
+                "generator": "NewTransmission",
+                "arguments": {"R2": {"name": "R2", "dtype": "float", "shape": ["${simulation_metadata.NUM_WEEKS}", 1],
+                                     "learnable": True, "initialization_function": None, "value": 4.75}},
+                "input_variables": {
+                    "SFInfector": "environment/SFInfector", "SFSusceptibility": "environment/SFSusceptibility",
+                    "adjacency_matrix": "network/agent_agent/infection_network/adjacency_matrix",
+                    "age": "agents/citizens/age", "daily_infected": "environment/daily_infected",
+                    "disease_stage": "agents/citizens/disease_stage",
+                    "exposed_to_infected_time": "environment/exposed_to_infected_time",
+                    "infected_time": "agents/citizens/infected_time",
+                    "lam_gamma_integrals": "environment/lam_gamma_integrals",
+                    "mean_interactions": "environment/mean_interactions",
+                    "next_stage_time": "agents/citizens/next_stage_time"},
+                "output_variables": ["disease_stage", "next_stage_time", "infected_time", "daily_infected"]}},
+        },
+        "1": {
+            "name": "Disease Progression", "description": "Evolution of previously infected agents",
+            "active_agents": ["citizens"], "observation": {"citizens": None}, "policy": {"citizens": None}, "reward": None,
+            "transition": {"seirm_progression": {
+                "generator": "SEIRMProgression",
+                "arguments": {"M": {"name": "Mortality Rate", "dtype": "float", "shape": [1], "learnable": True,
+                                    "initialization_function": None, "value": 0.12}},
+                "input_variables": {
+                    "daily_deaths": "environment/daily_deaths", "disease_stage": "agents/citizens/disease_stage",
+                    "exposed_to_infected_time": "environment/exposed_to_infected_time",
+                    "infected_to_recovered_time": "environment/infected_to_recovered_time",
+                    "next_stage_time": "agents/citizens/next_stage_time"},
+                "output_variables": ["disease_stage", "next_stage_time", "daily_deaths"]}},
+        },
+    },
+}
+out = os.path.join(ROOT, "agenttorch_b200", "models", "covid", "yamls", "config.yaml")
+with open(out, "w") as f:
+    f.write("# SEIRM covid model — same schema as the reference's models/covid/yamls/config.yaml; generated by tools/gen_covid_config.py\n")
+    yaml.safe_dump(cfg, f, sort_keys=True, default_flow_style=False)
+print("wrote", out)
