@@ -47,9 +47,10 @@ class NewTransmission(SubstepTransitionMessagePassing):
         return (self.r_tensor() * self._week_one_hot[int(t / 7)]).sum()
 
     def episode_seed(self):
-        if not self.advance_seed:
-            return self.noise_seed & ((1 << 64) - 1)
-        return (self.noise_seed + 0x9E3779B97F4A7C15 * self.episode_index) & ((1 << 64) - 1)
+        """64-bit seed of this episode's noise stream, as a signed int64 (custom-op integer arguments are int64)."""
+        v = self.noise_seed if not self.advance_seed else self.noise_seed + 0x9E3779B97F4A7C15 * self.episode_index
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
 
     def forward(self, state, action=None):
         iv = self.input_variables

@@ -79,6 +79,7 @@ def _(handle, stage, next_stage_time, infected_time, age, daily_infected, r_valu
 def _transmission_setup(ctx, inputs, output):
     ctx.t = inputs[7]
     ctx.r_shape = inputs[6].shape
+    ctx.mark_non_differentiable(output[1], output[2], output[4])
     ctx.save_for_backward(output[4])
 
 
@@ -126,6 +127,7 @@ def _progression_setup(ctx, inputs, output):
     ctx.t = inputs[5]
     ctx.m_shape = inputs[4].shape
     ctx.stage_shape = inputs[1].shape
+    ctx.mark_non_differentiable(output[1], output[3], output[4])
     ctx.save_for_backward(output[3], output[4], inputs[4])
 
 
@@ -196,6 +198,7 @@ def _episode_setup(ctx, inputs, output):
     ctx.handle, ctx.num_steps = inputs[0], inputs[5]
     ctx.want_grad = inputs[11]
     ctx.r_shape, ctx.m_shape = inputs[3].shape, inputs[4].shape
+    ctx.mark_non_differentiable(output[2], output[3])
     ctx.save_for_backward(inputs[4])
 
 
