@@ -76,6 +76,26 @@ class Runner(nn.Module):
         self.state = self.initializer.state
         self.state_trajectory = [[self._snapshot(self.state)]]
 
+    def restore_state(self, snapshot, non_blocking=True):
+        """Copy a saved agent/environment state (nested dict of tensors, host or device; e.g. pinned host
+        buffers of an initial condition or a checkpoint) INTO the live state tensors, keeping their storage —
+        and therefore the engine bindings and captured CUDA graphs — valid.  The cheap counterpart of
+        reset_state(), which re-runs every initialiser."""
+        def walk(dst, src):
+            for k, v in src.items():
+                if isinstance(v, dict):
+                    walk(dst[k], v)
+                elif torch.is_tensor(v) and torch.is_tensor(dst.get(k)):
+                    cur = dst[k]
+                    if cur.requires_grad or cur.grad_fn is not None or cur.shape != v.shape:
+                        dst[k] = v.to(cur.device, non_blocking=non_blocking).reshape(cur.shape).to(cur.dtype)
+                    else:
+                        cur.copy_(v, non_blocking=non_blocking)
+        walk(self.state, snapshot)
+        self.state["current_step"] = 0
+        self.state["current_substep"] = "0"
+        self.state_trajectory = [[self._snapshot(self.state)]]
+
     def reset_state_before_episode(self):
         self.state_trajectory = [[self._snapshot(self.state)]]
 
@@ -167,7 +187,7 @@ class Runner(nn.Module):
         dd = get_by_path(state, path(pv["daily_deaths"]))
         if num_steps > di.numel():
             raise IndexError(f"num_steps={num_steps} exceeds the length of daily_infected ({di.numel()})")
-        r_steps = torch.stack([tr.effective_r(t) for t in range(num_steps)])
+        r_steps = tr.r_steps(num_steps)
         m_value = pg.m_tensor()
         want_grad = bool(r_steps.requires_grad or m_value.requires_grad) and torch.is_grad_enabled()
         tr.episode_index += 1

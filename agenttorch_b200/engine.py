@@ -141,7 +141,7 @@ def _ptr(t, dtype=None, name="tensor"):
 
 
 class SeirmEngine:
-    def __init__(self, graph: ContactGraph, spec: SeirmSpec, process_group=None, use_smem_bitmap=-1, grid=0):
+    def __init__(self, graph: ContactGraph, spec: SeirmSpec, process_group=None, use_smem_bitmap=-1, grid=0, code_len=None):
         if not graph.row_ptr.is_cuda:
             raise RuntimeError("SeirmEngine needs the contact graph on a CUDA device; there is no CPU fallback")
         self.lib = nat.lib()
@@ -154,6 +154,10 @@ class SeirmEngine:
         self.grid = grid
         n_src = graph.n_sources
         self.n_code = ((n_src + 1023) // 1024) * 1024
+        if code_len is not None:      # multi-GPU: world_size equal slices, one per rank (graph.shard_bounds)
+            if code_len < n_src or code_len % 1024:
+                raise ValueError("code_len must cover all sources and be a multiple of 1024")
+            self.n_code = int(code_len)
         words = self.n_code // 32
         self.code = [torch.zeros(self.n_code, dtype=torch.uint8, device=self.device) for _ in range(2)]
         self.bitmap = [torch.zeros(words + 4, dtype=torch.int32, device=self.device) for _ in range(2)]

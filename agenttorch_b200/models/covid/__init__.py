@@ -17,6 +17,7 @@ def get_registry():
     for name in ("read_from_file", "get_lam_gamma_integrals", "get_mean_agent_interactions", "get_infected_time",
                  "get_next_stage_time", "load_population_attribute", "initialize_id"):
         reg.register(getattr(utils, name), name, key="initialization")
+    from . import synthetic  # noqa: F401  (registers the synthetic_* helpers)
     return reg
 
 

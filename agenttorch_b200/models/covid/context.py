@@ -6,7 +6,7 @@ import torch
 from agenttorch_b200 import ops
 from agenttorch_b200.core.helpers import get_by_path
 from agenttorch_b200.engine import SeirmEngine, SeirmSpec
-from agenttorch_b200.graph import build_contact_graph
+from agenttorch_b200.graph import ContactGraph, build_contact_graph
 
 _CACHE = {}
 _MAX_CACHED = 4
@@ -53,7 +53,12 @@ def get_context(config, state, input_variables):
     if ctx is None:
         mean_int = get_by_path(state, re.split("/", input_variables["mean_interactions"]))
         n = int(config["simulation_metadata"]["num_agents"])
-        graph = build_contact_graph(edge_index, n, edge_attr=edge_attr, mean_interactions=mean_int, device=edge_index.device)
+        net = get_by_path(state, re.split("/", input_variables["adjacency_matrix"])[:-1])
+        prebuilt = net.get("graph") if isinstance(net, dict) else None
+        if isinstance(prebuilt, ContactGraph) and prebuilt.num_edges == edge_index.shape[1]:
+            graph = prebuilt.to(edge_index.device)      # network helper already produced the dst-sorted CSR
+        else:
+            graph = build_contact_graph(edge_index, n, edge_attr=edge_attr, mean_interactions=mean_int, device=edge_index.device)
         ctx = SeirmContext(SeirmEngine(graph, spec_from_state(config, state, input_variables)))
         if len(_CACHE) >= _MAX_CACHED:
             old = next(iter(_CACHE))

@@ -46,6 +46,13 @@ class NewTransmission(SubstepTransitionMessagePassing):
         product broadcasts and `.sum()` adds every week (Q2); with a (NUM_WEEKS,) tensor it is R2[week]."""
         return (self.r_tensor() * self._week_one_hot[int(t / 7)]).sum()
 
+    def r_steps(self, num_steps):
+        """(num_steps,) per-step R: `effective_r` evaluated once per distinct week, then indexed, so the
+        values are identical to the per-step evaluation."""
+        weeks = [int(t / 7) for t in range(num_steps)]
+        per_week = {w: self.effective_r(7 * w) for w in sorted(set(weeks))}
+        return torch.stack([per_week[w] for w in weeks])
+
     def episode_seed(self):
         """64-bit seed of this episode's noise stream, as a signed int64 (custom-op integer arguments are int64)."""
         v = self.noise_seed if not self.advance_seed else self.noise_seed + 0x9E3779B97F4A7C15 * self.episode_index
