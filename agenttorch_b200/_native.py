@@ -15,17 +15,18 @@ LIB_PATH = os.path.join(_PKG, "lib", "libat_seirm.so")
 SRC_PATH = os.path.join(_PKG, "csrc", "at_seirm.cu")
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_SFS, MAX_SFI, MAX_LAMGAMMA = 16, 8, 84
 TIMER_F32, TIMER_I16 = 0, 1
 AGE_F32, AGE_U8 = 0, 1
 ISO_TENSOR, ISO_HASH_SOFT, ISO_HASH_HARD, ISO_NONE = 0, 1, 2, 3
 U_TENSOR, U_HASH = 0, 1
-DO_TRANSMISSION, DO_PROGRESSION, DO_ENCODE = 1, 2, 4
+DO_TRANSMISSION, DO_PROGRESSION, DO_ENCODE, DO_INIT = 1, 2, 4, 8
+MAX_BLOCKS = 64
 
 EXPORTS = [
     "at_seirm_abi_version", "at_last_error", "at_seirm_sizeof_launch", "at_seirm_sizeof_model",
-    "at_seirm_workspace_bytes", "at_seirm_smem_bitmap_capacity", "at_seirm_step",
+    "at_seirm_workspace_bytes", "at_seirm_max_block_size", "at_seirm_step",
     "at_seirm_episode_backward", "at_noise_fill",
 ]
 
@@ -45,20 +46,23 @@ class SeirmLaunch(ctypes.Structure):
     """Mirror of `at_seirm_launch` (field order and types must match include/at_seirm.h)."""
     _fields_ = [
         ("abi_version", ctypes.c_int32), ("flags", ctypes.c_int32), ("t", ctypes.c_int32), ("t_encode", ctypes.c_int32),
-        ("n_rows", ctypes.c_int64), ("n_sources", ctypes.c_int64), ("row_offset", ctypes.c_int64),
-        ("row_ptr", ctypes.c_void_p), ("col_idx", ctypes.c_void_p), ("edge_weight", ctypes.c_void_p),
+        ("n_rows", ctypes.c_int64), ("n_rows_pad", ctypes.c_int64), ("n_sources", ctypes.c_int64), ("row_offset", ctypes.c_int64),
+        ("n_blocks", ctypes.c_int32), ("block_size", ctypes.c_int32),
+        ("deg", ctypes.c_void_p), ("seg_base4", ctypes.c_void_p), ("col", ctypes.c_void_p), ("edge_weight", ctypes.c_void_p),
         ("stage", ctypes.c_void_p), ("next_stage_time", ctypes.c_void_p), ("infected_time", ctypes.c_void_p),
         ("age", ctypes.c_void_p), ("timer_dtype", ctypes.c_int32), ("age_dtype", ctypes.c_int32),
-        ("code_in", ctypes.c_void_p), ("bitmap_in", ctypes.c_void_p), ("code_out", ctypes.c_void_p),
-        ("bitmap_out", ctypes.c_void_p),
+        ("sus_bitmap", ctypes.c_void_p), ("exp_bitmap", ctypes.c_void_p), ("inf_bitmap", ctypes.c_void_p),
+        ("code_in", ctypes.c_void_p), ("hot_bitmap_in", ctypes.c_void_p), ("code_out", ctypes.c_void_p),
+        ("hot_bitmap_out", ctypes.c_void_p),
         ("iso_mode", ctypes.c_int32), ("u_mode", ctypes.c_int32),
         ("isolation", ctypes.c_void_p), ("uniform", ctypes.c_void_p),
         ("seed", ctypes.c_uint64), ("seed_ptr", ctypes.c_void_p), ("p_isolate", ctypes.c_float), ("_pad0", ctypes.c_int32),
         ("r_value", ctypes.c_void_p), ("r_index", ctypes.c_int64), ("m_value", ctypes.c_void_p),
         ("daily_infected", ctypes.c_void_p), ("daily_deaths", ctypes.c_void_p), ("dne_dr", ctypes.c_void_p),
         ("sum_dne_dr", ctypes.c_void_p), ("death_count", ctypes.c_void_p), ("recovered_step", ctypes.c_void_p),
-        ("partials", ctypes.c_void_p), ("error_flag", ctypes.c_void_p),
-        ("grid", ctypes.c_int32), ("use_smem_bitmap", ctypes.c_int32),
+        ("lam_part", ctypes.c_void_p), ("lam1_part", ctypes.c_void_p), ("dirty", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p), ("error_flag", ctypes.c_void_p),
+        ("grid", ctypes.c_int32), ("tasks_per_group", ctypes.c_int32),
     ]
 
 
@@ -102,9 +106,10 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.at_seirm_abi_version.restype = ctypes.c_int
         L.at_last_error.restype = ctypes.c_char_p
-        for name in ("at_seirm_sizeof_launch", "at_seirm_sizeof_model", "at_seirm_workspace_bytes",
-                     "at_seirm_smem_bitmap_capacity"):
+        for name in ("at_seirm_sizeof_launch", "at_seirm_sizeof_model", "at_seirm_workspace_bytes"):
             getattr(L, name).restype = ctypes.c_int64
+        L.at_seirm_max_block_size.restype = ctypes.c_int64
+        L.at_seirm_max_block_size.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
         L.at_seirm_step.restype = ctypes.c_int
         L.at_seirm_step.argtypes = [ctypes.POINTER(SeirmModel), ctypes.POINTER(SeirmLaunch), ctypes.c_void_p]
         L.at_seirm_episode_backward.restype = ctypes.c_int

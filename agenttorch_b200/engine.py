@@ -18,7 +18,6 @@ from typing import Optional
 import torch
 
 from . import _native as nat
-from .graph import ContactGraph
 
 
 # ----------------------------------------------------------------------------------------- model
@@ -141,30 +140,55 @@ def _ptr(t, dtype=None, name="tensor"):
 
 
 class SeirmEngine:
-    def __init__(self, graph: ContactGraph, spec: SeirmSpec, process_group=None, use_smem_bitmap=-1, grid=0, code_len=None):
-        if not graph.row_ptr.is_cuda:
+    def __init__(self, graph, spec: SeirmSpec, process_group=None, grid=0, code_len=None, block_size=None,
+                 tasks_per_group=0):
+        """graph: ContactGraph (plain CSR, re-blocked here) or a prebuilt BlockedGraph.  block_size: sources
+        per column block (default: the largest that fits the shared-memory bitmap, i.e. as few blocks as
+        possible); code_len: length of the code/bitmap arrays (multi-GPU: world_size equal slices)."""
+        from .graph import BlockedGraph, block_graph, choose_block_size
+
+        if not graph.device.type == "cuda":
             raise RuntimeError("SeirmEngine needs the contact graph on a CUDA device; there is no CPU fallback")
         self.lib = nat.lib()
-        self.graph = graph
         self.spec = spec
         self.device = graph.device
         self.model = spec.to_struct(graph.i_bar)
+        if float(spec.sfi[0]) != 0.0:
+            raise NotImplementedError("SFInfector[0] must be 0 (agents with a fractional stage are not tracked as infectious)")
         self.pg = process_group
-        self.use_smem_bitmap = use_smem_bitmap
         self.grid = grid
-        n_src = graph.n_sources
-        self.n_code = ((n_src + 1023) // 1024) * 1024
-        if code_len is not None:      # multi-GPU: world_size equal slices, one per rank (graph.shard_bounds)
-            if code_len < n_src or code_len % 1024:
-                raise ValueError("code_len must cover all sources and be a multiple of 1024")
-            self.n_code = int(code_len)
-        words = self.n_code // 32
-        self.code = [torch.zeros(self.n_code, dtype=torch.uint8, device=self.device) for _ in range(2)]
-        self.bitmap = [torch.zeros(words + 4, dtype=torch.int32, device=self.device) for _ in range(2)]
+        self.tasks_per_group = tasks_per_group
+        n_src = graph.n_sources if code_len is None else int(code_len)
+        if code_len is not None and (code_len < graph.n_sources or code_len % 1024):
+            raise ValueError("code_len must cover all sources and be a multiple of 1024")
+        with torch.cuda.device(self.device):
+            cap = int(self.lib.at_seirm_max_block_size(len(spec.sfs), len(spec.lam_gamma), 1))
+        if isinstance(graph, BlockedGraph):
+            self.graph = graph
+        else:
+            if block_size is None:
+                _, block_size = choose_block_size(n_src, cap)
+            self.graph = block_graph(graph, int(block_size))
+        if self.graph.block_size > cap:
+            raise RuntimeError(f"block_size {self.graph.block_size} exceeds the shared-memory bitmap capacity {cap}")
+        g = self.graph
+        self.n_code = max(((n_src + 1023) // 1024) * 1024, g.n_blocks * g.block_size)
+        dev = self.device
+        self.code = [torch.zeros(self.n_code, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.hot = [torch.zeros(self.n_code // 32 + 4, dtype=torch.int32, device=dev) for _ in range(2)]
         self.cur = 0
-        self.workspace = torch.zeros(self.lib.at_seirm_workspace_bytes() // 8 + 8, dtype=torch.float64, device=self.device)
-        self.error_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.seed_buf = torch.zeros(1, dtype=torch.int64, device=self.device)
+        nt = g.n_tasks
+        self.sus = torch.zeros(nt, dtype=torch.int32, device=dev)
+        self.exp = torch.zeros(nt, dtype=torch.int32, device=dev)
+        self.inf = torch.zeros(nt, dtype=torch.int32, device=dev)
+        self.lam_part = self.lam1_part = self.dirty = None
+        if g.n_blocks > 1:
+            self.lam_part = torch.zeros((g.n_blocks, g.n_rows_pad), dtype=torch.float64, device=dev)
+            self.lam1_part = torch.zeros((g.n_blocks, g.n_rows_pad), dtype=torch.float64, device=dev)
+            self.dirty = torch.zeros((g.n_blocks, nt), dtype=torch.int32, device=dev)
+        self.workspace = torch.zeros(self.lib.at_seirm_workspace_bytes() // 8 + 8, dtype=torch.float64, device=dev)
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.seed_buf = torch.zeros(1, dtype=torch.int64, device=dev)
         self.launch_count = 0
         self._graphs = {}
         self._saved = {}
@@ -180,9 +204,11 @@ class SeirmEngine:
         a.flags = int(flags)
         a.t = int(t)
         a.t_encode = int(t + 1 if t_encode is None else t_encode)
-        a.n_rows, a.n_sources, a.row_offset = g.n_rows, self.n_code, g.row_offset
-        a.row_ptr = _ptr(g.row_ptr, torch.int32, "row_ptr")
-        a.col_idx = _ptr(g.col_idx, torch.int32, "col_idx")
+        a.n_rows, a.n_rows_pad, a.n_sources, a.row_offset = g.n_rows, g.n_rows_pad, self.n_code, g.row_offset
+        a.n_blocks, a.block_size = g.n_blocks, g.block_size
+        a.deg = _ptr(g.deg, torch.int16, "deg")
+        a.seg_base4 = _ptr(g.seg_base4, torch.int32, "seg_base4")
+        a.col = _ptr(g.col, torch.int32, "col")
         a.edge_weight = _ptr(g.edge_weight, torch.float32, "edge_weight")
         if state.stage.shape[0] != g.n_rows:
             raise RuntimeError("state size does not match the graph shard")
@@ -196,12 +222,13 @@ class SeirmEngine:
             raise RuntimeError("age must be float32 or uint8")
         a.age = _ptr(state.age, None, "age")
         a.age_dtype = _AGE_TAG[state.age.dtype]
+        a.sus_bitmap, a.exp_bitmap, a.inf_bitmap = _ptr(self.sus), _ptr(self.exp), _ptr(self.inf)
         ci = self.cur if code_in is None else code_in
         co = 1 - ci if code_out is None else code_out
         a.code_in = _ptr(self.code[ci], torch.uint8)
-        a.bitmap_in = _ptr(self.bitmap[ci], torch.int32)
+        a.hot_bitmap_in = _ptr(self.hot[ci], torch.int32)
         a.code_out = _ptr(self.code[co], torch.uint8)
-        a.bitmap_out = _ptr(self.bitmap[co], torch.int32)
+        a.hot_bitmap_out = _ptr(self.hot[co], torch.int32)
         noise = noise or NoiseSpec()
         a.iso_mode, a.u_mode = noise.iso_mode(), noise.u_mode()
         a.isolation = _ptr(isolation, torch.float32, "isolation")
@@ -218,13 +245,14 @@ class SeirmEngine:
         a.sum_dne_dr = _ptr(sum_dne_dr, torch.float32, "sum_dne_dr")
         a.death_count = _ptr(death_count, torch.float32, "death_count")
         a.recovered_step = _ptr(recovered_step, torch.uint8, "recovered_step")
-        a.partials = _ptr(self.workspace, torch.float64)
+        a.lam_part, a.lam1_part, a.dirty = _ptr(self.lam_part), _ptr(self.lam1_part), _ptr(self.dirty)
+        a.workspace = _ptr(self.workspace, torch.float64)
         a.error_flag = _ptr(self.error_flag, torch.int32)
         a.grid = int(self.grid)
-        a.use_smem_bitmap = int(self.use_smem_bitmap)
+        a.tasks_per_group = int(self.tasks_per_group)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(self.lib.at_seirm_step(ctypes.byref(self.model), ctypes.byref(a), ctypes.c_void_p(stream)))
-        self.launch_count += 1
+        self.launch_count += 2 if (g.n_blocks > 1 and (flags & nat.DO_TRANSMISSION)) else 1
 
     # ------------------------------------------------------------------------ halo exchange
     def exchange(self, buf_index):
@@ -239,14 +267,15 @@ class SeirmEngine:
         rank = dist.get_rank(self.pg)
         code = self.code[buf_index]
         dist.all_gather_into_tensor(code, code[rank * per:(rank + 1) * per], group=self.pg)
-        bm = self.bitmap[buf_index][: self.n_code // 32]
+        bm = self.hot[buf_index][: self.n_code // 32]
         wper = per // 32
         dist.all_gather_into_tensor(bm, bm[rank * wper:(rank + 1) * wper], group=self.pg)
 
     # ----------------------------------------------------------------------------- substeps
     def encode(self, state, t):
-        """Write the infectiousness code/bitmap of step `t` from the current state into the live buffer."""
-        self.launch(state, flags=nat.DO_ENCODE, t=0, t_encode=t, code_in=1 - self.cur, code_out=self.cur)
+        """(Re)derive the row bitmaps from `state.stage` and write the infectiousness code/bitmap of step `t`
+        into the live buffer: the first launch on a state, or after the caller edited it."""
+        self.launch(state, flags=nat.DO_ENCODE | nat.DO_INIT, t=0, t_encode=t, code_in=1 - self.cur, code_out=self.cur)
         self.exchange(self.cur)
 
     def step(self, state, t, noise, r_value, r_index, m_value, *, isolation=None, uniform=None, flags=None,

@@ -213,3 +213,111 @@ def shard_graph(graph, row_begin, row_end):
     w = None if graph.edge_weight is None else _pad_cols(graph.edge_weight[e0:e1].clone())
     return ContactGraph(row_end - row_begin, graph.n_sources, row_begin, (rp[row_begin: row_end + 1] - e0).to(torch.int32),
                         _pad_cols(col), e1 - e0, w, graph.i_bar, graph.i_bar_agent)
+
+
+# --------------------------------------------------------------------------------------- BCSR
+TAIL_PAD = 1024          # ints of padding after the last segment (TMA chunks may read past a segment's end)
+
+
+@dataclass
+class BlockedGraph:
+    """Column-blocked, destination-sorted CSR — the layout the sm_100a kernels stream (include/at_seirm.h).
+
+    Rows are grouped in tasks of 32; sources are split in `n_blocks` ranges of `block_size` ids so that one
+    block's "hot" bitmap fits in shared memory.  Segment s = block*n_tasks + task stores the edges of the
+    task's rows whose source is in the block, row by row, each row in original edge order, 16-byte aligned."""
+    n_rows: int
+    n_rows_pad: int
+    n_sources: int
+    row_offset: int
+    n_blocks: int
+    block_size: int
+    deg: torch.Tensor            # (n_blocks, n_rows_pad) int16 holding uint16 counts
+    seg_base4: torch.Tensor      # (n_blocks*n_tasks + 1,) int32, units of 4 edges
+    col: torch.Tensor            # (padded edges + TAIL_PAD,) int32 block-local source ids
+    num_edges: int
+    edge_weight: Optional[torch.Tensor] = None
+    i_bar: float = 1.0
+    i_bar_agent: int = -1
+
+    @property
+    def device(self):
+        return self.col.device
+
+    @property
+    def n_tasks(self):
+        return self.n_rows_pad // 32
+
+    def avg_degree(self):
+        return self.num_edges / max(self.n_rows, 1)
+
+    def to(self, device):
+        return BlockedGraph(self.n_rows, self.n_rows_pad, self.n_sources, self.row_offset, self.n_blocks, self.block_size,
+                            self.deg.to(device), self.seg_base4.to(device), self.col.to(device), self.num_edges,
+                            None if self.edge_weight is None else self.edge_weight.to(device), self.i_bar, self.i_bar_agent)
+
+
+def choose_block_size(n_sources, max_block_size):
+    """Smallest number of equal blocks (multiples of 1024 ids) that fit the shared-memory bitmap capacity."""
+    if max_block_size < 1024:
+        raise RuntimeError("shared-memory bitmap capacity too small")
+    n_blocks = max(1, -(-n_sources // max_block_size))
+    block = -(-n_sources // n_blocks)
+    block = -(-block // 1024) * 1024
+    return n_blocks, block
+
+
+def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = None) -> BlockedGraph:
+    """ContactGraph (plain dst-sorted CSR, global source ids) -> BlockedGraph, on the graph's device."""
+    dev = graph.device
+    n_rows, e = graph.n_rows, graph.num_edges
+    n_rows_pad = -(-max(n_rows, 1) // 32) * 32
+    n_tasks = n_rows_pad // 32
+    if block_size % 1024:
+        raise ValueError("block_size must be a multiple of 1024")
+    nb = max(1, -(-graph.n_sources // block_size)) if n_blocks is None else n_blocks
+    if nb * block_size < graph.n_sources:
+        raise ValueError("blocks do not cover the source id space")
+    if nb > 64:
+        raise ValueError("more than 64 column blocks: shard the graph over more GPUs")
+    row_ptr = graph.row_ptr.long()
+    degf = row_ptr[1:] - row_ptr[:-1]
+    col = graph.col_idx[:e].long()
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=dev), degf)
+    if nb == 1:
+        key = rows
+        order = None
+    else:
+        blk = torch.div(col, block_size, rounding_mode="floor")
+        key = blk * n_rows_pad + rows
+        order = torch.sort(key, stable=True).indices
+        key = key[order]
+        col = col[order] - blk[order] * block_size
+        del blk
+    del rows
+    n_seg = nb * n_tasks
+    deg2 = torch.bincount(key, minlength=nb * n_rows_pad)
+    if e and int(deg2.max()) > 65535:
+        raise ValueError("a row has more than 65535 in-edges inside one column block")
+    seg = key >> 5
+    seg_len = torch.bincount(seg, minlength=n_seg)
+    seg_pad = ((seg_len + 3) >> 2) << 2
+    seg_base = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
+    seg_base[1:] = torch.cumsum(seg_pad, 0)
+    seg_first = torch.zeros(n_seg, dtype=torch.int64, device=dev)
+    seg_first[1:] = torch.cumsum(seg_len, 0)[:-1]
+    total = int(seg_base[-1])
+    if total // 4 >= 2**31:
+        raise ValueError("graph shard too large for int32 segment bases")
+    pos = torch.arange(e, device=dev) - seg_first[seg] + seg_base[:-1][seg]
+    col_out = torch.zeros(total + TAIL_PAD, dtype=torch.int32, device=dev)
+    col_out[pos] = col.to(torch.int32)
+    w_out = None
+    if graph.edge_weight is not None:
+        w = graph.edge_weight[:e]
+        w_out = torch.ones(total + TAIL_PAD, dtype=torch.float32, device=dev)
+        w_out[pos] = w if order is None else w[order]
+    deg16 = (deg2.reshape(nb, n_rows_pad) & 0xFFFF).to(torch.int32)
+    deg16 = torch.where(deg16 >= 32768, deg16 - 65536, deg16).to(torch.int16).contiguous()
+    return BlockedGraph(n_rows, n_rows_pad, graph.n_sources, graph.row_offset, nb, block_size, deg16,
+                        (seg_base >> 2).to(torch.int32).contiguous(), col_out, e, w_out, graph.i_bar, graph.i_bar_agent)

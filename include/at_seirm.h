@@ -27,30 +27,34 @@
 extern "C" {
 #endif
 
-#define AT_SEIRM_ABI_VERSION 3
-#define AT_MAX_SFS 16        /* SFSusceptibility entries (config.yaml:206-223 has 9)   */
-#define AT_MAX_SFI 8         /* SFInfector entries (config.yaml:191-205 has 5)         */
-#define AT_MAX_LAMGAMMA 84   /* lam_gamma_integrals entries; 1 + 3*K codes fit a byte  */
+#define AT_SEIRM_ABI_VERSION 4
+#define AT_MAX_SFS 16        /* SFSusceptibility entries (config.yaml has 9)                     */
+#define AT_MAX_SFI 8         /* SFInfector entries (config.yaml has 5)                           */
+#define AT_MAX_LAMGAMMA 84   /* lam_gamma_integrals entries; 1 + 3*K infectiousness codes fit a byte */
+#define AT_MAX_BLOCKS 64     /* column blocks of the contact graph                               */
 
 /* dtype tags for the timer / age arrays */
-#define AT_TIMER_F32 0       /* reference layout: float32 holding integers (Q3)        */
-#define AT_TIMER_I16 1       /* packed engine layout                                   */
+#define AT_TIMER_F32 0       /* reference layout: float32 holding integers (Q3)                  */
+#define AT_TIMER_I16 1       /* packed engine layout                                             */
 #define AT_AGE_F32 0
 #define AT_AGE_U8 1
 
 /* isolation decision W (MakeIsolationDecision.forward, new_transmission/action.py:51-67) */
-#define AT_ISO_TENSOR 0      /* W read from `isolation` (float32, any value in [0,1])   */
-#define AT_ISO_HASH_SOFT 1   /* W = uniform[0,1) from the counter hash (action.py:54)   */
-#define AT_ISO_HASH_HARD 2   /* W = 1 with probability p_isolate else 0                 */
-#define AT_ISO_NONE 3        /* W = 0                                                   */
+#define AT_ISO_TENSOR 0      /* W read from `isolation` (float32, any value in [0,1])             */
+#define AT_ISO_HASH_SOFT 1   /* W = uniform[0,1) from the counter hash (action.py:54)             */
+#define AT_ISO_HASH_HARD 2   /* W = 1 with probability p_isolate else 0                           */
+#define AT_ISO_NONE 3        /* W = 0                                                             */
 /* exposure uniform U (stands in for torch.bernoulli, distributions.py:16) */
-#define AT_U_TENSOR 0        /* U read from `uniform` (float32)                         */
-#define AT_U_HASH 1          /* U from the counter hash: top 24 bits of SplitMix64      */
+#define AT_U_TENSOR 0        /* U read from `uniform` (float32)                                   */
+#define AT_U_HASH 1          /* U from the counter hash: top 24 bits of SplitMix64                */
 
 /* what one launch does */
-#define AT_DO_TRANSMISSION 1 /* substep '0' transition (NewTransmission.forward)        */
-#define AT_DO_PROGRESSION 2  /* substep '1' transition (SEIRMProgression.forward)       */
-#define AT_DO_ENCODE 4       /* write the infectiousness code/bitmap of step `t_encode` */
+#define AT_DO_TRANSMISSION 1 /* substep '0' transition (NewTransmission.forward)                  */
+#define AT_DO_PROGRESSION 2  /* substep '1' transition (SEIRMProgression.forward)                 */
+#define AT_DO_ENCODE 4       /* write the infectiousness code/bitmap of step `t_encode`           */
+#define AT_DO_INIT 8         /* derive the row bitmaps (susceptible/exposed/infected) from `stage`
+                                instead of reading them (first launch on a state, or after the
+                                caller edited the state)                                          */
 
 /* Model constants (simulation_metadata + environment tables of config.yaml). Host struct. */
 typedef struct at_seirm_model {
@@ -64,31 +68,49 @@ typedef struct at_seirm_model {
     float lam_gamma[AT_MAX_LAMGAMMA];
 } at_seirm_model;
 
-/* One launch of the step kernel.  Host struct, passed by pointer; pointers inside are device. */
+/*
+ * One launch of the step kernels.  Host struct, passed by pointer; pointers inside are device.
+ *
+ * Contact graph = column-blocked, destination-sorted CSR ("BCSR"), replacing the (2,E) COO edge_index that
+ * the reference gathers through PyG (utils.py:129-148, transition.py:209-218):
+ *   rows (destinations) are grouped in tasks of 32; sources are split in n_blocks ranges of block_size ids;
+ *   segment s = block*n_tasks + task holds the edges of the task's 32 rows whose source lies in the block,
+ *   row by row, each row in ORIGINAL edge order, starting at col[4*seg_base4[s]] (16-byte aligned);
+ *   col holds block-local source ids (src - block*block_size); deg[block][row] is the row's edge count in
+ *   the block.  Edges are used as written: directed, duplicates and self-loops kept (Q9).
+ */
 typedef struct at_seirm_launch {
     int32_t abi_version;        /* = AT_SEIRM_ABI_VERSION */
     int32_t flags;              /* AT_DO_* */
     int32_t t;                  /* current_step */
     int32_t t_encode;           /* step whose infectiousness is encoded (normally t+1) */
-    /* destination-sorted CSR of the rows this rank owns (stable: original edge order in a row) */
+    /* graph */
     int64_t n_rows;             /* owned agents */
-    int64_t n_sources;          /* length of code_in / 32*words of bitmap_in (>= max col_idx+1) */
-    int64_t row_offset;         /* global id of local row 0: index of this rank's slice in code/bitmap,
-                                   and the agent id fed to the counter hash */
-    const int32_t* row_ptr;     /* n_rows+1 */
-    const int32_t* col_idx;     /* E (+ >= 4 ints of padding), source ids; 16-byte aligned */
-    const float* edge_weight;   /* E or NULL when all weights are 1 (utils.py:144) */
-    /* agent state, updated in place */
+    int64_t n_rows_pad;         /* n_rows rounded up to 32 (leading dimension of deg, dirty, lam_part) */
+    int64_t n_sources;          /* length of code_in (multiple of 1024) */
+    int64_t row_offset;         /* global id of local row 0 (multiple of 32): slice of this rank in
+                                   code/hot_bitmap, and the agent id fed to the counter hash */
+    int32_t n_blocks, block_size;   /* block_size multiple of 1024 */
+    const uint16_t* deg;        /* [n_blocks][n_rows_pad] */
+    const int32_t* seg_base4;   /* [n_blocks*n_tasks + 1], units of 4 edges */
+    const int32_t* col;         /* segment-padded, + >= 512 ints of tail padding */
+    const float* edge_weight;   /* parallel to col, or NULL when all weights are 1 (utils.py:144) */
+    /* agent state, updated in place and only where it changes */
     float* stage;               /* n_rows */
     void* next_stage_time;      /* n_rows, dtype timer_dtype */
     void* infected_time;        /* n_rows */
     const void* age;            /* n_rows, dtype age_dtype */
     int32_t timer_dtype, age_dtype;
-    /* infectiousness of step t (read) and of step t_encode (written for owned rows) */
+    /* row bitmaps (one bit per owned row, word = task): stage == 0 / == 1 / == 2.  Read unless AT_DO_INIT,
+       always rewritten. */
+    uint32_t* sus_bitmap;       /* n_rows_pad/32 words */
+    uint32_t* exp_bitmap;
+    uint32_t* inf_bitmap;
+    /* infectiousness of step t (read) and of step t_encode (written for owned rows), per SOURCE id */
     const uint8_t* code_in;     /* n_sources */
-    const uint32_t* bitmap_in;  /* ceil(n_sources/32) */
-    uint8_t* code_out;          /* n_sources; written at [row_offset, row_offset+n_rows) */
-    uint32_t* bitmap_out;       /* row_offset must be a multiple of 32 */
+    const uint32_t* hot_bitmap_in;  /* n_sources/32 (+4) words: code != 0 */
+    uint8_t* code_out;          /* written at [row_offset, row_offset+n_rows) */
+    uint32_t* hot_bitmap_out;
     /* noise */
     int32_t iso_mode, u_mode;
     const float* isolation;     /* n_rows or NULL */
@@ -108,11 +130,15 @@ typedef struct at_seirm_launch {
     float* sum_dne_dr;          /* [t] = sum_i dne_dr, or NULL */
     float* death_count;         /* [t] = sum(stage*rd/2), or NULL (d daily_deaths / d M) */
     uint8_t* recovered_step;    /* n_rows or NULL: set to t where the I->R transition fires */
-    /* workspace: caller-zeroed once; 4 doubles per CTA + one ticket word at the end */
-    double* partials;           /* at_seirm_workspace_bytes() bytes */
+    /* scratch for n_blocks > 1 (per-block partial lambdas), else NULL */
+    double* lam_part;           /* [n_blocks][n_rows_pad] */
+    double* lam1_part;          /* [n_blocks][n_rows_pad], needed when dne_dr != NULL */
+    uint32_t* dirty;            /* [n_blocks][n_rows_pad/32] */
+    /* workspace: at_seirm_workspace_bytes() bytes, zeroed once by the caller, reset by every launch */
+    void* workspace;
     int32_t* error_flag;        /* or NULL; set non-zero on a lam_gamma index out of range (Q10) */
-    /* launch geometry: 0 = library default */
-    int32_t grid, use_smem_bitmap; /* use_smem_bitmap: -1 auto, 0 off, 1 on */
+    int32_t grid;               /* CTAs, 0 = one per SM */
+    int32_t tasks_per_group;    /* scheduling granule (1..8 tasks of 32 rows), 0 = library default */
 } at_seirm_launch;
 
 /* ---- queries (host only) ---- */
@@ -121,17 +147,18 @@ const char* at_last_error(void);
 /* sizeof() of the two host structs, so that a foreign-language mirror can be checked at load time */
 int64_t at_seirm_sizeof_launch(void);
 int64_t at_seirm_sizeof_model(void);
-/* bytes of `partials` the step / backward kernels need (independent of N) */
 int64_t at_seirm_workspace_bytes(void);
-/* largest n_sources whose infectious bitmap the step kernel stages in shared memory */
-int64_t at_seirm_smem_bitmap_capacity(void);
+/* largest block_size (sources per column block) whose "hot" bitmap the gather stages in shared memory,
+   for a model with n_sfs susceptibility classes and n_lam_gamma integrals (tables share the same smem) */
+int64_t at_seirm_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t want_grad);
 
 /*
- * at_seirm_step — one launch of the fused agent update on `stream`.
- * Replaces, per the flags: NewTransmission.forward (transition.py:131-252, including the PyG
- * gather/scatter-add and the straight-through Bernoulli), SEIRMProgression.forward
- * (seirm_progression/transition.py:90-121), and produces what their autograd graph would have
- * saved (dne_dr, death_count, recovered_step) without any per-edge intermediate.
+ * at_seirm_step — one step (or part of one, per the flags) of the agent update on `stream`.
+ * Replaces NewTransmission.forward (transition.py:131-252, including the PyG gather/scatter-add and the
+ * straight-through Bernoulli), SEIRMProgression.forward (seirm_progression/transition.py:90-121), and
+ * produces what their autograd graph would have saved (dne_dr, death_count, recovered_step) without any
+ * per-edge intermediate.  n_blocks == 1: one fused launch; n_blocks > 1: a gather launch over all column
+ * blocks followed by the update launch.
  */
 int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, void* stream);
 
@@ -148,7 +175,7 @@ int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld,
                               const float* sum_dne_dr, const float* death_count,
                               const float* g_daily_infected, const float* g_daily_deaths,
                               const float* m_value, float* grad_r, float* grad_m,
-                              double* partials, int32_t grid, void* stream);
+                              void* workspace, int32_t grid, void* stream);
 
 /*
  * at_noise_fill — materialise the counter-hash noise (same values the step kernel generates in

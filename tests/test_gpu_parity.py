@@ -17,7 +17,7 @@ def _r_steps_and_grad(r2_np, T, num_weeks=3):
     return r2, r_steps
 
 
-def _run_engine(g, *, packed, smem, use_tensor_noise=False, cuda_graph=False, grid=0):
+def _run_engine(g, *, packed, block_size=None, use_tensor_noise=False, cuda_graph=False, grid=0, tasks_per_group=0):
     from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
     from agenttorch_b200.graph import build_contact_graph, mean_interactions_from_age
 
@@ -29,7 +29,7 @@ def _run_engine(g, *, packed, smem, use_tensor_noise=False, cuda_graph=False, gr
     edges = torch.from_numpy(g["edges"].astype(np.int64)).t().contiguous()
     graph = build_contact_graph(edges, n, mean_interactions=mi).to(dev)
     spec = SeirmSpec(num_steps=T)
-    eng = SeirmEngine(graph, spec, use_smem_bitmap=1 if smem else 0, grid=grid)
+    eng = SeirmEngine(graph, spec, block_size=block_size, grid=grid, tasks_per_group=tasks_per_group)
     st = SeirmState.from_initial(g["stage0"].astype(np.float32), g["age"], T, dev, packed=packed)
     if use_tensor_noise:
         U, W = make_noise(g["seed"], g["mode"], n, T, float(g["p_isolate"]))
@@ -57,18 +57,21 @@ def _check(g, st, grad_r2, grad_m):
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-@pytest.mark.parametrize("packed,smem", [(True, True), (False, False)])
-def test_episode_matches_reference_golden(case, packed, smem):
+@pytest.mark.parametrize("packed,block_size", [(True, None), (False, 1024), (True, 2048)])
+def test_episode_matches_reference_golden(case, packed, block_size):
+    """block_size=None: one column block, fused kernel; 1024/2048: column-blocked gather + update kernels."""
     g = load_golden(case)
-    st, gr2, gm, _ = _run_engine(g, packed=packed, smem=smem)
+    st, gr2, gm, eng = _run_engine(g, packed=packed, block_size=block_size)
+    if block_size is not None and len(g["age"]) > block_size:
+        assert eng.graph.n_blocks > 1
     _check(g, st, gr2, gm)
 
 
 @pytest.mark.parametrize("case", ["synth3k_soft", "astoria_hard"])
 def test_tensor_noise_and_cuda_graph_paths(case):
     g = load_golden(case)
-    st, gr2, gm, _ = _run_engine(g, packed=True, smem=True, use_tensor_noise=True)
+    st, gr2, gm, _ = _run_engine(g, packed=True, use_tensor_noise=True, tasks_per_group=1)
     _check(g, st, gr2, gm)
-    st, gr2, gm, eng = _run_engine(g, packed=True, smem=False, cuda_graph=True, grid=7)
+    st, gr2, gm, eng = _run_engine(g, packed=True, block_size=1024, cuda_graph=True, grid=7, tasks_per_group=8)
     _check(g, st, gr2, gm)
     assert eng.launch_count > 0

@@ -8,8 +8,8 @@ for n in (100_000, 300_000):
     age, stage0 = synthetic_population(n, 1234, device=dev)
     graph = synthetic_contact_graph(n, 20.0, 99, device=dev, mean_interactions=mean_interactions_from_age(age))
     for grid in (8, 37, 64, 65, 98, 128, 148, 0):
-        for smem in (0, 1):
-            eng = SeirmEngine(graph, SeirmSpec(num_steps=T), use_smem_bitmap=smem, grid=grid)
+        for smem in (None, 32768):
+            eng = SeirmEngine(graph, SeirmSpec(num_steps=T), block_size=smem, grid=grid)
             st = SeirmState.from_initial(stage0, age, T, dev)
             sv = eng.run_episode(st, torch.full((T,), 14.25, device=dev), torch.tensor([0.12], device=dev), T, NoiseSpec(seed=5, isolation="hard"), want_grad=True)
             torch.cuda.synchronize()
