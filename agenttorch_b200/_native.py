@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libat_seirm.so")
 SRC_PATH = os.path.join(_PKG, "csrc", "at_seirm.cu")
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_SFS, MAX_SFI, MAX_LAMGAMMA = 16, 8, 84
 TIMER_F32, TIMER_I16 = 0, 1
 AGE_F32, AGE_U8 = 0, 1
@@ -48,7 +48,8 @@ class SeirmLaunch(ctypes.Structure):
         ("abi_version", ctypes.c_int32), ("flags", ctypes.c_int32), ("t", ctypes.c_int32), ("t_encode", ctypes.c_int32),
         ("n_rows", ctypes.c_int64), ("n_rows_pad", ctypes.c_int64), ("n_sources", ctypes.c_int64), ("row_offset", ctypes.c_int64),
         ("n_blocks", ctypes.c_int32), ("block_size", ctypes.c_int32),
-        ("deg", ctypes.c_void_p), ("seg_base4", ctypes.c_void_p), ("col", ctypes.c_void_p), ("edge_weight", ctypes.c_void_p),
+        ("rows_per_task", ctypes.c_int32), ("edges_per_chunk", ctypes.c_int32),
+        ("row_start", ctypes.c_void_p), ("seg_info", ctypes.c_void_p), ("col", ctypes.c_void_p), ("edge_weight", ctypes.c_void_p),
         ("stage", ctypes.c_void_p), ("next_stage_time", ctypes.c_void_p), ("infected_time", ctypes.c_void_p),
         ("age", ctypes.c_void_p), ("timer_dtype", ctypes.c_int32), ("age_dtype", ctypes.c_int32),
         ("sus_bitmap", ctypes.c_void_p), ("exp_bitmap", ctypes.c_void_p), ("inf_bitmap", ctypes.c_void_p),
@@ -63,6 +64,7 @@ class SeirmLaunch(ctypes.Structure):
         ("lam_part", ctypes.c_void_p), ("lam1_part", ctypes.c_void_p), ("dirty", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("error_flag", ctypes.c_void_p),
         ("grid", ctypes.c_int32), ("tasks_per_group", ctypes.c_int32),
+        ("warps_per_cta", ctypes.c_int32), ("_pad1", ctypes.c_int32),
     ]
 
 
@@ -109,7 +111,7 @@ def lib():
         for name in ("at_seirm_sizeof_launch", "at_seirm_sizeof_model", "at_seirm_workspace_bytes"):
             getattr(L, name).restype = ctypes.c_int64
         L.at_seirm_max_block_size.restype = ctypes.c_int64
-        L.at_seirm_max_block_size.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+        L.at_seirm_max_block_size.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
         L.at_seirm_step.restype = ctypes.c_int
         L.at_seirm_step.argtypes = [ctypes.POINTER(SeirmModel), ctypes.POINTER(SeirmLaunch), ctypes.c_void_p]
         L.at_seirm_episode_backward.restype = ctypes.c_int

@@ -27,16 +27,12 @@
 
 #include "at_seirm.h"
 
-#define NT 512                      // threads per CTA
-#define NW (NT / 32)                // warps per CTA
-#define CH 512                      // edges per staged chunk (2 KB)
-#define LIST_CAP 256                // hit-list entries per warp
-#define MAXG 8                      // max tasks per scheduling group
-#define WARP_SMEM (2 * CH * 4 + LIST_CAP * 4 + 64)
+#define NT_MAX 512                  // max threads per CTA (16 warps); the host may launch fewer warps
+#define MAXG 8                      // max gather tasks per scheduling group
 #define FX_SCALE 4294967296.0       // 2^32 fixed point for the daily sums
 
-#define MODE_FUSED 0                // n_blocks == 1: gather + update per task
-#define MODE_GATHER 1               // n_blocks > 1: partial lambdas of every column block
+#define MODE_FUSED 0                // n_blocks == 1: gather + update per 32-row task
+#define MODE_GATHER 1               // n_blocks > 1: partial lambdas of every column block, 256-row tasks
 #define MODE_UPDATE 2               // update only (lambda from partials, or no transmission)
 
 // workspace layout (bytes)
@@ -74,15 +70,15 @@ __host__ __device__ __forceinline__ float at_u_isolation(uint64_t z) {
 }
 
 // --------------------------------------------------------------------------------- typed accessors
-template <typename T> __device__ __forceinline__ int load_timer(const void* p, int64_t i);
-template <> __device__ __forceinline__ int load_timer<float>(const void* p, int64_t i) { return (int)((const float*)p)[i]; }
-template <> __device__ __forceinline__ int load_timer<int16_t>(const void* p, int64_t i) { return (int)((const int16_t*)p)[i]; }
-template <typename T> __device__ __forceinline__ void store_timer(void* p, int64_t i, int v);
-template <> __device__ __forceinline__ void store_timer<float>(void* p, int64_t i, int v) { ((float*)p)[i] = (float)v; }
-template <> __device__ __forceinline__ void store_timer<int16_t>(void* p, int64_t i, int v) { ((int16_t*)p)[i] = (int16_t)v; }
-template <typename T> __device__ __forceinline__ int load_age(const void* p, int64_t i);
-template <> __device__ __forceinline__ int load_age<float>(const void* p, int64_t i) { return (int)((const float*)p)[i]; }
-template <> __device__ __forceinline__ int load_age<uint8_t>(const void* p, int64_t i) { return (int)((const uint8_t*)p)[i]; }
+__device__ __forceinline__ int load_timer(const void* p, int64_t i, bool f32) {
+    return f32 ? (int)((const float*)p)[i] : (int)((const int16_t*)p)[i];
+}
+__device__ __forceinline__ void store_timer(void* p, int64_t i, int v, bool f32) {
+    if (f32) ((float*)p)[i] = (float)v; else ((int16_t*)p)[i] = (int16_t)v;
+}
+__device__ __forceinline__ int load_age(const void* p, int64_t i, bool f32) {
+    return f32 ? (int)((const float*)p)[i] : (int)((const uint8_t*)p)[i];
+}
 
 // ------------------------------------------------------------------------------- TMA / mbarrier PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,19 +106,26 @@ struct KModel {   // device copy of at_seirm_model (kernel parameter, by value)
     float sfs[AT_MAX_SFS], sfi[AT_MAX_SFI], lg[AT_MAX_LAMGAMMA];
 };
 
+__host__ __device__ constexpr int warp_smem_bytes(int cap) { return 2 * cap * 4 + 128 + 64; }
+
 // -------------------------------------------------------------------------------------- the kernel
-template <int MODE, bool WEIGHTED, typename TimerT, typename AgeT>
-__global__ void __launch_bounds__(NT, 1)
+// RL4 = 128-bit loads per lane per chunk: a chunk holds CAP = 128*RL4 edges and lane L owns the RL = 4*RL4
+// consecutive edges [L*RL, (L+1)*RL) of it.
+template <int MODE, int RL4>
+__global__ void __launch_bounds__(NT_MAX, 1)
 seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const int NC, const int G)
 {
+    constexpr int RL = 4 * RL4, CAP = 32 * RL, WSM = warp_smem_bytes(CAP);
+    constexpr int ROWS = (MODE == MODE_GATHER) ? 8 : 1;        // rows per lane in a gather task
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [NW per-warp areas][Tdiv f64 n_sfs*NC][T1div f64 n_sfs*NC][s_A f32 256][s_G f32 256][hot bitmap]
-    double* s_T = reinterpret_cast<double*>(smem_raw + NW * WARP_SMEM);
+    const int nw = blockDim.x >> 5;
+    // [per-warp areas][Tdiv f64 n_sfs*NC][T1div f64 n_sfs*NC][s_A f32 256][s_G f32 256][hot bitmap]
+    double* s_T = reinterpret_cast<double*>(smem_raw + nw * WSM);
     double* s_T1 = s_T + m.n_sfs * NC;
     float* s_A = reinterpret_cast<float*>(s_T1 + m.n_sfs * NC);
     float* s_G = s_A + 256;
-    uint32_t* s_bm = reinterpret_cast<uint32_t*>(s_G + 256);
-    __shared__ long long s_red[NW][3];
+    const unsigned char* s_bm = reinterpret_cast<const unsigned char*>(s_G + 256);
+    __shared__ long long s_red[NT_MAX / 32][3];
     __shared__ int s_is_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -131,7 +134,9 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     const bool do_enc = (a.flags & AT_DO_ENCODE) != 0;
     const bool do_init = (a.flags & AT_DO_INIT) != 0;
     const bool want_grad = a.dne_dr != nullptr;
-    const bool has_gather = (MODE != MODE_UPDATE) && do_trans;
+    const bool weighted = a.edge_weight != nullptr;
+    const bool timer_f32 = a.timer_dtype == AT_TIMER_F32, age_f32 = a.age_dtype == AT_AGE_F32;
+    constexpr bool HAS_GATHER = (MODE != MODE_UPDATE);
     const int t = a.t;
     const int block = (MODE == MODE_GATHER) ? (int)(blockIdx.x % a.n_blocks) : 0;
     const float R = do_trans ? a.r_value[a.r_index] : 0.f;
@@ -150,10 +155,14 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
         s_G[tid] = gv;
     }
     __syncthreads();
-    if (has_gather) {
+    unsigned char* wsm = smem_raw + warp * WSM;
+    int32_t* s_col = reinterpret_cast<int32_t*>(wsm);
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(wsm + 2 * CAP * 4);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(wsm + 2 * CAP * 4 + 128);
+    if (HAS_GATHER) {
         // message of an unweighted edge, exactly as the reference forms it (transition.py:78-83):
         // float32 product chain ((R*S_i)*A_j)*G_j (B_n == 1 is exact), then float64 division by I_bar
-        for (int i = tid; i < m.n_sfs * NC; i += NT) {
+        for (int i = tid; i < m.n_sfs * NC; i += blockDim.x) {
             const int ag = i / NC, c = i % NC;
             const float s = m.sfs[ag];
             const float av = c < 256 ? s_A[c] : 0.f, gv = c < 256 ? s_G[c] : 0.f;
@@ -161,301 +170,363 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             s_T1[i] = (double)__fmul_rn(__fmul_rn(s, av), gv) / ibar;
         }
         const uint4* src = reinterpret_cast<const uint4*>(a.hot_bitmap_in + (size_t)block * (a.block_size >> 5));
-        uint4* dst = reinterpret_cast<uint4*>(s_bm);
-        for (int i = tid; i < (bm_words >> 2); i += NT) dst[i] = __ldg(src + i);
+        uint4* dst = reinterpret_cast<uint4*>(const_cast<unsigned char*>(s_bm));
+        for (int i = tid; i < (bm_words >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+        if (lane == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    unsigned char* wsm = smem_raw + warp * WARP_SMEM;
-    int32_t* s_col = reinterpret_cast<int32_t*>(wsm);
-    uint32_t* s_list = reinterpret_cast<uint32_t*>(wsm + 2 * CH * 4);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(wsm + 2 * CH * 4 + LIST_CAP * 4);
-    if (lane == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    const int64_t ntasks = a.n_rows_pad >> 5;
-    const int64_t ngroups = (ntasks + G - 1) / G;
-    int* counter = reinterpret_cast<int*>(ws + (MODE == MODE_GATHER ? WS_GCOUNTERS + 4 * block : WS_COUNTER));
-    const uint16_t* deg_b = a.deg ? a.deg + (size_t)block * a.n_rows_pad : nullptr;
-    const int32_t* segb = a.seg_base4 ? a.seg_base4 + (size_t)block * ntasks : nullptr;
-    const uint8_t* code_b = a.code_in ? a.code_in + (size_t)block * a.block_size : nullptr;
+    const int ntasks32 = (int)(a.n_rows_pad >> 5);                            // 32-row tasks (bitmap words)
+    const int ntasks = (MODE == MODE_GATHER) ? (int)(a.n_rows_pad >> 8) : ntasks32;
+    const uint16_t* rs_b = HAS_GATHER ? a.row_start + (size_t)block * a.n_rows_pad : nullptr;
+    const int2* seg_b = HAS_GATHER ? reinterpret_cast<const int2*>(a.seg_info) + (size_t)block * ntasks : nullptr;
+    const uint8_t* code_b = HAS_GATHER ? a.code_in + (size_t)block * a.block_size : nullptr;
     const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
+    if (HAS_GATHER) {   // the staging buffers must always hold valid encodings (lanes read past a chunk's end)
+        for (int i = lane; i < 2 * CAP; i += 32) s_col[i] = 0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+    }
+
+    // ---- static cyclic schedule: this warp owns tasks first, first+stride, ...  (deterministic, and the
+    //      next tasks are known in advance, so their metadata and edges are prefetched)
+    int first, stride;
+    if (MODE == MODE_GATHER) {
+        const int ctas_b = ((int)gridDim.x - block + a.n_blocks - 1) / a.n_blocks;      // CTAs serving this block
+        first = ((int)blockIdx.x / a.n_blocks) * nw + warp;
+        stride = ctas_b * nw;
+    } else {
+        first = (int)blockIdx.x * nw + warp;
+        stride = (int)gridDim.x * nw;
+    }
+
+    // Task metadata is prefetched three tasks ahead: `raw` is in flight (loaded last iteration), m2/m1/m0 are
+    // finalised (nothing below touches a freshly loaded register, so the loads never stall the pipeline).
+    struct Meta { int base4, len; uint32_t sus, exp, inf; };
+    struct MetaRaw { int2 seg; uint32_t sus, exp, inf; uint4 s0, s1; };
+    auto load_raw = [&](int task) -> MetaRaw {
+        MetaRaw r; r.seg = make_int2(0, 0); r.sus = 0; r.exp = 0; r.inf = 0;
+        r.s0 = make_uint4(0, 0, 0, 0); r.s1 = make_uint4(0, 0, 0, 0);
+        if (task < ntasks) {
+            if (MODE == MODE_GATHER) {
+                if (do_trans) {
+                    const uint4* sw = reinterpret_cast<const uint4*>(a.sus_bitmap + (size_t)task * 8);
+                    r.s0 = sw[0]; r.s1 = sw[1];
+                }
+            } else if (!do_init) {
+                r.sus = a.sus_bitmap[task];
+                r.exp = a.exp_bitmap[task];
+                r.inf = a.inf_bitmap[task];
+            }
+            if (HAS_GATHER && do_trans) r.seg = seg_b[task];
+        }
+        return r;
+    };
+    auto finalize = [&](const MetaRaw& r) -> Meta {
+        Meta mt;
+        mt.sus = (MODE == MODE_GATHER) ? (r.s0.x | r.s0.y | r.s0.z | r.s0.w | r.s1.x | r.s1.y | r.s1.z | r.s1.w) : r.sus;
+        mt.exp = r.exp; mt.inf = r.inf;
+        mt.base4 = r.seg.x;
+        mt.len = (mt.sus != 0u) ? r.seg.y : 0;            // no susceptible row: nothing to gather
+        return mt;
+    };
+    // per-lane row metadata of the NEXT task (row offsets inside its segment, destination age)
+    struct RowMeta { uint4 rs; int age; };
+    auto load_rows = [&](int task) -> RowMeta {
+        RowMeta rm; rm.rs = make_uint4(0, 0, 0, 0); rm.age = 0;
+        if (HAS_GATHER && do_trans && task < ntasks) {
+            const int64_t row0 = (int64_t)task * (32 * ROWS) + lane * ROWS;
+            if (ROWS == 1) {
+                rm.rs.x = rs_b[row0];
+                if (row0 < a.n_rows) rm.age = load_age(a.age, row0, age_f32);
+            } else {
+                rm.rs = *reinterpret_cast<const uint4*>(rs_b + row0);
+            }
+        }
+        return rm;
+    };
+    // first chunks of consecutive tasks alternate between the two slots; a task's later chunks reuse its slot
+    uint32_t first_issued = 0, first_consumed = 0, waits0 = 0, waits1 = 0;
+    auto issue_chunk = [&](int base4, int len, int ci, uint32_t slot) {
+        if (lane == 0) {
+            const int off = ci * CAP;
+            const uint32_t bytes = (uint32_t)((min(CAP, len - off) + 3) & ~3) * 4u;
+            mbar_expect_tx(&s_bar[slot], bytes);
+            bulk_g2s(s_col + slot * CAP, a.col + ((int64_t)base4 * 4 + off), bytes, &s_bar[slot]);
+        }
+    };
 
     long long acc_ne = 0, acc_dne = 0, acc_dead = 0;
-    uint32_t issued = 0, consumed = 0;      // chunks issued / consumed by this warp since kernel start
+    Meta m0 = finalize(load_raw(first)), m1 = finalize(load_raw(first + stride)), m2 = finalize(load_raw(first + 2 * stride));
+    MetaRaw raw = load_raw(first + 3 * stride);
+    RowMeta rows_next = load_rows(first);
+    if (HAS_GATHER && m0.len > 0) { issue_chunk(m0.base4, m0.len, 0, first_issued & 1u); ++first_issued; }
 
-    for (;;) {
-        int g = 0;
-        if (lane == 0) g = atomicAdd(counter, 1);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        if (g >= ngroups) break;
-        const int64_t task0 = (int64_t)g * G;
-        const int nt = (int)min((int64_t)G, ntasks - task0);
+    for (int task = first; task < ntasks; task += stride) {
+        const Meta mt = m0;
+        const RowMeta rows_cur = rows_next;
+        m0 = m1; m1 = m2;
+        m2 = finalize(raw);
+        raw = load_raw(task + 4 * stride);
+        rows_next = load_rows(task + stride);
+        // first chunk of the next task goes in flight before this one is processed
+        if (HAS_GATHER && m0.len > 0) { issue_chunk(m0.base4, m0.len, 0, first_issued & 1u); ++first_issued; }
 
-        // ---- group meta: lane i holds the susceptible word, segment base and edge total of task i
-        uint32_t my_sus = 0;
-        int my_base4 = 0, my_tot = 0;
-        if (has_gather) {
-            if (lane < nt) {
-                my_sus = a.sus_bitmap[task0 + lane];
-                my_base4 = segb[task0 + lane];
-            }
+        double lam = 0.0, lam1 = 0.0;        // FUSED: lambda of my row; GATHER: of the row being folded
+        // ================================================================== gather + fold
+        if (HAS_GATHER && mt.len > 0) {
+            const int len = mt.len;
+            const int64_t row0 = (int64_t)task * (32 * ROWS) + lane * ROWS;     // my first row
+            int rstart[ROWS + 1];
+            uint32_t my_sus;
+            if (ROWS == 1) {
+                rstart[0] = (int)rows_cur.rs.x;
+                my_sus = (mt.sus >> lane) & 1u;
+            } else {
+                const uint4 v = rows_cur.rs;
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int i = 0; i < MAXG; ++i) {
-                if (i < nt) {
-                    const int d = (int)deg_b[(task0 + i) * 32 + lane];
-                    const int tot = __reduce_add_sync(0xffffffffu, d);
-                    if (lane == i) my_tot = tot;
+                for (int r = 0; r < ROWS; ++r) rstart[r] = (int)((w[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu);
+                my_sus = reinterpret_cast<const uint8_t*>(a.sus_bitmap)[(size_t)task * 32 + lane];
+            }
+            {
+                const int nxt = __shfl_down_sync(0xffffffffu, rstart[0], 1);
+                rstart[ROWS] = (lane == 31) ? len : nxt;
+            }
+            int cur_r = -1;                  // GATHER: row (0..7) whose partial lambda is being accumulated
+            int cur_ag = rows_cur.age < 0 ? 0 : (rows_cur.age >= m.n_sfs ? m.n_sfs - 1 : rows_cur.age);
+            uint32_t dbits = 0;
+            auto flush_row = [&]() {          // GATHER: write the partial lambda of row cur_r
+                if (MODE == MODE_GATHER && cur_r >= 0 && (lam != 0.0 || lam1 != 0.0)) {
+                    const size_t idx = (size_t)block * a.n_rows_pad + row0 + cur_r;
+                    if (dbits & (1u << cur_r)) { lam += a.lam_part[idx]; if (want_grad) lam1 += a.lam1_part[idx]; }
+                    a.lam_part[idx] = lam;
+                    if (want_grad) a.lam1_part[idx] = lam1;
+                    dbits |= 1u << cur_r;
                 }
-            }
-            if (my_sus == 0) my_tot = 0;        // no susceptible row: nothing to gather for this task
-        }
-        // prefetch pointer (task index in group, chunk index)
-        int pf_ti = 0, pf_ci = 0;
-        auto pf_skip_empty = [&]() {
-            while (pf_ti < nt && __shfl_sync(0xffffffffu, my_tot, pf_ti) == 0) ++pf_ti;
-        };
-        auto pf_issue = [&]() {               // issue chunk (pf_ti, pf_ci) into slot issued&1, then advance
-            const int tot = __shfl_sync(0xffffffffu, my_tot, pf_ti);
-            const int base4 = __shfl_sync(0xffffffffu, my_base4, pf_ti);
-            const int off = pf_ci * CH;
-            const int n = min(CH, tot - off);
-            if (lane == 0) {
-                const uint32_t bytes = (uint32_t)((n + 3) & ~3) * 4u;
-                uint64_t* bar = &s_bar[issued & 1];
-                mbar_expect_tx(bar, bytes);
-                bulk_g2s(s_col + (issued & 1) * CH, a.col + ((int64_t)base4 * 4 + off), bytes, bar);
-            }
-            ++issued;
-            if (off + CH < tot) ++pf_ci; else { ++pf_ti; pf_ci = 0; pf_skip_empty(); }
-        };
-        if (has_gather) {
-            pf_skip_empty();
-            if (pf_ti < nt) pf_issue();
-        }
+                lam = 0.0; lam1 = 0.0;
+            };
 
-        for (int ti = 0; ti < nt; ++ti) {
-            const int64_t task = task0 + ti;
-            const int64_t row = task * 32 + lane;
-            const bool valid = row < a.n_rows;
-            double lam = 0.0, lam1 = 0.0;
-            uint32_t sus_w = 0;
-            int ag = -1;
-
-            // ================================================================== gather + fold
-            const int tot = has_gather ? __shfl_sync(0xffffffffu, my_tot, ti) : 0;
-            if (has_gather) sus_w = __shfl_sync(0xffffffffu, my_sus, ti);
-            if (tot > 0) {
-                const int base4 = __shfl_sync(0xffffffffu, my_base4, ti);
-                const int d = (int)deg_b[task * 32 + lane];
-                int incl = d;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
+            const int nch = (len + CAP - 1) / CAP;
+            const uint32_t slot = first_consumed & 1u;
+            ++first_consumed;
+            for (int ci = 0; ci < nch; ++ci) {
+                if (ci > 0) {
+                    // rare: a task larger than one chunk; its later chunks are fetched synchronously into its own
+                    // slot, which has just been drained (the other slot holds the next task's prefetch)
+                    __syncwarp();
+                    issue_chunk(mt.base4, len, ci, slot);
                 }
-                const int start = incl - d;
-                const bool my_sus_bit = (sus_w >> lane) & 1u;
-                int cnt = 0;
-
-                auto fold = [&]() {
-                    // entries are (edge offset << 8 | code), sorted by offset; mine are [start, start+d)
-                    if (my_sus_bit && d > 0) {
-                        int pos = 0;
+                mbar_wait(&s_bar[slot], (slot ? waits1 : waits0) & 1u);
+                if (slot) ++waits1; else ++waits0;
+                const int n = min(CAP, len - ci * CAP);
+                const int32_t* sc = s_col + slot * CAP;
+                const int4* sc4 = reinterpret_cast<const int4*>(sc) + lane * RL4;
+                uint32_t h = 0;
 #pragma unroll
-                        for (int step = LIST_CAP / 2; step >= 1; step >>= 1) {
-                            const int p = pos + step;
-                            if (p <= cnt && (int)(s_list[p - 1] >> 8) < start) pos = p;
-                        }
-                        if (pos < cnt && ag < 0) {
-                            ag = load_age<AgeT>(a.age, row);
-                            ag = ag < 0 ? 0 : (ag >= m.n_sfs ? m.n_sfs - 1 : ag);
-                        }
-                        const int end = start + d;
-                        for (; pos < cnt; ++pos) {
-                            const uint32_t e = s_list[pos];
-                            const int off = (int)(e >> 8);
-                            if (off >= end) break;
-                            const int c = (int)(e & 255u);
-                            if (!WEIGHTED) {
-                                lam += s_T[ag * NC + c];
-                                if (want_grad) lam1 += s_T1[ag * NC + c];
-                            } else {
-                                const float w = a.edge_weight[(int64_t)base4 * 4 + off];
-                                const float s = m.sfs[ag];
-                                lam += (double)__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(R, s), s_A[c]), w), s_G[c]) / ibar;
-                                if (want_grad) lam1 += (double)__fmul_rn(__fmul_rn(__fmul_rn(s, s_A[c]), w), s_G[c]) / ibar;
+                for (int q = 0; q < RL4; ++q) {
+                    const int4 c = sc4[q];
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.x >> 5));
+                    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.y >> 5));
+                    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.z >> 5));
+                    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.w >> 5));
+                    const uint32_t b = ((w0 >> (c.x & 31)) & 1u) | (((w1 >> (c.y & 31)) & 1u) << 1) |
+                                       (((w2 >> (c.z & 31)) & 1u) << 2) | (((w3 >> (c.w & 31)) & 1u) << 3);
+                    h |= b << (4 * q);
+                }
+                {   // drop the bits of positions past the end of the chunk
+                    const int mine = n - lane * RL;
+                    h &= mine >= RL ? 0xffffffffu >> (32 - RL) : (mine <= 0 ? 0u : ((1u << mine) - 1u));
+                }
+                if (__any_sync(0xffffffffu, h != 0u)) {
+                    s_mask[lane] = h;
+                    __syncwarp();
+                    // fold: every lane walks the hit bits of ITS rows, in edge order
+                    const int lo_all = max(rstart[0] - ci * CAP, 0), hi_all = min(rstart[ROWS] - ci * CAP, n);
+                    if (my_sus != 0u && lo_all < hi_all) {
+                        for (int w = lo_all / RL; w <= (hi_all - 1) / RL; ++w) {
+                            uint32_t bits = s_mask[w];
+                            const int b_lo = max(lo_all - w * RL, 0), b_hi = min(hi_all - w * RL, RL);
+                            bits &= (b_hi >= 32 ? 0xffffffffu : ((1u << b_hi) - 1u)) & ~((1u << b_lo) - 1u);
+                            while (bits) {
+                                // up to 4 hits per round: their code gathers (L2) are issued together
+                                int off[4], code[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    off[j] = -1;
+                                    if (bits) { off[j] = w * RL + (__ffs(bits) - 1); bits &= bits - 1u; }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    code[j] = 0;
+                                    if (off[j] >= 0) {
+                                        const uint32_t enc = (uint32_t)sc[off[j]];
+                                        code[j] = (int)__ldg(code_b + (((enc >> 7) << 5) | (enc & 31u)));
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    if (off[j] < 0) continue;
+                                    if (ROWS > 1) {
+                                        const int toff = off[j] + ci * CAP;
+                                        int r = 0;
+#pragma unroll
+                                        for (int q = 1; q < ROWS; ++q) r += (toff >= rstart[q]) ? 1 : 0;
+                                        if (!((my_sus >> r) & 1u)) continue;
+                                        if (r != cur_r) {
+                                            flush_row();
+                                            cur_r = r;
+                                            const int v = load_age(a.age, row0 + r, age_f32);
+                                            cur_ag = v < 0 ? 0 : (v >= m.n_sfs ? m.n_sfs - 1 : v);
+                                        }
+                                    }
+                                    if (!weighted) {
+                                        lam += s_T[cur_ag * NC + code[j]];
+                                        if (want_grad) lam1 += s_T1[cur_ag * NC + code[j]];
+                                    } else {
+                                        const float wgt = a.edge_weight[(int64_t)mt.base4 * 4 + ci * CAP + off[j]];
+                                        const float sa = m.sfs[cur_ag];
+                                        lam += (double)__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(R, sa), s_A[code[j]]), wgt), s_G[code[j]]) / ibar;
+                                        if (want_grad) lam1 += (double)__fmul_rn(__fmul_rn(__fmul_rn(sa, s_A[code[j]]), wgt), s_G[code[j]]) / ibar;
+                                    }
+                                }
                             }
                         }
                     }
-                    __syncwarp();
-                    cnt = 0;
-                };
-
-                const int nch = (tot + CH - 1) / CH;
-                for (int ci = 0; ci < nch; ++ci) {
-                    if (pf_ti < nt) pf_issue();                         // keep the next chunk in flight
-                    const uint32_t slot = consumed & 1u;
-                    mbar_wait(&s_bar[slot], (consumed >> 1) & 1u);
-                    ++consumed;
-                    const int n = min(CH, tot - ci * CH);
-                    const int4* sc = reinterpret_cast<const int4*>(s_col + slot * CH);
-                    for (int mth = 0; mth * 128 < n; ++mth) {
-                        const int i4 = mth * 32 + lane;
-                        uint32_t h = 0;
-                        int4 c = make_int4(0, 0, 0, 0);
-                        if (i4 * 4 < n) {
-                            c = sc[i4];
-                            const uint32_t w0 = s_bm[(uint32_t)c.x >> 5], w1 = s_bm[(uint32_t)c.y >> 5];
-                            const uint32_t w2 = s_bm[(uint32_t)c.z >> 5], w3 = s_bm[(uint32_t)c.w >> 5];
-                            h = ((w0 >> (c.x & 31)) & 1u) | (((w1 >> (c.y & 31)) & 1u) << 1) |
-                                (((w2 >> (c.z & 31)) & 1u) << 2) | (((w3 >> (c.w & 31)) & 1u) << 3);
-                        }
-                        if (__any_sync(0xffffffffu, h != 0u)) {
-                            if (cnt > LIST_CAP - 128) fold();
-                            const int k = __popc(h);
-                            const uint32_t b0 = __ballot_sync(0xffffffffu, k & 1), b1 = __ballot_sync(0xffffffffu, k & 2),
-                                           b2 = __ballot_sync(0xffffffffu, k & 4);
-                            const uint32_t lt = (1u << lane) - 1u;
-                            int pos = cnt + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-                            const uint32_t offb = (uint32_t)(ci * CH + i4 * 4) << 8;
-                            if (h & 1u) s_list[pos++] = offb | __ldg(code_b + c.x);
-                            if (h & 2u) s_list[pos++] = (offb + (1u << 8)) | __ldg(code_b + c.y);
-                            if (h & 4u) s_list[pos++] = (offb + (2u << 8)) | __ldg(code_b + c.z);
-                            if (h & 8u) s_list[pos++] = (offb + (3u << 8)) | __ldg(code_b + c.w);
-                            cnt += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-                            __syncwarp();
-                        }
-                    }
-                    __syncwarp();                                        // slot may be refilled two chunks later
-                    if (cnt > 0 && (ci == nch - 1 || cnt > LIST_CAP - 128)) fold();
                 }
+                __syncwarp();                                        // slot and mask are reused by later chunks
             }
-
             if (MODE == MODE_GATHER) {
-                const bool nz = (lam != 0.0) || (lam1 != 0.0);
-                const uint32_t dw = __ballot_sync(0xffffffffu, nz);
-                if (nz) {
-                    a.lam_part[(size_t)block * a.n_rows_pad + row] = lam;
-                    if (want_grad) a.lam1_part[(size_t)block * a.n_rows_pad + row] = lam1;
-                }
-                if (lane == 0) a.dirty[(size_t)block * ntasks + task] = dw;
-                continue;
+                flush_row();
+                reinterpret_cast<uint8_t*>(a.dirty + (size_t)block * ntasks32)[(size_t)task * 32 + lane] = (uint8_t)dbits;
             }
+        } else if (MODE == MODE_GATHER) {
+            reinterpret_cast<uint8_t*>(a.dirty + (size_t)block * ntasks32)[(size_t)task * 32 + lane] = 0;
+        }
+        if (MODE == MODE_GATHER) continue;
 
-            // ================================================================== update (lane <-> row)
-            uint32_t exp_w = 0, inf_w = 0;
-            float stage = 0.f;
-            bool stage_known = false;
-            if (do_init) {
-                stage = valid ? a.stage[row] : 3.0f;
-                stage_known = true;
-                sus_w = __ballot_sync(0xffffffffu, stage == 0.0f);
-                exp_w = __ballot_sync(0xffffffffu, stage == 1.0f);
-                inf_w = __ballot_sync(0xffffffffu, stage == 2.0f);
-            } else {
-                if (!has_gather) sus_w = a.sus_bitmap[task];
-                exp_w = a.exp_bitmap[task];
-                inf_w = a.inf_bitmap[task];
-            }
-            bool is_s = (sus_w >> lane) & 1u, is_e = (exp_w >> lane) & 1u, is_i = (inf_w >> lane) & 1u;
-            if (MODE == MODE_UPDATE && do_trans && a.dirty != nullptr && sus_w != 0u) {
-                // fold the per-block partial lambdas in block order
-                for (int b0 = 0; b0 < a.n_blocks; b0 += 32) {
-                    uint32_t dwl = 0;
-                    if (b0 + lane < a.n_blocks) dwl = a.dirty[(size_t)(b0 + lane) * ntasks + task];
-                    uint32_t any_b = __ballot_sync(0xffffffffu, dwl != 0u);
-                    while (any_b) {
-                        const int bl = __ffs(any_b) - 1;
-                        any_b &= any_b - 1;
-                        const uint32_t dw = __shfl_sync(0xffffffffu, dwl, bl);
-                        if ((dw >> lane) & 1u) {
-                            lam += a.lam_part[(size_t)(b0 + bl) * a.n_rows_pad + row];
-                            if (want_grad) lam1 += a.lam1_part[(size_t)(b0 + bl) * a.n_rows_pad + row];
-                        }
+        // ================================================================== update (lane <-> row)
+        const int64_t row = (int64_t)task * 32 + lane;
+        const bool valid = row < a.n_rows;
+        uint32_t sus_w = mt.sus, exp_w = mt.exp, inf_w = mt.inf;
+        float stage = 0.f;
+        bool stage_known = false;
+        if (do_init) {
+            stage = valid ? a.stage[row] : 3.0f;
+            stage_known = true;
+            sus_w = __ballot_sync(0xffffffffu, stage == 0.0f);
+            exp_w = __ballot_sync(0xffffffffu, stage == 1.0f);
+            inf_w = __ballot_sync(0xffffffffu, stage == 2.0f);
+        }
+        if (MODE == MODE_UPDATE && do_trans && a.dirty != nullptr && sus_w != 0u) {
+            // fold the per-block partial lambdas in block order
+            for (int b0 = 0; b0 < a.n_blocks; b0 += 32) {
+                uint32_t dwl = 0;
+                if (b0 + lane < a.n_blocks) dwl = a.dirty[(size_t)(b0 + lane) * ntasks32 + task];
+                uint32_t any_b = __ballot_sync(0xffffffffu, dwl != 0u);
+                while (any_b) {
+                    const int bl = __ffs(any_b) - 1;
+                    any_b &= any_b - 1;
+                    const uint32_t dw = __shfl_sync(0xffffffffu, dwl, bl);
+                    if ((dw >> lane) & 1u) {
+                        lam += a.lam_part[(size_t)(b0 + bl) * a.n_rows_pad + row];
+                        if (want_grad) lam1 += a.lam1_part[(size_t)(b0 + bl) * a.n_rows_pad + row];
                     }
                 }
             }
-
-            float dne = 0.f;
-            int nst = 0, itime = 0;
-            bool nst_known = false, itime_known = false;
-            if (do_trans && is_s && (lam > 0.0 || lam1 > 0.0)) {
-                float wiso = 0.f, u = 0.f;
-                if (a.iso_mode == AT_ISO_TENSOR) wiso = a.isolation[row];
-                if (a.u_mode == AT_U_TENSOR) u = a.uniform[row];
-                if (a.iso_mode != AT_ISO_TENSOR || a.u_mode != AT_U_TENSOR) {
-                    const uint64_t z = at_noise_u64(seed, (uint32_t)t, (uint64_t)(a.row_offset + row));
-                    if (a.u_mode != AT_U_TENSOR) u = at_u_exposure(z);
-                    if (a.iso_mode == AT_ISO_HASH_SOFT) wiso = at_u_isolation(z);
-                    else if (a.iso_mode == AT_ISO_HASH_HARD) wiso = at_u_isolation(z) < a.p_isolate ? 1.0f : 0.0f;
-                }
-                // p = 1 - exp(-lambda) (transition.py:220-221); u < p decided in float32 when it is far from the
-                // threshold (|error of p32| < 4e-7), in float64 otherwise: same decisions as the float64 reference
-                const float q32 = expf(-(float)lam);
-                const float p32 = 1.0f - q32;
-                bool hit;
-                if (fabsf(u - p32) > 1e-6f) hit = u < p32;
-                else hit = (double)u < 1.0 - exp(-lam);
-                const float omw = 1.0f - wiso;                  // float32, as (1.0 - will_isolate)
-                const float ne = hit ? omw : 0.0f;
-                if (want_grad) { dne = omw * q32 * (float)lam1; acc_dne += __double2ll_rn((double)dne * FX_SCALE); }
-                if (ne != 0.0f) {
-                    stage = ne; stage_known = true;            // 0 + ne
-                    a.stage[row] = stage;
-                    nst = t + 1 + m.e2i; nst_known = true;
-                    itime = t; itime_known = true;
-                    store_timer<TimerT>(a.next_stage_time, row, nst);
-                    store_timer<TimerT>(a.infected_time, row, itime);
-                    acc_ne += __double2ll_rn((double)ne * FX_SCALE);
-                    is_s = false;
-                    is_e = (stage == 1.0f);
-                }
-            }
-            if (do_prog && (is_e || is_i)) {
-                if (!nst_known) { nst = load_timer<TimerT>(a.next_stage_time, row); nst_known = true; }
-                if (nst <= t) {
-                    if (is_i) {
-                        acc_dead += 1;                         // stage * rd / INFECTED_VAR = 2/2
-                        if (a.recovered_step) a.recovered_step[row] = (uint8_t)t;
-                    }
-                    if (nst == t) store_timer<TimerT>(a.next_stage_time, row, is_i ? m.inf_time : t + m.i2r);
-                    stage = is_i ? 3.0f : 2.0f;
-                    stage_known = true;
-                    a.stage[row] = stage;
-                    const bool was_e = is_e;
-                    is_e = false;
-                    is_i = was_e;
-                }
-            }
-            if (want_grad && valid && do_trans) a.dne_dr[row] = dne;
-
-            uint32_t code = 0;
+        }
+        bool is_s = (sus_w >> lane) & 1u, is_e = (exp_w >> lane) & 1u, is_i = (inf_w >> lane) & 1u;
+        const bool exposed_candidate = do_trans && is_s && (lam > 0.0 || lam1 > 0.0);
+        // nothing to do for this task: no exposure candidate, nobody in E or I
+        if (!do_init && (exp_w | inf_w) == 0u && !__any_sync(0xffffffffu, exposed_candidate)) {
+            if (want_grad && do_trans && valid) a.dne_dr[row] = 0.f;
             if (do_enc) {
-                // infectious = 0 < stage < 3; fractional stages (soft isolation, Q4) index SFInfector[0]
-                const bool frac = stage_known && stage > 0.0f && stage < 3.0f && !(is_e || is_i);
-                if (is_e || is_i || frac) {
-                    if (!itime_known) itime = load_timer<TimerT>(a.infected_time, row);
-                    const int sidx = is_e ? 1 : (is_i ? 2 : (int)stage);
-                    int idx = a.t_encode - itime - 1;
-                    if (idx < 0 || idx >= m.n_lg) {
-                        if (a.error_flag && sidx < m.n_sfi && m.sfi[sidx] != 0.f) *a.error_flag = 1;
-                        idx = idx < 0 ? 0 : m.n_lg - 1;
-                    }
-                    code = 1u + (uint32_t)(sidx * m.n_lg + idx);
-                    if (s_A[code] == 0.f || s_G[code] == 0.f) code = 0;   // contributes exactly 0 to every lambda
+                if (valid) a.code_out[a.row_offset + row] = 0;
+                if (lane == 0) a.hot_bitmap_out[(a.row_offset >> 5) + task] = 0u;
+            }
+            continue;
+        }
+
+        float dne = 0.f;
+        int nst = 0, itime = 0;
+        bool nst_known = false, itime_known = false;
+        if (exposed_candidate) {
+            float wiso = 0.f, u = 0.f;
+            if (a.iso_mode == AT_ISO_TENSOR) wiso = a.isolation[row];
+            if (a.u_mode == AT_U_TENSOR) u = a.uniform[row];
+            if (a.iso_mode != AT_ISO_TENSOR || a.u_mode != AT_U_TENSOR) {
+                const uint64_t z = at_noise_u64(seed, (uint32_t)t, (uint64_t)(a.row_offset + row));
+                if (a.u_mode != AT_U_TENSOR) u = at_u_exposure(z);
+                if (a.iso_mode == AT_ISO_HASH_SOFT) wiso = at_u_isolation(z);
+                else if (a.iso_mode == AT_ISO_HASH_HARD) wiso = at_u_isolation(z) < a.p_isolate ? 1.0f : 0.0f;
+            }
+            // p = 1 - exp(-lambda) (transition.py:220-221); u < p decided in float32 when it is far from the
+            // threshold (|error of p32| < 4e-7), in float64 otherwise: same decisions as the float64 reference
+            const float q32 = expf(-(float)lam);
+            const float p32 = 1.0f - q32;
+            bool hit;
+            if (fabsf(u - p32) > 1e-6f) hit = u < p32;
+            else hit = (double)u < 1.0 - exp(-lam);
+            const float omw = 1.0f - wiso;                  // float32, as (1.0 - will_isolate)
+            const float ne = hit ? omw : 0.0f;
+            if (want_grad) { dne = omw * q32 * (float)lam1; acc_dne += __double2ll_rn((double)dne * FX_SCALE); }
+            if (ne != 0.0f) {
+                stage = ne; stage_known = true;            // 0 + ne
+                a.stage[row] = stage;
+                nst = t + 1 + m.e2i; nst_known = true;
+                itime = t; itime_known = true;
+                store_timer(a.next_stage_time, row, nst, timer_f32);
+                store_timer(a.infected_time, row, itime, timer_f32);
+                acc_ne += __double2ll_rn((double)ne * FX_SCALE);
+                is_s = false;
+                is_e = (stage == 1.0f);
+            }
+        }
+        if (do_prog && (is_e || is_i)) {
+            if (!nst_known) { nst = load_timer(a.next_stage_time, row, timer_f32); nst_known = true; }
+            if (nst <= t) {
+                if (is_i) {
+                    acc_dead += 1;                         // stage * rd / INFECTED_VAR = 2/2
+                    if (a.recovered_step) a.recovered_step[row] = (uint8_t)t;
                 }
-                const uint32_t hot = __ballot_sync(0xffffffffu, code != 0u);
-                if (valid) a.code_out[a.row_offset + row] = (uint8_t)code;
-                if (lane == 0) a.hot_bitmap_out[(a.row_offset >> 5) + task] = hot;
+                if (nst == t) store_timer(a.next_stage_time, row, is_i ? m.inf_time : t + m.i2r, timer_f32);
+                stage = is_i ? 3.0f : 2.0f;
+                stage_known = true;
+                a.stage[row] = stage;
+                const bool was_e = is_e;
+                is_e = false;
+                is_i = was_e;
             }
-            const uint32_t sus_o = __ballot_sync(0xffffffffu, is_s);
-            const uint32_t exp_o = __ballot_sync(0xffffffffu, is_e);
-            const uint32_t inf_o = __ballot_sync(0xffffffffu, is_i);
-            if (lane == 0) {
-                if (do_init || sus_o != sus_w) a.sus_bitmap[task] = sus_o;
-                if (do_init || exp_o != exp_w) a.exp_bitmap[task] = exp_o;
-                if (do_init || inf_o != inf_w) a.inf_bitmap[task] = inf_o;
+        }
+        if (want_grad && valid && do_trans) a.dne_dr[row] = dne;
+
+        if (do_enc) {
+            uint32_t code = 0;
+            // infectious = 0 < stage < 3; fractional stages (soft isolation, Q4) index SFInfector[0]
+            const bool frac = stage_known && stage > 0.0f && stage < 3.0f && !(is_e || is_i);
+            if (is_e || is_i || frac) {
+                if (!itime_known) itime = load_timer(a.infected_time, row, timer_f32);
+                const int sidx = is_e ? 1 : (is_i ? 2 : (int)stage);
+                int idx = a.t_encode - itime - 1;
+                if (idx < 0 || idx >= m.n_lg) {
+                    if (a.error_flag && sidx < m.n_sfi && m.sfi[sidx] != 0.f) *a.error_flag = 1;
+                    idx = idx < 0 ? 0 : m.n_lg - 1;
+                }
+                code = 1u + (uint32_t)(sidx * m.n_lg + idx);
+                if (s_A[code] == 0.f || s_G[code] == 0.f) code = 0;   // contributes exactly 0 to every lambda
             }
+            const uint32_t hot = __ballot_sync(0xffffffffu, code != 0u);
+            if (valid) a.code_out[a.row_offset + row] = (uint8_t)code;
+            if (lane == 0) a.hot_bitmap_out[(a.row_offset >> 5) + task] = hot;
+        }
+        const uint32_t sus_o = __ballot_sync(0xffffffffu, is_s);
+        const uint32_t exp_o = __ballot_sync(0xffffffffu, is_e);
+        const uint32_t inf_o = __ballot_sync(0xffffffffu, is_i);
+        if (lane == 0) {
+            if (do_init || sus_o != sus_w) a.sus_bitmap[task] = sus_o;
+            if (do_init || exp_o != exp_w) a.exp_bitmap[task] = exp_o;
+            if (do_init || inf_o != inf_w) a.inf_bitmap[task] = inf_o;
         }
     }
 
@@ -473,7 +544,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     if (tid == 0) {
         if (MODE != MODE_GATHER) {
             long long s0 = 0, s1 = 0, s2 = 0;
-            for (int w = 0; w < NW; ++w) { s0 += s_red[w][0]; s1 += s_red[w][1]; s2 += s_red[w][2]; }
+            for (int w = 0; w < nw; ++w) { s0 += s_red[w][0]; s1 += s_red[w][1]; s2 += s_red[w][2]; }
             if (s0) atomicAdd(&acc[0], (unsigned long long)s0);
             if (s1) atomicAdd(&acc[1], (unsigned long long)s1);
             if (s2) atomicAdd(&acc[2], (unsigned long long)s2);
@@ -484,9 +555,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     __syncthreads();
     if (s_is_last && tid == 0) {
         __threadfence();
-        if (MODE == MODE_GATHER) {
-            for (int b = 0; b < a.n_blocks; ++b) reinterpret_cast<int*>(ws + WS_GCOUNTERS)[b] = 0;
-        } else {
+        if (MODE != MODE_GATHER) {
             const volatile long long* av = reinterpret_cast<const volatile long long*>(acc);
             const double s0 = (double)av[0] / FX_SCALE, s1 = (double)av[1] / FX_SCALE, s2 = (double)av[2];
             if (do_trans) {
@@ -498,7 +567,6 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
                 if (a.daily_deaths) a.daily_deaths[t] += (float)s2 * a.m_value[0];   // progression :52-60
             }
             acc[0] = 0; acc[1] = 0; acc[2] = 0;
-            *reinterpret_cast<int*>(ws + WS_COUNTER) = 0;
         }
         *ticket = 0;
     }
@@ -602,34 +670,27 @@ static int device_props() {
 }
 
 static int code_count(int n_lg) { return ((1 + 3 * n_lg) + 7) & ~7; }
-static size_t fixed_smem(int n_sfs, int n_lg) {
-    return (size_t)NW * WARP_SMEM + (size_t)2 * n_sfs * code_count(n_lg) * 8 + 2 * 256 * 4;
-}
+static size_t table_smem(int n_sfs, int n_lg) { return (size_t)2 * n_sfs * code_count(n_lg) * 8 + 2 * 256 * 4; }
 
-template <int MODE, bool WEIGHTED, typename TimerT, typename AgeT>
-static int launch_kernel(const KModel& km, const at_seirm_launch& a, int grid, size_t smem, int bm_words, int NC, int G, cudaStream_t s) {
-    auto k = seirm_kernel<MODE, WEIGHTED, TimerT, AgeT>;
+template <int MODE, int RL4>
+static int launch_kernel(const KModel& km, const at_seirm_launch& a, int grid, int threads, size_t smem, int bm_words, int NC, int G, cudaStream_t s) {
+    auto k = seirm_kernel<MODE, RL4>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    k<<<grid, NT, smem, s>>>(km, a, bm_words, NC, G);
+    k<<<grid, threads, smem, s>>>(km, a, bm_words, NC, G);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail("seirm_kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }
 
-template <int MODE, bool WEIGHTED>
-static int dispatch_types(const KModel& km, const at_seirm_launch& a, int grid, size_t smem, int words, int NC, int G, cudaStream_t s) {
-    if (a.timer_dtype == AT_TIMER_F32 && a.age_dtype == AT_AGE_F32) return launch_kernel<MODE, WEIGHTED, float, float>(km, a, grid, smem, words, NC, G, s);
-    if (a.timer_dtype == AT_TIMER_F32 && a.age_dtype == AT_AGE_U8) return launch_kernel<MODE, WEIGHTED, float, uint8_t>(km, a, grid, smem, words, NC, G, s);
-    if (a.timer_dtype == AT_TIMER_I16 && a.age_dtype == AT_AGE_F32) return launch_kernel<MODE, WEIGHTED, int16_t, float>(km, a, grid, smem, words, NC, G, s);
-    if (a.timer_dtype == AT_TIMER_I16 && a.age_dtype == AT_AGE_U8) return launch_kernel<MODE, WEIGHTED, int16_t, uint8_t>(km, a, grid, smem, words, NC, G, s);
-    return fail("%s", "unsupported timer_dtype / age_dtype");
-}
-
 template <int MODE>
-static int dispatch(const KModel& km, const at_seirm_launch& a, int grid, size_t smem, int words, int NC, int G, cudaStream_t s) {
-    if (a.edge_weight != nullptr) return dispatch_types<MODE, true>(km, a, grid, smem, words, NC, G, s);
-    return dispatch_types<MODE, false>(km, a, grid, smem, words, NC, G, s);
+static int dispatch(const KModel& km, const at_seirm_launch& a, int grid, int threads, size_t smem, int words, int NC, int G, cudaStream_t s) {
+    switch (a.edges_per_chunk) {
+        case 512: return launch_kernel<MODE, 4>(km, a, grid, threads, smem, words, NC, G, s);
+        case 768: return launch_kernel<MODE, 6>(km, a, grid, threads, smem, words, NC, G, s);
+        case 1024: return launch_kernel<MODE, 8>(km, a, grid, threads, smem, words, NC, G, s);
+    }
+    return fail("%s", "edges_per_chunk must be 512, 768 or 1024");
 }
 
 extern "C" {
@@ -640,10 +701,10 @@ int64_t at_seirm_sizeof_model(void) { return (int64_t)sizeof(at_seirm_model); }
 const char* at_last_error(void) { return g_err; }
 int64_t at_seirm_workspace_bytes(void) { return (int64_t)WS_BYTES; }
 
-int64_t at_seirm_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t want_grad) {
-    (void)want_grad;
+int64_t at_seirm_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edges_per_chunk, int32_t warps) {
     if (device_props()) return 0;
-    int64_t bytes = (int64_t)g_smem_optin - (int64_t)fixed_smem(n_sfs, n_lam_gamma) - 2048;   // static __shared__ + slack
+    if (warps < 1) warps = 16;
+    int64_t bytes = (int64_t)g_smem_optin - (int64_t)table_smem(n_sfs, n_lam_gamma) - (int64_t)warps * warp_smem_bytes(edges_per_chunk) - 2048;
     if (bytes < 4096) return 0;
     return ((bytes * 8) / 1024) * 1024;
 }
@@ -654,13 +715,16 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     if (a.abi_version != AT_SEIRM_ABI_VERSION) return fail("%s", "at_seirm_launch.abi_version mismatch");
     if (model->n_lam_gamma < 1 || model->n_lam_gamma > AT_MAX_LAMGAMMA) return fail("%s", "n_lam_gamma out of range (1..84)");
     if (model->n_sfs < 1 || model->n_sfs > AT_MAX_SFS || model->n_sfi < 1 || model->n_sfi > AT_MAX_SFI) return fail("%s", "table size out of range");
-    if (a.n_rows < 0 || (a.row_offset & 31) != 0 || (a.n_rows_pad & 31) != 0 || a.n_rows_pad < a.n_rows) return fail("%s", "bad n_rows / n_rows_pad / row_offset");
+    if (a.n_rows < 0 || (a.row_offset & 31) != 0 || (a.n_rows_pad & 255) != 0 || a.n_rows_pad < a.n_rows) return fail("%s", "bad n_rows / n_rows_pad / row_offset");
     if (!a.stage || !a.workspace || !a.sus_bitmap || !a.exp_bitmap || !a.inf_bitmap) return fail("%s", "stage / workspace / row bitmaps must not be null");
     const bool do_trans = a.flags & AT_DO_TRANSMISSION;
+    const int epc = a.edges_per_chunk > 0 ? a.edges_per_chunk : 768;
+    if (epc != 512 && epc != 768 && epc != 1024) return fail("%s", "edges_per_chunk must be 512, 768 or 1024");
     if (do_trans) {
-        if (!a.deg || !a.seg_base4 || !a.col || !a.code_in || !a.hot_bitmap_in || !a.r_value || !a.age) return fail("%s", "transmission needs the graph, code_in, hot_bitmap_in, age, r_value");
+        if (!a.row_start || !a.seg_info || !a.col || !a.code_in || !a.hot_bitmap_in || !a.r_value || !a.age) return fail("%s", "transmission needs the graph, code_in, hot_bitmap_in, age, r_value");
         if (a.n_blocks < 1 || a.n_blocks > AT_MAX_BLOCKS || a.block_size < 1024 || (a.block_size & 1023)) return fail("%s", "bad n_blocks / block_size");
         if ((int64_t)a.n_blocks * a.block_size < a.n_sources) return fail("%s", "n_blocks * block_size does not cover n_sources");
+        if (a.rows_per_task != (a.n_blocks > 1 ? 256 : 32)) return fail("%s", "rows_per_task must be 32 (one block) or 256 (several blocks)");
         if (a.iso_mode == AT_ISO_TENSOR && !a.isolation) return fail("%s", "iso_mode TENSOR without isolation pointer");
         if (a.u_mode == AT_U_TENSOR && !a.uniform) return fail("%s", "u_mode TENSOR without uniform pointer");
         if (a.n_blocks > 1 && (!a.lam_part || !a.dirty || (a.dne_dr && !a.lam1_part))) return fail("%s", "n_blocks > 1 needs lam_part / lam1_part / dirty");
@@ -679,32 +743,49 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     memcpy(km.sfs, model->sfs, sizeof(km.sfs)); memcpy(km.sfi, model->sfi, sizeof(km.sfi)); memcpy(km.lg, model->lam_gamma, sizeof(km.lg));
 
     const int NC = code_count(model->n_lam_gamma);
-    const size_t fixed = fixed_smem(model->n_sfs, model->n_lam_gamma);
+    const size_t tables = table_smem(model->n_sfs, model->n_lam_gamma);
+    at_seirm_launch al = a;
+    al.edges_per_chunk = epc;
+    int warps = a.warps_per_cta > 0 ? a.warps_per_cta : 16;
+    if (warps > NT_MAX / 32) warps = NT_MAX / 32;
     int bm_words = 0;
     if (do_trans) {
-        if (a.block_size > at_seirm_max_block_size(model->n_sfs, model->n_lam_gamma, a.dne_dr != nullptr)) return fail("%s", "block_size exceeds the shared-memory bitmap capacity (at_seirm_max_block_size)");
+        while (warps > 4 && a.block_size > at_seirm_max_block_size(model->n_sfs, model->n_lam_gamma, epc, warps)) --warps;
+        if (a.block_size > at_seirm_max_block_size(model->n_sfs, model->n_lam_gamma, epc, warps)) return fail("%s", "block_size exceeds the shared-memory bitmap capacity (at_seirm_max_block_size)");
         bm_words = a.block_size / 32;
     }
-    const int64_t ntasks = a.n_rows_pad / 32;
-    int G = a.tasks_per_group > 0 ? a.tasks_per_group : (ntasks >= 131072 ? 8 : 4);
-    if (G > MAXG) G = MAXG;
-    const int64_t ngroups = (ntasks + G - 1) / G;
+    const size_t smem_gather = (size_t)warps * warp_smem_bytes(epc) + tables + (size_t)bm_words * 4;
+    const size_t smem_update = (size_t)16 * warp_smem_bytes(512) + tables;
+    const int64_t ntasks32 = a.n_rows_pad / 32;
     int grid = a.grid > 0 ? a.grid : g_sm_count;
     if (grid > 1024) grid = 1024;
     cudaStream_t s = (cudaStream_t)stream;
     if (do_trans && a.n_blocks > 1) {
+        const int Gg = a.tasks_per_group > 0 ? (a.tasks_per_group > MAXG ? MAXG : a.tasks_per_group) : 1;
         int ggrid = grid < a.n_blocks ? a.n_blocks : grid;
-        int rc = dispatch<MODE_GATHER>(km, a, ggrid, fixed + (size_t)bm_words * 4, bm_words, NC, G, s);
+        int rc = dispatch<MODE_GATHER>(km, al, ggrid, warps * 32, smem_gather, bm_words, NC, Gg, s);
         if (rc) return rc;
-        int64_t useful = (ngroups + NW - 1) / NW;
+        const int Gu = 8;
+        const int64_t ngroups = (ntasks32 + Gu - 1) / Gu;
+        int64_t useful = (ngroups + 15) / 16;
         int ugrid = grid > useful ? (int)useful : grid;
-        return dispatch<MODE_UPDATE>(km, a, ugrid < 1 ? 1 : ugrid, fixed, 0, NC, G, s);
+        al.edges_per_chunk = 512;
+        return launch_kernel<MODE_UPDATE, 4>(km, al, ugrid < 1 ? 1 : ugrid, 512, smem_update, 0, NC, Gu, s);
     }
-    int64_t useful = (ngroups + NW - 1) / NW;
+    int G = a.tasks_per_group > 0 ? a.tasks_per_group : (do_trans ? (ntasks32 >= 131072 ? 8 : 4) : 8);
+    if (G > MAXG) G = MAXG;
+    const int64_t ngroups = (ntasks32 + G - 1) / G;
+    if (do_trans) {
+        int64_t useful = (ngroups + warps - 1) / warps;
+        if (grid > useful) grid = (int)useful;
+        if (grid < 1) grid = 1;
+        return dispatch<MODE_FUSED>(km, al, grid, warps * 32, smem_gather, bm_words, NC, G, s);
+    }
+    int64_t useful = (ngroups + 15) / 16;
     if (grid > useful) grid = (int)useful;
     if (grid < 1) grid = 1;
-    if (do_trans) return dispatch<MODE_FUSED>(km, a, grid, fixed + (size_t)bm_words * 4, bm_words, NC, G, s);
-    return dispatch<MODE_UPDATE>(km, a, grid, fixed, 0, NC, G, s);
+    al.edges_per_chunk = 512;
+    return launch_kernel<MODE_UPDATE, 4>(km, al, grid, 512, smem_update, 0, NC, G, s);
 }
 
 int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, const float* dne_dr, const uint8_t* recovered_step,

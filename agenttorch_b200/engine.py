@@ -141,11 +141,11 @@ def _ptr(t, dtype=None, name="tensor"):
 
 class SeirmEngine:
     def __init__(self, graph, spec: SeirmSpec, process_group=None, grid=0, code_len=None, block_size=None,
-                 tasks_per_group=0):
+                 tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0):
         """graph: ContactGraph (plain CSR, re-blocked here) or a prebuilt BlockedGraph.  block_size: sources
         per column block (default: the largest that fits the shared-memory bitmap, i.e. as few blocks as
         possible); code_len: length of the code/bitmap arrays (multi-GPU: world_size equal slices)."""
-        from .graph import BlockedGraph, block_graph, choose_block_size
+        from .graph import BlockedGraph, block_graph, choose_block_size, choose_edges_per_chunk
 
         if not graph.device.type == "cuda":
             raise RuntimeError("SeirmEngine needs the contact graph on a CUDA device; there is no CPU fallback")
@@ -158,19 +158,28 @@ class SeirmEngine:
         self.pg = process_group
         self.grid = grid
         self.tasks_per_group = tasks_per_group
+        self.warps_per_cta = warps_per_cta
         n_src = graph.n_sources if code_len is None else int(code_len)
         if code_len is not None and (code_len < graph.n_sources or code_len % 1024):
             raise ValueError("code_len must cover all sources and be a multiple of 1024")
-        with torch.cuda.device(self.device):
-            cap = int(self.lib.at_seirm_max_block_size(len(spec.sfs), len(spec.lam_gamma), 1))
+        def capacity(epc, warps):
+            with torch.cuda.device(self.device):
+                return int(self.lib.at_seirm_max_block_size(len(spec.sfs), len(spec.lam_gamma), int(epc), int(warps)))
+
         if isinstance(graph, BlockedGraph):
             self.graph = graph
         else:
+            # one column block if the whole bitmap fits next to >= 12 warps of TMA buffers, else equal blocks
+            # sized for 16 warps
+            epc = edges_per_chunk or choose_edges_per_chunk(graph.num_edges / max(graph.n_rows, 1) * 32)
             if block_size is None:
-                _, block_size = choose_block_size(n_src, cap)
-            self.graph = block_graph(graph, int(block_size))
-        if self.graph.block_size > cap:
-            raise RuntimeError(f"block_size {self.graph.block_size} exceeds the shared-memory bitmap capacity {cap}")
+                if ((n_src + 1023) // 1024) * 1024 <= capacity(epc, 12):
+                    block_size = ((n_src + 1023) // 1024) * 1024
+                else:
+                    _, block_size = choose_block_size(n_src, capacity(epc, 16))
+            self.graph = block_graph(graph, int(block_size), edges_per_chunk=edges_per_chunk)
+        if self.graph.block_size > capacity(self.graph.edges_per_chunk, 4):
+            raise RuntimeError(f"block_size {self.graph.block_size} exceeds the shared-memory bitmap capacity")
         g = self.graph
         self.n_code = max(((n_src + 1023) // 1024) * 1024, g.n_blocks * g.block_size)
         dev = self.device
@@ -206,8 +215,9 @@ class SeirmEngine:
         a.t_encode = int(t + 1 if t_encode is None else t_encode)
         a.n_rows, a.n_rows_pad, a.n_sources, a.row_offset = g.n_rows, g.n_rows_pad, self.n_code, g.row_offset
         a.n_blocks, a.block_size = g.n_blocks, g.block_size
-        a.deg = _ptr(g.deg, torch.int16, "deg")
-        a.seg_base4 = _ptr(g.seg_base4, torch.int32, "seg_base4")
+        a.rows_per_task, a.edges_per_chunk = g.rows_per_task, g.edges_per_chunk
+        a.row_start = _ptr(g.row_start, torch.int16, "row_start")
+        a.seg_info = _ptr(g.seg_info, torch.int32, "seg_info")
         a.col = _ptr(g.col, torch.int32, "col")
         a.edge_weight = _ptr(g.edge_weight, torch.float32, "edge_weight")
         if state.stage.shape[0] != g.n_rows:
@@ -250,6 +260,7 @@ class SeirmEngine:
         a.error_flag = _ptr(self.error_flag, torch.int32)
         a.grid = int(self.grid)
         a.tasks_per_group = int(self.tasks_per_group)
+        a.warps_per_cta = int(self.warps_per_cta)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(self.lib.at_seirm_step(ctypes.byref(self.model), ctypes.byref(a), ctypes.c_void_p(stream)))
         self.launch_count += 2 if (g.n_blocks > 1 and (flags & nat.DO_TRANSMISSION)) else 1

@@ -216,26 +216,30 @@ def shard_graph(graph, row_begin, row_end):
 
 
 # --------------------------------------------------------------------------------------- BCSR
-TAIL_PAD = 1024          # ints of padding after the last segment (TMA chunks may read past a segment's end)
+TAIL_PAD = 2048          # ints of padding after the last segment (TMA chunks may read past a segment's end)
 
 
 @dataclass
 class BlockedGraph:
     """Column-blocked, destination-sorted CSR — the layout the sm_100a kernels stream (include/at_seirm.h).
 
-    Rows are grouped in tasks of 32; sources are split in `n_blocks` ranges of `block_size` ids so that one
-    block's "hot" bitmap fits in shared memory.  Segment s = block*n_tasks + task stores the edges of the
-    task's rows whose source is in the block, row by row, each row in original edge order, 16-byte aligned."""
+    Rows are grouped in gather tasks of `rows_per_task` rows (32 with one column block, 256 with several);
+    sources are split in `n_blocks` ranges of `block_size` ids so that one block's "hot" bitmap fits in shared
+    memory.  Segment s = block*n_gtasks + gtask stores the edges of the task's rows whose source is in the
+    block, row by row, each row in original edge order, 16-byte aligned.  `col` holds block-local source ids
+    encoded as ((c >> 5) << 7) | (c & 31)."""
     n_rows: int
     n_rows_pad: int
     n_sources: int
     row_offset: int
     n_blocks: int
     block_size: int
-    deg: torch.Tensor            # (n_blocks, n_rows_pad) int16 holding uint16 counts
-    seg_base4: torch.Tensor      # (n_blocks*n_tasks + 1,) int32, units of 4 edges
-    col: torch.Tensor            # (padded edges + TAIL_PAD,) int32 block-local source ids
+    rows_per_task: int
+    row_start: torch.Tensor      # (n_blocks, n_rows_pad) int16 holding uint16 offsets inside the segment
+    seg_info: torch.Tensor       # (n_blocks*n_gtasks, 2) int32: (first entry / 4, edges)
+    col: torch.Tensor            # (padded edges + TAIL_PAD,) int32
     num_edges: int
+    edges_per_chunk: int = 768
     edge_weight: Optional[torch.Tensor] = None
     i_bar: float = 1.0
     i_bar_agent: int = -1
@@ -246,6 +250,7 @@ class BlockedGraph:
 
     @property
     def n_tasks(self):
+        """32-row tasks (= words of the row bitmaps)"""
         return self.n_rows_pad // 32
 
     def avg_degree(self):
@@ -253,7 +258,8 @@ class BlockedGraph:
 
     def to(self, device):
         return BlockedGraph(self.n_rows, self.n_rows_pad, self.n_sources, self.row_offset, self.n_blocks, self.block_size,
-                            self.deg.to(device), self.seg_base4.to(device), self.col.to(device), self.num_edges,
+                            self.rows_per_task, self.row_start.to(device), self.seg_info.to(device), self.col.to(device),
+                            self.num_edges, self.edges_per_chunk,
                             None if self.edge_weight is None else self.edge_weight.to(device), self.i_bar, self.i_bar_agent)
 
 
@@ -267,12 +273,24 @@ def choose_block_size(n_sources, max_block_size):
     return n_blocks, block
 
 
-def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = None) -> BlockedGraph:
+def choose_edges_per_chunk(avg_edges_per_task):
+    """TMA chunk capacity: the smallest of 512/768/1024 edges that holds a typical gather task in one chunk."""
+    for cap in (512, 768, 1024):
+        if avg_edges_per_task * 1.12 + 16 <= cap:
+            return cap
+    return 1024
+
+
+def _to_i16(x):
+    x = x.to(torch.int32) & 0xFFFF
+    return torch.where(x >= 32768, x - 65536, x).to(torch.int16).contiguous()
+
+
+def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = None, edges_per_chunk: Optional[int] = None) -> BlockedGraph:
     """ContactGraph (plain dst-sorted CSR, global source ids) -> BlockedGraph, on the graph's device."""
     dev = graph.device
     n_rows, e = graph.n_rows, graph.num_edges
-    n_rows_pad = -(-max(n_rows, 1) // 32) * 32
-    n_tasks = n_rows_pad // 32
+    n_rows_pad = -(-max(n_rows, 1) // 256) * 256
     if block_size % 1024:
         raise ValueError("block_size must be a multiple of 1024")
     nb = max(1, -(-graph.n_sources // block_size)) if n_blocks is None else n_blocks
@@ -280,13 +298,16 @@ def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = 
         raise ValueError("blocks do not cover the source id space")
     if nb > 64:
         raise ValueError("more than 64 column blocks: shard the graph over more GPUs")
+    rpt = 32 if nb == 1 else 256
+    shift = 5 if nb == 1 else 8
+    n_gt = n_rows_pad // rpt
     row_ptr = graph.row_ptr.long()
     degf = row_ptr[1:] - row_ptr[:-1]
     col = graph.col_idx[:e].long()
     rows = torch.repeat_interleave(torch.arange(n_rows, device=dev), degf)
+    order = None
     if nb == 1:
         key = rows
-        order = None
     else:
         blk = torch.div(col, block_size, rounding_mode="floor")
         key = blk * n_rows_pad + rows
@@ -295,12 +316,15 @@ def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = 
         col = col[order] - blk[order] * block_size
         del blk
     del rows
-    n_seg = nb * n_tasks
+    n_seg = nb * n_gt
     deg2 = torch.bincount(key, minlength=nb * n_rows_pad)
-    if e and int(deg2.max()) > 65535:
-        raise ValueError("a row has more than 65535 in-edges inside one column block")
-    seg = key >> 5
-    seg_len = torch.bincount(seg, minlength=n_seg)
+    seg = key >> shift
+    seg_len = deg2.reshape(n_seg, rpt).sum(1)
+    if e and int(seg_len.max()) > 65535:
+        raise ValueError("a gather task has more than 65535 edges inside one column block (hub rows are not supported)")
+    # offset of each row inside its segment (exclusive prefix of the degrees within the task)
+    d3 = deg2.reshape(n_seg, rpt)
+    row_start = (torch.cumsum(d3, 1) - d3).reshape(nb, n_rows_pad)
     seg_pad = ((seg_len + 3) >> 2) << 2
     seg_base = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
     seg_base[1:] = torch.cumsum(seg_pad, 0)
@@ -310,14 +334,15 @@ def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = 
     if total // 4 >= 2**31:
         raise ValueError("graph shard too large for int32 segment bases")
     pos = torch.arange(e, device=dev) - seg_first[seg] + seg_base[:-1][seg]
+    enc = (((col >> 5) << 7) | (col & 31)).to(torch.int32)
     col_out = torch.zeros(total + TAIL_PAD, dtype=torch.int32, device=dev)
-    col_out[pos] = col.to(torch.int32)
+    col_out[pos] = enc
     w_out = None
     if graph.edge_weight is not None:
         w = graph.edge_weight[:e]
         w_out = torch.ones(total + TAIL_PAD, dtype=torch.float32, device=dev)
         w_out[pos] = w if order is None else w[order]
-    deg16 = (deg2.reshape(nb, n_rows_pad) & 0xFFFF).to(torch.int32)
-    deg16 = torch.where(deg16 >= 32768, deg16 - 65536, deg16).to(torch.int16).contiguous()
-    return BlockedGraph(n_rows, n_rows_pad, graph.n_sources, graph.row_offset, nb, block_size, deg16,
-                        (seg_base >> 2).to(torch.int32).contiguous(), col_out, e, w_out, graph.i_bar, graph.i_bar_agent)
+    seg_info = torch.stack(((seg_base[:-1] >> 2), seg_len), dim=1).to(torch.int32).contiguous()
+    epc = edges_per_chunk or choose_edges_per_chunk(e / max(n_seg, 1))
+    return BlockedGraph(n_rows, n_rows_pad, graph.n_sources, graph.row_offset, nb, block_size, rpt, _to_i16(row_start),
+                        seg_info, col_out, e, epc, w_out, graph.i_bar, graph.i_bar_agent)

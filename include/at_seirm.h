@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AT_SEIRM_ABI_VERSION 4
+#define AT_SEIRM_ABI_VERSION 5
 #define AT_MAX_SFS 16        /* SFSusceptibility entries (config.yaml has 9)                     */
 #define AT_MAX_SFI 8         /* SFInfector entries (config.yaml has 5)                           */
 #define AT_MAX_LAMGAMMA 84   /* lam_gamma_integrals entries; 1 + 3*K infectiousness codes fit a byte */
@@ -73,11 +73,15 @@ typedef struct at_seirm_model {
  *
  * Contact graph = column-blocked, destination-sorted CSR ("BCSR"), replacing the (2,E) COO edge_index that
  * the reference gathers through PyG (utils.py:129-148, transition.py:209-218):
- *   rows (destinations) are grouped in tasks of 32; sources are split in n_blocks ranges of block_size ids;
- *   segment s = block*n_tasks + task holds the edges of the task's 32 rows whose source lies in the block,
- *   row by row, each row in ORIGINAL edge order, starting at col[4*seg_base4[s]] (16-byte aligned);
- *   col holds block-local source ids (src - block*block_size); deg[block][row] is the row's edge count in
- *   the block.  Edges are used as written: directed, duplicates and self-loops kept (Q9).
+ *   destinations (rows) are grouped in gather tasks of rows_per_task rows (32 when n_blocks == 1, 256 otherwise);
+ *   sources are split in n_blocks ranges of block_size ids; segment s = block*n_gtasks + gtask holds the edges of
+ *   the task's rows whose source lies in the block, row by row, each row in ORIGINAL edge order:
+ *     seg_info[2*s]   = first entry / 4 (segments start 16-byte aligned),  seg_info[2*s+1] = number of edges,
+ *     row_start[block][row] = offset of the row's first edge inside its segment (uint16; a row ends where the
+ *     next one starts, the last one at the segment length),
+ *     col[] = block-local source id c encoded as ((c >> 5) << 7) | (c & 31): byte offset of its bitmap word
+ *     times 32, plus its bit — so that the shared-memory bitmap test needs no address arithmetic.
+ *   Edges are used as written: directed, duplicates and self-loops kept (Q9).
  */
 typedef struct at_seirm_launch {
     int32_t abi_version;        /* = AT_SEIRM_ABI_VERSION */
@@ -86,14 +90,15 @@ typedef struct at_seirm_launch {
     int32_t t_encode;           /* step whose infectiousness is encoded (normally t+1) */
     /* graph */
     int64_t n_rows;             /* owned agents */
-    int64_t n_rows_pad;         /* n_rows rounded up to 32 (leading dimension of deg, dirty, lam_part) */
+    int64_t n_rows_pad;         /* n_rows rounded up to 256 (leading dimension of row_start, dirty, lam_part) */
     int64_t n_sources;          /* length of code_in (multiple of 1024) */
     int64_t row_offset;         /* global id of local row 0 (multiple of 32): slice of this rank in
                                    code/hot_bitmap, and the agent id fed to the counter hash */
     int32_t n_blocks, block_size;   /* block_size multiple of 1024 */
-    const uint16_t* deg;        /* [n_blocks][n_rows_pad] */
-    const int32_t* seg_base4;   /* [n_blocks*n_tasks + 1], units of 4 edges */
-    const int32_t* col;         /* segment-padded, + >= 512 ints of tail padding */
+    int32_t rows_per_task, edges_per_chunk;  /* 32 or 256; TMA chunk capacity: 512, 768 or 1024 edges */
+    const uint16_t* row_start;  /* [n_blocks][n_rows_pad] */
+    const int32_t* seg_info;    /* [n_blocks*n_gtasks][2] = (first entry / 4, edges) */
+    const int32_t* col;         /* encoded source ids, segment-padded, + >= 1024 ints of tail padding */
     const float* edge_weight;   /* parallel to col, or NULL when all weights are 1 (utils.py:144) */
     /* agent state, updated in place and only where it changes */
     float* stage;               /* n_rows */
@@ -133,12 +138,14 @@ typedef struct at_seirm_launch {
     /* scratch for n_blocks > 1 (per-block partial lambdas), else NULL */
     double* lam_part;           /* [n_blocks][n_rows_pad] */
     double* lam1_part;          /* [n_blocks][n_rows_pad], needed when dne_dr != NULL */
-    uint32_t* dirty;            /* [n_blocks][n_rows_pad/32] */
+    uint32_t* dirty;            /* [n_blocks][n_rows_pad/32]: which rows of lam_part hold a value this step */
     /* workspace: at_seirm_workspace_bytes() bytes, zeroed once by the caller, reset by every launch */
     void* workspace;
     int32_t* error_flag;        /* or NULL; set non-zero on a lam_gamma index out of range (Q10) */
     int32_t grid;               /* CTAs, 0 = one per SM */
-    int32_t tasks_per_group;    /* scheduling granule (1..8 tasks of 32 rows), 0 = library default */
+    int32_t tasks_per_group;    /* scheduling granule (1..8 gather tasks), 0 = library default */
+    int32_t warps_per_cta;      /* 0 = as many (<= 16) as shared memory allows */
+    int32_t _pad1;
 } at_seirm_launch;
 
 /* ---- queries (host only) ---- */
@@ -148,9 +155,10 @@ const char* at_last_error(void);
 int64_t at_seirm_sizeof_launch(void);
 int64_t at_seirm_sizeof_model(void);
 int64_t at_seirm_workspace_bytes(void);
-/* largest block_size (sources per column block) whose "hot" bitmap the gather stages in shared memory,
-   for a model with n_sfs susceptibility classes and n_lam_gamma integrals (tables share the same smem) */
-int64_t at_seirm_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t want_grad);
+/* largest block_size (sources per column block) whose "hot" bitmap the gather stages in shared memory next to
+   `warps` warps' TMA buffers of `edges_per_chunk` edges, for a model with n_sfs susceptibility classes and
+   n_lam_gamma integrals (the term tables share the same shared memory) */
+int64_t at_seirm_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edges_per_chunk, int32_t warps);
 
 /*
  * at_seirm_step — one step (or part of one, per the flags) of the agent update on `stream`.
