@@ -106,7 +106,8 @@ struct KModel {   // device copy of at_seirm_model (kernel parameter, by value)
     float sfs[AT_MAX_SFS], sfi[AT_MAX_SFI], lg[AT_MAX_LAMGAMMA];
 };
 
-__host__ __device__ constexpr int warp_smem_bytes(int cap) { return 2 * cap * 4 + 128 + 64; }
+// per-warp shared memory: two col chunks, the hit mask and hit codes of the chunk being folded, two mbarriers
+__host__ __device__ constexpr int warp_smem_bytes(int cap) { return 2 * cap * 4 + cap + 128 + 64; }
 
 // -------------------------------------------------------------------------------------- the kernel
 // RL4 = 128-bit loads per lane per chunk: a chunk holds CAP = 128*RL4 edges and lane L owns the RL = 4*RL4
@@ -120,7 +121,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nw = blockDim.x >> 5;
     // [per-warp areas][Tdiv f64 n_sfs*NC][T1div f64 n_sfs*NC][s_A f32 256][s_G f32 256][hot bitmap]
-    double* s_T = reinterpret_cast<double*>(smem_raw + nw * WSM);
+    double* s_T = reinterpret_cast<double*>(smem_raw + (MODE != MODE_UPDATE ? nw * WSM : 0));
     double* s_T1 = s_T + m.n_sfs * NC;
     float* s_A = reinterpret_cast<float*>(s_T1 + m.n_sfs * NC);
     float* s_G = s_A + 256;
@@ -157,8 +158,9 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     __syncthreads();
     unsigned char* wsm = smem_raw + warp * WSM;
     int32_t* s_col = reinterpret_cast<int32_t*>(wsm);
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(wsm + 2 * CAP * 4);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(wsm + 2 * CAP * 4 + 128);
+    uint8_t* s_code = wsm + 2 * CAP * 4;                                              // [CAP] hit codes
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(wsm + 2 * CAP * 4 + CAP);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(wsm + 2 * CAP * 4 + CAP + 128);
     if (HAS_GATHER) {
         // message of an unweighted edge, exactly as the reference forms it (transition.py:78-83):
         // float32 product chain ((R*S_i)*A_j)*G_j (B_n == 1 is exact), then float64 division by I_bar
@@ -258,158 +260,11 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     };
 
     long long acc_ne = 0, acc_dne = 0, acc_dead = 0;
-    Meta m0 = finalize(load_raw(first)), m1 = finalize(load_raw(first + stride)), m2 = finalize(load_raw(first + 2 * stride));
-    MetaRaw raw = load_raw(first + 3 * stride);
-    RowMeta rows_next = load_rows(first);
-    if (HAS_GATHER && m0.len > 0) { issue_chunk(m0.base4, m0.len, 0, first_issued & 1u); ++first_issued; }
 
-    for (int task = first; task < ntasks; task += stride) {
-        const Meta mt = m0;
-        const RowMeta rows_cur = rows_next;
-        m0 = m1; m1 = m2;
-        m2 = finalize(raw);
-        raw = load_raw(task + 4 * stride);
-        rows_next = load_rows(task + stride);
-        // first chunk of the next task goes in flight before this one is processed
-        if (HAS_GATHER && m0.len > 0) { issue_chunk(m0.base4, m0.len, 0, first_issued & 1u); ++first_issued; }
-
-        double lam = 0.0, lam1 = 0.0;        // FUSED: lambda of my row; GATHER: of the row being folded
-        // ================================================================== gather + fold
-        if (HAS_GATHER && mt.len > 0) {
-            const int len = mt.len;
-            const int64_t row0 = (int64_t)task * (32 * ROWS) + lane * ROWS;     // my first row
-            int rstart[ROWS + 1];
-            uint32_t my_sus;
-            if (ROWS == 1) {
-                rstart[0] = (int)rows_cur.rs.x;
-                my_sus = (mt.sus >> lane) & 1u;
-            } else {
-                const uint4 v = rows_cur.rs;
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) rstart[r] = (int)((w[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu);
-                my_sus = reinterpret_cast<const uint8_t*>(a.sus_bitmap)[(size_t)task * 32 + lane];
-            }
-            {
-                const int nxt = __shfl_down_sync(0xffffffffu, rstart[0], 1);
-                rstart[ROWS] = (lane == 31) ? len : nxt;
-            }
-            int cur_r = -1;                  // GATHER: row (0..7) whose partial lambda is being accumulated
-            int cur_ag = rows_cur.age < 0 ? 0 : (rows_cur.age >= m.n_sfs ? m.n_sfs - 1 : rows_cur.age);
-            uint32_t dbits = 0;
-            auto flush_row = [&]() {          // GATHER: write the partial lambda of row cur_r
-                if (MODE == MODE_GATHER && cur_r >= 0 && (lam != 0.0 || lam1 != 0.0)) {
-                    const size_t idx = (size_t)block * a.n_rows_pad + row0 + cur_r;
-                    if (dbits & (1u << cur_r)) { lam += a.lam_part[idx]; if (want_grad) lam1 += a.lam1_part[idx]; }
-                    a.lam_part[idx] = lam;
-                    if (want_grad) a.lam1_part[idx] = lam1;
-                    dbits |= 1u << cur_r;
-                }
-                lam = 0.0; lam1 = 0.0;
-            };
-
-            const int nch = (len + CAP - 1) / CAP;
-            const uint32_t slot = first_consumed & 1u;
-            ++first_consumed;
-            for (int ci = 0; ci < nch; ++ci) {
-                if (ci > 0) {
-                    // rare: a task larger than one chunk; its later chunks are fetched synchronously into its own
-                    // slot, which has just been drained (the other slot holds the next task's prefetch)
-                    __syncwarp();
-                    issue_chunk(mt.base4, len, ci, slot);
-                }
-                mbar_wait(&s_bar[slot], (slot ? waits1 : waits0) & 1u);
-                if (slot) ++waits1; else ++waits0;
-                const int n = min(CAP, len - ci * CAP);
-                const int32_t* sc = s_col + slot * CAP;
-                const int4* sc4 = reinterpret_cast<const int4*>(sc) + lane * RL4;
-                uint32_t h = 0;
-#pragma unroll
-                for (int q = 0; q < RL4; ++q) {
-                    const int4 c = sc4[q];
-                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.x >> 5));
-                    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.y >> 5));
-                    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.z >> 5));
-                    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.w >> 5));
-                    const uint32_t b = ((w0 >> (c.x & 31)) & 1u) | (((w1 >> (c.y & 31)) & 1u) << 1) |
-                                       (((w2 >> (c.z & 31)) & 1u) << 2) | (((w3 >> (c.w & 31)) & 1u) << 3);
-                    h |= b << (4 * q);
-                }
-                {   // drop the bits of positions past the end of the chunk
-                    const int mine = n - lane * RL;
-                    h &= mine >= RL ? 0xffffffffu >> (32 - RL) : (mine <= 0 ? 0u : ((1u << mine) - 1u));
-                }
-                if (__any_sync(0xffffffffu, h != 0u)) {
-                    s_mask[lane] = h;
-                    __syncwarp();
-                    // fold: every lane walks the hit bits of ITS rows, in edge order
-                    const int lo_all = max(rstart[0] - ci * CAP, 0), hi_all = min(rstart[ROWS] - ci * CAP, n);
-                    if (my_sus != 0u && lo_all < hi_all) {
-                        for (int w = lo_all / RL; w <= (hi_all - 1) / RL; ++w) {
-                            uint32_t bits = s_mask[w];
-                            const int b_lo = max(lo_all - w * RL, 0), b_hi = min(hi_all - w * RL, RL);
-                            bits &= (b_hi >= 32 ? 0xffffffffu : ((1u << b_hi) - 1u)) & ~((1u << b_lo) - 1u);
-                            while (bits) {
-                                // up to 4 hits per round: their code gathers (L2) are issued together
-                                int off[4], code[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    off[j] = -1;
-                                    if (bits) { off[j] = w * RL + (__ffs(bits) - 1); bits &= bits - 1u; }
-                                }
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    code[j] = 0;
-                                    if (off[j] >= 0) {
-                                        const uint32_t enc = (uint32_t)sc[off[j]];
-                                        code[j] = (int)__ldg(code_b + (((enc >> 7) << 5) | (enc & 31u)));
-                                    }
-                                }
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    if (off[j] < 0) continue;
-                                    if (ROWS > 1) {
-                                        const int toff = off[j] + ci * CAP;
-                                        int r = 0;
-#pragma unroll
-                                        for (int q = 1; q < ROWS; ++q) r += (toff >= rstart[q]) ? 1 : 0;
-                                        if (!((my_sus >> r) & 1u)) continue;
-                                        if (r != cur_r) {
-                                            flush_row();
-                                            cur_r = r;
-                                            const int v = load_age(a.age, row0 + r, age_f32);
-                                            cur_ag = v < 0 ? 0 : (v >= m.n_sfs ? m.n_sfs - 1 : v);
-                                        }
-                                    }
-                                    if (!weighted) {
-                                        lam += s_T[cur_ag * NC + code[j]];
-                                        if (want_grad) lam1 += s_T1[cur_ag * NC + code[j]];
-                                    } else {
-                                        const float wgt = a.edge_weight[(int64_t)mt.base4 * 4 + ci * CAP + off[j]];
-                                        const float sa = m.sfs[cur_ag];
-                                        lam += (double)__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(R, sa), s_A[code[j]]), wgt), s_G[code[j]]) / ibar;
-                                        if (want_grad) lam1 += (double)__fmul_rn(__fmul_rn(__fmul_rn(sa, s_A[code[j]]), wgt), s_G[code[j]]) / ibar;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                __syncwarp();                                        // slot and mask are reused by later chunks
-            }
-            if (MODE == MODE_GATHER) {
-                flush_row();
-                reinterpret_cast<uint8_t*>(a.dirty + (size_t)block * ntasks32)[(size_t)task * 32 + lane] = (uint8_t)dbits;
-            }
-        } else if (MODE == MODE_GATHER) {
-            reinterpret_cast<uint8_t*>(a.dirty + (size_t)block * ntasks32)[(size_t)task * 32 + lane] = 0;
-        }
-        if (MODE == MODE_GATHER) continue;
-
-        // ================================================================== update (lane <-> row)
+    // ------------------------------------------------------------------ update of one 32-row subtask (lane <-> row)
+    auto update_subtask = [&](int task, uint32_t sus_w, uint32_t exp_w, uint32_t inf_w, double lam, double lam1) {
         const int64_t row = (int64_t)task * 32 + lane;
         const bool valid = row < a.n_rows;
-        uint32_t sus_w = mt.sus, exp_w = mt.exp, inf_w = mt.inf;
         float stage = 0.f;
         bool stage_known = false;
         if (do_init) {
@@ -419,35 +274,17 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             exp_w = __ballot_sync(0xffffffffu, stage == 1.0f);
             inf_w = __ballot_sync(0xffffffffu, stage == 2.0f);
         }
-        if (MODE == MODE_UPDATE && do_trans && a.dirty != nullptr && sus_w != 0u) {
-            // fold the per-block partial lambdas in block order
-            for (int b0 = 0; b0 < a.n_blocks; b0 += 32) {
-                uint32_t dwl = 0;
-                if (b0 + lane < a.n_blocks) dwl = a.dirty[(size_t)(b0 + lane) * ntasks32 + task];
-                uint32_t any_b = __ballot_sync(0xffffffffu, dwl != 0u);
-                while (any_b) {
-                    const int bl = __ffs(any_b) - 1;
-                    any_b &= any_b - 1;
-                    const uint32_t dw = __shfl_sync(0xffffffffu, dwl, bl);
-                    if ((dw >> lane) & 1u) {
-                        lam += a.lam_part[(size_t)(b0 + bl) * a.n_rows_pad + row];
-                        if (want_grad) lam1 += a.lam1_part[(size_t)(b0 + bl) * a.n_rows_pad + row];
-                    }
-                }
-            }
-        }
         bool is_s = (sus_w >> lane) & 1u, is_e = (exp_w >> lane) & 1u, is_i = (inf_w >> lane) & 1u;
         const bool exposed_candidate = do_trans && is_s && (lam > 0.0 || lam1 > 0.0);
-        // nothing to do for this task: no exposure candidate, nobody in E or I
+        // nothing to do: no exposure candidate, nobody in E or I
         if (!do_init && (exp_w | inf_w) == 0u && !__any_sync(0xffffffffu, exposed_candidate)) {
             if (want_grad && do_trans && valid) a.dne_dr[row] = 0.f;
             if (do_enc) {
                 if (valid) a.code_out[a.row_offset + row] = 0;
                 if (lane == 0) a.hot_bitmap_out[(a.row_offset >> 5) + task] = 0u;
             }
-            continue;
+            return;
         }
-
         float dne = 0.f;
         int nst = 0, itime = 0;
         bool nst_known = false, itime_known = false;
@@ -500,7 +337,6 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             }
         }
         if (want_grad && valid && do_trans) a.dne_dr[row] = dne;
-
         if (do_enc) {
             uint32_t code = 0;
             // infectious = 0 < stage < 3; fractional stages (soft isolation, Q4) index SFInfector[0]
@@ -528,6 +364,208 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             if (do_init || exp_o != exp_w) a.exp_bitmap[task] = exp_o;
             if (do_init || inf_o != inf_w) a.inf_bitmap[task] = inf_o;
         }
+    };
+
+    if (MODE == MODE_UPDATE) {
+        // ---- update-only kernel (blocked mode second pass, or launches without transmission): supertasks of 8
+        //      subtasks; lane i < 8 prefetches the bitmap words of subtask i one supertask ahead, the dirty words of
+        //      the column blocks one subtask ahead; partial lambdas are folded in block order
+        const int nsuper = (ntasks32 + 7) >> 3;
+        const bool use_partials = do_trans && a.dirty != nullptr;
+        auto load_words = [&](int st, uint32_t& sw, uint32_t& ew, uint32_t& iw) {
+            sw = 0; ew = 0; iw = 0;
+            const int task = st * 8 + lane;
+            if (!do_init && lane < 8 && st < nsuper && task < ntasks32) {
+                sw = a.sus_bitmap[task]; ew = a.exp_bitmap[task]; iw = a.inf_bitmap[task];
+            }
+        };
+        uint32_t nsus, nexp, ninf;
+        load_words(first, nsus, nexp, ninf);
+        for (int st = first; st < nsuper; st += stride) {
+            const uint32_t csus = nsus, cexp = nexp, cinf = ninf;
+            load_words(st + stride, nsus, nexp, ninf);
+            uint32_t dwl_next = 0;
+            if (use_partials && lane < a.n_blocks) dwl_next = a.dirty[(size_t)lane * ntasks32 + st * 8];
+            for (int r = 0; r < 8; ++r) {
+                const int task = st * 8 + r;
+                if (task >= ntasks32) break;
+                const uint32_t sus_w = __shfl_sync(0xffffffffu, csus, r), exp_w = __shfl_sync(0xffffffffu, cexp, r),
+                               inf_w = __shfl_sync(0xffffffffu, cinf, r);
+                const uint32_t dwl = dwl_next;
+                if (use_partials && r < 7 && task + 1 < ntasks32 && lane < a.n_blocks) dwl_next = a.dirty[(size_t)lane * ntasks32 + task + 1];
+                double lam = 0.0, lam1 = 0.0;
+                if (use_partials && sus_w != 0u) {
+                    uint32_t any_b = __ballot_sync(0xffffffffu, dwl != 0u);
+                    while (any_b) {
+                        const int bl = __ffs(any_b) - 1;
+                        any_b &= any_b - 1;
+                        const uint32_t dw = __shfl_sync(0xffffffffu, dwl, bl);
+                        if ((dw >> lane) & 1u) {
+                            const double2 v = reinterpret_cast<const double2*>(a.lam_part)[(size_t)bl * a.n_rows_pad + (size_t)task * 32 + lane];
+                            lam += v.x; lam1 += v.y;
+                        }
+                    }
+                    for (int b = 32; b < a.n_blocks; ++b) {                    // rare: more than 32 column blocks
+                        const uint32_t dw = a.dirty[(size_t)b * ntasks32 + task];
+                        if ((dw >> lane) & 1u) {
+                            const double2 v = reinterpret_cast<const double2*>(a.lam_part)[(size_t)b * a.n_rows_pad + (size_t)task * 32 + lane];
+                            lam += v.x; lam1 += v.y;
+                        }
+                    }
+                }
+                update_subtask(task, sus_w, exp_w, inf_w, lam, lam1);
+            }
+        }
+    }
+
+    Meta m0 = finalize(load_raw(first)), m1 = finalize(load_raw(first + stride)), m2 = finalize(load_raw(first + 2 * stride));
+    MetaRaw raw = load_raw(first + 3 * stride);
+    RowMeta rows_next = load_rows(first);
+    if (HAS_GATHER && m0.len > 0) { issue_chunk(m0.base4, m0.len, 0, first_issued & 1u); ++first_issued; }
+
+    for (int task = first; MODE != MODE_UPDATE && task < ntasks; task += stride) {
+        const Meta mt = m0;
+        const RowMeta rows_cur = rows_next;
+        m0 = m1; m1 = m2;
+        m2 = finalize(raw);
+        raw = load_raw(task + 4 * stride);
+        rows_next = load_rows(task + stride);
+        // first chunk of the next task goes in flight before this one is processed
+        if (HAS_GATHER && m0.len > 0) { issue_chunk(m0.base4, m0.len, 0, first_issued & 1u); ++first_issued; }
+
+        double lam = 0.0, lam1 = 0.0;        // FUSED: lambda of my row; GATHER: of the row being folded
+        // ================================================================== gather + fold
+        if (HAS_GATHER && mt.len > 0) {
+            const int len = mt.len;
+            const int64_t row0 = (int64_t)task * (32 * ROWS) + lane * ROWS;     // my first row
+            int rstart[ROWS + 1];
+            uint32_t my_sus;
+            if (ROWS == 1) {
+                rstart[0] = (int)rows_cur.rs.x;
+                my_sus = (mt.sus >> lane) & 1u;
+            } else {
+                const uint4 v = rows_cur.rs;
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) rstart[r] = (int)((w[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu);
+                my_sus = reinterpret_cast<const uint8_t*>(a.sus_bitmap)[(size_t)task * 32 + lane];
+            }
+            {
+                const int nxt = __shfl_down_sync(0xffffffffu, rstart[0], 1);
+                rstart[ROWS] = (lane == 31) ? len : nxt;
+            }
+            int cur_r = -1;                  // GATHER: row (0..7) whose partial lambda is being accumulated
+            int cur_ag = rows_cur.age < 0 ? 0 : (rows_cur.age >= m.n_sfs ? m.n_sfs - 1 : rows_cur.age);
+            uint32_t dbits = 0;
+            auto flush_row = [&]() {          // GATHER: write the partial lambda of row cur_r
+                if (MODE == MODE_GATHER && cur_r >= 0 && (lam != 0.0 || lam1 != 0.0)) {
+                    double2* dst = reinterpret_cast<double2*>(a.lam_part) + (size_t)block * a.n_rows_pad + row0 + cur_r;
+                    if (dbits & (1u << cur_r)) { const double2 old = *dst; lam += old.x; lam1 += old.y; }
+                    *dst = make_double2(lam, lam1);
+                    dbits |= 1u << cur_r;
+                }
+                lam = 0.0; lam1 = 0.0;
+            };
+
+            const int nch = (len + CAP - 1) / CAP;
+            const uint32_t slot = first_consumed & 1u;
+            ++first_consumed;
+            for (int ci = 0; ci < nch; ++ci) {
+                if (ci > 0) {
+                    // rare: a task larger than one chunk; its later chunks are fetched synchronously into its own
+                    // slot, which has just been drained (the other slot holds the next task's prefetch)
+                    __syncwarp();
+                    issue_chunk(mt.base4, len, ci, slot);
+                }
+                mbar_wait(&s_bar[slot], (slot ? waits1 : waits0) & 1u);
+                if (slot) ++waits1; else ++waits0;
+                const int n = min(CAP, len - ci * CAP);
+                const int32_t* sc = s_col + slot * CAP;
+                const int4* sc4 = reinterpret_cast<const int4*>(sc) + lane * RL4;
+                uint32_t h = 0;
+#pragma unroll
+                for (int q = 0; q < RL4; ++q) {
+                    const int4 c = sc4[q];
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.x >> 5));
+                    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.y >> 5));
+                    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.z >> 5));
+                    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.w >> 5));
+                    const uint32_t b = ((w0 >> (c.x & 31)) & 1u) | (((w1 >> (c.y & 31)) & 1u) << 1) |
+                                       (((w2 >> (c.z & 31)) & 1u) << 2) | (((w3 >> (c.w & 31)) & 1u) << 3);
+                    h |= b << (4 * q);
+                }
+                {   // drop the bits of positions past the end of the chunk
+                    const int mine = n - lane * RL;
+                    h &= mine >= RL ? 0xffffffffu >> (32 - RL) : (mine <= 0 ? 0u : ((1u << mine) - 1u));
+                }
+                if (__any_sync(0xffffffffu, h != 0u)) {
+                    s_mask[lane] = h;
+                    {   // the lane that found a hit fetches its code (all L2 gathers of the chunk in flight together)
+                        uint32_t hh = h;
+                        while (hh) {
+                            int o[4]; uint32_t cd[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { o[j] = -1; if (hh) { o[j] = lane * RL + (__ffs(hh) - 1); hh &= hh - 1u; } }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                cd[j] = 0;
+                                if (o[j] >= 0) { const uint32_t enc = (uint32_t)sc[o[j]]; cd[j] = __ldg(code_b + (((enc >> 7) << 5) | (enc & 31u))); }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (o[j] >= 0) s_code[o[j]] = (uint8_t)cd[j];
+                        }
+                    }
+                    __syncwarp();
+                    // fold: every lane walks the hit bits of ITS rows, in edge order
+                    const int lo_all = max(rstart[0] - ci * CAP, 0), hi_all = min(rstart[ROWS] - ci * CAP, n);
+                    if (my_sus != 0u && lo_all < hi_all) {
+                        for (int w = lo_all / RL; w <= (hi_all - 1) / RL; ++w) {
+                            uint32_t bits = s_mask[w];
+                            const int b_lo = max(lo_all - w * RL, 0), b_hi = min(hi_all - w * RL, RL);
+                            bits &= (b_hi >= 32 ? 0xffffffffu : ((1u << b_hi) - 1u)) & ~((1u << b_lo) - 1u);
+                            while (bits) {
+                                const int off = w * RL + (__ffs(bits) - 1);
+                                bits &= bits - 1u;
+                                const int code = (int)s_code[off];
+                                if (ROWS > 1) {
+                                    const int toff = off + ci * CAP;
+                                    int r = 0;
+#pragma unroll
+                                    for (int q = 1; q < ROWS; ++q) r += (toff >= rstart[q]) ? 1 : 0;
+                                    if (!((my_sus >> r) & 1u)) continue;
+                                    if (r != cur_r) {
+                                        flush_row();
+                                        cur_r = r;
+                                        const int v = load_age(a.age, row0 + r, age_f32);
+                                        cur_ag = v < 0 ? 0 : (v >= m.n_sfs ? m.n_sfs - 1 : v);
+                                    }
+                                }
+                                if (!weighted) {
+                                    lam += s_T[cur_ag * NC + code];
+                                    if (want_grad) lam1 += s_T1[cur_ag * NC + code];
+                                } else {
+                                    const float wgt = a.edge_weight[(int64_t)mt.base4 * 4 + ci * CAP + off];
+                                    const float sa = m.sfs[cur_ag];
+                                    lam += (double)__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(R, sa), s_A[code]), wgt), s_G[code]) / ibar;
+                                    if (want_grad) lam1 += (double)__fmul_rn(__fmul_rn(__fmul_rn(sa, s_A[code]), wgt), s_G[code]) / ibar;
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();                                        // slot and mask are reused by later chunks
+            }
+            if (MODE == MODE_GATHER) {
+                flush_row();
+                reinterpret_cast<uint8_t*>(a.dirty + (size_t)block * ntasks32)[(size_t)task * 32 + lane] = (uint8_t)dbits;
+            }
+        } else if (MODE == MODE_GATHER) {
+            reinterpret_cast<uint8_t*>(a.dirty + (size_t)block * ntasks32)[(size_t)task * 32 + lane] = 0;
+        }
+        if (MODE == MODE_GATHER) continue;
+
+        // ================================================================== update (lane <-> row)
+        update_subtask(task, mt.sus, mt.exp, mt.inf, lam, lam1);
     }
 
     // ---- daily sums: fixed-point integers, so the result does not depend on the schedule
@@ -727,7 +765,7 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         if (a.rows_per_task != (a.n_blocks > 1 ? 256 : 32)) return fail("%s", "rows_per_task must be 32 (one block) or 256 (several blocks)");
         if (a.iso_mode == AT_ISO_TENSOR && !a.isolation) return fail("%s", "iso_mode TENSOR without isolation pointer");
         if (a.u_mode == AT_U_TENSOR && !a.uniform) return fail("%s", "u_mode TENSOR without uniform pointer");
-        if (a.n_blocks > 1 && (!a.lam_part || !a.dirty || (a.dne_dr && !a.lam1_part))) return fail("%s", "n_blocks > 1 needs lam_part / lam1_part / dirty");
+        if (a.n_blocks > 1 && (!a.lam_part || !a.dirty)) return fail("%s", "n_blocks > 1 needs lam_part / dirty");
         if (a.flags & AT_DO_INIT) return fail("%s", "AT_DO_INIT cannot be combined with AT_DO_TRANSMISSION");
     }
     if ((a.flags & AT_DO_PROGRESSION) && (!a.next_stage_time || (a.daily_deaths && !a.m_value))) return fail("%s", "progression needs next_stage_time and m_value");
@@ -755,22 +793,25 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         bm_words = a.block_size / 32;
     }
     const size_t smem_gather = (size_t)warps * warp_smem_bytes(epc) + tables + (size_t)bm_words * 4;
-    const size_t smem_update = (size_t)16 * warp_smem_bytes(512) + tables;
+    const size_t smem_update = tables;
     const int64_t ntasks32 = a.n_rows_pad / 32;
     int grid = a.grid > 0 ? a.grid : g_sm_count;
     if (grid > 1024) grid = 1024;
     cudaStream_t s = (cudaStream_t)stream;
+    int ugrid = a.grid > 0 ? a.grid : g_sm_count * 3;          // update kernel: 8-warp CTAs, 3 per SM
+    {
+        const int64_t nsuper = (ntasks32 + 7) / 8;
+        const int64_t uuseful = (nsuper + 7) / 8;
+        if (ugrid > uuseful) ugrid = (int)uuseful;
+        if (ugrid < 1) ugrid = 1;
+    }
     if (do_trans && a.n_blocks > 1) {
         const int Gg = a.tasks_per_group > 0 ? (a.tasks_per_group > MAXG ? MAXG : a.tasks_per_group) : 1;
         int ggrid = grid < a.n_blocks ? a.n_blocks : grid;
         int rc = dispatch<MODE_GATHER>(km, al, ggrid, warps * 32, smem_gather, bm_words, NC, Gg, s);
         if (rc) return rc;
-        const int Gu = 8;
-        const int64_t ngroups = (ntasks32 + Gu - 1) / Gu;
-        int64_t useful = (ngroups + 15) / 16;
-        int ugrid = grid > useful ? (int)useful : grid;
         al.edges_per_chunk = 512;
-        return launch_kernel<MODE_UPDATE, 4>(km, al, ugrid < 1 ? 1 : ugrid, 512, smem_update, 0, NC, Gu, s);
+        return launch_kernel<MODE_UPDATE, 4>(km, al, ugrid, 256, smem_update, 0, NC, 8, s);
     }
     int G = a.tasks_per_group > 0 ? a.tasks_per_group : (do_trans ? (ntasks32 >= 131072 ? 8 : 4) : 8);
     if (G > MAXG) G = MAXG;
@@ -781,11 +822,8 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         if (grid < 1) grid = 1;
         return dispatch<MODE_FUSED>(km, al, grid, warps * 32, smem_gather, bm_words, NC, G, s);
     }
-    int64_t useful = (ngroups + 15) / 16;
-    if (grid > useful) grid = (int)useful;
-    if (grid < 1) grid = 1;
     al.edges_per_chunk = 512;
-    return launch_kernel<MODE_UPDATE, 4>(km, al, grid, 512, smem_update, 0, NC, G, s);
+    return launch_kernel<MODE_UPDATE, 4>(km, al, ugrid, 256, smem_update, 0, NC, 8, s);
 }
 
 int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, const float* dne_dr, const uint8_t* recovered_step,

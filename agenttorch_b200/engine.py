@@ -192,8 +192,8 @@ class SeirmEngine:
         self.inf = torch.zeros(nt, dtype=torch.int32, device=dev)
         self.lam_part = self.lam1_part = self.dirty = None
         if g.n_blocks > 1:
-            self.lam_part = torch.zeros((g.n_blocks, g.n_rows_pad), dtype=torch.float64, device=dev)
-            self.lam1_part = torch.zeros((g.n_blocks, g.n_rows_pad), dtype=torch.float64, device=dev)
+            self.lam_part = torch.zeros((g.n_blocks, g.n_rows_pad, 2), dtype=torch.float64, device=dev)
+            self.lam1_part = None
             self.dirty = torch.zeros((g.n_blocks, nt), dtype=torch.int32, device=dev)
         self.workspace = torch.zeros(self.lib.at_seirm_workspace_bytes() // 8 + 8, dtype=torch.float64, device=dev)
         self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)

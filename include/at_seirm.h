@@ -136,8 +136,8 @@ typedef struct at_seirm_launch {
     float* death_count;         /* [t] = sum(stage*rd/2), or NULL (d daily_deaths / d M) */
     uint8_t* recovered_step;    /* n_rows or NULL: set to t where the I->R transition fires */
     /* scratch for n_blocks > 1 (per-block partial lambdas), else NULL */
-    double* lam_part;           /* [n_blocks][n_rows_pad] */
-    double* lam1_part;          /* [n_blocks][n_rows_pad], needed when dne_dr != NULL */
+    double* lam_part;           /* [n_blocks][n_rows_pad][2]: (lambda, d lambda / dR) of the rows flagged in dirty */
+    double* lam1_part;          /* unused (kept for ABI layout) */
     uint32_t* dirty;            /* [n_blocks][n_rows_pad/32]: which rows of lam_part hold a value this step */
     /* workspace: at_seirm_workspace_bytes() bytes, zeroed once by the caller, reset by every launch */
     void* workspace;
