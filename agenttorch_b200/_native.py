@@ -64,7 +64,7 @@ class SeirmLaunch(ctypes.Structure):
         ("lam_part", ctypes.c_void_p), ("lam1_part", ctypes.c_void_p), ("dirty", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("error_flag", ctypes.c_void_p),
         ("grid", ctypes.c_int32), ("tasks_per_group", ctypes.c_int32),
-        ("warps_per_cta", ctypes.c_int32), ("_pad1", ctypes.c_int32),
+        ("warps_per_cta", ctypes.c_int32), ("hash_words", ctypes.c_int32),
     ]
 
 

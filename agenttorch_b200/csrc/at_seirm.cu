@@ -34,6 +34,8 @@
 #define MODE_FUSED 0                // n_blocks == 1: gather + update per 32-row task
 #define MODE_GATHER 1               // n_blocks > 1: partial lambdas of every column block, 256-row tasks
 #define MODE_UPDATE 2               // update only (lambda from partials, or no transmission)
+#define MODE_HASHED 3               // like FUSED, but the shared-memory bitmap is a HASHED filter: bit (src mod M);
+                                    // col holds raw source ids and false positives die on code == 0
 
 // workspace layout (bytes)
 #define WS_ACC 0                    // int64[3]: sum ne, sum dne, deaths (fixed point)
@@ -118,6 +120,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
 {
     constexpr int RL = 4 * RL4, CAP = 32 * RL, WSM = warp_smem_bytes(CAP);
     constexpr int ROWS = (MODE == MODE_GATHER) ? 8 : 1;        // rows per lane in a gather task
+    constexpr bool HASHED = (MODE == MODE_HASHED);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nw = blockDim.x >> 5;
     // [per-warp areas][Tdiv f64 n_sfs*NC][T1div f64 n_sfs*NC][s_A f32 256][s_G f32 256][hot bitmap]
@@ -138,6 +141,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     const bool weighted = a.edge_weight != nullptr;
     const bool timer_f32 = a.timer_dtype == AT_TIMER_F32, age_f32 = a.age_dtype == AT_AGE_F32;
     constexpr bool HAS_GATHER = (MODE != MODE_UPDATE);
+    const uint32_t hmask = (uint32_t)(bm_words - 1) << 2;        // HASHED: byte-offset mask of the filter words
     const int t = a.t;
     const int block = (MODE == MODE_GATHER) ? (int)(blockIdx.x % a.n_blocks) : 0;
     const float R = do_trans ? a.r_value[a.r_index] : 0.f;
@@ -173,7 +177,20 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
         }
         const uint4* src = reinterpret_cast<const uint4*>(a.hot_bitmap_in + (size_t)block * (a.block_size >> 5));
         uint4* dst = reinterpret_cast<uint4*>(const_cast<unsigned char*>(s_bm));
-        for (int i = tid; i < (bm_words >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+        if (!HASHED) {
+            for (int i = tid; i < (bm_words >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+        } else {
+            // hashed filter: word i = OR of the words i, i+M, i+2M, ... of the full bitmap (M = bm_words, power of 2)
+            const int total4 = (int)(a.n_sources >> 7);
+            for (int i = tid; i < (bm_words >> 2); i += blockDim.x) {
+                uint4 acc4 = make_uint4(0, 0, 0, 0);
+                for (int k = i; k < total4; k += (bm_words >> 2)) {
+                    const uint4 v = __ldg(src + k);
+                    acc4.x |= v.x; acc4.y |= v.y; acc4.z |= v.z; acc4.w |= v.w;
+                }
+                dst[i] = acc4;
+            }
+        }
         if (lane == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -486,10 +503,18 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
 #pragma unroll
                 for (int q = 0; q < RL4; ++q) {
                     const int4 c = sc4[q];
-                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.x >> 5));
-                    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.y >> 5));
-                    const uint32_t w2 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.z >> 5));
-                    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.w >> 5));
+                    uint32_t w0, w1, w2, w3;
+                    if (!HASHED) {
+                        w0 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.x >> 5));
+                        w1 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.y >> 5));
+                        w2 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.z >> 5));
+                        w3 = *reinterpret_cast<const uint32_t*>(s_bm + ((uint32_t)c.w >> 5));
+                    } else {
+                        w0 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.x >> 3) & hmask));
+                        w1 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.y >> 3) & hmask));
+                        w2 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.z >> 3) & hmask));
+                        w3 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.w >> 3) & hmask));
+                    }
                     const uint32_t b = ((w0 >> (c.x & 31)) & 1u) | (((w1 >> (c.y & 31)) & 1u) << 1) |
                                        (((w2 >> (c.z & 31)) & 1u) << 2) | (((w3 >> (c.w & 31)) & 1u) << 3);
                     h |= b << (4 * q);
@@ -499,7 +524,6 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
                     h &= mine >= RL ? 0xffffffffu >> (32 - RL) : (mine <= 0 ? 0u : ((1u << mine) - 1u));
                 }
                 if (__any_sync(0xffffffffu, h != 0u)) {
-                    s_mask[lane] = h;
                     {   // the lane that found a hit fetches its code (all L2 gathers of the chunk in flight together)
                         uint32_t hh = h;
                         while (hh) {
@@ -509,12 +533,21 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 cd[j] = 0;
-                                if (o[j] >= 0) { const uint32_t enc = (uint32_t)sc[o[j]]; cd[j] = __ldg(code_b + (((enc >> 7) << 5) | (enc & 31u))); }
+                                if (o[j] >= 0) {
+                                    const uint32_t enc = (uint32_t)sc[o[j]];
+                                    cd[j] = __ldg(code_b + (HASHED ? enc : (((enc >> 7) << 5) | (enc & 31u))));
+                                }
                             }
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) if (o[j] >= 0) s_code[o[j]] = (uint8_t)cd[j];
+                            for (int j = 0; j < 4; ++j) {
+                                if (o[j] >= 0) {
+                                    s_code[o[j]] = (uint8_t)cd[j];
+                                    if (HASHED && cd[j] == 0u) h &= ~(1u << (o[j] - lane * RL));   // filter false positive
+                                }
+                            }
                         }
                     }
+                    s_mask[lane] = h;
                     __syncwarp();
                     // fold: every lane walks the hit bits of ITS rows, in edge order
                     const int lo_all = max(rstart[0] - ci * CAP, 0), hi_all = min(rstart[ROWS] - ci * CAP, n);
@@ -787,10 +820,13 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     int warps = a.warps_per_cta > 0 ? a.warps_per_cta : 16;
     if (warps > NT_MAX / 32) warps = NT_MAX / 32;
     int bm_words = 0;
+    const bool hashed = do_trans && a.hash_words > 0;
     if (do_trans) {
-        while (warps > 4 && a.block_size > at_seirm_max_block_size(model->n_sfs, model->n_lam_gamma, epc, warps)) --warps;
-        if (a.block_size > at_seirm_max_block_size(model->n_sfs, model->n_lam_gamma, epc, warps)) return fail("%s", "block_size exceeds the shared-memory bitmap capacity (at_seirm_max_block_size)");
-        bm_words = a.block_size / 32;
+        const int64_t bits = hashed ? (int64_t)a.hash_words * 32 : (int64_t)a.block_size;
+        if (hashed && (a.n_blocks != 1 || (a.hash_words & (a.hash_words - 1)) != 0 || a.hash_words < 32)) return fail("%s", "hash_words must be a power of two >= 32 and n_blocks 1");
+        while (warps > 4 && bits > at_seirm_max_block_size(model->n_sfs, model->n_lam_gamma, epc, warps)) --warps;
+        if (bits > at_seirm_max_block_size(model->n_sfs, model->n_lam_gamma, epc, warps)) return fail("%s", "bitmap exceeds the shared-memory capacity (at_seirm_max_block_size)");
+        bm_words = (int)(bits / 32);
     }
     const size_t smem_gather = (size_t)warps * warp_smem_bytes(epc) + tables + (size_t)bm_words * 4;
     const size_t smem_update = tables;
@@ -820,6 +856,7 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         int64_t useful = (ngroups + warps - 1) / warps;
         if (grid > useful) grid = (int)useful;
         if (grid < 1) grid = 1;
+        if (hashed) return dispatch<MODE_HASHED>(km, al, grid, warps * 32, smem_gather, bm_words, NC, G, s);
         return dispatch<MODE_FUSED>(km, al, grid, warps * 32, smem_gather, bm_words, NC, G, s);
     }
     al.edges_per_chunk = 512;

@@ -141,7 +141,7 @@ def _ptr(t, dtype=None, name="tensor"):
 
 class SeirmEngine:
     def __init__(self, graph, spec: SeirmSpec, process_group=None, grid=0, code_len=None, block_size=None,
-                 tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0):
+                 tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0, hashed=None, hash_words=None):
         """graph: ContactGraph (plain CSR, re-blocked here) or a prebuilt BlockedGraph.  block_size: sources
         per column block (default: the largest that fits the shared-memory bitmap, i.e. as few blocks as
         possible); code_len: length of the code/bitmap arrays (multi-GPU: world_size equal slices)."""
@@ -171,14 +171,31 @@ class SeirmEngine:
         else:
             # one column block if the whole bitmap fits next to >= 12 warps of TMA buffers, else equal blocks
             # sized for 16 warps
+            # Default layout: ONE column block.  If all sources fit the shared-memory bitmap next to >= 12 warps of
+            # TMA buffers the bitmap is exact; otherwise it is a hashed filter (bit = src mod M) whose false positives
+            # are rejected by the code lookup.  block_size=... forces exact column blocks (gather + update kernels).
             epc = edges_per_chunk or choose_edges_per_chunk(graph.num_edges / max(graph.n_rows, 1) * 32)
+            full = ((n_src + 1023) // 1024) * 1024
+            if block_size is not None:
+                hash_words = 0
             if block_size is None:
-                if ((n_src + 1023) // 1024) * 1024 <= capacity(epc, 12):
-                    block_size = ((n_src + 1023) // 1024) * 1024
+                fits = full <= capacity(epc, 12)
+                if hash_words:
+                    hashed = True
+                forced_words = int(hash_words or 0)
+                hash_words = 0
+                if hashed is True or (hashed is None and not fits):
+                    hash_words = 1 << 10
+                    while hash_words * 2 * 32 <= min(capacity(epc, 14), full * 2 - 1):
+                        hash_words *= 2
+                    hash_words = forced_words or hash_words
+                    block_size = full
+                elif fits:
+                    block_size = full
                 else:
                     _, block_size = choose_block_size(n_src, capacity(epc, 16))
-            self.graph = block_graph(graph, int(block_size), edges_per_chunk=edges_per_chunk)
-        if self.graph.block_size > capacity(self.graph.edges_per_chunk, 4):
+            self.graph = block_graph(graph, int(block_size), edges_per_chunk=edges_per_chunk, hash_words=hash_words)
+        if (self.graph.hash_words * 32 or self.graph.block_size) > capacity(self.graph.edges_per_chunk, 4):
             raise RuntimeError(f"block_size {self.graph.block_size} exceeds the shared-memory bitmap capacity")
         g = self.graph
         self.n_code = max(((n_src + 1023) // 1024) * 1024, g.n_blocks * g.block_size)
@@ -261,6 +278,7 @@ class SeirmEngine:
         a.grid = int(self.grid)
         a.tasks_per_group = int(self.tasks_per_group)
         a.warps_per_cta = int(self.warps_per_cta)
+        a.hash_words = int(g.hash_words)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(self.lib.at_seirm_step(ctypes.byref(self.model), ctypes.byref(a), ctypes.c_void_p(stream)))
         self.launch_count += 2 if (g.n_blocks > 1 and (flags & nat.DO_TRANSMISSION)) else 1

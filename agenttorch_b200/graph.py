@@ -240,6 +240,7 @@ class BlockedGraph:
     col: torch.Tensor            # (padded edges + TAIL_PAD,) int32
     num_edges: int
     edges_per_chunk: int = 768
+    hash_words: int = 0          # > 0: col holds raw source ids and the smem bitmap is a hashed filter of that many words
     edge_weight: Optional[torch.Tensor] = None
     i_bar: float = 1.0
     i_bar_agent: int = -1
@@ -259,7 +260,7 @@ class BlockedGraph:
     def to(self, device):
         return BlockedGraph(self.n_rows, self.n_rows_pad, self.n_sources, self.row_offset, self.n_blocks, self.block_size,
                             self.rows_per_task, self.row_start.to(device), self.seg_info.to(device), self.col.to(device),
-                            self.num_edges, self.edges_per_chunk,
+                            self.num_edges, self.edges_per_chunk, self.hash_words,
                             None if self.edge_weight is None else self.edge_weight.to(device), self.i_bar, self.i_bar_agent)
 
 
@@ -286,8 +287,10 @@ def _to_i16(x):
     return torch.where(x >= 32768, x - 65536, x).to(torch.int16).contiguous()
 
 
-def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = None, edges_per_chunk: Optional[int] = None) -> BlockedGraph:
-    """ContactGraph (plain dst-sorted CSR, global source ids) -> BlockedGraph, on the graph's device."""
+def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = None, edges_per_chunk: Optional[int] = None,
+                hash_words: int = 0) -> BlockedGraph:
+    """ContactGraph (plain dst-sorted CSR, global source ids) -> BlockedGraph, on the graph's device.
+    hash_words > 0: single block, raw source ids in `col`, hashed shared-memory filter (see include/at_seirm.h)."""
     dev = graph.device
     n_rows, e = graph.n_rows, graph.num_edges
     n_rows_pad = -(-max(n_rows, 1) // 256) * 256
@@ -334,7 +337,7 @@ def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = 
     if total // 4 >= 2**31:
         raise ValueError("graph shard too large for int32 segment bases")
     pos = torch.arange(e, device=dev) - seg_first[seg] + seg_base[:-1][seg]
-    enc = (((col >> 5) << 7) | (col & 31)).to(torch.int32)
+    enc = col.to(torch.int32) if hash_words else (((col >> 5) << 7) | (col & 31)).to(torch.int32)
     col_out = torch.zeros(total + TAIL_PAD, dtype=torch.int32, device=dev)
     col_out[pos] = enc
     w_out = None
@@ -344,5 +347,7 @@ def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = 
         w_out[pos] = w if order is None else w[order]
     seg_info = torch.stack(((seg_base[:-1] >> 2), seg_len), dim=1).to(torch.int32).contiguous()
     epc = edges_per_chunk or choose_edges_per_chunk(e / max(n_seg, 1))
+    if hash_words and nb != 1:
+        raise ValueError("the hashed filter needs a single column block")
     return BlockedGraph(n_rows, n_rows_pad, graph.n_sources, graph.row_offset, nb, block_size, rpt, _to_i16(row_start),
-                        seg_info, col_out, e, epc, w_out, graph.i_bar, graph.i_bar_agent)
+                        seg_info, col_out, e, epc, int(hash_words), w_out, graph.i_bar, graph.i_bar_agent)

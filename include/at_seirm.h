@@ -145,7 +145,9 @@ typedef struct at_seirm_launch {
     int32_t grid;               /* CTAs, 0 = one per SM */
     int32_t tasks_per_group;    /* scheduling granule (1..8 gather tasks), 0 = library default */
     int32_t warps_per_cta;      /* 0 = as many (<= 16) as shared memory allows */
-    int32_t _pad1;
+    int32_t hash_words;         /* 0: exact bitmap, col holds encoded ids.  > 0 (power of two, n_blocks == 1): the
+                                   shared-memory bitmap is a hashed filter of hash_words words (bit src mod 32*hash_words),
+                                   col holds RAW source ids, false positives are rejected by code_in[src] == 0 */
 } at_seirm_launch;
 
 /* ---- queries (host only) ---- */

@@ -17,7 +17,7 @@ def _r_steps_and_grad(r2_np, T, num_weeks=3):
     return r2, r_steps
 
 
-def _run_engine(g, *, packed, block_size=None, use_tensor_noise=False, cuda_graph=False, grid=0, tasks_per_group=0):
+def _run_engine(g, *, packed, block_size=None, use_tensor_noise=False, cuda_graph=False, grid=0, tasks_per_group=0, hashed=None, hash_words=None):
     from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
     from agenttorch_b200.graph import build_contact_graph, mean_interactions_from_age
 
@@ -29,7 +29,7 @@ def _run_engine(g, *, packed, block_size=None, use_tensor_noise=False, cuda_grap
     edges = torch.from_numpy(g["edges"].astype(np.int64)).t().contiguous()
     graph = build_contact_graph(edges, n, mean_interactions=mi).to(dev)
     spec = SeirmSpec(num_steps=T)
-    eng = SeirmEngine(graph, spec, block_size=block_size, grid=grid, tasks_per_group=tasks_per_group)
+    eng = SeirmEngine(graph, spec, block_size=block_size, grid=grid, tasks_per_group=tasks_per_group, hashed=hashed, hash_words=hash_words)
     st = SeirmState.from_initial(g["stage0"].astype(np.float32), g["age"], T, dev, packed=packed)
     if use_tensor_noise:
         U, W = make_noise(g["seed"], g["mode"], n, T, float(g["p_isolate"]))
@@ -64,6 +64,16 @@ def test_episode_matches_reference_golden(case, packed, block_size):
     st, gr2, gm, eng = _run_engine(g, packed=packed, block_size=block_size)
     if block_size is not None and len(g["age"]) > block_size:
         assert eng.graph.n_blocks > 1
+    _check(g, st, gr2, gm)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_hashed_filter_mode(case):
+    """hashed shared-memory filter (used when the sources do not fit an exact bitmap): 1024 filter words here, so
+    astoria's 37518 sources alias ~1.1 per bit and false positives must be rejected by the code lookup"""
+    g = load_golden(case)
+    st, gr2, gm, eng = _run_engine(g, packed=True, hash_words=64)        # 2048 filter bits: heavy aliasing
+    assert eng.graph.hash_words == 64 and eng.graph.n_blocks == 1
     _check(g, st, gr2, gm)
 
 
