@@ -148,6 +148,8 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     const double ibar = (double)m.ibar;
     char* ws = reinterpret_cast<char*>(a.workspace);
 
+    __shared__ int s_any_hot;
+    if (tid == 0) s_any_hot = 0;
     // ---- tables: code -> (SFInfector[int(stage)], lam_gamma[idx]); code = 1 + sidx*K + idx
     if (tid < 256) {
         float av = 0.f, gv = 0.f;
@@ -177,8 +179,13 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
         }
         const uint4* src = reinterpret_cast<const uint4*>(a.hot_bitmap_in + (size_t)block * (a.block_size >> 5));
         uint4* dst = reinterpret_cast<uint4*>(const_cast<unsigned char*>(s_bm));
+        uint32_t seen = 0;
         if (!HASHED) {
-            for (int i = tid; i < (bm_words >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+            for (int i = tid; i < (bm_words >> 2); i += blockDim.x) {
+                const uint4 v = __ldg(src + i);
+                dst[i] = v;
+                seen |= v.x | v.y | v.z | v.w;
+            }
         } else {
             // hashed filter: word i = OR of the words i, i+M, i+2M, ... of the full bitmap (M = bm_words, power of 2)
             const int total4 = (int)(a.n_sources >> 7);
@@ -189,13 +196,16 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
                     acc4.x |= v.x; acc4.y |= v.y; acc4.z |= v.z; acc4.w |= v.w;
                 }
                 dst[i] = acc4;
+                seen |= acc4.x | acc4.y | acc4.z | acc4.w;
             }
         }
+        if (seen != 0u) s_any_hot = 1;                       // benign race: every writer stores 1
         if (lane == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
+    const bool any_hot = s_any_hot != 0;
     const int ntasks32 = (int)(a.n_rows_pad >> 5);                            // 32-row tasks (bitmap words)
     const int ntasks = (MODE == MODE_GATHER) ? (int)(a.n_rows_pad >> 8) : ntasks32;
     const uint16_t* rs_b = HAS_GATHER ? a.row_start + (size_t)block * a.n_rows_pad : nullptr;
@@ -247,7 +257,8 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
         mt.sus = (MODE == MODE_GATHER) ? (r.s0.x | r.s0.y | r.s0.z | r.s0.w | r.s1.x | r.s1.y | r.s1.z | r.s1.w) : r.sus;
         mt.exp = r.exp; mt.inf = r.inf;
         mt.base4 = r.seg.x;
-        mt.len = (mt.sus != 0u) ? r.seg.y : 0;            // no susceptible row: nothing to gather
+        // no susceptible row, or no infectious source at all (in this column block): nothing to gather
+        mt.len = (mt.sus != 0u && any_hot) ? r.seg.y : 0;
         return mt;
     };
     // per-lane row metadata of the NEXT task (row offsets inside its segment, destination age)
@@ -317,10 +328,10 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             }
             // p = 1 - exp(-lambda) (transition.py:220-221); u < p decided in float32 when it is far from the
             // threshold (|error of p32| < 4e-7), in float64 otherwise: same decisions as the float64 reference
-            const float q32 = expf(-(float)lam);
+            const float q32 = __expf(-(float)lam);
             const float p32 = 1.0f - q32;
             bool hit;
-            if (fabsf(u - p32) > 1e-6f) hit = u < p32;
+            if (fabsf(u - p32) > 2e-5f) hit = u < p32;       // __expf: |error of p32| < 4e-6 for lambda < 88
             else hit = (double)u < 1.0 - exp(-lam);
             const float omw = 1.0f - wiso;                  // float32, as (1.0 - will_isolate)
             const float ne = hit ? omw : 0.0f;
@@ -336,6 +347,15 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
                 is_s = false;
                 is_e = (stage == 1.0f);
             }
+        }
+        // common case: candidates were tested, nobody was exposed, nobody is in E or I
+        if (!do_init && (exp_w | inf_w) == 0u && !__any_sync(0xffffffffu, stage_known)) {
+            if (want_grad && do_trans && valid) a.dne_dr[row] = dne;
+            if (do_enc) {
+                if (valid) a.code_out[a.row_offset + row] = 0;
+                if (lane == 0) a.hot_bitmap_out[(a.row_offset >> 5) + task] = 0u;
+            }
+            return;
         }
         if (do_prog && (is_e || is_i)) {
             if (!nst_known) { nst = load_timer(a.next_stage_time, row, timer_f32); nst_known = true; }
@@ -383,7 +403,9 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
         }
     };
 
-    if (MODE == MODE_UPDATE) {
+    const bool update_only = (MODE == MODE_UPDATE) || (MODE != MODE_GATHER && !(do_trans && any_hot));
+    if (update_only) {
+        // ---- update-only pass (also taken by the fused kernels when no source is infectious: lambda == 0 everywhere)
         // ---- update-only kernel (blocked mode second pass, or launches without transmission): supertasks of 8
         //      subtasks; lane i < 8 prefetches the bitmap words of subtask i one supertask ahead, the dirty words of
         //      the column blocks one subtask ahead; partial lambdas are folded in block order
@@ -438,9 +460,9 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     Meta m0 = finalize(load_raw(first)), m1 = finalize(load_raw(first + stride)), m2 = finalize(load_raw(first + 2 * stride));
     MetaRaw raw = load_raw(first + 3 * stride);
     RowMeta rows_next = load_rows(first);
-    if (HAS_GATHER && m0.len > 0) { issue_chunk(m0.base4, m0.len, 0, first_issued & 1u); ++first_issued; }
+    if (HAS_GATHER && !update_only && m0.len > 0) { issue_chunk(m0.base4, m0.len, 0, first_issued & 1u); ++first_issued; }
 
-    for (int task = first; MODE != MODE_UPDATE && task < ntasks; task += stride) {
+    for (int task = first; !update_only && task < ntasks; task += stride) {
         const Meta mt = m0;
         const RowMeta rows_cur = rows_next;
         m0 = m1; m1 = m2;
@@ -527,11 +549,11 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
                     {   // the lane that found a hit fetches its code (all L2 gathers of the chunk in flight together)
                         uint32_t hh = h;
                         while (hh) {
-                            int o[4]; uint32_t cd[4];
+                            int o[8]; uint32_t cd[8];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) { o[j] = -1; if (hh) { o[j] = lane * RL + (__ffs(hh) - 1); hh &= hh - 1u; } }
+                            for (int j = 0; j < 8; ++j) { o[j] = -1; if (hh) { o[j] = lane * RL + (__ffs(hh) - 1); hh &= hh - 1u; } }
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
+                            for (int j = 0; j < 8; ++j) {
                                 cd[j] = 0;
                                 if (o[j] >= 0) {
                                     const uint32_t enc = (uint32_t)sc[o[j]];
@@ -539,7 +561,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
                                 }
                             }
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
+                            for (int j = 0; j < 8; ++j) {
                                 if (o[j] >= 0) {
                                     s_code[o[j]] = (uint8_t)cd[j];
                                     if (HASHED && cd[j] == 0u) h &= ~(1u << (o[j] - lane * RL));   // filter false positive
@@ -646,6 +668,9 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
 // -------------------------------------------------------------------------------- backward kernel
 // grad_r[t] = gI[t]*sum_dne[t] + sum_i dne[t,i] * c_i,  c_i = gD[recovered_step_i] * M / 2
 #define AT_BWD_THREADS 256
+// Agents with c_i != 0 (they recovered inside the episode) are sparse: a warp scans 32 agents at a time and, for
+// every such agent, lane t fetches dne[t, agent] — lane <-> step, so no cross-lane reduction is needed until the end.
+// Static assignment and fixed-order folds: deterministic.
 __global__ void __launch_bounds__(AT_BWD_THREADS)
 seirm_episode_bwd_kernel(int T, int64_t n, int64_t ld, const float* __restrict__ dne, const uint8_t* __restrict__ rstep,
                          const float* __restrict__ sum_dne, const float* __restrict__ death_count,
@@ -653,51 +678,38 @@ seirm_episode_bwd_kernel(int T, int64_t n, int64_t ld, const float* __restrict__
                          float* grad_r, float* grad_m, char* ws)
 {
     __shared__ float s_gd[256];
-    __shared__ double s_red[AT_BWD_THREADS / 32];
-    __shared__ double s_tot[BWD_MAXT];
+    __shared__ double s_acc[AT_BWD_THREADS / 32][BWD_MAXT];
     __shared__ int s_is_last;
     double* partials = reinterpret_cast<double*>(ws + WS_BPART);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float half_m = m_value[0] * 0.5f;
     if (tid < 256) s_gd[tid] = (tid < T) ? gD[tid] * half_m : 0.f;
-    if (tid < BWD_MAXT) s_tot[tid] = 0.0;
     __syncthreads();
-    // static tile assignment + fixed-order folds: deterministic
-    const int64_t tile = (int64_t)AT_BWD_THREADS * 4;
-    for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile) {
-        float c[4];
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t i = base + j * AT_BWD_THREADS + tid;
-            c[j] = (i < n) ? s_gd[rstep[i]] : 0.f;
-            any |= (c[j] != 0.f);
-        }
-        const bool warp_any = __any_sync(0xffffffffu, any);
-        if (!__syncthreads_or(warp_any)) continue;
-        for (int t = 0; t < T; ++t) {
-            double s = 0.0;
-            if (warp_any) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t i = base + j * AT_BWD_THREADS + tid;
-                    if (i < n && c[j] != 0.f) s += (double)(dne[(int64_t)t * ld + i] * c[j]);
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-            }
-            if (lane == 0) s_red[warp] = s;
-            __syncthreads();
-            if (tid == 0) {
-                double tot = 0.0;
-                for (int w = 0; w < AT_BWD_THREADS / 32; ++w) tot += s_red[w];
-                s_tot[t] += tot;
-            }
-            __syncthreads();
+    double acc0 = 0.0, acc1 = 0.0;                  // steps lane and lane + 32
+    const int64_t ngroups = (n + 31) >> 5;
+    const int64_t wstride = (int64_t)gridDim.x * (AT_BWD_THREADS / 32);
+    for (int64_t g = (int64_t)blockIdx.x * (AT_BWD_THREADS / 32) + warp; g < ngroups; g += wstride) {
+        const int64_t i = g * 32 + lane;
+        const float c = (i < n) ? s_gd[rstep[i]] : 0.f;
+        uint32_t mask = __ballot_sync(0xffffffffu, c != 0.f);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const float ci = __shfl_sync(0xffffffffu, c, src);
+            const int64_t agent = g * 32 + src;
+            if (lane < T) acc0 += (double)(dne[(int64_t)lane * ld + agent] * ci);
+            if (lane + 32 < T) acc1 += (double)(dne[(int64_t)(lane + 32) * ld + agent] * ci);
         }
     }
+    s_acc[warp][lane] = acc0;
+    s_acc[warp][lane + 32] = acc1;
+    __syncthreads();
     int* ticket = reinterpret_cast<int*>(ws + WS_BTICKET);
-    if (tid < T) partials[(size_t)blockIdx.x * BWD_MAXT + tid] = s_tot[tid];
+    if (tid < T) {
+        double tot = 0.0;
+        for (int w = 0; w < AT_BWD_THREADS / 32; ++w) tot += s_acc[w][tid];
+        partials[(size_t)blockIdx.x * BWD_MAXT + tid] = tot;
+    }
     __threadfence();
     __syncthreads();
     if (tid == 0) s_is_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
@@ -871,8 +883,8 @@ int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, con
     if (!dne_dr || !recovered_step || !sum_dne_dr || !death_count || !g_daily_infected || !g_daily_deaths || !m_value || !grad_r || !grad_m || !workspace)
         return fail("%s", "null argument");
     if (device_props()) return fail("%s", "cannot query device");
-    int g = grid > 0 ? grid : g_sm_count * 4;
-    const int64_t tiles = (n_rows + AT_BWD_THREADS * 4 - 1) / (AT_BWD_THREADS * 4);
+    int g = grid > 0 ? grid : g_sm_count * 6;
+    const int64_t tiles = (n_rows + AT_BWD_THREADS * 8 - 1) / (AT_BWD_THREADS * 8);
     if (g > tiles) g = (int)tiles;
     if (g > BWD_MAX_GRID) g = BWD_MAX_GRID;
     if (g < 1) g = 1;
