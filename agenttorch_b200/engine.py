@@ -289,16 +289,9 @@ class SeirmEngine:
         halo exchange of boundary-agent infectiousness).  No-op on one GPU."""
         if self.pg is None:
             return
-        import torch.distributed as dist
+        from .parallel import halo_exchange
 
-        world = dist.get_world_size(self.pg)
-        per = self.n_code // world
-        rank = dist.get_rank(self.pg)
-        code = self.code[buf_index]
-        dist.all_gather_into_tensor(code, code[rank * per:(rank + 1) * per], group=self.pg)
-        bm = self.hot[buf_index][: self.n_code // 32]
-        wper = per // 32
-        dist.all_gather_into_tensor(bm, bm[rank * wper:(rank + 1) * wper], group=self.pg)
+        halo_exchange(self.code[buf_index], self.hot[buf_index], self.n_code, self.pg)
 
     # ----------------------------------------------------------------------------- substeps
     def encode(self, state, t):
