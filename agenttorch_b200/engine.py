@@ -351,6 +351,8 @@ class SeirmEngine:
         sv["m_value"].copy_(m_value.detach().reshape(-1)[:1])
         self.seed_buf.fill_(_as_i64(noise.seed))
         if not cuda_graph or self.pg is not None:
+            # (NCCL collectives are not captured: capturing them hung on this stack; multi-GPU episodes are issued
+            # launch by launch)
             self._issue_episode(state, num_steps, noise, sv, want_grad)
             return sv
         key = (num_steps, want_grad, noise.isolation, noise.uniform, float(noise.p_isolate),

@@ -203,6 +203,13 @@ def shard_bounds(num_agents, world_size, align=1024):
     return [(min(r * per, num_agents), min((r + 1) * per, num_agents)) for r in range(world_size)]
 
 
+def shard_code_len(num_agents, world_size, align=1024):
+    """Length of the code / hot arrays for `world_size` equal slices (the last rank's slice is zero-padded)."""
+    per = -(-num_agents // world_size)
+    per = -(-per // align) * align
+    return per * world_size
+
+
 def shard_graph(graph, row_begin, row_end):
     """Rows [row_begin,row_end) of a full (row_offset == 0) graph as a shard with global column ids."""
     if graph.row_offset != 0:

@@ -115,7 +115,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -155,7 +155,7 @@ def ours(args):
     from agenttorch_b200 import _native
     from agenttorch_b200.core import Runner
     from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
-    from agenttorch_b200.graph import (mean_interactions_from_age, shard_bounds, synthetic_contact_graph,
+    from agenttorch_b200.graph import (mean_interactions_from_age, shard_bounds, shard_code_len, synthetic_contact_graph,
                                        synthetic_population)
     from agenttorch_b200.models import covid
     from agenttorch_b200.models.covid.synthetic import synthetic_config
@@ -278,7 +278,7 @@ def ours(args):
                                         mean_interactions=mi)
         graph.i_bar, graph.i_bar_agent = full0.i_bar, full0.i_bar_agent
         del full0
-        engine = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=(bounds[0][1] - bounds[0][0]) * world)
+        engine = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=shard_code_len(N, world))
         st0 = SeirmState.from_initial(stage_all[r0:r1], age_all[r0:r1], T, dev, packed=False)
         st = st0.clone()
         host = {k: getattr(st0, k).cpu().pin_memory() for k in ("stage", "next_stage_time", "infected_time")}
