@@ -141,7 +141,7 @@ def _ptr(t, dtype=None, name="tensor"):
 
 class SeirmEngine:
     def __init__(self, graph, spec: SeirmSpec, process_group=None, grid=0, code_len=None, block_size=None,
-                 tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0, hashed=None, hash_words=None):
+                 tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0, hashed=None, hash_words=None, hash_min_warps=16):
         """graph: ContactGraph (plain CSR, re-blocked here) or a prebuilt BlockedGraph.  block_size: sources
         per column block (default: the largest that fits the shared-memory bitmap, i.e. as few blocks as
         possible); code_len: length of the code/bitmap arrays (multi-GPU: world_size equal slices)."""
@@ -186,7 +186,7 @@ class SeirmEngine:
                 hash_words = 0
                 if hashed is True or (hashed is None and not fits):
                     hash_words = 1 << 10
-                    while hash_words * 2 * 32 <= min(capacity(epc, 14), full * 2 - 1):
+                    while hash_words * 2 * 32 <= min(capacity(epc, hash_min_warps), full * 2 - 1):
                         hash_words *= 2
                     hash_words = forced_words or hash_words
                     block_size = full

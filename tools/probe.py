@@ -14,6 +14,7 @@ ap.add_argument("--family", default="rand")
 ap.add_argument("--block", type=int, default=0)
 ap.add_argument("--tpg", type=int, default=0)
 ap.add_argument("--hashed", type=int, default=-1)
+ap.add_argument("--hmw", type=int, default=16)
 ap.add_argument("--grad", type=int, default=1)
 ap.add_argument("--r2", type=float, default=4.75)
 ap.add_argument("--reps", type=int, default=3)
@@ -25,7 +26,7 @@ age, stage0 = synthetic_population(args.n, 1234, device=dev)
 mi = mean_interactions_from_age(age)
 graph = synthetic_contact_graph(args.n, args.d, 99, family=args.family, device=dev, mean_interactions=mi)
 print("N", args.n, "E", graph.num_edges, "ibar", graph.i_bar, flush=True)
-eng = SeirmEngine(graph, SeirmSpec(num_steps=T), block_size=args.block or None, tasks_per_group=args.tpg, hashed=None if args.hashed < 0 else bool(args.hashed))
+eng = SeirmEngine(graph, SeirmSpec(num_steps=T), block_size=args.block or None, tasks_per_group=args.tpg, hashed=None if args.hashed < 0 else bool(args.hashed), hash_min_warps=args.hmw)
 print('blocks', eng.graph.n_blocks, 'block_size', eng.graph.block_size, 'hash_words', eng.graph.hash_words, flush=True)
 r_steps = torch.full((T,), 3 * args.r2, device=dev)
 m = torch.tensor([0.12], device=dev)
