@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libat_seirm.so")
 SRC_PATH = os.path.join(_PKG, "csrc", "at_seirm.cu")
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_SFS, MAX_SFI, MAX_LAMGAMMA = 16, 8, 84
 TIMER_F32, TIMER_I16 = 0, 1
 AGE_F32, AGE_U8 = 0, 1
@@ -54,7 +54,7 @@ class SeirmLaunch(ctypes.Structure):
         ("age", ctypes.c_void_p), ("timer_dtype", ctypes.c_int32), ("age_dtype", ctypes.c_int32),
         ("sus_bitmap", ctypes.c_void_p), ("exp_bitmap", ctypes.c_void_p), ("inf_bitmap", ctypes.c_void_p),
         ("code_in", ctypes.c_void_p), ("hot_bitmap_in", ctypes.c_void_p), ("code_out", ctypes.c_void_p),
-        ("hot_bitmap_out", ctypes.c_void_p),
+        ("hot_bitmap_out", ctypes.c_void_p), ("hot_filter_in", ctypes.c_void_p), ("hot_filter_out", ctypes.c_void_p),
         ("iso_mode", ctypes.c_int32), ("u_mode", ctypes.c_int32),
         ("isolation", ctypes.c_void_p), ("uniform", ctypes.c_void_p),
         ("seed", ctypes.c_uint64), ("seed_ptr", ctypes.c_void_p), ("p_isolate", ctypes.c_float), ("_pad0", ctypes.c_int32),

@@ -189,6 +189,12 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
         } else {
             // hashed filter: word i = OR of the words i, i+M, i+2M, ... of the full bitmap (M = bm_words, power of 2)
             const int total4 = (int)(a.n_sources >> 7);
+            if (a.hot_filter_in != nullptr) {
+                // already folded by the last CTA of the previous launch
+                const uint4* fsrc = reinterpret_cast<const uint4*>(a.hot_filter_in);
+                for (int i = tid; i < (bm_words >> 2); i += blockDim.x) dst[i] = __ldg(fsrc + i);
+                seen = __ldg(a.hot_filter_in + bm_words);
+            } else
             for (int i = tid; i < (bm_words >> 2); i += blockDim.x) {
                 uint4 acc4 = make_uint4(0, 0, 0, 0);
                 for (int k = i; k < total4; k += (bm_words >> 2)) {
@@ -423,6 +429,21 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
         for (int st = first; st < nsuper; st += stride) {
             const uint32_t csus = nsus, cexp = nexp, cinf = ninf;
             load_words(st + stride, nsus, nexp, ninf);
+            if (!do_init && !use_partials && st * 8 + 8 <= ntasks32 && (int64_t)st * 256 + 256 <= a.n_rows &&
+                !__any_sync(0xffffffffu, (cexp | cinf) != 0u)) {
+                // all 256 rows inert (lambda == 0, nobody in E or I): only the per-step outputs have to be cleared
+                const int64_t row0 = (int64_t)st * 256 + lane * 8;
+                if (want_grad && do_trans) {
+                    float4* d4 = reinterpret_cast<float4*>(a.dne_dr + row0);
+                    d4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    d4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (do_enc) {
+                    *reinterpret_cast<unsigned long long*>(a.code_out + a.row_offset + row0) = 0ull;
+                    if (lane < 8) a.hot_bitmap_out[(a.row_offset >> 5) + st * 8 + lane] = 0u;
+                }
+                continue;
+            }
             uint32_t dwl_next = 0;
             if (use_partials && lane < a.n_blocks) dwl_next = a.dirty[(size_t)lane * ntasks32 + st * 8];
             for (int r = 0; r < 8; ++r) {
@@ -665,6 +686,27 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     }
 }
 
+// Folds the hot bitmap of the next step into the hashed filter (word i = OR of words i, i+M, i+2M, ...) once, so that
+// the next step's CTAs read M words instead of the whole bitmap each; the word after the filter says "any source hot".
+__global__ void __launch_bounds__(256)
+hot_fold_kernel(const uint32_t* __restrict__ hot, uint32_t* __restrict__ filter, int hash_words, int total4)
+{
+    const int M4 = hash_words >> 2;
+    const uint4* src = reinterpret_cast<const uint4*>(hot);
+    uint4* dst = reinterpret_cast<uint4*>(filter);
+    uint32_t seen = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M4; i += gridDim.x * blockDim.x) {
+        uint4 acc4 = make_uint4(0, 0, 0, 0);
+        for (int k = i; k < total4; k += M4) {
+            const uint4 v = __ldg(src + k);
+            acc4.x |= v.x; acc4.y |= v.y; acc4.z |= v.z; acc4.w |= v.w;
+        }
+        dst[i] = acc4;
+        seen |= acc4.x | acc4.y | acc4.z | acc4.w;
+    }
+    if (__syncthreads_or(seen != 0u) && threadIdx.x == 0) atomicOr(&filter[hash_words], 1u);   // flag zeroed by the caller's memset node
+}
+
 // -------------------------------------------------------------------------------- backward kernel
 // grad_r[t] = gI[t]*sum_dne[t] + sum_i dne[t,i] * c_i,  c_i = gD[recovered_step_i] * M / 2
 #define AT_BWD_THREADS 256
@@ -864,15 +906,29 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     int G = a.tasks_per_group > 0 ? a.tasks_per_group : (do_trans ? (ntasks32 >= 131072 ? 8 : 4) : 8);
     if (G > MAXG) G = MAXG;
     const int64_t ngroups = (ntasks32 + G - 1) / G;
+    int rc;
     if (do_trans) {
         int64_t useful = (ngroups + warps - 1) / warps;
         if (grid > useful) grid = (int)useful;
         if (grid < 1) grid = 1;
-        if (hashed) return dispatch<MODE_HASHED>(km, al, grid, warps * 32, smem_gather, bm_words, NC, G, s);
-        return dispatch<MODE_FUSED>(km, al, grid, warps * 32, smem_gather, bm_words, NC, G, s);
+        if (hashed) rc = dispatch<MODE_HASHED>(km, al, grid, warps * 32, smem_gather, bm_words, NC, G, s);
+        else rc = dispatch<MODE_FUSED>(km, al, grid, warps * 32, smem_gather, bm_words, NC, G, s);
+    } else {
+        al.edges_per_chunk = 512;
+        rc = launch_kernel<MODE_UPDATE, 4>(km, al, ugrid, 256, smem_update, 0, NC, 8, s);
     }
-    al.edges_per_chunk = 512;
-    return launch_kernel<MODE_UPDATE, 4>(km, al, ugrid, 256, smem_update, 0, NC, 8, s);
+    if (rc) return rc;
+    if ((a.flags & AT_DO_ENCODE) && a.hot_filter_out != nullptr && a.hash_words > 0) {
+        cudaError_t e = cudaMemsetAsync(a.hot_filter_out + a.hash_words, 0, 4, s);
+        if (e != cudaSuccess) return fail("cudaMemsetAsync: %s", cudaGetErrorString(e));
+        const int M4 = a.hash_words >> 2;
+        int fgrid = (M4 + 255) / 256;
+        if (fgrid > g_sm_count) fgrid = g_sm_count;
+        hot_fold_kernel<<<fgrid, 256, 0, s>>>(a.hot_bitmap_out, a.hot_filter_out, a.hash_words, (int)(a.n_sources >> 7));
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail("hot_fold_kernel launch: %s", cudaGetErrorString(e));
+    }
+    return 0;
 }
 
 int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, const float* dne_dr, const uint8_t* recovered_step,

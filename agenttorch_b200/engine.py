@@ -203,6 +203,10 @@ class SeirmEngine:
         self.code = [torch.zeros(self.n_code, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.hot = [torch.zeros(self.n_code // 32 + 4, dtype=torch.int32, device=dev) for _ in range(2)]
         self.cur = 0
+        # hashed mode on one GPU: the folded filter of each hot bitmap, produced by the launch that writes the bitmap
+        self.filt = None
+        if g.hash_words and process_group is None:
+            self.filt = [torch.zeros(g.hash_words + 4, dtype=torch.int32, device=dev) for _ in range(2)]
         nt = g.n_tasks
         self.sus = torch.zeros(nt, dtype=torch.int32, device=dev)
         self.exp = torch.zeros(nt, dtype=torch.int32, device=dev)
@@ -256,6 +260,9 @@ class SeirmEngine:
         a.hot_bitmap_in = _ptr(self.hot[ci], torch.int32)
         a.code_out = _ptr(self.code[co], torch.uint8)
         a.hot_bitmap_out = _ptr(self.hot[co], torch.int32)
+        if self.filt is not None:
+            a.hot_filter_in = _ptr(self.filt[ci], torch.int32)
+            a.hot_filter_out = _ptr(self.filt[co], torch.int32)
         noise = noise or NoiseSpec()
         a.iso_mode, a.u_mode = noise.iso_mode(), noise.u_mode()
         a.isolation = _ptr(isolation, torch.float32, "isolation")
@@ -281,7 +288,18 @@ class SeirmEngine:
         a.hash_words = int(g.hash_words)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(self.lib.at_seirm_step(ctypes.byref(self.model), ctypes.byref(a), ctypes.c_void_p(stream)))
-        self.launch_count += 2 if (g.n_blocks > 1 and (flags & nat.DO_TRANSMISSION)) else 1
+        self.launch_count += self._kernels_of(flags)
+
+    def _kernels_of(self, flags):
+        """CUDA kernels one at_seirm_step call launches (gather + update in blocked mode, + the filter fold)"""
+        n = 2 if (self.graph.n_blocks > 1 and (flags & nat.DO_TRANSMISSION)) else 1
+        if self.filt is not None and (flags & nat.DO_ENCODE):
+            n += 1
+        return n
+
+    def kernels_per_episode(self, num_steps, backward=True):
+        full = nat.DO_TRANSMISSION | nat.DO_PROGRESSION | nat.DO_ENCODE
+        return self._kernels_of(nat.DO_ENCODE | nat.DO_INIT) + num_steps * self._kernels_of(full) + (1 if backward else 0)
 
     # ------------------------------------------------------------------------ halo exchange
     def exchange(self, buf_index):

@@ -244,7 +244,7 @@ def ours(args):
             episode(init_dev, False)          # the sampler needs >= 1 period under load before the timed region ends
         ms = timed(lambda: episode(init_dev, False), args.steps)
         clocks = sampler.stop()
-        launches = args.steps * (T + 2)
+        launches = args.steps * engine.kernels_per_episode(T)
         # forward-only graph time -> average step-kernel launch duration (includes the 1 encode launch: conservative)
         sv = engine.saved_buffers(T, True)
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -312,7 +312,7 @@ def ours(args):
             episode(False, False)
         ms = timed(lambda: episode(False, False), args.steps)
         clocks = sampler.stop()
-        launches = args.steps * (T + 2)
+        launches = args.steps * engine.kernels_per_episode(T)
         fwd_ms = None
         for _ in range(args.warmup):
             episode(True, True)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AT_SEIRM_ABI_VERSION 5
+#define AT_SEIRM_ABI_VERSION 6
 #define AT_MAX_SFS 16        /* SFSusceptibility entries (config.yaml has 9)                     */
 #define AT_MAX_SFI 8         /* SFInfector entries (config.yaml has 5)                           */
 #define AT_MAX_LAMGAMMA 84   /* lam_gamma_integrals entries; 1 + 3*K infectiousness codes fit a byte */
@@ -116,6 +116,11 @@ typedef struct at_seirm_launch {
     const uint32_t* hot_bitmap_in;  /* n_sources/32 (+4) words: code != 0 */
     uint8_t* code_out;          /* written at [row_offset, row_offset+n_rows) */
     uint32_t* hot_bitmap_out;
+    /* optional, hashed mode on one GPU: the folded filter (hash_words words, word i = OR of the hot words i, i+M, ...,
+       followed by one word that is non-zero iff any source is hot).  _in: read instead of folding hot_bitmap_in in
+       every CTA; _out: written by the last CTA to finish, from hot_bitmap_out.  NULL = fold in the kernel prologue. */
+    const uint32_t* hot_filter_in;
+    uint32_t* hot_filter_out;
     /* noise */
     int32_t iso_mode, u_mode;
     const float* isolation;     /* n_rows or NULL */
