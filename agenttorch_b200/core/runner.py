@@ -78,7 +78,7 @@ class Runner(nn.Module):
 
     def restore_state(self, snapshot, non_blocking=True):
         """Copy a saved agent/environment state (nested dict of tensors, host or device; e.g. pinned host
-        buffers of an initial condition or a checkpoint) INTO the live state tensors, keeping their storage —
+        buffers of an initial condition or a checkpoint, possibly in narrower dtypes) INTO the live state tensors, keeping their storage —
         and therefore the engine bindings and captured CUDA graphs — valid.  The cheap counterpart of
         reset_state(), which re-runs every initialiser."""
         def walk(dst, src):
@@ -89,6 +89,9 @@ class Runner(nn.Module):
                     cur = dst[k]
                     if cur.requires_grad or cur.grad_fn is not None or cur.shape != v.shape:
                         dst[k] = v.to(cur.device, non_blocking=non_blocking).reshape(cur.shape).to(cur.dtype)
+                    elif v.dtype != cur.dtype and v.device != cur.device:
+                        # compact snapshots (e.g. uint8 stages, int16 timers): move the narrow bytes, widen on the device
+                        cur.copy_(v.to(cur.device, non_blocking=non_blocking))
                     else:
                         cur.copy_(v, non_blocking=non_blocking)
         walk(self.state, snapshot)
