@@ -707,6 +707,38 @@ hot_fold_kernel(const uint32_t* __restrict__ hot, uint32_t* __restrict__ filter,
     if (__syncthreads_or(seen != 0u) && threadIdx.x == 0) atomicOr(&filter[hash_words], 1u);   // flag zeroed by the caller's memset node
 }
 
+// Multi-GPU: after the all-gather of the code bytes every rank rebuilds the hot bitmap (code != 0) and the hashed
+// filter locally, so only ONE array has to cross NVLink per step.  A warp handles 1024 sources per iteration:
+// lane L owns sources [32L, 32L+32) of the tile = one bitmap word.
+__global__ void __launch_bounds__(256)
+hot_from_code_kernel(const uint8_t* __restrict__ code, int64_t n_sources, uint32_t* __restrict__ hot,
+                     uint32_t* __restrict__ filter, int hash_words)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_words = n_sources >> 5;
+    uint32_t seen = 0;
+    for (int64_t w0 = warp_id * 32; w0 < n_words; w0 += n_warps * 32) {
+        const int64_t w = w0 + lane;
+        uint32_t word = 0;
+        if (w < n_words) {
+            const uint4* p = reinterpret_cast<const uint4*>(code + w * 32);
+            const uint4 a = __ldg(p), b = __ldg(p + 1);
+            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) word |= (((v[j] >> (8 * k)) & 255u) != 0u ? 1u : 0u) << (4 * j + k);
+            }
+            hot[w] = word;
+            if (word != 0u && filter != nullptr) atomicOr(&filter[w & (hash_words - 1)], word);
+        }
+        seen |= word;
+    }
+    if (filter != nullptr && __syncthreads_or(seen != 0u) && threadIdx.x == 0) atomicOr(&filter[hash_words], 1u);
+}
+
 // -------------------------------------------------------------------------------- backward kernel
 // grad_r[t] = gI[t]*sum_dne[t] + sum_i dne[t,i] * c_i,  c_i = gD[recovered_step_i] * M / 2
 #define AT_BWD_THREADS 256
@@ -948,6 +980,24 @@ int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, con
         death_count, g_daily_infected, g_daily_deaths, m_value, grad_r, grad_m, (char*)workspace);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("seirm_episode_bwd_kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int at_seirm_hot_from_code(const uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, uint32_t* hot_filter,
+                           int32_t hash_words, void* stream) {
+    if (!code || !hot_bitmap || n_sources <= 0 || (n_sources & 1023)) return fail("%s", "bad code / hot_bitmap / n_sources (multiple of 1024)");
+    if (hot_filter && (hash_words < 32 || (hash_words & (hash_words - 1)))) return fail("%s", "hash_words must be a power of two >= 32");
+    if (device_props()) return fail("%s", "cannot query device");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (hot_filter) {
+        cudaError_t e = cudaMemsetAsync(hot_filter, 0, ((size_t)hash_words + 1) * 4, s);
+        if (e != cudaSuccess) return fail("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
+    int64_t tiles = (n_sources / 32 + 255) / 256;
+    int grid = (int)(tiles < g_sm_count * 4 ? tiles : g_sm_count * 4);
+    hot_from_code_kernel<<<grid < 1 ? 1 : grid, 256, 0, s>>>(code, n_sources, hot_bitmap, hot_filter, hash_words);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("hot_from_code_kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -205,7 +205,7 @@ class SeirmEngine:
         self.cur = 0
         # hashed mode on one GPU: the folded filter of each hot bitmap, produced by the launch that writes the bitmap
         self.filt = None
-        if g.hash_words and process_group is None:
+        if g.hash_words:
             self.filt = [torch.zeros(g.hash_words + 4, dtype=torch.int32, device=dev) for _ in range(2)]
         nt = g.n_tasks
         self.sus = torch.zeros(nt, dtype=torch.int32, device=dev)
@@ -222,6 +222,8 @@ class SeirmEngine:
         self.launch_count = 0
         self._graphs = {}
         self._saved = {}
+        self._plans = {}
+        self._recording = None
 
     # ------------------------------------------------------------------------------ raw launch
     def launch(self, state: SeirmState, *, flags, t, t_encode=None, code_in=None, code_out=None,
@@ -262,7 +264,8 @@ class SeirmEngine:
         a.hot_bitmap_out = _ptr(self.hot[co], torch.int32)
         if self.filt is not None:
             a.hot_filter_in = _ptr(self.filt[ci], torch.int32)
-            a.hot_filter_out = _ptr(self.filt[co], torch.int32)
+            # multi-GPU: the filter is rebuilt from the all-gathered codes (exchange), not from this rank's slice
+            a.hot_filter_out = _ptr(self.filt[co], torch.int32) if self.pg is None else None
         noise = noise or NoiseSpec()
         a.iso_mode, a.u_mode = noise.iso_mode(), noise.u_mode()
         a.isolation = _ptr(isolation, torch.float32, "isolation")
@@ -286,14 +289,20 @@ class SeirmEngine:
         a.tasks_per_group = int(self.tasks_per_group)
         a.warps_per_cta = int(self.warps_per_cta)
         a.hash_words = int(g.hash_words)
+        rec = getattr(self, "_recording", None)
+        if rec is not None:
+            rec.append((a, self._kernels_of(flags)))
+        self._submit(a, self._kernels_of(flags))
+
+    def _submit(self, a, n_kernels):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(self.lib.at_seirm_step(ctypes.byref(self.model), ctypes.byref(a), ctypes.c_void_p(stream)))
-        self.launch_count += self._kernels_of(flags)
+        self.launch_count += n_kernels
 
     def _kernels_of(self, flags):
         """CUDA kernels one at_seirm_step call launches (gather + update in blocked mode, + the filter fold)"""
         n = 2 if (self.graph.n_blocks > 1 and (flags & nat.DO_TRANSMISSION)) else 1
-        if self.filt is not None and (flags & nat.DO_ENCODE):
+        if self.filt is not None and self.pg is None and (flags & nat.DO_ENCODE):
             n += 1
         return n
 
@@ -309,7 +318,13 @@ class SeirmEngine:
             return
         from .parallel import halo_exchange
 
-        halo_exchange(self.code[buf_index], self.hot[buf_index], self.n_code, self.pg)
+        # one all-gather of the code bytes per step; the hot bitmap / hashed filter are rebuilt locally from them
+        halo_exchange(self.code[buf_index], None, self.n_code, self.pg)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        filt = self.filt[buf_index] if self.filt is not None else None
+        nat.check(self.lib.at_seirm_hot_from_code(_ptr(self.code[buf_index]), int(self.n_code), _ptr(self.hot[buf_index]),
+                                                  _ptr(filt), int(self.graph.hash_words), ctypes.c_void_p(stream)))
+        self.launch_count += 1
 
     # ----------------------------------------------------------------------------- substeps
     def encode(self, state, t):
@@ -347,15 +362,41 @@ class SeirmEngine:
         return self._saved[key]
 
     def _issue_episode(self, state, num_steps, noise, sv, want_grad, t0=0):
+        """Issue the 1 + num_steps launches of an episode.  The filled launch structs are cached per (buffers, modes),
+        so that re-issuing an episode costs one ctypes call per step (matters when the episode cannot be replayed from
+        a CUDA graph, i.e. with the NCCL halo exchange between the steps)."""
+        key = ("plan", num_steps, want_grad, t0, self.cur, noise.isolation, noise.uniform, float(noise.p_isolate),
+               state.stage.data_ptr(), state.next_stage_time.data_ptr(), state.infected_time.data_ptr(),
+               state.age.data_ptr(), state.daily_infected.data_ptr(), state.daily_deaths.data_ptr(),
+               None if noise.isolation_tensor is None else noise.isolation_tensor.data_ptr(),
+               None if noise.uniform_tensor is None else noise.uniform_tensor.data_ptr())
         sv["recovered_step"].fill_(255)
-        self.encode(state, t0)
-        for k in range(num_steps):
-            t = t0 + k
-            iso = noise.isolation_tensor[k] if noise.isolation == "tensor" else None
-            uni = noise.uniform_tensor[k] if noise.uniform == "tensor" else None
-            self.step(state, t, noise, sv["r_steps"], k, sv["m_value"], isolation=iso, uniform=uni,
-                      dne_dr=sv["dne_dr"][k] if want_grad else None, sum_dne_dr=sv["sum_dne_dr"],
-                      death_count=sv["death_count"], recovered_step=sv["recovered_step"], seed_ptr=self.seed_buf)
+        plan = self._plans.get(key)
+        if plan is not None:
+            for a, nk, flips in plan:
+                self._submit(a, nk)
+                if flips:
+                    self.cur = 1 - self.cur
+                self.exchange(self.cur)
+            return
+        plan = []
+        self._recording = []
+        try:
+            self.encode(state, t0)
+            plan.append((*self._recording[-1], False))
+            for k in range(num_steps):
+                t = t0 + k
+                iso = noise.isolation_tensor[k] if noise.isolation == "tensor" else None
+                uni = noise.uniform_tensor[k] if noise.uniform == "tensor" else None
+                self.step(state, t, noise, sv["r_steps"], k, sv["m_value"], isolation=iso, uniform=uni,
+                          dne_dr=sv["dne_dr"][k] if want_grad else None, sum_dne_dr=sv["sum_dne_dr"],
+                          death_count=sv["death_count"], recovered_step=sv["recovered_step"], seed_ptr=self.seed_buf)
+                plan.append((*self._recording[-1], True))
+        finally:
+            self._recording = None
+        if len(self._plans) > 8:
+            self._plans.clear()
+        self._plans[key] = plan
 
     def run_episode(self, state, r_steps, m_value, num_steps, noise: NoiseSpec, want_grad=False, cuda_graph=False):
         """Advance `state` in place through `num_steps` steps (t = 0..num_steps-1, as Runner.step does).

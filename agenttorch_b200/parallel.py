@@ -9,7 +9,8 @@ import torch.distributed as dist
 
 
 def halo_exchange(code, hot_words, n_code, group=None):
-    """code: (n_code,) uint8; hot_words: (>= n_code/32,) int32 — this rank's slice already written in place.
+    """code: (n_code,) uint8; hot_words: (>= n_code/32,) int32 or None (the engine rebuilds the bitmap from the
+    gathered codes on the device) — this rank's slice already written in place.
     n_code must be world_size equal slices (graph.shard_bounds).  No-op without a process group."""
     if group is None and not (dist.is_available() and dist.is_initialized()):
         return
@@ -21,6 +22,8 @@ def halo_exchange(code, hot_words, n_code, group=None):
         raise ValueError("n_code must split into world_size slices of whole bitmap words")
     per = n_code // world
     dist.all_gather_into_tensor(code[:n_code], code[rank * per:(rank + 1) * per], group=group)
+    if hot_words is None:
+        return
     words = hot_words[: n_code // 32]
     wper = per // 32
     dist.all_gather_into_tensor(words, words[rank * wper:(rank + 1) * wper], group=group)

@@ -193,6 +193,14 @@ int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld,
                               void* workspace, int32_t grid, void* stream);
 
 /*
+ * at_seirm_hot_from_code — multi-GPU helper: after the ranks' code slices have been all-gathered (the per-step halo
+ * exchange of boundary-agent infectiousness; no reference equivalent, core/distributed_runner.py:218-228 is a stub),
+ * rebuild hot_bitmap (bit = code != 0) and, if hot_filter != NULL, the hashed filter of hash_words (+1 flag) words.
+ */
+int at_seirm_hot_from_code(const uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, uint32_t* hot_filter,
+                           int32_t hash_words, void* stream);
+
+/*
  * at_noise_fill — materialise the counter-hash noise (same values the step kernel generates in
  * registers) for the tensor-mode API: what = 0 exposure uniform U, 1 isolation uniform,
  * 2 hard isolation decision (uses p_isolate).  Stands in for torch.rand (action.py:54).
