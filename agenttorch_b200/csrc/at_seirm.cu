@@ -691,20 +691,24 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
 __global__ void __launch_bounds__(256)
 hot_fold_kernel(const uint32_t* __restrict__ hot, uint32_t* __restrict__ filter, int hash_words, int total4)
 {
+    // blockIdx.y picks every gridDim.y-th slice, so the (latency-bound) loads of the slices run in parallel; the
+    // filter was zeroed by the caller and is assembled with atomicOr (bitwise OR: order-independent)
     const int M4 = hash_words >> 2;
     const uint4* src = reinterpret_cast<const uint4*>(hot);
-    uint4* dst = reinterpret_cast<uint4*>(filter);
     uint32_t seen = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M4; i += gridDim.x * blockDim.x) {
         uint4 acc4 = make_uint4(0, 0, 0, 0);
-        for (int k = i; k < total4; k += M4) {
+        for (int k = i + (int)blockIdx.y * M4; k < total4; k += (int)gridDim.y * M4) {
             const uint4 v = __ldg(src + k);
             acc4.x |= v.x; acc4.y |= v.y; acc4.z |= v.z; acc4.w |= v.w;
         }
-        dst[i] = acc4;
+        if (acc4.x) atomicOr(&filter[4 * i + 0], acc4.x);
+        if (acc4.y) atomicOr(&filter[4 * i + 1], acc4.y);
+        if (acc4.z) atomicOr(&filter[4 * i + 2], acc4.z);
+        if (acc4.w) atomicOr(&filter[4 * i + 3], acc4.w);
         seen |= acc4.x | acc4.y | acc4.z | acc4.w;
     }
-    if (__syncthreads_or(seen != 0u) && threadIdx.x == 0) atomicOr(&filter[hash_words], 1u);   // flag zeroed by the caller's memset node
+    if (__syncthreads_or(seen != 0u) && threadIdx.x == 0) atomicOr(&filter[hash_words], 1u);
 }
 
 // Multi-GPU: after the all-gather of the code bytes every rank rebuilds the hot bitmap (code != 0) and the hashed
@@ -951,12 +955,15 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     }
     if (rc) return rc;
     if ((a.flags & AT_DO_ENCODE) && a.hot_filter_out != nullptr && a.hash_words > 0) {
-        cudaError_t e = cudaMemsetAsync(a.hot_filter_out + a.hash_words, 0, 4, s);
+        cudaError_t e = cudaMemsetAsync(a.hot_filter_out, 0, ((size_t)a.hash_words + 1) * 4, s);
         if (e != cudaSuccess) return fail("cudaMemsetAsync: %s", cudaGetErrorString(e));
-        const int M4 = a.hash_words >> 2;
+        const int M4 = a.hash_words >> 2, total4 = (int)(a.n_sources >> 7);
         int fgrid = (M4 + 255) / 256;
         if (fgrid > g_sm_count) fgrid = g_sm_count;
-        hot_fold_kernel<<<fgrid, 256, 0, s>>>(a.hot_bitmap_out, a.hot_filter_out, a.hash_words, (int)(a.n_sources >> 7));
+        int slices = (total4 + M4 - 1) / M4;
+        if (slices > 16) slices = 16;
+        if (slices < 1) slices = 1;
+        hot_fold_kernel<<<dim3(fgrid, slices), 256, 0, s>>>(a.hot_bitmap_out, a.hot_filter_out, a.hash_words, total4);
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail("hot_fold_kernel launch: %s", cudaGetErrorString(e));
     }
