@@ -27,7 +27,7 @@ MAX_BLOCKS = 64
 EXPORTS = [
     "at_seirm_abi_version", "at_last_error", "at_seirm_sizeof_launch", "at_seirm_sizeof_model",
     "at_seirm_workspace_bytes", "at_seirm_max_block_size", "at_seirm_step",
-    "at_seirm_episode_backward", "at_seirm_hot_from_code", "at_noise_fill",
+    "at_seirm_episode_backward", "at_seirm_hot_from_code", "at_seirm_pull_codes", "at_noise_fill",
 ]
 
 
@@ -122,6 +122,9 @@ def lib():
         L.at_seirm_hot_from_code.restype = ctypes.c_int
         L.at_seirm_hot_from_code.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_int32, ctypes.c_void_p]
+        L.at_seirm_pull_codes.restype = ctypes.c_int
+        L.at_seirm_pull_codes.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                          ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
         L.at_noise_fill.restype = ctypes.c_int
         L.at_noise_fill.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32,
                                     ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]

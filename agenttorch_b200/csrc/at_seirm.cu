@@ -714,9 +714,15 @@ hot_fold_kernel(const uint32_t* __restrict__ hot, uint32_t* __restrict__ filter,
 // Multi-GPU: after the all-gather of the code bytes every rank rebuilds the hot bitmap (code != 0) and the hashed
 // filter locally, so only ONE array has to cross NVLink per step.  A warp handles 1024 sources per iteration:
 // lane L owns sources [32L, 32L+32) of the tile = one bitmap word.
+struct PeerPtrs { const uint8_t* p[16]; };
+
+// PULL = true: fused halo exchange — the slices of the other ranks are read straight from their (symmetric-memory)
+// code buffers over NVLink (P2P loads), copied into the local code array and turned into bitmap/filter bits in the
+// same pass.  peers.p[r] = base of rank r's buffer (the rank's own base for its own slice).
+template <bool PULL>
 __global__ void __launch_bounds__(256)
-hot_from_code_kernel(const uint8_t* __restrict__ code, int64_t n_sources, uint32_t* __restrict__ hot,
-                     uint32_t* __restrict__ filter, int hash_words)
+hot_from_code_kernel(uint8_t* __restrict__ code, int64_t n_sources, uint32_t* __restrict__ hot,
+                     uint32_t* __restrict__ filter, int hash_words, PeerPtrs peers, int rank, int64_t per)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -727,8 +733,22 @@ hot_from_code_kernel(const uint8_t* __restrict__ code, int64_t n_sources, uint32
         const int64_t w = w0 + lane;
         uint32_t word = 0;
         if (w < n_words) {
-            const uint4* p = reinterpret_cast<const uint4*>(code + w * 32);
-            const uint4 a = __ldg(p), b = __ldg(p + 1);
+            const uint8_t* base = code;
+            bool remote = false;
+            if (PULL) {
+                const int owner = (int)((w0 * 32) / per);            // a 1024-source tile never straddles two slices
+                remote = owner != rank;
+                base = peers.p[owner];
+            }
+            const uint4* p = reinterpret_cast<const uint4*>(base + w * 32);
+            uint4 a, b;
+            if (PULL && remote) {
+                a = __ldcv(p); b = __ldcv(p + 1);               // peer memory: never served from a stale L1 line
+                uint4* q = reinterpret_cast<uint4*>(code + w * 32);
+                q[0] = a; q[1] = b;
+            } else {
+                a = __ldg(p); b = __ldg(p + 1);
+            }
             const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -990,8 +1010,8 @@ int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, con
     return 0;
 }
 
-int at_seirm_hot_from_code(const uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, uint32_t* hot_filter,
-                           int32_t hash_words, void* stream) {
+static int hot_from_code_impl(uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, uint32_t* hot_filter, int32_t hash_words,
+                              const void* const* peer_code, int32_t world, int32_t rank, void* stream) {
     if (!code || !hot_bitmap || n_sources <= 0 || (n_sources & 1023)) return fail("%s", "bad code / hot_bitmap / n_sources (multiple of 1024)");
     if (hot_filter && (hash_words < 32 || (hash_words & (hash_words - 1)))) return fail("%s", "hash_words must be a power of two >= 32");
     if (device_props()) return fail("%s", "cannot query device");
@@ -1002,10 +1022,31 @@ int at_seirm_hot_from_code(const uint8_t* code, int64_t n_sources, uint32_t* hot
     }
     int64_t tiles = (n_sources / 32 + 255) / 256;
     int grid = (int)(tiles < g_sm_count * 4 ? tiles : g_sm_count * 4);
-    hot_from_code_kernel<<<grid < 1 ? 1 : grid, 256, 0, s>>>(code, n_sources, hot_bitmap, hot_filter, hash_words);
+    if (grid < 1) grid = 1;
+    PeerPtrs pp;
+    memset(&pp, 0, sizeof(pp));
+    if (peer_code) {
+        if (world < 1 || world > 16 || rank < 0 || rank >= world || (n_sources % world) || ((n_sources / world) & 1023))
+            return fail("%s", "pull: world (<= 16) equal slices of whole 1024-source tiles are required");
+        for (int r = 0; r < world; ++r) pp.p[r] = (const uint8_t*)peer_code[r];
+        hot_from_code_kernel<true><<<grid, 256, 0, s>>>(code, n_sources, hot_bitmap, hot_filter, hash_words, pp, rank, n_sources / world);
+    } else {
+        hot_from_code_kernel<false><<<grid, 256, 0, s>>>(code, n_sources, hot_bitmap, hot_filter, hash_words, pp, 0, n_sources);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("hot_from_code_kernel launch: %s", cudaGetErrorString(e));
     return 0;
+}
+
+int at_seirm_hot_from_code(const uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, uint32_t* hot_filter,
+                           int32_t hash_words, void* stream) {
+    return hot_from_code_impl(const_cast<uint8_t*>(code), n_sources, hot_bitmap, hot_filter, hash_words, nullptr, 1, 0, stream);
+}
+
+int at_seirm_pull_codes(uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, uint32_t* hot_filter, int32_t hash_words,
+                        const void* const* peer_code, int32_t world, int32_t rank, void* stream) {
+    if (!peer_code) return fail("%s", "peer_code must not be null");
+    return hot_from_code_impl(code, n_sources, hot_bitmap, hot_filter, hash_words, peer_code, world, rank, stream);
 }
 
 int at_noise_fill(float* out, int64_t n, int64_t id_offset, uint64_t seed, int32_t step, int32_t what, float p_isolate, void* stream) {

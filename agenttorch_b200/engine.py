@@ -141,7 +141,7 @@ def _ptr(t, dtype=None, name="tensor"):
 
 class SeirmEngine:
     def __init__(self, graph, spec: SeirmSpec, process_group=None, grid=0, code_len=None, block_size=None,
-                 tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0, hashed=None, hash_words=None, hash_min_warps=16):
+                 tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0, hashed=None, hash_words=None, hash_min_warps=16, symmetric=None):
         """graph: ContactGraph (plain CSR, re-blocked here) or a prebuilt BlockedGraph.  block_size: sources
         per column block (default: the largest that fits the shared-memory bitmap, i.e. as few blocks as
         possible); code_len: length of the code/bitmap arrays (multi-GPU: world_size equal slices)."""
@@ -200,7 +200,24 @@ class SeirmEngine:
         g = self.graph
         self.n_code = max(((n_src + 1023) // 1024) * 1024, g.n_blocks * g.block_size)
         dev = self.device
-        self.code = [torch.zeros(self.n_code, dtype=torch.uint8, device=dev) for _ in range(2)]
+        # Multi-GPU: the code arrays live in symmetric memory when available, so that the per-step halo exchange is a
+        # device-side barrier + peer copies over NVLink that can be captured into the episode's CUDA graph (NCCL
+        # collectives could not).  symmetric=None: try, fall back to the NCCL all-gather.
+        self.code_hdl = None
+        if process_group is not None and symmetric is not False:
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                self.code = [symm.empty(self.n_code, dtype=torch.uint8, device=dev) for _ in range(2)]
+                self.code_hdl = [symm.rendezvous(c, process_group) for c in self.code]
+                for c in self.code:
+                    c.zero_()
+            except Exception:
+                if symmetric is True:
+                    raise
+                self.code_hdl = None
+        if self.code_hdl is None:
+            self.code = [torch.zeros(self.n_code, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.hot = [torch.zeros(self.n_code // 32 + 4, dtype=torch.int32, device=dev) for _ in range(2)]
         self.cur = 0
         # hashed mode on one GPU: the folded filter of each hot bitmap, produced by the launch that writes the bitmap
@@ -318,12 +335,24 @@ class SeirmEngine:
             return
         from .parallel import halo_exchange
 
-        # one all-gather of the code bytes per step; the hot bitmap / hashed filter are rebuilt locally from them
-        halo_exchange(self.code[buf_index], None, self.n_code, self.pg)
+        # the code bytes are the whole halo; the hot bitmap / hashed filter are rebuilt locally from them
         stream = torch.cuda.current_stream(self.device).cuda_stream
         filt = self.filt[buf_index] if self.filt is not None else None
-        nat.check(self.lib.at_seirm_hot_from_code(_ptr(self.code[buf_index]), int(self.n_code), _ptr(self.hot[buf_index]),
-                                                  _ptr(filt), int(self.graph.hash_words), ctypes.c_void_p(stream)))
+        if self.code_hdl is not None:
+            import torch.distributed as dist
+
+            hdl = self.code_hdl[buf_index]
+            world, rank = dist.get_world_size(self.pg), dist.get_rank(self.pg)
+            hdl.barrier(channel=buf_index)                       # every rank has written its slice of this buffer
+            ptrs = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+            # fused: pull the peers' slices over NVLink (P2P loads) + rebuild bitmap/filter, one kernel
+            nat.check(self.lib.at_seirm_pull_codes(_ptr(self.code[buf_index]), int(self.n_code), _ptr(self.hot[buf_index]),
+                                                   _ptr(filt), int(self.graph.hash_words), ptrs, world, rank,
+                                                   ctypes.c_void_p(stream)))
+        else:
+            halo_exchange(self.code[buf_index], None, self.n_code, self.pg)
+            nat.check(self.lib.at_seirm_hot_from_code(_ptr(self.code[buf_index]), int(self.n_code), _ptr(self.hot[buf_index]),
+                                                      _ptr(filt), int(self.graph.hash_words), ctypes.c_void_p(stream)))
         self.launch_count += 1
 
     # ----------------------------------------------------------------------------- substeps
@@ -409,9 +438,9 @@ class SeirmEngine:
         sv["r_steps"].copy_(r_steps.detach().reshape(-1)[:num_steps])
         sv["m_value"].copy_(m_value.detach().reshape(-1)[:1])
         self.seed_buf.fill_(_as_i64(noise.seed))
-        if not cuda_graph or self.pg is not None:
-            # (NCCL collectives are not captured: capturing them hung on this stack; multi-GPU episodes are issued
-            # launch by launch)
+        if not cuda_graph or (self.pg is not None and self.code_hdl is None):
+            # (NCCL collectives are not captured: capturing them hung on this stack; without symmetric memory a
+            # multi-GPU episode is issued launch by launch)
             self._issue_episode(state, num_steps, noise, sv, want_grad)
             return sv
         key = (num_steps, want_grad, noise.isolation, noise.uniform, float(noise.p_isolate),

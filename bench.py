@@ -300,7 +300,8 @@ def ours(args):
             for k in ("stage", "next_stage_time", "infected_time"):
                 getattr(st, k).copy_(host[k] if from_host else getattr(st0, k), non_blocking=True)
             st.daily_infected.zero_(); st.daily_deaths.zero_()
-            sv = engine.run_episode(st, r_steps, m_val, T, NoiseSpec(seed=SEED, isolation="soft"), want_grad=True)
+            sv = engine.run_episode(st, r_steps, m_val, T, NoiseSpec(seed=SEED, isolation="soft"), want_grad=True,
+                                    cuda_graph=engine.code_hdl is not None)
             di, dd = st.daily_infected.clone(), st.daily_deaths.clone()
             dist.all_reduce(di); dist.all_reduce(dd)
             gr, gm = engine.episode_backward(sv, T, gI, gD, m_val)

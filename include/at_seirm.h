@@ -201,6 +201,16 @@ int at_seirm_hot_from_code(const uint8_t* code, int64_t n_sources, uint32_t* hot
                            int32_t hash_words, void* stream);
 
 /*
+ * at_seirm_pull_codes — the halo exchange fused with the rebuild, for code arrays in symmetric (peer-mapped) memory:
+ * peer_code is a HOST array of `world` device pointers, peer_code[r] = base of rank r's code buffer as mapped into
+ * this process (own buffer for r == rank).  After a device-side barrier (all ranks have written their slice), one
+ * kernel reads the other ranks' slices over NVLink (P2P loads), stores them into the local `code` array and sets the
+ * hot bitmap / hashed filter bits in the same pass.
+ */
+int at_seirm_pull_codes(uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, uint32_t* hot_filter, int32_t hash_words,
+                        const void* const* peer_code, int32_t world, int32_t rank, void* stream);
+
+/*
  * at_noise_fill — materialise the counter-hash noise (same values the step kernel generates in
  * registers) for the tensor-mode API: what = 0 exposure uniform U, 1 isolation uniform,
  * 2 hard isolation decision (uses p_isolate).  Stands in for torch.rand (action.py:54).

@@ -38,7 +38,8 @@ def _episode(rank, world, port, out_dir, cuda_graph):
     full = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, mean_interactions=mean_interactions_from_age(age))
     graph = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, row_begin=r0, row_end=r1)
     graph.i_bar, graph.i_bar_agent = full.i_bar, full.i_bar_agent
-    eng = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=shard_code_len(N, world))
+    eng = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=shard_code_len(N, world),
+                      symmetric=None if cuda_graph else False)      # False: NCCL all-gather path
     st = SeirmState.from_initial(stage0[r0:r1], age[r0:r1], T, dev)
     r_steps = torch.full((T,), 14.25, device=dev)
     m = torch.tensor([0.12], device=dev)
@@ -59,8 +60,9 @@ def _episode(rank, world, port, out_dir, cuda_graph):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cuda_graph", [False])
+@pytest.mark.parametrize("cuda_graph", [False, True])
 def test_two_gpus_reproduce_one_gpu(tmp_path, cuda_graph):
+    """cuda_graph=True: symmetric-memory halo exchange (barrier + peer copies) replayed from one CUDA graph per rank"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
