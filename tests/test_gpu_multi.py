@@ -79,3 +79,54 @@ def test_two_gpus_reproduce_one_gpu(tmp_path, cuda_graph):
     assert float(one["di"].sum()) > 1000                        # a real epidemic happened
     np.testing.assert_allclose(parts[0]["gr"].numpy(), one["gr"].numpy(), rtol=1e-6)
     np.testing.assert_allclose(parts[0]["gm"].numpy(), one["gm"].numpy(), rtol=1e-6)
+
+
+def _distributed_runner(rank, world, port, out_dir, pop_dir):
+    import torch.distributed as dist
+
+    from agenttorch_b200.core import envs
+    from agenttorch_b200.models import covid
+    from tests.helpers import load_golden
+
+    g = load_golden("synth3k_soft")
+    torch.cuda.set_device(rank)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    runner = envs.create(model=covid, population=pop_dir, distributed=True, world_size=world)
+    dev = runner.initializer.device
+    r2 = torch.tensor(g["r2"], dtype=torch.float32, device=dev, requires_grad=True)
+    m = torch.tensor(g["m"], dtype=torch.float32, device=dev, requires_grad=True)
+    runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": r2,
+                            "initializer.transition_function.1.seirm_progression.learnable_args.M": m})
+    runner.tr.noise_seed, runner.tr.advance_seed = g["seed"], False
+    runner.step(g["num_steps"])
+    env = runner.state_trajectory[-1][-1]["environment"]
+    loss = (torch.from_numpy(g["gI"]).to(dev) * env["daily_infected"].reshape(-1)).sum() + \
+           (torch.from_numpy(g["gD"]).to(dev) * env["daily_deaths"].reshape(-1)).sum()
+    loss.backward()
+    final = runner.gather_final_state()
+    assert runner.agent_partition_map["local_size"] == runner.state["agents"]["citizens"]["disease_stage"].shape[0]
+    torch.save({"stage": final["disease_stage"].cpu(), "nst": final["next_stage_time"].cpu(), "di": env["daily_infected"].detach().cpu(),
+                "dd": env["daily_deaths"].detach().cpu(), "gr2": r2.grad.cpu(), "gm": m.grad.cpu()}, os.path.join(out_dir, f"dr{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_distributed_runner_api_matches_reference_golden(tmp_path):
+    """envs.create(distributed=True) on 2 GPUs reproduces the REAL reference's golden outputs"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from agenttorch_b200.populations import write_population_folder
+    from tests.helpers import load_golden, rel_err
+
+    g = load_golden("synth3k_soft")
+    pop = write_population_folder(str(tmp_path / "pop"), g["age"], g["stage0"], g["edges"])
+    mp.spawn(_distributed_runner, args=(2, _free_port(), str(tmp_path), pop), nprocs=2, join=True)
+    for r in range(2):
+        o = torch.load(os.path.join(str(tmp_path), f"dr{r}.pt"))
+        assert np.array_equal(o["stage"].numpy().reshape(-1).astype(np.float64), g["ref_stage"])
+        assert np.array_equal(o["nst"].numpy().reshape(-1).astype(np.int64), g["ref_next_stage_time"].astype(np.int64))
+        assert tuple(o["dd"].shape) == (1, g["num_steps"])
+        assert rel_err(g["ref_daily_infected"], o["di"].numpy()) <= 1e-5 and rel_err(g["ref_daily_deaths"], o["dd"].numpy()) <= 1e-5
+        assert rel_err(g["ref_grad_R2"], o["gr2"].numpy()) <= 1e-4 and rel_err(g["ref_grad_M"], o["gm"].numpy()) <= 1e-4
