@@ -212,6 +212,8 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     __syncthreads();
 
     const bool any_hot = s_any_hot != 0;
+    // hashed filter with many sources per bit: most positives are false, check the exact bitmap before the code array
+    const bool exact_check = HASHED && a.n_sources > (int64_t)bm_words * 32 * 24;
     const int ntasks32 = (int)(a.n_rows_pad >> 5);                            // 32-row tasks (bitmap words)
     const int ntasks = (MODE == MODE_GATHER) ? (int)(a.n_rows_pad >> 8) : ntasks32;
     const uint16_t* rs_b = HAS_GATHER ? a.row_start + (size_t)block * a.n_rows_pad : nullptr;
@@ -573,12 +575,28 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
                             int o[8]; uint32_t cd[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) { o[j] = -1; if (hh) { o[j] = lane * RL + (__ffs(hh) - 1); hh &= hh - 1u; } }
+                            if (HASHED && exact_check) {
+                                // large source sets: a filter positive is first checked against the exact hot bitmap
+                                // (n/8 bytes, L2-resident) so that only true hits touch the code array (n bytes)
+                                uint32_t src[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                cd[j] = 0;
-                                if (o[j] >= 0) {
-                                    const uint32_t enc = (uint32_t)sc[o[j]];
-                                    cd[j] = __ldg(code_b + (HASHED ? enc : (((enc >> 7) << 5) | (enc & 31u))));
+                                for (int j = 0; j < 8; ++j) {
+                                    src[j] = 0; cd[j] = 0;
+                                    if (o[j] >= 0) { src[j] = (uint32_t)sc[o[j]]; cd[j] = __ldg(a.hot_bitmap_in + (src[j] >> 5)); }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const bool hot = o[j] >= 0 && ((cd[j] >> (src[j] & 31u)) & 1u);
+                                    cd[j] = hot ? (uint32_t)__ldg(code_b + src[j]) : 0u;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    cd[j] = 0;
+                                    if (o[j] >= 0) {
+                                        const uint32_t enc = (uint32_t)sc[o[j]];
+                                        cd[j] = __ldg(code_b + (HASHED ? enc : (((enc >> 7) << 5) | (enc & 31u))));
+                                    }
                                 }
                             }
 #pragma unroll

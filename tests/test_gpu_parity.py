@@ -68,12 +68,15 @@ def test_episode_matches_reference_golden(case, packed, block_size):
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-def test_hashed_filter_mode(case):
+@pytest.mark.parametrize("hash_words", [64, 32])
+def test_hashed_filter_mode(case, hash_words):
     """hashed shared-memory filter (used when the sources do not fit an exact bitmap): 1024 filter words here, so
     astoria's 37518 sources alias ~1.1 per bit and false positives must be rejected by the code lookup"""
     g = load_golden(case)
-    st, gr2, gm, eng = _run_engine(g, packed=True, hash_words=64)        # 2048 filter bits: heavy aliasing
-    assert eng.graph.hash_words == 64 and eng.graph.n_blocks == 1
+    # 2048 / 1024 filter bits: heavy aliasing; with 32 words astoria has > 24 sources per bit, which switches on the
+    # exact-bitmap check in front of the code gather
+    st, gr2, gm, eng = _run_engine(g, packed=True, hash_words=hash_words)
+    assert eng.graph.hash_words == hash_words and eng.graph.n_blocks == 1
     _check(g, st, gr2, gm)
 
 
