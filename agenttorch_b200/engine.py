@@ -457,6 +457,8 @@ class SeirmEngine:
             with torch.cuda.graph(g):
                 self._issue_episode(state, num_steps, noise, sv, want_grad)
             entry = (g, cur0, self.cur)
+            if len(self._graphs) >= 4:               # state tensors were re-created (reset_state): drop old captures
+                self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = entry
             self.cur = cur0
         g, cur0, cur1 = entry
