@@ -27,7 +27,7 @@
 
 #include "at_seirm.h"
 
-#define NT_MAX 512                  // max threads per CTA (16 warps); the host may launch fewer warps
+#define NT_MAX 640                  // max threads per CTA (20 warps); the host may launch fewer warps
 #define MAXG 8                      // max gather tasks per scheduling group
 #define FX_SCALE 4294967296.0       // 2^32 fixed point for the daily sums
 
@@ -560,10 +560,13 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
                         w2 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.z >> 3) & hmask));
                         w3 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.w >> 3) & hmask));
                     }
-                    const uint32_t b = ((w0 >> (c.x & 31)) & 1u) | (((w1 >> (c.y & 31)) & 1u) << 1) |
-                                       (((w2 >> (c.z & 31)) & 1u) << 2) | (((w3 >> (c.w & 31)) & 1u) << 3);
-                    h |= b << (4 * q);
+                    // funnel shift: each test result enters h at bit 31 and moves down, one instruction per edge
+                    h = __funnelshift_r(h, w0 >> (c.x & 31), 1);
+                    h = __funnelshift_r(h, w1 >> (c.y & 31), 1);
+                    h = __funnelshift_r(h, w2 >> (c.z & 31), 1);
+                    h = __funnelshift_r(h, w3 >> (c.w & 31), 1);
                 }
+                h >>= (32 - RL);                                        // edge j of this lane's run is bit j
                 {   // drop the bits of positions past the end of the chunk
                     const int mine = n - lane * RL;
                     h &= mine >= RL ? 0xffffffffu >> (32 - RL) : (mine <= 0 ? 0u : ((1u << mine) - 1u));
@@ -902,7 +905,7 @@ int64_t at_seirm_workspace_bytes(void) { return (int64_t)WS_BYTES; }
 
 int64_t at_seirm_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edges_per_chunk, int32_t warps) {
     if (device_props()) return 0;
-    if (warps < 1) warps = 16;
+    if (warps < 1) warps = NT_MAX / 32;
     int64_t bytes = (int64_t)g_smem_optin - (int64_t)table_smem(n_sfs, n_lam_gamma) - (int64_t)warps * warp_smem_bytes(edges_per_chunk) - 2048;
     if (bytes < 4096) return 0;
     return ((bytes * 8) / 1024) * 1024;
@@ -945,7 +948,7 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     const size_t tables = table_smem(model->n_sfs, model->n_lam_gamma);
     at_seirm_launch al = a;
     al.edges_per_chunk = epc;
-    int warps = a.warps_per_cta > 0 ? a.warps_per_cta : 16;
+    int warps = a.warps_per_cta > 0 ? a.warps_per_cta : NT_MAX / 32;
     if (warps > NT_MAX / 32) warps = NT_MAX / 32;
     int bm_words = 0;
     const bool hashed = do_trans && a.hash_words > 0;

@@ -141,7 +141,7 @@ def _ptr(t, dtype=None, name="tensor"):
 
 class SeirmEngine:
     def __init__(self, graph, spec: SeirmSpec, process_group=None, grid=0, code_len=None, block_size=None,
-                 tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0, hashed=None, hash_words=None, hash_min_warps=16, symmetric=None):
+                 tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0, hashed=None, hash_words=None, hash_min_warps=20, symmetric=None):
         """graph: ContactGraph (plain CSR, re-blocked here) or a prebuilt BlockedGraph.  block_size: sources
         per column block (default: the largest that fits the shared-memory bitmap, i.e. as few blocks as
         possible); code_len: length of the code/bitmap arrays (multi-GPU: world_size equal slices)."""
