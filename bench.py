@@ -318,7 +318,23 @@ def ours(args):
         ms = timed(lambda: episode(False, False), args.steps)
         clocks = sampler.stop()
         launches = args.steps * engine.kernels_per_episode(T)
-        fwd_ms = None
+        # forward-only time of this rank's episode -> average step-kernel launch duration (max over ranks)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fwd = []
+        for _ in range(max(4, args.steps // 2)):
+            for k in ("stage", "next_stage_time", "infected_time"):
+                getattr(st, k).copy_(getattr(st0, k))
+            st.daily_infected.zero_(); st.daily_deaths.zero_()
+            barrier()
+            f0.record()
+            engine.run_episode(st, r_steps, m_val, T, NoiseSpec(seed=SEED, isolation="soft"), want_grad=True,
+                               cuda_graph=engine.code_hdl is not None)
+            f1.record()
+            torch.cuda.synchronize()
+            fwd.append(f0.elapsed_time(f1))
+        fwd_t = torch.tensor([statistics.median(fwd[1:])], device=dev)
+        dist.all_reduce(fwd_t, op=dist.ReduceOp.MAX)
+        fwd_ms = float(fwd_t.item())
         for _ in range(args.warmup):
             episode(True, True)
         ms_e2e = timed(lambda: episode(True, True), args.steps)
@@ -349,8 +365,9 @@ def ours(args):
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "kernel": "seirm_kernel<MODE_HASHED>", "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": launch_ms,
-                    "note": "bytes = N*(4*d+41): SURVEY 8d forward 4d+45, in-kernel noise (-8), dne_dr save (+4); "
-                            "launch time = forward CUDA-graph time / 21 (includes the one encode launch)"}
+                    "note": "bytes = (N/n_gpus)*(4*d+41) per GPU: SURVEY 8d forward 4d+45, in-kernel noise (-8), dne_dr save (+4); "
+                            "launch time = forward episode time / 21 (includes the encode launch and, on several GPUs, "
+                            "the per-step halo exchange)"}
     line = {
         "metric": "agent-steps/s fwd+bwd, 8.4M-agent SEIRM", "value": value, "unit": "agent-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
