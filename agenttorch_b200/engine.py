@@ -325,7 +325,10 @@ class SeirmEngine:
 
     def kernels_per_episode(self, num_steps, backward=True):
         full = nat.DO_TRANSMISSION | nat.DO_PROGRESSION | nat.DO_ENCODE
-        return self._kernels_of(nat.DO_ENCODE | nat.DO_INIT) + num_steps * self._kernels_of(full) + (1 if backward else 0)
+        n = self._kernels_of(nat.DO_ENCODE | nat.DO_INIT) + num_steps * self._kernels_of(full) + (1 if backward else 0)
+        if self.pg is not None:
+            n += num_steps + 1               # one pull / rebuild kernel per halo exchange
+        return n
 
     # ------------------------------------------------------------------------ halo exchange
     def exchange(self, buf_index):
