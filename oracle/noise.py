@@ -53,3 +53,10 @@ def isolation_decision(seed, step, agent_ids, mode="soft", p_isolate=0.3):
     if mode == "hard":
         return (w < np.float32(p_isolate)).astype(np.float32)
     raise ValueError(mode)
+
+
+def move_draw(seed, step, species, agent_ids):
+    """24-bit draw that picks a predator-prey agent's move: neighbour number (draw * n_neighbours) >> 24.
+    Species 0 = predator, 1 = prey; the species is bit 39 of the counter's agent field."""
+    ids = np.asarray(agent_ids, dtype=np.uint64) | (np.uint64(species) << np.uint64(39))
+    return (noise_u64(seed, step, ids) >> np.uint64(40)).astype(np.int64)

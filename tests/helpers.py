@@ -36,3 +36,28 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64).reshape(-1)
     b = np.asarray(b, dtype=np.float64).reshape(-1)
     return float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-30))
+
+
+# ------------------------------------------------------------------------------------ predator-prey
+PREDPREY_CASES = ["predprey_18x25", "predprey_18x25_work", "predprey_24x28", "predprey_18x25_starve", "predprey_40x40_work"]
+
+
+def load_predprey_golden(name):
+    """Fixture written by oracle/ref_harness/make_golden_predprey.py (outputs of the real reference)."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    g["seed"], g["steps"], g["n_cells"] = int(g["seed"]), int(g["steps"]), int(g["n_cells"])
+    g["adjacency"] = np.unpackbits(g["adjacency"], axis=1)[:, : g["n_cells"]]
+    g["update_outputs"] = [str(s) for s in g["update_outputs"]]
+    return g
+
+
+def predprey_port_from_golden(g, use_adjacency=False):
+    from oracle.predprey_port import PredPreyConstants, PredPreyPort
+
+    pw, yw, pn, gn, rt = (float(v) for v in g["consts"])
+    consts = PredPreyConstants(int(g["bounds"][0]), int(g["bounds"][1]), pw, yw, pn, gn, rt, g["update_outputs"])
+    return PredPreyPort(consts, g["init_pred_pos"], g["init_pred_energy"], g["init_prey_pos"], g["init_prey_energy"],
+                        g["init_growth_stage"], g["init_growth_countdown"], adjacency=g["adjacency"] if use_adjacency else None)
+
+
+PREDPREY_KEYS = ("pred_pos", "pred_energy", "prey_pos", "prey_energy", "growth_stage", "growth_countdown")
