@@ -76,7 +76,7 @@ def nvcc_command(out_path=LIB_PATH, extra=()):
 def build_library(force=False, verbose=False):
     """Compile csrc/at_seirm.cu for sm_100a into agenttorch_b200/lib/ (nvcc cross-compiles without a GPU)."""
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    deps = [SRC_PATH, os.path.join(INCLUDE_DIR, "at_seirm.h")]
+    deps = [SRC_PATH, os.path.join(INCLUDE_DIR, "at_seirm.h"), os.path.join(_PKG, "csrc", "at_noise.cuh")]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
         return LIB_PATH

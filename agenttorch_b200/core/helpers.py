@@ -147,6 +147,28 @@ def read_config(config_file, register_resolvers=True):
         raise ValueError(f"Could not load config file. Please check path and file type. Error message is {str(e)}")
 
 
+def read_from_file(shape, params):
+    """CSV (with a header row) -> tensor of the file's own dtype (general.py:132-143)."""
+    import pandas as pd
+
+    file_path = params["file_path"]
+    if not str(file_path).endswith("csv"):
+        raise ValueError(f"read_from_file: only csv files are supported, got {file_path}")
+    values = pd.read_csv(file_path).values
+    assert values.shape == tuple(shape), f"read_from_file: shape mismatch {values.shape} vs {tuple(shape)} for {file_path}"
+    return torch.from_numpy(values.copy())
+
+
+def grid_network(params):
+    """`grid` network helper (core/helpers/environment.py:6-9).  The reference materialises the dense
+    (cells x cells) adjacency matrix of nx.grid_graph(dim=shape); that is 2.8e14 entries for a 4096x4096 grid, so
+    this returns the same lattice in implicit form (agenttorch_b200.predprey.GridLattice; `.to_dense()` gives the
+    reference's matrix for small grids)."""
+    from agenttorch_b200.predprey import GridLattice
+
+    return None, GridLattice(params["shape"])
+
+
 def memory_checkpoint(name):
     allocated, reserved = torch.cuda.memory_allocated(), torch.cuda.memory_reserved()
     print("Checkpoint: ", name, " Allocated: ", allocated, " Reserved: ", reserved)

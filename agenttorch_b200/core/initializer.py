@@ -35,6 +35,8 @@ class Initializer(nn.Module):
         """Literal `value:` -> tensor; float32 whatever the YAML dtype says (initializer.py:78-116)."""
         if type(src_val) == str:
             return src_val
+        if isinstance(shape, int):            # predator_prey/config.yaml:31 writes `shape: 2`
+            shape = [shape]
         if type(src_val) == list:
             src = torch.tensor(src_val)
             if shape and list(src.shape) != list(shape):
@@ -102,8 +104,10 @@ class Initializer(nn.Module):
                 continue
             for name, spec in nets.items():
                 graph, adjacency = self.registry.network_helpers[spec["type"]](spec["arguments"])
-                if len(adjacency) == 2:
+                if isinstance(adjacency, (tuple, list)) and len(adjacency) == 2:
                     adjacency = (self._to_device(adjacency[0]), self._to_device(adjacency[1]))
+                elif torch.is_tensor(adjacency):
+                    adjacency = self._to_device(adjacency)
                 self.networks[itype][name] = {"graph": graph, "adjacency_matrix": adjacency}
 
     def simulator(self):

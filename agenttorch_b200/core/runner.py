@@ -19,6 +19,10 @@ from .helpers import to_cpu
 from .initializer import Initializer
 
 
+# callables `(runner) -> callable(num_steps) | None`, appended by the model packages that ship a fused path
+FUSED_PLANNERS = []
+
+
 class _LazyEnvironment(dict):
     """Environment view of an intermediate (step, substep) of a fused episode: the (T,) series are masked to
     the steps already simulated when they are read."""
@@ -64,6 +68,8 @@ class Runner(nn.Module):
                 "environment": dict(state.get("environment", {}))}
 
     def init(self):
+        self._plan_cache = None               # the substep modules are rebuilt: fused plans must be re-derived
+        self._pp_plan = None
         self.initializer.initialize()
         self.state = self.initializer.state
         self.state_trajectory = [[self._snapshot(self.state)]]
@@ -110,6 +116,11 @@ class Runner(nn.Module):
         plan = self._fused_plan() if self._fused_enabled else None
         if plan is not None:
             return self._step_fused(num_steps, plan)
+        if self._fused_enabled:
+            for planner in FUSED_PLANNERS:     # other models served by one fused launch sequence per step() call
+                fused_step = planner(self)
+                if fused_step is not None:
+                    return fused_step(num_steps)
         return self._step_generic(num_steps)
 
     def _step_generic(self, num_steps):

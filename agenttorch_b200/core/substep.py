@@ -22,7 +22,8 @@ class _SubstepBase(nn.Module, ABC):
         self.learnable_args, self.fixed_args = arguments["learnable"], arguments["fixed"]
         if self.learnable_args:
             self.learnable_args = nn.ParameterDict(self.learnable_args)
-        if self.config["simulation_metadata"]["calibration"] == True:  # noqa: E712 (reference semantics)
+        # config may be None when a substep is built stand-alone (the reference's tests/test_vmap_substeps.py do so)
+        if self.config is not None and self.config["simulation_metadata"]["calibration"] == True:  # noqa: E712
             for key, value in self.learnable_args.items():
                 setattr(self, f"calibrate_{key}", value.detach().clone().requires_grad_(True))
         self.args = {**self.fixed_args, **self.learnable_args}

@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include "at_seirm.h"
+#include "at_noise.cuh"
 
 #define NT_MAX 640                  // max threads per CTA (20 warps); the host may launch fewer warps
 #define MAXG 8                      // max gather tasks per scheduling group
@@ -57,15 +58,7 @@ static int fail(const char* fmt, const char* detail) {
 }
 
 // ------------------------------------------------------------------------------------------ noise
-// SplitMix64 output number ((step << 40) | agent) of the stream seeded `seed`
-// (numpy restatement: oracle/noise.py, torch restatement: agenttorch_b200/noise.py).
-__host__ __device__ __forceinline__ uint64_t at_noise_u64(uint64_t seed, uint32_t step, uint64_t agent) {
-    uint64_t z = (((uint64_t)step << 40) | agent) + 1ull;
-    z = z * 0x9E3779B97F4A7C15ull + seed;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
+// at_noise_u64: see at_noise.cuh
 __host__ __device__ __forceinline__ float at_u_exposure(uint64_t z) { return (float)(z >> 40) * (1.0f / 16777216.0f); }
 __host__ __device__ __forceinline__ float at_u_isolation(uint64_t z) {
     return (float)((z >> 8) & 0xFFFFFFull) * (1.0f / 16777216.0f);

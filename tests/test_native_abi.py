@@ -54,3 +54,52 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="CUDA"):
         SeirmEngine(g, SeirmSpec())
     assert not torch.cuda.is_available() or True
+
+
+# ------------------------------------------------------------------------------- libat_predprey.so
+@pytest.fixture(scope="module")
+def built_pp():
+    from agenttorch_b200 import _native_pp
+
+    _native_pp.build_library()
+    return _native_pp.lib()
+
+
+def test_predprey_header_symbols_are_exported(built_pp):
+    from agenttorch_b200 import _native_pp
+
+    header = open(os.path.join(ROOT, "include", "at_predprey.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(at_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert declared == set(_native_pp.EXPORTS), declared ^ set(_native_pp.EXPORTS)
+    handle = ctypes.CDLL(_native_pp.LIB_PATH)
+    for name in declared:
+        assert getattr(handle, name) is not None
+    assert built_pp.at_pp_sizeof_launch() == ctypes.sizeof(_native_pp.PPLaunch)
+    assert built_pp.at_pp_sizeof_model() == ctypes.sizeof(_native_pp.PPModel)
+    assert f"#define AT_PP_ABI_VERSION {_native_pp.ABI_VERSION}" in header
+    assert built_pp.at_pp_bitmap_words(450) == 16 and built_pp.at_pp_bitmap_words(4096 * 4096) == 4096 * 128
+
+
+def test_predprey_bad_arguments_return_errors(built_pp):
+    from agenttorch_b200 import _native_pp
+
+    assert built_pp.at_pp_step(None, None, None) != 0
+    assert b"null" in built_pp.at_pp_last_error()
+    m, a = _native_pp.PPModel(), _native_pp.PPLaunch()
+    m.abi_version, a.abi_version = _native_pp.ABI_VERSION, _native_pp.ABI_VERSION + 1
+    assert built_pp.at_pp_step(ctypes.byref(m), ctypes.byref(a), None) != 0
+    assert b"ABI" in built_pp.at_pp_last_error()
+    a.abi_version = _native_pp.ABI_VERSION
+    assert built_pp.at_pp_step(ctypes.byref(m), ctypes.byref(a), None) != 0           # n_cells == 0
+    assert b"n_cells" in built_pp.at_pp_last_error()
+
+
+def test_predprey_no_cpu_fallback():
+    import torch
+
+    from agenttorch_b200.predprey import PredPreyEngine, PredPreySpec, pack_cells
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        PredPreyEngine(PredPreySpec(4, 4, 16, 4), "cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pack_cells(torch.zeros(3, 2, dtype=torch.int64), 4, 16)
