@@ -14,11 +14,12 @@ LIB_PATH = os.path.join(_PKG, "lib", "libat_predprey.so")
 SRC_PATH = os.path.join(_PKG, "csrc", "at_predprey.cu")
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 
-ABI_VERSION = 1
-OCCUPANCY, EAT, HUNT, MOVE, EAT_APPLY, GROW, CLEAR = 1, 2, 4, 8, 16, 32, 64
+ABI_VERSION = 2
+OCCUPANCY, EAT, HUNT, MOVE, EAT_APPLY, GROW, CLEAR, EAT_IMPLICIT = 1, 2, 4, 8, 16, 32, 64, 128
+INFO_GROWN, INFO_EATEN = 1, 2
 
 EXPORTS = [
-    "at_pp_abi_version", "at_pp_last_error", "at_pp_sizeof_model", "at_pp_sizeof_launch", "at_pp_bitmap_words",
+    "at_pp_abi_version", "at_pp_last_error", "at_pp_sizeof_model", "at_pp_sizeof_launch", "at_pp_info_bytes",
     "at_pp_step", "at_pp_pack_cells", "at_pp_unpack_cells", "at_pp_pack_stage", "at_pp_unpack_stage", "at_pp_census",
 ]
 
@@ -42,9 +43,8 @@ class PPLaunch(ctypes.Structure):
         ("n_pred", ctypes.c_int64), ("n_prey", ctypes.c_int64),
         ("pred_cell", ctypes.c_void_p), ("pred_energy", ctypes.c_void_p),
         ("prey_cell", ctypes.c_void_p), ("prey_energy", ctypes.c_void_p),
-        ("grown", ctypes.c_void_p), ("countdown", ctypes.c_void_p), ("eaten", ctypes.c_void_p),
-        ("occ_pred_in", ctypes.c_void_p), ("occ_prey_in", ctypes.c_void_p),
-        ("occ_pred_out", ctypes.c_void_p), ("occ_prey_out", ctypes.c_void_p),
+        ("info", ctypes.c_void_p), ("countdown", ctypes.c_void_p),
+        ("occ_in", ctypes.c_int32), ("occ_out", ctypes.c_int32),
         ("nbr_ptr", ctypes.c_void_p), ("nbr_idx", ctypes.c_void_p),
         ("grid", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
@@ -93,8 +93,8 @@ def lib():
         L.at_pp_last_error.restype = ctypes.c_char_p
         L.at_pp_sizeof_model.restype = i64
         L.at_pp_sizeof_launch.restype = i64
-        L.at_pp_bitmap_words.restype = i64
-        L.at_pp_bitmap_words.argtypes = [i64]
+        L.at_pp_info_bytes.restype = i64
+        L.at_pp_info_bytes.argtypes = [i64]
         L.at_pp_step.restype = ctypes.c_int
         L.at_pp_step.argtypes = [ctypes.POINTER(PPModel), ctypes.POINTER(PPLaunch), vp]
         L.at_pp_pack_cells.restype = ctypes.c_int

@@ -3,19 +3,19 @@
 // The reference walks Python lists: for every agent the row of a dense (cells x cells) adjacency matrix
 // (substeps/move.py:24-46), for every eatable / target position a comparison against ALL agents
 // (eat.py:80-89, hunt.py:70-80).  Here an agent is (cell, energy) and every "is anybody / is grown grass at this
-// cell" question is one bit of a cell-indexed bitmap (2 MB for 16.8 M cells: L2-resident), so a step is two
-// streaming passes — agents (16 B per agent) and cells (8 or 16 B per cell) — with random single-bit lookups
-// served by L2.  Bits are set with atomicOr (bitwise OR: order-independent), so the results are deterministic.
-// HBM-bound; no tensor cores.
+// cell" question is a bit of the cell's INFO byte (16.8 MB for 4096 x 4096 cells: L2-resident), so a step is two
+// streaming passes — agents (16 B per agent) and cells (1 + 4 or 8 B per cell, read and written) — with ONE random
+// byte lookup and at most two random bit-sets per agent, served by L2.  Bits are set with atomicOr (bitwise OR:
+// order-independent), so the results are deterministic.  No tensor cores.
 //
 //   pp_agent_kernel   thread <-> agent: EAT (prey on grown grass gain nutrition, mark `eaten`), HUNT (prey on a
 //                     cell with a predator -> energy 0; predator on a cell with a prey gains nutrition), MOVE
 //                     (counter-hash draw -> neighbour cell if energy > 0; energy -= work; mark occupancy of the
 //                     new cell).  Fusing [EAT, HUNT](t) with MOVE(t+1) is legal: MOVE only needs the agent's own
 //                     energy, and writes the OTHER pair of occupancy bitmaps.
-//   pp_cell_kernel    lane <-> cell, warp <-> bitmap word: eaten -> countdown reset (float32-rounded increment, as
-//                     the reference's float32 mask does, eat.py:72,99), GROW, and clearing of the finished step's
-//                     occupancy words.
+//   pp_cell_kernel    thread <-> 4 cells (one info word + one countdown vector): eaten -> countdown reset
+//                     (float32-rounded increment, as the reference's float32 mask does, eat.py:72,99), GROW, and
+//                     clearing of the finished step's occupancy bits.
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -44,8 +44,18 @@ static int default_grid() {
     return sms * (2048 / PP_THREADS);          // full occupancy, one wave
 }
 
-__device__ __forceinline__ bool test_bit(const uint32_t* __restrict__ bm, int cell) {
-    return (__ldg(bm + (cell >> 5)) >> (cell & 31)) & 1u;
+#define PP_GROWN 1u
+#define PP_EATEN 2u
+#define PP_OCC_PRED(parity) (4u << (2 * (parity)))
+#define PP_OCC_PREY(parity) (8u << (2 * (parity)))
+
+// The info byte of a cell, read from L2 (other threads of the same launch OR bits into neighbouring positions of the
+// byte with atomics; the bits tested here are not written by this launch, so any snapshot of the byte is good).
+__device__ __forceinline__ uint32_t cell_info(const uint8_t* info, int cell) {
+    return (uint32_t)__ldcg(info + cell);          // measured: .cg / .nc / default loads all time the same here
+}
+__device__ __forceinline__ void mark_cell(uint8_t* info, int cell, uint32_t bits) {
+    atomicOr(reinterpret_cast<uint32_t*>(info) + (cell >> 2), bits << (8 * (cell & 3)));     // OR: order-independent
 }
 
 // neighbour number (draw * count) >> 24 of the ascending list [k - width, k - 1, k + 1, k + width] (those that exist)
@@ -68,7 +78,7 @@ pp_occupancy_kernel(at_pp_launch a)
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
         const bool prey = idx >= a.n_pred;
         const int cell = prey ? a.prey_cell[idx - a.n_pred] : a.pred_cell[idx];
-        atomicOr((prey ? a.occ_prey_in : a.occ_pred_in) + (cell >> 5), 1u << (cell & 31));
+        mark_cell(a.info, cell, prey ? PP_OCC_PREY(a.occ_in) : PP_OCC_PRED(a.occ_in));
     }
 }
 
@@ -79,6 +89,7 @@ pp_agent_kernel(at_pp_model m, at_pp_launch a)
     const int64_t n = a.n_pred + a.n_prey;
     const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
     const uint32_t t = (uint32_t)(a.t_move + (a.t_ptr ? *a.t_ptr : 0));
+    const bool look = (flags & (AT_PP_EAT | AT_PP_HUNT)) != 0;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
         const bool prey = idx >= a.n_pred;
         const int64_t i = prey ? idx - a.n_pred : idx;
@@ -88,14 +99,15 @@ pp_agent_kernel(at_pp_model m, at_pp_launch a)
         const float e0 = *energy_p;
         int cell = cell0;
         float e = e0;
+        const uint32_t here = look ? cell_info(a.info, cell) : 0u;                  // ONE random access answers everything
         if (prey) {
-            if ((flags & AT_PP_EAT) && test_bit(a.grown, cell)) {                     // eat.py:41, :93-97
+            if ((flags & AT_PP_EAT) && (here & PP_GROWN)) {                           // eat.py:41, :93-97
                 e = __fadd_rn(e, m.grass_nutrition);
-                atomicOr(a.eaten + (cell >> 5), 1u << (cell & 31));
+                if (!(flags & AT_PP_EAT_IMPLICIT) && !(here & PP_EATEN)) mark_cell(a.info, cell, PP_EATEN);
             }
-            if ((flags & AT_PP_HUNT) && test_bit(a.occ_pred_in, cell)) e = 0.0f;       // hunt.py:81
+            if ((flags & AT_PP_HUNT) && (here & PP_OCC_PRED(a.occ_in))) e = 0.0f;      // hunt.py:81
         } else {
-            if ((flags & AT_PP_HUNT) && test_bit(a.occ_prey_in, cell)) e = __fadd_rn(e, m.prey_nutrition);   // hunt.py:83-86
+            if ((flags & AT_PP_HUNT) && (here & PP_OCC_PREY(a.occ_in))) e = __fadd_rn(e, m.prey_nutrition);   // hunt.py:83-86
         }
         if (flags & AT_PP_MOVE) {
             if (e > 0.0f) {                                                         // move.py:89
@@ -110,55 +122,74 @@ pp_agent_kernel(at_pp_model m, at_pp_launch a)
             }
             if (prey ? m.apply_prey_work : m.apply_pred_work)                       // move.py:112-116
                 e = __fadd_rn(e, -(prey ? m.prey_work : m.pred_work));
-            uint32_t* occ = prey ? a.occ_prey_out : a.occ_pred_out;
-            if (occ != nullptr) atomicOr(occ + (cell >> 5), 1u << (cell & 31));
+            if (a.occ_out >= 0) mark_cell(a.info, cell, prey ? PP_OCC_PREY(a.occ_out) : PP_OCC_PRED(a.occ_out));
         }
         if (cell != cell0) *cell_p = cell;
         if (e != e0) *energy_p = e;
     }
 }
 
+// thread <-> 4 consecutive cells: one 32-bit info word + one 16/32-byte countdown vector
 template <typename T>
 __global__ void __launch_bounds__(PP_THREADS)
 pp_cell_kernel(at_pp_model m, at_pp_launch a)
 {
     const int flags = a.flags;
-    const int lane = threadIdx.x & 31;
-    const int64_t n_words = (m.n_cells + 31) >> 5;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_quads = (m.n_cells + 3) >> 2;
+    uint32_t* info4 = reinterpret_cast<uint32_t*>(a.info);
     T* cd = reinterpret_cast<T*>(a.countdown);
-    for (int64_t w = warp0; w < n_words; w += n_warps) {
-        const uint32_t ew = (flags & AT_PP_EAT_APPLY) ? a.eaten[w] : 0u;
-        if ((flags & AT_PP_GROW) || ew != 0u) {
-            const int64_t cell = w * 32 + lane;
-            const bool in = cell < m.n_cells;
-            bool g = (a.grown[w] >> lane) & 1u;
-            const bool eat = (ew >> lane) & 1u;
-            if (in && ((flags & AT_PP_GROW) || eat)) {
-                T c = cd[cell];
-                if (eat) {
+    const uint32_t clear_mask = (flags & AT_PP_CLEAR) ? (PP_OCC_PRED(a.occ_in) | PP_OCC_PREY(a.occ_in)) * 0x01010101u : 0u;
+    const bool grow = (flags & AT_PP_GROW) != 0, apply = (flags & AT_PP_EAT_APPLY) != 0;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t w0 = info4[q];
+        uint32_t w = w0 & ~clear_mask;
+        // eaten cells, as PP_EATEN bits: marked by EAT, or (EAT_IMPLICIT) grown cells on which a prey stands
+        const uint32_t eaten = !apply ? 0u
+            : (flags & AT_PP_EAT_IMPLICIT) ? ((w0 & (PP_GROWN * 0x01010101u)) << 1) & ((w0 & (PP_OCC_PREY(a.occ_in) * 0x01010101u)) >> (2 + 2 * a.occ_in))
+                                           : (w0 & (PP_EATEN * 0x01010101u));
+        if (grow || eaten) {
+            const int64_t c0 = q * 4;
+            const bool full = c0 + 4 <= m.n_cells;
+            T c[4];
+            if (full) {
+                if constexpr (sizeof(T) == 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(cd + c0);
+                    c[0] = (T)v.x; c[1] = (T)v.y; c[2] = (T)v.z; c[3] = (T)v.w;
+                } else {
+                    const double2 v0 = *reinterpret_cast<const double2*>(cd + c0), v1 = *reinterpret_cast<const double2*>(cd + c0 + 2);
+                    c[0] = (T)v0.x; c[1] = (T)v0.y; c[2] = (T)v1.x; c[3] = (T)v1.y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[j] = c0 + j < m.n_cells ? cd[c0 + j] : (T)1;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t sh = 8 * j;
+                if ((eaten >> sh) & PP_EATEN) {
                     // countdown_mask[node] = regrowth_time - countdown[node] lives in a float32 tensor (eat.py:72,99)
-                    const float reset = (float)((T)m.regrowth_time - c);
-                    c = c + (T)reset;
-                    g = false;                                                      // stage 1 + (-1), eat.py:98,104
+                    const float reset = (float)((T)m.regrowth_time - c[j]);
+                    c[j] = c[j] + (T)reset;
+                    w &= ~((PP_GROWN | PP_EATEN) << sh);                            // stage 1 + (-1), eat.py:98,104
                 }
-                if (flags & AT_PP_GROW) {                                           // grow.py:34-40
-                    c = c - (T)1;
-                    g = c <= (T)0;
+                if (grow) {                                                         // grow.py:34-40
+                    c[j] = c[j] - (T)1;
+                    w = (w & ~(PP_GROWN << sh)) | ((c[j] <= (T)0 && c0 + j < m.n_cells) ? (PP_GROWN << sh) : 0u);
                 }
-                cd[cell] = c;
             }
-            const uint32_t word = __ballot_sync(0xffffffffu, in && g);
-            if (lane == 0) {
-                a.grown[w] = word;
-                if (ew != 0u) a.eaten[w] = 0u;
+            if (full) {
+                if constexpr (sizeof(T) == 4) {
+                    *reinterpret_cast<float4*>(cd + c0) = make_float4((float)c[0], (float)c[1], (float)c[2], (float)c[3]);
+                } else {
+                    *reinterpret_cast<double2*>(cd + c0) = make_double2((double)c[0], (double)c[1]);
+                    *reinterpret_cast<double2*>(cd + c0 + 2) = make_double2((double)c[2], (double)c[3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (c0 + j < m.n_cells) cd[c0 + j] = c[j];
             }
         }
-        if ((flags & AT_PP_CLEAR) && lane == 0) {
-            a.occ_pred_in[w] = 0u;
-            a.occ_prey_in[w] = 0u;
-        }
+        if (w != w0) info4[q] = w;
     }
 }
 
@@ -185,25 +216,20 @@ pp_unpack_cells_kernel(const int32_t* __restrict__ cells, int64_t n, int max_y, 
 }
 
 __global__ void __launch_bounds__(PP_THREADS)
-pp_pack_stage_kernel(const void* stage, int dtype, int64_t n_cells, uint32_t* grown)
+pp_pack_stage_kernel(const void* stage, int dtype, int64_t n_cells, int64_t n_bytes, uint8_t* info)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t n_words = (n_cells + 31) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += n_warps) {
-        const int64_t cell = w * 32 + lane;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_bytes; c += (int64_t)gridDim.x * blockDim.x) {
         bool g = false;
-        if (cell < n_cells) g = dtype == 0 ? ((const int64_t*)stage)[cell] == 1 : ((const float*)stage)[cell] == 1.0f;
-        const uint32_t word = __ballot_sync(0xffffffffu, g);
-        if (lane == 0) grown[w] = word;
+        if (c < n_cells) g = dtype == 0 ? ((const int64_t*)stage)[c] == 1 : ((const float*)stage)[c] == 1.0f;
+        info[c] = g ? (uint8_t)PP_GROWN : (uint8_t)0;
     }
 }
 
 __global__ void __launch_bounds__(PP_THREADS)
-pp_unpack_stage_kernel(const uint32_t* __restrict__ grown, int64_t n_cells, void* stage, int dtype)
+pp_unpack_stage_kernel(const uint8_t* __restrict__ info, int64_t n_cells, void* stage, int dtype)
 {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t g = (grown[c >> 5] >> (c & 31)) & 1u;
+        const uint32_t g = info[c] & PP_GROWN;
         if (dtype == 0) ((int64_t*)stage)[c] = g; else ((float*)stage)[c] = (float)g;
     }
 }
@@ -212,13 +238,14 @@ __global__ void __launch_bounds__(PP_THREADS)
 pp_census_kernel(at_pp_launch a, int64_t n_cells, unsigned long long* out)
 {
     const int64_t n = a.n_pred + a.n_prey;
-    const int64_t n_words = (n_cells + 31) >> 5;
+    const int64_t n_words = (n_cells + 3) >> 2;                    // padding bytes are never grown
     unsigned long long c0 = 0, c1 = 0, c2 = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
         if (idx < a.n_pred) c0 += a.pred_energy[idx] > 0.0f; else c1 += a.prey_energy[idx - a.n_pred] > 0.0f;
     }
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) c2 += __popc(a.grown[w]);
+    const uint32_t* info4 = reinterpret_cast<const uint32_t*>(a.info);
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) c2 += __popc(info4[w] & (PP_GROWN * 0x01010101u));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         c0 += __shfl_down_sync(0xffffffffu, c0, o);
@@ -251,7 +278,7 @@ int at_pp_abi_version(void) { return AT_PP_ABI_VERSION; }
 const char* at_pp_last_error(void) { return g_err; }
 int64_t at_pp_sizeof_model(void) { return (int64_t)sizeof(at_pp_model); }
 int64_t at_pp_sizeof_launch(void) { return (int64_t)sizeof(at_pp_launch); }
-int64_t at_pp_bitmap_words(int64_t n_cells) { return (((n_cells + 31) >> 5) + 3) & ~(int64_t)3; }
+int64_t at_pp_info_bytes(int64_t n_cells) { return (n_cells + 15) & ~(int64_t)15; }
 
 int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* stream)
 {
@@ -271,28 +298,26 @@ int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* strea
     if ((agent_flags || (flags & AT_PP_OCCUPANCY)) && n > 0 &&
         ((a.n_pred && (!a.pred_cell || !a.pred_energy)) || (a.n_prey && (!a.prey_cell || !a.prey_energy))))
         return fail("at_pp_step: %s", "agent arrays missing");
-    if ((flags & (AT_PP_EAT | AT_PP_EAT_APPLY)) && (!a.grown || !a.eaten)) return fail("at_pp_step: %s", "EAT needs grown + eaten bitmaps");
-    if ((flags & (AT_PP_HUNT | AT_PP_OCCUPANCY | AT_PP_CLEAR)) && (!a.occ_pred_in || !a.occ_prey_in))
-        return fail("at_pp_step: %s", "HUNT / OCCUPANCY / CLEAR need the occ_*_in bitmaps");
-    if ((flags & (AT_PP_EAT_APPLY | AT_PP_GROW)) && (!a.grown || !a.countdown)) return fail("at_pp_step: %s", "cell pass needs grown + countdown");
+    if ((flags & (AT_PP_OCCUPANCY | AT_PP_EAT | AT_PP_HUNT | AT_PP_EAT_APPLY | AT_PP_GROW | AT_PP_CLEAR)) && !a.info)
+        return fail("at_pp_step: %s", "info bytes missing");
+    if ((flags & AT_PP_MOVE) && a.occ_out >= 0 && !a.info) return fail("at_pp_step: %s", "MOVE with occ_out >= 0 needs the info bytes");
+    if ((flags & (AT_PP_HUNT | AT_PP_OCCUPANCY | AT_PP_CLEAR)) && (a.occ_in < 0 || a.occ_in > 1)) return fail("at_pp_step: %s", "occ_in must be 0 or 1");
+    if (a.occ_out > 1) return fail("at_pp_step: %s", "occ_out must be < 0, 0 or 1");
+    if ((flags & (AT_PP_EAT_APPLY | AT_PP_GROW)) && !a.countdown) return fail("at_pp_step: %s", "cell pass needs the countdown array");
+    if ((flags & AT_PP_EAT_IMPLICIT) && ((flags & (AT_PP_EAT | AT_PP_EAT_APPLY)) != (AT_PP_EAT | AT_PP_EAT_APPLY) || a.occ_in < 0 || a.occ_in > 1))
+        return fail("at_pp_step: %s", "EAT_IMPLICIT needs EAT and EAT_APPLY in the same call and a valid occ_in");
     if ((a.nbr_ptr == nullptr) != (a.nbr_idx == nullptr)) return fail("at_pp_step: %s", "nbr_ptr and nbr_idx go together");
 
-    if (flags & AT_PP_OCCUPANCY) {
-        const size_t bytes = (size_t)at_pp_bitmap_words(m.n_cells) * 4;
-        cudaError_t e = cudaMemsetAsync(a.occ_pred_in, 0, bytes, s);
-        if (e == cudaSuccess) e = cudaMemsetAsync(a.occ_prey_in, 0, bytes, s);
-        if (e != cudaSuccess) return fail("cudaMemsetAsync: %s", cudaGetErrorString(e));
-        if (n > 0) {
-            pp_occupancy_kernel<<<blocks_for(n, a.grid), PP_THREADS, 0, s>>>(a);
-            if (check("pp_occupancy_kernel launch")) return 1;
-        }
+    if ((flags & AT_PP_OCCUPANCY) && n > 0) {
+        pp_occupancy_kernel<<<blocks_for(n, a.grid), PP_THREADS, 0, s>>>(a);
+        if (check("pp_occupancy_kernel launch")) return 1;
     }
     if (agent_flags && n > 0) {
         pp_agent_kernel<<<blocks_for(n, a.grid), PP_THREADS, 0, s>>>(m, a);
         if (check("pp_agent_kernel launch")) return 1;
     }
     if (cell_flags) {
-        const int64_t threads = ((m.n_cells + 31) >> 5) * 32;
+        const int64_t threads = (m.n_cells + 3) >> 2;
         if (a.countdown_f64) pp_cell_kernel<double><<<blocks_for(threads, a.grid), PP_THREADS, 0, s>>>(m, a);
         else pp_cell_kernel<float><<<blocks_for(threads, a.grid), PP_THREADS, 0, s>>>(m, a);
         if (check("pp_cell_kernel launch")) return 1;
@@ -316,28 +341,29 @@ int at_pp_unpack_cells(const int32_t* cells, int64_t n, int32_t max_y, int64_t* 
     return check("pp_unpack_cells_kernel launch");
 }
 
-int at_pp_pack_stage(const void* stage, int32_t stage_dtype, int64_t n_cells, uint32_t* grown, void* stream)
+int at_pp_pack_stage(const void* stage, int32_t stage_dtype, int64_t n_cells, uint8_t* info, void* stream)
 {
-    if (n_cells <= 0 || !stage || !grown || (stage_dtype != 0 && stage_dtype != 1)) return fail("at_pp_pack_stage: %s", "bad arguments");
-    pp_pack_stage_kernel<<<blocks_for(((n_cells + 31) >> 5) * 32, 0), PP_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(stage, stage_dtype, n_cells, grown);
+    if (n_cells <= 0 || !stage || !info || (stage_dtype != 0 && stage_dtype != 1)) return fail("at_pp_pack_stage: %s", "bad arguments");
+    const int64_t n_bytes = at_pp_info_bytes(n_cells);
+    pp_pack_stage_kernel<<<blocks_for(n_bytes, 0), PP_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(stage, stage_dtype, n_cells, n_bytes, info);
     return check("pp_pack_stage_kernel launch");
 }
 
-int at_pp_unpack_stage(const uint32_t* grown, int64_t n_cells, void* stage, int32_t stage_dtype, void* stream)
+int at_pp_unpack_stage(const uint8_t* info, int64_t n_cells, void* stage, int32_t stage_dtype, void* stream)
 {
-    if (n_cells <= 0 || !stage || !grown || (stage_dtype != 0 && stage_dtype != 1)) return fail("at_pp_unpack_stage: %s", "bad arguments");
-    pp_unpack_stage_kernel<<<blocks_for(n_cells, 0), PP_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(grown, n_cells, stage, stage_dtype);
+    if (n_cells <= 0 || !stage || !info || (stage_dtype != 0 && stage_dtype != 1)) return fail("at_pp_unpack_stage: %s", "bad arguments");
+    pp_unpack_stage_kernel<<<blocks_for(n_cells, 0), PP_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(info, n_cells, stage, stage_dtype);
     return check("pp_unpack_stage_kernel launch");
 }
 
 int at_pp_census(const at_pp_launch* launch, int64_t n_cells, int64_t* out3, void* stream)
 {
-    if (!launch || !out3 || !launch->grown) return fail("at_pp_census: %s", "bad arguments");
+    if (!launch || !out3 || !launch->info) return fail("at_pp_census: %s", "bad arguments");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const cudaError_t e = cudaMemsetAsync(out3, 0, 24, s);
     if (e != cudaSuccess) return fail("cudaMemsetAsync: %s", cudaGetErrorString(e));
     const int64_t n = launch->n_pred + launch->n_prey;
-    const int64_t work = n > ((n_cells + 31) >> 5) ? n : ((n_cells + 31) >> 5);
+    const int64_t work = n > ((n_cells + 3) >> 2) ? n : ((n_cells + 3) >> 2);
     pp_census_kernel<<<blocks_for(work, 0), PP_THREADS, 0, s>>>(*launch, n_cells, reinterpret_cast<unsigned long long*>(out3));
     return check("pp_census_kernel launch");
 }

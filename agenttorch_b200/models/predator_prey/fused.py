@@ -141,11 +141,11 @@ class _FusedPredPrey:
             yc, f1 = pack_cells(fixed["prey_pos"], spec.max_y, spec.n_cells)
             if int((f0 | f1).item()):
                 raise ValueError("agent coordinates outside the grid (cell = max_y * x + y must be in [0, n_cells))")
-            grown = pack_stage(stage, spec.n_cells)
+            info = pack_stage(stage, spec.n_cells)
             if self.st is not None and self.st.pred_cell.shape == pc.shape and self.st.prey_cell.shape == yc.shape:
-                self.st.pred_cell.copy_(pc); self.st.prey_cell.copy_(yc); self.st.grown.copy_(grown)     # keep graph pointers
+                self.st.pred_cell.copy_(pc); self.st.prey_cell.copy_(yc); self.st.info.copy_(info)       # keep graph pointers
             else:
-                self.st = PredPreyState(pc, None, yc, None, grown, None)
+                self.st = PredPreyState(pc, None, yc, None, info, None)
         self.st.pred_energy, self.st.prey_energy = fixed["pred_energy"].view(-1), fixed["prey_energy"].view(-1)
         self.st.countdown = cd.view(-1)
         return fixed, stage
@@ -160,7 +160,7 @@ class _FusedPredPrey:
             m.calls = t0 + int(num_steps)
         unpack_cells(self.st.pred_cell, self.spec.max_y, out=fixed["pred_pos"])
         unpack_cells(self.st.prey_cell, self.spec.max_y, out=fixed["prey_pos"])
-        unpack_stage(self.st.grown, self.spec.n_cells, out=stage.view(-1, 1))
+        unpack_stage(self.st.info, self.spec.n_cells, out=stage.view(-1, 1))
         self._seen = [(x, x._version) for x in (fixed["pred_pos"], fixed["prey_pos"], stage)]
         state["current_step"] = int(num_steps) - 1
         state["current_substep"] = "0"

@@ -3,7 +3,7 @@ import torch
 
 from agenttorch_b200.core.registry import Registry
 from agenttorch_b200.core.substep import SubstepAction, SubstepTransition
-from agenttorch_b200.predprey import PredPreyState, bitmap_words, pack_cells, pack_stage, unpack_stage
+from agenttorch_b200.predprey import PredPreyState, info_bytes, pack_cells, unpack_stage
 
 from ..context import engine_for, get_var, require_cuda, spec_from_bounds
 
@@ -31,13 +31,10 @@ class MaskedPositions:
         return iter(self.rows())
 
 
-def cells_bitmap(position_list, max_y, n_cells, device):
-    """Bitmap of the cells named by an explicit list of [x, y] positions."""
+def listed_cells(position_list, max_y, n_cells, device):
+    """Cells named by an explicit list of [x, y] positions (int64 tensor)."""
     pos = torch.stack([torch.as_tensor(p) for p in position_list]).to(device=device, dtype=torch.int64)
-    cells, flag = pack_cells(pos, max_y, n_cells)
-    mark = torch.zeros(bitmap_words(n_cells) * 32, dtype=torch.float32, device=device)
-    mark[cells.to(torch.int64)] = 1.0
-    return pack_stage(mark[:n_cells], n_cells)
+    return pack_cells(pos, max_y, n_cells)[0].to(torch.int64)
 
 
 @Registry.register_substep("find_eatable_grass", "policy")
@@ -71,13 +68,15 @@ class EatGrass(SubstepTransition):
         st.pred_cell = none_i
         if not isinstance(eatable, MaskedPositions):
             # explicit position list (the reference's unit tests): exactly the listed cells are eaten (eat.py:80-99)
-            true_grown, listed = st.grown, cells_bitmap(eatable, spec.max_y, n_cells, dev)
-            st.grown = listed.clone()
+            true_info, cells = st.info, listed_cells(eatable, spec.max_y, n_cells, dev)
+            st.info = torch.zeros(info_bytes(n_cells), dtype=torch.uint8, device=dev)
+            st.info[cells] = 1
             eng.eat(st)
-            st.grown = true_grown & ~listed
+            st.info = true_info
+            st.info[cells] = 0
         else:
             eng.eat(st)
-        out_stage = unpack_stage(st.grown, n_cells, dtype=growth.dtype if growth.dtype in (torch.int64, torch.float32) else torch.int64)
+        out_stage = unpack_stage(st.info, n_cells, dtype=growth.dtype if growth.dtype in (torch.int64, torch.float32) else torch.int64)
         ov = self.output_variables
         return {ov[0]: st.prey_energy.reshape(energy.shape).to(energy.dtype), ov[1]: out_stage.reshape(growth.shape),
                 ov[2]: st.countdown.reshape(countdown.shape)}

@@ -27,4 +27,4 @@ class GrowGrass(SubstepTransition):
         new_cd = st.countdown.reshape(countdown.shape)
         if not countdown.is_floating_point():
             new_cd = new_cd.to(countdown.dtype)
-        return {ov[0]: unpack_stage(st.grown, n_cells).view(-1, 1), ov[1]: new_cd}              # grow.py:43-46
+        return {ov[0]: unpack_stage(st.info, n_cells).view(-1, 1), ov[1]: new_cd}              # grow.py:43-46

@@ -4,10 +4,10 @@ import torch
 from agenttorch_b200 import _native_pp as nat
 from agenttorch_b200.core.registry import Registry
 from agenttorch_b200.core.substep import SubstepAction, SubstepTransition
-from agenttorch_b200.predprey import PredPreyState, pack_cells
+from agenttorch_b200.predprey import PredPreyState, info_bytes, occupancy_bits, pack_cells
 
 from ..context import engine_for, get_var, require_cuda, spec_from_bounds
-from .eat import MaskedPositions, cells_bitmap
+from .eat import MaskedPositions, listed_cells
 
 
 def _grid_extent(*positions):
@@ -47,16 +47,15 @@ class HuntPrey(SubstepTransition):
         eng = engine_for(spec, dev)
         f32 = lambda t: t.reshape(-1).to(torch.float32).clone().contiguous()          # noqa: E731
         none_f = torch.zeros(0, dtype=torch.float32, device=dev)
+        info = torch.zeros(info_bytes(mx * my), dtype=torch.uint8, device=dev)
         st = PredPreyState(pack_cells(pred_pos, my, mx * my)[0], f32(pred_energy), pack_cells(prey_pos, my, mx * my)[0],
-                           f32(prey_energy), eng.eaten, none_f)
+                           f32(prey_energy), info, none_f)
         if isinstance(targets, MaskedPositions):
             eng.hunt(st)                          # target cells = cells holding a predator and a prey (hunt.py:36-40)
         else:
             # explicit target list (the reference's unit tests): prey / predators AT the listed cells (hunt.py:69-80)
-            listed = cells_bitmap(targets, my, mx * my, dev)
-            eng.occ[0][0].copy_(listed)
-            eng.occ[0][1].copy_(listed)
-            eng._launch(st, nat.HUNT | nat.CLEAR)
+            info[listed_cells(targets, my, mx * my, dev)] = sum(occupancy_bits(0))
+            eng._launch(st, nat.HUNT)
         ov = self.output_variables
         return {ov[0]: st.prey_energy.reshape(prey_energy.shape).to(prey_energy.dtype),
                 ov[1]: st.pred_energy.reshape(pred_energy.shape).to(pred_energy.dtype)}

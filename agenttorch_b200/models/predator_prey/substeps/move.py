@@ -73,8 +73,8 @@ class DecideMovement(SubstepAction):
         e = energy.reshape(-1).to(torch.float32).clone().contiguous()
         none_i = torch.zeros(0, dtype=torch.int32, device=positions.device)
         none_f = torch.zeros(0, dtype=torch.float32, device=positions.device)
-        st = PredPreyState(cells, e, none_i, none_f, eng.eaten, none_f) if species == 0 else \
-            PredPreyState(none_i, none_f, cells, e, eng.eaten, none_f)
+        st = PredPreyState(cells, e, none_i, none_f, None, none_f) if species == 0 else \
+            PredPreyState(none_i, none_f, cells, e, None, none_f)
         eng.move(st, t, self.seed)
         return {self.output_variables[0]: unpack_cells(cells, spec.max_y)}
 

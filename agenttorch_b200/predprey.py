@@ -118,8 +118,13 @@ class PredPreySpec:
                            regrowth_time=float(self.regrowth_time))
 
 
-def bitmap_words(n_cells):
-    return (((n_cells + 31) >> 5) + 3) & ~3
+def info_bytes(n_cells):
+    return (int(n_cells) + 15) & ~15
+
+
+def occupancy_bits(parity):
+    """(predator bit, prey bit) of the info byte for occupancy parity 0 / 1 (include/at_predprey.h)."""
+    return 4 << (2 * parity), 8 << (2 * parity)
 
 
 def pack_cells(coords, max_y, n_cells):
@@ -145,25 +150,25 @@ def pack_stage(stage, n_cells):
     if stage.dtype not in (torch.int64, torch.float32):
         stage = stage.to(torch.float32)
     stage = stage.contiguous()
-    grown = torch.zeros(bitmap_words(n_cells), dtype=torch.int32, device=stage.device)
-    nat.check(nat.lib().at_pp_pack_stage(_ptr(stage), 0 if stage.dtype == torch.int64 else 1, int(n_cells), _ptr(grown), _stream()))
-    return grown
+    info = torch.empty(info_bytes(n_cells), dtype=torch.uint8, device=stage.device)
+    nat.check(nat.lib().at_pp_pack_stage(_ptr(stage), 0 if stage.dtype == torch.int64 else 1, int(n_cells), _ptr(info), _stream()))
+    return info
 
 
-def unpack_stage(grown, n_cells, dtype=torch.int64, out=None):
+def unpack_stage(info, n_cells, dtype=torch.int64, out=None):
     if out is None:
-        out = torch.empty(n_cells, 1, dtype=dtype, device=grown.device)
-    nat.check(nat.lib().at_pp_unpack_stage(_ptr(grown, torch.int32), int(n_cells), _ptr(out), 0 if out.dtype == torch.int64 else 1, _stream()))
+        out = torch.empty(n_cells, 1, dtype=dtype, device=info.device)
+    nat.check(nat.lib().at_pp_unpack_stage(_ptr(info, torch.uint8), int(n_cells), _ptr(out), 0 if out.dtype == torch.int64 else 1, _stream()))
     return out
 
 
 class PredPreyState:
     """Device state in the engine's layout."""
 
-    def __init__(self, pred_cell, pred_energy, prey_cell, prey_energy, grown, countdown):
+    def __init__(self, pred_cell, pred_energy, prey_cell, prey_energy, info, countdown):
         self.pred_cell, self.pred_energy = pred_cell, pred_energy
         self.prey_cell, self.prey_energy = prey_cell, prey_energy
-        self.grown, self.countdown = grown, countdown
+        self.info, self.countdown = info, countdown          # info: one byte per cell (bit 0 = grown; other bits are scratch of a step)
 
     @classmethod
     def from_reference(cls, spec, pred_pos, pred_energy, prey_pos, prey_energy, growth_stage, growth_countdown, validate=True):
@@ -181,17 +186,17 @@ class PredPreyState:
 
     def clone(self):
         return PredPreyState(*(t.clone() for t in (self.pred_cell, self.pred_energy, self.prey_cell, self.prey_energy,
-                                                    self.grown, self.countdown)))
+                                                    self.info, self.countdown)))
 
     def copy_(self, other):
-        for k in ("pred_cell", "pred_energy", "prey_cell", "prey_energy", "grown", "countdown"):
+        for k in ("pred_cell", "pred_energy", "prey_cell", "prey_energy", "info", "countdown"):
             getattr(self, k).copy_(getattr(other, k))
 
     def to_reference(self, spec):
         """Dict of tensors in the reference's shapes."""
         return {"pred_pos": unpack_cells(self.pred_cell, spec.max_y), "pred_energy": self.pred_energy.reshape(-1, 1).clone(),
                 "prey_pos": unpack_cells(self.prey_cell, spec.max_y), "prey_energy": self.prey_energy.reshape(-1, 1).clone(),
-                "growth_stage": unpack_stage(self.grown, spec.n_cells), "growth_countdown": self.countdown.reshape(-1, 1).clone()}
+                "growth_stage": unpack_stage(self.info, spec.n_cells), "growth_countdown": self.countdown.reshape(-1, 1).clone()}
 
 
 class PredPreyEngine:
@@ -206,10 +211,6 @@ class PredPreyEngine:
         nat.lib()
         self.model = spec.c_model()
         self.csr = adjacency if isinstance(adjacency, CsrAdjacency) else None
-        words = bitmap_words(spec.n_cells)
-        z = lambda: torch.zeros(words, dtype=torch.int32, device=self.device)        # noqa: E731
-        self.eaten = z()
-        self.occ = [(z(), z()), (z(), z())]                   # two (predator, prey) pairs, alternating between steps
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.grid = int(grid)
@@ -228,10 +229,8 @@ class PredPreyEngine:
         a.n_pred, a.n_prey = st.pred_cell.numel(), st.prey_cell.numel()
         a.pred_cell, a.pred_energy = _ptr(st.pred_cell, torch.int32), _ptr(st.pred_energy, torch.float32)
         a.prey_cell, a.prey_energy = _ptr(st.prey_cell, torch.int32), _ptr(st.prey_energy, torch.float32)
-        a.grown, a.countdown, a.eaten = _ptr(st.grown, torch.int32), _ptr(st.countdown), _ptr(self.eaten)
-        a.occ_pred_in, a.occ_prey_in = _ptr(self.occ[occ_in][0]), _ptr(self.occ[occ_in][1])
-        if occ_out is not None:
-            a.occ_pred_out, a.occ_prey_out = _ptr(self.occ[occ_out][0]), _ptr(self.occ[occ_out][1])
+        a.info, a.countdown = _ptr(st.info, torch.uint8) if st.info is not None else None, _ptr(st.countdown)
+        a.occ_in, a.occ_out = int(occ_in), -1 if occ_out is None else int(occ_out)
         if self.csr is not None:
             a.nbr_ptr, a.nbr_idx = _ptr(self.csr.ptr, torch.int64), _ptr(self.csr.idx, torch.int32)
         a.grid = self.grid
@@ -266,7 +265,7 @@ class PredPreyEngine:
         base = 0 if dev_clock else t0
         self._launch(st, nat.MOVE, t_move=base, occ_in=1, occ_out=0, **kw)
         for s in range(num_steps):
-            flags = nat.EAT | nat.HUNT | nat.EAT_APPLY | nat.GROW | nat.CLEAR
+            flags = nat.EAT | nat.HUNT | nat.EAT_APPLY | nat.GROW | nat.CLEAR | nat.EAT_IMPLICIT
             if s + 1 < num_steps:
                 flags |= nat.MOVE
             self._launch(st, flags, t_move=base + s + 1, occ_in=s & 1, occ_out=(s + 1) & 1, **kw)
@@ -275,16 +274,13 @@ class PredPreyEngine:
         """Advance `st` in place by `num_steps` steps; the move draws are addressed by steps t0, t0+1, ..."""
         if num_steps <= 0:
             return
-        for pair in self.occ:
-            for o in pair:
-                o.zero_()
-        self.eaten.zero_()
+        st.info.bitwise_and_(nat.INFO_GROWN)                   # scratch bits of an interrupted earlier call
         if not cuda_graph:
             self._issue(st, num_steps, seed, t0, dev_clock=False)
             return
         self.seed_dev.fill_(int(seed) if int(seed) < 2 ** 63 else int(seed) - 2 ** 64)
         self.t_dev.fill_(int(t0))
-        key = (num_steps,) + tuple(t.data_ptr() for t in (st.pred_cell, st.pred_energy, st.prey_cell, st.prey_energy, st.grown, st.countdown))
+        key = (num_steps,) + tuple(t.data_ptr() for t in (st.pred_cell, st.pred_energy, st.prey_cell, st.prey_energy, st.info, st.countdown))
         graph = self._graphs.get(key)
         if graph is None:
             before = self.launch_count
@@ -304,7 +300,7 @@ class PredPreyEngine:
         a = nat.PPLaunch()
         a.abi_version = nat.ABI_VERSION
         a.n_pred, a.n_prey = st.pred_cell.numel(), st.prey_cell.numel()
-        a.pred_energy, a.prey_energy, a.grown = _ptr(st.pred_energy), _ptr(st.prey_energy), _ptr(st.grown)
+        a.pred_energy, a.prey_energy, a.info = _ptr(st.pred_energy), _ptr(st.prey_energy), _ptr(st.info, torch.uint8)
         out = torch.zeros(3, dtype=torch.int64, device=self.device)
         nat.check(nat.lib().at_pp_census(ctypes.byref(a), int(self.spec.n_cells), _ptr(out), _stream()))
         return tuple(int(v) for v in out.tolist())

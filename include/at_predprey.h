@@ -11,9 +11,15 @@
  * at_pp_last_error()), never throws; the library allocates nothing — all buffers are caller-owned DEVICE memory;
  * all work is stream-ordered on `stream` (a cudaStream_t) and CUDA-graph capturable.  No CPU fallback.
  *
- * Data layout (SoA): an agent is (cell int32, energy float32) with cell = max_y * x + y (move.py:36); the grass is
- * one bit per cell (growth_stage == 1) + one countdown per cell (float32 or float64, as the population file gave it).
- * Cell-indexed bitmaps have (n_cells + 31) / 32 words, rounded up to a multiple of 4 words.
+ * Data layout (SoA): an agent is (cell int32, energy float32) with cell = max_y * x + y (move.py:36).  A cell is one
+ * INFO byte + one countdown (float32 or float64, as the population file gave it).  The info byte answers every
+ * "what is at this cell" question of a step with ONE random access:
+ *     bit 0  grown      growth_stage == 1
+ *     bit 1  eaten      set by EAT, consumed (and cleared) by EAT_APPLY
+ *     bit 2  a predator stands here   } occupancy of parity 0
+ *     bit 3  a prey stands here       }
+ *     bit 4, 5  the same for parity 1 (the occupancy of consecutive steps alternates between the two pairs)
+ * The info array has at_pp_info_bytes(n_cells) bytes (n_cells rounded up to a multiple of 16).
  */
 #ifndef AT_PREDPREY_H
 #define AT_PREDPREY_H
@@ -24,16 +30,19 @@
 extern "C" {
 #endif
 
-#define AT_PP_ABI_VERSION 1
+#define AT_PP_ABI_VERSION 2
 
 /* at_pp_launch.flags — what one call does, always in this order:
- *   OCCUPANCY  mark the cells holding >= 1 predator / >= 1 prey in occ_*_in (needed by HUNT when the positions did
- *              not come from a MOVE of this library)
- *   EAT, HUNT  per agent, on the positions as they are
- *   MOVE       per agent: draw + step to a neighbouring cell if energy > 0, energy -= work; marks occ_*_out
+ *   OCCUPANCY  mark the cells holding >= 1 predator / >= 1 prey in the occupancy bits of parity `occ_in` (needed by
+ *              HUNT when the positions did not come from a MOVE of this library; the bits must be clear before)
+ *   EAT, HUNT  per agent, on the positions as they are; HUNT reads the occupancy bits of parity `occ_in`
+ *   MOVE       per agent: draw + step to a neighbouring cell if energy > 0, energy -= work; marks the occupancy
+ *              bits of parity `occ_out` at the new cell (occ_out < 0: no marking)
  *   EAT_APPLY  per cell: eaten grass -> stage 0, countdown c + float32(regrowth_time - c)
  *   GROW       per cell: countdown -= 1, stage = (countdown <= 0)
- *   CLEAR      per cell word: zero occ_*_in (their step is over)                                     */
+ *   CLEAR      per cell: clear the occupancy bits of parity `occ_in` (their step is over)
+ * Modifier EAT_IMPLICIT (with EAT and EAT_APPLY in the same call, occupancy of parity `occ_in` valid): a grown cell
+ * holding a prey IS an eaten cell, so EAT sets no bit and EAT_APPLY derives it — one atomic less per eating prey. */
 #define AT_PP_OCCUPANCY 1
 #define AT_PP_EAT 2
 #define AT_PP_HUNT 4
@@ -41,6 +50,7 @@ extern "C" {
 #define AT_PP_EAT_APPLY 16
 #define AT_PP_GROW 32
 #define AT_PP_CLEAR 64
+#define AT_PP_EAT_IMPLICIT 128
 
 typedef struct at_pp_model {
     int32_t abi_version;
@@ -71,13 +81,10 @@ typedef struct at_pp_launch {
     float* pred_energy;
     int32_t* prey_cell;
     float* prey_energy;
-    uint32_t* grown;          /* bitmap: growth_stage == 1 */
+    uint8_t* info;            /* [at_pp_info_bytes(n_cells)] cell info bytes, see above */
     void* countdown;          /* [n_cells] */
-    uint32_t* eaten;          /* bitmap: cells eaten by EAT, consumed (and zeroed) by EAT_APPLY */
-    uint32_t* occ_pred_in;    /* bitmaps of the cells holding a predator / a prey at the CURRENT positions */
-    uint32_t* occ_prey_in;
-    uint32_t* occ_pred_out;   /* bitmaps MOVE marks with the NEW positions (zeroed by the caller or by an earlier CLEAR) */
-    uint32_t* occ_prey_out;
+    int32_t occ_in;           /* parity (0/1) of the occupancy bits that describe the CURRENT positions */
+    int32_t occ_out;          /* parity MOVE marks with the NEW positions; < 0: none */
     const int64_t* nbr_ptr;   /* optional CSR adjacency (ascending neighbours) for non-lattice networks; NULL = lattice */
     const int32_t* nbr_idx;
     int32_t grid;             /* CTAs per kernel; 0 = library default (multiple of the SM count) */
@@ -88,17 +95,17 @@ int at_pp_abi_version(void);
 const char* at_pp_last_error(void);
 int64_t at_pp_sizeof_model(void);
 int64_t at_pp_sizeof_launch(void);
-int64_t at_pp_bitmap_words(int64_t n_cells);
+int64_t at_pp_info_bytes(int64_t n_cells);
 
 /* One call = up to three kernels (occupancy; agents; cells), see the flag list. */
 int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* stream);
 
 /* (n,2) int64 [x, y] coordinates  <->  int32 cells;  (n_cells) stage values (int64 / float32, == 1 means grown)
- * <->  bitmap.  `stage_dtype`: 0 = int64, 1 = float32. */
+ * <->  bit 0 of the info bytes (pack overwrites the whole byte).  `stage_dtype`: 0 = int64, 1 = float32. */
 int at_pp_pack_cells(const int64_t* coords, int64_t n, int32_t max_y, int64_t n_cells, int32_t* cells, int32_t* error_flag, void* stream);
 int at_pp_unpack_cells(const int32_t* cells, int64_t n, int32_t max_y, int64_t* coords, void* stream);
-int at_pp_pack_stage(const void* stage, int32_t stage_dtype, int64_t n_cells, uint32_t* grown, void* stream);
-int at_pp_unpack_stage(const uint32_t* grown, int64_t n_cells, void* stage, int32_t stage_dtype, void* stream);
+int at_pp_pack_stage(const void* stage, int32_t stage_dtype, int64_t n_cells, uint8_t* info, void* stream);
+int at_pp_unpack_stage(const uint8_t* info, int64_t n_cells, void* stage, int32_t stage_dtype, void* stream);
 
 /* Counts for reporting: out[0] = predators with energy > 0, out[1] = prey with energy > 0, out[2] = grown cells. */
 int at_pp_census(const at_pp_launch* launch, int64_t n_cells, int64_t* out3, void* stream);

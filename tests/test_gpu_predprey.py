@@ -283,11 +283,12 @@ def test_baseline_size_properties():
     a, b = st0.clone(), st0.clone()
     eng.run(a, 10, 99, cuda_graph=True)
     eng.run(b, 4, 99, cuda_graph=False); eng.run(b, 6, 99, t0=4, cuda_graph=True)
-    for k in ("pred_cell", "pred_energy", "prey_cell", "prey_energy", "grown", "countdown"):
+    for k in ("pred_cell", "pred_energy", "prey_cell", "prey_energy", "info", "countdown"):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
     # grass: stage <=> countdown <= 0 after every grow; countdowns stay in [-(steps), regrowth]
     from agenttorch_b200.predprey import unpack_stage
-    stage = unpack_stage(a.grown, C).reshape(-1)
+    stage = unpack_stage(a.info, C).reshape(-1)
+    assert int(a.info.max()) <= 1                                # no scratch bit survives a run
     assert torch.equal(stage == 1, a.countdown <= 0)
     assert float(a.countdown.max()) <= 100.0 and float(a.countdown.min()) >= -10.0
     # agents moved at most one lattice step per step (Manhattan distance <= 10), none left the grid

@@ -77,7 +77,7 @@ def test_predprey_header_symbols_are_exported(built_pp):
     assert built_pp.at_pp_sizeof_launch() == ctypes.sizeof(_native_pp.PPLaunch)
     assert built_pp.at_pp_sizeof_model() == ctypes.sizeof(_native_pp.PPModel)
     assert f"#define AT_PP_ABI_VERSION {_native_pp.ABI_VERSION}" in header
-    assert built_pp.at_pp_bitmap_words(450) == 16 and built_pp.at_pp_bitmap_words(4096 * 4096) == 4096 * 128
+    assert built_pp.at_pp_info_bytes(450) == 464 and built_pp.at_pp_info_bytes(4096 * 4096) == 4096 * 4096
 
 
 def test_predprey_bad_arguments_return_errors(built_pp):

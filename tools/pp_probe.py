@@ -38,6 +38,6 @@ for i in range(args.reps + 2):
 ms = statistics.median(times[2:])
 n = args.pred + args.prey
 cd_b = 8 if args.f64 else 4
-bytes_step = n * 16 + C * 2 * cd_b            # agents: cell + energy read and written; cells: countdown read and written
+bytes_step = n * 16 + C * 2 * (cd_b + 1)      # agents: cell + energy read and written; cells: info byte + countdown read and written
 print(f"predator-prey {n/1e6:.1f} M agents, {mx}x{my} cells, {args.steps} steps: {ms:.3f} ms -> {ms/args.steps*1e3:.1f} us/step, "
       f"{n*args.steps/ms/1e6:.1f} G agent-steps/s, algorithmic {bytes_step/1e6:.0f} MB/step -> {bytes_step*args.steps/ms/1e9:.2f} TB/s; census {eng.census(st)}")
