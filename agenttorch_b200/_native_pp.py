@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libat_predprey.so")
 SRC_PATH = os.path.join(_PKG, "csrc", "at_predprey.cu")
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OCCUPANCY, EAT, HUNT, MOVE, EAT_APPLY, GROW, CLEAR, EAT_IMPLICIT = 1, 2, 4, 8, 16, 32, 64, 128
 INFO_GROWN, INFO_EATEN = 1, 2
 
@@ -45,6 +45,7 @@ class PPLaunch(ctypes.Structure):
         ("prey_cell", ctypes.c_void_p), ("prey_energy", ctypes.c_void_p),
         ("info", ctypes.c_void_p), ("countdown", ctypes.c_void_p),
         ("occ_in", ctypes.c_int32), ("occ_out", ctypes.c_int32),
+        ("pred_id", ctypes.c_void_p), ("prey_id", ctypes.c_void_p),
         ("nbr_ptr", ctypes.c_void_p), ("nbr_idx", ctypes.c_void_p),
         ("grid", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]

@@ -111,7 +111,9 @@ pp_agent_kernel(at_pp_model m, at_pp_launch a)
         }
         if (flags & AT_PP_MOVE) {
             if (e > 0.0f) {                                                         // move.py:89
-                const uint64_t z = at_noise_u64(seed, t, ((uint64_t)(prey ? 1 : 0) << PP_SPECIES_BIT) | (uint64_t)i);
+                const int32_t* ids = prey ? a.prey_id : a.pred_id;                  // draws follow the agent, not its slot
+                const uint64_t who = ids ? (uint64_t)(uint32_t)ids[i] : (uint64_t)i;
+                const uint64_t z = at_noise_u64(seed, t, ((uint64_t)(prey ? 1 : 0) << PP_SPECIES_BIT) | who);
                 const uint32_t draw = (uint32_t)(z >> 40);
                 if (a.nbr_ptr == nullptr) {
                     cell = lattice_step(cell, draw, m.width, m.n_cells);

@@ -2,8 +2,9 @@
 instead of n x 4 substeps x (observe, act, progress) Python passes (reference core/runner.py:121-153).
 
 The plan is recognised from the initialised substep modules (exactly this package's classes under the reference's
-registry names); anything else runs through the generic Controller path.  Energies and countdowns of the public state
-are aliased by the engine (no copies); coordinates and growth stages are converted at the boundary, in place."""
+registry names); anything else runs through the generic Controller path.  Positions, energies and growth stages
+are converted at the boundary: the engine keeps the agents as (cell, energy) pairs sorted by cell (locality of the
+per-cell lookups), the public tensors stay in agent-number order and are updated in place after every call."""
 import re
 
 import torch
@@ -76,6 +77,9 @@ class _FusedPredPrey:
         self.engine = None
         self.st = None
         self._seen = None
+        cuda_params = runner.config["simulation_metadata"].get("cuda_params", {}) or {}
+        self.sort = bool(cuda_params.get("sort_agents_by_cell", True))
+        self.resort_every = int(cuda_params.get("resort_every", 32)) if self.sort else 0
 
     def _tensors(self, state):
         u, e = self.up.input_variables, self.eat.input_variables
@@ -109,59 +113,59 @@ class _FusedPredPrey:
         return self._seen is not None and all(x is y and x._version == v for x, (y, v) in zip(tensors, self._seen))
 
     def _adopt(self, state):
-        """Bring the engine state in line with the public tensors; aliases what can be aliased."""
+        """Bring the engine state in line with the public tensors.  The engine keeps its own cell-sorted copy of the
+        agents; the countdown array (no order involved) is aliased."""
         t = self._tensors(state)
         if self.engine is None:
             self._build(state, t)
         spec = self.spec
         paths_u, paths_e = self.up.input_variables, self.eat.input_variables
         fixed = {}
-        for key, path in (("pred_energy", paths_u["pred_energy"]), ("prey_energy", paths_u["prey_energy"])):
+        for key, path, dtype in (("pred_energy", paths_u["pred_energy"], torch.float32), ("prey_energy", paths_u["prey_energy"], torch.float32),
+                                 ("pred_pos", paths_u["pred_pos"], torch.int64), ("prey_pos", paths_u["prey_pos"], torch.int64)):
             v = t[key]
-            if v.dtype != torch.float32 or not v.is_contiguous():
-                v = v.to(torch.float32).contiguous()
+            if v.dtype != dtype or not v.is_contiguous():
+                v = v.to(dtype).contiguous()
                 set_by_path(state, _path(path), v)
             fixed[key] = v
         cd = t["countdown"]
         if cd.dtype not in (torch.float32, torch.float64) or not cd.is_contiguous():
             cd = cd.to(torch.float32).contiguous()
             set_by_path(state, _path(paths_e["growth_countdown"]), cd)
-        for key, path in (("pred_pos", paths_u["pred_pos"]), ("prey_pos", paths_u["prey_pos"])):
-            v = t[key]
-            if v.dtype != torch.int64 or not v.is_contiguous():
-                v = v.to(torch.int64).contiguous()
-                set_by_path(state, _path(path), v)
-            fixed[key] = v
         stage = t["stage"]
         if stage.dtype not in (torch.int64, torch.float32) or not stage.is_contiguous():
             stage = stage.to(torch.int64).contiguous()
             set_by_path(state, _path(paths_e["grass_growth"]), stage)
-        if self.st is None or not self._unchanged(fixed["pred_pos"], fixed["prey_pos"], stage):
-            pc, f0 = pack_cells(fixed["pred_pos"], spec.max_y, spec.n_cells)
-            yc, f1 = pack_cells(fixed["prey_pos"], spec.max_y, spec.n_cells)
-            if int((f0 | f1).item()):
-                raise ValueError("agent coordinates outside the grid (cell = max_y * x + y must be in [0, n_cells))")
-            info = pack_stage(stage, spec.n_cells)
-            if self.st is not None and self.st.pred_cell.shape == pc.shape and self.st.prey_cell.shape == yc.shape:
-                self.st.pred_cell.copy_(pc); self.st.prey_cell.copy_(yc); self.st.info.copy_(info)       # keep graph pointers
+        fixed["stage"], fixed["countdown"] = stage, cd
+        watched = [fixed[k] for k in ("pred_pos", "pred_energy", "prey_pos", "prey_energy", "stage")]
+        if self.st is None or not self._unchanged(*watched):
+            fresh = PredPreyState.from_reference(spec, fixed["pred_pos"], fixed["pred_energy"], fixed["prey_pos"], fixed["prey_energy"],
+                                                 stage, cd[:0].new_zeros(spec.n_cells), sort=self.sort)
+            if self.st is not None and self.st.pred_cell.shape == fresh.pred_cell.shape and self.st.prey_cell.shape == fresh.prey_cell.shape \
+                    and (self.st.pred_id is None) == (fresh.pred_id is None):
+                fresh.countdown = self.st.countdown
+                self.st.copy_(fresh)                                                    # keep the buffers captured graphs point to
             else:
-                self.st = PredPreyState(pc, None, yc, None, info, None)
-        self.st.pred_energy, self.st.prey_energy = fixed["pred_energy"].view(-1), fixed["prey_energy"].view(-1)
+                self.st = fresh
         self.st.countdown = cd.view(-1)
-        return fixed, stage
+        return fixed
 
     def __call__(self, num_steps):
         runner, state = self.runner, self.runner.state
-        fixed, stage = self._adopt(state)
+        fixed = self._adopt(state)
+        st = self.st
         t0 = self.movers[0].calls
         before = self.engine.launch_count
-        self.engine.run(self.st, int(num_steps), self.seed, t0=t0, cuda_graph=runner._use_cuda_graph)
+        self.engine.run(st, int(num_steps), self.seed, t0=t0, cuda_graph=runner._use_cuda_graph, resort_every=self.resort_every)
         for m in self.movers:
             m.calls = t0 + int(num_steps)
-        unpack_cells(self.st.pred_cell, self.spec.max_y, out=fixed["pred_pos"])
-        unpack_cells(self.st.prey_cell, self.spec.max_y, out=fixed["prey_pos"])
-        unpack_stage(self.st.info, self.spec.n_cells, out=stage.view(-1, 1))
-        self._seen = [(x, x._version) for x in (fixed["pred_pos"], fixed["prey_pos"], stage)]
+        # publish: agents back in agent-number order, in place in the public tensors
+        unpack_cells(st.in_agent_order("pred_cell"), self.spec.max_y, out=fixed["pred_pos"])
+        unpack_cells(st.in_agent_order("prey_cell"), self.spec.max_y, out=fixed["prey_pos"])
+        fixed["pred_energy"].view(-1).copy_(st.in_agent_order("pred_energy"))
+        fixed["prey_energy"].view(-1).copy_(st.in_agent_order("prey_energy"))
+        unpack_stage(st.info, self.spec.n_cells, out=fixed["stage"].view(-1, 1))
+        self._seen = [(x, x._version) for x in (fixed[k] for k in ("pred_pos", "pred_energy", "prey_pos", "prey_energy", "stage"))]
         state["current_step"] = int(num_steps) - 1
         state["current_substep"] = "0"
         runner.perf_stats["fused_episodes"] += 1

@@ -163,15 +163,23 @@ def unpack_stage(info, n_cells, dtype=torch.int64, out=None):
 
 
 class PredPreyState:
-    """Device state in the engine's layout."""
+    """Device state in the engine's layout.  Agents may be kept in any slot order: `pred_id` / `prey_id` (None =
+    identity) give the agent number of every slot.  `sort_by_cell()` orders the slots by cell, so that the random
+    cell lookups of a warp fall into a few 128-byte lines; random walks destroy that order only slowly (a warp's
+    agents spread over ~sqrt(steps) grid rows)."""
 
-    def __init__(self, pred_cell, pred_energy, prey_cell, prey_energy, info, countdown):
+    AGENT_KEYS = ("pred_cell", "pred_energy", "prey_cell", "prey_energy")
+    KEYS = AGENT_KEYS + ("info", "countdown")
+
+    def __init__(self, pred_cell, pred_energy, prey_cell, prey_energy, info, countdown, pred_id=None, prey_id=None):
         self.pred_cell, self.pred_energy = pred_cell, pred_energy
         self.prey_cell, self.prey_energy = prey_cell, prey_energy
         self.info, self.countdown = info, countdown          # info: one byte per cell (bit 0 = grown; other bits are scratch of a step)
+        self.pred_id, self.prey_id = pred_id, prey_id
 
     @classmethod
-    def from_reference(cls, spec, pred_pos, pred_energy, prey_pos, prey_energy, growth_stage, growth_countdown, validate=True):
+    def from_reference(cls, spec, pred_pos, pred_energy, prey_pos, prey_energy, growth_stage, growth_countdown, validate=True,
+                       sort=False):
         """From tensors in the reference's shapes (copies; the inputs are not aliased)."""
         pc, f0 = pack_cells(pred_pos, spec.max_y, spec.n_cells)
         yc, f1 = pack_cells(prey_pos, spec.max_y, spec.n_cells)
@@ -182,20 +190,57 @@ class PredPreyState:
         if growth_stage.numel() != spec.n_cells or cd.numel() != spec.n_cells:
             raise ValueError("grass tensors must have one entry per cell")
         f32 = lambda t: t.reshape(-1).to(torch.float32).clone().contiguous()          # noqa: E731
-        return cls(pc, f32(pred_energy), yc, f32(prey_energy), pack_stage(growth_stage, spec.n_cells), cd.contiguous())
+        st = cls(pc, f32(pred_energy), yc, f32(prey_energy), pack_stage(growth_stage, spec.n_cells), cd.contiguous())
+        if sort:
+            st.sort_by_cell()
+        return st
+
+    def sort_by_cell(self):
+        """Reorder the slots of both species by cell, IN PLACE (buffer addresses — and captured graphs — stay valid)."""
+        for cell, energy, name in ((self.pred_cell, self.pred_energy, "pred_id"), (self.prey_cell, self.prey_energy, "prey_id")):
+            if cell.numel() == 0:
+                continue
+            order = torch.argsort(cell)
+            ids = getattr(self, name)
+            if ids is None:
+                setattr(self, name, order.to(torch.int32))
+            else:
+                ids.copy_(ids[order])
+            cell.copy_(cell[order])
+            energy.copy_(energy[order])
 
     def clone(self):
-        return PredPreyState(*(t.clone() for t in (self.pred_cell, self.pred_energy, self.prey_cell, self.prey_energy,
-                                                    self.info, self.countdown)))
+        c = lambda t: None if t is None else t.clone()                                 # noqa: E731
+        return PredPreyState(*(c(getattr(self, k)) for k in self.KEYS), pred_id=c(self.pred_id), prey_id=c(self.prey_id))
 
     def copy_(self, other):
-        for k in ("pred_cell", "pred_energy", "prey_cell", "prey_energy", "info", "countdown"):
+        for k in self.KEYS:
             getattr(self, k).copy_(getattr(other, k))
+        for k in ("pred_id", "prey_id"):
+            mine, theirs = getattr(self, k), getattr(other, k)
+            if theirs is None:
+                setattr(self, k, None)
+            elif mine is None:
+                setattr(self, k, theirs.clone())
+            else:
+                mine.copy_(theirs)
+
+    def in_agent_order(self, key):
+        """The per-agent array `key` indexed by agent number (undoes the slot order)."""
+        v = getattr(self, key)
+        ids = self.pred_id if key.startswith("pred") else self.prey_id
+        if ids is None:
+            return v
+        out = torch.empty_like(v)
+        out[ids.to(torch.int64)] = v
+        return out
 
     def to_reference(self, spec):
-        """Dict of tensors in the reference's shapes."""
-        return {"pred_pos": unpack_cells(self.pred_cell, spec.max_y), "pred_energy": self.pred_energy.reshape(-1, 1).clone(),
-                "prey_pos": unpack_cells(self.prey_cell, spec.max_y), "prey_energy": self.prey_energy.reshape(-1, 1).clone(),
+        """Dict of tensors in the reference's shapes (agents in agent-number order)."""
+        return {"pred_pos": unpack_cells(self.in_agent_order("pred_cell"), spec.max_y),
+                "pred_energy": self.in_agent_order("pred_energy").reshape(-1, 1).clone(),
+                "prey_pos": unpack_cells(self.in_agent_order("prey_cell"), spec.max_y),
+                "prey_energy": self.in_agent_order("prey_energy").reshape(-1, 1).clone(),
                 "growth_stage": unpack_stage(self.info, spec.n_cells), "growth_countdown": self.countdown.reshape(-1, 1).clone()}
 
 
@@ -231,6 +276,10 @@ class PredPreyEngine:
         a.prey_cell, a.prey_energy = _ptr(st.prey_cell, torch.int32), _ptr(st.prey_energy, torch.float32)
         a.info, a.countdown = _ptr(st.info, torch.uint8) if st.info is not None else None, _ptr(st.countdown)
         a.occ_in, a.occ_out = int(occ_in), -1 if occ_out is None else int(occ_out)
+        if st.pred_id is not None:
+            a.pred_id = _ptr(st.pred_id, torch.int32)
+        if st.prey_id is not None:
+            a.prey_id = _ptr(st.prey_id, torch.int32)
         if self.csr is not None:
             a.nbr_ptr, a.nbr_idx = _ptr(self.csr.ptr, torch.int64), _ptr(self.csr.idx, torch.int32)
         a.grid = self.grid
@@ -242,8 +291,9 @@ class PredPreyEngine:
         return (int(bool(flags & nat.OCCUPANCY)) + int(bool(flags & (nat.EAT | nat.HUNT | nat.MOVE)))
                 + int(bool(flags & (nat.EAT_APPLY | nat.GROW | nat.CLEAR))))
 
-    def kernels_per_run(self, num_steps):
-        return 1 + 2 * num_steps
+    def kernels_per_run(self, num_steps, resort_every=0):
+        chunks = -(-num_steps // resort_every) if resort_every else 1
+        return chunks + 2 * num_steps
 
     # substep-level entry points (the Controller path and the parity tests drive these one by one)
     def move(self, st, t, seed):
@@ -260,40 +310,48 @@ class PredPreyEngine:
         self._launch(st, nat.GROW)
 
     # ------------------------------------------------------------------------------------- fused steps
-    def _issue(self, st, num_steps, seed, t0, dev_clock):
+    def _issue(self, st, num_steps, seed, t0, dev_clock, resort_every=0):
         kw = dict(seed=seed, use_dev_clock=dev_clock)
         base = 0 if dev_clock else t0
-        self._launch(st, nat.MOVE, t_move=base, occ_in=1, occ_out=0, **kw)
-        for s in range(num_steps):
-            flags = nat.EAT | nat.HUNT | nat.EAT_APPLY | nat.GROW | nat.CLEAR | nat.EAT_IMPLICIT
-            if s + 1 < num_steps:
-                flags |= nat.MOVE
-            self._launch(st, flags, t_move=base + s + 1, occ_in=s & 1, occ_out=(s + 1) & 1, **kw)
+        done = 0
+        while done < num_steps:
+            chunk = min(resort_every, num_steps - done) if resort_every else num_steps
+            if done and st.pred_id is not None:
+                st.sort_by_cell()                      # between two steps: nothing is in flight, the order is free
+            self._launch(st, nat.MOVE, t_move=base + done, occ_in=1, occ_out=0, **kw)
+            for s in range(chunk):
+                flags = nat.EAT | nat.HUNT | nat.EAT_APPLY | nat.GROW | nat.CLEAR | nat.EAT_IMPLICIT
+                if s + 1 < chunk:
+                    flags |= nat.MOVE
+                self._launch(st, flags, t_move=base + done + s + 1, occ_in=s & 1, occ_out=(s + 1) & 1, **kw)
+            done += chunk
 
-    def run(self, st, num_steps, seed, t0=0, cuda_graph=True):
-        """Advance `st` in place by `num_steps` steps; the move draws are addressed by steps t0, t0+1, ..."""
+    def run(self, st, num_steps, seed, t0=0, cuda_graph=True, resort_every=0):
+        """Advance `st` in place by `num_steps` steps; the move draws are addressed by steps t0, t0+1, ...
+        `resort_every` = k > 0 re-sorts a cell-sorted state (st.pred_id set) every k steps."""
         if num_steps <= 0:
             return
         st.info.bitwise_and_(nat.INFO_GROWN)                   # scratch bits of an interrupted earlier call
         if not cuda_graph:
-            self._issue(st, num_steps, seed, t0, dev_clock=False)
+            self._issue(st, num_steps, seed, t0, dev_clock=False, resort_every=resort_every)
             return
         self.seed_dev.fill_(int(seed) if int(seed) < 2 ** 63 else int(seed) - 2 ** 64)
         self.t_dev.fill_(int(t0))
-        key = (num_steps,) + tuple(t.data_ptr() for t in (st.pred_cell, st.pred_energy, st.prey_cell, st.prey_energy, st.info, st.countdown))
+        key = (num_steps, resort_every) + tuple(0 if t is None else t.data_ptr() for t in (
+            st.pred_cell, st.pred_energy, st.prey_cell, st.prey_energy, st.info, st.countdown, st.pred_id, st.prey_id))
         graph = self._graphs.get(key)
         if graph is None:
             before = self.launch_count
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             with torch.cuda.graph(graph):
-                self._issue(st, num_steps, seed, t0, dev_clock=True)
+                self._issue(st, num_steps, seed, t0, dev_clock=True, resort_every=resort_every)
             self.launch_count = before
             if len(self._graphs) >= 4:
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = graph
         graph.replay()
-        self.launch_count += self.kernels_per_run(num_steps)
+        self.launch_count += self.kernels_per_run(num_steps, resort_every)
 
     def census(self, st):
         """(predators alive, prey alive, grown cells) — counts the reference's scripts print (vmap_simulation.py:193-200)."""

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AT_PP_ABI_VERSION 2
+#define AT_PP_ABI_VERSION 3
 
 /* at_pp_launch.flags — what one call does, always in this order:
  *   OCCUPANCY  mark the cells holding >= 1 predator / >= 1 prey in the occupancy bits of parity `occ_in` (needed by
@@ -85,6 +85,8 @@ typedef struct at_pp_launch {
     void* countdown;          /* [n_cells] */
     int32_t occ_in;           /* parity (0/1) of the occupancy bits that describe the CURRENT positions */
     int32_t occ_out;          /* parity MOVE marks with the NEW positions; < 0: none */
+    const int32_t* pred_id;   /* optional: the agent number that addresses the draws of slot i (the caller keeps the agents */
+    const int32_t* prey_id;   /* sorted by cell for locality and records their original numbers here); NULL = slot number   */
     const int64_t* nbr_ptr;   /* optional CSR adjacency (ascending neighbours) for non-lattice networks; NULL = lattice */
     const int32_t* nbr_idx;
     int32_t grid;             /* CTAs per kernel; 0 = library default (multiple of the SM count) */

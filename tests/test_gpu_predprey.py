@@ -41,7 +41,7 @@ def _assert_equal(st, spec, want, where):
 
 
 @pytest.mark.parametrize("case", PREDPREY_CASES)
-@pytest.mark.parametrize("mode", ["substeps", "substeps_csr", "fused_graph", "fused_chunks"])
+@pytest.mark.parametrize("mode", ["substeps", "substeps_csr", "fused_graph", "fused_chunks", "fused_sorted"])
 def test_kernels_match_reference_trajectory(case, mode):
     from agenttorch_b200.predprey import CsrAdjacency, PredPreyEngine
 
@@ -55,6 +55,12 @@ def test_kernels_match_reference_trajectory(case, mode):
         for t in range(T):
             eng.move(st, t, seed); eng.eat(st); eng.hunt(st); eng.grow(st)
             _assert_equal(st, spec, {k: g["traj_" + k][t] for k in PREDPREY_KEYS}, (case, mode, t))
+    elif mode == "fused_sorted":
+        st.sort_by_cell()                                # slots ordered by cell; the draws still follow the agent numbers
+        assert bool((st.prey_cell[1:] >= st.prey_cell[:-1]).all())
+        eng.run(st, T, seed, cuda_graph=True, resort_every=5)
+        _assert_equal(st, spec, {k: g["traj_" + k][T - 1] for k in PREDPREY_KEYS}, (case, mode))
+        eng.run(st, 0, seed)
     elif mode == "fused_graph":
         eng.run(st, T, seed, cuda_graph=True)
         _assert_equal(st, spec, {k: g["traj_" + k][T - 1] for k in PREDPREY_KEYS}, (case, mode))
@@ -99,7 +105,9 @@ def test_fused_steps_match_oracle_on_seeded_grids(shape, n_pred, n_prey, f64):
     T, seed = 12, 2026
     for t in range(T):
         port.step(t, seed)
-    eng.run(st, T, seed)
+    if f64:
+        st.sort_by_cell()
+    eng.run(st, T, seed, resort_every=4 if f64 else 0)
     _assert_equal(st, spec, port.snapshot(), (shape, "fused"))
     alive_pred, alive_prey, grown = eng.census(st)
     assert alive_pred == int((port.pred_energy > 0).sum()) and alive_prey == int((port.prey_energy > 0).sum())
@@ -280,11 +288,16 @@ def test_baseline_size_properties():
     st0 = PredPreyState.from_reference(spec, pos(n_pred), 30 + 71 * torch.rand(n_pred, 1, generator=g, device=DEV), pos(n_prey),
                                        40 + 61 * torch.rand(n_prey, 1, generator=g, device=DEV), (cd <= 0).long(), cd)
     eng = PredPreyEngine(spec, DEV)
-    a, b = st0.clone(), st0.clone()
+    a, b, c = st0.clone(), st0.clone(), st0.clone()
     eng.run(a, 10, 99, cuda_graph=True)
     eng.run(b, 4, 99, cuda_graph=False); eng.run(b, 6, 99, t0=4, cuda_graph=True)
     for k in ("pred_cell", "pred_energy", "prey_cell", "prey_energy", "info", "countdown"):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
+    c.sort_by_cell()                                   # the cell-sorted slot order changes nothing but the speed
+    eng.run(c, 10, 99, cuda_graph=True, resort_every=4)
+    for k in ("pred_cell", "pred_energy", "prey_cell", "prey_energy"):
+        assert torch.equal(getattr(a, k), c.in_agent_order(k)), k
+    assert torch.equal(a.info, c.info) and torch.equal(a.countdown, c.countdown)
     # grass: stage <=> countdown <= 0 after every grow; countdowns stay in [-(steps), regrowth]
     from agenttorch_b200.predprey import unpack_stage
     stage = unpack_stage(a.info, C).reshape(-1)
