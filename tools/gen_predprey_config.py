@@ -69,7 +69,8 @@ cfg = {
     "simulation_metadata": {
         "device": "auto", "num_episodes": 3, "num_steps_per_episode": 20, "num_substeps_per_step": 4, "calibration": False,
         "visualize": False, "seed": 0, "max_x": 64, "max_y": 64, "num_predators": 400, "num_prey": 800, "num_grass": 4096,
-        "cuda_params": {"fused_episode": True, "cuda_graph": True, "inplace_progress": False},
+        "cuda_params": {"fused_episode": True, "cuda_graph": True, "inplace_progress": False, "sort_agents_by_cell": True,
+                        "resort_every": 0},
     },
     "state": {
         "environment": {"bounds": prop("Bounds", [2], "int", value=[M % "max_x", M % "max_y"])},

@@ -14,7 +14,7 @@ ap.add_argument("--reps", type=int, default=7)
 ap.add_argument("--f64", type=int, default=0)
 ap.add_argument("--grid", type=int, default=0)
 ap.add_argument("--sort", type=int, default=1)
-ap.add_argument("--resort", type=int, default=32)
+ap.add_argument("--resort", type=int, default=0)
 args = ap.parse_args()
 dev = "cuda:0"
 mx = my = args.side
