@@ -54,21 +54,39 @@ static int default_grid() {
 __device__ __forceinline__ uint32_t cell_info(const uint8_t* info, int cell) {
     return (uint32_t)__ldcg(info + cell);          // measured: .cg / .nc / default loads all time the same here
 }
+// (measured: aggregating the marks of a warp per word with __match_any_sync costs 2.4x more than the atomics it saves)
 __device__ __forceinline__ void mark_cell(uint8_t* info, int cell, uint32_t bits) {
     atomicOr(reinterpret_cast<uint32_t*>(info) + (cell >> 2), bits << (8 * (cell & 3)));     // OR: order-independent
 }
 
+// cell / width without a hardware division: q = (cell * mul) >> (31 + log2ceil(width)), exact for 0 <= cell < 2^31
+// (round-up method of Granlund & Montgomery; mul = floor(2^(31+l) / width) + 1 fits in 32 bits)
+struct FastDiv { uint32_t mul; uint32_t shift; };
+static FastDiv make_fastdiv(uint32_t d) {
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    FastDiv f;
+    f.mul = (uint32_t)(((1ull << (31 + l)) / d) + 1ull);
+    f.shift = 31 + l;
+    return f;
+}
+__device__ __forceinline__ int fast_div(int n, FastDiv f) { return (int)(((uint64_t)(uint32_t)n * f.mul) >> f.shift); }
+
 // neighbour number (draw * count) >> 24 of the ascending list [k - width, k - 1, k + 1, k + width] (those that exist)
-__device__ __forceinline__ int lattice_step(int cell, uint32_t draw24, int width, int64_t n_cells) {
-    const int i = cell % width;
-    const bool up = cell - width >= 0, left = i > 0, right = i < width - 1, down = (int64_t)cell + width < n_cells;
+__device__ __forceinline__ int lattice_step(int cell, uint32_t draw24, int width, int n_cells, FastDiv fd) {
+    const int i = cell - fast_div(cell, fd) * width;
+    const bool up = cell >= width, left = i > 0, right = i < width - 1, down = cell < n_cells - width;
     const int cnt = (int)up + (int)left + (int)right + (int)down;
     if (cnt == 0) return cell;
-    int k = (int)((draw24 * (uint32_t)cnt) >> 24);
-    if (up) { if (k == 0) return cell - width; --k; }
-    if (left) { if (k == 0) return cell - 1; --k; }
-    if (right) { if (k == 0) return cell + 1; --k; }
-    return cell + width;
+    const int k = (int)((draw24 * (uint32_t)cnt) >> 24);
+    // k-th existing neighbour, branch-free: position of each candidate in the ascending list
+    const int p_left = (int)up, p_right = p_left + (int)left, p_down = p_right + (int)right;
+    int next = cell + width;                                                     // k == p_down
+    next = (right && k == p_right) ? cell + 1 : next;
+    next = (left && k == p_left) ? cell - 1 : next;
+    next = (up && k == 0) ? cell - width : next;
+    (void)p_down;
+    return next;
 }
 
 __global__ void __launch_bounds__(PP_THREADS)
@@ -82,53 +100,110 @@ pp_occupancy_kernel(at_pp_launch a)
     }
 }
 
-__global__ void __launch_bounds__(PP_THREADS)
-pp_agent_kernel(at_pp_model m, at_pp_launch a)
-{
-    const int flags = a.flags;
-    const int64_t n = a.n_pred + a.n_prey;
-    const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
-    const uint32_t t = (uint32_t)(a.t_move + (a.t_ptr ? *a.t_ptr : 0));
-    const bool look = (flags & (AT_PP_EAT | AT_PP_HUNT)) != 0;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-        const bool prey = idx >= a.n_pred;
-        const int64_t i = prey ? idx - a.n_pred : idx;
-        int32_t* cell_p = (prey ? a.prey_cell : a.pred_cell) + i;
-        float* energy_p = (prey ? a.prey_energy : a.pred_energy) + i;
-        const int cell0 = *cell_p;
-        const float e0 = *energy_p;
-        int cell = cell0;
-        float e = e0;
-        const uint32_t here = look ? cell_info(a.info, cell) : 0u;                  // ONE random access answers everything
-        if (prey) {
-            if ((flags & AT_PP_EAT) && (here & PP_GROWN)) {                           // eat.py:41, :93-97
+// One species.  A thread owns 4 consecutive agent slots (one 16-byte load per array, four independent cell lookups
+// in flight), the last n % 4 slots are handled one by one.  EAT (prey), HUNT, then MOVE.
+template <bool PREY>
+struct AgentPass {
+    const at_pp_model& m;
+    const at_pp_launch& a;
+    FastDiv fd;
+    uint64_t seed;
+    uint32_t t;
+    int flags;
+    bool look, move, eat, hunt, mark_eaten, apply_work;
+    uint32_t other_here, my_mark;
+    float work;
+    const int32_t* __restrict__ ids;
+
+    __device__ __forceinline__ AgentPass(const at_pp_model& m_, const at_pp_launch& a_, FastDiv fd_, uint64_t seed_, uint32_t t_)
+        : m(m_), a(a_), fd(fd_), seed(seed_), t(t_) {
+        flags = a.flags;
+        look = (flags & (AT_PP_EAT | AT_PP_HUNT)) != 0;
+        move = (flags & AT_PP_MOVE) != 0;
+        eat = PREY && (flags & AT_PP_EAT);
+        hunt = (flags & AT_PP_HUNT) != 0;
+        mark_eaten = !(flags & AT_PP_EAT_IMPLICIT);
+        other_here = PREY ? PP_OCC_PRED(a.occ_in) : PP_OCC_PREY(a.occ_in);
+        my_mark = a.occ_out >= 0 ? (PREY ? PP_OCC_PREY(a.occ_out) : PP_OCC_PRED(a.occ_out)) : 0u;
+        apply_work = PREY ? m.apply_prey_work : m.apply_pred_work;
+        work = -(PREY ? m.prey_work : m.pred_work);
+        ids = PREY ? a.prey_id : a.pred_id;
+    }
+
+    // `here` = info byte of the agent's cell (0 when nothing looks at it)
+    __device__ __forceinline__ void one(int slot, int id, uint32_t here, int& cell, float& e) const {
+        if (PREY) {
+            if (eat && (here & PP_GROWN)) {                                           // eat.py:41, :93-97
                 e = __fadd_rn(e, m.grass_nutrition);
-                if (!(flags & AT_PP_EAT_IMPLICIT) && !(here & PP_EATEN)) mark_cell(a.info, cell, PP_EATEN);
+                if (mark_eaten && !(here & PP_EATEN)) mark_cell(a.info, cell, PP_EATEN);
             }
-            if ((flags & AT_PP_HUNT) && (here & PP_OCC_PRED(a.occ_in))) e = 0.0f;      // hunt.py:81
+            if (hunt && (here & other_here)) e = 0.0f;                                // hunt.py:81
         } else {
-            if ((flags & AT_PP_HUNT) && (here & PP_OCC_PREY(a.occ_in))) e = __fadd_rn(e, m.prey_nutrition);   // hunt.py:83-86
+            if (hunt && (here & other_here)) e = __fadd_rn(e, m.prey_nutrition);      // hunt.py:83-86
         }
-        if (flags & AT_PP_MOVE) {
+        if (move) {
             if (e > 0.0f) {                                                         // move.py:89
-                const int32_t* ids = prey ? a.prey_id : a.pred_id;                  // draws follow the agent, not its slot
-                const uint64_t who = ids ? (uint64_t)(uint32_t)ids[i] : (uint64_t)i;
-                const uint64_t z = at_noise_u64(seed, t, ((uint64_t)(prey ? 1 : 0) << PP_SPECIES_BIT) | who);
-                const uint32_t draw = (uint32_t)(z >> 40);
+                // draws follow the agent number, not the slot
+                const uint64_t who = ((uint64_t)(PREY ? 1 : 0) << PP_SPECIES_BIT) | (uint64_t)(uint32_t)id;
+                const uint32_t draw = (uint32_t)(at_noise_u64(seed, t, who) >> 40);
                 if (a.nbr_ptr == nullptr) {
-                    cell = lattice_step(cell, draw, m.width, m.n_cells);
+                    cell = lattice_step(cell, draw, m.width, (int)m.n_cells, fd);
                 } else {
                     const int64_t lo = a.nbr_ptr[cell], cnt = a.nbr_ptr[cell + 1] - lo;
                     if (cnt > 0) cell = a.nbr_idx[lo + (int64_t)(((uint64_t)draw * (uint64_t)cnt) >> 24)];
                 }
             }
-            if (prey ? m.apply_prey_work : m.apply_pred_work)                       // move.py:112-116
-                e = __fadd_rn(e, -(prey ? m.prey_work : m.pred_work));
-            if (a.occ_out >= 0) mark_cell(a.info, cell, prey ? PP_OCC_PREY(a.occ_out) : PP_OCC_PRED(a.occ_out));
+            if (apply_work) e = __fadd_rn(e, work);                                 // move.py:112-116
+            if (my_mark) mark_cell(a.info, cell, my_mark);
         }
-        if (cell != cell0) *cell_p = cell;
-        if (e != e0) *energy_p = e;
+        (void)slot;
     }
+
+    __device__ __forceinline__ void run(bool vec) const {
+        const int n = (int)(PREY ? a.n_prey : a.n_pred);
+        int32_t* __restrict__ cells = PREY ? a.prey_cell : a.pred_cell;
+        float* __restrict__ energies = PREY ? a.prey_energy : a.pred_energy;
+        const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+        const int n4 = vec ? n >> 2 : 0;
+        for (int q = tid; q < n4; q += nthr) {
+            // the agent arrays stream through once per launch: evict-first, so that the info bytes stay in L2
+            const int4 c0 = __ldcs(reinterpret_cast<const int4*>(cells) + q);
+            const float4 e0 = __ldcs(reinterpret_cast<const float4*>(energies) + q);
+            int4 id = make_int4(4 * q, 4 * q + 1, 4 * q + 2, 4 * q + 3);
+            if (ids != nullptr && move) id = __ldcs(reinterpret_cast<const int4*>(ids) + q);
+            uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+            if (look) {                                              // four independent lookups in flight
+                h0 = cell_info(a.info, c0.x); h1 = cell_info(a.info, c0.y);
+                h2 = cell_info(a.info, c0.z); h3 = cell_info(a.info, c0.w);
+            }
+            int4 c = c0;
+            float4 e = e0;
+            one(4 * q, id.x, h0, c.x, e.x);
+            one(4 * q + 1, id.y, h1, c.y, e.y);
+            one(4 * q + 2, id.z, h2, c.z, e.z);
+            one(4 * q + 3, id.w, h3, c.w, e.w);
+            if (c.x != c0.x || c.y != c0.y || c.z != c0.z || c.w != c0.w) __stcs(reinterpret_cast<int4*>(cells) + q, c);
+            if (e.x != e0.x || e.y != e0.y || e.z != e0.z || e.w != e0.w) __stcs(reinterpret_cast<float4*>(energies) + q, e);
+        }
+        for (int i = 4 * n4 + tid; i < n; i += nthr) {
+            const int cell0 = __ldcs(cells + i);
+            const float e0 = __ldcs(energies + i);
+            int cell = cell0;
+            float e = e0;
+            one(i, ids ? __ldcs(ids + i) : i, look ? cell_info(a.info, cell) : 0u, cell, e);
+            if (cell != cell0) __stcs(cells + i, cell);
+            if (e != e0) __stcs(energies + i, e);
+        }
+    }
+};
+
+__global__ void __launch_bounds__(PP_THREADS)
+pp_agent_kernel(at_pp_model m, at_pp_launch a, FastDiv fd, int vec_pred, int vec_prey)
+{
+    const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
+    const uint32_t t = (uint32_t)(a.t_move + (a.t_ptr ? *a.t_ptr : 0));
+    AgentPass<false>(m, a, fd, seed, t).run(vec_pred != 0);
+    AgentPass<true>(m, a, fd, seed, t).run(vec_prey != 0);
 }
 
 // thread <-> 4 consecutive cells: one 32-bit info word + one 16/32-byte countdown vector
@@ -155,10 +230,10 @@ pp_cell_kernel(at_pp_model m, at_pp_launch a)
             T c[4];
             if (full) {
                 if constexpr (sizeof(T) == 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(cd + c0);
+                    const float4 v = __ldcs(reinterpret_cast<const float4*>(cd + c0));
                     c[0] = (T)v.x; c[1] = (T)v.y; c[2] = (T)v.z; c[3] = (T)v.w;
                 } else {
-                    const double2 v0 = *reinterpret_cast<const double2*>(cd + c0), v1 = *reinterpret_cast<const double2*>(cd + c0 + 2);
+                    const double2 v0 = __ldcs(reinterpret_cast<const double2*>(cd + c0)), v1 = __ldcs(reinterpret_cast<const double2*>(cd + c0 + 2));
                     c[0] = (T)v0.x; c[1] = (T)v0.y; c[2] = (T)v1.x; c[3] = (T)v1.y;
                 }
             } else {
@@ -181,10 +256,10 @@ pp_cell_kernel(at_pp_model m, at_pp_launch a)
             }
             if (full) {
                 if constexpr (sizeof(T) == 4) {
-                    *reinterpret_cast<float4*>(cd + c0) = make_float4((float)c[0], (float)c[1], (float)c[2], (float)c[3]);
+                    __stcs(reinterpret_cast<float4*>(cd + c0), make_float4((float)c[0], (float)c[1], (float)c[2], (float)c[3]));
                 } else {
-                    *reinterpret_cast<double2*>(cd + c0) = make_double2((double)c[0], (double)c[1]);
-                    *reinterpret_cast<double2*>(cd + c0 + 2) = make_double2((double)c[2], (double)c[3]);
+                    __stcs(reinterpret_cast<double2*>(cd + c0), make_double2((double)c[0], (double)c[1]));
+                    __stcs(reinterpret_cast<double2*>(cd + c0 + 2), make_double2((double)c[2], (double)c[3]));
                 }
             } else {
 #pragma unroll
@@ -293,7 +368,8 @@ int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* strea
     const int flags = a.flags;
     if (m.n_cells <= 0 || m.n_cells > 0x7fffffffll) return fail("at_pp_step: %s", "n_cells must be in [1, 2^31)");
     if (m.width <= 0 || m.max_y <= 0) return fail("at_pp_step: %s", "width and max_y must be positive");
-    if (a.n_pred < 0 || a.n_prey < 0) return fail("at_pp_step: %s", "negative agent count");
+    if (a.n_pred < 0 || a.n_prey < 0 || a.n_pred > 0x7fffffffll || a.n_prey > 0x7fffffffll)
+        return fail("at_pp_step: %s", "agent counts must be in [0, 2^31)");
     const int64_t n = a.n_pred + a.n_prey;
     const int agent_flags = flags & (AT_PP_EAT | AT_PP_HUNT | AT_PP_MOVE);
     const int cell_flags = flags & (AT_PP_EAT_APPLY | AT_PP_GROW | AT_PP_CLEAR);
@@ -315,7 +391,12 @@ int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* strea
         if (check("pp_occupancy_kernel launch")) return 1;
     }
     if (agent_flags && n > 0) {
-        pp_agent_kernel<<<blocks_for(n, a.grid), PP_THREADS, 0, s>>>(m, a);
+        // 16-byte vector access when the arrays allow it (torch allocations do; odd views fall back to scalar access)
+        auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+        const int vec_pred = aligned(a.pred_cell) && aligned(a.pred_energy) && aligned(a.pred_id);
+        const int vec_prey = aligned(a.prey_cell) && aligned(a.prey_energy) && aligned(a.prey_id);
+        const int64_t longest = a.n_pred > a.n_prey ? a.n_pred : a.n_prey;
+        pp_agent_kernel<<<blocks_for((longest + 3) / 4 + 3, a.grid), PP_THREADS, 0, s>>>(m, a, make_fastdiv((uint32_t)m.width), vec_pred, vec_prey);
         if (check("pp_agent_kernel launch")) return 1;
     }
     if (cell_flags) {
