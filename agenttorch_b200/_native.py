@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libat_seirm.so")
 SRC_PATH = os.path.join(_PKG, "csrc", "at_seirm.cu")
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_SFS, MAX_SFI, MAX_LAMGAMMA = 16, 8, 84
 TIMER_F32, TIMER_I16 = 0, 1
 AGE_F32, AGE_U8 = 0, 1
@@ -27,7 +27,8 @@ MAX_BLOCKS = 64
 EXPORTS = [
     "at_seirm_abi_version", "at_last_error", "at_seirm_sizeof_launch", "at_seirm_sizeof_model",
     "at_seirm_workspace_bytes", "at_seirm_max_block_size", "at_seirm_step",
-    "at_seirm_episode_backward", "at_seirm_hot_from_code", "at_seirm_pull_codes", "at_noise_fill",
+    "at_seirm_episode_backward", "at_seirm_hot_from_code", "at_seirm_pull_codes", "at_seirm_exchange_bytes",
+    "at_seirm_exchange_sparse", "at_noise_fill",
 ]
 
 
@@ -125,6 +126,12 @@ def lib():
         L.at_seirm_pull_codes.restype = ctypes.c_int
         L.at_seirm_pull_codes.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                           ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+        L.at_seirm_exchange_bytes.restype = ctypes.c_int64
+        L.at_seirm_exchange_bytes.argtypes = [ctypes.c_int64]
+        L.at_seirm_exchange_sparse.restype = ctypes.c_int
+        L.at_seirm_exchange_sparse.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
+                                               ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_void_p]
         L.at_noise_fill.restype = ctypes.c_int
         L.at_noise_fill.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32,
                                     ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]

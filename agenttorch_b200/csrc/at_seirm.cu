@@ -777,6 +777,102 @@ hot_from_code_kernel(uint8_t* __restrict__ code, int64_t n_sources, uint32_t* __
     if (filter != nullptr && __syncthreads_or(seen != 0u) && threadIdx.x == 0) atomicOr(&filter[hash_words], 1u);
 }
 
+// Sparse, barrier-free halo exchange.  Every rank keeps ONE symmetric (peer-mapped) buffer per parity:
+//   [ code bytes : n ][ hot bitmap : n/8 (+64) ][ arrival flags : 64 words ]
+// Its step kernel writes the code bytes and the hot-bitmap words of its OWN slice.  This kernel then
+//   1. tells every peer "my slice of this buffer is written" (a release store of the buffer's epoch into the peer's
+//      flag word for this rank) and waits until every peer has said the same — the per-step barrier, inside the
+//      kernel that needs it;
+//   2. reads the peers' bitmap slices (1 bit per agent) and pulls a 32-byte code sector only where a bitmap word is
+//      non-zero (about a quarter of the sectors at 1 % infectious, none in a step without infectious agents),
+//      zeroing local sectors whose word just became zero;
+//   3. folds the whole bitmap (own slice included) into the hashed filter.
+// Double-buffering by step parity makes one rendezvous per step sufficient: a rank overwrites a buffer two steps
+// later, after a rendezvous on the other buffer that every peer only joins once it has finished reading this one.
+#define AT_XCHG_FLAG_WORDS 64
+#define AT_XCHG_BITMAP_PAD 64
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct PeerBufs { uint8_t* p[16]; };
+
+__global__ void __launch_bounds__(256)
+exchange_sparse_kernel(uint8_t* __restrict__ local, int64_t n_sources, uint32_t* __restrict__ filter, int hash_words,
+                       PeerBufs peers, int world, int rank, int64_t per, uint32_t* sync_state, int32_t* error_flag)
+{
+    __shared__ uint32_t s_epoch;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(sync_state) + 1u;
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
+    const size_t flag_off = (size_t)n_sources + (size_t)(n_sources >> 3) + AT_XCHG_BITMAP_PAD;
+    if (tid < world && tid != rank) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<uint32_t*>(peers.p[tid] + flag_off) + rank, epoch);
+        }
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(local + flag_off) + tid;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (clock64() - t0 > 40000000000ll) {            // ~20 s: a peer never arrived; report instead of hanging
+                if (error_flag) *error_flag = 2;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+
+    uint32_t* hot_local = reinterpret_cast<uint32_t*>(local + n_sources);
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + tid) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_words = n_sources >> 5;
+    uint32_t seen = 0;
+    for (int64_t w0 = warp_id * 32; w0 < n_words; w0 += n_warps * 32) {
+        const int64_t w = w0 + lane;                          // a 1024-source tile never straddles two slices
+        uint32_t word = 0;
+        if (w < n_words) {
+            const int owner = (int)((w0 * 32) / per);
+            if (owner == rank) {
+                word = hot_local[w];
+            } else {
+                const uint8_t* peer = peers.p[owner];
+                word = __ldcv(reinterpret_cast<const uint32_t*>(peer + n_sources) + w);     // never from a stale L1 line
+                const uint32_t old = hot_local[w];
+                uint4* dst = reinterpret_cast<uint4*>(local + w * 32);
+                if (word != 0u) {
+                    const uint4* src = reinterpret_cast<const uint4*>(peer + w * 32);
+                    const uint4 a = __ldcv(src), b = __ldcv(src + 1);
+                    dst[0] = a; dst[1] = b;
+                } else if (old != 0u) {
+                    dst[0] = make_uint4(0, 0, 0, 0); dst[1] = make_uint4(0, 0, 0, 0);
+                }
+                if (word != old) hot_local[w] = word;
+            }
+            if (word != 0u && filter != nullptr) atomicOr(&filter[w & (hash_words - 1)], word);
+        }
+        seen |= word;
+    }
+    if (filter != nullptr && __syncthreads_or(seen != 0u) && tid == 0) atomicOr(&filter[hash_words], 1u);
+    // the last CTA to finish publishes the epoch (every CTA has read the old value by then)
+    __shared__ int s_last;
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(reinterpret_cast<int*>(sync_state) + 1, 1) == (int)gridDim.x - 1;
+        if (s_last) {
+            reinterpret_cast<int*>(sync_state)[1] = 0;
+            *reinterpret_cast<volatile uint32_t*>(sync_state) = epoch;
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------- backward kernel
 // grad_r[t] = gI[t]*sum_dne[t] + sum_i dne[t,i] * c_i,  c_i = gD[recovered_step_i] * M / 2
 #define AT_BWD_THREADS 256
@@ -1055,6 +1151,42 @@ static int hot_from_code_impl(uint8_t* code, int64_t n_sources, uint32_t* hot_bi
 int at_seirm_hot_from_code(const uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, uint32_t* hot_filter,
                            int32_t hash_words, void* stream) {
     return hot_from_code_impl(const_cast<uint8_t*>(code), n_sources, hot_bitmap, hot_filter, hash_words, nullptr, 1, 0, stream);
+}
+
+int64_t at_seirm_exchange_bytes(int64_t n_sources) {
+    return n_sources + (n_sources >> 3) + AT_XCHG_BITMAP_PAD + AT_XCHG_FLAG_WORDS * 4;
+}
+
+int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* hot_filter, int32_t hash_words,
+                             void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, int32_t* error_flag,
+                             void* stream) {
+    if (!local_buf || !peer_buf || !sync_state) return fail("%s", "exchange_sparse: null buffer");
+    if (n_sources <= 0 || (n_sources & 1023)) return fail("%s", "exchange_sparse: n_sources must be a positive multiple of 1024");
+    if (world < 2 || world > 16 || rank < 0 || rank >= world || (n_sources % world) || ((n_sources / world) & 1023))
+        return fail("%s", "exchange_sparse: 2..16 ranks owning equal slices of whole 1024-source tiles are required");
+    if (hot_filter && (hash_words < 32 || (hash_words & (hash_words - 1)))) return fail("%s", "hash_words must be a power of two >= 32");
+    if (device_props()) return fail("%s", "cannot query device");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (hot_filter) {
+        cudaError_t e = cudaMemsetAsync(hot_filter, 0, ((size_t)hash_words + 1) * 4, s);
+        if (e != cudaSuccess) return fail("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
+    PeerBufs pb;
+    memset(&pb, 0, sizeof(pb));
+    for (int r = 0; r < world; ++r) {
+        if (!peer_buf[r]) return fail("%s", "exchange_sparse: null peer pointer");
+        pb.p[r] = (uint8_t*)peer_buf[r];
+    }
+    if (pb.p[rank] != local_buf) return fail("%s", "exchange_sparse: peer_buf[rank] must be the local buffer");
+    // every CTA spins on the arrival flags: keep all of them co-resident (one wave)
+    int64_t tiles = (n_sources / 32 + 255) / 256;
+    int grid = (int)(tiles < g_sm_count * 4 ? tiles : g_sm_count * 4);
+    if (grid < 1) grid = 1;
+    exchange_sparse_kernel<<<grid, 256, 0, s>>>(local_buf, n_sources, hot_filter, hash_words, pb, world, rank, n_sources / world,
+                                                sync_state, error_flag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("exchange_sparse_kernel launch: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 int at_seirm_pull_codes(uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, uint32_t* hot_filter, int32_t hash_words,

@@ -30,10 +30,12 @@ class _EpisodeFn(torch.autograd.Function):
         eng, st = runner.engine, runner.local_state
         noise = NoiseSpec(seed=runner.episode_seed(), isolation="soft")
         sv = eng.run_episode(st, r_steps, m_value, num_steps, noise, want_grad=want_grad, cuda_graph=eng.code_hdl is not None)
-        di, dd = st.daily_infected.clone(), st.daily_deaths.clone()
         if eng.pg is not None:
-            dist.all_reduce(di, group=eng.pg)
-            dist.all_reduce(dd, group=eng.pg)
+            from .parallel import reduce_daily_series
+
+            di, dd = reduce_daily_series(st, eng.pg)
+        else:
+            di, dd = st.daily_infected.clone(), st.daily_deaths.clone()
         ctx.runner, ctx.sv, ctx.num_steps, ctx.want_grad = runner, sv, num_steps, want_grad
         ctx.save_for_backward(m_value)
         ctx.r_shape, ctx.m_shape = r_steps.shape, m_value.shape

@@ -141,7 +141,7 @@ def _ptr(t, dtype=None, name="tensor"):
 
 class SeirmEngine:
     def __init__(self, graph, spec: SeirmSpec, process_group=None, grid=0, code_len=None, block_size=None,
-                 tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0, hashed=None, hash_words=None, hash_min_warps=20, symmetric=None):
+                 tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0, hashed=None, hash_words=None, hash_min_warps=20, symmetric=None, sparse_exchange=True):
         """graph: ContactGraph (plain CSR, re-blocked here) or a prebuilt BlockedGraph.  block_size: sources
         per column block (default: the largest that fits the shared-memory bitmap, i.e. as few blocks as
         possible); code_len: length of the code/bitmap arrays (multi-GPU: world_size equal slices)."""
@@ -204,21 +204,32 @@ class SeirmEngine:
         # device-side barrier + peer copies over NVLink that can be captured into the episode's CUDA graph (NCCL
         # collectives could not).  symmetric=None: try, fall back to the NCCL all-gather.
         self.code_hdl = None
+        self.sparse_exchange = bool(sparse_exchange)
         if process_group is not None and symmetric is not False:
             try:
                 import torch.distributed._symmetric_memory as symm
 
-                self.code = [symm.empty(self.n_code, dtype=torch.uint8, device=dev) for _ in range(2)]
-                self.code_hdl = [symm.rendezvous(c, process_group) for c in self.code]
-                for c in self.code:
+                # one symmetric buffer per step parity: [code bytes][hot bitmap][arrival flags] (include/at_seirm.h,
+                # at_seirm_exchange_sparse); the step kernel writes this rank's slice of the first two parts
+                nbytes = int(self.lib.at_seirm_exchange_bytes(self.n_code))
+                self.xbuf = [symm.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+                self.code_hdl = [symm.rendezvous(c, process_group) for c in self.xbuf]
+                for c in self.xbuf:
                     c.zero_()
+                self.code = [c[: self.n_code] for c in self.xbuf]
+                self.hot = [c[self.n_code: self.n_code + self.n_code // 8 + 16].view(torch.int32) for c in self.xbuf]
+                self.xsync = [torch.zeros(4, dtype=torch.int32, device=dev) for _ in range(2)]
+                torch.cuda.synchronize(dev)
+                import torch.distributed as dist
+
+                dist.barrier(group=process_group)               # nobody signals into a buffer that is still being zeroed
             except Exception:
                 if symmetric is True:
                     raise
                 self.code_hdl = None
         if self.code_hdl is None:
             self.code = [torch.zeros(self.n_code, dtype=torch.uint8, device=dev) for _ in range(2)]
-        self.hot = [torch.zeros(self.n_code // 32 + 4, dtype=torch.int32, device=dev) for _ in range(2)]
+            self.hot = [torch.zeros(self.n_code // 32 + 4, dtype=torch.int32, device=dev) for _ in range(2)]
         self.cur = 0
         # hashed mode on one GPU: the folded filter of each hot bitmap, produced by the launch that writes the bitmap
         self.filt = None
@@ -346,12 +357,20 @@ class SeirmEngine:
 
             hdl = self.code_hdl[buf_index]
             world, rank = dist.get_world_size(self.pg), dist.get_rank(self.pg)
-            hdl.barrier(channel=buf_index)                       # every rank has written its slice of this buffer
             ptrs = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
-            # fused: pull the peers' slices over NVLink (P2P loads) + rebuild bitmap/filter, one kernel
-            nat.check(self.lib.at_seirm_pull_codes(_ptr(self.code[buf_index]), int(self.n_code), _ptr(self.hot[buf_index]),
-                                                   _ptr(filt), int(self.graph.hash_words), ptrs, world, rank,
-                                                   ctypes.c_void_p(stream)))
+            if self.sparse_exchange:
+                # one kernel: rendezvous (arrival flags in the peers' buffers) + bitmap-directed pull over NVLink
+                # (P2P loads of the non-empty 32-byte code sectors only) + filter fold
+                nat.check(self.lib.at_seirm_exchange_sparse(_ptr(self.xbuf[buf_index]), int(self.n_code), _ptr(filt),
+                                                            int(self.graph.hash_words), ptrs, world, rank,
+                                                            _ptr(self.xsync[buf_index]), _ptr(self.error_flag),
+                                                            ctypes.c_void_p(stream)))
+            else:
+                hdl.barrier(channel=buf_index)                   # every rank has written its slice of this buffer
+                # dense: pull the peers' whole slices (P2P loads) + rebuild bitmap/filter from the codes, one kernel
+                nat.check(self.lib.at_seirm_pull_codes(_ptr(self.code[buf_index]), int(self.n_code), _ptr(self.hot[buf_index]),
+                                                       _ptr(filt), int(self.graph.hash_words), ptrs, world, rank,
+                                                       ctypes.c_void_p(stream)))
         else:
             halo_exchange(self.code[buf_index], None, self.n_code, self.pg)
             nat.check(self.lib.at_seirm_hot_from_code(_ptr(self.code[buf_index]), int(self.n_code), _ptr(self.hot[buf_index]),
@@ -488,12 +507,16 @@ class SeirmEngine:
         if self.pg is not None:
             import torch.distributed as dist
 
-            dist.all_reduce(grad_r, group=self.pg)
-            dist.all_reduce(grad_m, group=self.pg)
+            packed = torch.cat([grad_r, grad_m])               # one small all-reduce instead of two
+            dist.all_reduce(packed, group=self.pg)
+            grad_r, grad_m = packed[:num_steps].clone(), packed[num_steps:].clone()
         return grad_r, grad_m
 
     def check_errors(self):
-        if int(self.error_flag.item()) != 0:
+        code = int(self.error_flag.item())
+        if code == 2:
+            raise RuntimeError("halo exchange: a peer rank never arrived at the rendezvous (at_seirm_exchange_sparse timed out)")
+        if code != 0:
             raise RuntimeError("lam_gamma_integrals index out of range during the episode (SURVEY.md A.2 Q10)")
 
 

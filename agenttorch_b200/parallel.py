@@ -37,3 +37,15 @@ def reduce_episode_outputs(tensors, group=None):
         for t in tensors:
             dist.all_reduce(t, group=group)
     return tensors
+
+
+def reduce_daily_series(state, group=None):
+    """(daily_infected, daily_deaths) summed over the ranks with ONE small all-reduce (the two series packed)."""
+    di, dd = state.daily_infected, state.daily_deaths
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return di.clone(), dd.clone()
+    packed = torch.cat([di.reshape(-1), dd.reshape(-1)])
+    if dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, group=group)
+    n = di.numel()
+    return packed[:n].reshape(di.shape).clone(), packed[n:].reshape(dd.shape).clone()

@@ -274,6 +274,8 @@ def ours(args):
         final_di = runner.state["environment"]["daily_infected"].detach().sum().item()
     else:
         # ---- N>1: agents sharded by contiguous id range; per-step halo exchange of the infectiousness code/bitmap
+        from agenttorch_b200.parallel import reduce_daily_series
+
         bounds = shard_bounds(N, world)
         r0, r1 = bounds[rank]
         age_all, stage_all = synthetic_population(N, SEED, device=dev)
@@ -302,8 +304,7 @@ def ours(args):
             st.daily_infected.zero_(); st.daily_deaths.zero_()
             sv = engine.run_episode(st, r_steps, m_val, T, NoiseSpec(seed=SEED, isolation="soft"), want_grad=True,
                                     cuda_graph=engine.code_hdl is not None)
-            di, dd = st.daily_infected.clone(), st.daily_deaths.clone()
-            dist.all_reduce(di); dist.all_reduce(dd)
+            di, dd = reduce_daily_series(st, pg)                 # one packed all-reduce
             gr, gm = engine.episode_backward(sv, T, gI, gD, m_val)
             if to_host:
                 out_host.copy_(torch.cat([di, dd, gr, gm]), non_blocking=True)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AT_SEIRM_ABI_VERSION 6
+#define AT_SEIRM_ABI_VERSION 7
 #define AT_MAX_SFS 16        /* SFSusceptibility entries (config.yaml has 9)                     */
 #define AT_MAX_SFI 8         /* SFInfector entries (config.yaml has 5)                           */
 #define AT_MAX_LAMGAMMA 84   /* lam_gamma_integrals entries; 1 + 3*K infectiousness codes fit a byte */
@@ -209,6 +209,21 @@ int at_seirm_hot_from_code(const uint8_t* code, int64_t n_sources, uint32_t* hot
  */
 int at_seirm_pull_codes(uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, uint32_t* hot_filter, int32_t hash_words,
                         const void* const* peer_code, int32_t world, int32_t rank, void* stream);
+
+/*
+ * at_seirm_exchange_sparse — the per-step halo exchange as ONE kernel with the rendezvous inside (no separate barrier,
+ * no communicator).  Each rank owns one symmetric (peer-mapped) buffer per step parity of at_seirm_exchange_bytes(n)
+ * bytes: [code : n][hot bitmap : n/8 (+64)][arrival flags]; point at_seirm_launch.code_* / hot_bitmap_* at its first
+ * two parts.  peer_buf is a HOST array of `world` device pointers (peer_buf[rank] == local_buf).  The kernel signals
+ * "my slice is written" to every peer, waits for theirs, pulls 32-byte code sectors only where a peer's bitmap word is
+ * non-zero, and folds the whole bitmap into hot_filter (may be NULL).  sync_state: 2 zero-initialised device words
+ * per buffer, owned by this call sequence.  A peer that never arrives sets *error_flag = 2 after ~20 s.
+ * Replaces nothing in the reference (core/distributed_runner.py:218-228 is `pass`).
+ */
+int64_t at_seirm_exchange_bytes(int64_t n_sources);
+int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* hot_filter, int32_t hash_words,
+                             void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, int32_t* error_flag,
+                             void* stream);
 
 /*
  * at_noise_fill — materialise the counter-hash noise (same values the step kernel generates in

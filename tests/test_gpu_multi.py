@@ -38,8 +38,11 @@ def _episode(rank, world, port, out_dir, cuda_graph):
     full = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, mean_interactions=mean_interactions_from_age(age))
     graph = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, row_begin=r0, row_end=r1)
     graph.i_bar, graph.i_bar_agent = full.i_bar, full.i_bar_agent
+    dense = cuda_graph == "dense"                                  # symmetric memory, barrier + whole-slice pull
+    cuda_graph = bool(cuda_graph)
     eng = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=shard_code_len(N, world),
-                      symmetric=None if cuda_graph else False)      # False: NCCL all-gather path
+                      symmetric=None if cuda_graph else False,      # False: NCCL all-gather path
+                      sparse_exchange=not dense)
     st = SeirmState.from_initial(stage0[r0:r1], age[r0:r1], T, dev)
     r_steps = torch.full((T,), 14.25, device=dev)
     m = torch.tensor([0.12], device=dev)
@@ -54,15 +57,18 @@ def _episode(rank, world, port, out_dir, cuda_graph):
     if world > 1:
         dist.all_reduce(di); dist.all_reduce(dd)
     gr, gm = eng.episode_backward(sv, T, torch.linspace(0.5, 1.5, T, device=dev), torch.linspace(2, 1, T, device=dev), m)
+    eng.check_errors()
     torch.save({"stage": st.stage.cpu(), "nst": st.next_stage_time.cpu(), "di": di.cpu(), "dd": dd.cpu(), "gr": gr.cpu(), "gm": gm.cpu(),
                 "bounds": bounds}, os.path.join(out_dir, f"w{world}_r{rank}.pt"))
     if world > 1:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cuda_graph", [False, True])
+@pytest.mark.parametrize("cuda_graph", [False, True, "dense"])
 def test_two_gpus_reproduce_one_gpu(tmp_path, cuda_graph):
-    """cuda_graph=True: symmetric-memory halo exchange (barrier + peer copies) replayed from one CUDA graph per rank"""
+    """False: NCCL all-gather, issued step by step.  True: symmetric memory, one kernel per step with the rendezvous
+    inside and a bitmap-directed sparse pull, the whole episode replayed from one CUDA graph per rank.
+    "dense": symmetric memory with a separate barrier and a whole-slice pull (the round-1 first version)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
