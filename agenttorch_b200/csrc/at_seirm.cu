@@ -42,6 +42,7 @@
 #define WS_ACC 0                    // int64[3]: sum ne, sum dne, deaths (fixed point)
 #define WS_TICKET 32                // int: CTAs finished (main kernel)
 #define WS_COUNTER 36               // int: group counter (main kernel)
+#define WS_ANYHOT 40                // uint: some agent of this rank is infectious in the step just encoded (read + reset by the exchange)
 #define WS_GCOUNTERS 64             // int[AT_MAX_BLOCKS]: group counters of the gather kernel
 #define WS_GTICKET 384              // int
 #define WS_BTICKET 512              // int: backward kernel
@@ -141,8 +142,8 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     const double ibar = (double)m.ibar;
     char* ws = reinterpret_cast<char*>(a.workspace);
 
-    __shared__ int s_any_hot;
-    if (tid == 0) s_any_hot = 0;
+    __shared__ int s_any_hot, s_any_out;
+    if (tid == 0) { s_any_hot = 0; s_any_out = 0; }
     // ---- tables: code -> (SFInfector[int(stage)], lam_gamma[idx]); code = 1 + sidx*K + idx
     if (tid < 256) {
         float av = 0.f, gv = 0.f;
@@ -392,7 +393,10 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             }
             const uint32_t hot = __ballot_sync(0xffffffffu, code != 0u);
             if (valid) a.code_out[a.row_offset + row] = (uint8_t)code;
-            if (lane == 0) a.hot_bitmap_out[(a.row_offset >> 5) + task] = hot;
+            if (lane == 0) {
+                a.hot_bitmap_out[(a.row_offset >> 5) + task] = hot;
+                if (hot != 0u) s_any_out = 1;                    // benign race: every writer stores 1
+            }
         }
         const uint32_t sus_o = __ballot_sync(0xffffffffu, is_s);
         const uint32_t exp_o = __ballot_sync(0xffffffffu, is_e);
@@ -676,6 +680,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             if (s0) atomicAdd(&acc[0], (unsigned long long)s0);
             if (s1) atomicAdd(&acc[1], (unsigned long long)s1);
             if (s2) atomicAdd(&acc[2], (unsigned long long)s2);
+            if (s_any_out) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_ANYHOT), 1u);
         }
         __threadfence();
         s_is_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
@@ -804,47 +809,71 @@ struct PeerBufs { uint8_t* p[16]; };
 
 __global__ void __launch_bounds__(256)
 exchange_sparse_kernel(uint8_t* __restrict__ local, int64_t n_sources, uint32_t* __restrict__ filter, int hash_words,
-                       PeerBufs peers, int world, int rank, int64_t per, uint32_t* sync_state, int32_t* error_flag)
+                       PeerBufs peers, int world, int rank, int64_t per, uint32_t* sync_state, uint32_t* any_word,
+                       int32_t* error_flag)
 {
+    // sync_state: [0] epoch of this buffer, [1] CTA ticket, [2 + r] "my copy of rank r's slice holds non-zero data"
     __shared__ uint32_t s_epoch;
+    __shared__ int s_any[16], s_skip[16];
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(sync_state) + 1u;
     __syncthreads();
     const uint32_t epoch = s_epoch;
+    uint32_t* hot_local = reinterpret_cast<uint32_t*>(local + n_sources);
     const size_t flag_off = (size_t)n_sources + (size_t)(n_sources >> 3) + AT_XCHG_BITMAP_PAD;
-    if (tid < world && tid != rank) {
-        if (blockIdx.x == 0) {
-            __threadfence_system();
-            st_release_sys(reinterpret_cast<uint32_t*>(peers.p[tid] + flag_off) + rank, epoch);
+    const int64_t words_per = per >> 5;
+    if (blockIdx.x == 0) {
+        // does my own slice hold any infectious agent?  (travels with the arrival signal, so that peers skip it)
+        // (the step kernel leaves the answer in its workspace; without it the slice's bitmap is scanned)
+        uint32_t acc = 0;
+        if (any_word != nullptr) {
+            if (tid == 0) acc = atomicExch(any_word, 0u);
+        } else {
+            const uint4* mine4 = reinterpret_cast<const uint4*>(hot_local + rank * words_per);
+            for (int64_t i = tid; i < (words_per >> 2); i += blockDim.x) { const uint4 v = mine4[i]; acc |= v.x | v.y | v.z | v.w; }
         }
+        const int any_own = __syncthreads_or(acc != 0u);
+        if (tid < world && tid != rank) {
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<uint32_t*>(peers.p[tid] + flag_off) + rank, (epoch << 1) | (uint32_t)(any_own != 0));
+        }
+        if (tid == 0) *(reinterpret_cast<volatile uint32_t*>(local + flag_off) + rank) = (epoch << 1) | (uint32_t)(any_own != 0);
+    }
+    if (tid < world) {
         const uint32_t* mine = reinterpret_cast<const uint32_t*>(local + flag_off) + tid;
         const long long t0 = clock64();
-        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+        uint32_t v = ld_acquire_sys(mine);
+        while ((int32_t)((v >> 1) - epoch) < 0) {
             if (clock64() - t0 > 40000000000ll) {            // ~20 s: a peer never arrived; report instead of hanging
                 if (error_flag) *error_flag = 2;
                 break;
             }
-            __nanosleep(200);
+            __nanosleep(100);
+            v = ld_acquire_sys(mine);
         }
+        // (a peer cannot be more than one use of this buffer ahead, so the low bit belongs to this epoch)
+        s_any[tid] = (int)(v & 1u);
+        const int live = (int)reinterpret_cast<volatile uint32_t*>(sync_state)[2 + tid];
+        s_skip[tid] = !(v & 1u) && (tid == rank || !live);          // nothing hot there now and nothing to clear here
     }
     __syncthreads();
 
-    uint32_t* hot_local = reinterpret_cast<uint32_t*>(local + n_sources);
     const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + tid) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_words = n_sources >> 5;
     uint32_t seen = 0;
     for (int64_t w0 = warp_id * 32; w0 < n_words; w0 += n_warps * 32) {
-        const int64_t w = w0 + lane;                          // a 1024-source tile never straddles two slices
+        const int owner = (int)((w0 * 32) / per);             // a 1024-source tile never straddles two slices
+        if (s_skip[owner]) continue;
+        const int64_t w = w0 + lane;
         uint32_t word = 0;
         if (w < n_words) {
-            const int owner = (int)((w0 * 32) / per);
             if (owner == rank) {
                 word = hot_local[w];
             } else {
                 const uint8_t* peer = peers.p[owner];
-                word = __ldcv(reinterpret_cast<const uint32_t*>(peer + n_sources) + w);     // never from a stale L1 line
                 const uint32_t old = hot_local[w];
+                if (s_any[owner]) word = __ldcv(reinterpret_cast<const uint32_t*>(peer + n_sources) + w);   // never from a stale L1 line
                 uint4* dst = reinterpret_cast<uint4*>(local + w * 32);
                 if (word != 0u) {
                     const uint4* src = reinterpret_cast<const uint4*>(peer + w * 32);
@@ -860,14 +889,19 @@ exchange_sparse_kernel(uint8_t* __restrict__ local, int64_t n_sources, uint32_t*
         seen |= word;
     }
     if (filter != nullptr && __syncthreads_or(seen != 0u) && tid == 0) atomicOr(&filter[hash_words], 1u);
-    // the last CTA to finish publishes the epoch (every CTA has read the old value by then)
+    // the last CTA to finish publishes the epoch and the slice states (every CTA has read the old values by then)
     __shared__ int s_last;
     __syncthreads();
     if (tid == 0) {
         __threadfence();
         s_last = atomicAdd(reinterpret_cast<int*>(sync_state) + 1, 1) == (int)gridDim.x - 1;
-        if (s_last) {
+    }
+    __syncthreads();
+    if (s_last) {
+        if (tid < world) reinterpret_cast<volatile uint32_t*>(sync_state)[2 + tid] = (uint32_t)s_any[tid];
+        if (tid == 0) {
             reinterpret_cast<int*>(sync_state)[1] = 0;
+            __threadfence();
             *reinterpret_cast<volatile uint32_t*>(sync_state) = epoch;
         }
     }
@@ -1158,8 +1192,8 @@ int64_t at_seirm_exchange_bytes(int64_t n_sources) {
 }
 
 int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* hot_filter, int32_t hash_words,
-                             void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, int32_t* error_flag,
-                             void* stream) {
+                             void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, void* step_workspace,
+                             int32_t* error_flag, void* stream) {
     if (!local_buf || !peer_buf || !sync_state) return fail("%s", "exchange_sparse: null buffer");
     if (n_sources <= 0 || (n_sources & 1023)) return fail("%s", "exchange_sparse: n_sources must be a positive multiple of 1024");
     if (world < 2 || world > 16 || rank < 0 || rank >= world || (n_sources % world) || ((n_sources / world) & 1023))
@@ -1182,8 +1216,9 @@ int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* ho
     int64_t tiles = (n_sources / 32 + 255) / 256;
     int grid = (int)(tiles < g_sm_count * 4 ? tiles : g_sm_count * 4);
     if (grid < 1) grid = 1;
+    uint32_t* any_word = step_workspace ? reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(step_workspace) + WS_ANYHOT) : nullptr;
     exchange_sparse_kernel<<<grid, 256, 0, s>>>(local_buf, n_sources, hot_filter, hash_words, pb, world, rank, n_sources / world,
-                                                sync_state, error_flag);
+                                                sync_state, any_word, error_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("exchange_sparse_kernel launch: %s", cudaGetErrorString(e));
     return 0;

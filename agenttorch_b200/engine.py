@@ -218,7 +218,7 @@ class SeirmEngine:
                     c.zero_()
                 self.code = [c[: self.n_code] for c in self.xbuf]
                 self.hot = [c[self.n_code: self.n_code + self.n_code // 8 + 16].view(torch.int32) for c in self.xbuf]
-                self.xsync = [torch.zeros(4, dtype=torch.int32, device=dev) for _ in range(2)]
+                self.xsync = [torch.zeros(32, dtype=torch.int32, device=dev) for _ in range(2)]
                 torch.cuda.synchronize(dev)
                 import torch.distributed as dist
 
@@ -363,8 +363,8 @@ class SeirmEngine:
                 # (P2P loads of the non-empty 32-byte code sectors only) + filter fold
                 nat.check(self.lib.at_seirm_exchange_sparse(_ptr(self.xbuf[buf_index]), int(self.n_code), _ptr(filt),
                                                             int(self.graph.hash_words), ptrs, world, rank,
-                                                            _ptr(self.xsync[buf_index]), _ptr(self.error_flag),
-                                                            ctypes.c_void_p(stream)))
+                                                            _ptr(self.xsync[buf_index]), _ptr(self.workspace),
+                                                            _ptr(self.error_flag), ctypes.c_void_p(stream)))
             else:
                 hdl.barrier(channel=buf_index)                   # every rank has written its slice of this buffer
                 # dense: pull the peers' whole slices (P2P loads) + rebuild bitmap/filter from the codes, one kernel

@@ -216,14 +216,16 @@ int at_seirm_pull_codes(uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, 
  * bytes: [code : n][hot bitmap : n/8 (+64)][arrival flags]; point at_seirm_launch.code_* / hot_bitmap_* at its first
  * two parts.  peer_buf is a HOST array of `world` device pointers (peer_buf[rank] == local_buf).  The kernel signals
  * "my slice is written" to every peer, waits for theirs, pulls 32-byte code sectors only where a peer's bitmap word is
- * non-zero, and folds the whole bitmap into hot_filter (may be NULL).  sync_state: 2 zero-initialised device words
- * per buffer, owned by this call sequence.  A peer that never arrives sets *error_flag = 2 after ~20 s.
+ * non-zero (a slice whose owner reports no infectious agent, and of which no stale copy is held, is skipped altogether),
+ * and folds the whole bitmap into hot_filter (may be NULL).  sync_state: 32 zero-initialised device words per buffer,
+ * owned by this call sequence.  step_workspace: the at_seirm_launch.workspace of the step kernel that wrote this rank's
+ * slice (it records there whether the slice holds any infectious agent; NULL = scan the slice).  A peer that never arrives sets *error_flag = 2 after ~20 s.
  * Replaces nothing in the reference (core/distributed_runner.py:218-228 is `pass`).
  */
 int64_t at_seirm_exchange_bytes(int64_t n_sources);
 int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* hot_filter, int32_t hash_words,
-                             void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, int32_t* error_flag,
-                             void* stream);
+                             void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, void* step_workspace,
+                             int32_t* error_flag, void* stream);
 
 /*
  * at_noise_fill — materialise the counter-hash noise (same values the step kernel generates in

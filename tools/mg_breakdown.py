@@ -41,11 +41,8 @@ def timed_exchange(buf_index):
     stream = torch.cuda.current_stream(dev).cuda_stream
     filt = engine.filt[buf_index] if engine.filt is not None else None
     a = ev()
-    hdl.barrier(channel=buf_index)
-    b = ev()
-    ptrs = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
-    nat.check(engine.lib.at_seirm_pull_codes(_ptr(engine.code[buf_index]), int(engine.n_code), _ptr(engine.hot[buf_index]),
-                                             _ptr(filt), int(engine.graph.hash_words), ptrs, world, rank, ctypes.c_void_p(stream)))
+    b = a
+    orig_exchange(buf_index)                      # one kernel: rendezvous + sparse pull + filter fold
     c = ev()
     marks.append((a, b, c))
 orig_launch = engine._submit
@@ -84,18 +81,16 @@ for _ in range(3): fwd()
 t_fwd = tm(fwd)
 t_restore = tm(restore)
 def reduces():
-    di, dd = st.daily_infected.clone(), st.daily_deaths.clone()
-    dist.all_reduce(di); dist.all_reduce(dd)
+    from agenttorch_b200.parallel import reduce_daily_series
+    reduce_daily_series(st, pg)
 t_red = tm(reduces)
 t_bwd = tm(lambda: engine.episode_backward(sv, T, gI, gD, m_val))
 if rank == 0:
     f = lambda v: f"n={len(v)} med={statistics.median(v):.1f} min={min(v):.1f} max={max(v):.1f} sum={sum(v):.0f}"
     print(f"world {world}: step kernels  us: {f(kern)}")
-    print(f"world {world}: barrier       us: {f(bar)}")
-    print(f"world {world}: pull kernel   us: {f(pull)}")
-    print(f"world {world}: graph episode fwd incl restore {t_fwd:.0f} us, restore {t_restore:.0f} us, 2 all-reduces {t_red:.0f} us, backward (incl. its all-reduce) {t_bwd:.0f} us")
+    print(f"world {world}: exchange (rendezvous + sparse pull) us: {f(pull)}")
+    print(f"world {world}: graph episode fwd incl restore {t_fwd:.0f} us, restore {t_restore:.0f} us, packed all-reduce of the series {t_red:.0f} us, backward (incl. its all-reduce) {t_bwd:.0f} us")
     print("kernels:", " ".join(f"{v:.0f}" for v in kern))
-    print("barrier:", " ".join(f"{v:.0f}" for v in bar))
     print("pull:", " ".join(f"{v:.0f}" for v in pull))
 dist.barrier()
 dist.destroy_process_group()
