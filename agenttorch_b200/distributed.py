@@ -178,6 +178,7 @@ class DistributedRunner:
         return out[: self.num_agents]
 
     def gather_final_state(self):
+        self.engine.check_errors()                # e.g. a halo-exchange rendezvous that timed out (device-side flag)
         cit = self.state["agents"][self.config["substeps"]["0"]["active_agents"][0]]
         return {k: self.gather_agent_states(v) for k, v in cit.items()
                 if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == self.agent_partition_map["local_size"]}

@@ -10,8 +10,7 @@ import re
 import torch
 
 from agenttorch_b200.core.helpers import get_by_path, set_by_path
-from agenttorch_b200.predprey import (PredPreyEngine, PredPreySpec, PredPreyState, pack_cells, pack_stage,
-                                      unpack_cells, unpack_stage)
+from agenttorch_b200.predprey import PredPreyEngine, PredPreySpec, PredPreyState, unpack_cells, unpack_stage
 
 from .context import topology
 

@@ -340,6 +340,7 @@ def ours(args):
             episode(True, True)
         ms_e2e = timed(lambda: episode(True, True), args.steps)
         final_di = episode(False, False).sum().item()
+        engine.check_errors()                                  # e.g. a halo-exchange rendezvous that timed out
 
     if rank != 0:
         if world > 1:

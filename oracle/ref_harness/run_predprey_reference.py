@@ -10,11 +10,9 @@ and the bundled CSV populations (`models/predator_prey/data/*`).  The only rando
 first (config.yaml:224-226 active_agents order).  It is replaced by an object whose `choice(seq)` consumes injected
 draws: seq[(u24 * len(seq)) >> 24] with u24 = oracle.noise.move_draw(seed, step, species, agent).
 """
-import copy
 import os
 import sys
 
-import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))

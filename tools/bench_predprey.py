@@ -9,7 +9,6 @@ the headline metric of this repo is the SEIRM episode.  A "step" here is one 20-
 import argparse
 import json
 import os
-import statistics
 import sys
 import time
 

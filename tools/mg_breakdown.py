@@ -1,12 +1,11 @@
 """Where a multi-GPU SEIRM episode spends its time (run under torchrun on N >= 2 GPUs).
-Eager (non-graph) episode with CUDA events around the three pieces of every step — step kernel, symmetric-memory
-barrier, fused pull kernel — plus the per-episode extras (restore, all-reduces, backward) and the captured-graph total."""
-import ctypes, os, statistics, sys
+Eager (non-graph) episode with CUDA events around the two pieces of every step — step kernel, halo-exchange kernel
+(rendezvous + sparse pull) — plus the per-episode extras (restore, all-reduces, backward) and the captured-graph total."""
+import os, statistics, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
-from agenttorch_b200 import _native as nat
-from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState, _ptr
+from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
 from agenttorch_b200.graph import (mean_interactions_from_age, shard_bounds, shard_code_len, synthetic_contact_graph,
                                    synthetic_population)
 
@@ -37,9 +36,6 @@ def ev():
 
 orig_exchange = engine.exchange
 def timed_exchange(buf_index):
-    hdl = engine.code_hdl[buf_index]
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    filt = engine.filt[buf_index] if engine.filt is not None else None
     a = ev()
     b = a
     orig_exchange(buf_index)                      # one kernel: rendezvous + sparse pull + filter fold
