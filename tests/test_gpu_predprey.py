@@ -313,3 +313,50 @@ def test_baseline_size_properties():
     assert float(d.min()) >= -10.001 and float(((d + 10) / 20).round().sub((d + 10) / 20).abs().max()) < 1e-3
     assert int((a.prey_energy == 0).sum()) > 0
     assert eng.census(a) == (int((a.pred_energy > 0).sum()), int((a.prey_energy > 0).sum()), int((stage == 1).sum()))
+
+
+# ----------------------------------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("shape,n_pred,n_prey", [((7, 1), 5, 9), ((1, 9), 4, 4), ((6, 5), 0, 37), ((6, 5), 23, 0), ((2, 2), 50, 50),
+                                                 ((33, 31), 1, 1)])
+def test_edge_cases_match_oracle(shape, n_pred, n_prey):
+    """Degenerate lattices (one row / one column: cells with 1 or 2 neighbours), a missing species, crowded cells, and
+    cell counts that are not a multiple of 4 / 16 / 32 (ragged tail of the cell pass)."""
+    from agenttorch_b200.predprey import PredPreyEngine, PredPreySpec
+    from oracle.predprey_port import PredPreyConstants, PredPreyPort
+
+    mx, my = shape
+    C = mx * my
+    rng = np.random.default_rng(C * 31 + n_pred)
+    init = {
+        "pred_pos": np.stack([rng.integers(0, mx, n_pred), rng.integers(0, my, n_pred)], 1).reshape(-1, 2),
+        "prey_pos": np.stack([rng.integers(0, mx, n_prey), rng.integers(0, my, n_prey)], 1).reshape(-1, 2),
+        "pred_energy": rng.uniform(-1, 6, (n_pred, 1)).astype(np.float32),
+        "prey_energy": rng.uniform(-1, 9, (n_prey, 1)).astype(np.float32),
+        "growth_countdown": np.where(rng.random(C) < 0.5, 0.0, rng.uniform(0.5, 3.0, C)).reshape(-1, 1),
+    }
+    init["growth_stage"] = (init["growth_countdown"] <= 0).astype(np.int64)
+    consts = dict(pred_work=0.75, prey_work=1.25, prey_nutrition=2.5, grass_nutrition=1.5, regrowth_time=2.2)
+    port = PredPreyPort(PredPreyConstants(mx, my, **consts), **init)
+    spec = PredPreySpec(mx, my, C, mx, **consts)
+    eng = PredPreyEngine(spec, DEV)
+    st = _state_from(spec, init, prefix="")
+    st.sort_by_cell()
+    for t in range(9):
+        port.step(t, 77)
+    eng.run(st, 4, 77, cuda_graph=False)
+    eng.run(st, 5, 77, t0=4, cuda_graph=True)
+    _assert_equal(st, spec, port.snapshot(), (shape, n_pred, n_prey))
+    assert eng.census(st) == (int((port.pred_energy > 0).sum()), int((port.prey_energy > 0).sum()), int(port.growth_stage.sum()))
+
+
+def test_invalid_inputs_fail_loudly():
+    from agenttorch_b200.predprey import PredPreySpec, PredPreyState
+
+    spec = PredPreySpec(4, 4, 16, 4)
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=DEV)             # noqa: E731
+    with pytest.raises(ValueError, match="outside the grid"):
+        PredPreyState.from_reference(spec, torch.tensor([[4, 0]], device=DEV), z(1, 1), z(0, 2, dt=torch.int64), z(0, 1),
+                                     z(16, 1, dt=torch.int64), z(16, 1))
+    with pytest.raises(ValueError, match="one entry per cell"):
+        PredPreyState.from_reference(spec, z(0, 2, dt=torch.int64), z(0, 1), z(0, 2, dt=torch.int64), z(0, 1),
+                                     z(15, 1, dt=torch.int64), z(15, 1))
