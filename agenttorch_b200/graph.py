@@ -105,6 +105,30 @@ def build_contact_graph(edge_index, num_agents, edge_attr=None, mean_interaction
     return g
 
 
+GRAPH_FILE_VERSION = 1
+
+
+def save_contact_graph(graph, path):
+    """Binary CSR on disk: what `build_contact_graph` produced (sorted rows, int32 columns, I_bar), so that a population's
+    edge-list CSV (`mobility_networks/0.csv`, 2.5 GB of text for 168 M edges) is parsed and sorted once."""
+    cpu = graph.to("cpu")
+    torch.save({"version": GRAPH_FILE_VERSION, "n_rows": cpu.n_rows, "n_sources": cpu.n_sources, "row_offset": cpu.row_offset,
+                "row_ptr": cpu.row_ptr, "col_idx": cpu.col_idx[: cpu.num_edges].clone(), "num_edges": cpu.num_edges,
+                "edge_weight": None if cpu.edge_weight is None else cpu.edge_weight[: cpu.num_edges].clone(),
+                "i_bar": cpu.i_bar, "i_bar_agent": cpu.i_bar_agent}, path)
+
+
+def load_contact_graph(path, device="cpu"):
+    d = torch.load(path, map_location="cpu", weights_only=True)
+    if d.get("version") != GRAPH_FILE_VERSION:
+        raise ValueError(f"{path}: unsupported contact-graph file version {d.get('version')}")
+    if d["row_ptr"].numel() != d["n_rows"] + 1 or int(d["row_ptr"][-1]) != d["num_edges"] or d["col_idx"].numel() != d["num_edges"]:
+        raise ValueError(f"{path}: inconsistent contact-graph file")
+    g = ContactGraph(d["n_rows"], d["n_sources"], d["row_offset"], d["row_ptr"], _pad_cols(d["col_idx"]), d["num_edges"],
+                     None if d["edge_weight"] is None else _pad_cols(d["edge_weight"]), d["i_bar"], d["i_bar_agent"])
+    return g.to(device)
+
+
 # Astoria's age histogram (populations/astoria/age.pickle), used for synthetic populations (SURVEY.md 8d)
 ASTORIA_AGE_COUNTS = (6723, 11573, 5724, 4647, 3910, 4941)
 

@@ -2,6 +2,9 @@
 and values (agent_torch/models/covid/substeps/utils.py:14-148).  Differences: the disease-stage column is
 kept in float32 (every value the model produces is exactly representable) so that the
 CUDA kernels read it without a conversion pass."""
+import hashlib
+import os
+
 import numpy as np
 import pandas as pd
 import torch
@@ -62,14 +65,36 @@ def initialize_id(shape, params):
     return torch.arange(0, shape[0]).reshape(-1, 1).float()
 
 
+def _edge_cache_path(path):
+    """Opt-in cache of parsed edge lists: set AGENTTORCH_B200_CACHE_DIR.  Keyed by path, size and mtime of the CSV."""
+    root = os.environ.get("AGENTTORCH_B200_CACHE_DIR")
+    if not root:
+        return None
+    st = os.stat(path)
+    key = hashlib.sha1(f"{os.path.abspath(path)}|{st.st_size}|{st.st_mtime_ns}".encode()).hexdigest()[:20]
+    return os.path.join(root, f"edges_{key}.npy")
+
+
 def network_from_file(params):
-    """Edge-list CSV -> (None, (edge_index (2,E) int64, edge_attr (2,E) float32 = [type==1; weight==1]))."""
+    """Edge-list CSV -> (None, (edge_index (2,E) int64, edge_attr (2,E) float32 = [type==1; weight==1])).
+    (reference utils.py:129-148).  Parsing 168 M text edges takes minutes; with AGENTTORCH_B200_CACHE_DIR set the parsed
+    (E,2) int32 array is kept as .npy and memory-mapped on the next run."""
     path = params["file_path"]
-    df = pd.read_csv(path, header=None)
-    if df.iloc[0].apply(lambda v: isinstance(v, str)).any():
-        df = pd.read_csv(path, header=0)
-    df = df.iloc[:, :2].apply(pd.to_numeric, errors="coerce").dropna().astype("int64")
-    edge_index = torch.tensor(df.values.T, dtype=torch.long).contiguous()
+    cache = _edge_cache_path(path)
+    if cache is not None and os.path.exists(cache):
+        pairs = np.load(cache, mmap_mode="r")
+        edge_index = torch.from_numpy(np.array(pairs.T, dtype=np.int64, order="C"))
+    else:
+        df = pd.read_csv(path, header=None)
+        if df.iloc[0].apply(lambda v: isinstance(v, str)).any():
+            df = pd.read_csv(path, header=0)
+        df = df.iloc[:, :2].apply(pd.to_numeric, errors="coerce").dropna().astype("int64")
+        edge_index = torch.tensor(df.values.T, dtype=torch.long).contiguous()
+        if cache is not None and edge_index.numel() and int(edge_index.max()) < 2**31:
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
+            tmp = cache + f".{os.getpid()}.tmp.npy"
+            np.save(tmp, edge_index.t().to(torch.int32).numpy())
+            os.replace(tmp, cache)
     e = edge_index.shape[1]
     edge_attr = torch.vstack((torch.ones(e, dtype=torch.float32), torch.ones(e, dtype=torch.float32)))
     return None, (edge_index, edge_attr)

@@ -130,3 +130,37 @@ def test_noise_twins_agree_bitwise():
     assert int(onoise.noise_u64(0, 0, [0])[0]) == 0xE220A8397B1DCDAF        # SplitMix64 known answer (seed 0, first output)
     u = onoise.exposure_uniform(3, 1, np.arange(200000))
     assert u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3
+
+
+def test_contact_graph_file_round_trip_and_edge_list_cache(tmp_path, monkeypatch):
+    import pandas as pd
+
+    from agenttorch_b200.graph import build_contact_graph, load_contact_graph, save_contact_graph
+    from agenttorch_b200.models.covid.substeps import utils
+
+    rng = np.random.default_rng(3)
+    n, e = 500, 4000
+    edges = np.stack([rng.integers(0, n, e), rng.integers(0, n, e)], 1)
+    g = build_contact_graph(torch.from_numpy(edges.T.copy()), n, mean_interactions=torch.full((n,), 3.0))
+    path = str(tmp_path / "graph.atg")
+    save_contact_graph(g, path)
+    h = load_contact_graph(path)
+    assert (h.n_rows, h.n_sources, h.num_edges, h.i_bar, h.i_bar_agent) == (g.n_rows, g.n_sources, g.num_edges, g.i_bar, g.i_bar_agent)
+    assert torch.equal(h.row_ptr, g.row_ptr) and torch.equal(h.col_idx, g.col_idx) and h.edge_weight is None
+    torch.save({"version": 99}, path)
+    with pytest.raises(ValueError, match="version"):
+        load_contact_graph(path)
+
+    csv = tmp_path / "0.csv"
+    pd.DataFrame(edges).to_csv(csv, header=False, index=False)
+    monkeypatch.setenv("AGENTTORCH_B200_CACHE_DIR", str(tmp_path / "cache"))
+    _, (ei1, attr1) = utils.network_from_file({"file_path": str(csv)})
+    assert np.array_equal(ei1.numpy(), edges.T) and attr1.shape == (2, e) and bool((attr1 == 1).all())
+    monkeypatch.setattr(utils.pd, "read_csv", lambda *a, **k: (_ for _ in ()).throw(AssertionError("the cache should have been used")))
+    _, (ei2, _) = utils.network_from_file({"file_path": str(csv)})
+    assert torch.equal(ei1, ei2) and ei2.dtype == torch.int64
+    monkeypatch.undo()
+    csv.write_text("1,2\n3,4\n")                                   # the CSV changed: the stale cache entry is not used
+    monkeypatch.setenv("AGENTTORCH_B200_CACHE_DIR", str(tmp_path / "cache"))
+    _, (ei3, _) = utils.network_from_file({"file_path": str(csv)})
+    assert ei3.tolist() == [[1, 3], [2, 4]]
