@@ -122,16 +122,9 @@ def main():
     cd_bytes = st0.countdown.element_size()
     bytes_step = n * 20 + C * 2 * (cd_bytes + 1)          # cell + energy read and written, agent number read; info byte + countdown read and written
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak, peak_src = 6551.0, "fallback (B200_PROFILING.md copy bandwidth)"
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     if os.path.exists(peaks_path):
-        try:
-            pk = json.load(open(peaks_path))
-            for key in ("hbm_gbps_sustained", "hbm_gbps", "hbm_copy_gbps", "hbm_gbps_burst"):
-                if key in pk:
-                    peak, peak_src = float(pk[key]), f"MEASURED_PEAKS.json:{key}"
-                    break
-        except Exception:
-            pass
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     achieved = bytes_step * EPISODE / (ms_value * 1e-3) / 1e9
     line = {
         "metric": "agent-steps/s, predator-prey grid model (BASELINE configs[3])", "value": n * EPISODE / (ms_value * 1e-3), "unit": "agent-steps/s",
