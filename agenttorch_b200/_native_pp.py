@@ -14,12 +14,13 @@ LIB_PATH = os.path.join(_PKG, "lib", "libat_predprey.so")
 SRC_PATH = os.path.join(_PKG, "csrc", "at_predprey.cu")
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 OCCUPANCY, EAT, HUNT, MOVE, EAT_APPLY, GROW, CLEAR, EAT_IMPLICIT = 1, 2, 4, 8, 16, 32, 64, 128
 INFO_GROWN, INFO_EATEN = 1, 2
 
 EXPORTS = [
     "at_pp_abi_version", "at_pp_last_error", "at_pp_sizeof_model", "at_pp_sizeof_launch", "at_pp_info_bytes",
+    "at_pp_storage_cells",
     "at_pp_step", "at_pp_pack_cells", "at_pp_unpack_cells", "at_pp_pack_stage", "at_pp_unpack_stage", "at_pp_census",
 ]
 
@@ -28,10 +29,11 @@ class PPModel(ctypes.Structure):
     """Mirror of `at_pp_model`."""
     _fields_ = [
         ("abi_version", ctypes.c_int32), ("width", ctypes.c_int32), ("max_y", ctypes.c_int32),
-        ("apply_pred_work", ctypes.c_int32), ("apply_prey_work", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("apply_pred_work", ctypes.c_int32), ("apply_prey_work", ctypes.c_int32), ("tiles_per_row", ctypes.c_int32),
         ("n_cells", ctypes.c_int64),
         ("pred_work", ctypes.c_float), ("prey_work", ctypes.c_float), ("prey_nutrition", ctypes.c_float),
         ("grass_nutrition", ctypes.c_float), ("regrowth_time", ctypes.c_float), ("reserved_f", ctypes.c_float),
+        ("n_storage", ctypes.c_int64),
     ]
 
 
@@ -96,6 +98,8 @@ def lib():
         L.at_pp_sizeof_launch.restype = i64
         L.at_pp_info_bytes.restype = i64
         L.at_pp_info_bytes.argtypes = [i64]
+        L.at_pp_storage_cells.restype = i64
+        L.at_pp_storage_cells.argtypes = [i32, i64, i32]
         L.at_pp_step.restype = ctypes.c_int
         L.at_pp_step.argtypes = [ctypes.POINTER(PPModel), ctypes.POINTER(PPLaunch), vp]
         L.at_pp_pack_cells.restype = ctypes.c_int

@@ -73,30 +73,37 @@ static FastDiv make_fastdiv(uint32_t d) {
 __device__ __forceinline__ int fast_div(int n, FastDiv f) { return (int)(((uint64_t)(uint32_t)n * f.mul) >> f.shift); }
 
 // neighbour number (draw * count) >> 24 of the ascending list [k - width, k - 1, k + 1, k + width] (those that exist)
-__device__ __forceinline__ int lattice_step(int cell, uint32_t draw24, int width, int n_cells, FastDiv fd) {
-    const int i = cell - fast_div(cell, fd) * width;
+__device__ __forceinline__ int lattice_step(int cell, int i /* cell % width */, uint32_t draw24, int width, int n_cells) {
     const bool up = cell >= width, left = i > 0, right = i < width - 1, down = cell < n_cells - width;
     const int cnt = (int)up + (int)left + (int)right + (int)down;
     if (cnt == 0) return cell;
     const int k = (int)((draw24 * (uint32_t)cnt) >> 24);
     // k-th existing neighbour, branch-free: position of each candidate in the ascending list
-    const int p_left = (int)up, p_right = p_left + (int)left, p_down = p_right + (int)right;
-    int next = cell + width;                                                     // k == p_down
+    const int p_left = (int)up, p_right = p_left + (int)left;
+    int next = cell + width;                                                     // the last candidate
     next = (right && k == p_right) ? cell + 1 : next;
     next = (left && k == p_left) ? cell - 1 : next;
     next = (up && k == 0) ? cell - width : next;
-    (void)p_down;
     return next;
 }
 
+// Where a cell's info byte (and countdown) is stored.  Untiled (tiles_per_row == 0): at the cell number.  Tiled: the
+// lattice is cut into tiles of 8 rows x 16 columns = one 128-byte line of info bytes, so that the four neighbours of a
+// cell are almost always in the same line and a random walker stays near its line for many steps.
+__device__ __forceinline__ int storage_of(int row, int col, int tiles_per_row) {
+    return ((((row >> 3) * tiles_per_row + (col >> 4)) << 7) | ((row & 7) << 4) | (col & 15));
+}
+
 __global__ void __launch_bounds__(PP_THREADS)
-pp_occupancy_kernel(at_pp_launch a)
+pp_occupancy_kernel(at_pp_model m, at_pp_launch a, FastDiv fd)
 {
     const int64_t n = a.n_pred + a.n_prey;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
         const bool prey = idx >= a.n_pred;
         const int cell = prey ? a.prey_cell[idx - a.n_pred] : a.pred_cell[idx];
-        mark_cell(a.info, cell, prey ? PP_OCC_PREY(a.occ_in) : PP_OCC_PRED(a.occ_in));
+        int addr = cell;
+        if (m.tiles_per_row) { const int row = fast_div(cell, fd); addr = storage_of(row, cell - row * m.width, m.tiles_per_row); }
+        mark_cell(a.info, addr, prey ? PP_OCC_PREY(a.occ_in) : PP_OCC_PRED(a.occ_in));
     }
 }
 
@@ -110,7 +117,7 @@ struct AgentPass {
     uint64_t seed;
     uint32_t t;
     int flags;
-    bool look, move, eat, hunt, mark_eaten, apply_work;
+    bool look, move, eat, hunt, mark_eaten, apply_work, tiled;
     uint32_t other_here, my_mark;
     float work;
     const int32_t* __restrict__ ids;
@@ -128,35 +135,58 @@ struct AgentPass {
         apply_work = PREY ? m.apply_prey_work : m.apply_pred_work;
         work = -(PREY ? m.prey_work : m.pred_work);
         ids = PREY ? a.prey_id : a.pred_id;
+        tiled = m.tiles_per_row != 0;
+    }
+
+    struct Where { int row, col, addr; };
+    // row / column / storage address of a cell (one multiply-shift; skipped when neither is needed)
+    __device__ __forceinline__ Where locate(int cell) const {
+        Where w; w.row = 0; w.col = 0; w.addr = cell;
+        if (tiled || (move && a.nbr_ptr == nullptr)) {
+            w.row = fast_div(cell, fd);
+            w.col = cell - w.row * m.width;
+            if (tiled) w.addr = storage_of(w.row, w.col, m.tiles_per_row);
+        }
+        return w;
     }
 
     // `here` = info byte of the agent's cell (0 when nothing looks at it)
-    __device__ __forceinline__ void one(int slot, int id, uint32_t here, int& cell, float& e) const {
+    __device__ __forceinline__ void one(int id, uint32_t here, Where w, int& cell, float& e) const {
         if (PREY) {
             if (eat && (here & PP_GROWN)) {                                           // eat.py:41, :93-97
                 e = __fadd_rn(e, m.grass_nutrition);
-                if (mark_eaten && !(here & PP_EATEN)) mark_cell(a.info, cell, PP_EATEN);
+                if (mark_eaten && !(here & PP_EATEN)) mark_cell(a.info, w.addr, PP_EATEN);
             }
             if (hunt && (here & other_here)) e = 0.0f;                                // hunt.py:81
         } else {
             if (hunt && (here & other_here)) e = __fadd_rn(e, m.prey_nutrition);      // hunt.py:83-86
         }
         if (move) {
+            int addr = w.addr;
             if (e > 0.0f) {                                                         // move.py:89
                 // draws follow the agent number, not the slot
                 const uint64_t who = ((uint64_t)(PREY ? 1 : 0) << PP_SPECIES_BIT) | (uint64_t)(uint32_t)id;
                 const uint32_t draw = (uint32_t)(at_noise_u64(seed, t, who) >> 40);
                 if (a.nbr_ptr == nullptr) {
-                    cell = lattice_step(cell, draw, m.width, (int)m.n_cells, fd);
+                    const int next = lattice_step(cell, w.col, draw, m.width, (int)m.n_cells);
+                    if (tiled) {
+                        const int d = next - cell;                                  // +-width: one row; +-1: one column
+                        const int row = w.row + (d == m.width ? 1 : (d == -m.width ? -1 : 0));
+                        const int col = w.col + ((d == m.width || d == -m.width) ? 0 : d);
+                        addr = storage_of(row, col, m.tiles_per_row);
+                    } else {
+                        addr = next;
+                    }
+                    cell = next;
                 } else {
                     const int64_t lo = a.nbr_ptr[cell], cnt = a.nbr_ptr[cell + 1] - lo;
                     if (cnt > 0) cell = a.nbr_idx[lo + (int64_t)(((uint64_t)draw * (uint64_t)cnt) >> 24)];
+                    addr = cell;
                 }
             }
             if (apply_work) e = __fadd_rn(e, work);                                 // move.py:112-116
-            if (my_mark) mark_cell(a.info, cell, my_mark);
+            if (my_mark) mark_cell(a.info, addr, my_mark);
         }
-        (void)slot;
     }
 
     __device__ __forceinline__ void run(bool vec) const {
@@ -171,17 +201,18 @@ struct AgentPass {
             const float4 e0 = __ldcs(reinterpret_cast<const float4*>(energies) + q);
             int4 id = make_int4(4 * q, 4 * q + 1, 4 * q + 2, 4 * q + 3);
             if (ids != nullptr && move) id = __ldcs(reinterpret_cast<const int4*>(ids) + q);
+            const Where w0 = locate(c0.x), w1 = locate(c0.y), w2 = locate(c0.z), w3 = locate(c0.w);
             uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
             if (look) {                                              // four independent lookups in flight
-                h0 = cell_info(a.info, c0.x); h1 = cell_info(a.info, c0.y);
-                h2 = cell_info(a.info, c0.z); h3 = cell_info(a.info, c0.w);
+                h0 = cell_info(a.info, w0.addr); h1 = cell_info(a.info, w1.addr);
+                h2 = cell_info(a.info, w2.addr); h3 = cell_info(a.info, w3.addr);
             }
             int4 c = c0;
             float4 e = e0;
-            one(4 * q, id.x, h0, c.x, e.x);
-            one(4 * q + 1, id.y, h1, c.y, e.y);
-            one(4 * q + 2, id.z, h2, c.z, e.z);
-            one(4 * q + 3, id.w, h3, c.w, e.w);
+            one(id.x, h0, w0, c.x, e.x);
+            one(id.y, h1, w1, c.y, e.y);
+            one(id.z, h2, w2, c.z, e.z);
+            one(id.w, h3, w3, c.w, e.w);
             if (c.x != c0.x || c.y != c0.y || c.z != c0.z || c.w != c0.w) __stcs(reinterpret_cast<int4*>(cells) + q, c);
             if (e.x != e0.x || e.y != e0.y || e.z != e0.z || e.w != e0.w) __stcs(reinterpret_cast<float4*>(energies) + q, e);
         }
@@ -190,7 +221,8 @@ struct AgentPass {
             const float e0 = __ldcs(energies + i);
             int cell = cell0;
             float e = e0;
-            one(i, ids ? __ldcs(ids + i) : i, look ? cell_info(a.info, cell) : 0u, cell, e);
+            const Where w = locate(cell);
+            one(ids ? __ldcs(ids + i) : i, look ? cell_info(a.info, w.addr) : 0u, w, cell, e);
             if (cell != cell0) __stcs(cells + i, cell);
             if (e != e0) __stcs(energies + i, e);
         }
@@ -212,7 +244,8 @@ __global__ void __launch_bounds__(PP_THREADS)
 pp_cell_kernel(at_pp_model m, at_pp_launch a)
 {
     const int flags = a.flags;
-    const int64_t n_quads = (m.n_cells + 3) >> 2;
+    const int64_t n_store = m.n_storage ? m.n_storage : m.n_cells;      // cells as stored (tiled: padded to whole tiles)
+    const int64_t n_quads = (n_store + 3) >> 2;
     uint32_t* info4 = reinterpret_cast<uint32_t*>(a.info);
     T* cd = reinterpret_cast<T*>(a.countdown);
     const uint32_t clear_mask = (flags & AT_PP_CLEAR) ? (PP_OCC_PRED(a.occ_in) | PP_OCC_PREY(a.occ_in)) * 0x01010101u : 0u;
@@ -226,7 +259,7 @@ pp_cell_kernel(at_pp_model m, at_pp_launch a)
                                            : (w0 & (PP_EATEN * 0x01010101u));
         if (grow || eaten) {
             const int64_t c0 = q * 4;
-            const bool full = c0 + 4 <= m.n_cells;
+            const bool full = c0 + 4 <= n_store;
             T c[4];
             if (full) {
                 if constexpr (sizeof(T) == 4) {
@@ -238,7 +271,7 @@ pp_cell_kernel(at_pp_model m, at_pp_launch a)
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) c[j] = c0 + j < m.n_cells ? cd[c0 + j] : (T)1;
+                for (int j = 0; j < 4; ++j) c[j] = c0 + j < n_store ? cd[c0 + j] : (T)1;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -251,7 +284,7 @@ pp_cell_kernel(at_pp_model m, at_pp_launch a)
                 }
                 if (grow) {                                                         // grow.py:34-40
                     c[j] = c[j] - (T)1;
-                    w = (w & ~(PP_GROWN << sh)) | ((c[j] <= (T)0 && c0 + j < m.n_cells) ? (PP_GROWN << sh) : 0u);
+                    w = (w & ~(PP_GROWN << sh)) | ((c[j] <= (T)0 && c0 + j < n_store) ? (PP_GROWN << sh) : 0u);
                 }
             }
             if (full) {
@@ -263,7 +296,7 @@ pp_cell_kernel(at_pp_model m, at_pp_launch a)
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (c0 + j < m.n_cells) cd[c0 + j] = c[j];
+                for (int j = 0; j < 4; ++j) if (c0 + j < n_store) cd[c0 + j] = c[j];
             }
         }
         if (w != w0) info4[q] = w;
@@ -356,6 +389,11 @@ const char* at_pp_last_error(void) { return g_err; }
 int64_t at_pp_sizeof_model(void) { return (int64_t)sizeof(at_pp_model); }
 int64_t at_pp_sizeof_launch(void) { return (int64_t)sizeof(at_pp_launch); }
 int64_t at_pp_info_bytes(int64_t n_cells) { return (n_cells + 15) & ~(int64_t)15; }
+int64_t at_pp_storage_cells(int32_t width, int64_t n_cells, int32_t tiled) {
+    if (!tiled || width <= 0) return n_cells;
+    const int64_t rows = (n_cells + width - 1) / width;
+    return ((rows + 7) / 8) * ((width + 15) / 16) * 128;
+}
 
 int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* stream)
 {
@@ -368,6 +406,10 @@ int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* strea
     const int flags = a.flags;
     if (m.n_cells <= 0 || m.n_cells > 0x7fffffffll) return fail("at_pp_step: %s", "n_cells must be in [1, 2^31)");
     if (m.width <= 0 || m.max_y <= 0) return fail("at_pp_step: %s", "width and max_y must be positive");
+    if (m.tiles_per_row < 0 || (m.tiles_per_row && (a.nbr_ptr || m.n_cells % m.width || m.tiles_per_row != (m.width + 15) / 16 ||
+                                                    m.n_storage != at_pp_storage_cells(m.width, m.n_cells, 1))))
+        return fail("at_pp_step: %s", "tiled storage needs the implicit lattice, n_cells = width * rows, tiles_per_row = ceil(width / 16) and n_storage = at_pp_storage_cells()");
+    if (!m.tiles_per_row && m.n_storage && m.n_storage != m.n_cells) return fail("at_pp_step: %s", "untiled storage: n_storage must be 0 or n_cells");
     if (a.n_pred < 0 || a.n_prey < 0 || a.n_pred > 0x7fffffffll || a.n_prey > 0x7fffffffll)
         return fail("at_pp_step: %s", "agent counts must be in [0, 2^31)");
     const int64_t n = a.n_pred + a.n_prey;
@@ -387,7 +429,7 @@ int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* strea
     if ((a.nbr_ptr == nullptr) != (a.nbr_idx == nullptr)) return fail("at_pp_step: %s", "nbr_ptr and nbr_idx go together");
 
     if ((flags & AT_PP_OCCUPANCY) && n > 0) {
-        pp_occupancy_kernel<<<blocks_for(n, a.grid), PP_THREADS, 0, s>>>(a);
+        pp_occupancy_kernel<<<blocks_for(n, a.grid), PP_THREADS, 0, s>>>(m, a, make_fastdiv((uint32_t)m.width));
         if (check("pp_occupancy_kernel launch")) return 1;
     }
     if (agent_flags && n > 0) {
@@ -400,7 +442,7 @@ int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* strea
         if (check("pp_agent_kernel launch")) return 1;
     }
     if (cell_flags) {
-        const int64_t threads = (m.n_cells + 3) >> 2;
+        const int64_t threads = ((m.n_storage ? m.n_storage : m.n_cells) + 3) >> 2;
         if (a.countdown_f64) pp_cell_kernel<double><<<blocks_for(threads, a.grid), PP_THREADS, 0, s>>>(m, a);
         else pp_cell_kernel<float><<<blocks_for(threads, a.grid), PP_THREADS, 0, s>>>(m, a);
         if (check("pp_cell_kernel launch")) return 1;

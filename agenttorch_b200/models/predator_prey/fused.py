@@ -101,7 +101,8 @@ class _FusedPredPrey:
                             width=int(lattice.width) if lattice is not None else int(bounds[0]),
                             pred_work=one(u["pred_work"]), prey_work=one(u["prey_work"]), prey_nutrition=one(h["nutritional_value"]),
                             grass_nutrition=one(e["nutrition"]), regrowth_time=one(e["regrowth_time"]),
-                            apply_pred_work=apply_pred, apply_prey_work=apply_prey)
+                            apply_pred_work=apply_pred, apply_prey_work=apply_prey,
+                            tiled=self.sort and lattice is not None and n_cells % int(lattice.width) == 0)
         if lattice is not None and lattice.n_cells != n_cells:
             raise ValueError(f"grid network has {lattice.n_cells} cells but the grass has {n_cells}")
         self.engine = PredPreyEngine(spec, dev, adjacency=csr)
@@ -113,8 +114,8 @@ class _FusedPredPrey:
         return self._seen is not None and all(x is y and x._version == v for x, (y, v) in zip(tensors, self._seen))
 
     def _adopt(self, state):
-        """Bring the engine state in line with the public tensors.  The engine keeps its own cell-sorted copy of the
-        agents; the countdown array (no order involved) is aliased."""
+        """Bring the engine state in line with the public tensors.  The engine keeps its own copy: agents sorted by cell,
+        grass in tile order."""
         t = self._tensors(state)
         if self.engine is None:
             self._build(state, t)
@@ -137,17 +138,15 @@ class _FusedPredPrey:
             stage = stage.to(torch.int64).contiguous()
             set_by_path(state, _path(paths_e["grass_growth"]), stage)
         fixed["stage"], fixed["countdown"] = stage, cd
-        watched = [fixed[k] for k in ("pred_pos", "pred_energy", "prey_pos", "prey_energy", "stage")]
+        watched = [fixed[k] for k in ("pred_pos", "pred_energy", "prey_pos", "prey_energy", "stage", "countdown")]
         if self.st is None or not self._unchanged(*watched):
             fresh = PredPreyState.from_reference(spec, fixed["pred_pos"], fixed["pred_energy"], fixed["prey_pos"], fixed["prey_energy"],
-                                                 stage, cd[:0].new_zeros(spec.n_cells), sort=self.sort)
+                                                 stage, cd, sort=self.sort)
             if self.st is not None and self.st.pred_cell.shape == fresh.pred_cell.shape and self.st.prey_cell.shape == fresh.prey_cell.shape \
-                    and (self.st.pred_id is None) == (fresh.pred_id is None):
-                fresh.countdown = self.st.countdown
+                    and (self.st.pred_id is None) == (fresh.pred_id is None) and self.st.countdown.dtype == fresh.countdown.dtype:
                 self.st.copy_(fresh)                                                    # keep the buffers captured graphs point to
             else:
                 self.st = fresh
-        self.st.countdown = cd.view(-1)
         return fixed
 
     def __call__(self, num_steps):
@@ -164,8 +163,10 @@ class _FusedPredPrey:
         unpack_cells(st.in_agent_order("prey_cell"), self.spec.max_y, out=fixed["prey_pos"])
         fixed["pred_energy"].view(-1).copy_(st.in_agent_order("pred_energy"))
         fixed["prey_energy"].view(-1).copy_(st.in_agent_order("prey_energy"))
-        unpack_stage(st.info, self.spec.n_cells, out=fixed["stage"].view(-1, 1))
-        self._seen = [(x, x._version) for x in (fixed[k] for k in ("pred_pos", "pred_energy", "prey_pos", "prey_energy", "stage"))]
+        info, countdown = st.grass_in_cell_order(self.spec)
+        unpack_stage(info, self.spec.n_cells, out=fixed["stage"].view(-1, 1))
+        fixed["countdown"].view(-1).copy_(countdown)
+        self._seen = [(x, x._version) for x in (fixed[k] for k in ("pred_pos", "pred_energy", "prey_pos", "prey_energy", "stage", "countdown"))]
         state["current_step"] = int(num_steps) - 1
         state["current_substep"] = "0"
         runner.perf_stats["fused_episodes"] += 1

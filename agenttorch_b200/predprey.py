@@ -100,6 +100,33 @@ class PredPreySpec:
     regrowth_time: float = 100.0
     apply_pred_work: bool = True
     apply_prey_work: bool = True
+    tiled: bool = False       # info bytes / countdowns stored in tiles of 8 rows x 16 columns (implicit lattice only)
+
+    @property
+    def tiles_per_row(self):
+        return (int(self.width) + 15) // 16 if self.tiled else 0
+
+    @property
+    def n_storage(self):
+        """Cells as stored: the lattice padded to whole tiles when tiled."""
+        if not self.tiled:
+            return int(self.n_cells)
+        rows = -(-int(self.n_cells) // int(self.width))
+        return -(-rows // 8) * self.tiles_per_row * 128
+
+    def storage_index(self, device):
+        """(n_cells,) int64: where cell k is stored (identity when untiled).  Cached per device."""
+        if not self.tiled:
+            return None
+        key = (str(device), int(self.width), int(self.n_cells))
+        hit = _STORAGE_INDEX.get(key)
+        if hit is None:
+            if len(_STORAGE_INDEX) > 4:
+                _STORAGE_INDEX.clear()
+            k = torch.arange(int(self.n_cells), device=device)
+            row, col = k // int(self.width), k % int(self.width)
+            hit = _STORAGE_INDEX[key] = (((row >> 3) * self.tiles_per_row + (col >> 4)) << 7) | ((row & 7) << 4) | (col & 15)
+        return hit
 
     @staticmethod
     def work_flags(update_outputs):
@@ -113,9 +140,12 @@ class PredPreySpec:
     def c_model(self):
         return nat.PPModel(abi_version=nat.ABI_VERSION, width=int(self.width), max_y=int(self.max_y),
                            apply_pred_work=int(self.apply_pred_work), apply_prey_work=int(self.apply_prey_work),
-                           n_cells=int(self.n_cells), pred_work=float(self.pred_work), prey_work=float(self.prey_work),
+                           tiles_per_row=int(self.tiles_per_row), n_storage=int(self.n_storage), n_cells=int(self.n_cells), pred_work=float(self.pred_work), prey_work=float(self.prey_work),
                            prey_nutrition=float(self.prey_nutrition), grass_nutrition=float(self.grass_nutrition),
                            regrowth_time=float(self.regrowth_time))
+
+
+_STORAGE_INDEX = {}
 
 
 def info_bytes(n_cells):
@@ -190,17 +220,27 @@ class PredPreyState:
         if growth_stage.numel() != spec.n_cells or cd.numel() != spec.n_cells:
             raise ValueError("grass tensors must have one entry per cell")
         f32 = lambda t: t.reshape(-1).to(torch.float32).clone().contiguous()          # noqa: E731
-        st = cls(pc, f32(pred_energy), yc, f32(prey_energy), pack_stage(growth_stage, spec.n_cells), cd.contiguous())
+        info = pack_stage(growth_stage, spec.n_cells)
+        if spec.tiled:                            # cell-number order -> tile order; the padding never grows
+            sidx = spec.storage_index(cd.device)
+            tiled_info = torch.zeros(info_bytes(spec.n_storage), dtype=torch.uint8, device=cd.device)
+            tiled_info[sidx] = info[: spec.n_cells]
+            tiled_cd = torch.full((spec.n_storage,), float("inf"), dtype=cd.dtype, device=cd.device)
+            tiled_cd[sidx] = cd
+            info, cd = tiled_info, tiled_cd
+        st = cls(pc, f32(pred_energy), yc, f32(prey_energy), info, cd.contiguous())
         if sort:
-            st.sort_by_cell()
+            st.sort_by_cell(spec)
         return st
 
-    def sort_by_cell(self):
-        """Reorder the slots of both species by cell, IN PLACE (buffer addresses — and captured graphs — stay valid)."""
+    def sort_by_cell(self, spec=None):
+        """Reorder the slots of both species by (the storage address of) their cell, IN PLACE (buffer addresses — and
+        captured graphs — stay valid)."""
+        sidx = spec.storage_index(self.pred_cell.device) if spec is not None and spec.tiled else None
         for cell, energy, name in ((self.pred_cell, self.pred_energy, "pred_id"), (self.prey_cell, self.prey_energy, "prey_id")):
             if cell.numel() == 0:
                 continue
-            order = torch.argsort(cell)
+            order = torch.argsort(cell if sidx is None else sidx[cell.to(torch.int64)])
             ids = getattr(self, name)
             if ids is None:
                 setattr(self, name, order.to(torch.int32))
@@ -235,13 +275,23 @@ class PredPreyState:
         out[ids.to(torch.int64)] = v
         return out
 
+    def grass_in_cell_order(self, spec):
+        """(info bytes, countdown) indexed by cell number (undoes the tiled storage order)."""
+        if not spec.tiled:
+            return self.info, self.countdown
+        sidx = spec.storage_index(self.info.device)
+        info = torch.zeros(info_bytes(spec.n_cells), dtype=torch.uint8, device=self.info.device)
+        info[: spec.n_cells] = self.info[sidx]
+        return info, self.countdown[sidx]
+
     def to_reference(self, spec):
-        """Dict of tensors in the reference's shapes (agents in agent-number order)."""
+        """Dict of tensors in the reference's shapes (agents in agent-number order, grass in cell-number order)."""
+        info, cd = self.grass_in_cell_order(spec)
         return {"pred_pos": unpack_cells(self.in_agent_order("pred_cell"), spec.max_y),
                 "pred_energy": self.in_agent_order("pred_energy").reshape(-1, 1).clone(),
                 "prey_pos": unpack_cells(self.in_agent_order("prey_cell"), spec.max_y),
                 "prey_energy": self.in_agent_order("prey_energy").reshape(-1, 1).clone(),
-                "growth_stage": unpack_stage(self.info, spec.n_cells), "growth_countdown": self.countdown.reshape(-1, 1).clone()}
+                "growth_stage": unpack_stage(info, spec.n_cells), "growth_countdown": cd.reshape(-1, 1).clone()}
 
 
 class PredPreyEngine:
@@ -256,6 +306,8 @@ class PredPreyEngine:
         nat.lib()
         self.model = spec.c_model()
         self.csr = adjacency if isinstance(adjacency, CsrAdjacency) else None
+        if spec.tiled and self.csr is not None:
+            raise ValueError("tiled cell storage needs the implicit lattice (no CSR adjacency)")
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.grid = int(grid)
@@ -317,7 +369,7 @@ class PredPreyEngine:
         while done < num_steps:
             chunk = min(resort_every, num_steps - done) if resort_every else num_steps
             if done and st.pred_id is not None:
-                st.sort_by_cell()                      # between two steps: nothing is in flight, the order is free
+                st.sort_by_cell(self.spec)             # between two steps: nothing is in flight, the order is free
             self._launch(st, nat.MOVE, t_move=base + done, occ_in=1, occ_out=0, **kw)
             for s in range(chunk):
                 flags = nat.EAT | nat.HUNT | nat.EAT_APPLY | nat.GROW | nat.CLEAR | nat.EAT_IMPLICIT
@@ -360,5 +412,5 @@ class PredPreyEngine:
         a.n_pred, a.n_prey = st.pred_cell.numel(), st.prey_cell.numel()
         a.pred_energy, a.prey_energy, a.info = _ptr(st.pred_energy), _ptr(st.prey_energy), _ptr(st.info, torch.uint8)
         out = torch.zeros(3, dtype=torch.int64, device=self.device)
-        nat.check(nat.lib().at_pp_census(ctypes.byref(a), int(self.spec.n_cells), _ptr(out), _stream()))
+        nat.check(nat.lib().at_pp_census(ctypes.byref(a), int(self.spec.n_storage), _ptr(out), _stream()))
         return tuple(int(v) for v in out.tolist())

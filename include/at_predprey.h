@@ -19,7 +19,8 @@
  *     bit 2  a predator stands here   } occupancy of parity 0
  *     bit 3  a prey stands here       }
  *     bit 4, 5  the same for parity 1 (the occupancy of consecutive steps alternates between the two pairs)
- * The info array has at_pp_info_bytes(n_cells) bytes (n_cells rounded up to a multiple of 16).
+ * The info array has at_pp_info_bytes(n_cells) bytes (n_cells rounded up to a multiple of 16), or
+ * at_pp_storage_cells(...) bytes with tiled storage.
  */
 #ifndef AT_PREDPREY_H
 #define AT_PREDPREY_H
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AT_PP_ABI_VERSION 3
+#define AT_PP_ABI_VERSION 4
 
 /* at_pp_launch.flags — what one call does, always in this order:
  *   OCCUPANCY  mark the cells holding >= 1 predator / >= 1 prey in the occupancy bits of parity `occ_in` (needed by
@@ -58,7 +59,8 @@ typedef struct at_pp_model {
     int32_t max_y;            /* coordinates: x = cell / max_y, y = cell % max_y (move.py:36,43-44) */
     int32_t apply_pred_work;  /* 0 when the YAML output mapping drops the new predator energy (controller.py:73-81) */
     int32_t apply_prey_work;  /* 0 for the shipped config.yaml:281-285 (pred_energy listed twice) */
-    int32_t reserved;
+    int32_t tiles_per_row;    /* 0: info / countdown stored at the cell number.  ceil(width / 16): stored in tiles of 8 rows x 16
+                                 columns (one 128-byte line of info bytes per tile), see at_pp_storage_cells */
     int64_t n_cells;
     float pred_work;          /* agents/predator/stride_work */
     float prey_work;          /* agents/prey/stride_work */
@@ -66,6 +68,7 @@ typedef struct at_pp_model {
     float grass_nutrition;    /* objects/grass/nutritional_value: gained by a prey that eats */
     float regrowth_time;      /* objects/grass/regrowth_time */
     float reserved_f;
+    int64_t n_storage;        /* cells as stored: n_cells (or 0) untiled, at_pp_storage_cells(width, n_cells, 1) tiled */
 } at_pp_model;
 
 typedef struct at_pp_launch {
@@ -98,6 +101,10 @@ const char* at_pp_last_error(void);
 int64_t at_pp_sizeof_model(void);
 int64_t at_pp_sizeof_launch(void);
 int64_t at_pp_info_bytes(int64_t n_cells);
+/* Tiled storage: cell (row, col) of the lattice lives at ((row/8 * tiles_per_row + col/16) * 128 + (row%8) * 16 + col%16);
+ * cells of the padding must hold info 0 and countdown +inf.  The pack/unpack helpers below work on cell-number order;
+ * the caller permutes (agenttorch_b200/predprey.py does it with one gather per array at the boundary). */
+int64_t at_pp_storage_cells(int32_t width, int64_t n_cells, int32_t tiled);
 
 /* One call = up to three kernels (occupancy; agents; cells), see the flag list. */
 int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* stream);

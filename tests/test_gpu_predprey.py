@@ -45,8 +45,12 @@ def _assert_equal(st, spec, want, where):
 def test_kernels_match_reference_trajectory(case, mode):
     from agenttorch_b200.predprey import CsrAdjacency, PredPreyEngine
 
+    import dataclasses
+
     g = load_predprey_golden(case)
     spec = _spec_from_golden(g)
+    if mode == "fused_sorted":
+        spec = dataclasses.replace(spec, tiled=True)         # grass stored in 8 x 16 tiles, agents sorted by tile address
     adj = CsrAdjacency(torch.from_numpy(g["adjacency"].astype(np.int64)), DEV) if mode == "substeps_csr" else None
     eng = PredPreyEngine(spec, DEV, adjacency=adj)
     st = _state_from(spec, g)
@@ -56,8 +60,9 @@ def test_kernels_match_reference_trajectory(case, mode):
             eng.move(st, t, seed); eng.eat(st); eng.hunt(st); eng.grow(st)
             _assert_equal(st, spec, {k: g["traj_" + k][t] for k in PREDPREY_KEYS}, (case, mode, t))
     elif mode == "fused_sorted":
-        st.sort_by_cell()                                # slots ordered by cell; the draws still follow the agent numbers
-        assert bool((st.prey_cell[1:] >= st.prey_cell[:-1]).all())
+        st.sort_by_cell(spec)                            # slots ordered by cell; the draws still follow the agent numbers
+        addr = spec.storage_index(DEV)[st.prey_cell.long()]
+        assert bool((addr[1:] >= addr[:-1]).all())
         eng.run(st, T, seed, cuda_graph=True, resort_every=5)
         _assert_equal(st, spec, {k: g["traj_" + k][T - 1] for k in PREDPREY_KEYS}, (case, mode))
         eng.run(st, 0, seed)
@@ -99,14 +104,14 @@ def test_fused_steps_match_oracle_on_seeded_grids(shape, n_pred, n_prey, f64):
     init["growth_stage"] = (init["growth_countdown"] <= 0).astype(np.int64)
     consts = dict(pred_work=1.5, prey_work=2.25, prey_nutrition=6.5, grass_nutrition=3.3, regrowth_time=7.7)
     port = PredPreyPort(PredPreyConstants(mx, my, **consts), **init)
-    spec = PredPreySpec(mx, my, C, mx, **consts)
+    spec = PredPreySpec(mx, my, C, mx, tiled=f64, **consts)
     eng = PredPreyEngine(spec, DEV)
     st = _state_from(spec, init, prefix="")
     T, seed = 12, 2026
     for t in range(T):
         port.step(t, seed)
     if f64:
-        st.sort_by_cell()
+        st.sort_by_cell(spec)
     eng.run(st, T, seed, resort_every=4 if f64 else 0)
     _assert_equal(st, spec, port.snapshot(), (shape, "fused"))
     alive_pred, alive_prey, grown = eng.census(st)
@@ -293,11 +298,17 @@ def test_baseline_size_properties():
     eng.run(b, 4, 99, cuda_graph=False); eng.run(b, 6, 99, t0=4, cuda_graph=True)
     for k in ("pred_cell", "pred_energy", "prey_cell", "prey_energy", "info", "countdown"):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
-    c.sort_by_cell()                                   # the cell-sorted slot order changes nothing but the speed
-    eng.run(c, 10, 99, cuda_graph=True, resort_every=4)
+    # tiled grass storage + slots sorted by tile address change nothing but the speed
+    import dataclasses
+    tspec = dataclasses.replace(spec, tiled=True)
+    ref0 = st0.to_reference(spec)
+    c = PredPreyState.from_reference(tspec, ref0["pred_pos"], ref0["pred_energy"], ref0["prey_pos"], ref0["prey_energy"],
+                                     ref0["growth_stage"], ref0["growth_countdown"], sort=True)
+    PredPreyEngine(tspec, DEV).run(c, 10, 99, cuda_graph=True, resort_every=4)
     for k in ("pred_cell", "pred_energy", "prey_cell", "prey_energy"):
         assert torch.equal(getattr(a, k), c.in_agent_order(k)), k
-    assert torch.equal(a.info, c.info) and torch.equal(a.countdown, c.countdown)
+    c_info, c_cd = c.grass_in_cell_order(tspec)
+    assert torch.equal(a.info, c_info) and torch.equal(a.countdown, c_cd)
     # grass: stage <=> countdown <= 0 after every grow; countdowns stay in [-(steps), regrowth]
     from agenttorch_b200.predprey import unpack_stage
     stage = unpack_stage(a.info, C).reshape(-1)
@@ -337,10 +348,10 @@ def test_edge_cases_match_oracle(shape, n_pred, n_prey):
     init["growth_stage"] = (init["growth_countdown"] <= 0).astype(np.int64)
     consts = dict(pred_work=0.75, prey_work=1.25, prey_nutrition=2.5, grass_nutrition=1.5, regrowth_time=2.2)
     port = PredPreyPort(PredPreyConstants(mx, my, **consts), **init)
-    spec = PredPreySpec(mx, my, C, mx, **consts)
+    spec = PredPreySpec(mx, my, C, mx, tiled=True, **consts)
     eng = PredPreyEngine(spec, DEV)
     st = _state_from(spec, init, prefix="")
-    st.sort_by_cell()
+    st.sort_by_cell(spec)
     for t in range(9):
         port.step(t, 77)
     eng.run(st, 4, 77, cuda_graph=False)

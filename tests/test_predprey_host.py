@@ -66,3 +66,20 @@ def test_reference_file_helpers(tmp_path):
     assert t.dtype == torch.int64 and t.tolist() == [[3, 12], [1, 5]]
     g, lat = grid_network({"shape": [4, 6]})
     assert g is None and lat.n_cells == 24 and lat.width == 4
+
+
+@pytest.mark.parametrize("shape", [(18, 25), (16, 8), (1, 9), (33, 31), (64, 64)])
+def test_tiled_storage_index_is_an_injection_into_whole_tiles(shape):
+    w, h = shape
+    spec = PredPreySpec(w, h, w * h, w, tiled=True)
+    sidx = spec.storage_index("cpu")
+    assert sidx.shape == (w * h,) and int(sidx.min()) >= 0 and int(sidx.max()) < spec.n_storage
+    assert torch.unique(sidx).numel() == w * h and spec.n_storage % 128 == 0
+    # the four lattice neighbours of an interior cell share its 128-byte tile unless it sits on the tile's border
+    k = torch.arange(w * h)
+    row, col = k // w, k % w
+    inner = (row % 8 > 0) & (row % 8 < 7) & (col % 16 > 0) & (col % 16 < 15) & (row + 1 < h) & (col + 1 < w)
+    for d in (-w, -1, 1, w):
+        kk = k[inner] + d
+        assert bool(((sidx[kk] >> 7) == (sidx[k[inner]] >> 7)).all())
+    assert PredPreySpec(w, h, w * h, w).storage_index("cpu") is None and PredPreySpec(w, h, w * h, w).n_storage == w * h

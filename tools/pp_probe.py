@@ -15,12 +15,13 @@ ap.add_argument("--f64", type=int, default=0)
 ap.add_argument("--grid", type=int, default=0)
 ap.add_argument("--sort", type=int, default=1)
 ap.add_argument("--resort", type=int, default=0)
+ap.add_argument("--tiled", type=int, default=1)
 args = ap.parse_args()
 dev = "cuda:0"
 mx = my = args.side
 C = mx * my
 g = torch.Generator(device=dev); g.manual_seed(1)
-spec = PredPreySpec(mx, my, C, mx)
+spec = PredPreySpec(mx, my, C, mx, tiled=bool(args.tiled and args.sort))
 pos = lambda n: torch.stack([torch.randint(0, mx, (n,), generator=g, device=dev), torch.randint(0, my, (n,), generator=g, device=dev)], 1)
 cd = torch.where(torch.rand(C, generator=g, device=dev) < 0.4, 0.0, torch.randint(1, 101, (C,), generator=g, device=dev).float())
 if args.f64:
@@ -28,7 +29,7 @@ if args.f64:
 st0 = PredPreyState.from_reference(spec, pos(args.pred), 30 + 71 * torch.rand(args.pred, 1, generator=g, device=dev), pos(args.prey),
                                    40 + 61 * torch.rand(args.prey, 1, generator=g, device=dev), (cd <= 0).long(), cd)
 if args.sort:
-    st0.sort_by_cell()
+    st0.sort_by_cell(spec)
 eng = PredPreyEngine(spec, dev, grid=args.grid)
 st = st0.clone()
 times = []
@@ -43,5 +44,5 @@ ms = statistics.median(times[2:])
 n = args.pred + args.prey
 cd_b = 8 if args.f64 else 4
 bytes_step = n * (20 if args.sort else 16) + C * 2 * (cd_b + 1)      # agents: cell + energy read and written; cells: info byte + countdown read and written
-print(f"sort={args.sort} resort={args.resort} predator-prey {n/1e6:.1f} M agents, {mx}x{my} cells, {args.steps} steps: {ms:.3f} ms -> {ms/args.steps*1e3:.1f} us/step, "
+print(f"sort={args.sort} tiled={args.tiled} resort={args.resort} predator-prey {n/1e6:.1f} M agents, {mx}x{my} cells, {args.steps} steps: {ms:.3f} ms -> {ms/args.steps*1e3:.1f} us/step, "
       f"{n*args.steps/ms/1e6:.1f} G agent-steps/s, algorithmic {bytes_step/1e6:.0f} MB/step -> {bytes_step*args.steps/ms/1e9:.2f} TB/s; census {eng.census(st)}")
