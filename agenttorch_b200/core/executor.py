@@ -10,7 +10,11 @@ class BaseExecutor:
         self.model = model
 
     def _get_runner(self, config):
-        registry = importlib.import_module(self.model.__name__).registry
+        # The registry tables are class-level and shared by every model in the process (registry.py:8-14): another
+        # model imported later may have re-registered a helper of the same name (both covid and predator_prey bring a
+        # `read_from_file`).  Re-assert this model's registrations before building its runner.
+        module = importlib.import_module(self.model.__name__)
+        registry = module.get_registry() if hasattr(module, "get_registry") else module.registry
         return Runner(config, registry)
 
 

@@ -24,7 +24,7 @@ def get_registry():
 registry = get_registry()
 
 
-def get_runner(config, registry):
+def get_runner(config, registry=None):
     from agenttorch_b200.core.runner import Runner
 
-    return Runner(config, registry)
+    return Runner(config, get_registry())          # re-assert this model's helpers in the shared tables (see Executor)

@@ -26,7 +26,7 @@ if plan_for not in FUSED_PLANNERS:
     FUSED_PLANNERS.append(plan_for)
 
 
-def get_runner(config, registry):
+def get_runner(config, registry=None):
     from agenttorch_b200.core.runner import Runner
 
-    return Runner(config, registry)
+    return Runner(config, get_registry())          # re-assert this model's helpers in the shared tables (see Executor)

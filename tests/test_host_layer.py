@@ -2,6 +2,7 @@
 decorators, vmap.  Cases follow the reference's own tests where they exist (tests/test_initializer.py)."""
 import os
 
+import numpy as np
 import pytest
 import torch
 import yaml
@@ -229,3 +230,25 @@ def test_reference_r_quirk_q2():
     tr.calibrate_R2 = torch.tensor([1.0, 2.0, 3.0], requires_grad=True)
     assert [float(tr.effective_r(t)) for t in (0, 7, 14)] == [1.0, 2.0, 3.0]
     assert runner.state["agents"]["citizens"]["age"].shape == (256, 1)
+
+
+def test_models_sharing_helper_names_do_not_break_each_other(tmp_path):
+    """The registry tables are class-level (registry.py:8-14) and both models register a `read_from_file`; whichever
+    model builds a runner must get its own helpers, whatever the import order."""
+    from agenttorch_b200.core import envs
+    from agenttorch_b200.core.registry import Registry
+    from agenttorch_b200.models import covid, predator_prey
+    from agenttorch_b200.models.covid.substeps import utils
+    from agenttorch_b200.populations import write_population_folder
+
+    predator_prey.get_registry()                                   # last registration wins ...
+    assert Registry.helpers["initialization"]["read_from_file"] is not utils.read_from_file
+    rng = np.random.default_rng(0)
+    folder = write_population_folder(str(tmp_path / "pop"), rng.integers(0, 6, 64), (rng.random(64) < 0.1).astype(np.float64),
+                                     np.stack([rng.integers(0, 64, 200), rng.integers(0, 64, 200)], 1))
+    runner = envs.create(model=covid, population=folder)           # ... but covid's executor re-asserts covid's helpers
+    assert Registry.helpers["initialization"]["read_from_file"] is utils.read_from_file
+    assert runner.state["agents"]["citizens"]["disease_stage"].shape == (64, 1)
+    pp_runner = predator_prey.get_runner(predator_prey.synthetic.synthetic_config(8, 8, 5, 9, device="cpu"))
+    pp_runner.init()
+    assert Registry.helpers["initialization"]["read_from_file"] is not utils.read_from_file
