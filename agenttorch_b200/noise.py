@@ -47,3 +47,14 @@ def isolation_decision(seed, step, agent_ids, mode="soft", p_isolate=0.3):
     if mode == "hard":
         return (w < torch.tensor(p_isolate, dtype=torch.float32)).to(torch.float32)
     raise ValueError(mode)
+
+
+STREAM_QUARANTINE, STREAM_TESTING, STREAM_MORTALITY = 1, 2, 3
+
+
+def stream_uniforms(seed, step, agent_ids, stream):
+    """(top 24 bits, bits 8..31) of the hash addressed (seed, step, agent | stream << 36): the draws of the
+    intervention kernels (csrc/at_interventions.cu) as tensors."""
+    z = noise_u64(seed, step, agent_ids.to(torch.int64) | (int(stream) << 36))
+    return (_lsr(z, 40).to(torch.float32) * (1.0 / 16777216.0),
+            (_lsr(z, 8) & 0xFFFFFF).to(torch.float32) * (1.0 / 16777216.0))

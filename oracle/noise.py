@@ -60,3 +60,17 @@ def move_draw(seed, step, species, agent_ids):
     Species 0 = predator, 1 = prey; the species is bit 39 of the counter's agent field."""
     ids = np.asarray(agent_ids, dtype=np.uint64) | (np.uint64(species) << np.uint64(39))
     return (noise_u64(seed, step, ids) >> np.uint64(40)).astype(np.int64)
+
+
+# ----------------------------------------------------------------- intervention substeps (SURVEY.md 8f row 3)
+# Streams live in bits 36..38 of the counter's agent field (agent ids stay below 2^36):
+STREAM_QUARANTINE, STREAM_TESTING, STREAM_MORTALITY = 1, 2, 3
+
+
+def stream_uniforms(seed, step, agent_ids, stream):
+    """Two uniforms per (seed, step, agent, stream): (top 24 bits, bits 8..31) of one hash, float32 k * 2^-24.
+    quarantine: (start draw, break draw); testing: (compliance draw, unused); mortality: (death draw, unused)."""
+    ids = np.asarray(agent_ids, dtype=np.uint64) | (np.uint64(stream) << np.uint64(36))
+    z = noise_u64(seed, step, ids)
+    return ((z >> np.uint64(40)).astype(np.float32) * _INV24,
+            ((z >> np.uint64(8)) & np.uint64(0xFFFFFF)).astype(np.float32) * _INV24)

@@ -61,3 +61,19 @@ def predprey_port_from_golden(g, use_adjacency=False):
 
 
 PREDPREY_KEYS = ("pred_pos", "pred_energy", "prey_pos", "prey_energy", "growth_stage", "growth_countdown")
+
+
+# ------------------------------------------------------------------- quarantine / testing / SEIRMS progression
+INTERVENTION_CASES = ["interventions_1500_hard", "interventions_1500_default", "interventions_1500_busy"]
+SEIRMS_CASES = ["seirms_1500_hard", "seirms_1500_soft", "seirms_64_hard"]
+
+
+def load_interventions_golden(name):
+    """Fixture written by oracle/ref_harness/make_golden_interventions.py (outputs of the real reference)."""
+    import json
+
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    g["mode"], g["variant"] = str(g["mode"]), str(g["variant"])
+    g["seed"], g["num_steps"] = int(g["seed"]), int(g["num_steps"])
+    g["overrides"] = json.loads(str(g["overrides"]))
+    return g
