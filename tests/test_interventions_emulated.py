@@ -1,0 +1,163 @@
+"""The DEVICE code of csrc/at_interventions.cu, compiled for the host with a small shim (tests/host_emulation/), against
+the reference's outputs and the oracle: the kernel source itself is checked on a machine without a GPU.  (The -m gpu
+tests run the same comparisons on the real library.)"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from agenttorch_b200 import _native_iv as nat
+from oracle import noise as onoise
+from oracle.interventions_port import SeirmsPort
+from tests.helpers import INTERVENTION_CASES, SEIRMS_CASES, load_interventions_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emu") / "iv_emulation.so")
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "host_emulation", "iv_emulation.cpp"), "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    lib = ctypes.CDLL(out)
+    for name, struct in (("emu_quarantine", nat.QuarantineArgs), ("emu_testing", nat.TestingArgs), ("emu_seirms", nat.SeirmsArgs)):
+        getattr(lib, name).argtypes = [ctypes.POINTER(struct), ctypes.c_int, ctypes.c_int]
+        getattr(lib, name).restype = None
+    return lib
+
+
+def aligned(n, dtype, fill=0, offset=0):
+    """(n,) array whose first element sits `offset` elements after a 16-byte boundary."""
+    item = np.dtype(dtype).itemsize
+    raw = np.zeros((n + offset) * item + 64, dtype=np.uint8)
+    start = (-raw.ctypes.data) % 16
+    arr = raw[start:start + (n + offset) * item].view(dtype)[offset:]
+    arr[:] = fill
+    return arr
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def make_quarantine_args(g, t, flags, stage, q_in, d_in, q_out, d_out, start=None, brk=None, us=None, ub=None):
+    ov = g["overrides"]
+    return nat.QuarantineArgs(
+        abi_version=nat.ABI_VERSION, flags=flags, t=t, stage_f64=int(stage.dtype == np.float64), n=len(q_in), id_offset=0,
+        seed=g["seed"], seed_ptr=None, p_start=ov["env"]["quarantine_start_prob"], p_break=ov["env"]["quarantine_break_prob"],
+        quarantine_days=ov["meta"]["quarantine_days"], infinity_time=ov["meta"]["INFINITY_TIME"], stage=ptr(stage), u_start=ptr(us),
+        u_break=ptr(ub), is_q_in=ptr(q_in), start_date_in=ptr(d_in), start_action=ptr(start), break_action=ptr(brk),
+        is_q_out=ptr(q_out), start_date_out=ptr(d_out))
+
+
+def make_testing_args(g, t, flags, is_q, aw, rd, re, aw_o, rd_o, re_o, accept=None, uc=None):
+    ov = g["overrides"]
+    return nat.TestingArgs(
+        abi_version=nat.ABI_VERSION, flags=flags, t=t, reserved=0, n=len(aw), id_offset=0, seed=g["seed"], seed_ptr=None,
+        p_comply=ov["env"]["test_compliance_prob"], ineligible_days=ov["meta"]["test_ineligible_days"],
+        result_delay_days=ov["meta"]["test_result_delay_days"], infinity_time=ov["meta"]["INFINITY_TIME"], u_comply=ptr(uc),
+        is_q=ptr(is_q), accept_action=ptr(accept), awaiting_in=ptr(aw), result_date_in=ptr(rd), re_eligible_in=ptr(re),
+        awaiting_out=ptr(aw_o), result_date_out=ptr(rd_o), re_eligible_out=ptr(re_o))
+
+
+@pytest.mark.parametrize("name", INTERVENTION_CASES)
+@pytest.mark.parametrize("variant", ["fused_inplace_vec", "split_scalar_f64stage", "split_injected_unaligned"])
+def test_quarantine_and_testing_kernels_match_reference(emu, name, variant):
+    g = load_interventions_golden(name)
+    n, T = len(g["age"]), g["num_steps"]
+    ov = g["overrides"]
+    ini, inf_t = ov["initial"], ov["meta"]["INFINITY_TIME"]
+    off = 1 if variant == "split_injected_unaligned" else 0
+    vec = int(variant == "fused_inplace_vec")
+    f = np.float32
+    q = aligned(n, f, ini.get("is_quarantined", 0), off)
+    d = aligned(n, f, ini.get("quarantine_start_date", inf_t), off)
+    aw = aligned(n, f, ini.get("awaiting_test_result", 0), off)
+    rd = aligned(n, f, ini.get("test_result_date", inf_t), off)
+    re = aligned(n, f, ini.get("test_re_eligble_date", inf_t), off)
+    ids = np.arange(n)
+    for t in range(T):
+        stage32 = aligned(n, f, 0, off)
+        stage32[:] = g["ref_disease_stage_history"][t]
+        if variant == "fused_inplace_vec":
+            emu.emu_quarantine(make_quarantine_args(g, t, nat.DECIDE | nat.APPLY, stage32, q, d, q, d), vec, 3)
+            emu.emu_testing(make_testing_args(g, t, nat.DECIDE | nat.APPLY, q, aw, rd, re, aw, rd, re), vec, 2)
+        else:
+            stage = stage32.astype(np.float64) if variant == "split_scalar_f64stage" else stage32
+            us = ub = uc = None
+            if variant == "split_injected_unaligned":
+                u0, u1 = onoise.stream_uniforms(g["seed"], t, ids, onoise.STREAM_QUARANTINE)
+                us, ub = aligned(n, f, 0, off), aligned(n, f, 0, off)
+                us[:], ub[:] = u0, u1
+                uc = aligned(n, f, 0, off)
+                uc[:] = onoise.stream_uniforms(g["seed"], t, ids, onoise.STREAM_TESTING)[0]
+            start, brk = aligned(n, np.uint8, 7, off), aligned(n, np.uint8, 7, off)
+            # the two policies are separate launches, each writing its own action
+            emu.emu_quarantine(make_quarantine_args(g, t, nat.DECIDE, stage, q, None, None, None, start=start, us=us, ub=ub), vec, 2)
+            emu.emu_quarantine(make_quarantine_args(g, t, nat.DECIDE, stage, q, None, None, None, brk=brk, us=us, ub=ub), vec, 2)
+            assert set(np.unique(start)) <= {0, 1} and set(np.unique(brk)) <= {0, 1}
+            q2, d2 = aligned(n, f, -77, off), aligned(n, f, -77, off)
+            emu.emu_quarantine(make_quarantine_args(g, t, nat.APPLY, stage, q, d, q2, d2, start=start, brk=brk), vec, 5)
+            q, d = q2, d2
+            accept = aligned(n, f, -5, off)
+            emu.emu_testing(make_testing_args(g, t, nat.DECIDE, q, aw, None, None, None, None, None, accept=accept, uc=uc), vec, 1)
+            o = [aligned(n, f, -77, off) for _ in range(3)]
+            emu.emu_testing(make_testing_args(g, t, nat.APPLY, None, aw, rd, re, *o, accept=accept), vec, 4)
+            aw, rd, re = o
+        for key, arr in (("is_quarantined", q), ("quarantine_start_date", d), ("awaiting_test_result", aw), ("test_result_date", rd),
+                         ("test_re_eligble_date", re)):
+            assert np.array_equal(arr.astype(np.float64), g["ref_" + key + "_history"][t].astype(np.float64)), (key, t)
+
+
+@pytest.mark.parametrize("name", SEIRMS_CASES)
+@pytest.mark.parametrize("variant", ["inplace_vec", "scalar_injected_unaligned"])
+def test_seirms_kernel_matches_oracle_and_reference(emu, name, variant):
+    g = load_interventions_golden(name)
+    n, T = len(g["age"]), g["num_steps"]
+    meta = g["overrides"]["meta"]
+    port = SeirmsPort(g["age"], g["stage0"], g["edges"], recovered_to_susceptible_time=meta["RECOVERED_TO_SUSCEPTIBLE_TIME"])
+    r2, m = torch.tensor(g["r2"]), torch.tensor(g["m"])
+    st = port.initial_state()
+    ids = np.arange(n)
+    off = 0 if variant == "inplace_vec" else 3
+    f = np.float32
+    dd = aligned(T, f)
+    m_dev = aligned(1, f, float(g["m"][0]))
+    for t in range(T):
+        w = torch.from_numpy(onoise.isolation_decision(g["seed"], t, ids, g["mode"], float(g["p_isolate"])))
+        u = torch.from_numpy(onoise.exposure_uniform(g["seed"], t, ids))
+        st, _ = port.transmission(st, t, w, u, r2)
+        s_in, nt_in = aligned(n, f, 0, off), aligned(n, f, 0, off)
+        s_in[:], nt_in[:] = st.stage.numpy(), st.next_stage_time.numpy()
+        ud = None
+        if off:
+            ud = aligned(n, f, 0, off)
+            ud[:] = onoise.stream_uniforms(g["seed"], t, ids, onoise.STREAM_MORTALITY)[0]
+            s_out, nt_out = aligned(n, f, -9, off), aligned(n, f, -9, off)
+        else:
+            s_out, nt_out = s_in, nt_in
+        code = aligned(n, np.uint8, 9, off)
+        counts = aligned(4, np.int64)
+        args = nat.SeirmsArgs(
+            abi_version=nat.ABI_VERSION, t=t, n=n, id_offset=0, seed=g["seed"], seed_ptr=None, infected_to_recovered_time=5.0,
+            infinity_time=T + 20.0, recovered_to_susceptible_time=meta["RECOVERED_TO_SUSCEPTIBLE_TIME"], num_steps=T, m_value=ptr(m_dev),
+            u_death=ptr(ud), stage_in=ptr(s_in), next_stage_time_in=ptr(nt_in), stage_out=ptr(s_out), next_stage_time_out=ptr(nt_out),
+            move_code=ptr(code), counts=ptr(counts), daily_deaths=ptr(dd))
+        before = st.stage.numpy().copy()
+        emu.emu_seirms(args, int(off == 0), 3)
+        st = port.progression_seirms(st, t, m, onoise.stream_uniforms(g["seed"], t, ids, onoise.STREAM_MORTALITY)[0])
+        assert np.array_equal(s_out.astype(np.float64), st.stage.numpy()), t
+        assert np.array_equal(nt_out, st.next_stage_time.numpy()), t
+        assert np.array_equal(s_out.astype(np.float64), g["ref_disease_stage_history"][t].astype(np.float64)), t
+        assert np.array_equal(nt_out.astype(np.float64), g["ref_next_stage_time_history"][t].astype(np.float64)), t
+        due = (before == 2) & (code >= nat.MOVE_SURVIVED)
+        assert counts[0] == due.sum() == counts[1] + counts[2] and counts[1] == (code == nat.MOVE_DIED).sum()
+        assert np.array_equal(code == nat.MOVE_E_TO_I, (before == 1) & (s_out == 2))
+        assert np.array_equal(code == nat.MOVE_R_TO_S, (before == 3) & (s_out == 0))
+    assert np.allclose(dd, g["ref_daily_deaths"], rtol=1e-6, atol=0)
+    assert np.array_equal(dd, st.daily_deaths.numpy())

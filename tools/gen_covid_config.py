@@ -34,6 +34,7 @@ cfg = {
     "simulation_metadata": {
         "EXECUTION_MODE": "heuristic", "EXPOSED_TO_INFECTED_TIME": 5, "EXPOSED_VAR": 1, "INFECTED_TO_RECOVERED_TIME": 5,
         "INFECTED_VAR": 2, "INFINITY_TIME": 130, "MORTALITY_VAR": 4, "NUM_WEEKS": 3, "RECOVERED_VAR": 3,
+        "RECOVERED_TO_SUSCEPTIBLE_TIME": 100, "quarantine_days": 12, "test_ineligible_days": 2, "test_result_delay_days": 3,
         "SUSCEPTIBLE_VAR": 0, "calibration": True, "device": "auto",
         "cuda_params": {"fused_episode": True, "cuda_graph": True, "snapshot_pack_bools": True, "batch_size": 16384,
                         "pool_limit_per_shape": 8, "inplace_progress": False},
@@ -55,6 +56,15 @@ cfg = {
                                   args={**stage_file, "num_steps": arg("Num steps per episode", T)}),
             "next_stage_time": prop("Timestep for next transition", [N, 1], "int", gen="get_next_stage_time",
                                     args={**stage_file, "num_steps": arg("Num steps per episode", T)}),
+            # state of the quarantine / testing substeps (reference config.yaml:79-87,145-203; float32 after `value * ones`)
+            "awaiting_test_result": prop("agent is awaiting test result currently", [N, 1], "bool", value=False),
+            "is_quarantined": prop("Quarantine status for a citizen", [N, 1], "bool", value=False),
+            "quarantine_start_date": prop("Start date for last quarantine of agent", [N, 1], "int",
+                                          value="${simulation_metadata.INFINITY_TIME}"),
+            "test_re_eligble_date": prop("Date when agent becomes eligible for taking a test again", [N, 1], "int",
+                                         value="${simulation_metadata.INFINITY_TIME}"),
+            "test_result_date": prop("Date when agent receives test result", [N, 1], "int",
+                                     value="${simulation_metadata.INFINITY_TIME}"),
         }}},
         "environment": {
             "SFInfector": prop("Infectiousness of Infector", [5], "float", value=[0.0, 0.33, 0.72, 0.0, 0.0]),
@@ -70,6 +80,11 @@ cfg = {
             "mean_interactions": prop("Mean agent interactions across networks", [N, 1], "int",
                                       gen="get_mean_agent_interactions", args=age_file),
             "mortality_rate": prop("Mortality Rate", [1], "float", value=0.2),
+            "quarantine_break_prob": prop("Probability of breaking a quarantine mandate prior to recovery", [1], "float", value=0.1),
+            "quarantine_start_prob": prop("Probability of complying to a quarantine mandate", [1], "float", value=0.7),
+            "test_compliance_prob": prop("Probability of complying to test recommendation", [1], "float", value=0.95),
+            "test_false_positive_prob": prop("Probability of false positive test result", [1], "float", value=0.3),
+            "test_true_positive_prob": prop("Probability of true positive test result", [1], "float", value=0.8),
         },
         "network": {"agent_agent": {"infection_network": {
             "type": "network_from_file", "arguments": {"file_path": "${simulation_metadata.infection_network_file}"}}}},
