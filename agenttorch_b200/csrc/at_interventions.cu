@@ -111,6 +111,15 @@ __device__ __forceinline__ void load4_u8(const uint8_t* __restrict__ p, int64_t 
     }
 }
 
+// The next iteration's lines are requested from HBM into L2 while this iteration's loads are still in flight: twice the
+// bytes in flight per SM without holding them in registers (a thread's 16 bytes; a warp covers four 128-byte lines).
+__device__ __forceinline__ void prefetch4(const void* base, int64_t i, int64_t n, int elem_bytes = 4)
+{
+#ifndef AT_IV_HOST_EMULATION
+    if (base != nullptr && i < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + i * elem_bytes));
+#endif
+}
+
 __device__ __forceinline__ bool differs(const F4& a, const F4& b)
 {
     return a.v[0] != b.v[0] || a.v[1] != b.v[1] || a.v[2] != b.v[2] || a.v[3] != b.v[3];
@@ -121,7 +130,7 @@ __device__ __forceinline__ float u_lo(uint64_t z) { return (float)(uint32_t)((z 
 __device__ __forceinline__ uint64_t agent_key(int64_t id, int stream) { return (uint64_t)id | ((uint64_t)stream << 36); }
 
 // ------------------------------------------------------------------------------------------- quarantine
-__global__ void __launch_bounds__(IV_THREADS) iv_quarantine_kernel(const at_iv_quarantine_args a, const bool vec)
+__global__ void __launch_bounds__(IV_THREADS, 5) iv_quarantine_kernel(const at_iv_quarantine_args a, const bool vec)
 {
     const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
     const bool decide = a.flags & AT_IV_DECIDE, apply = a.flags & AT_IV_APPLY;
@@ -129,8 +138,24 @@ __global__ void __launch_bounds__(IV_THREADS) iv_quarantine_kernel(const at_iv_q
     const float tf = (float)a.t;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = g << 2;
+        // every load of the group is issued before anything is computed: one round of memory latency per group
         const F4 q = load4(a.is_q_in, i, a.n, vec);
+        {
+            const int64_t nx = (g + (int64_t)gridDim.x * blockDim.x) << 2;
+            prefetch4(a.is_q_in, nx, a.n);
+            if (apply) prefetch4(a.start_date_in, nx, a.n);
+            if (decide) prefetch4(a.stage, nx, a.n, a.stage_f64 ? 8 : 4);
+        }
+        F4 d, sv, us, ub;
+        if (apply) d = load4(a.start_date_in, i, a.n, vec);
+        if (decide && !a.stage_f64) sv = load4(reinterpret_cast<const float*>(a.stage), i, a.n, vec);
+        if (decide && a.u_start) us = load4(a.u_start, i, a.n, vec, 1.f);
+        if (decide && a.u_break) ub = load4(a.u_break, i, a.n, vec, 1.f);
         bool start[4], brk[4];
+        if (!decide) {
+            load4_u8(a.start_action, i, a.n, start);
+            load4_u8(a.break_action, i, a.n, brk);
+        }
         if (decide) {
             // quarantine/action.py:27-46,59-66: start = draw & not quarantined (I2) & (E or I); break = quarantined & draw
             float s[4];
@@ -138,13 +163,9 @@ __global__ void __launch_bounds__(IV_THREADS) iv_quarantine_kernel(const at_iv_q
 #pragma unroll
                 for (int k = 0; k < 4; ++k) s[k] = (i + k < a.n) ? (float)reinterpret_cast<const double*>(a.stage)[i + k] : 0.f;
             } else {
-                const F4 sv = load4(reinterpret_cast<const float*>(a.stage), i, a.n, vec);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) s[k] = sv.v[k];
             }
-            F4 us, ub;
-            if (a.u_start) us = load4(a.u_start, i, a.n, vec, 1.f);
-            if (a.u_break) ub = load4(a.u_break, i, a.n, vec, 1.f);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const bool ei = (s[k] == 1.f) | (s[k] == 2.f);
@@ -165,13 +186,9 @@ __global__ void __launch_bounds__(IV_THREADS) iv_quarantine_kernel(const at_iv_q
             }
             if (a.start_action) store4_u8(a.start_action, i, a.n, start);
             if (a.break_action) store4_u8(a.break_action, i, a.n, brk);
-        } else {
-            load4_u8(a.start_action, i, a.n, start);
-            load4_u8(a.break_action, i, a.n, brk);
         }
         if (apply) {
             // quarantine/transition.py:31-90: end (I1: not conditioned on the status), start, break — in this order
-            const F4 d = load4(a.start_date_in, i, a.n, vec);
             F4 nq, nd;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -192,7 +209,7 @@ __global__ void __launch_bounds__(IV_THREADS) iv_quarantine_kernel(const at_iv_q
 }
 
 // ---------------------------------------------------------------------------------------------- testing
-__global__ void __launch_bounds__(IV_THREADS) iv_testing_kernel(const at_iv_testing_args a, const bool vec)
+__global__ void __launch_bounds__(IV_THREADS, 4) iv_testing_kernel(const at_iv_testing_args a, const bool vec)
 {
     const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
     const bool decide = a.flags & AT_IV_DECIDE, apply = a.flags & AT_IV_APPLY;
@@ -200,12 +217,26 @@ __global__ void __launch_bounds__(IV_THREADS) iv_testing_kernel(const at_iv_test
     const float tf = (float)a.t;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = g << 2;
-        F4 w;
+        F4 w, q, uc, aw, rd, re;
+        {
+            const int64_t nx = (g + (int64_t)gridDim.x * blockDim.x) << 2;
+            if (decide) prefetch4(a.is_q, nx, a.n);
+            if (apply) {
+                prefetch4(a.awaiting_in, nx, a.n);
+                prefetch4(a.result_date_in, nx, a.n);
+                prefetch4(a.re_eligible_in, nx, a.n);
+            }
+        }
+        if (decide) q = load4(a.is_q, i, a.n, vec);
+        if (decide && a.u_comply) uc = load4(a.u_comply, i, a.n, vec, 1.f);
+        if (!decide) w = load4(a.accept_action, i, a.n, vec);
+        if (apply) {
+            aw = load4(a.awaiting_in, i, a.n, vec);
+            rd = load4(a.result_date_in, i, a.n, vec);
+            re = load4(a.re_eligible_in, i, a.n, vec);
+        }
         if (decide) {
             // testing/action.py:29-53: every stage is "eligible" (I3); willing = not quarantined (I2) & compliance draw
-            const F4 q = load4(a.is_q, i, a.n, vec);
-            F4 uc;
-            if (a.u_comply) uc = load4(a.u_comply, i, a.n, vec, 1.f);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float u = a.u_comply ? uc.v[k]
@@ -213,14 +244,9 @@ __global__ void __launch_bounds__(IV_THREADS) iv_testing_kernel(const at_iv_test
                 w.v[k] = ((truncf(q.v[k]) == 0.f) & (u < a.p_comply)) ? 1.f : 0.f;
             }
             if (a.accept_action) store4(a.accept_action, i, a.n, vec, w);
-        } else {
-            w = load4(a.accept_action, i, a.n, vec);
         }
         if (apply) {
             // testing/transition.py:53-58,96-100 (results due today), :146-163 (enrolment)
-            const F4 aw = load4(a.awaiting_in, i, a.n, vec);
-            const F4 rd = load4(a.result_date_in, i, a.n, vec);
-            const F4 re = load4(a.re_eligible_in, i, a.n, vec);
             F4 naw, nrd, nre;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -244,19 +270,40 @@ __global__ void __launch_bounds__(IV_THREADS) iv_testing_kernel(const at_iv_test
 }
 
 // ----------------------------------------------------------------------------------- SEIRMS progression
-__global__ void __launch_bounds__(IV_THREADS) iv_seirms_kernel(const at_iv_seirms_args a, const bool vec)
+// The death draw is needed by the few agents whose infection ends today: kept out of line so that its 64-bit arithmetic does
+// not take registers away from the loads of the streaming loop.
+__device__ __noinline__ float seirms_death_draw(uint64_t seed, uint32_t t, int64_t id)
+{
+    return u_hi(at_noise_u64(seed, t, agent_key(id, STREAM_MORTALITY)));
+}
+
+__global__ void __launch_bounds__(IV_THREADS, 4) iv_seirms_kernel(const at_iv_seirms_args a, const bool vec)
 {
     const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
     const int64_t groups = (a.n + 3) >> 2;
     const float tf = (float)a.t;
     const float m = *a.m_value;
     int n_due = 0, n_died = 0, n_survived = 0;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    // Two groups (8 agents) per thread and iteration, all their loads issued first: with only two 16-byte loads per group a
+    // single group would leave too few bytes in flight per SM to cover the HBM latency.
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < groups; g0 += 2 * stride) {
+        F4 s2[2], nt2[2], ud2[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t i = (g0 + h * stride) << 2;            // past the end: load4 fills, nothing is stored
+            s2[h] = load4(a.stage_in, i, a.n, vec);
+            nt2[h] = load4(a.next_stage_time_in, i, a.n, vec, 3.0e38f);
+            prefetch4(a.stage_in, i + (stride << 3), a.n);                  // the same thread's group of the next iteration
+            prefetch4(a.next_stage_time_in, i + (stride << 3), a.n);
+            if (a.u_death) ud2[h] = load4(a.u_death, i, a.n, vec, 1.f);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+        const int64_t g = g0 + h * stride;
+        if (g < groups) {
         const int64_t i = g << 2;
-        const F4 s = load4(a.stage_in, i, a.n, vec);
-        const F4 nt = load4(a.next_stage_time_in, i, a.n, vec, 3.0e38f);
-        F4 ud;
-        if (a.u_death) ud = load4(a.u_death, i, a.n, vec, 1.f);
+        const F4 s = s2[h], nt = nt2[h], ud = ud2[h];
         F4 ns, nn;
         uint8_t codes[4];
 #pragma unroll
@@ -272,8 +319,7 @@ __global__ void __launch_bounds__(IV_THREADS) iv_seirms_kernel(const at_iv_seirm
                 x = 0.f;
                 c = 2;
             } else if (due && st == 2.f) {             // I: Bernoulli(M) death draw             (:66-70)
-                const float u = a.u_death ? ud.v[k]
-                                          : u_hi(at_noise_u64(seed, (uint32_t)a.t, agent_key(a.id_offset + i + k, STREAM_MORTALITY)));
+                const float u = a.u_death ? ud.v[k] : seirms_death_draw(seed, (uint32_t)a.t, a.id_offset + i + k);
                 const bool died = u < m;
                 ++n_due;
                 if (died) {                            // I5: the dead take the one-level path -> stage 3
@@ -302,6 +348,8 @@ __global__ void __launch_bounds__(IV_THREADS) iv_seirms_kernel(const at_iv_seirm
                 for (int k = 0; k < 4; ++k)
                     if (i + k < a.n) a.move_code[i + k] = codes[k];
             }
+        }
+        }
         }
     }
     // integer counts: order-independent, so the result is bitwise reproducible for any grid

@@ -11,8 +11,9 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __shfl_xor_sync(mask, value, offset) 0
 
 struct emu_dim { int x; };
