@@ -111,15 +111,6 @@ __device__ __forceinline__ void load4_u8(const uint8_t* __restrict__ p, int64_t 
     }
 }
 
-// The next iteration's lines are requested from HBM into L2 while this iteration's loads are still in flight: twice the
-// bytes in flight per SM without holding them in registers (a thread's 16 bytes; a warp covers four 128-byte lines).
-__device__ __forceinline__ void prefetch4(const void* base, int64_t i, int64_t n, int elem_bytes = 4)
-{
-#ifndef AT_IV_HOST_EMULATION
-    if (base != nullptr && i < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + i * elem_bytes));
-#endif
-}
-
 __device__ __forceinline__ bool differs(const F4& a, const F4& b)
 {
     return a.v[0] != b.v[0] || a.v[1] != b.v[1] || a.v[2] != b.v[2] || a.v[3] != b.v[3];
@@ -140,12 +131,6 @@ __global__ void __launch_bounds__(IV_THREADS, 5) iv_quarantine_kernel(const at_i
         const int64_t i = g << 2;
         // every load of the group is issued before anything is computed: one round of memory latency per group
         const F4 q = load4(a.is_q_in, i, a.n, vec);
-        {
-            const int64_t nx = (g + (int64_t)gridDim.x * blockDim.x) << 2;
-            prefetch4(a.is_q_in, nx, a.n);
-            if (apply) prefetch4(a.start_date_in, nx, a.n);
-            if (decide) prefetch4(a.stage, nx, a.n, a.stage_f64 ? 8 : 4);
-        }
         F4 d, sv, us, ub;
         if (apply) d = load4(a.start_date_in, i, a.n, vec);
         if (decide && !a.stage_f64) sv = load4(reinterpret_cast<const float*>(a.stage), i, a.n, vec);
@@ -218,15 +203,6 @@ __global__ void __launch_bounds__(IV_THREADS, 4) iv_testing_kernel(const at_iv_t
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = g << 2;
         F4 w, q, uc, aw, rd, re;
-        {
-            const int64_t nx = (g + (int64_t)gridDim.x * blockDim.x) << 2;
-            if (decide) prefetch4(a.is_q, nx, a.n);
-            if (apply) {
-                prefetch4(a.awaiting_in, nx, a.n);
-                prefetch4(a.result_date_in, nx, a.n);
-                prefetch4(a.re_eligible_in, nx, a.n);
-            }
-        }
         if (decide) q = load4(a.is_q, i, a.n, vec);
         if (decide && a.u_comply) uc = load4(a.u_comply, i, a.n, vec, 1.f);
         if (!decide) w = load4(a.accept_action, i, a.n, vec);
@@ -294,8 +270,6 @@ __global__ void __launch_bounds__(IV_THREADS, 4) iv_seirms_kernel(const at_iv_se
             const int64_t i = (g0 + h * stride) << 2;            // past the end: load4 fills, nothing is stored
             s2[h] = load4(a.stage_in, i, a.n, vec);
             nt2[h] = load4(a.next_stage_time_in, i, a.n, vec, 3.0e38f);
-            prefetch4(a.stage_in, i + (stride << 3), a.n);                  // the same thread's group of the next iteration
-            prefetch4(a.next_stage_time_in, i + (stride << 3), a.n);
             if (a.u_death) ud2[h] = load4(a.u_death, i, a.n, vec, 1.f);
         }
 #pragma unroll
