@@ -161,3 +161,33 @@ def test_seirms_kernel_matches_oracle_and_reference(emu, name, variant):
         assert np.array_equal(code == nat.MOVE_R_TO_S, (before == 3) & (s_out == 0))
     assert np.allclose(dd, g["ref_daily_deaths"], rtol=1e-6, atol=0)
     assert np.array_equal(dd, st.daily_deaths.numpy())
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 63, 1025])
+@pytest.mark.parametrize("off", [0, 1])
+def test_ragged_sizes_and_every_status_combination_against_the_oracle(emu, n, off):
+    """Tail groups (n not a multiple of 4), unaligned arrays, negative / fractional statuses, dates at and around t."""
+    from oracle.interventions_port import quarantine_step, testing_step as oracle_testing_step
+
+    rng = np.random.default_rng(1000 * n + off)
+    f = np.float32
+    g = {"seed": 77, "overrides": {"env": {"quarantine_start_prob": 0.6, "quarantine_break_prob": 0.35, "test_compliance_prob": 0.7},
+                                   "meta": {"quarantine_days": 2, "INFINITY_TIME": 130, "test_ineligible_days": 1,
+                                            "test_result_delay_days": 2}}}
+    stage = aligned(n, f, 0, off)
+    stage[:] = rng.choice([0, 1, 2, 3, 4, 0.5], size=n)
+    q, d = aligned(n, f, 0, off), aligned(n, f, 0, off)
+    q[:] = rng.choice([-2, -1, 0, 1, 0.5], size=n)
+    d[:] = rng.choice([0, 1, 2, 3, 130], size=n)
+    aw, rd, re = aligned(n, f, 0, off), aligned(n, f, 0, off), aligned(n, f, 0, off)
+    aw[:], rd[:], re[:] = rng.choice([0, 1, -1], size=n), rng.choice([3, 4, 5, 130], size=n), rng.choice([0, 3, 4, 5, 6], size=n)
+    ids = np.arange(n)
+    for t in (3, 4, 5):
+        us, ub = onoise.stream_uniforms(77, t, ids, onoise.STREAM_QUARANTINE)
+        uc = onoise.stream_uniforms(77, t, ids, onoise.STREAM_TESTING)[0]
+        eq, ed = quarantine_step(t, stage, q, d, us, ub, 0.6, 0.35, 2, 130)
+        ea, er, ee = oracle_testing_step(t, eq, aw, rd, re, uc, 0.7, 1, 2, 130)
+        emu.emu_quarantine(make_quarantine_args(g, t, nat.DECIDE | nat.APPLY, stage, q, d, q, d), int(off == 0), 2)
+        emu.emu_testing(make_testing_args(g, t, nat.DECIDE | nat.APPLY, q, aw, rd, re, aw, rd, re), int(off == 0), 3)
+        for got, want in ((q, eq), (d, ed), (aw, ea), (rd, er), (re, ee)):
+            assert np.array_equal(got, want), t
