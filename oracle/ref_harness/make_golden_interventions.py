@@ -22,7 +22,8 @@ ENV_DEFAULT = {"quarantine_start_prob": 0.7, "quarantine_break_prob": 0.1, "test
 SMALL = {"is_quarantined": np.int8, "awaiting_test_result": np.int8}
 
 
-def save_case(name, variant, age, stage0, edges, seed, mode, r2, m, meta=None, initial=None, env=None):
+def save_case(name, variant, age, stage0, edges, seed, mode, r2, m, meta=None, initial=None, env=None, keep_steps=None,
+              store_inputs=True):
     gI = np.linspace(0.5, 1.5, T).astype(np.float32)
     gD = np.linspace(2.0, 1.0, T).astype(np.float32)
     meta_all = dict(META_DEFAULT, **(meta or {}))
@@ -33,15 +34,20 @@ def save_case(name, variant, age, stage0, edges, seed, mode, r2, m, meta=None, i
         seed=np.int64(seed), mode=np.array(mode), p_isolate=np.float32(0.3), num_steps=np.int64(T), variant=np.array(variant),
         gI=gI, gD=gD, r2=np.asarray(r2, dtype=np.float32), m=np.asarray(m, dtype=np.float32),
         overrides=np.array(json.dumps({"meta": meta_all, "initial": initial or {}, "env": env_all})),
-        age=age.astype(np.uint8), stage0=stage0.astype(np.uint8), edges=edges.astype(np.int32),
         ref_daily_infected=out["daily_infected"].astype(np.float32), ref_daily_deaths=out["daily_deaths"].astype(np.float32),
         ref_grad_R2=out["grad_R2"].astype(np.float32), ref_grad_M=out["grad_M"].astype(np.float32), ref_loss=np.float64(out["loss"]),
     )
+    if store_inputs:
+        payload.update(age=age.astype(np.uint8), stage0=stage0.astype(np.uint8), edges=edges.astype(np.int32))
+    if keep_steps is not None:
+        payload["kept_steps"] = np.asarray(keep_steps, dtype=np.int64)
     keys = ["disease_stage", "next_stage_time"]
     if variant == "interventions":
         keys += ["is_quarantined", "quarantine_start_date", "awaiting_test_result", "test_result_date", "test_re_eligble_date"]
     for k in keys:
         h = out[k + "_history"]
+        if keep_steps is not None:
+            h = h[list(keep_steps)]
         dt = np.float32 if k == "disease_stage" else SMALL.get(k, np.int16)
         payload["ref_" + k + "_history"] = h.astype(dt)
         assert np.array_equal(payload["ref_" + k + "_history"].astype(np.float64), h), k
@@ -49,6 +55,18 @@ def save_case(name, variant, age, stage0, edges, seed, mode, r2, m, meta=None, i
     np.savez_compressed(path, **payload)
     print(name, "%.0f KB" % (os.path.getsize(path) / 1024), "deaths", out["daily_deaths"][:8], "grad_R2", out["grad_R2"].reshape(-1),
           "grad_M", out["grad_M"], {k: (float(out[k + "_history"].min()), float(out[k + "_history"].max())) for k in keys})
+
+
+def astoria():
+    """The bundled astoria population (inputs: tests/golden/astoria_inputs.npz): states kept at steps 0, 10 and 20."""
+    from oracle.ref_harness.run_reference import load_bundled_population
+
+    age, stage0, edges = load_bundled_population("astoria")
+    r2 = np.full((3, 1), 4.75, dtype=np.float32)
+    save_case("interventions_astoria", "interventions", age, stage0, edges, seed=57, mode="hard", r2=r2, m=np.array([0.12], dtype=np.float32),
+              meta={"quarantine_days": 5}, initial={"test_re_eligble_date": 0}, keep_steps=(0, 10, 20), store_inputs=False)
+    save_case("seirms_astoria", "seirms", age, stage0, edges, seed=58, mode="hard", r2=r2, m=np.array([0.4], dtype=np.float32),
+              keep_steps=(0, 10, 20), store_inputs=False)
 
 
 def main():
@@ -70,6 +88,7 @@ def main():
               m=np.array([0.6], dtype=np.float32))
     a, s, e = synthetic_population(64, 4.0, seed=9, frac_e=0.2, frac_i=0.3)
     save_case("seirms_64_hard", "seirms", a, s, e, seed=56, mode="hard", r2=r2, m=np.array([0.5], dtype=np.float32))
+    astoria()
 
 
 if __name__ == "__main__":
