@@ -133,13 +133,13 @@ def test_edge_cases_empty_graph_and_no_infection():
     assert dd[5] == pytest.approx(1.5) and dd[8] == pytest.approx(2.5) and dd.sum() == pytest.approx(4.0)
 
 
-def test_invariants_at_one_million_agents():
+@pytest.mark.parametrize("n", [1_000_000, 8_400_000])       # BASELINE configs[1] and configs[2] sizes (d = 20)
+def test_invariants_at_baseline_sizes(n):
     """size-independent properties where the oracle is too slow: conservation, monotone stages, series = stage counts"""
     from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
     from agenttorch_b200.graph import mean_interactions_from_age, synthetic_contact_graph, synthetic_population
 
     dev = torch.device("cuda:0")
-    n = 1_000_000
     age, stage0 = synthetic_population(n, 1, device=dev)
     graph = synthetic_contact_graph(n, 20.0, 2, device=dev, mean_interactions=mean_interactions_from_age(age))
     eng = SeirmEngine(graph, SeirmSpec(num_steps=T))
