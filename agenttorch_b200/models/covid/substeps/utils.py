@@ -75,22 +75,33 @@ def _edge_cache_path(path):
     return os.path.join(root, f"edges_{key}.npy")
 
 
+def _parse_edge_list(path):
+    """(2, E) int64 edge_index of an edge-list CSV.  Native parser (libat_io.so, include/at_io.h: memory-mapped, one thread
+    per core, same row semantics) when it has been built, else the reference's pandas sequence."""
+    from agenttorch_b200 import _native_io
+
+    if _native_io.available():
+        return _native_io.read_edge_list(path)[0]
+    df = pd.read_csv(path, header=None)
+    if df.iloc[0].apply(lambda v: isinstance(v, str)).any():
+        df = pd.read_csv(path, header=0)
+    df = df.iloc[:, :2].apply(pd.to_numeric, errors="coerce").dropna().astype("int64")
+    return torch.tensor(df.values.T, dtype=torch.long).contiguous()
+
+
 def network_from_file(params):
     """Edge-list CSV -> (None, (edge_index (2,E) int64, edge_attr (2,E) float32 = [type==1; weight==1])).
-    (reference utils.py:129-148).  Parsing 168 M text edges takes minutes; with AGENTTORCH_B200_CACHE_DIR set the parsed
-    (E,2) int32 array is kept as .npy and memory-mapped on the next run."""
+    (reference utils.py:129-148).  pandas needs minutes for 168 M text edges; the native parser reads them at several
+    hundred MB/s, and with AGENTTORCH_B200_CACHE_DIR set the parsed (E,2) int32 array is also kept as .npy and
+    memory-mapped on the next run."""
     path = params["file_path"]
     cache = _edge_cache_path(path)
     if cache is not None and os.path.exists(cache):
         pairs = np.load(cache, mmap_mode="r")
         edge_index = torch.from_numpy(np.array(pairs.T, dtype=np.int64, order="C"))
     else:
-        df = pd.read_csv(path, header=None)
-        if df.iloc[0].apply(lambda v: isinstance(v, str)).any():
-            df = pd.read_csv(path, header=0)
-        df = df.iloc[:, :2].apply(pd.to_numeric, errors="coerce").dropna().astype("int64")
-        edge_index = torch.tensor(df.values.T, dtype=torch.long).contiguous()
-        if cache is not None and edge_index.numel() and int(edge_index.max()) < 2**31:
+        edge_index = _parse_edge_list(path)
+        if cache is not None and edge_index.numel() and int(edge_index.max()) < 2**31 and int(edge_index.min()) >= -2**31:
             os.makedirs(os.path.dirname(cache), exist_ok=True)
             tmp = cache + f".{os.getpid()}.tmp.npy"
             np.save(tmp, edge_index.t().to(torch.int32).numpy())
