@@ -260,8 +260,9 @@ __global__ void __launch_bounds__(IV_THREADS, 4) iv_seirms_kernel(const at_iv_se
     const float tf = (float)a.t;
     const float m = *a.m_value;
     int n_due = 0, n_died = 0, n_survived = 0;
-    // Two groups (8 agents) per thread and iteration, all their loads issued first: with only two 16-byte loads per group a
-    // single group would leave too few bytes in flight per SM to cover the HBM latency.
+    // Two groups (8 agents) per thread and iteration, all their loads issued before the arithmetic (64 bytes in flight per
+    // thread).  Measured: 81 us per launch at 33.5 M agents against 76 us with one group — the pass is bound by instruction
+    // issue, not by latency (profiles/r01_interventions_kernels.md).
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < groups; g0 += 2 * stride) {
         F4 s2[2], nt2[2], ud2[2];
@@ -274,56 +275,56 @@ __global__ void __launch_bounds__(IV_THREADS, 4) iv_seirms_kernel(const at_iv_se
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-        const int64_t g = g0 + h * stride;
-        if (g < groups) {
-        const int64_t i = g << 2;
-        const F4 s = s2[h], nt = nt2[h], ud = ud2[h];
-        F4 ns, nn;
-        uint8_t codes[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const bool due = nt.v[k] <= tf;
-            const float st = s.v[k];
-            float x = st, y = nt.v[k];
-            uint8_t c = 0;
-            if (due && st == 1.f) {                    // E -> I: stage + (stage/E)*1            (transition.py:87-91,103)
-                x = 2.f;
-                c = 1;
-            } else if (due && st == 3.f) {             // R -> S: stage + (stage/R)*(-R)         (:92-96,106)
-                x = 0.f;
-                c = 2;
-            } else if (due && st == 2.f) {             // I: Bernoulli(M) death draw             (:66-70)
-                const float u = a.u_death ? ud.v[k] : seirms_death_draw(seed, (uint32_t)a.t, a.id_offset + i + k);
-                const bool died = u < m;
-                ++n_due;
-                if (died) {                            // I5: the dead take the one-level path -> stage 3
-                    x = 3.f;
-                    c = 4;
-                    ++n_died;
-                } else {                               //     the survivors the two-level path -> stage 4
-                    x = 4.f;
-                    c = 3;
-                    ++n_survived;
+            const int64_t g = g0 + h * stride;
+            if (g < groups) {
+                const int64_t i = g << 2;
+                const F4 s = s2[h], nt = nt2[h], ud = ud2[h];
+                F4 ns, nn;
+                uint8_t codes[4];
+        #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool due = nt.v[k] <= tf;
+                    const float st = s.v[k];
+                    float x = st, y = nt.v[k];
+                    uint8_t c = 0;
+                    if (due && st == 1.f) {                    // E -> I: stage + (stage/E)*1            (transition.py:87-91,103)
+                        x = 2.f;
+                        c = 1;
+                    } else if (due && st == 3.f) {             // R -> S: stage + (stage/R)*(-R)         (:92-96,106)
+                        x = 0.f;
+                        c = 2;
+                    } else if (due && st == 2.f) {             // I: Bernoulli(M) death draw             (:66-70)
+                        const float u = a.u_death ? ud.v[k] : seirms_death_draw(seed, (uint32_t)a.t, a.id_offset + i + k);
+                        const bool died = u < m;
+                        ++n_due;
+                        if (died) {                            // I5: the dead take the one-level path -> stage 3
+                            x = 3.f;
+                            c = 4;
+                            ++n_died;
+                        } else {                               //     the survivors the two-level path -> stage 4
+                            x = 4.f;
+                            c = 3;
+                            ++n_survived;
+                        }
+                    }
+                    if (st == 1.f && nt.v[k] == tf) y = tf + a.infected_to_recovered_time;      // :131-133; others: see the epilogue (I6)
+                    ns.v[k] = x;
+                    nn.v[k] = y;
+                    codes[k] = c;
+                }
+                if (a.stage_out != a.stage_in || differs(ns, s)) store4(a.stage_out, i, a.n, vec, ns);
+                if (a.next_stage_time_out != a.next_stage_time_in || differs(nn, nt)) store4(a.next_stage_time_out, i, a.n, vec, nn);
+                if (a.move_code) {
+                    if (i + 3 < a.n && (reinterpret_cast<uintptr_t>(a.move_code + i) & 3u) == 0) {
+                        *reinterpret_cast<uint32_t*>(a.move_code + i) =
+                            (uint32_t)codes[0] | ((uint32_t)codes[1] << 8) | ((uint32_t)codes[2] << 16) | ((uint32_t)codes[3] << 24);
+                    } else {
+        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (i + k < a.n) a.move_code[i + k] = codes[k];
+                    }
                 }
             }
-            if (st == 1.f && nt.v[k] == tf) y = tf + a.infected_to_recovered_time;      // :131-133; others: see the epilogue (I6)
-            ns.v[k] = x;
-            nn.v[k] = y;
-            codes[k] = c;
-        }
-        if (a.stage_out != a.stage_in || differs(ns, s)) store4(a.stage_out, i, a.n, vec, ns);
-        if (a.next_stage_time_out != a.next_stage_time_in || differs(nn, nt)) store4(a.next_stage_time_out, i, a.n, vec, nn);
-        if (a.move_code) {
-            if (i + 3 < a.n && (reinterpret_cast<uintptr_t>(a.move_code + i) & 3u) == 0) {
-                *reinterpret_cast<uint32_t*>(a.move_code + i) =
-                    (uint32_t)codes[0] | ((uint32_t)codes[1] << 8) | ((uint32_t)codes[2] << 16) | ((uint32_t)codes[3] << 24);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (i + k < a.n) a.move_code[i + k] = codes[k];
-            }
-        }
-        }
         }
     }
     // integer counts: order-independent, so the result is bitwise reproducible for any grid
