@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(IV_THREADS, 4) iv_seirms_kernel(const at_iv_se
                 const F4 s = s2[h], nt = nt2[h], ud = ud2[h];
                 F4 ns, nn;
                 uint8_t codes[4];
-        #pragma unroll
+#pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const bool due = nt.v[k] <= tf;
                     const float st = s.v[k];
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(IV_THREADS, 4) iv_seirms_kernel(const at_iv_se
                         *reinterpret_cast<uint32_t*>(a.move_code + i) =
                             (uint32_t)codes[0] | ((uint32_t)codes[1] << 8) | ((uint32_t)codes[2] << 16) | ((uint32_t)codes[3] << 24);
                     } else {
-        #pragma unroll
+#pragma unroll
                         for (int k = 0; k < 4; ++k)
                             if (i + k < a.n) a.move_code[i + k] = codes[k];
                     }
