@@ -119,10 +119,38 @@ static void* run_chunk(void* arg)
     const char* p = c->begin;
     int64_t n = 0, mx = -1;
     int text = 0;
-    while (p < c->end) {
-        const char* nl = (const char*)memchr(p, '\n', (size_t)(c->end - p));
-        const char* e = nl ? nl : c->end;
+    const char* const end = c->end;
+    while (p < end) {
         int64_t s, d;
+        /* fast path for the common row "digits,digits\n": one scan, no calls */
+        {
+            const char* q = p;
+            int64_t a = 0, b = 0;
+            while (q < end && (unsigned)(*q - '0') < 10u) a = a * 10 + (*q++ - '0');
+            if (q > p && q - p <= 18 && q < end && *q == ',') {
+                const char* f = ++q;
+                while (q < end && (unsigned)(*q - '0') < 10u) b = b * 10 + (*q++ - '0');
+                if (q > f && q - f <= 18) {
+                    const char* next = NULL;
+                    if (q == end) next = end;
+                    else if (*q == '\n') next = q + 1;
+                    else if (*q == '\r' && q + 1 < end && q[1] == '\n') next = q + 2;
+                    if (next) {
+                        if (c->src) {
+                            c->src[c->offset + n] = a;
+                            c->dst[c->offset + n] = b;
+                            if (a > mx) mx = a;
+                            if (b > mx) mx = b;
+                        }
+                        ++n;
+                        p = next;
+                        continue;
+                    }
+                }
+            }
+        }
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* e = nl ? nl : end;
         if (parse_row(p, e, &s, &d, &text) == 1) {
             if (c->src) {
                 c->src[c->offset + n] = s;
