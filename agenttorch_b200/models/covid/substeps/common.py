@@ -26,7 +26,8 @@ class EpisodeNoise:
 
 
 class ScalarCache:
-    """float() of a one-element device tensor costs a device sync: read it once per (storage, version)."""
+    """float() of a one-element device tensor costs a device sync: read it once per (tensor object, version).  The tensor is
+    kept referenced so that its storage address cannot be reused by another tensor while the entry is alive."""
 
     def __init__(self):
         self._seen = {}
@@ -34,12 +35,11 @@ class ScalarCache:
     def __call__(self, name, tensor):
         if not torch.is_tensor(tensor):
             return float(tensor)
-        key = (tensor.data_ptr(), tensor._version)
         hit = self._seen.get(name)
-        if hit is None or hit[0] != key:
-            hit = (key, float(tensor.detach().reshape(-1)[0]))
+        if hit is None or hit[0] is not tensor or hit[1] != tensor._version:
+            hit = (tensor, tensor._version, float(tensor.detach().reshape(-1)[0]))
             self._seen[name] = hit
-        return hit[1]
+        return hit[2]
 
 
 def state_var(state, input_variables, name):

@@ -145,3 +145,24 @@ def test_seirms_backward_formula_equals_autograd_of_the_oracle(seed):
     expect[code == nat.MOVE_E_TO_I], expect[code == nat.MOVE_R_TO_S] = 2, 0
     expect[code == nat.MOVE_SURVIVED], expect[code == nat.MOVE_DIED] = 4, 3
     assert np.array_equal(out.stage.detach().numpy(), expect)
+
+
+def test_scalar_cache_follows_replacement_and_in_place_edits():
+    from agenttorch_b200.models.covid.substeps.common import EpisodeNoise, ScalarCache
+
+    cache = ScalarCache()
+    p = torch.tensor([0.25])
+    assert cache("p", p) == 0.25 and cache("p", p) == 0.25
+    p.fill_(0.5)                                   # in-place edit bumps the version
+    assert cache("p", p) == 0.5
+    assert cache("p", torch.tensor([0.75])) == 0.75 and cache("p", 0.1) == 0.1
+
+    class N(EpisodeNoise):
+        pass
+
+    n = N()
+    n.init_noise({"noise_seed": 5})
+    s1 = n.episode_seed(0)
+    assert n.episode_seed(3) == s1 and n.episode_seed(0) != s1          # one stream per episode
+    n.advance_seed = False
+    assert n.episode_seed(0) == 5 and -(1 << 63) <= s1 < (1 << 63)
