@@ -7,6 +7,8 @@ import torch
 import yaml
 from torch import nn
 
+from .soft import *  # noqa: F401,F403  (the reference's core.helpers re-exports soft.py and initializer.py the same way)
+
 
 def _walk(root, keys):
     node = root
