@@ -252,3 +252,28 @@ def test_models_sharing_helper_names_do_not_break_each_other(tmp_path):
     pp_runner = predator_prey.get_runner(predator_prey.synthetic.synthetic_config(8, 8, 5, 9, device="cpu"))
     pp_runner.init()
     assert Registry.helpers["initialization"]["read_from_file"] is not utils.read_from_file
+
+
+def test_core_exports_match_the_reference_package():
+    """agent_torch/core/__init__.py:1-13: Registry, Runner, Controller, Initializer, VectorizedRunner, vectorized,
+    DistributedRunner, launch_distributed_simulation, __version__, distributions, soft helpers."""
+    from agenttorch_b200 import core
+    from agenttorch_b200.core.vectorization import is_vectorized
+    from agenttorch_b200.models import covid
+    from agenttorch_b200.models.covid.synthetic import synthetic_config
+
+    for name in ("Registry", "Runner", "Controller", "Initializer", "VectorizedRunner", "vectorized", "DistributedRunner",
+                 "launch_distributed_simulation", "__version__", "distributions", "compare", "logical_and", "discrete_sample"):
+        assert hasattr(core, name), name
+
+    @core.vectorized(in_dims=(0, None))
+    def f(x, y):
+        return x + y
+
+    assert is_vectorized(f) and f._vmap_in_dims == (0, None) and f(1, 2) == 3 and not is_vectorized(len)
+
+    runner = core.VectorizedRunner(synthetic_config(128, 4.0, device="cpu"), covid.get_registry())
+    runner.init()
+    assert runner.is_vectorized and isinstance(runner, core.Runner)
+    assert runner.vectorized_functions["transition"] == {"0/new_transmission": True, "1/seirm_progression": True}
+    assert runner.vectorized_functions["policy"] == {"0/citizens/make_isolation_decision": True}
