@@ -28,8 +28,8 @@ def arg(name, value, shape=(1,), learnable=False, dtype=None):
     return d
 
 
-stage_file = {"file_path": arg("Disease Stage File", "${simulation_metadata.disease_stage_file}")}
-age_file = {"file_path": arg("Filepath for age group stage", "${simulation_metadata.age_group_file}")}
+stage_file = {"file_path": arg("CSV with one initial disease stage per agent", "${simulation_metadata.disease_stage_file}")}
+age_file = {"file_path": arg("pickle with one age-group index per agent", "${simulation_metadata.age_group_file}")}
 cfg = {
     "simulation_metadata": {
         "EXECUTION_MODE": "heuristic", "EXPOSED_TO_INFECTED_TIME": 5, "EXPOSED_VAR": 1, "INFECTED_TO_RECOVERED_TIME": 5,
@@ -47,44 +47,44 @@ cfg = {
     },
     "state": {
         "agents": {"citizens": {"number": N, "properties": {
-            "age": prop("Age", [N, 1], "int", gen="load_population_attribute",
-                        args={"attribute": arg("Age", "age", shape=None), **age_file}),
-            "disease_stage": prop("Disease Stage", [N, 1], "int", gen="read_from_file", args=stage_file),
-            "id": prop("id", [N, 1], "float", gen="initialize_id",
-                       args={"pop_size": arg("population size", "${simulation_metadata.num_agents}")}),
-            "infected_time": prop("Last Infected timestep", [N, 1], "int", gen="get_infected_time",
-                                  args={**stage_file, "num_steps": arg("Num steps per episode", T)}),
-            "next_stage_time": prop("Timestep for next transition", [N, 1], "int", gen="get_next_stage_time",
-                                    args={**stage_file, "num_steps": arg("Num steps per episode", T)}),
+            "age": prop("age-group index 0..5", [N, 1], "int", gen="load_population_attribute",
+                        args={"attribute": arg("attribute to load", "age", shape=None), **age_file}),
+            "disease_stage": prop("S=0 E=1 I=2 R=3 (M=4)", [N, 1], "int", gen="read_from_file", args=stage_file),
+            "id": prop("agent number", [N, 1], "float", gen="initialize_id",
+                       args={"pop_size": arg("agents in the population", "${simulation_metadata.num_agents}")}),
+            "infected_time": prop("step of the last exposure (500 = never)", [N, 1], "int", gen="get_infected_time",
+                                  args={**stage_file, "num_steps": arg("steps in an episode", T)}),
+            "next_stage_time": prop("step of the next stage change (500 = none pending)", [N, 1], "int", gen="get_next_stage_time",
+                                    args={**stage_file, "num_steps": arg("steps in an episode", T)}),
             # state of the quarantine / testing substeps (reference config.yaml:79-87,145-203; float32 after `value * ones`)
-            "awaiting_test_result": prop("agent is awaiting test result currently", [N, 1], "bool", value=False),
-            "is_quarantined": prop("Quarantine status for a citizen", [N, 1], "bool", value=False),
-            "quarantine_start_date": prop("Start date for last quarantine of agent", [N, 1], "int",
+            "awaiting_test_result": prop("1 while a test result is pending", [N, 1], "bool", value=False),
+            "is_quarantined": prop("quarantine counter (1 = in quarantine)", [N, 1], "bool", value=False),
+            "quarantine_start_date": prop("step at which the current quarantine began", [N, 1], "int",
                                           value="${simulation_metadata.INFINITY_TIME}"),
-            "test_re_eligble_date": prop("Date when agent becomes eligible for taking a test again", [N, 1], "int",
+            "test_re_eligble_date": prop("first step at which the agent may test again", [N, 1], "int",
                                          value="${simulation_metadata.INFINITY_TIME}"),
-            "test_result_date": prop("Date when agent receives test result", [N, 1], "int",
+            "test_result_date": prop("step at which the pending result arrives", [N, 1], "int",
                                      value="${simulation_metadata.INFINITY_TIME}"),
         }}},
         "environment": {
-            "SFInfector": prop("Infectiousness of Infector", [5], "float", value=[0.0, 0.33, 0.72, 0.0, 0.0]),
-            "SFSusceptibility": prop("Susceptibility by Age Group", [9], "float",
+            "SFInfector": prop("infectiousness factor by disease stage of the source", [5], "float", value=[0.0, 0.33, 0.72, 0.0, 0.0]),
+            "SFSusceptibility": prop("susceptibility factor by age group of the target", [9], "float",
                                      value=[0.35, 0.69, 1.03, 1.03, 1.03, 1.03, 1.27, 1.52, 1.52]),
-            "daily_deaths": prop("daily_deaths", [T], "float", value=0),
-            "daily_infected": prop("daily_infected", [T], "float", value=0),
-            "exposed_to_infected_time": prop("Time from Exposed to Infected", [1], "float", value=3),
-            "infected_to_recovered_time": prop("Infected to Recovered time", [1], "float", value=5),
-            "lam_gamma_integrals": prop("Lam Gamma Integrals", [10], "float", gen="get_lam_gamma_integrals", args={
-                "rate": arg("Lam Gamma Rate", 2.4, dtype="float"), "scale": arg("Lam Gamma Scale", 5.5, dtype="float"),
-                "t": arg("Num Steps", T, dtype="int")}),
-            "mean_interactions": prop("Mean agent interactions across networks", [N, 1], "int",
+            "daily_deaths": prop("deaths per step", [T], "float", value=0),
+            "daily_infected": prop("new exposures per step", [T], "float", value=0),
+            "exposed_to_infected_time": prop("E to I delay (unused by the substeps)", [1], "float", value=3),
+            "infected_to_recovered_time": prop("I to R delay (unused by the substeps)", [1], "float", value=5),
+            "lam_gamma_integrals": prop("infectiousness by days since exposure (gamma CDF differences)", [10], "float", gen="get_lam_gamma_integrals", args={
+                "rate": arg("gamma rate", 2.4, dtype="float"), "scale": arg("gamma scale", 5.5, dtype="float"),
+                "t": arg("number of days", T, dtype="int")}),
+            "mean_interactions": prop("mean daily contacts by age group", [N, 1], "int",
                                       gen="get_mean_agent_interactions", args=age_file),
-            "mortality_rate": prop("Mortality Rate", [1], "float", value=0.2),
-            "quarantine_break_prob": prop("Probability of breaking a quarantine mandate prior to recovery", [1], "float", value=0.1),
-            "quarantine_start_prob": prop("Probability of complying to a quarantine mandate", [1], "float", value=0.7),
-            "test_compliance_prob": prop("Probability of complying to test recommendation", [1], "float", value=0.95),
-            "test_false_positive_prob": prop("Probability of false positive test result", [1], "float", value=0.3),
-            "test_true_positive_prob": prop("Probability of true positive test result", [1], "float", value=0.8),
+            "mortality_rate": prop("unused legacy mortality", [1], "float", value=0.2),
+            "quarantine_break_prob": prop("P(break) per step while quarantined", [1], "float", value=0.1),
+            "quarantine_start_prob": prop("P(start) per step while exposed or infected", [1], "float", value=0.7),
+            "test_compliance_prob": prop("P(accept a test) per step", [1], "float", value=0.95),
+            "test_false_positive_prob": prop("P(positive | healthy)", [1], "float", value=0.3),
+            "test_true_positive_prob": prop("P(positive | exposed or infected)", [1], "float", value=0.8),
         },
         "network": {"agent_agent": {"infection_network": {
             "type": "network_from_file", "arguments": {"file_path": "${simulation_metadata.infection_network_file}"}}}},
@@ -92,7 +92,7 @@ cfg = {
     },
     "substeps": {
         "0": {
-            "name": "Transmission", "description": "Transmission of new infections", "active_agents": ["citizens"],
+            "name": "Transmission", "description": "contact-graph exposure of susceptible agents", "active_agents": ["citizens"],
             "observation": {"citizens": None},
             "policy": {"citizens": {"make_isolation_decision": {
                 "generator": "MakeIsolationDecision", "arguments": None,
@@ -115,11 +115,11 @@ cfg = {
                 "output_variables": ["disease_stage", "next_stage_time", "infected_time", "daily_infected"]}},
         },
         "1": {
-            "name": "Disease Progression", "description": "Evolution of previously infected agents",
+            "name": "Disease Progression", "description": "E to I to R on the stage timers, daily deaths",
             "active_agents": ["citizens"], "observation": {"citizens": None}, "policy": {"citizens": None}, "reward": None,
             "transition": {"seirm_progression": {
                 "generator": "SEIRMProgression",
-                "arguments": {"M": {"name": "Mortality Rate", "dtype": "float", "shape": [1], "learnable": True,
+                "arguments": {"M": {"name": "mortality M", "dtype": "float", "shape": [1], "learnable": True,
                                     "initialization_function": None, "value": 0.12}},
                 "input_variables": {
                     "daily_deaths": "environment/daily_deaths", "disease_stage": "agents/citizens/disease_stage",
@@ -133,5 +133,5 @@ cfg = {
 out = os.path.join(ROOT, "agenttorch_b200", "models", "covid", "yamls", "config.yaml")
 with open(out, "w") as f:
     f.write("# SEIRM covid model — same schema as the reference's models/covid/yamls/config.yaml; generated by tools/gen_covid_config.py\n")
-    yaml.safe_dump(cfg, f, sort_keys=True, default_flow_style=False)
+    yaml.safe_dump(cfg, f, sort_keys=False, default_flow_style=None, width=118)
 print("wrote", out)
