@@ -171,6 +171,36 @@ def grid_network(params):
     return None, GridLattice(params["shape"])
 
 
+def _nx_network(graph):
+    """networkx graph -> (graph, (edge_index (2,E) int64, edge_attr (E,1) ones)): the payload of the reference's random-graph
+    helpers (core/helpers/environment.py:12-41), each edge listed once in networkx's order."""
+    edges = list(graph.edges())
+    edge_index = torch.tensor(edges, dtype=torch.long).reshape(-1, 2).t().contiguous()
+    return graph, (edge_index, torch.ones(edge_index.shape[1], 1))
+
+
+def small_world(params):
+    """Watts-Strogatz graph: n (or num_agents, default 1000), k = 10 neighbours, rewiring probability p = 0.1."""
+    import networkx as nx
+
+    return _nx_network(nx.watts_strogatz_graph(params.get("n", params.get("num_agents", 1000)), params.get("k", 10),
+                                               params.get("p", 0.1)))
+
+
+def erdos_renyi(params):
+    """G(n, p) graph: n (or num_agents, default 1000), p = 0.05."""
+    import networkx as nx
+
+    return _nx_network(nx.erdos_renyi_graph(params.get("n", params.get("num_agents", 1000)), params.get("p", 0.05)))
+
+
+def scale_free(params):
+    """Barabasi-Albert graph: n (or num_agents, default 1000), m = 3 edges per new node."""
+    import networkx as nx
+
+    return _nx_network(nx.barabasi_albert_graph(params.get("n", params.get("num_agents", 1000)), params.get("m", 3)))
+
+
 def memory_checkpoint(name):
     allocated, reserved = torch.cuda.memory_allocated(), torch.cuda.memory_reserved()
     print("Checkpoint: ", name, " Allocated: ", allocated, " Reserved: ", reserved)

@@ -57,3 +57,15 @@ def test_reexports_and_initialisation_helpers():
     assert z.dtype == torch.int32 and z.shape == (2, 3) and h.zeros([1], {"dtype": "float"}).dtype == torch.float32
     assert h.constant([2, 1], {"value": 2.5}).tolist() == [[2.5], [2.5]]
     assert h.random_normal([4], {"mu": 1.5, "sigma": 0.0}).tolist() == [1.5] * 4
+
+
+def test_random_graph_helpers_return_the_reference_payload():
+    import random
+
+    for fn, params, edges in ((h.small_world, {"n": 30, "k": 4, "p": 0.0}, 60), (h.scale_free, {"num_agents": 20, "m": 2}, None),
+                              (h.erdos_renyi, {"n": 12, "p": 1.0}, 66)):
+        random.seed(0)
+        graph, (edge_index, edge_attr) = fn(params)
+        assert edge_index.dtype == torch.int64 and edge_index.shape[0] == 2 and edge_attr.shape == (edge_index.shape[1], 1)
+        assert graph.number_of_edges() == edge_index.shape[1] and (edges is None or edge_index.shape[1] == edges)
+        assert bool((edge_attr == 1).all())
