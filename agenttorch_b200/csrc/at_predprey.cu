@@ -17,7 +17,10 @@
 //                     (float32-rounded increment, as the reference's float32 mask does, eat.py:72,99), GROW, and
 //                     clearing of the finished step's occupancy bits.
 
+#ifndef AT_HOST_EMULATION           // tests/host_emulation/ compiles this file for the CPU: a shim stands in for the runtime
 #include <cuda_runtime.h>
+#define AT_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
 #include <stdint.h>
 #include <stdio.h>
 
@@ -429,7 +432,7 @@ int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* strea
     if ((a.nbr_ptr == nullptr) != (a.nbr_idx == nullptr)) return fail("at_pp_step: %s", "nbr_ptr and nbr_idx go together");
 
     if ((flags & AT_PP_OCCUPANCY) && n > 0) {
-        pp_occupancy_kernel<<<blocks_for(n, a.grid), PP_THREADS, 0, s>>>(m, a, make_fastdiv((uint32_t)m.width));
+        AT_LAUNCH(pp_occupancy_kernel, blocks_for(n, a.grid), PP_THREADS, s, m, a, make_fastdiv((uint32_t)m.width));
         if (check("pp_occupancy_kernel launch")) return 1;
     }
     if (agent_flags && n > 0) {
@@ -438,13 +441,13 @@ int at_pp_step(const at_pp_model* model, const at_pp_launch* launch, void* strea
         const int vec_pred = aligned(a.pred_cell) && aligned(a.pred_energy) && aligned(a.pred_id);
         const int vec_prey = aligned(a.prey_cell) && aligned(a.prey_energy) && aligned(a.prey_id);
         const int64_t longest = a.n_pred > a.n_prey ? a.n_pred : a.n_prey;
-        pp_agent_kernel<<<blocks_for((longest + 3) / 4 + 3, a.grid), PP_THREADS, 0, s>>>(m, a, make_fastdiv((uint32_t)m.width), vec_pred, vec_prey);
+        AT_LAUNCH(pp_agent_kernel, blocks_for((longest + 3) / 4 + 3, a.grid), PP_THREADS, s, m, a, make_fastdiv((uint32_t)m.width), vec_pred, vec_prey);
         if (check("pp_agent_kernel launch")) return 1;
     }
     if (cell_flags) {
         const int64_t threads = ((m.n_storage ? m.n_storage : m.n_cells) + 3) >> 2;
-        if (a.countdown_f64) pp_cell_kernel<double><<<blocks_for(threads, a.grid), PP_THREADS, 0, s>>>(m, a);
-        else pp_cell_kernel<float><<<blocks_for(threads, a.grid), PP_THREADS, 0, s>>>(m, a);
+        if (a.countdown_f64) AT_LAUNCH(pp_cell_kernel<double>, blocks_for(threads, a.grid), PP_THREADS, s, m, a);
+        else AT_LAUNCH(pp_cell_kernel<float>, blocks_for(threads, a.grid), PP_THREADS, s, m, a);
         if (check("pp_cell_kernel launch")) return 1;
     }
     return 0;
@@ -454,7 +457,7 @@ int at_pp_pack_cells(const int64_t* coords, int64_t n, int32_t max_y, int64_t n_
 {
     if (n <= 0) return 0;
     if (!coords || !cells || max_y <= 0) return fail("at_pp_pack_cells: %s", "bad arguments");
-    pp_pack_cells_kernel<<<blocks_for(n, 0), PP_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(coords, n, max_y, n_cells, cells, error_flag);
+    AT_LAUNCH(pp_pack_cells_kernel, blocks_for(n, 0), PP_THREADS, reinterpret_cast<cudaStream_t>(stream), coords, n, max_y, n_cells, cells, error_flag);
     return check("pp_pack_cells_kernel launch");
 }
 
@@ -462,7 +465,7 @@ int at_pp_unpack_cells(const int32_t* cells, int64_t n, int32_t max_y, int64_t* 
 {
     if (n <= 0) return 0;
     if (!coords || !cells || max_y <= 0) return fail("at_pp_unpack_cells: %s", "bad arguments");
-    pp_unpack_cells_kernel<<<blocks_for(n, 0), PP_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(cells, n, max_y, coords);
+    AT_LAUNCH(pp_unpack_cells_kernel, blocks_for(n, 0), PP_THREADS, reinterpret_cast<cudaStream_t>(stream), cells, n, max_y, coords);
     return check("pp_unpack_cells_kernel launch");
 }
 
@@ -470,14 +473,14 @@ int at_pp_pack_stage(const void* stage, int32_t stage_dtype, int64_t n_cells, ui
 {
     if (n_cells <= 0 || !stage || !info || (stage_dtype != 0 && stage_dtype != 1)) return fail("at_pp_pack_stage: %s", "bad arguments");
     const int64_t n_bytes = at_pp_info_bytes(n_cells);
-    pp_pack_stage_kernel<<<blocks_for(n_bytes, 0), PP_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(stage, stage_dtype, n_cells, n_bytes, info);
+    AT_LAUNCH(pp_pack_stage_kernel, blocks_for(n_bytes, 0), PP_THREADS, reinterpret_cast<cudaStream_t>(stream), stage, stage_dtype, n_cells, n_bytes, info);
     return check("pp_pack_stage_kernel launch");
 }
 
 int at_pp_unpack_stage(const uint8_t* info, int64_t n_cells, void* stage, int32_t stage_dtype, void* stream)
 {
     if (n_cells <= 0 || !stage || !info || (stage_dtype != 0 && stage_dtype != 1)) return fail("at_pp_unpack_stage: %s", "bad arguments");
-    pp_unpack_stage_kernel<<<blocks_for(n_cells, 0), PP_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(info, n_cells, stage, stage_dtype);
+    AT_LAUNCH(pp_unpack_stage_kernel, blocks_for(n_cells, 0), PP_THREADS, reinterpret_cast<cudaStream_t>(stream), info, n_cells, stage, stage_dtype);
     return check("pp_unpack_stage_kernel launch");
 }
 
@@ -489,7 +492,7 @@ int at_pp_census(const at_pp_launch* launch, int64_t n_cells, int64_t* out3, voi
     if (e != cudaSuccess) return fail("cudaMemsetAsync: %s", cudaGetErrorString(e));
     const int64_t n = launch->n_pred + launch->n_prey;
     const int64_t work = n > ((n_cells + 3) >> 2) ? n : ((n_cells + 3) >> 2);
-    pp_census_kernel<<<blocks_for(work, 0), PP_THREADS, 0, s>>>(*launch, n_cells, reinterpret_cast<unsigned long long*>(out3));
+    AT_LAUNCH(pp_census_kernel, blocks_for(work, 0), PP_THREADS, s, *launch, n_cells, reinterpret_cast<unsigned long long*>(out3));
     return check("pp_census_kernel launch");
 }
 

@@ -17,11 +17,17 @@ from . import _native_pp as nat
 STD_OUTPUTS = ("prey_pos", "prey_energy", "pred_pos", "pred_energy")
 
 
+def _require_cuda(what, is_cuda):
+    """No CPU fallback: every tensor and the engine's device must be CUDA.  (One function so that the host-emulation tests,
+    which drive this engine against the kernel source compiled for the CPU, can lift the check.)"""
+    if not is_cuda:
+        raise RuntimeError(f"agenttorch_b200 predator-prey {what} need CUDA (no CPU fallback)")
+
+
 def _ptr(t, dtype=None):
     if t is None:
         return None
-    if not t.is_cuda:
-        raise RuntimeError("agenttorch_b200 predator-prey kernels need CUDA tensors (no CPU fallback)")
+    _require_cuda("kernels: tensors", t.is_cuda)
     if dtype is not None and t.dtype != dtype:
         raise TypeError(f"expected {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -301,8 +307,7 @@ class PredPreyEngine:
     def __init__(self, spec, device, adjacency=None, grid=0):
         self.spec = spec
         self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise RuntimeError("PredPreyEngine needs a CUDA device (no CPU fallback)")
+        _require_cuda("engine: the device", self.device.type == "cuda")
         nat.lib()
         self.model = spec.c_model()
         self.csr = adjacency if isinstance(adjacency, CsrAdjacency) else None
