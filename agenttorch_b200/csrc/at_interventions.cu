@@ -5,8 +5,9 @@
 // 4 consecutive agents: one 16-byte load per property, the draws regenerated in registers from the counter hash,
 // one 16-byte store per property and only where a value changed (when the output aliases the input).  Grids are
 // sized to the SM count (persistent grid-stride loop).
-#ifndef AT_IV_HOST_EMULATION        // tests/host_emulation/ compiles the kernels below for the CPU with a small shim
+#ifndef AT_HOST_EMULATION           // tests/host_emulation/ compiles this file for the CPU: a shim stands in for the runtime
 #include <cuda_runtime.h>
+#define AT_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #endif
 #include <stdarg.h>
 #include <stdint.h>
@@ -20,7 +21,6 @@ namespace {
 constexpr int IV_THREADS = 256;
 constexpr int STREAM_QUARANTINE = 1, STREAM_TESTING = 2, STREAM_MORTALITY = 3;
 
-#ifndef AT_IV_HOST_EMULATION
 thread_local char g_err[512] = "";
 
 int fail(const char* fmt, ...)
@@ -58,7 +58,6 @@ int blocks_for(int64_t groups)
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-#endif
 
 // ---- 4-agent group access: vector when the caller's arrays are 16-byte aligned and the group is full
 struct F4 { float v[4]; };
@@ -358,7 +357,6 @@ __global__ void iv_seirms_epilogue_kernel(const at_iv_seirms_args a)
 
 }  // namespace
 
-#ifndef AT_IV_HOST_EMULATION
 extern "C" {
 
 int at_iv_abi_version(void) { return AT_IV_ABI_VERSION; }
@@ -383,7 +381,7 @@ int at_iv_quarantine(const at_iv_quarantine_args* args, void* stream)
     if ((a.flags & AT_IV_APPLY) && (!a.start_date_in || !a.is_q_out || !a.start_date_out)) return fail("at_iv_quarantine: %s", "APPLY needs start_date_in, is_q_out, start_date_out");
     const bool vec = aligned16(a.is_q_in) && aligned16(a.start_date_in) && aligned16(a.is_q_out) && aligned16(a.start_date_out) &&
                      aligned16(a.u_start) && aligned16(a.u_break) && (a.stage_f64 || aligned16(a.stage));
-    iv_quarantine_kernel<<<blocks_for((a.n + 3) >> 2), IV_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, vec);
+    AT_LAUNCH(iv_quarantine_kernel, blocks_for((a.n + 3) >> 2), IV_THREADS, reinterpret_cast<cudaStream_t>(stream), a, vec);
     return check("iv_quarantine_kernel launch");
 }
 
@@ -403,7 +401,7 @@ int at_iv_testing(const at_iv_testing_args* args, void* stream)
     const bool vec = aligned16(a.is_q) && aligned16(a.u_comply) && aligned16(a.accept_action) && aligned16(a.awaiting_in) &&
                      aligned16(a.result_date_in) && aligned16(a.re_eligible_in) && aligned16(a.awaiting_out) &&
                      aligned16(a.result_date_out) && aligned16(a.re_eligible_out);
-    iv_testing_kernel<<<blocks_for((a.n + 3) >> 2), IV_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, vec);
+    AT_LAUNCH(iv_testing_kernel, blocks_for((a.n + 3) >> 2), IV_THREADS, reinterpret_cast<cudaStream_t>(stream), a, vec);
     return check("iv_testing_kernel launch");
 }
 
@@ -420,11 +418,10 @@ int at_iv_seirms_progression(const at_iv_seirms_args* args, void* stream)
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const bool vec = aligned16(a.stage_in) && aligned16(a.next_stage_time_in) && aligned16(a.stage_out) &&
                      aligned16(a.next_stage_time_out) && aligned16(a.u_death);
-    iv_seirms_kernel<<<blocks_for((a.n + 3) >> 2), IV_THREADS, 0, s>>>(a, vec);
+    AT_LAUNCH(iv_seirms_kernel, blocks_for((a.n + 3) >> 2), IV_THREADS, s, a, vec);
     if (check("iv_seirms_kernel launch")) return 1;
-    iv_seirms_epilogue_kernel<<<1, 32, 0, s>>>(a);
+    AT_LAUNCH(iv_seirms_epilogue_kernel, 1, 32, s, a);
     return check("iv_seirms_epilogue_kernel launch");
 }
 
 }  // extern "C"
-#endif

@@ -28,11 +28,17 @@ def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def _require_cuda(name, t):
+    """No CPU fallback.  (One function so that the host-emulation tests, which drive these ops against the kernel source
+    compiled for the CPU, can lift the check.)"""
+    if not t.is_cuda:
+        raise RuntimeError(f"agenttorch_b200 intervention kernels need CUDA tensors ({name} is on {t.device}); there is no CPU fallback")
+
+
 def _f32(t, name):
     if t is None:
         return None
-    if not t.is_cuda:
-        raise RuntimeError(f"agenttorch_b200 intervention kernels need CUDA tensors ({name} is on {t.device}); there is no CPU fallback")
+    _require_cuda(name, t)
     return t if t.dtype == torch.float32 and t.is_contiguous() else t.to(torch.float32).contiguous()
 
 
@@ -107,7 +113,8 @@ def quarantine_step(stage: Tensor, is_quarantined: Tensor, quarantine_start_date
     """Policies + transition of one quarantine substep IN PLACE (float32 contiguous state), one launch, untouched 16-byte
     groups are not written."""
     for x in (is_quarantined, quarantine_start_date):
-        if x.dtype != torch.float32 or not x.is_contiguous() or not x.is_cuda:
+        _require_cuda("in-place state", x)
+        if x.dtype != torch.float32 or not x.is_contiguous():
             raise RuntimeError("quarantine_step works in place on contiguous float32 CUDA tensors")
     _quarantine(nat.DECIDE | nat.APPLY, t, seed, id_offset, p_start, p_break, quarantine_days, infinity_time, stage.reshape(-1),
                 is_quarantined.view(-1), quarantine_start_date.view(-1), None, None, None, None, is_quarantined.view(-1),
@@ -164,7 +171,8 @@ def testing_step(is_quarantined: Tensor, awaiting_test_result: Tensor, test_resu
                  infinity_time: float) -> None:
     """Policy + transition of one testing substep IN PLACE, one launch."""
     for x in (awaiting_test_result, test_result_date, test_re_eligble_date):
-        if x.dtype != torch.float32 or not x.is_contiguous() or not x.is_cuda:
+        _require_cuda("in-place state", x)
+        if x.dtype != torch.float32 or not x.is_contiguous():
             raise RuntimeError("testing_step works in place on contiguous float32 CUDA tensors")
     aw, rd, re = awaiting_test_result.view(-1), test_result_date.view(-1), test_re_eligble_date.view(-1)
     _testing(nat.DECIDE | nat.APPLY, t, seed, id_offset, p_comply, ineligible_days, result_delay_days, infinity_time, None,

@@ -191,3 +191,131 @@ def test_ragged_sizes_and_every_status_combination_against_the_oracle(emu, n, of
         emu.emu_testing(make_testing_args(g, t, nat.DECIDE | nat.APPLY, q, aw, rd, re, aw, rd, re), int(off == 0), 3)
         for got, want in ((q, eq), (d, ed), (aw, ea), (rd, er), (re, ee)):
             assert np.array_equal(got, want), t
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The torch custom ops (agenttorch_b200/interventions.py) and the substep classes against the same host-compiled source,
+# through its C-ABI wrappers: argument structs, flags, action dtypes and the registered autograd on a machine without a GPU.
+@pytest.fixture()
+def ops_on_host(emu, monkeypatch):
+    from agenttorch_b200 import interventions as ops
+
+    monkeypatch.setattr(nat, "LIB_PATH", emu._name)
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setattr(ops, "_require_cuda", lambda name, t: None)
+    monkeypatch.setattr(ops, "_stream", lambda t: None)
+    yield ops
+    monkeypatch.setattr(nat, "_lib", None)
+
+
+@pytest.mark.parametrize("name", INTERVENTION_CASES)
+@pytest.mark.parametrize("variant", ["fused_inplace", "split"])
+def test_custom_ops_match_reference_histories(ops_on_host, name, variant):
+    ops = ops_on_host
+    g = load_interventions_golden(name)
+    n, T = len(g["age"]), g["num_steps"]
+    meta, env, ini = g["overrides"]["meta"], g["overrides"]["env"], g["overrides"]["initial"]
+    inf_t = float(meta["INFINITY_TIME"])
+    default = {"is_quarantined": 0, "quarantine_start_date": inf_t, "awaiting_test_result": 0, "test_result_date": inf_t,
+               "test_re_eligble_date": inf_t}
+    s = {k: torch.full((n, 1), float(ini.get(k, v)), dtype=torch.float32) for k, v in default.items()}
+    for t in range(T):
+        stage = torch.from_numpy(g["ref_disease_stage_history"][t].astype(np.float64)).reshape(n, 1)
+        if variant == "fused_inplace":
+            ops.quarantine_step(stage.float(), s["is_quarantined"], s["quarantine_start_date"], env["quarantine_start_prob"],
+                                env["quarantine_break_prob"], t, g["seed"], 0, float(meta["quarantine_days"]), inf_t)
+            ops.testing_step(s["is_quarantined"], s["awaiting_test_result"], s["test_result_date"], s["test_re_eligble_date"],
+                             env["test_compliance_prob"], t, g["seed"], 0, float(meta["test_ineligible_days"]),
+                             float(meta["test_result_delay_days"]), inf_t)
+        else:
+            start, _ = ops.quarantine_decide(stage, s["is_quarantined"], env["quarantine_start_prob"], 0.0, t, g["seed"], 0, None, None)
+            _, brk = ops.quarantine_decide(stage, s["is_quarantined"], 0.0, env["quarantine_break_prob"], t, g["seed"], 0, None, None)
+            assert start.dtype == torch.bool and start.shape == (n, 1)
+            s["is_quarantined"], s["quarantine_start_date"] = ops.quarantine_update(
+                s["is_quarantined"], s["quarantine_start_date"], start, brk.long(), t, float(meta["quarantine_days"]), inf_t)
+            accept = ops.testing_accept(s["is_quarantined"], env["test_compliance_prob"], t, g["seed"], 0, None)
+            s["awaiting_test_result"], s["test_result_date"], s["test_re_eligble_date"] = ops.testing_update(
+                s["awaiting_test_result"], s["test_result_date"], s["test_re_eligble_date"], accept, t,
+                float(meta["test_ineligible_days"]), float(meta["test_result_delay_days"]), inf_t)
+        for k in default:
+            assert np.array_equal(s[k].numpy().reshape(-1).astype(np.float64), g["ref_" + k + "_history"][t].astype(np.float64)), (k, t)
+
+
+@pytest.mark.parametrize("name", SEIRMS_CASES)
+def test_seirms_op_and_its_autograd_against_the_oracle(ops_on_host, name):
+    """Step by step: the op (kernel + epilogue + registered backward) against torch autograd of the oracle's progression,
+    for a random cotangent on (stage, daily_deaths)."""
+    ops = ops_on_host
+    g = load_interventions_golden(name)
+    n, T = len(g["age"]), g["num_steps"]
+    meta = g["overrides"]["meta"]
+    port = SeirmsPort(g["age"], g["stage0"], g["edges"], recovered_to_susceptible_time=meta["RECOVERED_TO_SUSCEPTIBLE_TIME"])
+    r2 = torch.tensor(g["r2"])
+    st = port.initial_state()
+    ids = np.arange(n)
+    rng = np.random.default_rng(5)
+    dd_op = torch.zeros(T)
+    for t in range(T):
+        w = torch.from_numpy(onoise.isolation_decision(g["seed"], t, ids, g["mode"], float(g["p_isolate"])))
+        u = torch.from_numpy(onoise.exposure_uniform(g["seed"], t, ids))
+        st, _ = port.transmission(st, t, w, u, r2)
+        st.stage = st.stage.detach().requires_grad_(True)
+        m_ref = torch.tensor(g["m"], requires_grad=True)
+        out = port.progression_seirms(st, t, m_ref, onoise.stream_uniforms(g["seed"], t, ids, onoise.STREAM_MORTALITY)[0])
+        stage_in = st.stage.detach().float().reshape(n, 1).requires_grad_(True)
+        m_op = torch.tensor(g["m"], requires_grad=True)
+        s2, n2, dd2, code, counts = ops.seirms_progression(stage_in, st.next_stage_time.reshape(n, 1), dd_op, m_op, t, g["seed"], 0, None,
+                                                           5.0, T + 20.0, float(meta["RECOVERED_TO_SUSCEPTIBLE_TIME"]))
+        assert np.array_equal(s2.detach().numpy().reshape(-1).astype(np.float64), out.stage.detach().numpy())
+        assert np.array_equal(n2.numpy().reshape(-1), out.next_stage_time.numpy())
+        assert torch.equal(dd2.detach(), out.daily_deaths.detach())
+        g_stage = torch.from_numpy(rng.standard_normal(n).astype(np.float32))
+        g_dd = torch.from_numpy(rng.standard_normal(T).astype(np.float32))
+        ((out.stage * g_stage.double()).sum() + (out.daily_deaths * g_dd).sum()).backward()
+        ((s2.reshape(-1) * g_stage).sum() + (dd2 * g_dd).sum()).backward()
+        assert torch.allclose(stage_in.grad.reshape(-1).double(), st.stage.grad, rtol=1e-5, atol=1e-6), t
+        assert torch.allclose(m_op.grad, m_ref.grad, rtol=1e-4, atol=1e-4), t
+        dd_op = dd2.detach()
+        st = type(st)(out.stage.detach(), out.next_stage_time, out.infected_time, out.daily_infected.detach(), out.daily_deaths.detach())
+
+
+def test_substep_classes_on_host(ops_on_host, monkeypatch):
+    """StartCompliance / BreakCompliance / UpdateQuarantineStatus / AcceptTest / UpdateTestStatus through the Controller."""
+    from agenttorch_b200.core.runner import Runner
+    from agenttorch_b200.models import covid
+    from agenttorch_b200.models.covid.interventions import add_intervention_substeps
+    from agenttorch_b200.models.covid.substeps.quarantine import action as q_action, transition as q_transition
+    from agenttorch_b200.models.covid.substeps.testing import action as t_action, transition as t_transition
+    from agenttorch_b200.models.covid.synthetic import synthetic_config
+    from oracle.interventions_port import quarantine_step, testing_step as oracle_testing_step
+
+    cfg = add_intervention_substeps(synthetic_config(500, 4.0, device="cpu", noise_seed=31))
+    cfg["state"]["agents"]["citizens"]["properties"]["test_re_eligble_date"]["value"] = 0
+    runner = Runner(cfg, covid.get_registry())
+    runner.init()
+    for module in (q_action, q_transition, t_action, t_transition):
+        monkeypatch.setattr(module, "require_cuda", lambda t, what: None)
+    state = runner.state
+    cit = state["agents"]["citizens"]
+    cit["disease_stage"] = torch.from_numpy(np.random.default_rng(2).choice([0.0, 1.0, 2.0, 3.0], size=(500, 1)))
+    pf, tf, of = runner.initializer.policy_function, runner.initializer.transition_function, runner.initializer.observation_function
+    for mod in (pf["2"]["citizens"]["start_compliance"], pf["2"]["citizens"]["break_compliance"], pf["3"]["citizens"]["accept_test"]):
+        mod.advance_seed = False
+    ids = np.arange(500)
+    q, d = np.zeros(500, np.float32), np.full(500, 130, np.float32)
+    aw, rd, re = np.zeros(500, np.float32), np.full(500, 130, np.float32), np.zeros(500, np.float32)
+    for t in range(6):
+        state["current_step"] = t
+        for sub in ("2", "3"):
+            state["current_substep"] = sub
+            obs = runner.controller.observe(state, of, "citizens")
+            act = {"citizens": runner.controller.act(state, obs, pf, "citizens")}
+            state = runner.controller.progress(state, act, tf)
+        us, ub = onoise.stream_uniforms(31, t, ids, onoise.STREAM_QUARANTINE)
+        q, d = quarantine_step(t, cit["disease_stage"].numpy().reshape(-1), q, d, us, ub, 0.7, 0.1, 12, 130)
+        aw, rd, re = oracle_testing_step(t, q, aw, rd, re, onoise.stream_uniforms(31, t, ids, onoise.STREAM_TESTING)[0], 0.95, 2, 3, 130)
+        c = state["agents"]["citizens"]
+        for key, want in (("is_quarantined", q), ("quarantine_start_date", d), ("awaiting_test_result", aw), ("test_result_date", rd),
+                          ("test_re_eligble_date", re)):
+            assert np.array_equal(c[key].numpy().reshape(-1), want), (key, t)
+    assert (q != 0).any() and (aw != 0).any()
