@@ -20,7 +20,12 @@
 // them in block order.  Daily sums use 64-bit fixed-point integer accumulation, so they are bitwise
 // reproducible under dynamic scheduling.  HBM-bound by the col stream; no tensor cores.
 
+#ifndef AT_HOST_EMULATION           // tests/host_emulation/ compiles this file for the CPU: a SIMT shim stands in for CUDA
 #include <cuda_runtime.h>
+#define AT_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define AT_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define AT_DYNAMIC_SMEM(type, name, alignment) extern __shared__ __align__(alignment) type name[]
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -77,6 +82,7 @@ __device__ __forceinline__ int load_age(const void* p, int64_t i, bool f32) {
 }
 
 // ------------------------------------------------------------------------------- TMA / mbarrier PTX
+#ifndef AT_HOST_EMULATION
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -95,6 +101,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#else
+// host emulation: a bulk copy completes when it is issued (a legal order: the source, `col`, is never written), so the
+// mbarrier bookkeeping has nothing left to do
+inline void mbar_init(uint64_t*, uint32_t) {}
+inline void mbar_expect_tx(uint64_t*, uint32_t) {}
+inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
+inline void mbar_wait(uint64_t*, uint32_t) {}
+inline void fence_mbarrier_init() {}
+inline void fence_proxy_async_smem() {}
+#endif
 
 struct KModel {   // device copy of at_seirm_model (kernel parameter, by value)
     int n_sfs, n_sfi, n_lg, e2i, i2r, inf_time;
@@ -115,7 +133,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     constexpr int RL = 4 * RL4, CAP = 32 * RL, WSM = warp_smem_bytes(CAP);
     constexpr int ROWS = (MODE == MODE_GATHER) ? 8 : 1;        // rows per lane in a gather task
     constexpr bool HASHED = (MODE == MODE_HASHED);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    AT_DYNAMIC_SMEM(unsigned char, smem_raw, 128);
     const int nw = blockDim.x >> 5;
     // [per-warp areas][Tdiv f64 n_sfs*NC][T1div f64 n_sfs*NC][s_A f32 256][s_G f32 256][hot bitmap]
     double* s_T = reinterpret_cast<double*>(smem_raw + (MODE != MODE_UPDATE ? nw * WSM : 0));
@@ -201,7 +219,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
         }
         if (seen != 0u) s_any_hot = 1;                       // benign race: every writer stores 1
         if (lane == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbarrier_init();
     }
     __syncthreads();
 
@@ -216,7 +234,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
     if (HAS_GATHER) {   // the staging buffers must always hold valid encodings (lanes read past a chunk's end)
         for (int i = lane; i < 2 * CAP; i += 32) s_col[i] = 0;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fence_proxy_async_smem();
         __syncwarp();
     }
 
@@ -796,6 +814,7 @@ hot_from_code_kernel(uint8_t* __restrict__ code, int64_t n_sources, uint32_t* __
 // later, after a rendezvous on the other buffer that every peer only joins once it has finished reading this one.
 #define AT_XCHG_FLAG_WORDS 64
 #define AT_XCHG_BITMAP_PAD 64
+#ifndef AT_HOST_EMULATION
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -804,6 +823,10 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+#else
+inline uint32_t ld_acquire_sys(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_sys(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#endif
 
 struct PeerBufs { uint8_t* p[16]; };
 
@@ -1002,7 +1025,7 @@ static int launch_kernel(const KModel& km, const at_seirm_launch& a, int grid, i
     auto k = seirm_kernel<MODE, RL4>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    k<<<grid, threads, smem, s>>>(km, a, bm_words, NC, G);
+    AT_LAUNCH_SMEM(k, grid, threads, smem, s, km, a, bm_words, NC, G);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail("seirm_kernel launch: %s", cudaGetErrorString(e));
     return 0;
@@ -1127,7 +1150,7 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         int slices = (total4 + M4 - 1) / M4;
         if (slices > 16) slices = 16;
         if (slices < 1) slices = 1;
-        hot_fold_kernel<<<dim3(fgrid, slices), 256, 0, s>>>(a.hot_bitmap_out, a.hot_filter_out, a.hash_words, total4);
+        AT_LAUNCH(hot_fold_kernel, dim3(fgrid, slices), 256, s, a.hot_bitmap_out, a.hot_filter_out, a.hash_words, total4);
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail("hot_fold_kernel launch: %s", cudaGetErrorString(e));
     }
@@ -1147,7 +1170,7 @@ int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, con
     if (g > tiles) g = (int)tiles;
     if (g > BWD_MAX_GRID) g = BWD_MAX_GRID;
     if (g < 1) g = 1;
-    seirm_episode_bwd_kernel<<<g, AT_BWD_THREADS, 0, (cudaStream_t)stream>>>(num_steps, n_rows, ld, dne_dr, recovered_step, sum_dne_dr,
+    AT_LAUNCH(seirm_episode_bwd_kernel, g, AT_BWD_THREADS, (cudaStream_t)stream, num_steps, n_rows, ld, dne_dr, recovered_step, sum_dne_dr,
         death_count, g_daily_infected, g_daily_deaths, m_value, grad_r, grad_m, (char*)workspace);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("seirm_episode_bwd_kernel launch: %s", cudaGetErrorString(e));
@@ -1173,9 +1196,9 @@ static int hot_from_code_impl(uint8_t* code, int64_t n_sources, uint32_t* hot_bi
         if (world < 1 || world > 16 || rank < 0 || rank >= world || (n_sources % world) || ((n_sources / world) & 1023))
             return fail("%s", "pull: world (<= 16) equal slices of whole 1024-source tiles are required");
         for (int r = 0; r < world; ++r) pp.p[r] = (const uint8_t*)peer_code[r];
-        hot_from_code_kernel<true><<<grid, 256, 0, s>>>(code, n_sources, hot_bitmap, hot_filter, hash_words, pp, rank, n_sources / world);
+        AT_LAUNCH(hot_from_code_kernel<true>, grid, 256, s, code, n_sources, hot_bitmap, hot_filter, hash_words, pp, rank, n_sources / world);
     } else {
-        hot_from_code_kernel<false><<<grid, 256, 0, s>>>(code, n_sources, hot_bitmap, hot_filter, hash_words, pp, 0, n_sources);
+        AT_LAUNCH(hot_from_code_kernel<false>, grid, 256, s, code, n_sources, hot_bitmap, hot_filter, hash_words, pp, 0, n_sources);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("hot_from_code_kernel launch: %s", cudaGetErrorString(e));
@@ -1217,7 +1240,7 @@ int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* ho
     int grid = (int)(tiles < g_sm_count * 4 ? tiles : g_sm_count * 4);
     if (grid < 1) grid = 1;
     uint32_t* any_word = step_workspace ? reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(step_workspace) + WS_ANYHOT) : nullptr;
-    exchange_sparse_kernel<<<grid, 256, 0, s>>>(local_buf, n_sources, hot_filter, hash_words, pb, world, rank, n_sources / world,
+    AT_LAUNCH(exchange_sparse_kernel, grid, 256, s, local_buf, n_sources, hot_filter, hash_words, pb, world, rank, n_sources / world,
                                                 sync_state, any_word, error_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("exchange_sparse_kernel launch: %s", cudaGetErrorString(e));
@@ -1235,7 +1258,7 @@ int at_noise_fill(float* out, int64_t n, int64_t id_offset, uint64_t seed, int32
     if (n <= 0) return 0;
     int grid = (int)((n + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    noise_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n, id_offset, seed, step, what, p_isolate);
+    AT_LAUNCH(noise_fill_kernel, grid, 256, (cudaStream_t)stream, out, n, id_offset, seed, step, what, p_isolate);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("noise_fill_kernel launch: %s", cudaGetErrorString(e));
     return 0;

@@ -127,11 +127,17 @@ _TIMER_TAG = {torch.float32: nat.TIMER_F32, torch.int16: nat.TIMER_I16}
 _AGE_TAG = {torch.float32: nat.AGE_F32, torch.uint8: nat.AGE_U8}
 
 
+def _require_cuda(message, is_cuda):
+    """No CPU path.  (One function so that the host-emulation tests, which drive this engine against the kernel source
+    compiled for the CPU, can lift the check.)"""
+    if not is_cuda:
+        raise RuntimeError(message)
+
+
 def _ptr(t, dtype=None, name="tensor"):
     if t is None:
         return None
-    if not t.is_cuda:
-        raise RuntimeError(f"{name} must be a CUDA tensor (agenttorch_b200 has no CPU path)")
+    _require_cuda(f"{name} must be a CUDA tensor (agenttorch_b200 has no CPU path)", t.is_cuda)
     if not t.is_contiguous():
         raise RuntimeError(f"{name} must be contiguous")
     if dtype is not None and t.dtype != dtype:
@@ -147,8 +153,7 @@ class SeirmEngine:
         possible); code_len: length of the code/bitmap arrays (multi-GPU: world_size equal slices)."""
         from .graph import BlockedGraph, block_graph, choose_block_size, choose_edges_per_chunk
 
-        if not graph.device.type == "cuda":
-            raise RuntimeError("SeirmEngine needs the contact graph on a CUDA device; there is no CPU fallback")
+        _require_cuda("SeirmEngine needs the contact graph on a CUDA device; there is no CPU fallback", graph.device.type == "cuda")
         self.lib = nat.lib()
         self.spec = spec
         self.device = graph.device

@@ -1,0 +1,102 @@
+"""The SEIRM engine (agenttorch_b200/engine.py) driven against csrc/at_seirm.cu COMPILED FOR THE HOST on a small SIMT
+emulator (tests/host_emulation/simt_shim.h: one OS thread per CUDA thread, block/warp rendezvous for __syncthreads and the
+warp intrinsics, TMA bulk copies completed at issue): the step kernel in its three layouts, the update-only kernel, the
+filter fold and the fused backward kernel are checked against the real reference's golden outputs on a machine without a
+GPU.  The -m gpu tests (tests/test_gpu_parity.py) run the same comparisons on the real library."""
+import contextlib
+import os
+import subprocess
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from agenttorch_b200 import _native, engine
+from tests.helpers import load_golden, make_noise, rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emulated_library(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("seirm_emu") / "libat_seirm_emulated.so")
+    cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "host_emulation", "seirm_emulation.cpp"), "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return out
+
+
+@pytest.fixture()
+def engine_on_host(emulated_library, monkeypatch):
+    """Point the ctypes binding at the emulated library; lift the engine's CUDA checks and stream / device calls."""
+    monkeypatch.setattr(_native, "LIB_PATH", emulated_library)
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(engine, "_require_cuda", lambda message, is_cuda: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda device: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: types.SimpleNamespace(cuda_stream=0))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda device=None: None)
+    yield
+    monkeypatch.setattr(_native, "_lib", None)              # the next user loads the real library again
+
+
+def _episode(g, *, packed=True, tensor_noise=False, **engine_kw):
+    from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
+    from agenttorch_b200.graph import build_contact_graph, mean_interactions_from_age
+
+    T, n = g["num_steps"], len(g["age"])
+    age = torch.from_numpy(g["age"].astype(np.int64))
+    edges = torch.from_numpy(g["edges"].astype(np.int64)).t().contiguous()
+    graph = build_contact_graph(edges, n, mean_interactions=mean_interactions_from_age(age))
+    eng = SeirmEngine(graph, SeirmSpec(num_steps=T), warps_per_cta=2, **engine_kw)          # 64 OS threads per block
+    st = SeirmState.from_initial(g["stage0"].astype(np.float32), g["age"], T, torch.device("cpu"), packed=packed)
+    if tensor_noise:
+        U, W = make_noise(g["seed"], g["mode"], n, T, float(g["p_isolate"]))
+        noise = NoiseSpec(seed=0, isolation="tensor", uniform="tensor", isolation_tensor=torch.from_numpy(W),
+                          uniform_tensor=torch.from_numpy(U))
+    else:
+        noise = NoiseSpec(seed=g["seed"], isolation=g["mode"], p_isolate=float(g["p_isolate"]))
+    r2 = torch.tensor(g["r2"], dtype=torch.float32, requires_grad=True)
+    eye = torch.eye(3)
+    r_steps = torch.stack([(r2 * eye[int(t / 7)]).sum() for t in range(T)])
+    m = torch.tensor(g["m"], dtype=torch.float32)
+    sv = eng.run_episode(st, r_steps.detach(), m, T, noise, want_grad=True, cuda_graph=False)
+    gr, gm = eng.episode_backward(sv, T, torch.from_numpy(g["gI"]), torch.from_numpy(g["gD"]), m)
+    eng.check_errors()
+    r_steps.backward(gr)
+    return st, r2.grad.numpy(), gm.numpy()
+
+
+def _check(g, st, grad_r2, grad_m):
+    assert np.array_equal(st.stage.numpy().astype(np.float64), g["ref_stage"])                                 # bit-exact
+    assert np.array_equal(st.next_stage_time.numpy().astype(np.int64), g["ref_next_stage_time"].astype(np.int64))
+    assert np.array_equal(st.infected_time.numpy().astype(np.int64), g["ref_infected_time"].astype(np.int64))
+    assert rel_err(g["ref_daily_infected"], st.daily_infected.numpy()) <= 1e-5
+    assert rel_err(g["ref_daily_deaths"], st.daily_deaths.numpy()) <= 1e-5
+    assert rel_err(g["ref_grad_R2"], grad_r2) <= 1e-4
+    assert rel_err(g["ref_grad_M"], grad_m) <= 1e-4
+
+
+@pytest.mark.parametrize("case,kw", [
+    ("tiny96_hard", dict()),                                         # fused kernel, exact shared-memory bitmap
+    ("tiny96_hard", dict(packed=False, tensor_noise=True)),          # float32 timers, injected uniforms
+    ("noiso500", dict()),
+    ("synth3k_hard", dict()),
+    ("synth3k_soft", dict(block_size=1024)),                         # column blocks: gather + update kernels
+    ("synth3k_r2vec", dict(hashed=True, hash_words=32)),             # hashed filter + hot_fold_kernel
+])
+def test_kernel_source_matches_reference_golden(engine_on_host, case, kw):
+    g = load_golden(case)
+    st, grad_r2, grad_m = _episode(g, **kw)
+    _check(g, st, grad_r2, grad_m)
+
+
+def test_the_real_binding_is_restored_after_emulation():
+    assert _native.LIB_PATH.endswith(os.path.join("lib", "libat_seirm.so"))
+    assert engine._require_cuda.__module__ == "agenttorch_b200.engine"
+    from agenttorch_b200.engine import SeirmEngine, SeirmSpec
+    from agenttorch_b200.graph import synthetic_contact_graph
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        SeirmEngine(synthetic_contact_graph(512, 4.0, 1, device="cpu"), SeirmSpec())
