@@ -40,14 +40,19 @@ class SeirmContext:
         self.handle = ops.register_engine(engine)
 
 
+def _require_cuda(is_cuda):
+    """No CPU fallback.  (One function so that the host-emulation tests can lift the check.)"""
+    if not is_cuda:
+        raise RuntimeError("agenttorch_b200 SEIRM substeps need CUDA tensors (simulation_metadata.device: cuda); "
+                           "there is no CPU fallback")
+
+
 def get_context(config, state, input_variables):
     """Engine for the contact network this substep reads; built on first use and cached by the identity
     of the adjacency payload.  Raises on CPU tensors: the kernels are the only implementation."""
     adjacency = get_by_path(state, re.split("/", input_variables["adjacency_matrix"]))
     edge_index, edge_attr = adjacency
-    if not edge_index.is_cuda:
-        raise RuntimeError("agenttorch_b200 SEIRM substeps need CUDA tensors (simulation_metadata.device: cuda); "
-                           "there is no CPU fallback")
+    _require_cuda(edge_index.is_cuda)
     key = (edge_index.data_ptr(), edge_index.shape[1], str(edge_index.device))
     ctx = _CACHE.get(key)
     if ctx is None:

@@ -100,3 +100,72 @@ def test_the_real_binding_is_restored_after_emulation():
 
     with pytest.raises(RuntimeError, match="CUDA"):
         SeirmEngine(synthetic_contact_graph(512, 4.0, 1, device="cpu"), SeirmSpec())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference-facing API (envs.create / runner.step / loss.backward) on the emulated library: the generic Controller path
+# (one custom op per substep, registered autograd) and the fused-episode path, as in tests/test_gpu_runner.py.
+def _runner(g, tmp_path, monkeypatch, fused):
+    from agenttorch_b200.core import envs
+    from agenttorch_b200.models import covid
+    from agenttorch_b200.models.covid import context
+    from agenttorch_b200.populations import write_population_folder
+
+    monkeypatch.setattr(context, "_require_cuda", lambda is_cuda: None)
+    monkeypatch.setattr(context, "_CACHE", {})
+    monkeypatch.setattr(context, "SeirmEngine", lambda graph, spec: engine.SeirmEngine(graph, spec, warps_per_cta=2))
+    folder = write_population_folder(str(tmp_path / "pop"), g["age"], g["stage0"], g["edges"])
+    runner = envs.create(model=covid, population=folder)
+    assert runner.initializer.device.type == "cpu"
+    runner._fused_enabled, runner._use_cuda_graph = fused, False
+    tr = runner.initializer.transition_function["0"]["new_transmission"]
+    pg = runner.initializer.transition_function["1"]["seirm_progression"]
+    pol = runner.initializer.policy_function["0"]["citizens"]["make_isolation_decision"]
+    r2 = torch.tensor(g["r2"], dtype=torch.float32, requires_grad=True)
+    m = torch.tensor(g["m"], dtype=torch.float32, requires_grad=True)
+    runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": r2,
+                            "initializer.transition_function.1.seirm_progression.learnable_args.M": m})
+    if fused:
+        tr.noise_seed, tr.advance_seed = g["seed"], False
+        runner._plan_cache = {"transmission": tr, "progression": pg, "policy": pol}     # the planner insists on a CUDA device
+    else:
+        U, W = make_noise(g["seed"], g["mode"], len(g["age"]), g["num_steps"], float(g["p_isolate"]))
+        Ut, Wt = torch.from_numpy(U), torch.from_numpy(W)
+        pol.mode = "injected"
+        pol.behavior = lambda obs: Wt[int(runner.state["current_step"])].reshape(-1, 1)
+        tr.exposure_uniform = lambda t: Ut[t]
+    return runner, r2, m
+
+
+def _check_runner(g, runner, r2, m):
+    env = runner.state_trajectory[-1][-1]["environment"]
+    di, dd = env["daily_infected"], env["daily_deaths"]
+    loss = (torch.from_numpy(g["gI"]) * di.reshape(-1)).sum() + (torch.from_numpy(g["gD"]) * dd.reshape(-1)).sum()
+    loss.backward()
+    ag = runner.state["agents"]["citizens"]
+    assert np.array_equal(ag["disease_stage"].detach().numpy().reshape(-1).astype(np.float64), g["ref_stage"])
+    assert np.array_equal(ag["next_stage_time"].numpy().reshape(-1).astype(np.int64), g["ref_next_stage_time"].astype(np.int64))
+    assert np.array_equal(ag["infected_time"].numpy().reshape(-1).astype(np.int64), g["ref_infected_time"].astype(np.int64))
+    assert tuple(dd.shape) == (1, g["num_steps"])
+    assert rel_err(g["ref_daily_infected"], di.detach().numpy()) <= 1e-5
+    assert rel_err(g["ref_daily_deaths"], dd.detach().numpy()) <= 1e-5
+    assert rel_err(g["ref_grad_R2"], r2.grad.numpy()) <= 1e-4
+    assert rel_err(g["ref_grad_M"], m.grad.numpy()) <= 1e-4
+    assert abs(float(loss) - float(g["ref_loss"])) <= 1e-5 * abs(float(g["ref_loss"]))
+
+
+@pytest.mark.parametrize("case", ["tiny96_hard", "synth3k_r2vec"])
+def test_runner_generic_path_on_host(engine_on_host, monkeypatch, tmp_path, case):
+    g = load_golden(case)
+    runner, r2, m = _runner(g, tmp_path, monkeypatch, fused=False)
+    runner.step(g["num_steps"])
+    assert runner.perf_stats["fused_episodes"] == 0 and len(runner.state_trajectory) == g["num_steps"] + 1
+    _check_runner(g, runner, r2, m)
+
+
+def test_runner_fused_episode_path_on_host(engine_on_host, monkeypatch, tmp_path):
+    g = load_golden("synth3k_soft")
+    runner, r2, m = _runner(g, tmp_path, monkeypatch, fused=True)
+    runner.step(g["num_steps"])
+    assert runner.perf_stats["fused_episodes"] == 1
+    _check_runner(g, runner, r2, m)
