@@ -153,7 +153,8 @@ class Runner(nn.Module):
         except ImportError:
             return None
         subs = self.config["substeps"]
-        if list(subs.keys()) != ["0", "1"] or self.initializer.device.type != "cuda":
+        keys = list(subs.keys())
+        if keys[:2] != ["0", "1"] or self.initializer.device.type != "cuda":
             return None
         tf, pf, of = self.initializer.transition_function, self.initializer.policy_function, self.initializer.observation_function
         if list(tf["0"].keys()) != ["new_transmission"] or list(tf["1"].keys()) != ["seirm_progression"]:
@@ -169,7 +170,16 @@ class Runner(nn.Module):
             return None
         if any(len(pf["1"][a]) for a in subs["1"]["active_agents"]):
             return None
-        self._plan_cache = {"transmission": tr, "progression": pg, "policy": pols["make_isolation_decision"]}
+        after_step = None
+        if keys[2:]:
+            # further substeps: only this package's quarantine / testing blocks, which ride along as one in-place launch each
+            # after every step of the fused episode (models/covid/interventions.py)
+            from agenttorch_b200.models.covid.interventions import plan_intervention_substeps
+
+            after_step = plan_intervention_substeps(self, keys[2:])
+            if after_step is None:
+                return None
+        self._plan_cache = {"transmission": tr, "progression": pg, "policy": pols["make_isolation_decision"], "after_step": after_step}
         return self._plan_cache if self._plan_cache["policy"].draws_uniform() else None
 
     def _step_fused(self, num_steps, plan):
@@ -212,15 +222,21 @@ class Runner(nn.Module):
         before = ctx.engine.launch_count
         ops.bind_state(ctx.handle, tensors["disease_stage"], tensors["next_stage_time"], tensors["infected_time"],
                        tensors["age"])
-        new_di, new_dd, _, _ = ops.seirm_episode(
-            ctx.handle, di.reshape(-1), dd.reshape(-1), r_steps, m_value, int(num_steps), tr.episode_seed(), "soft", 0.0,
-            None, uniform, want_grad, self._use_cuda_graph and uniform is None)
+        make_hook = plan.get("after_step")
+        hook = make_hook(state) if make_hook is not None else None
+        ctx.engine.after_step = hook
+        try:
+            new_di, new_dd, _, _ = ops.seirm_episode(
+                ctx.handle, di.reshape(-1), dd.reshape(-1), r_steps, m_value, int(num_steps), tr.episode_seed(), "soft", 0.0,
+                None, uniform, want_grad, self._use_cuda_graph and uniform is None)
+        finally:
+            ctx.engine.after_step = None
         set_by_path(state, path(iv["daily_infected"]), new_di.view_as(di))
         set_by_path(state, path(pv["daily_deaths"]), new_dd.reshape(1, -1))       # (1,T) like the reference (Q6)
         state["current_step"] = num_steps - 1
         state["current_substep"] = "0"
         self.perf_stats["fused_episodes"] += 1
-        self.perf_stats["kernel_launches"] += ctx.engine.launch_count - before
+        self.perf_stats["kernel_launches"] += ctx.engine.launch_count - before + (hook.launches_per_step * num_steps if hook else 0)
         di_key, dd_key = path(iv["daily_infected"])[-1], path(pv["daily_deaths"])[-1]
         env = state["environment"]
         n_sub = len(self.config["substeps"])
@@ -228,7 +244,7 @@ class Runner(nn.Module):
             self.state_trajectory.append([])
             for s in range(n_sub):
                 last = t == num_steps - 1 and s == n_sub - 1
-                upto = {di_key: t + 1, dd_key: t + 1 if s == n_sub - 1 else t}
+                upto = {di_key: t + 1, dd_key: t + 1 if s >= 1 else t}          # deaths are written by substep '1'
                 self.state_trajectory[-1].append({
                     "current_step": t, "current_substep": str((s + 1) % n_sub),
                     "environment": dict(env) if last else _LazyEnvironment(env, upto)})

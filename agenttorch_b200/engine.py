@@ -257,6 +257,10 @@ class SeirmEngine:
         self._saved = {}
         self._plans = {}
         self._recording = None
+        # optional callable(t) issued on the same stream right after the launches of step t (e.g. the quarantine / testing
+        # kernels of a covid config, which read the stage array the step just updated); episodes with a hook are not captured
+        # into CUDA graphs (the hook's buffers are not part of the capture key)
+        self.after_step = None
 
     # ------------------------------------------------------------------------------ raw launch
     def launch(self, state: SeirmState, *, flags, t, t_encode=None, code_in=None, code_out=None,
@@ -429,11 +433,13 @@ class SeirmEngine:
         sv["recovered_step"].fill_(255)
         plan = self._plans.get(key)
         if plan is not None:
-            for a, nk, flips in plan:
+            for k, (a, nk, flips) in enumerate(plan):
                 self._submit(a, nk)
                 if flips:
                     self.cur = 1 - self.cur
                 self.exchange(self.cur)
+                if flips and self.after_step is not None:
+                    self.after_step(t0 + k - 1)              # entry 0 is the encode launch
             return
         plan = []
         self._recording = []
@@ -448,6 +454,8 @@ class SeirmEngine:
                           dne_dr=sv["dne_dr"][k] if want_grad else None, sum_dne_dr=sv["sum_dne_dr"],
                           death_count=sv["death_count"], recovered_step=sv["recovered_step"], seed_ptr=self.seed_buf)
                 plan.append((*self._recording[-1], True))
+                if self.after_step is not None:
+                    self.after_step(t)
         finally:
             self._recording = None
         if len(self._plans) > 8:
@@ -465,7 +473,7 @@ class SeirmEngine:
         sv["r_steps"].copy_(r_steps.detach().reshape(-1)[:num_steps])
         sv["m_value"].copy_(m_value.detach().reshape(-1)[:1])
         self.seed_buf.fill_(_as_i64(noise.seed))
-        if not cuda_graph or (self.pg is not None and self.code_hdl is None):
+        if not cuda_graph or self.after_step is not None or (self.pg is not None and self.code_hdl is None):
             # (NCCL collectives are not captured: capturing them hung on this stack; without symmetric memory a
             # multi-GPU episode is issued launch by launch)
             self._issue_episode(state, num_steps, noise, sv, want_grad)

@@ -67,3 +67,101 @@ def use_seirms_progression(config, substep="1", name="seirm_progression"):
     block["generator"] = "SEIRMSProgression"
     cfg["substeps"][substep]["transition"]["seirms_progression"] = block
     return cfg
+
+
+# ------------------------------------------------------------------------------------------ fused execution
+def plan_intervention_substeps(runner, extra_keys):
+    """For a config whose substeps after '0' (transmission) and '1' (progression) are exactly this package's quarantine and/or
+    testing blocks: a factory `make_hook(state) -> hook(t)`; the Runner's fused SEIRM episode calls hook(t) right after the
+    launches of step t, and the hook issues ONE in-place launch per block (policies + transition, no action tensors, no state
+    copies) on the same stream.  None if any block is something else (then the generic Controller path runs)."""
+    import re
+
+    import torch
+
+    from agenttorch_b200 import interventions as iv_ops
+    from agenttorch_b200.core.helpers import get_by_path, set_by_path
+    from agenttorch_b200.models.covid.substeps.common import ScalarCache
+    from agenttorch_b200.models.covid.substeps.quarantine.action import BreakCompliance, StartCompliance
+    from agenttorch_b200.models.covid.substeps.quarantine.observation import GetFromState
+    from agenttorch_b200.models.covid.substeps.quarantine.transition import UpdateQuarantineStatus
+    from agenttorch_b200.models.covid.substeps.testing.action import AcceptTest
+    from agenttorch_b200.models.covid.substeps.testing.transition import UpdateTestStatus
+
+    init = runner.initializer
+    subs = runner.config["substeps"]
+    tf, pf, of = init.transition_function, init.policy_function, init.observation_function
+    scalar = ScalarCache()
+
+    def modules(table, key, agent):
+        return dict(table[key][agent]) if agent in table[key] else {}
+
+    def exactly(mods, wanted):
+        return list(mods.keys()) == [n for n, _ in wanted] and all(type(mods[n]) is c for n, c in wanted)
+
+    def in_place(state, path):
+        """float32 contiguous tensor at `path`, converted once and written back so the kernels can update it in place"""
+        cur = get_by_path(state, re.split("/", path))
+        fixed = cur if cur.dtype == torch.float32 and cur.is_contiguous() else cur.to(torch.float32).contiguous()
+        if fixed is not cur:
+            set_by_path(state, re.split("/", path), fixed)
+        return fixed
+
+    blocks = []
+    for key in extra_keys:
+        agents = subs[key]["active_agents"]
+        if list(agents) != ["citizens"]:
+            return None
+        obs, pol, trn = modules(of, key, "citizens"), modules(pf, key, "citizens"), dict(tf[key])
+        if (exactly(obs, [("get_from_state", GetFromState)]) and exactly(trn, [("update_quarantine_status", UpdateQuarantineStatus)])
+                and sorted(pol) == ["break_compliance", "start_compliance"] and type(pol["start_compliance"]) is StartCompliance
+                and type(pol["break_compliance"]) is BreakCompliance):
+            start, brk = pol["start_compliance"], pol["break_compliance"]
+            if start.uniform is not None or brk.uniform is not None:
+                return None                                    # injected draws: only the per-substep ops take them
+            if (start.noise_seed, start.advance_seed, start.episode_index) != (brk.noise_seed, brk.advance_seed, brk.episode_index):
+                return None                                    # the fused launch draws both decisions from ONE hash per agent
+            blocks.append(("quarantine", obs["get_from_state"], start, brk, trn["update_quarantine_status"]))
+        elif (not obs and exactly(pol, [("accept_test", AcceptTest)]) and exactly(trn, [("update_test_status", UpdateTestStatus)])):
+            if pol["accept_test"].uniform is not None:
+                return None
+            blocks.append(("testing", pol["accept_test"], trn["update_test_status"]))
+        else:
+            return None
+
+    def make_hook(state):
+        calls = []
+        for block in blocks:
+            if block[0] == "quarantine":
+                _, obs_mod, start, brk, upd = block
+                iv, tv = obs_mod.input_variables, upd.input_variables
+                stage = get_by_path(state, re.split("/", iv["disease_stage"]))
+                is_q, date = in_place(state, tv["is_quarantined"]), in_place(state, tv["quarantine_start_date"])
+                p_start = scalar("p_start", get_by_path(state, re.split("/", iv["quarantine_start_prob"])))
+                p_break = scalar("p_break", get_by_path(state, re.split("/", iv["quarantine_break_prob"])))
+
+                def run_quarantine(t, stage=stage, is_q=is_q, date=date, start=start, brk=brk, upd=upd, p_start=p_start, p_break=p_break):
+                    seed, seed_b = start.episode_seed(t), brk.episode_seed(t)
+                    assert seed == seed_b
+                    iv_ops.quarantine_step(stage.detach(), is_q, date, p_start, p_break, t, seed, start.id_offset,
+                                           float(upd.quarantine_days), float(upd.INFINITY_TIME))
+                calls.append(run_quarantine)
+            else:
+                _, acc, upd = block
+                pv, tv = acc.input_variables, upd.input_variables
+                is_q = in_place(state, pv["is_quarantined"])
+                aw, rd, re_ = (in_place(state, tv[k]) for k in ("awaiting_test_result", "test_result_date", "test_re_eligble_date"))
+                p = scalar("p_comply", get_by_path(state, re.split("/", pv["test_compliance_prob"])))
+
+                def run_testing(t, is_q=is_q, aw=aw, rd=rd, re_=re_, acc=acc, upd=upd, p=p):
+                    iv_ops.testing_step(is_q, aw, rd, re_, p, t, acc.episode_seed(t), acc.id_offset, float(upd.test_ineligible_days),
+                                        float(upd.test_result_delay_days), float(upd.INFINITY_TIME))
+                calls.append(run_testing)
+
+        def hook(t):
+            for call in calls:
+                call(int(t))
+        hook.launches_per_step = len(calls)
+        return hook
+
+    return make_hook

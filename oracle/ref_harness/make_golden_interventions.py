@@ -83,6 +83,10 @@ def main():
               initial={"is_quarantined": 1, "quarantine_start_date": 1, "awaiting_test_result": 1, "test_result_date": 2,
                        "test_re_eligble_date": 4},
               env={"quarantine_start_prob": 0.5, "quarantine_break_prob": 0.4, "test_compliance_prob": 0.6})
+    # reference-default soft isolation with an open testing queue: the case the fused Runner path is checked on
+    save_case("interventions_1500_softopen", "interventions", a, s, e, seed=59, mode="soft", r2=np.array([[4.0], [3.0], [2.0]], dtype=np.float32),
+              m=np.array([0.25], dtype=np.float32), meta={"quarantine_days": 4}, initial={"test_re_eligble_date": 0},
+              env={"quarantine_break_prob": 0.25, "test_compliance_prob": 0.6})
     save_case("seirms_1500_hard", "seirms", a, s, e, seed=54, mode="hard", r2=r2, m=np.array([0.3], dtype=np.float32))
     save_case("seirms_1500_soft", "seirms", a, s, e, seed=55, mode="soft", r2=np.array([[4.0], [3.0], [2.0]], dtype=np.float32),
               m=np.array([0.6], dtype=np.float32))

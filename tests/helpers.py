@@ -64,7 +64,7 @@ PREDPREY_KEYS = ("pred_pos", "pred_energy", "prey_pos", "prey_energy", "growth_s
 
 
 # ------------------------------------------------------------------- quarantine / testing / SEIRMS progression
-INTERVENTION_CASES = ["interventions_1500_hard", "interventions_1500_default", "interventions_1500_busy"]
+INTERVENTION_CASES = ["interventions_1500_hard", "interventions_1500_default", "interventions_1500_busy", "interventions_1500_softopen"]
 SEIRMS_CASES = ["seirms_1500_hard", "seirms_1500_soft", "seirms_64_hard"]
 
 

@@ -169,3 +169,92 @@ def test_runner_fused_episode_path_on_host(engine_on_host, monkeypatch, tmp_path
     runner.step(g["num_steps"])
     assert runner.perf_stats["fused_episodes"] == 1
     _check_runner(g, runner, r2, m)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Fused episode of a config WITH the quarantine / testing substeps: the SEIRM step launches and, after each, one in-place
+# launch per intervention block (models/covid/interventions.py::plan_intervention_substeps), both libraries emulated.
+@pytest.fixture(scope="module")
+def emulated_interventions_library(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("iv_emu") / "libat_interventions_emulated.so")
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "host_emulation", "iv_emulation.cpp"), "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return out
+
+
+@pytest.mark.parametrize("name", ["interventions_1500_softopen", "interventions_1500_default"])
+def test_fused_episode_with_intervention_substeps_on_host(engine_on_host, emulated_interventions_library, monkeypatch, tmp_path, name):
+    from agenttorch_b200 import _native_iv
+    from agenttorch_b200 import interventions as iv_ops
+    from agenttorch_b200.core.dataloader import DataLoader, LoadPopulation
+    from agenttorch_b200.core.runner import Runner
+    from agenttorch_b200.models import covid
+    from agenttorch_b200.models.covid import context
+    from agenttorch_b200.models.covid.interventions import add_intervention_substeps, plan_intervention_substeps
+    from agenttorch_b200.populations import write_population_folder
+    from tests.helpers import load_interventions_golden
+
+    monkeypatch.setattr(_native_iv, "LIB_PATH", emulated_interventions_library)
+    monkeypatch.setattr(_native_iv, "_lib", None)
+    monkeypatch.setattr(iv_ops, "_require_cuda", lambda name, t: None)
+    monkeypatch.setattr(iv_ops, "_stream", lambda t: None)
+    monkeypatch.setattr(context, "_require_cuda", lambda is_cuda: None)
+    monkeypatch.setattr(context, "_CACHE", {})
+    monkeypatch.setattr(context, "SeirmEngine", lambda graph, spec: engine.SeirmEngine(graph, spec, warps_per_cta=2))
+
+    g = load_interventions_golden(name)
+    ov = g["overrides"]
+    folder = write_population_folder(str(tmp_path / "pop"), g["age"], g["stage0"], g["edges"])
+    loader = DataLoader(covid, LoadPopulation(folder))
+    for k, v in ov["meta"].items():
+        loader.set_config_attribute(k, v)
+    loader.set_config_attribute("noise_seed", g["seed"])
+    for k, v in ov["initial"].items():
+        loader.config["state"]["agents"]["citizens"]["properties"][k]["value"] = v
+    for k, v in ov["env"].items():
+        loader.config["state"]["environment"][k]["value"] = v
+    runner = Runner(add_intervention_substeps(loader.get_config()), covid.get_registry())
+    runner.init()
+    runner._use_cuda_graph = False
+    tf, pf = runner.initializer.transition_function, runner.initializer.policy_function
+    tr, pg = tf["0"]["new_transmission"], tf["1"]["seirm_progression"]
+    noisy = [tr, pf["2"]["citizens"]["start_compliance"], pf["2"]["citizens"]["break_compliance"], pf["3"]["citizens"]["accept_test"]]
+    for mod in noisy:
+        assert mod.noise_seed == g["seed"]
+        mod.advance_seed = False
+    r2 = torch.tensor(g["r2"], dtype=torch.float32, requires_grad=True)
+    m = torch.tensor(g["m"], dtype=torch.float32, requires_grad=True)
+    runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": r2,
+                            "initializer.transition_function.1.seirm_progression.learnable_args.M": m})
+    assert runner._fused_plan() is None                                   # the planner insists on a CUDA device ...
+    make_hook = plan_intervention_substeps(runner, ["2", "3"])            # ... so the plan is assembled by hand
+    assert make_hook is not None
+    runner._plan_cache = {"transmission": tr, "progression": pg, "policy": pf["0"]["citizens"]["make_isolation_decision"],
+                          "after_step": make_hook}
+    T = g["num_steps"]
+    runner.step(T)
+    assert runner.perf_stats["fused_episodes"] == 1 and runner.perf_stats["kernel_launches"] >= 3 * T
+    assert len(runner.state_trajectory) == T + 1 and len(runner.state_trajectory[-1]) == 4
+    cit = runner.state["agents"]["citizens"]
+    for k in ("disease_stage", "next_stage_time", "is_quarantined", "quarantine_start_date", "awaiting_test_result",
+              "test_result_date", "test_re_eligble_date"):
+        got = cit[k].detach().numpy().reshape(-1).astype(np.float64)
+        assert np.array_equal(got, g["ref_" + k + "_history"][T - 1].astype(np.float64)), k
+    env = runner.state["environment"]
+    di, dd = env["daily_infected"], env["daily_deaths"]
+    assert rel_err(g["ref_daily_infected"], di.detach().numpy()) <= 1e-5 and rel_err(g["ref_daily_deaths"], dd.detach().numpy()) <= 1e-5
+    loss = (torch.from_numpy(g["gI"]) * di.reshape(-1)).sum() + (torch.from_numpy(g["gD"]) * dd.reshape(-1)).sum()
+    loss.backward()
+    assert rel_err(g["ref_grad_R2"], r2.grad.numpy()) <= 1e-4 and rel_err(g["ref_grad_M"], m.grad.numpy()) <= 1e-4
+    # a second episode replays the cached launch plan: the hook must fire there as well
+    before = cit["is_quarantined"].clone()
+    runner.step(2)
+    assert not torch.equal(before, runner.state["agents"]["citizens"]["is_quarantined"]) or name.endswith("default")
+    # substeps of another kind, or injected draws, are not fused
+    pf["3"]["citizens"]["accept_test"].uniform = lambda t: None
+    assert plan_intervention_substeps(runner, ["2", "3"]) is None
+    pf["3"]["citizens"]["accept_test"].uniform = None
+    pf["2"]["citizens"]["break_compliance"].noise_seed += 1
+    assert plan_intervention_substeps(runner, ["2", "3"]) is None
