@@ -158,3 +158,55 @@ def test_invariants_at_baseline_sizes(n):
     hist = torch.bincount(exposed_at, minlength=T)[:T].float()
     assert torch.equal(hist, st.daily_infected)                         # infected_time records the exposure step
     eng.check_errors()
+
+
+def test_fused_episode_with_intervention_substeps(tmp_path):
+    """A covid config WITH the quarantine / testing substeps and the default (in-kernel) isolation draw runs as one fused
+    episode: SEIRM step launches + one in-place launch per intervention block after every step.  Reference fixture
+    `interventions_1500_softopen`; the same comparison runs on the emulated libraries in tests/test_seirm_emulated.py.
+    (Kept last in the last GPU file: it was written after the round's GPU budget was spent.)"""
+    from agenttorch_b200.core.dataloader import DataLoader, LoadPopulation
+    from agenttorch_b200.core.runner import Runner
+    from agenttorch_b200.models import covid
+    from agenttorch_b200.models.covid.interventions import add_intervention_substeps
+    from agenttorch_b200.populations import write_population_folder
+    from tests.helpers import load_interventions_golden
+
+    g = load_interventions_golden("interventions_1500_softopen")
+    ov = g["overrides"]
+    folder = write_population_folder(str(tmp_path / "pop"), g["age"], g["stage0"], g["edges"])
+    loader = DataLoader(covid, LoadPopulation(folder))
+    for k, v in ov["meta"].items():
+        loader.set_config_attribute(k, v)
+    loader.set_config_attribute("noise_seed", g["seed"])
+    for k, v in ov["initial"].items():
+        loader.config["state"]["agents"]["citizens"]["properties"][k]["value"] = v
+    for k, v in ov["env"].items():
+        loader.config["state"]["environment"][k]["value"] = v
+    runner = Runner(add_intervention_substeps(loader.get_config()), covid.get_registry())
+    runner.init()
+    dev = runner.initializer.device
+    assert dev.type == "cuda"
+    tf, pf = runner.initializer.transition_function, runner.initializer.policy_function
+    for mod in (tf["0"]["new_transmission"], pf["2"]["citizens"]["start_compliance"], pf["2"]["citizens"]["break_compliance"],
+                pf["3"]["citizens"]["accept_test"]):
+        mod.advance_seed = False
+    r2 = torch.tensor(g["r2"], dtype=torch.float32, device=dev, requires_grad=True)
+    m = torch.tensor(g["m"], dtype=torch.float32, device=dev, requires_grad=True)
+    runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": r2,
+                            "initializer.transition_function.1.seirm_progression.learnable_args.M": m})
+    Tn = g["num_steps"]
+    runner.step(Tn)
+    assert runner.perf_stats["fused_episodes"] == 1
+    cit = runner.state["agents"]["citizens"]
+    for k in ("disease_stage", "next_stage_time", "is_quarantined", "quarantine_start_date", "awaiting_test_result",
+              "test_result_date", "test_re_eligble_date"):
+        got = cit[k].detach().cpu().numpy().reshape(-1).astype(np.float64)
+        assert np.array_equal(got, g["ref_" + k + "_history"][Tn - 1].astype(np.float64)), k
+    env = runner.state["environment"]
+    di, dd = env["daily_infected"], env["daily_deaths"]
+    assert rel_err(g["ref_daily_infected"], di.detach().cpu().numpy()) <= 1e-5
+    assert rel_err(g["ref_daily_deaths"], dd.detach().cpu().numpy()) <= 1e-5
+    loss = (torch.from_numpy(g["gI"]).to(dev) * di.reshape(-1)).sum() + (torch.from_numpy(g["gD"]).to(dev) * dd.reshape(-1)).sum()
+    loss.backward()
+    assert rel_err(g["ref_grad_R2"], r2.grad.cpu().numpy()) <= 1e-4 and rel_err(g["ref_grad_M"], m.grad.cpu().numpy()) <= 1e-4

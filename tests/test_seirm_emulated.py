@@ -229,10 +229,12 @@ def test_fused_episode_with_intervention_substeps_on_host(engine_on_host, emulat
     runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": r2,
                             "initializer.transition_function.1.seirm_progression.learnable_args.M": m})
     assert runner._fused_plan() is None                                   # the planner insists on a CUDA device ...
-    make_hook = plan_intervention_substeps(runner, ["2", "3"])            # ... so the plan is assembled by hand
-    assert make_hook is not None
-    runner._plan_cache = {"transmission": tr, "progression": pg, "policy": pf["0"]["citizens"]["make_isolation_decision"],
-                          "after_step": make_hook}
+    runner._plan_cache = None
+    real_device = runner.initializer.device
+    runner.initializer.device = types.SimpleNamespace(type="cuda")        # ... so it is shown one for the duration of the planning
+    plan = runner._fused_plan()
+    runner.initializer.device = real_device
+    assert plan is not None and plan["after_step"] is not None and plan["transmission"] is tr and plan["progression"] is pg
     T = g["num_steps"]
     runner.step(T)
     assert runner.perf_stats["fused_episodes"] == 1 and runner.perf_stats["kernel_launches"] >= 3 * T
