@@ -21,6 +21,12 @@ from .engine import NoiseSpec, SeirmEngine, SeirmState
 from .graph import build_contact_graph, shard_bounds, shard_code_len, shard_graph
 
 
+def _require_cuda(is_cuda):
+    """No CPU fallback.  (One function so that the host-emulation tests can lift the check.)"""
+    if not is_cuda:
+        raise RuntimeError("DistributedRunner needs simulation_metadata.device: cuda (no CPU fallback)")
+
+
 class _EpisodeFn(torch.autograd.Function):
     """Differentiable multi-GPU episode: forward advances the local shard, backward runs the fused backward kernel and
     all-reduces the parameter gradients."""
@@ -101,8 +107,7 @@ class DistributedRunner:
             return get_by_path(full, re.split("/", iv[name]))
 
         edge_index, edge_attr = var("adjacency_matrix")
-        if not edge_index.is_cuda:
-            raise RuntimeError("DistributedRunner needs simulation_metadata.device: cuda (no CPU fallback)")
+        _require_cuda(edge_index.is_cuda)
         from .models.covid.context import spec_from_state
 
         graph_full = build_contact_graph(edge_index, n, edge_attr=edge_attr, mean_interactions=var("mean_interactions"),

@@ -155,3 +155,86 @@ def test_sharded_engine_reproduces_single_rank(emulated_library, single_rank, tm
     np.testing.assert_allclose(parts[0]["dd"].numpy(), one["dd"].numpy(), rtol=1e-6)          # f32(count_r) * M per rank
     np.testing.assert_allclose(parts[0]["gr"].numpy(), one["gr"].numpy(), rtol=1e-6)
     np.testing.assert_allclose(parts[0]["gm"].numpy(), one["gm"].numpy(), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# envs.create(distributed=True) — the reference's multi-GPU entry point — on two emulated ranks, against the real reference's
+# golden outputs (the 2-GPU version is tests/test_gpu_multi.py::test_distributed_runner_api_matches_reference_golden).
+def _distributed_runner(rank, world, port, out_dir, lib_path, pop_dir, tag):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from agenttorch_b200 import _native, distributed, engine
+    from agenttorch_b200.core import envs
+    from agenttorch_b200.core.runner import Runner
+    from agenttorch_b200.models import covid
+    from agenttorch_b200.models.covid import context
+    from tests.helpers import load_golden
+
+    _native.LIB_PATH, _native._lib = lib_path, None
+    no_check = lambda *args: None                                                # noqa: E731
+    engine._require_cuda = context._require_cuda = distributed._require_cuda = no_check
+    torch.cuda.device = lambda device: contextlib.nullcontext()
+    torch.cuda.current_stream = lambda device=None: types.SimpleNamespace(cuda_stream=0)
+    torch.cuda.synchronize = lambda device=None: None
+    torch.set_num_threads(1)
+    real_engine = engine.SeirmEngine
+    distributed.SeirmEngine = lambda graph, spec, **kw: real_engine(graph, spec, warps_per_cta=2, **kw)
+    eager_episode = real_engine.run_episode                                      # no CUDA graphs without CUDA
+    real_engine.run_episode = lambda self, *args, cuda_graph=False, **kw: eager_episode(self, *args, cuda_graph=False, **kw)
+    real_plan = Runner._fused_plan
+
+    def plan_as_if_on_cuda(self):                            # the planner insists on a CUDA device
+        real_device = self.initializer.device
+        self.initializer.device = types.SimpleNamespace(type="cuda")
+        try:
+            return real_plan(self)
+        finally:
+            self.initializer.device = real_device
+
+    Runner._fused_plan = plan_as_if_on_cuda
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    symm = _SharedSymmetricMemory(tag, rank, world)
+    sys.modules["torch.distributed._symmetric_memory"] = symm
+    torch.distributed._symmetric_memory = symm
+    try:
+        g = load_golden("synth3k_soft")
+        runner = envs.create(model=covid, population=pop_dir, distributed=True, world_size=world)
+        assert runner.engine.code_hdl is not None                                # the symmetric-memory exchange is in use
+        r2 = torch.tensor(g["r2"], dtype=torch.float32, requires_grad=True)
+        m = torch.tensor(g["m"], dtype=torch.float32, requires_grad=True)
+        runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": r2,
+                                "initializer.transition_function.1.seirm_progression.learnable_args.M": m})
+        runner.tr.noise_seed, runner.tr.advance_seed = g["seed"], False
+        runner.step(g["num_steps"])
+        env = runner.state_trajectory[-1][-1]["environment"]
+        loss = (torch.from_numpy(g["gI"]) * env["daily_infected"].reshape(-1)).sum() + \
+               (torch.from_numpy(g["gD"]) * env["daily_deaths"].reshape(-1)).sum()
+        loss.backward()
+        final = runner.gather_final_state()
+        assert runner.agent_partition_map["local_size"] == runner.state["agents"]["citizens"]["disease_stage"].shape[0]
+        torch.save({"stage": final["disease_stage"], "nst": final["next_stage_time"], "di": env["daily_infected"].detach(),
+                    "dd": env["daily_deaths"].detach(), "gr2": r2.grad, "gm": m.grad}, os.path.join(out_dir, f"dr{rank}.pt"))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+        symm.cleanup()
+
+
+def test_distributed_runner_api_on_two_emulated_ranks(emulated_library, tmp_path):
+    import torch.multiprocessing as mp
+
+    from agenttorch_b200.populations import write_population_folder
+    from tests.helpers import load_golden, rel_err
+
+    g = load_golden("synth3k_soft")
+    pop = write_population_folder(str(tmp_path / "pop"), g["age"], g["stage0"], g["edges"])
+    mp.spawn(_distributed_runner, args=(2, _free_port(), str(tmp_path), emulated_library, pop, f"{os.getpid()}_dr"), nprocs=2, join=True)
+    for r in range(2):
+        o = torch.load(os.path.join(str(tmp_path), f"dr{r}.pt"))
+        assert np.array_equal(o["stage"].numpy().reshape(-1).astype(np.float64), g["ref_stage"])
+        assert np.array_equal(o["nst"].numpy().reshape(-1).astype(np.int64), g["ref_next_stage_time"].astype(np.int64))
+        assert tuple(o["dd"].shape) == (1, g["num_steps"])
+        assert rel_err(g["ref_daily_infected"], o["di"].numpy()) <= 1e-5 and rel_err(g["ref_daily_deaths"], o["dd"].numpy()) <= 1e-5
+        assert rel_err(g["ref_grad_R2"], o["gr2"].numpy()) <= 1e-4 and rel_err(g["ref_grad_M"], o["gm"].numpy()) <= 1e-4
