@@ -104,12 +104,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #else
-// host emulation: a bulk copy completes when it is issued (a legal order: the source, `col`, is never written), so the
-// mbarrier bookkeeping has nothing left to do
-inline void mbar_init(uint64_t*, uint32_t) {}
+// host emulation: the bulk copy is a memcpy by the issuing thread; the mbarrier word counts completed phases (one copy per
+// phase here), and a wait on parity P returns once the current phase's parity differs from P — the hardware's rule
+inline void mbar_init(uint64_t* bar, uint32_t) { __atomic_store_n(bar, (uint64_t)0, __ATOMIC_RELEASE); }
 inline void mbar_expect_tx(uint64_t*, uint32_t) {}
-inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
-inline void mbar_wait(uint64_t*, uint32_t) {}
+inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    memcpy(dst, src, bytes);
+    __atomic_fetch_add(bar, (uint64_t)1, __ATOMIC_RELEASE);
+}
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1u) == parity) __nanosleep(0);
+}
 inline void fence_mbarrier_init() {}
 inline void fence_proxy_async_smem() {}
 #endif

@@ -1,6 +1,6 @@
 """The SEIRM engine (agenttorch_b200/engine.py) driven against csrc/at_seirm.cu COMPILED FOR THE HOST on a small SIMT
 emulator (tests/host_emulation/simt_shim.h: one OS thread per CUDA thread, block/warp rendezvous for __syncthreads and the
-warp intrinsics, TMA bulk copies completed at issue): the step kernel in its three layouts, the update-only kernel, the
+warp intrinsics, TMA bulk copies as memcpy + mbarrier phase counts): the step kernel in its three layouts, the update-only kernel, the
 filter fold and the fused backward kernel are checked against the real reference's golden outputs on a machine without a
 GPU.  The -m gpu tests (tests/test_gpu_parity.py) run the same comparisons on the real library."""
 import contextlib
@@ -260,3 +260,71 @@ def test_fused_episode_with_intervention_substeps_on_host(engine_on_host, emulat
     pf["3"]["citizens"]["accept_test"].uniform = None
     pf["2"]["citizens"]["break_compliance"].noise_seed += 1
     assert plan_intervention_substeps(runner, ["2", "3"]) is None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Seeded synthetic inputs against the oracle, as in tests/test_gpu_synthetic.py: tasks spanning several TMA chunks, weighted
+# edges, an empty graph — small enough for the emulator.
+def _synthetic(n, deg, seed, frac_e=0.02, frac_i=0.01):
+    rng = np.random.default_rng(seed)
+    age = rng.integers(0, 6, n)
+    stage0 = np.zeros(n)
+    r = rng.random(n)
+    stage0[r < frac_e] = 1.0
+    stage0[(r >= frac_e) & (r < frac_e + frac_i)] = 2.0
+    edges = np.stack([rng.integers(0, n, int(n * deg)), rng.integers(0, n, int(n * deg))], axis=1)
+    return age, stage0, edges
+
+
+def _against_oracle(age, stage0, edges, seed, mode, r2, m, weights=None, **engine_kw):
+    from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
+    from agenttorch_b200.graph import build_contact_graph, mean_interactions_from_age
+    from oracle.seirm_port import SeirmPort, episode_with_grads
+
+    T, n = 21, len(age)
+    U, W = make_noise(seed, mode, n, T)
+    gI, gD = np.linspace(0.5, 1.5, T, dtype=np.float32), np.linspace(2.0, 1.0, T, dtype=np.float32)
+    ref = episode_with_grads(SeirmPort(age, stage0, edges, edge_weight=weights), W, U, gI, gD, r2=r2, m=m)
+    ei = torch.from_numpy(edges.astype(np.int64)).t().contiguous()
+    attr = None if weights is None else torch.stack((torch.ones(len(edges)), torch.from_numpy(weights.astype(np.float32))))
+    graph = build_contact_graph(ei, n, edge_attr=attr, mean_interactions=mean_interactions_from_age(torch.from_numpy(age)))
+    eng = SeirmEngine(graph, SeirmSpec(num_steps=T), warps_per_cta=2, **engine_kw)
+    st = SeirmState.from_initial(stage0.astype(np.float32), age, T, torch.device("cpu"))
+    r2_t = torch.tensor(r2, dtype=torch.float32, requires_grad=True)
+    eye = torch.eye(3)
+    r_steps = torch.stack([(r2_t * eye[int(t / 7)]).sum() for t in range(T)])
+    m_t = torch.tensor(m, dtype=torch.float32)
+    sv = eng.run_episode(st, r_steps.detach(), m_t, T, NoiseSpec(seed=seed, isolation=mode), want_grad=True)
+    gr, gm = eng.episode_backward(sv, T, torch.from_numpy(gI), torch.from_numpy(gD), m_t)
+    eng.check_errors()
+    r_steps.backward(gr)
+    assert np.array_equal(st.stage.numpy().astype(np.float64), ref["stage"])
+    assert np.array_equal(st.next_stage_time.numpy().astype(np.float32), ref["next_stage_time"])
+    assert np.array_equal(st.infected_time.numpy().astype(np.float32), ref["infected_time"])
+    assert rel_err(ref["daily_infected"], st.daily_infected.numpy()) <= 1e-5 and rel_err(ref["daily_deaths"], st.daily_deaths.numpy()) <= 1e-5
+    assert rel_err(ref["grad_R2"], r2_t.grad.numpy()) <= 1e-4 and rel_err(ref["grad_M"], gm.numpy()) <= 1e-4
+    return st
+
+
+_R2, _M = np.array([[0.30], [0.25], [0.20]], dtype=np.float32), np.array([0.2], dtype=np.float32)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(edges_per_chunk=512), dict(hash_words=32)])
+def test_tasks_larger_than_one_chunk_on_host(engine_on_host, kw):
+    """average in-degree 45: a 32-row task holds ~1440 edges = 2-3 chunks of 512/768 edges"""
+    age, stage0, edges = _synthetic(1536, 45.0, 3)
+    st = _against_oracle(age, stage0, edges, 77, "hard", _R2 * 0.3, _M, **kw)
+    assert float(st.daily_infected.sum()) > 20
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(block_size=1024)])
+def test_weighted_edges_on_host(engine_on_host, kw):
+    age, stage0, edges = _synthetic(2048, 7.0, 4)
+    w = np.random.default_rng(9).uniform(0.25, 2.0, len(edges)).astype(np.float32)
+    _against_oracle(age, stage0, edges, 5, "hard", _R2 * 4, _M, weights=w, **kw)
+
+
+def test_empty_graph_on_host(engine_on_host):
+    age, stage0, _ = _synthetic(200, 1.0, 6, frac_e=0.05, frac_i=0.05)
+    st = _against_oracle(age, stage0, np.zeros((0, 2), dtype=np.int64), 1, "soft", _R2, _M)
+    assert float(st.daily_infected.sum()) == 0.0
