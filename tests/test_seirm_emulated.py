@@ -328,3 +328,34 @@ def test_empty_graph_on_host(engine_on_host):
     age, stage0, _ = _synthetic(200, 1.0, 6, frac_e=0.05, frac_i=0.05)
     st = _against_oracle(age, stage0, np.zeros((0, 2), dtype=np.int64), 1, "soft", _R2, _M)
     assert float(st.daily_infected.sum()) == 0.0
+
+
+def test_after_step_hook_fires_in_recorded_and_replayed_episodes(engine_on_host):
+    """SeirmEngine.after_step: called once per step with the step number, both when an episode's launches are recorded and
+    when the cached launch plan is replayed; results do not depend on it."""
+    from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
+    from agenttorch_b200.graph import build_contact_graph, mean_interactions_from_age
+
+    g = load_golden("tiny96_hard")
+    T, n = g["num_steps"], len(g["age"])
+    age = torch.from_numpy(g["age"].astype(np.int64))
+    graph = build_contact_graph(torch.from_numpy(g["edges"].astype(np.int64)).t().contiguous(), n,
+                                mean_interactions=mean_interactions_from_age(age))
+    eng = SeirmEngine(graph, SeirmSpec(num_steps=T), warps_per_cta=2)
+    fresh = SeirmState.from_initial(g["stage0"].astype(np.float32), g["age"], T, torch.device("cpu"))
+    st = fresh.clone()
+    noise = NoiseSpec(seed=g["seed"], isolation=g["mode"], p_isolate=float(g["p_isolate"]))
+    r_steps, m = torch.full((T,), 4.5), torch.tensor(g["m"], dtype=torch.float32)
+    seen, stages = [], []
+    eng.after_step = lambda t: (seen.append(t), stages.append(st.stage.clone()))
+    results = []
+    for _ in range(3):                                       # 1st: recorded; 2nd and 3rd: replayed from the cached plan
+        for k in ("stage", "next_stage_time", "infected_time", "daily_infected", "daily_deaths"):
+            getattr(st, k).copy_(getattr(fresh, k))
+        eng.run_episode(st, r_steps, m, T, noise, want_grad=True, cuda_graph=True)     # a hook forces eager launches
+        results.append((st.stage.clone(), st.daily_infected.clone()))
+    assert seen == list(range(T)) * 3
+    assert all(torch.equal(results[0][0], r[0]) and torch.equal(results[0][1], r[1]) for r in results[1:])
+    assert all(torch.equal(stages[t], stages[T + t]) for t in range(T))               # the hook saw the state after step t
+    assert torch.equal(stages[T - 1], results[0][0])
+    eng.after_step = None
