@@ -105,6 +105,75 @@ class Runner(nn.Module):
         self.state["current_substep"] = "0"
         self.state_trajectory = [[self._snapshot(self.state)]]
 
+    # ---------------------------------------------------------------------------- checkpoint / resume
+    def _noise_modules(self):
+        """(name, module) of every substep module that owns a counter-hash noise address."""
+        init = self.initializer
+        for kind, table in (("observation", init.observation_function), ("policy", init.policy_function)):
+            for substep, per_agent in table.items():
+                for agent, mods in per_agent.items():
+                    for name, mod in mods.items():
+                        if hasattr(mod, "noise_seed"):
+                            yield f"{kind}.{substep}.{agent}.{name}", mod
+        for substep, mods in init.transition_function.items():
+            for name, mod in mods.items():
+                if hasattr(mod, "noise_seed"):
+                    yield f"transition.{substep}.{name}", mod
+
+    def checkpoint(self):
+        """Everything a later episode depends on, as CPU tensors and plain numbers: the agent / environment / object state
+        (SoA tensors), the learnable and calibration parameters of every substep module, and the noise counters (seed, episode
+        index) of the modules that draw from the counter hash — the reference pickles `state` + `parameters_dict`
+        (initializer.py:434-444) and has no reproducible random stream to save.  Episodes run from a restored checkpoint
+        are bitwise identical to the ones the original runner would have run."""
+        def to_cpu_tree(tree):
+            out = {}
+            for k, v in tree.items():
+                if isinstance(v, dict):
+                    out[k] = to_cpu_tree(v)
+                elif torch.is_tensor(v):
+                    out[k] = v.detach().to("cpu").clone()
+            return out
+
+        params = {}
+        for mod_name, mod in self.initializer.named_modules():
+            for attr, value in vars(mod).items():
+                if attr.startswith("calibrate_") and torch.is_tensor(value):
+                    params[f"{mod_name}.{attr}"] = value.detach().to("cpu").clone()
+            if hasattr(mod, "external_M") and torch.is_tensor(mod.external_M):
+                params[f"{mod_name}.external_M"] = mod.external_M.detach().to("cpu").clone()
+        noise = {name: {"noise_seed": int(m.noise_seed), "episode_index": int(m.episode_index), "advance_seed": bool(m.advance_seed)}
+                 for name, m in self._noise_modules()}
+        return {"format": 1, "num_agents": int(self.config["simulation_metadata"]["num_agents"]),
+                "state": to_cpu_tree({k: v for k, v in self.state.items() if k in ("agents", "environment", "objects")}),
+                "module_state": {k: v.detach().to("cpu").clone() for k, v in self.initializer.state_dict().items()},
+                "parameters": params, "noise": noise, "episode_index": int(self._episode_index)}
+
+    def save_checkpoint(self, path):
+        torch.save(self.checkpoint(), path)
+
+    def load_checkpoint(self, source):
+        """Restore a checkpoint (a path or the dict `checkpoint()` returned) into this initialised runner."""
+        ck = torch.load(source, map_location="cpu", weights_only=True) if isinstance(source, (str, bytes)) or hasattr(source, "__fspath__") else source
+        if ck.get("format") != 1:
+            raise ValueError(f"unsupported checkpoint format {ck.get('format')}")
+        if ck["num_agents"] != int(self.config["simulation_metadata"]["num_agents"]):
+            raise ValueError(f"checkpoint of {ck['num_agents']} agents, runner has {self.config['simulation_metadata']['num_agents']}")
+        self.restore_state(ck["state"], non_blocking=False)
+        self.initializer.load_state_dict(ck["module_state"], strict=False)
+        modules = dict(self.initializer.named_modules())
+        for key, value in ck["parameters"].items():
+            mod_name, attr = key.rsplit(".", 1)
+            mod = modules[mod_name]
+            cur = getattr(mod, attr)
+            setattr(mod, attr, value.to(cur.device).to(cur.dtype).requires_grad_(cur.requires_grad))
+        mine = dict(self._noise_modules())
+        for name, counters in ck["noise"].items():
+            if name in mine:
+                mod = mine[name]
+                mod.noise_seed, mod.episode_index, mod.advance_seed = counters["noise_seed"], counters["episode_index"], counters["advance_seed"]
+        self._episode_index = int(ck.get("episode_index", 0))
+
     def reset_state_before_episode(self):
         self.state_trajectory = [[self._snapshot(self.state)]]
 

@@ -359,3 +359,41 @@ def test_after_step_hook_fires_in_recorded_and_replayed_episodes(engine_on_host)
     assert all(torch.equal(stages[t], stages[T + t]) for t in range(T))               # the hook saw the state after step t
     assert torch.equal(stages[T - 1], results[0][0])
     eng.after_step = None
+
+
+def test_checkpoint_and_resume_reproduce_the_next_episode(engine_on_host, monkeypatch, tmp_path):
+    """Runner.save_checkpoint / load_checkpoint: state tensors + parameters + noise counters; an episode run
+    from the restored checkpoint is bitwise the episode the original runner runs next."""
+    g = load_golden("tiny96_hard")
+
+    def fresh():
+        runner, r2, m = _runner(g, tmp_path, monkeypatch, fused=True)
+        tr = runner.initializer.transition_function["0"]["new_transmission"]
+        tr.noise_seed, tr.advance_seed = 1234, True                      # a new noise stream every episode
+        return runner, tr
+
+    a, tr_a = fresh()
+    a.step(g["num_steps"])
+    path = str(tmp_path / "episode1.ckpt")
+    a.save_checkpoint(path)
+    assert tr_a.episode_index == 1
+    a.step(g["num_steps"])                                                # episode 2 of the original runner
+    want = {k: v.detach().clone() for k, v in a.state["agents"]["citizens"].items()}
+    want_env = {k: a.state["environment"][k].detach().clone() for k in ("daily_infected", "daily_deaths")}
+
+    b, tr_b = fresh()
+    r2_b = b.initializer.transition_function["0"]["new_transmission"].calibrate_R2
+    b.load_checkpoint(path)
+    assert tr_b.episode_index == 1 and tr_b.noise_seed == 1234
+    restored = b.initializer.transition_function["0"]["new_transmission"].calibrate_R2
+    assert torch.equal(restored.detach(), torch.tensor(g["r2"])) and restored.requires_grad == r2_b.requires_grad
+    b._plan_cache = {"transmission": tr_b, "progression": b.initializer.transition_function["1"]["seirm_progression"],
+                     "policy": b.initializer.policy_function["0"]["citizens"]["make_isolation_decision"]}
+    b.step(g["num_steps"])
+    for k, v in want.items():
+        assert torch.equal(b.state["agents"]["citizens"][k].detach(), v), k
+    for k, v in want_env.items():
+        assert torch.equal(b.state["environment"][k].detach().reshape(-1), v.reshape(-1)), k
+    assert float(want_env["daily_infected"].sum()) != float(torch.tensor(g["ref_daily_infected"]).sum())   # a different stream than episode 1
+    with pytest.raises(ValueError, match="format"):
+        b.load_checkpoint({"format": 99})
