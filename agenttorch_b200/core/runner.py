@@ -15,7 +15,6 @@ import torch
 import torch.nn as nn
 
 from .controller import Controller
-from .helpers import to_cpu
 from .initializer import Initializer
 
 

@@ -12,7 +12,7 @@ Replaces the reference's per-substep ATen op chains (new_transmission/transition
 seirm_progression/transition.py:90-121) and its T-step autograd graph.
 """
 import ctypes
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional
 
 import torch

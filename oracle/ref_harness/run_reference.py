@@ -14,7 +14,6 @@ through the reference's own hooks:
   * transition.st_bernoulli = injected sampler  (transition.py:30,223)
 No reference source is copied into this repository.
 """
-import importlib
 import os
 import shutil
 import sys

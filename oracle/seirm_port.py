@@ -22,7 +22,7 @@ float64, timers float32, daily series float32.
 Autograd is torch's own, applied to the same op sequence, so gradients follow
 the reference's straight-through convention by construction.
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 import torch

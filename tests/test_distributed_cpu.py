@@ -4,7 +4,6 @@ the exchanged arrays is emulated with torch ops and compared with the single-pro
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

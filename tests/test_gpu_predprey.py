@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import PREDPREY_CASES, PREDPREY_KEYS, load_predprey_golden, predprey_port_from_golden
+from tests.helpers import PREDPREY_CASES, PREDPREY_KEYS, load_predprey_golden
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

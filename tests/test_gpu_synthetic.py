@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.seirm_port import SeirmConstants, SeirmPort, episode_with_grads
+from oracle.seirm_port import SeirmPort, episode_with_grads
 from tests.helpers import make_noise, rel_err
 
 pytestmark = pytest.mark.gpu

@@ -1,7 +1,6 @@
 """Emit agenttorch_b200/models/covid/yamls/config.yaml (same schema as the reference's covid config:
 simulation_metadata / state / substeps; property = {name, shape, dtype, learnable, value | initialization_function})."""
 import os
-import sys
 
 import yaml
 

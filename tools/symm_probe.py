@@ -1,5 +1,5 @@
 """Probe: symmetric memory + barrier + peer copies inside a CUDA graph (run under torchrun on >= 2 GPUs)."""
-import os, sys, time
+import os, time
 import torch
 import torch.distributed as dist
 import torch.distributed._symmetric_memory as symm
