@@ -55,11 +55,11 @@ static int default_grid() {
 // The info byte of a cell, read from L2 (other threads of the same launch OR bits into neighbouring positions of the
 // byte with atomics; the bits tested here are not written by this launch, so any snapshot of the byte is good).
 __device__ __forceinline__ uint32_t cell_info(const uint8_t* info, int cell) {
-    return (uint32_t)__ldcg(info + cell);          // measured: .cg / .nc / default loads all time the same here
+    return (uint32_t)__ldcg(info + cell);          // benign race with mark_cell (see above); .cg / .nc / default loads time the same
 }
 // (measured: aggregating the marks of a warp per word with __match_any_sync costs 2.4x more than the atomics it saves)
 __device__ __forceinline__ void mark_cell(uint8_t* info, int cell, uint32_t bits) {
-    atomicOr(reinterpret_cast<uint32_t*>(info) + (cell >> 2), bits << (8 * (cell & 3)));     // OR: order-independent
+    atomicOr(reinterpret_cast<uint32_t*>(info) + (cell >> 2), bits << (8 * (cell & 3)));     // OR: order-independent; benign race with cell_info
 }
 
 // cell / width without a hardware division: q = (cell * mul) >> (31 + log2ceil(width)), exact for 0 <= cell < 2^31

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE — run SEIRM episodes on the emulated library given on the command line, in the layouts given, and check
-them against the reference golden.  Started by tests/test_seirm_racecheck.py under ThreadSanitizer (LD_PRELOAD=libtsan.so with
+them against the reference golden.  Started by tests/test_racecheck.py under ThreadSanitizer (LD_PRELOAD=libtsan.so with
 the emulated library built with -fsanitize=thread): every CUDA thread of the emulator is an OS thread, so TSan sees the
 kernel's shared- and global-memory accesses with the happens-before edges of the barriers, warp rendezvous and atomics.
 
