@@ -78,3 +78,24 @@ def test_predator_prey_threads_only_meet_in_the_occupancy_marks(tmp_path):
     assert pairs, "ThreadSanitizer saw no thread interaction at all: the check did not run"
     bad = sorted({ln for pair in pairs for ln in pair if ln is None or "benign race" not in source[ln - 1]}, key=str)
     assert not bad, [(ln, source[ln - 1].strip() if ln else "frame outside the kernel source") for ln in bad]
+
+
+@pytest.mark.skipif(_libtsan() is None, reason="libtsan.so not available")
+def test_intervention_kernels_are_race_free(tmp_path):
+    """csrc/at_interventions.cu: a thread owns its 4 agents, the SEIRMS counts go through warp shuffles + atomics, the
+    epilogue runs after the launch boundary — ThreadSanitizer must report nothing at all."""
+    lib = str(tmp_path / "libat_interventions_emulated_tsan.so")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-shared", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "host_emulation", "iv_simt_emulation.cpp"), "-o", lib]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    symbols = subprocess.run(["nm", "-D", "--undefined-only", lib], capture_output=True, text=True).stdout
+    assert "__tsan_" in symbols                                  # the library really is instrumented
+    log = str(tmp_path / "tsan")
+    env = dict(os.environ, LD_PRELOAD=_libtsan(), TSAN_OPTIONS=f"report_signal_unsafe=0 exitcode=0 history_size=2 log_path={log}")
+    run = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_emulation", "racecheck_interventions.py"), lib],
+                         capture_output=True, text=True, env=env, timeout=1200)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "episode ok: interventions" in run.stdout
+    reports = "".join(open(p).read() for p in glob.glob(log + "*"))
+    assert "WARNING: ThreadSanitizer" not in reports, reports[:2000]
