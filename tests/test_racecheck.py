@@ -24,33 +24,13 @@ def _libtsan():
     return path if res.returncode == 0 and os.path.isabs(path) and os.path.exists(path) else None
 
 
-@pytest.mark.skipif(_libtsan() is None, reason="libtsan.so not available")
-def test_only_the_documented_benign_races(tmp_path):
-    lib = str(tmp_path / "libat_seirm_emulated_tsan.so")
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fsanitize=thread", "-shared", "-fPIC", "-pthread",
-           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "host_emulation", "seirm_emulation.cpp"), "-o", lib]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    assert res.returncode == 0, res.stderr
-    log = str(tmp_path / "tsan")
-    env = dict(os.environ, LD_PRELOAD=_libtsan(), TSAN_OPTIONS=f"report_signal_unsafe=0 exitcode=0 history_size=2 log_path={log}")
-    run = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_emulation", "racecheck_episode.py"), lib, "tiny96_hard",
-                          "fused", "blocked", "hashed"], capture_output=True, text=True, env=env, timeout=1200)
-    assert run.returncode == 0, run.stdout + run.stderr
-    assert run.stdout.count("episode ok:") == 3
-    source = open(SOURCE).read().splitlines()
-    reports = "".join(open(p).read() for p in glob.glob(log + "*"))
-    races = re.findall(r"SUMMARY: ThreadSanitizer: data race \S*at_seirm\.cu:(\d+)", reports)
-    other = re.findall(r"SUMMARY: ThreadSanitizer: (?!data race \S*at_seirm\.cu)(.*)", reports)
-    assert not other, other                                  # nothing outside the kernel source (e.g. in the shim) either
-    not_benign = sorted({int(ln) for ln in races if "benign race" not in source[int(ln) - 1]})
-    assert not not_benign, [(ln, source[ln - 1].strip()) for ln in not_benign]
-    assert races, "ThreadSanitizer saw no thread interaction at all: the check did not run"
-
-
 def _first_source_frames(reports, source_name):
-    """For every TSan report: the source lines (in `source_name`) of the innermost frames of the two racing accesses."""
+    """For every TSan report that touches `source_name`: the source lines of the innermost frames (in that file) of the two
+    racing accesses."""
     out = []
     for report in reports.split("WARNING: ThreadSanitizer: data race")[1:]:
+        if source_name not in report:
+            continue
         lines = []
         for access in re.split(r"\n  (?:Previous )?(?:atomic )?(?:[Ww]rite|[Rr]ead) of size", report)[1:3]:
             m = re.search(re.escape(source_name) + r":(\d+)", access)
@@ -59,43 +39,74 @@ def _first_source_frames(reports, source_name):
     return out
 
 
-@pytest.mark.skipif(_libtsan() is None, reason="libtsan.so not available")
-def test_predator_prey_threads_only_meet_in_the_occupancy_marks(tmp_path):
-    lib = str(tmp_path / "libat_predprey_emulated_tsan.so")
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-shared", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "tests", "host_emulation", "pp_simt_emulation.cpp"), "-o", lib]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    assert res.returncode == 0, res.stderr
-    log = str(tmp_path / "tsan")
-    env = dict(os.environ, LD_PRELOAD=_libtsan(), TSAN_OPTIONS=f"report_signal_unsafe=0 exitcode=0 history_size=2 log_path={log}")
-    run = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_emulation", "racecheck_predprey.py"), lib],
-                         capture_output=True, text=True, env=env, timeout=1200)
-    assert run.returncode == 0, run.stdout + run.stderr
-    assert run.stdout.count("episode ok:") == 2
-    source = open(os.path.join(ROOT, "agenttorch_b200", "csrc", "at_predprey.cu")).read().splitlines()
-    reports = "".join(open(p).read() for p in glob.glob(log + "*"))
-    pairs = _first_source_frames(reports, "at_predprey.cu")
-    assert pairs, "ThreadSanitizer saw no thread interaction at all: the check did not run"
+WORKLOADS = {   # kernel source -> (emulation translation unit, extra compiler flags, driver script and its arguments)
+    "at_seirm.cu": ("seirm_emulation.cpp", ["-ffp-contract=off"], ["racecheck_episode.py", "{lib}", "tiny96_hard", "fused", "blocked", "hashed"]),
+    "at_predprey.cu": ("pp_simt_emulation.cpp", [], ["racecheck_predprey.py", "{lib}"]),
+    "at_interventions.cu": ("iv_simt_emulation.cpp", [], ["racecheck_interventions.py", "{lib}"]),
+}
+
+
+@pytest.fixture(scope="module")
+def tsan_reports(tmp_path_factory):
+    """Builds the three emulated libraries with -fsanitize=thread and runs each workload of tests/host_emulation/racecheck_*.py
+    under libtsan in its own subprocess (all three at the same time); returns {source: (stdout, reports)}."""
+    if _libtsan() is None:
+        pytest.skip("libtsan.so not available")
+    tmp = tmp_path_factory.mktemp("racecheck")
+    emu = os.path.join(ROOT, "tests", "host_emulation")
+    builds = {}
+    for source, (unit, extra, _) in WORKLOADS.items():
+        lib = str(tmp / (unit.replace(".cpp", "") + "_tsan.so"))
+        cmd = ["g++", "-O1", "-g", "-std=c++17", *extra, "-fsanitize=thread", "-Wno-tsan", "-shared", "-fPIC", "-pthread",
+               "-I", os.path.join(ROOT, "include"), os.path.join(emu, unit), "-o", lib]
+        builds[source] = (lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    runs = {}
+    for source, (lib, proc) in builds.items():
+        out, _ = proc.communicate()
+        assert proc.returncode == 0, out
+        assert "__tsan_" in subprocess.run(["nm", "-D", "--undefined-only", lib], capture_output=True, text=True).stdout
+        log = str(tmp / ("tsan_" + source))
+        env = dict(os.environ, LD_PRELOAD=_libtsan(), TSAN_OPTIONS=f"report_signal_unsafe=0 exitcode=0 history_size=2 log_path={log}")
+        script, *args = WORKLOADS[source][2]
+        runs[source] = (log, subprocess.Popen([sys.executable, os.path.join(emu, script), *[a.format(lib=lib) for a in args]],
+                                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+    results = {}
+    for source, (log, proc) in runs.items():
+        out, _ = proc.communicate(timeout=1800)
+        assert proc.returncode == 0, out
+        reports = "".join(open(p).read() for p in glob.glob(log + "*"))
+        other = re.findall(r"SUMMARY: ThreadSanitizer: (?!data race)(.*)", reports)
+        assert not other, other
+        results[source] = (out, reports)
+    return results
+
+
+def _not_benign(reports, source_name):
+    source = open(os.path.join(ROOT, "agenttorch_b200", "csrc", source_name)).read().splitlines()
+    pairs = _first_source_frames(reports, source_name)
     bad = sorted({ln for pair in pairs for ln in pair if ln is None or "benign race" not in source[ln - 1]}, key=str)
-    assert not bad, [(ln, source[ln - 1].strip() if ln else "frame outside the kernel source") for ln in bad]
+    return pairs, [(ln, source[ln - 1].strip() if ln else "frame outside the kernel source") for ln in bad]
 
 
-@pytest.mark.skipif(_libtsan() is None, reason="libtsan.so not available")
-def test_intervention_kernels_are_race_free(tmp_path):
-    """csrc/at_interventions.cu: a thread owns its 4 agents, the SEIRMS counts go through warp shuffles + atomics, the
-    epilogue runs after the launch boundary — ThreadSanitizer must report nothing at all."""
-    lib = str(tmp_path / "libat_interventions_emulated_tsan.so")
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-shared", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "tests", "host_emulation", "iv_simt_emulation.cpp"), "-o", lib]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    assert res.returncode == 0, res.stderr
-    symbols = subprocess.run(["nm", "-D", "--undefined-only", lib], capture_output=True, text=True).stdout
-    assert "__tsan_" in symbols                                  # the library really is instrumented
-    log = str(tmp_path / "tsan")
-    env = dict(os.environ, LD_PRELOAD=_libtsan(), TSAN_OPTIONS=f"report_signal_unsafe=0 exitcode=0 history_size=2 log_path={log}")
-    run = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_emulation", "racecheck_interventions.py"), lib],
-                         capture_output=True, text=True, env=env, timeout=1200)
-    assert run.returncode == 0, run.stdout + run.stderr
-    assert "episode ok: interventions" in run.stdout
-    reports = "".join(open(p).read() for p in glob.glob(log + "*"))
+def test_seirm_only_the_documented_benign_races(tsan_reports):
+    stdout, reports = tsan_reports["at_seirm.cu"]
+    assert stdout.count("episode ok: tiny96_hard") == 3                      # fused, blocked, hashed (+ backward each)
+    pairs, bad = _not_benign(reports, "at_seirm.cu")
+    assert pairs, "ThreadSanitizer saw no thread interaction at all: the check did not run"
+    assert not bad, bad
+
+
+def test_predator_prey_threads_only_meet_in_the_occupancy_marks(tsan_reports):
+    stdout, reports = tsan_reports["at_predprey.cu"]
+    assert stdout.count("episode ok: predprey") == 2
+    pairs, bad = _not_benign(reports, "at_predprey.cu")
+    assert pairs, "ThreadSanitizer saw no thread interaction at all: the check did not run"
+    assert not bad, bad
+
+
+def test_intervention_kernels_are_race_free(tsan_reports):
+    """A thread owns its 4 agents, the SEIRMS counts go through warp shuffles + atomics, the epilogue runs after the launch
+    boundary: ThreadSanitizer must report nothing at all."""
+    stdout, reports = tsan_reports["at_interventions.cu"]
+    assert "episode ok: interventions" in stdout
     assert "WARNING: ThreadSanitizer" not in reports, reports[:2000]
