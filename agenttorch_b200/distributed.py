@@ -92,8 +92,10 @@ class DistributedRunner:
                                "(launch one process per GPU with torchrun)")
         self.world_size, self.rank = world, rank
         plan = self.runner._fused_plan()
-        if plan is None:
-            raise NotImplementedError("distributed execution is implemented for the fused SEIRM path only")
+        if plan is None or plan.get("after_step") is not None:
+            # (a config with the quarantine / testing substeps has a fused single-GPU plan, but their state is not sharded here)
+            raise NotImplementedError("distributed execution is implemented for the fused SEIRM path only "
+                                      "(substeps: transmission + progression)")
         self.tr, self.pg_mod = plan["transmission"], plan["progression"]
         iv = self.tr.input_variables
         n = int(self.config["simulation_metadata"]["num_agents"])
