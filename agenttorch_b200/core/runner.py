@@ -212,7 +212,7 @@ class Runner(nn.Module):
         """Returns the modules of the SEIRM pattern if this config can run as one fused episode."""
         if getattr(self, "_plan_cache", None) is not None:
             plan = self._plan_cache
-            return plan if plan and plan["policy"].draws_uniform() else None
+            return plan if plan and self._plan_still_valid(plan) else None
         self._plan_cache = False
         try:
             from agenttorch_b200.models.covid.substeps.new_transmission.action import MakeIsolationDecision
@@ -248,7 +248,15 @@ class Runner(nn.Module):
             if after_step is None:
                 return None
         self._plan_cache = {"transmission": tr, "progression": pg, "policy": pols["make_isolation_decision"], "after_step": after_step}
-        return self._plan_cache if self._plan_cache["policy"].draws_uniform() else None
+        return self._plan_cache if self._plan_still_valid(self._plan_cache) else None
+
+    @staticmethod
+    def _plan_still_valid(plan):
+        """The parts of a cached plan a user can change between calls: an attached behaviour / injected draws."""
+        if not plan["policy"].draws_uniform():
+            return False
+        after_step = plan.get("after_step")
+        return after_step is None or getattr(after_step, "still_fusable", lambda: True)()
 
     def _step_fused(self, num_steps, plan):
         import re

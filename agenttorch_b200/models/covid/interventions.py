@@ -116,18 +116,29 @@ def plan_intervention_substeps(runner, extra_keys):
         if (exactly(obs, [("get_from_state", GetFromState)]) and exactly(trn, [("update_quarantine_status", UpdateQuarantineStatus)])
                 and sorted(pol) == ["break_compliance", "start_compliance"] and type(pol["start_compliance"]) is StartCompliance
                 and type(pol["break_compliance"]) is BreakCompliance):
-            start, brk = pol["start_compliance"], pol["break_compliance"]
-            if start.uniform is not None or brk.uniform is not None:
-                return None                                    # injected draws: only the per-substep ops take them
-            if (start.noise_seed, start.advance_seed, start.episode_index) != (brk.noise_seed, brk.advance_seed, brk.episode_index):
-                return None                                    # the fused launch draws both decisions from ONE hash per agent
-            blocks.append(("quarantine", obs["get_from_state"], start, brk, trn["update_quarantine_status"]))
+            blocks.append(("quarantine", obs["get_from_state"], pol["start_compliance"], pol["break_compliance"],
+                           trn["update_quarantine_status"]))
         elif (not obs and exactly(pol, [("accept_test", AcceptTest)]) and exactly(trn, [("update_test_status", UpdateTestStatus)])):
-            if pol["accept_test"].uniform is not None:
-                return None
             blocks.append(("testing", pol["accept_test"], trn["update_test_status"]))
         else:
             return None
+
+    def still_fusable():
+        """Conditions a user can change between calls: injected draws are only taken by the per-substep ops, and the fused
+        quarantine launch draws both decisions from ONE hash per agent, so the two policies must share their noise address."""
+        for block in blocks:
+            if block[0] == "quarantine":
+                start, brk = block[2], block[3]
+                if start.uniform is not None or brk.uniform is not None:
+                    return False
+                if (start.noise_seed, start.advance_seed, start.episode_index) != (brk.noise_seed, brk.advance_seed, brk.episode_index):
+                    return False
+            elif block[1].uniform is not None:
+                return False
+        return True
+
+    if not still_fusable():
+        return None
 
     def make_hook(state):
         calls = []
@@ -164,4 +175,5 @@ def plan_intervention_substeps(runner, extra_keys):
         hook.launches_per_step = len(calls)
         return hook
 
+    make_hook.still_fusable = still_fusable
     return make_hook

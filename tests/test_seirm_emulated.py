@@ -254,12 +254,13 @@ def test_fused_episode_with_intervention_substeps_on_host(engine_on_host, emulat
     before = cit["is_quarantined"].clone()
     runner.step(2)
     assert not torch.equal(before, runner.state["agents"]["citizens"]["is_quarantined"]) or name.endswith("default")
-    # substeps of another kind, or injected draws, are not fused
+    # injected draws or policies with different noise addresses are not fused — also when that changes after planning
+    assert runner._plan_still_valid(plan)
     pf["3"]["citizens"]["accept_test"].uniform = lambda t: None
-    assert plan_intervention_substeps(runner, ["2", "3"]) is None
+    assert plan_intervention_substeps(runner, ["2", "3"]) is None and not runner._plan_still_valid(plan)
     pf["3"]["citizens"]["accept_test"].uniform = None
     pf["2"]["citizens"]["break_compliance"].noise_seed += 1
-    assert plan_intervention_substeps(runner, ["2", "3"]) is None
+    assert plan_intervention_substeps(runner, ["2", "3"]) is None and not runner._plan_still_valid(plan)
 
 
 # ------------------------------------------------------------------------------------------------------------------
