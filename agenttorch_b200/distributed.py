@@ -35,7 +35,12 @@ class _EpisodeFn(torch.autograd.Function):
     def forward(ctx, runner, r_steps, m_value, num_steps, want_grad):
         eng, st = runner.engine, runner.local_state
         noise = NoiseSpec(seed=runner.episode_seed(), isolation="soft")
-        sv = eng.run_episode(st, r_steps, m_value, num_steps, noise, want_grad=want_grad, cuda_graph=eng.code_hdl is not None)
+        factory = getattr(runner, "_after_step_factory", None)
+        eng.after_step = factory(runner.state) if factory is not None else None      # episodes with a hook are issued eagerly
+        try:
+            sv = eng.run_episode(st, r_steps, m_value, num_steps, noise, want_grad=want_grad, cuda_graph=eng.code_hdl is not None)
+        finally:
+            eng.after_step = None
         if eng.pg is not None:
             from .parallel import reduce_daily_series
 
@@ -68,6 +73,7 @@ class DistributedRunner:
         self.pg = process_group
         self.engine = None
         self.local_state = None
+        self._after_step_factory = None
         self.state = None
         self.state_trajectory = []
         self._episode = 0
@@ -92,10 +98,12 @@ class DistributedRunner:
                                "(launch one process per GPU with torchrun)")
         self.world_size, self.rank = world, rank
         plan = self.runner._fused_plan()
-        if plan is None or plan.get("after_step") is not None:
-            # (a config with the quarantine / testing substeps has a fused single-GPU plan, but their state is not sharded here)
-            raise NotImplementedError("distributed execution is implemented for the fused SEIRM path only "
-                                      "(substeps: transmission + progression)")
+        if plan is None:
+            raise NotImplementedError("distributed execution is implemented for the fused SEIRM path only (transmission + "
+                                      "progression, optionally followed by this package's quarantine / testing substeps)")
+        # quarantine / testing substeps ride along: per-agent state, sliced like every agent tensor below, draws addressed by
+        # the GLOBAL agent id (id_offset = first owned agent), one in-place launch per block after every step
+        self._after_step_factory = plan.get("after_step")
         self.tr, self.pg_mod = plan["transmission"], plan["progression"]
         iv = self.tr.input_variables
         n = int(self.config["simulation_metadata"]["num_agents"])
@@ -131,6 +139,10 @@ class DistributedRunner:
         cit["disease_stage"] = self.local_state.stage.view(-1, 1)
         cit["next_stage_time"] = self.local_state.next_stage_time.view(-1, 1)
         cit["infected_time"] = self.local_state.infected_time.view(-1, 1)
+        if self._after_step_factory is not None:
+            for _, mod in self.runner._noise_modules():
+                if hasattr(mod, "id_offset"):
+                    mod.id_offset = r0
         self.config["simulation_metadata"]["local_num_agents"] = r1 - r0
         self.state = full
         self.state_trajectory = [[{"current_step": 0, "current_substep": "0", "environment": dict(full["environment"])}]]

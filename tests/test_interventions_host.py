@@ -166,19 +166,3 @@ def test_scalar_cache_follows_replacement_and_in_place_edits():
     assert n.episode_seed(3) == s1 and n.episode_seed(0) != s1          # one stream per episode
     n.advance_seed = False
     assert n.episode_seed(0) == 5 and -(1 << 63) <= s1 < (1 << 63)
-
-
-def test_distributed_runner_refuses_configs_with_intervention_substeps(monkeypatch):
-    """The sharded runner only knows the two SEIRM substeps: a config whose fused plan carries the quarantine / testing hook
-    must be refused, not run without them."""
-    from agenttorch_b200.core.runner import Runner
-    from agenttorch_b200.distributed import DistributedRunner
-    from agenttorch_b200.models import covid
-    from agenttorch_b200.models.covid.interventions import add_intervention_substeps
-    from agenttorch_b200.models.covid.synthetic import synthetic_config
-
-    runner = Runner(add_intervention_substeps(synthetic_config(256, 4.0, device="cpu")), covid.get_registry())
-    monkeypatch.setattr(Runner, "_fused_plan", lambda self: {"transmission": None, "progression": None, "policy": None,
-                                                              "after_step": lambda state: None})
-    with pytest.raises(NotImplementedError, match="transmission \\+ progression"):
-        DistributedRunner(runner).init()

@@ -238,3 +238,106 @@ def test_distributed_runner_api_on_two_emulated_ranks(emulated_library, tmp_path
         assert tuple(o["dd"].shape) == (1, g["num_steps"])
         assert rel_err(g["ref_daily_infected"], o["di"].numpy()) <= 1e-5 and rel_err(g["ref_daily_deaths"], o["dd"].numpy()) <= 1e-5
         assert rel_err(g["ref_grad_R2"], o["gr2"].numpy()) <= 1e-4 and rel_err(g["ref_grad_M"], o["gm"].numpy()) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# A config WITH the quarantine / testing substeps on two emulated ranks: their per-agent state is sharded like every agent
+# tensor, the draws are addressed by the global agent id, one in-place launch per block after every step on every rank.
+def _distributed_interventions(rank, world, port, out_dir, seirm_lib, iv_lib, pop_dir, tag):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from agenttorch_b200 import _native, _native_iv, distributed, engine
+    from agenttorch_b200 import interventions as iv_ops
+    from agenttorch_b200.core.dataloader import DataLoader, LoadPopulation
+    from agenttorch_b200.core.runner import Runner
+    from agenttorch_b200.models import covid
+    from agenttorch_b200.models.covid import context
+    from agenttorch_b200.models.covid.interventions import add_intervention_substeps
+    from tests.helpers import load_interventions_golden
+
+    _native.LIB_PATH, _native._lib = seirm_lib, None
+    _native_iv.LIB_PATH, _native_iv._lib = iv_lib, None
+    no_check = lambda *args: None                                                # noqa: E731
+    engine._require_cuda = context._require_cuda = distributed._require_cuda = iv_ops._require_cuda = no_check
+    iv_ops._stream = lambda t: None
+    torch.cuda.device = lambda device: contextlib.nullcontext()
+    torch.cuda.current_stream = lambda device=None: types.SimpleNamespace(cuda_stream=0)
+    torch.cuda.synchronize = lambda device=None: None
+    torch.set_num_threads(1)
+    real_engine = engine.SeirmEngine
+    distributed.SeirmEngine = lambda graph, spec, **kw: real_engine(graph, spec, warps_per_cta=2, **kw)
+    real_plan = Runner._fused_plan
+
+    def plan_as_if_on_cuda(self):
+        real_device = self.initializer.device
+        self.initializer.device = types.SimpleNamespace(type="cuda")
+        try:
+            return real_plan(self)
+        finally:
+            self.initializer.device = real_device
+
+    Runner._fused_plan = plan_as_if_on_cuda
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    symm = _SharedSymmetricMemory(tag, rank, world)
+    sys.modules["torch.distributed._symmetric_memory"] = symm
+    torch.distributed._symmetric_memory = symm
+    try:
+        g = load_interventions_golden("interventions_1500_softopen")
+        ov = g["overrides"]
+        loader = DataLoader(covid, LoadPopulation(pop_dir))
+        for k, v in ov["meta"].items():
+            loader.set_config_attribute(k, v)
+        loader.set_config_attribute("noise_seed", g["seed"])
+        for k, v in ov["initial"].items():
+            loader.config["state"]["agents"]["citizens"]["properties"][k]["value"] = v
+        for k, v in ov["env"].items():
+            loader.config["state"]["environment"][k]["value"] = v
+        runner = distributed.DistributedRunner(Runner(add_intervention_substeps(loader.get_config()), covid.get_registry()), world_size=world)
+        runner.init()
+        pf = runner.initializer.policy_function
+        for mod in (runner.tr, pf["2"]["citizens"]["start_compliance"], pf["2"]["citizens"]["break_compliance"], pf["3"]["citizens"]["accept_test"]):
+            mod.advance_seed = False
+        assert pf["3"]["citizens"]["accept_test"].id_offset == runner.agent_partition_map["start_idx"]
+        r2 = torch.tensor(g["r2"], dtype=torch.float32, requires_grad=True)
+        m = torch.tensor(g["m"], dtype=torch.float32, requires_grad=True)
+        runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": r2,
+                                "initializer.transition_function.1.seirm_progression.learnable_args.M": m})
+        runner.step(g["num_steps"])
+        env = runner.state_trajectory[-1][-1]["environment"]
+        loss = (torch.from_numpy(g["gI"]) * env["daily_infected"].reshape(-1)).sum() + \
+               (torch.from_numpy(g["gD"]) * env["daily_deaths"].reshape(-1)).sum()
+        loss.backward()
+        final = runner.gather_final_state()
+        out = {k: v.detach() for k, v in final.items()}
+        out.update(di=env["daily_infected"].detach(), dd=env["daily_deaths"].detach(), gr2=r2.grad, gm=m.grad)
+        torch.save(out, os.path.join(out_dir, f"iv{rank}.pt"))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+        symm.cleanup()
+
+
+def test_intervention_substeps_on_two_emulated_ranks(emulated_library, tmp_path):
+    import torch.multiprocessing as mp
+
+    from agenttorch_b200.populations import write_population_folder
+    from tests.helpers import load_interventions_golden, rel_err
+
+    iv_lib = str(tmp_path / "libat_interventions_emulated.so")
+    res = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                          os.path.join(ROOT, "tests", "host_emulation", "iv_emulation.cpp"), "-o", iv_lib], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    g = load_interventions_golden("interventions_1500_softopen")
+    pop = write_population_folder(str(tmp_path / "pop"), g["age"], g["stage0"], g["edges"])
+    mp.spawn(_distributed_interventions, args=(2, _free_port(), str(tmp_path), emulated_library, iv_lib, pop, f"{os.getpid()}_iv"),
+             nprocs=2, join=True)
+    T = g["num_steps"]
+    for r in range(2):
+        o = torch.load(os.path.join(str(tmp_path), f"iv{r}.pt"))
+        for k in ("disease_stage", "next_stage_time", "is_quarantined", "quarantine_start_date", "awaiting_test_result",
+                  "test_result_date", "test_re_eligble_date"):
+            assert np.array_equal(o[k].numpy().reshape(-1).astype(np.float64), g["ref_" + k + "_history"][T - 1].astype(np.float64)), k
+        assert rel_err(g["ref_daily_infected"], o["di"].numpy()) <= 1e-5 and rel_err(g["ref_daily_deaths"], o["dd"].numpy()) <= 1e-5
+        assert rel_err(g["ref_grad_R2"], o["gr2"].numpy()) <= 1e-4 and rel_err(g["ref_grad_M"], o["gm"].numpy()) <= 1e-4
