@@ -168,15 +168,16 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     __shared__ int s_any_hot, s_any_out;
     if (tid == 0) { s_any_hot = 0; s_any_out = 0; }
     // ---- tables: code -> (SFInfector[int(stage)], lam_gamma[idx]); code = 1 + sidx*K + idx
-    if (tid < 256) {
+    // (strided: a CTA may have fewer than 256 threads — few warps next to a large bitmap, or warps_per_cta set by the caller)
+    for (int c = tid; c < 256; c += blockDim.x) {
         float av = 0.f, gv = 0.f;
-        if (tid >= 1 && tid <= 3 * m.n_lg) {
-            const int sidx = (tid - 1) / m.n_lg, idx = (tid - 1) % m.n_lg;
+        if (c >= 1 && c <= 3 * m.n_lg) {
+            const int sidx = (c - 1) / m.n_lg, idx = (c - 1) % m.n_lg;
             av = sidx < m.n_sfi ? m.sfi[sidx] : 0.f;
             gv = m.lg[idx];
         }
-        s_A[tid] = av;
-        s_G[tid] = gv;
+        s_A[c] = av;
+        s_G[c] = gv;
     }
     __syncthreads();
     unsigned char* wsm = smem_raw + warp * WSM;

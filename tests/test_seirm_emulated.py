@@ -49,7 +49,8 @@ def _episode(g, *, packed=True, tensor_noise=False, **engine_kw):
     age = torch.from_numpy(g["age"].astype(np.int64))
     edges = torch.from_numpy(g["edges"].astype(np.int64)).t().contiguous()
     graph = build_contact_graph(edges, n, mean_interactions=mean_interactions_from_age(age))
-    eng = SeirmEngine(graph, SeirmSpec(num_steps=T), warps_per_cta=2, **engine_kw)          # 64 OS threads per block
+    engine_kw.setdefault("warps_per_cta", 2)                                                # 64 OS threads per block
+    eng = SeirmEngine(graph, SeirmSpec(num_steps=T), **engine_kw)
     st = SeirmState.from_initial(g["stage0"].astype(np.float32), g["age"], T, torch.device("cpu"), packed=packed)
     if tensor_noise:
         U, W = make_noise(g["seed"], g["mode"], n, T, float(g["p_isolate"]))
@@ -85,6 +86,8 @@ def _check(g, st, grad_r2, grad_m):
     ("synth3k_hard", dict()),
     ("synth3k_soft", dict(block_size=1024)),                         # column blocks: gather + update kernels
     ("synth3k_r2vec", dict(hashed=True, hash_words=32)),             # hashed filter + hot_fold_kernel
+    ("tiny96_hard", dict(warps_per_cta=1)),                          # a CTA smaller than the code tables (found by tools/fuzz_emulated.py)
+    ("noiso500", dict(warps_per_cta=1, hashed=True, hash_words=32)),
 ])
 def test_kernel_source_matches_reference_golden(engine_on_host, case, kw):
     g = load_golden(case)
