@@ -167,6 +167,14 @@ class SeirmEngine:
         n_src = graph.n_sources if code_len is None else int(code_len)
         if code_len is not None and (code_len < graph.n_sources or code_len % 1024):
             raise ValueError("code_len must cover all sources and be a multiple of 1024")
+        if process_group is not None and code_len is not None:
+            import torch.distributed as dist
+
+            world = dist.get_world_size(process_group)
+            if graph.n_sources <= (world - 1) * (int(code_len) // world):
+                # every rank sees the same numbers, so every rank raises (no rank is left waiting in a rendezvous)
+                raise ValueError(f"{graph.n_sources} agents leave a rank without agents: ownership ranges are aligned to 1024, "
+                                 f"so {world} ranks need more than {(world - 1) * (int(code_len) // world)} agents")
         def capacity(epc, warps):
             with torch.cuda.device(self.device):
                 return int(self.lib.at_seirm_max_block_size(len(spec.sfs), len(spec.lam_gamma), int(epc), int(warps)))

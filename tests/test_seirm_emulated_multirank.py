@@ -21,7 +21,10 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-N, DEG, T, SEED = 4096, 6.0, 21, 5
+# (overridable through the environment by tools/fuzz_emulated_multirank.py; spawned workers re-import this module)
+N, DEG, T, SEED = int(os.environ.get("AT_EMU_N", 4096)), float(os.environ.get("AT_EMU_DEG", 6.0)), 21, int(os.environ.get("AT_EMU_SEED", 5))
+R_VALUE, EXPOSED0 = float(os.environ.get("AT_EMU_R", 9.0)), float(os.environ.get("AT_EMU_EXPOSED", 0.03))
+ISOLATION, HASHED = os.environ.get("AT_EMU_ISOLATION", "hard"), os.environ.get("AT_EMU_HASHED", "0") == "1"
 
 
 def _free_port():
@@ -104,18 +107,18 @@ def _episode(rank, world, port, out_dir, lib_path, exchange, tag):
     try:
         bounds = shard_bounds(N, world)
         r0, r1 = bounds[rank]
-        age, stage0 = synthetic_population(N, SEED, initial_exposed=0.03, device="cpu")
+        age, stage0 = synthetic_population(N, SEED, initial_exposed=EXPOSED0, device="cpu")
         full = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", mean_interactions=mean_interactions_from_age(age))
         graph = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", row_begin=r0, row_end=r1)
         graph.i_bar, graph.i_bar_agent = full.i_bar, full.i_bar_agent
         eng = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=shard_code_len(N, world), warps_per_cta=2,
                           symmetric=(exchange != "allgather") if world > 1 else None, sparse_exchange=exchange == "sparse",
-                          hashed=True if exchange == "sparse_hashed" else None, hash_words=32 if exchange == "sparse_hashed" else None)
+                          hashed=True if HASHED else None, hash_words=32 if HASHED else None)
         if world > 1:
             assert (eng.code_hdl is not None) == (exchange != "allgather")
         st = SeirmState.from_initial(stage0[r0:r1], age[r0:r1], T, torch.device("cpu"))
-        r_steps, m = torch.full((T,), 9.0), torch.tensor([0.12])
-        sv = eng.run_episode(st, r_steps, m, T, NoiseSpec(seed=9, isolation="hard"), want_grad=True, cuda_graph=False)
+        r_steps, m = torch.full((T,), R_VALUE), torch.tensor([0.12])
+        sv = eng.run_episode(st, r_steps, m, T, NoiseSpec(seed=9, isolation=ISOLATION), want_grad=True, cuda_graph=False)
         di, dd = st.daily_infected.clone(), st.daily_deaths.clone()
         if world > 1:
             dist.all_reduce(di); dist.all_reduce(dd)
@@ -341,3 +344,35 @@ def test_intervention_substeps_on_two_emulated_ranks(emulated_library, tmp_path)
             assert np.array_equal(o[k].numpy().reshape(-1).astype(np.float64), g["ref_" + k + "_history"][T - 1].astype(np.float64)), k
         assert rel_err(g["ref_daily_infected"], o["di"].numpy()) <= 1e-5 and rel_err(g["ref_daily_deaths"], o["dd"].numpy()) <= 1e-5
         assert rel_err(g["ref_grad_R2"], o["gr2"].numpy()) <= 1e-4 and rel_err(g["ref_grad_M"], o["gm"].numpy()) <= 1e-4
+
+
+def test_a_rank_without_agents_is_refused_on_every_rank():
+    """shard_bounds aligns the ownership ranges to 1024 agents: 2048 agents on 4 ranks would leave two ranks empty, and the
+    others waiting for them in every rendezvous.  The engine refuses up front, from numbers every rank sees."""
+    import torch.distributed as dist
+
+    from agenttorch_b200 import engine as eng_mod
+    from agenttorch_b200.engine import SeirmEngine, SeirmSpec
+    from agenttorch_b200.graph import shard_bounds, shard_code_len, synthetic_contact_graph
+
+    port = _free_port()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        class FourRanks:                                           # stands in for a 4-rank group: only its size is consulted
+            pass
+
+        real = dist.get_world_size
+        dist.get_world_size = lambda group=None: 4 if isinstance(group, FourRanks) else real(group)
+        real_check = eng_mod._require_cuda
+        eng_mod._require_cuda = lambda message, is_cuda: None
+        try:
+            assert shard_bounds(2048, 4)[2] == (2048, 2048)
+            graph = synthetic_contact_graph(2048, 4.0, 1, device="cpu", row_begin=0, row_end=1024)
+            with pytest.raises(ValueError, match="without agents"):
+                SeirmEngine(graph, SeirmSpec(), process_group=FourRanks(), code_len=shard_code_len(2048, 4))
+        finally:
+            dist.get_world_size = real
+            eng_mod._require_cuda = real_check
+    finally:
+        dist.destroy_process_group()
