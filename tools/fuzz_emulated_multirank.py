@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Differential fuzzing of the SHARDED SEIRM engine WITHOUT a GPU: random population sizes, degrees, epidemic strengths (from
 epidemics that die out at once to ones that reach everybody), isolation modes, exact / hashed filters, 2-4 emulated ranks and
-the three halo-exchange paths — every run must reproduce the one-rank result bit for bit (tests/test_seirm_emulated_multirank.py
+the three halo-exchange paths — every run must reproduce the one-rank stages and timers bit for bit and the daily series /
+gradients to 1e-6 (each rank rounds its partial sums to float32 before the all-reduce) (tests/test_seirm_emulated_multirank.py
 is the harness; one OS process per rank, gloo, POSIX shared memory standing in for symmetric memory).
 
     python tools/fuzz_emulated_multirank.py [--cases 12] [--seed 0]
@@ -42,7 +43,7 @@ def main():
                 f"mp.spawn(M._episode, args=({world}, M._free_port(), out, lib, {exchange!r}, 'fz' + str(os.getpid())), nprocs={world}, join=True)\n"
                 f"one = torch.load(os.path.join(out, 'single_w1_r0.pt'))\n"
                 f"parts = [torch.load(os.path.join(out, '{exchange}_w{world}_r%d.pt' % r)) for r in range({world})]\n"
-                f"ok = all(torch.equal(torch.cat([p[k] for p in parts]), one[k]) for k in ('stage', 'nst', 'itime')) and torch.equal(parts[0]['di'], one['di'])\n"
+                f"ok = all(torch.equal(torch.cat([p[k] for p in parts]), one[k]) for k in ('stage', 'nst', 'itime')) and np.allclose(parts[0]['di'].numpy(), one['di'].numpy(), rtol=1e-6, atol=0)\n"
                 f"ok = ok and np.allclose(parts[0]['gr'].numpy(), one['gr'].numpy(), rtol=1e-6) and np.allclose(parts[0]['dd'].numpy(), one['dd'].numpy(), rtol=1e-6)\n"
                 f"print('RESULT', ok, float(one['di'].sum()))\n")
         res = subprocess.run([sys.executable, "-c", code, LIB], capture_output=True, text=True, env=env, timeout=1200)
