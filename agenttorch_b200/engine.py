@@ -274,7 +274,7 @@ class SeirmEngine:
     def launch(self, state: SeirmState, *, flags, t, t_encode=None, code_in=None, code_out=None,
                noise: Optional[NoiseSpec] = None, isolation=None, uniform=None, r_value=None, r_index=0,
                m_value=None, dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None,
-               seed_ptr=None):
+               seed_ptr=None, check_range=True):
         g = self.graph
         a = nat.SeirmLaunch()
         a.abi_version = nat.ABI_VERSION
@@ -329,7 +329,9 @@ class SeirmEngine:
         a.recovered_step = _ptr(recovered_step, torch.uint8, "recovered_step")
         a.lam_part, a.lam1_part, a.dirty = _ptr(self.lam_part), _ptr(self.lam1_part), _ptr(self.dirty)
         a.workspace = _ptr(self.workspace, torch.float64)
-        a.error_flag = _ptr(self.error_flag, torch.int32)
+        # check_range=False: the launch encodes the infectiousness of a step that is never simulated (the last step of an
+        # episode), so an infection older than lam_gamma_integrals there is not an error — the reference never looks it up
+        a.error_flag = _ptr(self.error_flag, torch.int32) if check_range else None
         a.grid = int(self.grid)
         a.tasks_per_group = int(self.tasks_per_group)
         a.warps_per_cta = int(self.warps_per_cta)
@@ -402,12 +404,12 @@ class SeirmEngine:
         self.exchange(self.cur)
 
     def step(self, state, t, noise, r_value, r_index, m_value, *, isolation=None, uniform=None, flags=None,
-             dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None, seed_ptr=None):
+             dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None, seed_ptr=None, check_range=True):
         """One fused step: transmission + progression + encode of step t+1; flips the live buffer."""
         flags = (nat.DO_TRANSMISSION | nat.DO_PROGRESSION | nat.DO_ENCODE) if flags is None else flags
         self.launch(state, flags=flags, t=t, t_encode=t + 1, noise=noise, isolation=isolation, uniform=uniform,
                     r_value=r_value, r_index=r_index, m_value=m_value, dne_dr=dne_dr, sum_dne_dr=sum_dne_dr,
-                    death_count=death_count, recovered_step=recovered_step, seed_ptr=seed_ptr)
+                    death_count=death_count, recovered_step=recovered_step, seed_ptr=seed_ptr, check_range=check_range)
         if flags & nat.DO_ENCODE:
             self.cur = 1 - self.cur
             self.exchange(self.cur)
@@ -460,7 +462,8 @@ class SeirmEngine:
                 uni = noise.uniform_tensor[k] if noise.uniform == "tensor" else None
                 self.step(state, t, noise, sv["r_steps"], k, sv["m_value"], isolation=iso, uniform=uni,
                           dne_dr=sv["dne_dr"][k] if want_grad else None, sum_dne_dr=sv["sum_dne_dr"],
-                          death_count=sv["death_count"], recovered_step=sv["recovered_step"], seed_ptr=self.seed_buf)
+                          death_count=sv["death_count"], recovered_step=sv["recovered_step"], seed_ptr=self.seed_buf,
+                          check_range=k + 1 < num_steps)
                 plan.append((*self._recording[-1], True))
                 if self.after_step is not None:
                     self.after_step(t)

@@ -401,3 +401,36 @@ def test_checkpoint_and_resume_reproduce_the_next_episode(engine_on_host, monkey
     assert float(want_env["daily_infected"].sum()) != float(torch.tensor(g["ref_daily_infected"]).sum())   # a different stream than episode 1
     with pytest.raises(ValueError, match="format"):
         b.load_checkpoint({"format": 99})
+
+
+def test_infection_older_than_the_table_only_at_the_unused_last_encode(engine_on_host):
+    """12-step episode, 12 days of infectiousness: agents exposed at the start are still infectious when the episode ends, and
+    their age at step 12 — which is never simulated — is past lam_gamma_integrals.  The reference never looks that entry up; the
+    engine used to refuse (the last step encodes the next step's infectiousness).  Found by tools/fuzz_emulated.py."""
+    from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
+    from agenttorch_b200.graph import build_contact_graph, mean_interactions_from_age
+    from oracle.seirm_port import SeirmConstants, SeirmPort, episode_with_grads
+
+    T = 12
+    age, stage0, edges = _synthetic(600, 8.0, 12, frac_e=0.1, frac_i=0.0)
+    consts = SeirmConstants(num_steps=T, num_weeks=2, exposed_to_infected_time=5, infected_to_recovered_time=12)
+    r2, m = np.array([[1.5], [0.8]], dtype=np.float32), np.array([0.3], dtype=np.float32)
+    U, W = make_noise(3, "hard", len(age), T)
+    gI, gD = np.linspace(0.5, 1.5, T, dtype=np.float32), np.linspace(2.0, 1.0, T, dtype=np.float32)
+    ref = episode_with_grads(SeirmPort(age, stage0, edges, consts=consts), W, U, gI, gD, r2=r2, m=m, num_steps=T)
+    graph = build_contact_graph(torch.from_numpy(edges).t().contiguous(), len(age),
+                                mean_interactions=mean_interactions_from_age(torch.from_numpy(age)))
+    eng = SeirmEngine(graph, SeirmSpec(num_steps=T, infected_to_recovered_time=12), warps_per_cta=2)
+    st = SeirmState.from_initial(stage0.astype(np.float32), age, T, torch.device("cpu"))
+    r2_t = torch.tensor(r2, requires_grad=True)
+    r_steps = torch.stack([(r2_t * torch.eye(2)[int(t / 7)]).sum() for t in range(T)])
+    sv = eng.run_episode(st, r_steps.detach(), torch.tensor(m), T, NoiseSpec(seed=3, isolation="hard"), want_grad=True)
+    eng.check_errors()                                              # no refusal
+    assert np.array_equal(st.stage.numpy().astype(np.float64), ref["stage"]) and float(ref["daily_infected"].sum()) > 20
+    assert rel_err(ref["daily_infected"], st.daily_infected.numpy()) <= 1e-5
+    # an infection older than the table INSIDE the episode is still refused
+    st2 = SeirmState.from_initial(stage0.astype(np.float32), age, T, torch.device("cpu"))
+    st2.infected_time.fill_(-9)
+    eng.run_episode(st2, r_steps.detach(), torch.tensor(m), T, NoiseSpec(seed=3, isolation="hard"), want_grad=False)
+    with pytest.raises(RuntimeError, match="lam_gamma_integrals index out of range"):
+        eng.check_errors()

@@ -146,11 +146,6 @@ def main():
         try:
             problems, infected = run_case(c)
         except Exception as exc:                                    # refusals (e.g. too many in-edges per block) are reported too
-            if "lam_gamma_integrals index out of range" in str(exc):
-                # known limit: an agent still infectious when the episode ends, older than the table at
-                # step T, makes the engine refuse although the reference never evaluates step T
-                print(f"[{i}] refused (known limit: infectiousness older than lam_gamma_integrals at the end of the episode)  {desc}", flush=True)
-                continue
             problems, infected = [f"{type(exc).__name__}: {exc}"], -1.0
         if problems is None:
             print(f"[{i}] skipped: the reference raises IndexError on this input  {desc}", flush=True)
