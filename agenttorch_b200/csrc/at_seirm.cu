@@ -729,6 +729,259 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     }
 }
 
+// ------------------------------------------------------------------------------- packed-layout gather
+// AT_LAYOUT_PACKED: the gather for source sets larger than one shared-memory bitmap.  Sources are split in column
+// blocks; CTA c keeps the EXACT hot bitmap of block c % n_blocks in shared memory and streams that block's segments
+// (one per row tile) with per-warp double-buffered TMA bulk copies.  Every 32-bit entry carries its row
+// ((row_in_tile << 21) | source), so a segment is a flat stream: lane L tests its RL consecutive entries against the
+// bitmap (one LDS per edge), and only TRUE hits of SUSCEPTIBLE rows are compacted (edge order) and looked at again:
+// code byte from the L2-resident code array, destination age, table term, and an in-order segmented sum over the
+// hits of the same row (rows are contiguous in a segment).  Per-(block,row) partial lambdas go to lam_part / dirty,
+// which MODE_UPDATE folds in block order.  No atomics on floating point, static schedule: deterministic.
+__host__ __device__ constexpr int packed_warp_smem_bytes(int cap) { return 2 * cap * 4 + cap * 2 + 64 * 4 + 64 * 4 + 64; }
+
+template <int RL4>
+__global__ void __launch_bounds__(NT_MAX, 1)
+gather_packed_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const int NC, const int tile_shift)
+{
+    constexpr int RL = 4 * RL4, CAP = 32 * RL, WSM = packed_warp_smem_bytes(CAP);
+    constexpr uint32_t SRC_MASK = (1u << AT_PACKED_SRC_BITS) - 1u;
+    AT_DYNAMIC_SMEM(unsigned char, smem_raw, 128);
+    const int nw = blockDim.x >> 5;
+    // [per-warp areas][Tdiv f64 n_sfs*NC][T1div f64 n_sfs*NC][s_A f32 256][s_G f32 256][hot bitmap of this CTA's block]
+    double* s_T = reinterpret_cast<double*>(smem_raw + nw * WSM);
+    double* s_T1 = s_T + m.n_sfs * NC;
+    float* s_A = reinterpret_cast<float*>(s_T1 + m.n_sfs * NC);
+    float* s_G = s_A + 256;
+    const unsigned char* s_bm = reinterpret_cast<const unsigned char*>(s_G + 256);
+    __shared__ int s_any_hot_p;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool want_grad = a.dne_dr != nullptr;
+    const bool age_f32 = a.age_dtype == AT_AGE_F32;
+    const int block = (int)(blockIdx.x % a.n_blocks);
+    const float R = a.r_value[a.r_index];
+    const double ibar = (double)m.ibar;
+    if (tid == 0) s_any_hot_p = 0;
+    for (int c = tid; c < 256; c += blockDim.x) {
+        float av = 0.f, gv = 0.f;
+        if (c >= 1 && c <= 3 * m.n_lg) {
+            const int sidx = (c - 1) / m.n_lg, idx = (c - 1) % m.n_lg;
+            av = sidx < m.n_sfi ? m.sfi[sidx] : 0.f;
+            gv = m.lg[idx];
+        }
+        s_A[c] = av;
+        s_G[c] = gv;
+    }
+    __syncthreads();
+    unsigned char* wsm = smem_raw + warp * WSM;
+    int32_t* s_col = reinterpret_cast<int32_t*>(wsm);
+    uint16_t* s_pos = reinterpret_cast<uint16_t*>(wsm + 2 * CAP * 4);                 // [CAP] positions of the hits, edge order
+    uint32_t* s_dirty = reinterpret_cast<uint32_t*>(wsm + 2 * CAP * 4 + CAP * 2);     // [64] rows of the tile with a partial
+    uint32_t* s_sus = s_dirty + 64;                                                   // [64] susceptible rows of the tile
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sus + 64);
+    for (int i = tid; i < m.n_sfs * NC; i += blockDim.x) {
+        const int ag = i / NC, c = i % NC;
+        const float s = m.sfs[ag];
+        const float av = c < 256 ? s_A[c] : 0.f, gv = c < 256 ? s_G[c] : 0.f;
+        s_T[i] = (double)__fmul_rn(__fmul_rn(__fmul_rn(R, s), av), gv) / ibar;
+        s_T1[i] = (double)__fmul_rn(__fmul_rn(s, av), gv) / ibar;
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.hot_bitmap_in + (size_t)block * (a.block_size >> 5));
+        uint4* dst = reinterpret_cast<uint4*>(const_cast<unsigned char*>(s_bm));
+        uint32_t seen = 0;
+        for (int i = tid; i < (bm_words >> 2); i += blockDim.x) {
+            const uint4 v = __ldg(src + i);
+            dst[i] = v;
+            seen |= v.x | v.y | v.z | v.w;
+        }
+        if (seen != 0u) s_any_hot_p = 1;                     // benign race: every writer stores 1
+        if (lane == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+        fence_mbarrier_init();
+    }
+    for (int i = lane; i < 2 * CAP; i += 32) s_col[i] = 0;
+    fence_proxy_async_smem();
+    __syncthreads();
+    const bool any_hot = s_any_hot_p != 0;
+
+    const int TILE = 1 << tile_shift, wpt = TILE >> 5;                       // rows / bitmap words per tile (wpt <= 64)
+    const int n_tiles = (int)(a.n_rows_pad >> tile_shift);
+    const int ntasks32 = (int)(a.n_rows_pad >> 5);
+    const int2* seg_b = reinterpret_cast<const int2*>(a.seg_info) + (size_t)block * n_tiles;
+    const uint8_t* code_b = a.code_in + (size_t)block * a.block_size;
+    double2* part_b = reinterpret_cast<double2*>(a.lam_part) + (size_t)block * a.n_rows_pad;
+    uint32_t* dirty_b = a.dirty + (size_t)block * ntasks32;
+    const int ctas_b = ((int)gridDim.x - block + a.n_blocks - 1) / a.n_blocks;      // CTAs serving this block
+    const int first = ((int)blockIdx.x / a.n_blocks) * nw + warp, stride = ctas_b * nw;
+
+    // segment metadata, prefetched two tiles ahead (raw = loads in flight, finalised one iteration later)
+    struct Seg { int base4, len; uint32_t sus0, sus1; };
+    auto load_seg = [&](int tile) -> Seg {
+        Seg r; r.base4 = 0; r.len = 0; r.sus0 = 0; r.sus1 = 0;
+        if (tile < n_tiles) {
+            const int2 sg = seg_b[tile];
+            r.base4 = sg.x; r.len = sg.y;
+            const uint32_t* sw = a.sus_bitmap + (size_t)tile * wpt;
+            if (lane < wpt) r.sus0 = sw[lane];
+            if (lane + 32 < wpt) r.sus1 = sw[lane + 32];
+        }
+        return r;
+    };
+    auto finalize = [&](Seg r) -> Seg {
+        // no infectious source in this column block, or no susceptible row in the tile: nothing to stream
+        if (!any_hot || !__any_sync(0xffffffffu, (r.sus0 | r.sus1) != 0u)) r.len = 0;
+        return r;
+    };
+    uint32_t issued = 0, consumed = 0;                        // chunks of this warp; chunk k lives in slot k & 1
+    auto issue_chunk = [&](int base4, int len, int ci) {
+        if (lane == 0) {
+            const uint32_t slot = issued & 1u;
+            const int off = ci * CAP;
+            const uint32_t bytes = (uint32_t)((min(CAP, len - off) + 3) & ~3) * 4u;
+            mbar_expect_tx(&s_bar[slot], bytes);
+            bulk_g2s(s_col + slot * CAP, a.col + ((int64_t)base4 * 4 + off), bytes, &s_bar[slot]);
+        }
+        ++issued;
+    };
+
+    Seg g0 = finalize(load_seg(first)), g1 = finalize(load_seg(first + stride));
+    Seg raw = load_seg(first + 2 * stride);
+    bool first_issued = false;                                // chunk 0 of g0 is already in flight
+    for (int tile = first; tile < n_tiles; tile += stride) {
+        const Seg sg = g0;
+        g0 = g1;
+        g1 = finalize(raw);
+        raw = load_seg(tile + 3 * stride);
+        uint32_t* dirty_t = dirty_b + (size_t)tile * wpt;
+        if (sg.len == 0) {
+            if (lane < wpt) dirty_t[lane] = 0u;
+            if (lane + 32 < wpt) dirty_t[lane + 32] = 0u;
+            first_issued = false;
+            continue;
+        }
+        s_sus[lane] = sg.sus0; s_sus[lane + 32] = sg.sus1;
+        s_dirty[lane] = 0u; s_dirty[lane + 32] = 0u;
+        __syncwarp();
+        if (!first_issued) issue_chunk(sg.base4, sg.len, 0);
+        first_issued = false;
+        const int64_t row_base = (int64_t)tile << tile_shift;
+        const int nch = (sg.len + CAP - 1) / CAP;
+        // the run of hits that may continue in the next batch / chunk: row, lambda, d lambda / dR (warp-uniform)
+        int carry_row = -1;
+        double carry = 0.0, carry1 = 0.0;
+        auto write_partial = [&](int row, double v, double v1) {
+            if (v != 0.0 || v1 != 0.0) {
+                part_b[row_base + row] = make_double2(v, v1);
+                atomicOr(&s_dirty[row >> 5], 1u << (row & 31));          // integer OR on a warp-private word
+            }
+        };
+        for (int ci = 0; ci < nch; ++ci) {
+            // successor in flight before this chunk is touched: the segment's next chunk, else the next segment's first
+            if (ci + 1 < nch) issue_chunk(sg.base4, sg.len, ci + 1);
+            else if (g0.len > 0) { issue_chunk(g0.base4, g0.len, 0); first_issued = true; }
+            const uint32_t slot = consumed & 1u;
+            mbar_wait(&s_bar[slot], (consumed >> 1) & 1u);
+            ++consumed;
+            const int n = min(CAP, sg.len - ci * CAP);
+            const int32_t* sc = s_col + slot * CAP;
+            const int4* sc4 = reinterpret_cast<const int4*>(sc) + lane * RL4;
+            uint32_t h = 0;
+#pragma unroll
+            for (int q = 0; q < RL4; ++q) {
+                const int4 c = sc4[q];
+                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.x >> 3) & (SRC_MASK >> 5 << 2)));
+                const uint32_t w1 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.y >> 3) & (SRC_MASK >> 5 << 2)));
+                const uint32_t w2 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.z >> 3) & (SRC_MASK >> 5 << 2)));
+                const uint32_t w3 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.w >> 3) & (SRC_MASK >> 5 << 2)));
+                h = __funnelshift_r(h, w0 >> (c.x & 31), 1);
+                h = __funnelshift_r(h, w1 >> (c.y & 31), 1);
+                h = __funnelshift_r(h, w2 >> (c.z & 31), 1);
+                h = __funnelshift_r(h, w3 >> (c.w & 31), 1);
+            }
+            h >>= (32 - RL);                                            // edge j of this lane's run is bit j
+            {
+                const int mine = n - lane * RL;
+                h &= mine >= RL ? 0xffffffffu >> (32 - RL) : (mine <= 0 ? 0u : ((1u << mine) - 1u));
+            }
+            if (__any_sync(0xffffffffu, h != 0u)) {
+                // keep the hits of susceptible rows only (nobody else's lambda is used)
+                {
+                    uint32_t hh = h;
+                    while (hh) {
+                        const int b = __ffs(hh) - 1;
+                        hh &= hh - 1u;
+                        const uint32_t row = (uint32_t)sc[lane * RL + b] >> AT_PACKED_SRC_BITS;
+                        if (!((s_sus[row >> 5] >> (row & 31u)) & 1u)) h &= ~(1u << b);
+                    }
+                }
+                int incl = __popc(h);
+                const int cnt = incl;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int nh = __shfl_sync(0xffffffffu, incl, 31);
+                {
+                    int off = incl - cnt;
+                    uint32_t hh = h;
+                    while (hh) {
+                        s_pos[off++] = (uint16_t)(lane * RL + (__ffs(hh) - 1));
+                        hh &= hh - 1u;
+                    }
+                }
+                __syncwarp();
+                for (int base = 0; base < nh; base += 32) {
+                    const int i = base + lane;
+                    const int nvalid = min(32, nh - base);
+                    const bool valid = lane < nvalid;
+                    int row = -2 - lane;                                  // never equal to a row or to another lane's filler
+                    double v = 0.0, v1 = 0.0;
+                    if (valid) {
+                        const uint32_t e = (uint32_t)sc[s_pos[i]];
+                        row = (int)(e >> AT_PACKED_SRC_BITS);
+                        const uint32_t code = __ldg(code_b + (e & SRC_MASK));
+                        int ag = load_age(a.age, row_base + row, age_f32);
+                        ag = ag < 0 ? 0 : (ag >= m.n_sfs ? m.n_sfs - 1 : ag);
+                        v = s_T[ag * NC + code];
+                        if (want_grad) v1 = s_T1[ag * NC + code];
+                    }
+                    // runs of equal rows; the first lane's run may continue the carry
+                    int prow = __shfl_up_sync(0xffffffffu, row, 1);
+                    if (lane == 0) prow = -1;
+                    const uint32_t heads = __ballot_sync(0xffffffffu, row != prow);          // bit 0 always set
+                    const int head = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
+                    const bool tail = valid && (lane == nvalid - 1 || ((heads >> (lane + 1)) & 1u));
+                    const int rlen = lane - head + 1;
+                    int K = tail ? rlen : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) K = max(K, __shfl_xor_sync(0xffffffffu, K, o));
+                    const bool cont = (__shfl_sync(0xffffffffu, row, 0) == carry_row);
+                    double sum = 0.0, sum1 = 0.0;
+                    if (head == 0 && cont) { sum = carry; sum1 = carry1; }
+                    for (int k = K - 1; k >= 0; --k) {                    // lanes head .. tail, in edge order
+                        const double x = __shfl_up_sync(0xffffffffu, v, k);
+                        const double x1 = __shfl_up_sync(0xffffffffu, v1, k);
+                        if (tail && k < rlen) { sum += x; sum1 += x1; }
+                    }
+                    if (!cont && carry_row >= 0 && lane == 0) write_partial(carry_row, carry, carry1);
+                    if (tail && lane != nvalid - 1) write_partial(row, sum, sum1);
+                    carry_row = __shfl_sync(0xffffffffu, row, nvalid - 1);
+                    carry = __shfl_sync(0xffffffffu, sum, nvalid - 1);
+                    carry1 = __shfl_sync(0xffffffffu, sum1, nvalid - 1);
+                }
+            }
+            __syncwarp();                                                // slot and position list are reused
+        }
+        if (carry_row >= 0 && lane == 0) write_partial(carry_row, carry, carry1);
+        __syncwarp();
+        if (lane < wpt) dirty_t[lane] = s_dirty[lane];
+        if (lane + 32 < wpt) dirty_t[lane + 32] = s_dirty[lane + 32];
+        __syncwarp();
+    }
+}
+
 // Folds the hot bitmap of the next step into the hashed filter (word i = OR of words i, i+M, i+2M, ...) once, so that
 // the next step's CTAs read M words instead of the whole bitmap each; the word after the filter says "any source hot".
 __global__ void __launch_bounds__(256)
@@ -1047,6 +1300,17 @@ static int dispatch(const KModel& km, const at_seirm_launch& a, int grid, int th
     return fail("%s", "edges_per_chunk must be 512, 768 or 1024");
 }
 
+template <int RL4>
+static int launch_packed(const KModel& km, const at_seirm_launch& a, int grid, int threads, size_t smem, int bm_words, int NC, int tile_shift, cudaStream_t s) {
+    auto k = gather_packed_kernel<RL4>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    AT_LAUNCH_SMEM(k, grid, threads, smem, s, km, a, bm_words, NC, tile_shift);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("gather_packed_kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" {
 
 int at_seirm_abi_version(void) { return AT_SEIRM_ABI_VERSION; }
@@ -1063,6 +1327,15 @@ int64_t at_seirm_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edge
     return ((bytes * 8) / 1024) * 1024;
 }
 
+int64_t at_seirm_packed_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edges_per_chunk, int32_t warps) {
+    if (device_props()) return 0;
+    if (warps < 1) warps = NT_MAX / 32;
+    int64_t bytes = (int64_t)g_smem_optin - (int64_t)table_smem(n_sfs, n_lam_gamma) - (int64_t)warps * packed_warp_smem_bytes(edges_per_chunk) - 2048;
+    if (bytes < 4096) return 0;
+    int64_t bits = ((bytes * 8) / 1024) * 1024;
+    return bits > ((int64_t)1 << AT_PACKED_SRC_BITS) ? ((int64_t)1 << AT_PACKED_SRC_BITS) : bits;
+}
+
 int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, void* stream) {
     if (!model || !launch) return fail("%s", "null argument");
     const at_seirm_launch& a = *launch;
@@ -1072,16 +1345,26 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     if (a.n_rows < 0 || (a.row_offset & 31) != 0 || (a.n_rows_pad & 255) != 0 || a.n_rows_pad < a.n_rows) return fail("%s", "bad n_rows / n_rows_pad / row_offset");
     if (!a.stage || !a.workspace || !a.sus_bitmap || !a.exp_bitmap || !a.inf_bitmap) return fail("%s", "stage / workspace / row bitmaps must not be null");
     const bool do_trans = a.flags & AT_DO_TRANSMISSION;
+    if (a.layout != AT_LAYOUT_BCSR && a.layout != AT_LAYOUT_PACKED) return fail("%s", "unknown layout");
+    const bool packed = a.layout == AT_LAYOUT_PACKED;
     const int epc = a.edges_per_chunk > 0 ? a.edges_per_chunk : 768;
     if (epc != 512 && epc != 768 && epc != 1024) return fail("%s", "edges_per_chunk must be 512, 768 or 1024");
     if (do_trans) {
-        if (!a.row_start || !a.seg_info || !a.col || !a.code_in || !a.hot_bitmap_in || !a.r_value || !a.age) return fail("%s", "transmission needs the graph, code_in, hot_bitmap_in, age, r_value");
+        if ((!packed && !a.row_start) || !a.seg_info || !a.col || !a.code_in || !a.hot_bitmap_in || !a.r_value || !a.age) return fail("%s", "transmission needs the graph, code_in, hot_bitmap_in, age, r_value");
         if (a.n_blocks < 1 || a.n_blocks > AT_MAX_BLOCKS || a.block_size < 1024 || (a.block_size & 1023)) return fail("%s", "bad n_blocks / block_size");
         if ((int64_t)a.n_blocks * a.block_size < a.n_sources) return fail("%s", "n_blocks * block_size does not cover n_sources");
-        if (a.rows_per_task != (a.n_blocks > 1 ? 256 : 32)) return fail("%s", "rows_per_task must be 32 (one block) or 256 (several blocks)");
+        if (!packed && a.rows_per_task != (a.n_blocks > 1 ? 256 : 32)) return fail("%s", "rows_per_task must be 32 (one block) or 256 (several blocks)");
+        if (packed) {
+            if (a.tile_rows < 32 || a.tile_rows > AT_PACKED_MAX_TILE_ROWS || (a.tile_rows & (a.tile_rows - 1)) || (a.n_rows_pad % a.tile_rows))
+                return fail("%s", "packed layout: tile_rows must be a power of two in 32..2048 dividing n_rows_pad");
+            if (a.block_size > (1 << AT_PACKED_SRC_BITS)) return fail("%s", "packed layout: block_size exceeds 2^21 sources");
+            if (a.edge_weight) return fail("%s", "packed layout: edge weights are not supported");
+            if (a.hash_words) return fail("%s", "packed layout: hash_words must be 0");
+            if (!a.lam_part || !a.dirty) return fail("%s", "packed layout needs lam_part / dirty");
+        }
         if (a.iso_mode == AT_ISO_TENSOR && !a.isolation) return fail("%s", "iso_mode TENSOR without isolation pointer");
         if (a.u_mode == AT_U_TENSOR && !a.uniform) return fail("%s", "u_mode TENSOR without uniform pointer");
-        if (a.n_blocks > 1 && (!a.lam_part || !a.dirty)) return fail("%s", "n_blocks > 1 needs lam_part / dirty");
+        if (!packed && a.n_blocks > 1 && (!a.lam_part || !a.dirty)) return fail("%s", "n_blocks > 1 needs lam_part / dirty");
         if (a.flags & AT_DO_INIT) return fail("%s", "AT_DO_INIT cannot be combined with AT_DO_TRANSMISSION");
     }
     if ((a.flags & AT_DO_PROGRESSION) && (!a.next_stage_time || (a.daily_deaths && !a.m_value))) return fail("%s", "progression needs next_stage_time and m_value");
@@ -1104,7 +1387,7 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     if (warps > NT_MAX / 32) warps = NT_MAX / 32;
     int bm_words = 0;
     const bool hashed = do_trans && a.hash_words > 0;
-    if (do_trans) {
+    if (do_trans && !packed) {
         const int64_t bits = hashed ? (int64_t)a.hash_words * 32 : (int64_t)a.block_size;
         if (hashed && (a.n_blocks != 1 || (a.hash_words & (a.hash_words - 1)) != 0 || a.hash_words < 32)) return fail("%s", "hash_words must be a power of two >= 32 and n_blocks 1");
         while (warps > 4 && bits > at_seirm_max_block_size(model->n_sfs, model->n_lam_gamma, epc, warps)) --warps;
@@ -1123,6 +1406,27 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         const int64_t uuseful = (nsuper + 7) / 8;
         if (ugrid > uuseful) ugrid = (int)uuseful;
         if (ugrid < 1) ugrid = 1;
+    }
+    if (do_trans && packed) {
+        int pw = a.warps_per_cta > 0 ? a.warps_per_cta : NT_MAX / 32;
+        if (pw > NT_MAX / 32) pw = NT_MAX / 32;
+        while (pw > 4 && a.block_size > at_seirm_packed_max_block_size(model->n_sfs, model->n_lam_gamma, epc, pw)) --pw;
+        if (a.block_size > at_seirm_packed_max_block_size(model->n_sfs, model->n_lam_gamma, epc, pw))
+            return fail("%s", "packed layout: block bitmap exceeds the shared-memory capacity (at_seirm_packed_max_block_size)");
+        const int words = a.block_size / 32;
+        const size_t smem = (size_t)pw * packed_warp_smem_bytes(epc) + tables + (size_t)words * 4;
+        int tile_shift = 0;
+        while ((1 << tile_shift) < a.tile_rows) ++tile_shift;
+        int ggrid = grid < a.n_blocks ? a.n_blocks : grid;
+        int rc;
+        switch (epc) {
+            case 512: rc = launch_packed<4>(km, al, ggrid, pw * 32, smem, words, NC, tile_shift, s); break;
+            case 768: rc = launch_packed<6>(km, al, ggrid, pw * 32, smem, words, NC, tile_shift, s); break;
+            default: rc = launch_packed<8>(km, al, ggrid, pw * 32, smem, words, NC, tile_shift, s); break;
+        }
+        if (rc) return rc;
+        al.edges_per_chunk = 512;
+        return launch_kernel<MODE_UPDATE, 4>(km, al, ugrid, 256, smem_update, 0, NC, 8, s);
     }
     if (do_trans && a.n_blocks > 1) {
         const int Gg = a.tasks_per_group > 0 ? (a.tasks_per_group > MAXG ? MAXG : a.tasks_per_group) : 1;

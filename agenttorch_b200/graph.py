@@ -275,6 +275,8 @@ class BlockedGraph:
     edge_weight: Optional[torch.Tensor] = None
     i_bar: float = 1.0
     i_bar_agent: int = -1
+    layout: int = 0              # 0 = BCSR (row_start + col), 1 = packed (every col entry carries its row; include/at_seirm.h)
+    tile_rows: int = 0           # packed layout: rows per tile
 
     @property
     def device(self):
@@ -292,7 +294,8 @@ class BlockedGraph:
         return BlockedGraph(self.n_rows, self.n_rows_pad, self.n_sources, self.row_offset, self.n_blocks, self.block_size,
                             self.rows_per_task, self.row_start.to(device), self.seg_info.to(device), self.col.to(device),
                             self.num_edges, self.edges_per_chunk, self.hash_words,
-                            None if self.edge_weight is None else self.edge_weight.to(device), self.i_bar, self.i_bar_agent)
+                            None if self.edge_weight is None else self.edge_weight.to(device), self.i_bar, self.i_bar_agent,
+                            self.layout, self.tile_rows)
 
 
 def choose_block_size(n_sources, max_block_size):
@@ -382,3 +385,71 @@ def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = 
         raise ValueError("the hashed filter needs a single column block")
     return BlockedGraph(n_rows, n_rows_pad, graph.n_sources, graph.row_offset, nb, block_size, rpt, _to_i16(row_start),
                         seg_info, col_out, e, epc, int(hash_words), w_out, graph.i_bar, graph.i_bar_agent)
+
+
+PACKED_SRC_BITS = 21
+PACKED_MAX_TILE_ROWS = 2048
+
+
+def choose_tile_rows(n_rows, n_blocks, warps_total, min_segments_per_warp=8):
+    """Rows per tile of the packed layout: as large as the 11 row bits allow, smaller when the shard has so few rows
+    that the warps of the gather grid would get fewer than `min_segments_per_warp` segments each."""
+    tile = PACKED_MAX_TILE_ROWS
+    while tile > 256 and (-(-n_rows // tile)) * n_blocks < warps_total * min_segments_per_warp:
+        tile //= 2
+    return tile
+
+
+def block_graph_packed(graph: ContactGraph, block_size: int, tile_rows: int = PACKED_MAX_TILE_ROWS,
+                       edges_per_chunk: int = 512) -> BlockedGraph:
+    """ContactGraph -> packed column-blocked layout (AT_LAYOUT_PACKED, include/at_seirm.h): segment (block, tile) holds the
+    edges of the tile's rows whose source lies in the block, sorted by row and, inside a row, in original edge order, as
+    entries (row_in_tile << 21) | block-local source id.  Replaces the (2,E) COO edge_index of the reference
+    (utils.py:129-148) for source sets that need more than one shared-memory bitmap."""
+    dev = graph.device
+    if graph.edge_weight is not None:
+        raise NotImplementedError("the packed layout does not carry edge weights")
+    if block_size % 1024 or block_size > (1 << PACKED_SRC_BITS):
+        raise ValueError("block_size must be a multiple of 1024 and at most 2^21")
+    if tile_rows & (tile_rows - 1) or not 32 <= tile_rows <= PACKED_MAX_TILE_ROWS:
+        raise ValueError("tile_rows must be a power of two in 32..2048")
+    n_rows, e = graph.n_rows, graph.num_edges
+    pad = max(tile_rows, 256)
+    n_rows_pad = -(-max(n_rows, 1) // pad) * pad
+    nb = max(1, -(-graph.n_sources // block_size))
+    if nb > 64:
+        raise ValueError("more than 64 column blocks: shard the graph over more GPUs")
+    n_tiles = n_rows_pad // tile_rows
+    shift = tile_rows.bit_length() - 1
+    row_ptr = graph.row_ptr.long()
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=dev), row_ptr[1:] - row_ptr[:-1])
+    col = graph.col_idx[:e].long()
+    blk = torch.div(col, block_size, rounding_mode="floor")
+    key = blk * n_rows_pad + rows                       # (block, row): a stable sort keeps the edge order inside a row
+    if nb > 1:
+        order = torch.sort(key, stable=True).indices
+        key, col, blk = key[order], col[order], blk[order]
+        del order
+    enc = (((key - blk * n_rows_pad) & (tile_rows - 1)) << PACKED_SRC_BITS) | (col - blk * block_size)
+    del col, blk, rows
+    n_seg = nb * n_tiles
+    seg = key >> shift                                  # = block * n_tiles + tile
+    del key
+    seg_len = torch.bincount(seg, minlength=n_seg)
+    seg_pad = ((seg_len + 3) >> 2) << 2
+    seg_base = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
+    seg_base[1:] = torch.cumsum(seg_pad, 0)
+    seg_first = torch.zeros(n_seg, dtype=torch.int64, device=dev)
+    seg_first[1:] = torch.cumsum(seg_len, 0)[:-1]
+    total = int(seg_base[-1])
+    if total // 4 >= 2**31:
+        raise ValueError("graph shard too large for int32 segment bases")
+    pos = torch.arange(e, device=dev) - seg_first[seg] + seg_base[:-1][seg]
+    del seg
+    col_out = torch.zeros(total + TAIL_PAD, dtype=torch.int32, device=dev)
+    enc = torch.where(enc >= 2**31, enc - 2**32, enc).to(torch.int32)     # the 32-bit pattern, as int32
+    col_out[pos] = enc
+    seg_info = torch.stack(((seg_base[:-1] >> 2), seg_len), dim=1).to(torch.int32).contiguous()
+    row_start = torch.zeros(1, dtype=torch.int16, device=dev)            # unused in this layout
+    return BlockedGraph(n_rows, n_rows_pad, graph.n_sources, graph.row_offset, nb, block_size, tile_rows, row_start,
+                        seg_info, col_out, e, int(edges_per_chunk), 0, None, graph.i_bar, graph.i_bar_agent, 1, tile_rows)

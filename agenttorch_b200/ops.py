@@ -111,7 +111,9 @@ def seirm_progression(handle: int, stage: Tensor, next_stage_time: Tensor, daily
     st.age = torch.zeros(1, dtype=torch.uint8, device=dev)          # not read by the progression pass
     rstep = torch.full((st.stage.numel(),), 255, dtype=torch.uint8, device=dev)
     dcount = torch.zeros(max(daily_deaths.numel(), t + 1), dtype=torch.float32, device=dev)
-    eng.launch(st, flags=nat.DO_PROGRESSION, t=t, m_value=m_value.detach().reshape(-1).to(torch.float32).contiguous(),
+    # DO_INIT: the E / I row bitmaps are derived from THIS stage tensor (the engine's cached bitmaps describe whatever state
+    # its previous launch saw, which need not be this one: a fresh engine, a state edited between substeps, two states)
+    eng.launch(st, flags=nat.DO_PROGRESSION | nat.DO_INIT, t=t, m_value=m_value.detach().reshape(-1).to(torch.float32).contiguous(),
                death_count=dcount, recovered_step=rstep)
     return (st.stage.view_as(stage), st.next_stage_time.view_as(next_stage_time), st.daily_deaths.view_as(daily_deaths),
             (rstep == t).to(torch.uint8), dcount[t:t + 1].clone())

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AT_SEIRM_ABI_VERSION 7
+#define AT_SEIRM_ABI_VERSION 8
 #define AT_MAX_SFS 16        /* SFSusceptibility entries (config.yaml has 9)                     */
 #define AT_MAX_SFI 8         /* SFInfector entries (config.yaml has 5)                           */
 #define AT_MAX_LAMGAMMA 84   /* lam_gamma_integrals entries; 1 + 3*K infectiousness codes fit a byte */
@@ -47,6 +47,12 @@ extern "C" {
 /* exposure uniform U (stands in for torch.bernoulli, distributions.py:16) */
 #define AT_U_TENSOR 0        /* U read from `uniform` (float32)                                   */
 #define AT_U_HASH 1          /* U from the counter hash: top 24 bits of SplitMix64                */
+
+/* contact-graph layouts (at_seirm_launch.layout) */
+#define AT_LAYOUT_BCSR 0     /* row_start + seg_info + col: 32-row tasks (one column block) or 256-row tasks    */
+#define AT_LAYOUT_PACKED 1   /* seg_info + col only: every entry carries its row, (row_in_tile << 21) | source  */
+#define AT_PACKED_SRC_BITS 21
+#define AT_PACKED_MAX_TILE_ROWS 2048
 
 /* what one launch does */
 #define AT_DO_TRANSMISSION 1 /* substep '0' transition (NewTransmission.forward)                  */
@@ -82,6 +88,16 @@ typedef struct at_seirm_model {
  *     col[] = block-local source id c encoded as ((c >> 5) << 7) | (c & 31): byte offset of its bitmap word
  *     times 32, plus its bit — so that the shared-memory bitmap test needs no address arithmetic.
  *   Edges are used as written: directed, duplicates and self-loops kept (Q9).
+ *
+ * layout == AT_LAYOUT_PACKED ("PBCSR", the layout for source sets larger than one shared-memory bitmap): rows are
+ *   grouped in TILES of tile_rows rows (a power of two <= 2048; n_rows_pad is a multiple of it), sources in n_blocks
+ *   ranges of block_size <= 2^21 ids.  Segment s = block*n_tiles + tile holds the tile's edges whose source lies in
+ *   the block, sorted by row, each row in original edge order, as 32-bit entries
+ *     col[] = (row_in_tile << 21) | block-local source id,
+ *   so a segment is a flat stream that needs no per-row metadata (row_start is NULL) and no limit on a row's degree.
+ *   seg_info as above.  The gather kernel (one column block's EXACT hot bitmap in shared memory per CTA) leaves
+ *   per-(block,row) partial lambdas in lam_part + dirty, which the update kernel folds in block order.  Edge weights are
+ *   not supported in this layout (edge_weight must be NULL).
  */
 typedef struct at_seirm_launch {
     int32_t abi_version;        /* = AT_SEIRM_ABI_VERSION */
@@ -95,7 +111,7 @@ typedef struct at_seirm_launch {
     int64_t row_offset;         /* global id of local row 0 (multiple of 32): slice of this rank in
                                    code/hot_bitmap, and the agent id fed to the counter hash */
     int32_t n_blocks, block_size;   /* block_size multiple of 1024 */
-    int32_t rows_per_task, edges_per_chunk;  /* 32 or 256; TMA chunk capacity: 512, 768 or 1024 edges */
+    int32_t rows_per_task, edges_per_chunk;  /* 32 or 256 (BCSR; ignored for PACKED); TMA chunk capacity: 512, 768 or 1024 edges */
     const uint16_t* row_start;  /* [n_blocks][n_rows_pad] */
     const int32_t* seg_info;    /* [n_blocks*n_gtasks][2] = (first entry / 4, edges) */
     const int32_t* col;         /* encoded source ids, segment-padded, + >= 1024 ints of tail padding */
@@ -142,7 +158,8 @@ typedef struct at_seirm_launch {
     uint8_t* recovered_step;    /* n_rows or NULL: set to t where the I->R transition fires */
     /* scratch for n_blocks > 1 (per-block partial lambdas), else NULL */
     double* lam_part;           /* [n_blocks][n_rows_pad][2]: (lambda, d lambda / dR) of the rows flagged in dirty */
-    double* lam1_part;          /* unused (kept for ABI layout) */
+    int32_t layout;             /* AT_LAYOUT_* */
+    int32_t tile_rows;          /* AT_LAYOUT_PACKED: rows per tile (power of two, 32..2048), else 0 */
     uint32_t* dirty;            /* [n_blocks][n_rows_pad/32]: which rows of lam_part hold a value this step */
     /* workspace: at_seirm_workspace_bytes() bytes, zeroed once by the caller, reset by every launch */
     void* workspace;
@@ -166,6 +183,8 @@ int64_t at_seirm_workspace_bytes(void);
    `warps` warps' TMA buffers of `edges_per_chunk` edges, for a model with n_sfs susceptibility classes and
    n_lam_gamma integrals (the term tables share the same shared memory) */
 int64_t at_seirm_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edges_per_chunk, int32_t warps);
+/* the same for AT_LAYOUT_PACKED (its per-warp staging area differs); never more than 2^21 */
+int64_t at_seirm_packed_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edges_per_chunk, int32_t warps);
 
 /*
  * at_seirm_step — one step (or part of one, per the flags) of the agent update on `stream`.

@@ -124,6 +124,12 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d, i
     const int src = t_emu_lane + (int)d;
     return emu_exchange(v, src < 32 ? src : t_emu_lane);
 }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32)
+{
+    (void)width;
+    const int src = t_emu_lane - (int)d;
+    return emu_exchange(v, src >= 0 ? src : t_emu_lane);
+}
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int mask, int width = 32) { (void)width; return emu_exchange(v, (t_emu_lane ^ mask) & 31); }
 static inline unsigned __ballot_sync(unsigned mask, int pred)
 {

@@ -86,6 +86,11 @@ def _check(g, st, grad_r2, grad_m):
     ("synth3k_hard", dict()),
     ("synth3k_soft", dict(block_size=1024)),                         # column blocks: gather + update kernels
     ("synth3k_r2vec", dict(hashed=True, hash_words=32)),             # hashed filter + hot_fold_kernel
+    ("synth3k_soft", dict(layout="packed", block_size=1024, tile_rows=256)),     # packed layout: 3 column blocks, 12 tiles
+    ("synth3k_hard", dict(layout="packed", block_size=2048, tile_rows=2048)),    # segments of several TMA chunks (carry across chunks)
+    ("synth3k_r2vec", dict(layout="packed", block_size=4096, tile_rows=64, warps_per_cta=1)),   # one block, tiny tiles
+    ("tiny96_hard", dict(layout="packed", block_size=1024, tile_rows=32)),
+    ("noiso500", dict(layout="packed", block_size=1024, tile_rows=128, packed=False, tensor_noise=True)),
     ("tiny96_hard", dict(warps_per_cta=1)),                          # a CTA smaller than the code tables (found by tools/fuzz_emulated.py)
     ("noiso500", dict(warps_per_cta=1, hashed=True, hash_words=32)),
 ])

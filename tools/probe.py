@@ -19,6 +19,11 @@ ap.add_argument("--grad", type=int, default=1)
 ap.add_argument("--r2", type=float, default=4.75)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--iso", default="soft")
+ap.add_argument("--layout", default="auto")
+ap.add_argument("--tile", type=int, default=0)
+ap.add_argument("--epc", type=int, default=0)
+ap.add_argument("--pw", type=int, default=14)
+ap.add_argument("--warps", type=int, default=0)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 T = args.steps
@@ -26,8 +31,9 @@ age, stage0 = synthetic_population(args.n, 1234, device=dev)
 mi = mean_interactions_from_age(age)
 graph = synthetic_contact_graph(args.n, args.d, 99, family=args.family, device=dev, mean_interactions=mi)
 print("N", args.n, "E", graph.num_edges, "ibar", graph.i_bar, flush=True)
-eng = SeirmEngine(graph, SeirmSpec(num_steps=T), block_size=args.block or None, tasks_per_group=args.tpg, hashed=None if args.hashed < 0 else bool(args.hashed), hash_min_warps=args.hmw)
-print('blocks', eng.graph.n_blocks, 'block_size', eng.graph.block_size, 'hash_words', eng.graph.hash_words, flush=True)
+eng = SeirmEngine(graph, SeirmSpec(num_steps=T), block_size=args.block or None, tasks_per_group=args.tpg, hashed=None if args.hashed < 0 else bool(args.hashed), hash_min_warps=args.hmw,
+                  layout=args.layout, tile_rows=args.tile or None, edges_per_chunk=args.epc or None, packed_warps=args.pw, warps_per_cta=args.warps)
+print('layout', eng.graph.layout, 'blocks', eng.graph.n_blocks, 'block_size', eng.graph.block_size, 'hash_words', eng.graph.hash_words, 'tile', eng.graph.tile_rows, 'epc', eng.graph.edges_per_chunk, flush=True)
 r_steps = torch.full((T,), 3 * args.r2, device=dev)
 m = torch.tensor([0.12], device=dev)
 noise = NoiseSpec(seed=5, isolation=args.iso)
