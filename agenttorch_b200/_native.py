@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libat_seirm.so")
 SRC_PATH = os.path.join(_PKG, "csrc", "at_seirm.cu")
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_SFS, MAX_SFI, MAX_LAMGAMMA = 16, 8, 84
 TIMER_F32, TIMER_I16 = 0, 1
 AGE_F32, AGE_U8 = 0, 1
@@ -23,12 +23,12 @@ ISO_TENSOR, ISO_HASH_SOFT, ISO_HASH_HARD, ISO_NONE = 0, 1, 2, 3
 U_TENSOR, U_HASH = 0, 1
 DO_TRANSMISSION, DO_PROGRESSION, DO_ENCODE, DO_INIT = 1, 2, 4, 8
 MAX_BLOCKS = 64
-LAYOUT_BCSR, LAYOUT_PACKED = 0, 1
-PACKED_SRC_BITS, PACKED_MAX_TILE_ROWS = 21, 2048
+LAYOUT_BCSR, LAYOUT_STREAM = 0, 1
+STREAM_UNIT, STREAM_MAX_TILE_ROWS, STREAM_MAX_BLOCK_SIZE = 256, 2048, (1 << 21) - 1024
 
 EXPORTS = [
     "at_seirm_abi_version", "at_last_error", "at_seirm_sizeof_launch", "at_seirm_sizeof_model",
-    "at_seirm_workspace_bytes", "at_seirm_max_block_size", "at_seirm_packed_max_block_size", "at_seirm_step",
+    "at_seirm_workspace_bytes", "at_seirm_max_block_size", "at_seirm_stream_max_block_size", "at_seirm_step",
     "at_seirm_episode_backward", "at_seirm_hot_from_code", "at_seirm_pull_codes", "at_seirm_exchange_bytes",
     "at_seirm_exchange_sparse", "at_noise_fill",
 ]
@@ -68,6 +68,9 @@ class SeirmLaunch(ctypes.Structure):
         ("workspace", ctypes.c_void_p), ("error_flag", ctypes.c_void_p),
         ("grid", ctypes.c_int32), ("tasks_per_group", ctypes.c_int32),
         ("warps_per_cta", ctypes.c_int32), ("hash_words", ctypes.c_int32),
+        ("unit_tile", ctypes.c_void_p), ("block_units", ctypes.c_void_p), ("tile_rec_base", ctypes.c_void_p),
+        ("tile_count", ctypes.c_void_p), ("rec", ctypes.c_void_p),
+        ("lam_deg_bits", ctypes.c_int32), ("_pad1", ctypes.c_int32),
     ]
 
 
@@ -115,8 +118,8 @@ def lib():
             getattr(L, name).restype = ctypes.c_int64
         L.at_seirm_max_block_size.restype = ctypes.c_int64
         L.at_seirm_max_block_size.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
-        L.at_seirm_packed_max_block_size.restype = ctypes.c_int64
-        L.at_seirm_packed_max_block_size.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+        L.at_seirm_stream_max_block_size.restype = ctypes.c_int64
+        L.at_seirm_stream_max_block_size.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
         L.at_seirm_step.restype = ctypes.c_int
         L.at_seirm_step.argtypes = [ctypes.POINTER(SeirmModel), ctypes.POINTER(SeirmLaunch), ctypes.c_void_p]
         L.at_seirm_episode_backward.restype = ctypes.c_int

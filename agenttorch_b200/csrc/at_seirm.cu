@@ -729,41 +729,220 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     }
 }
 
-// ------------------------------------------------------------------------------- packed-layout gather
-// AT_LAYOUT_PACKED: the gather for source sets larger than one shared-memory bitmap.  Sources are split in column
-// blocks; CTA c keeps the EXACT hot bitmap of block c % n_blocks in shared memory and streams that block's segments
-// (one per row tile) with per-warp double-buffered TMA bulk copies.  Every 32-bit entry carries its row
-// ((row_in_tile << 21) | source), so a segment is a flat stream: lane L tests its RL consecutive entries against the
-// bitmap (one LDS per edge), and only TRUE hits of SUSCEPTIBLE rows are compacted (edge order) and looked at again:
-// code byte from the L2-resident code array, destination age, table term, and an in-order segmented sum over the
-// hits of the same row (rows are contiguous in a segment).  Per-(block,row) partial lambdas go to lam_part / dirty,
-// which MODE_UPDATE folds in block order.  No atomics on floating point, static schedule: deterministic.
-__host__ __device__ constexpr int packed_warp_smem_bytes(int cap) { return 2 * cap * 4 + cap * 2 + 64 * 4 + 64 * 4 + 64; }
+// ------------------------------------------------------------------------------- stream-layout gather
+// AT_LAYOUT_STREAM: the contact graph as flat streams, one per source block (include/at_seirm.h).  A CTA owns a
+// contiguous range of 256-entry units; for every source block the range touches it stages the block's EXACT hot
+// bitmap in shared memory (one TMA bulk copy) and its warps stream the units through registers: 2 x 128-bit loads
+// per lane and unit, three units in flight per warp, one shared-memory bitmap test (5 instructions) per edge.  The
+// rare hits are parked (entry + unit) in a per-warp list; when the list fills up the warp resolves it in one sweep,
+// every lane up to ST_RK hits and all loads of a phase in flight together: tile of the unit -> susceptible bit of the
+// row -> infectiousness code of the source -> the pair (row in tile, code) is appended to the tile's RECORD list
+// (slot from an integer atomic counter; capacity = the tile's edge count, so it cannot overflow).  Pure integer
+// work: no table, no R, no floating point.  MODE_TUPDATE turns a tile's records into its rows' lambdas by summing
+// 64-bit FIXED-POINT terms — integer addition commutes, so the result does not depend on the order in which warps,
+// CTAs or steps of the schedule appended the records: deterministic without ordering edges, no float atomics.
+#define ST_NT 1024                  // max threads per CTA
+#define ST_PEND 128                 // parked hits per warp
+#define ST_RK 4                     // hits per lane in one resolve sweep (ST_PEND = 32 * ST_RK)
 
-template <int RL4>
-__global__ void __launch_bounds__(NT_MAX, 1)
-gather_packed_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const int NC, const int tile_shift)
+struct StreamResolveCtx {
+    const int32_t* unit_tile; const uint32_t* sus; const uint8_t* code_b; const int64_t* tile_rec_base;
+    uint32_t* tile_count; uint32_t* rec;
+    int tile_shift;
+};
+__device__ __noinline__ void stream_resolve(const StreamResolveCtx& c, const uint2* s_pend, int count, int lane)
 {
-    constexpr int RL = 4 * RL4, CAP = 32 * RL, WSM = packed_warp_smem_bytes(CAP);
-    constexpr uint32_t SRC_MASK = (1u << AT_PACKED_SRC_BITS) - 1u;
+    __syncwarp();
+    uint32_t e[ST_RK], sw[ST_RK], cd[ST_RK];
+    int tile[ST_RK];
+    int64_t base[ST_RK];
+#pragma unroll
+    for (int k = 0; k < ST_RK; ++k) {
+        const int i = k * 32 + lane;
+        e[k] = 0u; tile[k] = -1;
+        if (i < count) {
+            const uint2 p = s_pend[i];
+            e[k] = p.x;
+            tile[k] = __ldg(c.unit_tile + p.y);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ST_RK; ++k) {
+        sw[k] = 0u; base[k] = 0;
+        if (tile[k] >= 0) {
+            const int64_t row = ((int64_t)tile[k] << c.tile_shift) + (int64_t)((e[k] >> 5) & 0x7FFu);
+            sw[k] = (__ldg(c.sus + (row >> 5)) >> (row & 31)) & 1u;
+            base[k] = __ldg(c.tile_rec_base + tile[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ST_RK; ++k) {
+        cd[k] = 0u;
+        if (sw[k]) cd[k] = __ldg(c.code_b + (((e[k] >> 16) << 5) | (e[k] & 31u)));    // only susceptible rows use their lambda
+    }
+#pragma unroll
+    for (int k = 0; k < ST_RK; ++k) {
+        if (cd[k] != 0u) {
+            const uint32_t slot = atomicAdd(c.tile_count + tile[k], 1u);
+            c.rec[base[k] + slot] = (((e[k] >> 5) & 0x7FFu) << 8) | cd[k];
+        }
+    }
+    __syncwarp();
+}
+
+// NTHREADS: CTA size the kernel is compiled for (register budget); UF: units in flight per warp (register sets)
+template <int NTHREADS, int UF>
+__global__ void __launch_bounds__(NTHREADS, 1)
+stream_gather_kernel(const at_seirm_launch a, const int bm_words, const int tile_shift)
+{
     AT_DYNAMIC_SMEM(unsigned char, smem_raw, 128);
     const int nw = blockDim.x >> 5;
-    // [per-warp areas][Tdiv f64 n_sfs*NC][T1div f64 n_sfs*NC][s_A f32 256][s_G f32 256][hot bitmap of this CTA's block]
-    double* s_T = reinterpret_cast<double*>(smem_raw + nw * WSM);
-    double* s_T1 = s_T + m.n_sfs * NC;
-    float* s_A = reinterpret_cast<float*>(s_T1 + m.n_sfs * NC);
-    float* s_G = s_A + 256;
-    const unsigned char* s_bm = reinterpret_cast<const unsigned char*>(s_G + 256);
-    __shared__ int s_any_hot_p;
+    // [hot bitmap of the current block: bm_words + 4 words, the last 4 always zero (padding entries point there)]
+    // [mbarrier 16 B][parked hits uint2 nw*ST_PEND]
+    uint32_t* s_bm = reinterpret_cast<uint32_t*>(smem_raw);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)(bm_words + 4) * 4);
+    uint2* s_pend_all = reinterpret_cast<uint2*>(s_bar + 2);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool want_grad = a.dne_dr != nullptr;
+    uint2* s_pend = s_pend_all + warp * ST_PEND;
+    if (tid == 0) mbar_init(s_bar, 1);
+    if (tid < 4) s_bm[bm_words + tid] = 0u;
+    fence_mbarrier_init();
+
+    // ---- this CTA's units: an equal share of all units, whatever blocks it touches
+    const int64_t n_units = a.block_units[a.n_blocks];
+    const int64_t U0 = n_units * (int64_t)blockIdx.x / (int64_t)gridDim.x, U1 = n_units * ((int64_t)blockIdx.x + 1) / (int64_t)gridDim.x;
+    const int4* colv = reinterpret_cast<const int4*>(a.col);
+    const int block_words = a.block_size >> 5;
+    uint32_t bar_phase = 0;
+    int count = 0;                                                // parked hits of this warp (warp-uniform)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    StreamResolveCtx rc;
+    rc.unit_tile = a.unit_tile; rc.sus = a.sus_bitmap; rc.code_b = a.code_in; rc.tile_rec_base = a.tile_rec_base;
+    rc.tile_count = a.tile_count; rc.rec = a.rec; rc.tile_shift = tile_shift;
+    int block = 0;
+    while (block < a.n_blocks && (int64_t)a.block_units[block + 1] <= U0) ++block;
+    for (; block < a.n_blocks && (int64_t)a.block_units[block] < U1; ++block) {
+        const int64_t s0 = max(U0, (int64_t)a.block_units[block]), s1 = min(U1, (int64_t)a.block_units[block + 1]);
+        if (s0 >= s1) continue;
+        // ---- stage the block's hot bitmap (TMA bulk copy, one mbarrier phase per block)
+        __syncthreads();                                         // barrier initialised; previous block's bitmap no longer read
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)block_words * 4u;
+            fence_proxy_async_smem();
+            mbar_expect_tx(s_bar, bytes);
+            bulk_g2s(s_bm, a.hot_bitmap_in + (size_t)block * block_words, bytes, s_bar);
+        }
+        mbar_wait(s_bar, bar_phase & 1u);
+        ++bar_phase;
+        uint32_t seen = 0;
+        {
+            const uint4* b4 = reinterpret_cast<const uint4*>(s_bm);
+            for (int i = tid; i < (block_words >> 2); i += blockDim.x) { const uint4 v = b4[i]; seen |= v.x | v.y | v.z | v.w; }
+        }
+        if (!__syncthreads_or(seen != 0u)) continue;             // no infectious source in this block: nothing can hit
+        rc.code_b = a.code_in + (size_t)block * a.block_size;
+        auto resolve = [&]() { stream_resolve(rc, s_pend, count, lane); count = 0; };
+        // edge test: byte offset of the bitmap word from the top 16 bits, bit index in the low 5 (the shift uses them alone)
+#define ST_TEST(E) h = __funnelshift_r(h, s_bm[(uint32_t)(E) >> 16] >> ((uint32_t)(E) & 31u), 1)
+        const int my_units = (s0 + warp < s1) ? (int)((s1 - s0 - warp + nw - 1) / nw) : 0;
+        const int4* p = colv + (s0 + warp) * (AT_STREAM_UNIT / 4) + lane;
+        const size_t pstep = (size_t)nw * (AT_STREAM_UNIT / 4);
+        uint32_t ucur = (uint32_t)(s0 + warp);                  // unit being processed
+        const int4* pn = p;                                     // next unit to request
+        int to_load = my_units;
+        auto load_next = [&](int4& x0, int4& x1) {              // streaming loads (evict-first), the warp's units in order
+            if (to_load > 0) {
+                x0 = __ldcs(pn);
+                x1 = __ldcs(pn + 32);
+                pn += pstep;
+            }
+            --to_load;
+        };
+        auto process = [&](const int4 x0, const int4 x1) {
+            uint32_t h = 0;
+            ST_TEST(x0.x); ST_TEST(x0.y); ST_TEST(x0.z); ST_TEST(x0.w);
+            ST_TEST(x1.x); ST_TEST(x1.y); ST_TEST(x1.z); ST_TEST(x1.w);
+            uint32_t any = __ballot_sync(0xffffffffu, h != 0u);
+            if (any) {
+                h >>= 24;                                        // bits 0..3: entries of x0, bits 4..7: entries of x1
+                do {
+                    if (count > ST_PEND - 32) resolve();
+                    if (h != 0u) {
+                        const int b = __ffs((int)h) - 1;
+                        h &= h - 1u;
+                        const int4 xs = (b & 4) ? x1 : x0;
+                        const int e = (b & 2) ? ((b & 1) ? xs.w : xs.z) : ((b & 1) ? xs.y : xs.x);
+                        s_pend[count + __popc(any & lt_mask)] = make_uint2((uint32_t)e, ucur);
+                    }
+                    count += __popc(any);
+                    any = __ballot_sync(0xffffffffu, h != 0u);
+                } while (any);
+            }
+            ucur += (uint32_t)nw;
+        };
+        // UF register sets: slot u is processed, then refilled with the unit UF places further on (indices are static
+        // after unrolling, so the sets live in registers)
+        int4 x0[UF], x1[UF];
+#pragma unroll
+        for (int u = 0; u < UF; ++u) { x0[u] = make_int4(0, 0, 0, 0); x1[u] = x0[u]; load_next(x0[u], x1[u]); }
+        for (int k = my_units; k > 0; k -= UF) {
+#pragma unroll
+            for (int u = 0; u < UF; ++u) {
+                if (u < k) {
+                    process(x0[u], x1[u]);
+                    load_next(x0[u], x1[u]);
+                }
+            }
+        }
+#undef ST_TEST
+        if (count > 0) resolve();                                // the code array of the next block is another one
+    }
+}
+
+// ------------------------------------------------------------------------------- stream-layout update
+// Second kernel of a stream-layout step: transmission decision + progression + encoding of the next step
+// (reference: transition.py:219-252, seirm_progression/transition.py:41-121).  A CTA takes whole row tiles and works in
+// phases that each touch only the rows that need them (most rows of a step need nothing but their zeroed outputs):
+//   0  zero-fill the tile's dne_dr / code_out / hot words with 128-bit stores; stage the tile's row bitmaps in shared memory
+//   1  sum the tile's hit records (row in tile, source code) into one 64-bit FIXED-POINT lambda per row in shared memory
+//      (integer atomics: the order of the records does not matter, the sum is bitwise reproducible; scale 2^fx_shift chosen
+//      so that in-degree * largest term < 2^62)
+//   A  compact the exposure candidates (susceptible rows with lambda != 0) of the tile and decide them densely, one
+//      candidate per thread: noise, p = 1 - exp(-lambda), stage / timer writes, d ne / dR
+//   B  32-row tasks that hold a row in E or I: progression and the code of the next step, lane <-> row
+// The per-row logic is the one of seirm_kernel's update_subtask (the generic kernel), restated for launches with
+// transmission (row bitmaps valid, no AT_DO_INIT).
+#define TU_THREADS 256
+#define TU_MAX_TASKS (AT_STREAM_MAX_TILE_ROWS / 32)
+template <bool TF32, bool GRAD>
+__global__ void __launch_bounds__(TU_THREADS, 4)
+stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
+{
+    AT_DYNAMIC_SMEM(unsigned char, smem_raw, 128);
+    // [s_fix i64 n_sfs*NC][s_A f32 256][s_G f32 256][s_lam i64 tile_rows][s_cand u16 tile_rows]
+    long long* s_fix = reinterpret_cast<long long*>(smem_raw);
+    float* s_A = reinterpret_cast<float*>(s_fix + m.n_sfs * NC);
+    float* s_G = s_A + 256;
+    long long* s_lam = reinterpret_cast<long long*>(s_G + 256);
+    uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_lam + a.tile_rows);
+    __shared__ long long s_red[TU_THREADS / 32][3];
+    __shared__ unsigned long long s_tmax;
+    __shared__ uint32_t s_w[3][TU_MAX_TASKS], s_orig[3][TU_MAX_TASKS], s_hot[TU_MAX_TASKS];   // sus / exp / inf words of the tile
+    __shared__ int s_is_last, s_any_out, s_ncand;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = TU_THREADS / 32;
     const bool age_f32 = a.age_dtype == AT_AGE_F32;
-    const int block = (int)(blockIdx.x % a.n_blocks);
+    const bool do_prog = (a.flags & AT_DO_PROGRESSION) != 0, do_enc = (a.flags & AT_DO_ENCODE) != 0;
+    const int t = a.t;
     const float R = a.r_value[a.r_index];
     const double ibar = (double)m.ibar;
-    if (tid == 0) s_any_hot_p = 0;
-    for (int c = tid; c < 256; c += blockDim.x) {
+    const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
+    char* ws = reinterpret_cast<char*>(a.workspace);
+
+    if (tid == 0) { s_tmax = 0ull; s_any_out = 0; s_ncand = 0; }
+    for (int c = tid; c < 256; c += TU_THREADS) {
         float av = 0.f, gv = 0.f;
         if (c >= 1 && c <= 3 * m.n_lg) {
             const int sidx = (c - 1) / m.n_lg, idx = (c - 1) % m.n_lg;
@@ -774,211 +953,254 @@ gather_packed_kernel(const KModel m, const at_seirm_launch a, const int bm_words
         s_G[c] = gv;
     }
     __syncthreads();
-    unsigned char* wsm = smem_raw + warp * WSM;
-    int32_t* s_col = reinterpret_cast<int32_t*>(wsm);
-    uint16_t* s_pos = reinterpret_cast<uint16_t*>(wsm + 2 * CAP * 4);                 // [CAP] positions of the hits, edge order
-    uint32_t* s_dirty = reinterpret_cast<uint32_t*>(wsm + 2 * CAP * 4 + CAP * 2);     // [64] rows of the tile with a partial
-    uint32_t* s_sus = s_dirty + 64;                                                   // [64] susceptible rows of the tile
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_sus + 64);
-    for (int i = tid; i < m.n_sfs * NC; i += blockDim.x) {
-        const int ag = i / NC, c = i % NC;
-        const float s = m.sfs[ag];
-        const float av = c < 256 ? s_A[c] : 0.f, gv = c < 256 ? s_G[c] : 0.f;
-        s_T[i] = (double)__fmul_rn(__fmul_rn(__fmul_rn(R, s), av), gv) / ibar;
-        s_T1[i] = (double)__fmul_rn(__fmul_rn(s, av), gv) / ibar;
-    }
+    // R != 0: lambda terms f64(f32(((R*S)*A)*G)) / I_bar, the reference's message (transition.py:78-83), rounded once to the
+    // 2^-fx_shift grid; R == 0 (lambda == 0 everywhere): the terms of d lambda / dR instead, all the update then needs
+    double* s_Td = reinterpret_cast<double*>(s_fix);
     {
-        const uint4* src = reinterpret_cast<const uint4*>(a.hot_bitmap_in + (size_t)block * (a.block_size >> 5));
-        uint4* dst = reinterpret_cast<uint4*>(const_cast<unsigned char*>(s_bm));
-        uint32_t seen = 0;
-        for (int i = tid; i < (bm_words >> 2); i += blockDim.x) {
-            const uint4 v = __ldg(src + i);
-            dst[i] = v;
-            seen |= v.x | v.y | v.z | v.w;
+        double mymax = 0.0;
+        for (int i = tid; i < m.n_sfs * NC; i += TU_THREADS) {
+            const int ag = i / NC, c = i % NC;
+            const float s = m.sfs[ag];
+            const float av = c < 256 ? s_A[c] : 0.f, gv = c < 256 ? s_G[c] : 0.f;
+            const double d = (R != 0.f) ? (double)__fmul_rn(__fmul_rn(__fmul_rn(R, s), av), gv) / ibar
+                                        : (double)__fmul_rn(__fmul_rn(s, av), gv) / ibar;
+            s_Td[i] = d;
+            const double ad = fabs(d);
+            if (ad < 1e300 && ad > mymax) mymax = ad;
         }
-        if (seen != 0u) s_any_hot_p = 1;                     // benign race: every writer stores 1
-        if (lane == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
-        fence_mbarrier_init();
+        if (mymax > 0.0) atomicMax(&s_tmax, (unsigned long long)__double_as_longlong(mymax));   // bit order == value order
     }
-    for (int i = lane; i < 2 * CAP; i += 32) s_col[i] = 0;
-    fence_proxy_async_smem();
     __syncthreads();
-    const bool any_hot = s_any_hot_p != 0;
+    int fx_shift = 0;
+    {
+        const double tmax = __longlong_as_double((long long)s_tmax);
+        if (tmax > 0.0) {
+            int ex = 0;
+            frexp(tmax, &ex);                                   // tmax < 2^ex
+            fx_shift = 62 - ex - a.lam_deg_bits;
+            fx_shift = fx_shift > 1000 ? 1000 : (fx_shift < -1000 ? -1000 : fx_shift);
+        }
+    }
+    for (int i = tid; i < m.n_sfs * NC; i += TU_THREADS) {
+        const double d = s_Td[i];                               // written by this thread
+        s_fix[i] = (fabs(d) < 1e300) ? __double2ll_rn(ldexp(d, fx_shift)) : 0ll;
+    }
+    __syncthreads();
+    const double inv_scale = ldexp(1.0, -fx_shift);             // exact power of two
+    const double inv_r = (R != 0.f) ? 1.0 / (double)R : 1.0;
 
-    const int TILE = 1 << tile_shift, wpt = TILE >> 5;                       // rows / bitmap words per tile (wpt <= 64)
-    const int n_tiles = (int)(a.n_rows_pad >> tile_shift);
-    const int ntasks32 = (int)(a.n_rows_pad >> 5);
-    const int2* seg_b = reinterpret_cast<const int2*>(a.seg_info) + (size_t)block * n_tiles;
-    const uint8_t* code_b = a.code_in + (size_t)block * a.block_size;
-    double2* part_b = reinterpret_cast<double2*>(a.lam_part) + (size_t)block * a.n_rows_pad;
-    uint32_t* dirty_b = a.dirty + (size_t)block * ntasks32;
-    const int ctas_b = ((int)gridDim.x - block + a.n_blocks - 1) / a.n_blocks;      // CTAs serving this block
-    const int first = ((int)blockIdx.x / a.n_blocks) * nw + warp, stride = ctas_b * nw;
+    const int tile_rows = a.tile_rows, tpt = tile_rows >> 5;   // 32-row tasks per tile
+    const int n_tiles = (int)(a.n_rows_pad / tile_rows);
+    const int n_rows = (int)a.n_rows;
+    uint8_t* code_out = a.code_out + a.row_offset;
+    uint32_t* hot_out = a.hot_bitmap_out + (a.row_offset >> 5);
+    const uint64_t agent0 = (uint64_t)a.row_offset;
+    long long acc_ne = 0, acc_dne = 0, acc_dead = 0;
 
-    // segment metadata, prefetched two tiles ahead (raw = loads in flight, finalised one iteration later)
-    struct Seg { int base4, len; uint32_t sus0, sus1; };
-    auto load_seg = [&](int tile) -> Seg {
-        Seg r; r.base4 = 0; r.len = 0; r.sus0 = 0; r.sus1 = 0;
-        if (tile < n_tiles) {
-            const int2 sg = seg_b[tile];
-            r.base4 = sg.x; r.len = sg.y;
-            const uint32_t* sw = a.sus_bitmap + (size_t)tile * wpt;
-            if (lane < wpt) r.sus0 = sw[lane];
-            if (lane + 32 < wpt) r.sus1 = sw[lane + 32];
-        }
-        return r;
+    auto ld_timer = [&](const void* p, int row) -> int {
+        return TF32 ? (int)reinterpret_cast<const float*>(p)[row] : (int)reinterpret_cast<const int16_t*>(p)[row];
     };
-    auto finalize = [&](Seg r) -> Seg {
-        // no infectious source in this column block, or no susceptible row in the tile: nothing to stream
-        if (!any_hot || !__any_sync(0xffffffffu, (r.sus0 | r.sus1) != 0u)) r.len = 0;
-        return r;
+    auto st_timer = [&](void* p, int row, int v) {
+        if (TF32) reinterpret_cast<float*>(p)[row] = (float)v; else reinterpret_cast<int16_t*>(p)[row] = (int16_t)v;
     };
-    uint32_t issued = 0, consumed = 0;                        // chunks of this warp; chunk k lives in slot k & 1
-    auto issue_chunk = [&](int base4, int len, int ci) {
-        if (lane == 0) {
-            const uint32_t slot = issued & 1u;
-            const int off = ci * CAP;
-            const uint32_t bytes = (uint32_t)((min(CAP, len - off) + 3) & ~3) * 4u;
-            mbar_expect_tx(&s_bar[slot], bytes);
-            bulk_g2s(s_col + slot * CAP, a.col + ((int64_t)base4 * 4 + off), bytes, &s_bar[slot]);
+    // infectiousness code of step t_encode for a row in stage class sidx infected at itime (0: contributes nothing)
+    auto encode = [&](int sidx, int itime) -> uint32_t {
+        int idx = a.t_encode - itime - 1;
+        if (idx < 0 || idx >= m.n_lg) {
+            if (a.error_flag && sidx < m.n_sfi && m.sfi[sidx] != 0.f) *a.error_flag = 1;
+            idx = idx < 0 ? 0 : m.n_lg - 1;
         }
-        ++issued;
+        uint32_t code = 1u + (uint32_t)(sidx * m.n_lg + idx);
+        if (s_A[code] == 0.f || s_G[code] == 0.f) code = 0;       // contributes exactly 0 to every lambda
+        return code;
     };
 
-    Seg g0 = finalize(load_seg(first)), g1 = finalize(load_seg(first + stride));
-    Seg raw = load_seg(first + 2 * stride);
-    bool first_issued = false;                                // chunk 0 of g0 is already in flight
-    for (int tile = first; tile < n_tiles; tile += stride) {
-        const Seg sg = g0;
-        g0 = g1;
-        g1 = finalize(raw);
-        raw = load_seg(tile + 3 * stride);
-        uint32_t* dirty_t = dirty_b + (size_t)tile * wpt;
-        if (sg.len == 0) {
-            if (lane < wpt) dirty_t[lane] = 0u;
-            if (lane + 32 < wpt) dirty_t[lane + 32] = 0u;
-            first_issued = false;
-            continue;
+    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
+        const int row_base = tile * tile_rows;
+        const int rows_here = min(tile_rows, n_rows - row_base);        // valid rows of the tile (<= 0: padding only)
+        const uint32_t nrec = a.tile_count[tile];
+        // ---- phase 0: outputs of rows that need nothing, bitmaps of the tile
+        if (GRAD) {
+            float4* d4 = reinterpret_cast<float4*>(a.dne_dr + row_base);
+            for (int i = tid; i * 4 < rows_here; i += TU_THREADS) {
+                if (i * 4 + 4 <= rows_here) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                else for (int r = i * 4; r < rows_here; ++r) a.dne_dr[row_base + r] = 0.f;
+            }
         }
-        s_sus[lane] = sg.sus0; s_sus[lane + 32] = sg.sus1;
-        s_dirty[lane] = 0u; s_dirty[lane + 32] = 0u;
-        __syncwarp();
-        if (!first_issued) issue_chunk(sg.base4, sg.len, 0);
-        first_issued = false;
-        const int64_t row_base = (int64_t)tile << tile_shift;
-        const int nch = (sg.len + CAP - 1) / CAP;
-        // the run of hits that may continue in the next batch / chunk: row, lambda, d lambda / dR (warp-uniform)
-        int carry_row = -1;
-        double carry = 0.0, carry1 = 0.0;
-        auto write_partial = [&](int row, double v, double v1) {
-            if (v != 0.0 || v1 != 0.0) {
-                part_b[row_base + row] = make_double2(v, v1);
-                atomicOr(&s_dirty[row >> 5], 1u << (row & 31));          // integer OR on a warp-private word
+        if (do_enc) {
+            uint4* c4 = reinterpret_cast<uint4*>(code_out + row_base);
+            for (int i = tid; i * 16 < rows_here; i += TU_THREADS) {
+                if (i * 16 + 16 <= rows_here) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+                else for (int r = i * 16; r < rows_here; ++r) code_out[row_base + r] = 0;
             }
-        };
-        for (int ci = 0; ci < nch; ++ci) {
-            // successor in flight before this chunk is touched: the segment's next chunk, else the next segment's first
-            if (ci + 1 < nch) issue_chunk(sg.base4, sg.len, ci + 1);
-            else if (g0.len > 0) { issue_chunk(g0.base4, g0.len, 0); first_issued = true; }
-            const uint32_t slot = consumed & 1u;
-            mbar_wait(&s_bar[slot], (consumed >> 1) & 1u);
-            ++consumed;
-            const int n = min(CAP, sg.len - ci * CAP);
-            const int32_t* sc = s_col + slot * CAP;
-            const int4* sc4 = reinterpret_cast<const int4*>(sc) + lane * RL4;
-            uint32_t h = 0;
-#pragma unroll
-            for (int q = 0; q < RL4; ++q) {
-                const int4 c = sc4[q];
-                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.x >> 3) & (SRC_MASK >> 5 << 2)));
-                const uint32_t w1 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.y >> 3) & (SRC_MASK >> 5 << 2)));
-                const uint32_t w2 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.z >> 3) & (SRC_MASK >> 5 << 2)));
-                const uint32_t w3 = *reinterpret_cast<const uint32_t*>(s_bm + (((uint32_t)c.w >> 3) & (SRC_MASK >> 5 << 2)));
-                h = __funnelshift_r(h, w0 >> (c.x & 31), 1);
-                h = __funnelshift_r(h, w1 >> (c.y & 31), 1);
-                h = __funnelshift_r(h, w2 >> (c.z & 31), 1);
-                h = __funnelshift_r(h, w3 >> (c.w & 31), 1);
-            }
-            h >>= (32 - RL);                                            // edge j of this lane's run is bit j
-            {
-                const int mine = n - lane * RL;
-                h &= mine >= RL ? 0xffffffffu >> (32 - RL) : (mine <= 0 ? 0u : ((1u << mine) - 1u));
-            }
-            if (__any_sync(0xffffffffu, h != 0u)) {
-                // keep the hits of susceptible rows only (nobody else's lambda is used)
-                {
-                    uint32_t hh = h;
-                    while (hh) {
-                        const int b = __ffs(hh) - 1;
-                        hh &= hh - 1u;
-                        const uint32_t row = (uint32_t)sc[lane * RL + b] >> AT_PACKED_SRC_BITS;
-                        if (!((s_sus[row >> 5] >> (row & 31u)) & 1u)) h &= ~(1u << b);
-                    }
-                }
-                int incl = __popc(h);
-                const int cnt = incl;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const int nh = __shfl_sync(0xffffffffu, incl, 31);
-                {
-                    int off = incl - cnt;
-                    uint32_t hh = h;
-                    while (hh) {
-                        s_pos[off++] = (uint16_t)(lane * RL + (__ffs(hh) - 1));
-                        hh &= hh - 1u;
-                    }
-                }
-                __syncwarp();
-                for (int base = 0; base < nh; base += 32) {
-                    const int i = base + lane;
-                    const int nvalid = min(32, nh - base);
-                    const bool valid = lane < nvalid;
-                    int row = -2 - lane;                                  // never equal to a row or to another lane's filler
-                    double v = 0.0, v1 = 0.0;
-                    if (valid) {
-                        const uint32_t e = (uint32_t)sc[s_pos[i]];
-                        row = (int)(e >> AT_PACKED_SRC_BITS);
-                        const uint32_t code = __ldg(code_b + (e & SRC_MASK));
-                        int ag = load_age(a.age, row_base + row, age_f32);
-                        ag = ag < 0 ? 0 : (ag >= m.n_sfs ? m.n_sfs - 1 : ag);
-                        v = s_T[ag * NC + code];
-                        if (want_grad) v1 = s_T1[ag * NC + code];
-                    }
-                    // runs of equal rows; the first lane's run may continue the carry
-                    int prow = __shfl_up_sync(0xffffffffu, row, 1);
-                    if (lane == 0) prow = -1;
-                    const uint32_t heads = __ballot_sync(0xffffffffu, row != prow);          // bit 0 always set
-                    const int head = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
-                    const bool tail = valid && (lane == nvalid - 1 || ((heads >> (lane + 1)) & 1u));
-                    const int rlen = lane - head + 1;
-                    int K = tail ? rlen : 0;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) K = max(K, __shfl_xor_sync(0xffffffffu, K, o));
-                    const bool cont = (__shfl_sync(0xffffffffu, row, 0) == carry_row);
-                    double sum = 0.0, sum1 = 0.0;
-                    if (head == 0 && cont) { sum = carry; sum1 = carry1; }
-                    for (int k = K - 1; k >= 0; --k) {                    // lanes head .. tail, in edge order
-                        const double x = __shfl_up_sync(0xffffffffu, v, k);
-                        const double x1 = __shfl_up_sync(0xffffffffu, v1, k);
-                        if (tail && k < rlen) { sum += x; sum1 += x1; }
-                    }
-                    if (!cont && carry_row >= 0 && lane == 0) write_partial(carry_row, carry, carry1);
-                    if (tail && lane != nvalid - 1) write_partial(row, sum, sum1);
-                    carry_row = __shfl_sync(0xffffffffu, row, nvalid - 1);
-                    carry = __shfl_sync(0xffffffffu, sum, nvalid - 1);
-                    carry1 = __shfl_sync(0xffffffffu, sum1, nvalid - 1);
-                }
-            }
-            __syncwarp();                                                // slot and position list are reused
         }
-        if (carry_row >= 0 && lane == 0) write_partial(carry_row, carry, carry1);
-        __syncwarp();
-        if (lane < wpt) dirty_t[lane] = s_dirty[lane];
-        if (lane + 32 < wpt) dirty_t[lane + 32] = s_dirty[lane + 32];
-        __syncwarp();
+        if (tid < tpt) {
+            const int task = tile * tpt + tid;
+            const uint32_t sw = a.sus_bitmap[task], ew = a.exp_bitmap[task], iw = a.inf_bitmap[task];
+            s_w[0][tid] = sw; s_w[1][tid] = ew; s_w[2][tid] = iw;
+            s_orig[0][tid] = sw; s_orig[1][tid] = ew; s_orig[2][tid] = iw;
+            s_hot[tid] = 0u;
+            if (do_enc) hot_out[task] = 0u;
+        }
+        if (nrec != 0u) for (int i = tid; i < tile_rows; i += TU_THREADS) s_lam[i] = 0ll;
+        __syncthreads();
+        if (nrec != 0u) {
+            // ---- phase 1: records -> fixed-point lambda per row
+            const uint32_t* recs = a.rec + a.tile_rec_base[tile];
+            for (uint32_t i = tid; i < nrec; i += TU_THREADS) {
+                const uint32_t rec = recs[i];
+                const int r = (int)(rec >> 8);
+                int ag = (r < rows_here) ? load_age(a.age, row_base + r, age_f32) : 0;
+                ag = ag < 0 ? 0 : (ag >= m.n_sfs ? m.n_sfs - 1 : ag);
+                const long long v = s_fix[ag * NC + (int)(rec & 255u)];
+                if (v != 0ll) atomicAdd(reinterpret_cast<unsigned long long*>(s_lam) + r, (unsigned long long)v);
+            }
+            __syncthreads();
+            if (tid == 0) a.tile_count[tile] = 0u;
+            // ---- phase A: the exposure candidates of the tile, compacted (lambda != 0, or with R == 0 d lambda / dR != 0,
+            //      <=> a non-zero fixed-point sum)
+            for (int tk = warp; tk < tpt; tk += nw) {
+                const uint32_t sw = s_w[0][tk];
+                const bool cand = ((sw >> lane) & 1u) && s_lam[tk * 32 + lane] != 0ll;
+                const uint32_t cw = __ballot_sync(0xffffffffu, cand);
+                if (cw != 0u) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_ncand, __popc(cw));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (cand) s_cand[base + __popc(cw & ((1u << lane) - 1u))] = (uint16_t)(tk * 32 + lane);
+                }
+            }
+            __syncthreads();
+            const int ncand = s_ncand;
+            for (int i = tid; i < ncand; i += TU_THREADS) {
+                const int r = (int)s_cand[i];
+                const int row = row_base + r;
+                const double v = (double)s_lam[r] * inv_scale;
+                const double lam = (R != 0.f) ? v : 0.0, lam1 = v * inv_r;
+                float wiso = 0.f, u = 0.f;
+                if (a.iso_mode == AT_ISO_TENSOR) wiso = a.isolation[row];
+                if (a.u_mode == AT_U_TENSOR) u = a.uniform[row];
+                if (a.iso_mode != AT_ISO_TENSOR || a.u_mode != AT_U_TENSOR) {
+                    const uint64_t z = at_noise_u64(seed, (uint32_t)t, agent0 + (uint64_t)row);
+                    if (a.u_mode != AT_U_TENSOR) u = at_u_exposure(z);
+                    if (a.iso_mode == AT_ISO_HASH_SOFT) wiso = at_u_isolation(z);
+                    else if (a.iso_mode == AT_ISO_HASH_HARD) wiso = at_u_isolation(z) < a.p_isolate ? 1.0f : 0.0f;
+                }
+                // p = 1 - exp(-lambda) (transition.py:220-221); u < p decided in float32 when it is far from the threshold
+                // (|error of p32| < 4e-6 for lambda < 88), in float64 otherwise: the decisions of the float64 reference
+                const float q32 = __expf(-(float)lam);
+                const float p32 = 1.0f - q32;
+                bool hit;
+                if (fabsf(u - p32) > 2e-5f) hit = u < p32;
+                else hit = (double)u < 1.0 - exp(-lam);
+                const float omw = 1.0f - wiso;                  // float32, as (1.0 - will_isolate)
+                const float ne = hit ? omw : 0.0f;
+                if (GRAD) {
+                    const float dne = omw * q32 * (float)lam1;
+                    acc_dne += __double2ll_rn((double)dne * FX_SCALE);
+                    a.dne_dr[row] = dne;
+                }
+                if (ne != 0.0f) {
+                    a.stage[row] = ne;                         // 0 + ne
+                    st_timer(a.next_stage_time, row, t + 1 + m.e2i);
+                    st_timer(a.infected_time, row, t);
+                    acc_ne += __double2ll_rn((double)ne * FX_SCALE);
+                    const uint32_t bit = 1u << (r & 31);
+                    atomicAnd(&s_w[0][r >> 5], ~bit);
+                    if (ne == 1.0f) atomicOr(&s_w[1][r >> 5], bit);
+                    else if (do_enc && ne > 0.0f && ne < 3.0f) {
+                        // fractional stage (soft isolation, Q4): indexes SFInfector[int(stage)], never progresses
+                        const uint32_t code = encode((int)ne, t);
+                        if (code != 0u) { code_out[row] = (uint8_t)code; atomicOr(&s_hot[r >> 5], bit); }
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_ncand = 0;
+        }
+        // ---- phase B: tasks with a row in E or I (timers written in phase A are visible: same CTA, after the barrier)
+        for (int tk = warp; tk < tpt; tk += nw) {
+            const uint32_t exp_w = s_w[1][tk], inf_w = s_w[2][tk];
+            const uint32_t frac_hot = s_hot[tk];
+            if ((exp_w | inf_w) == 0u) {
+                if (frac_hot != 0u && lane == 0) { hot_out[tile * tpt + tk] = frac_hot; s_any_out = 1; }
+                continue;
+            }
+            const int task = tile * tpt + tk;
+            const int row = task * 32 + lane;
+            bool is_e = (exp_w >> lane) & 1u, is_i = (inf_w >> lane) & 1u;
+            uint32_t code = 0;
+            if (is_e || is_i) {
+                if (do_prog) {
+                    const int nst = ld_timer(a.next_stage_time, row);
+                    if (nst <= t) {                              // progression (seirm_progression/transition.py:41-88)
+                        if (is_i) {
+                            acc_dead += 1;                      // stage * rd / INFECTED_VAR = 2/2
+                            if (a.recovered_step) a.recovered_step[row] = (uint8_t)t;
+                        }
+                        if (nst == t) st_timer(a.next_stage_time, row, is_i ? m.inf_time : t + m.i2r);
+                        a.stage[row] = is_i ? 3.0f : 2.0f;
+                        const bool was_e = is_e;
+                        is_e = false;
+                        is_i = was_e;
+                    }
+                }
+                if (do_enc && (is_e || is_i)) code = encode(is_e ? 1 : 2, ld_timer(a.infected_time, row));
+            }
+            const uint32_t hot = __ballot_sync(0xffffffffu, code != 0u) | frac_hot;
+            if (code != 0u) code_out[row] = (uint8_t)code;
+            const uint32_t exp_o = __ballot_sync(0xffffffffu, is_e);
+            const uint32_t inf_o = __ballot_sync(0xffffffffu, is_i);
+            if (lane == 0) {
+                if (do_enc && hot != 0u) { hot_out[task] = hot; s_any_out = 1; }     // benign race: every writer stores 1
+                s_w[1][tk] = exp_o; s_w[2][tk] = inf_o;
+            }
+        }
+        __syncthreads();
+        // ---- the tile's bitmap words that changed; hot words of tasks without a hot row
+        if (tid < tpt) {
+            const int task = tile * tpt + tid;
+            if (s_w[0][tid] != s_orig[0][tid]) a.sus_bitmap[task] = s_w[0][tid];
+            if (s_w[1][tid] != s_orig[1][tid]) a.exp_bitmap[task] = s_w[1][tid];
+            if (s_w[2][tid] != s_orig[2][tid]) a.inf_bitmap[task] = s_w[2][tid];
+        }
+        __syncthreads();                                         // shared arrays are reused by the next tile
+    }
+
+    // ---- daily sums: fixed-point integers, so the result does not depend on the schedule
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_ne += __shfl_down_sync(0xffffffffu, acc_ne, o);
+        acc_dne += __shfl_down_sync(0xffffffffu, acc_dne, o);
+        acc_dead += __shfl_down_sync(0xffffffffu, acc_dead, o);
+    }
+    if (lane == 0) { s_red[warp][0] = acc_ne; s_red[warp][1] = acc_dne; s_red[warp][2] = acc_dead; }
+    __syncthreads();
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(ws + WS_ACC);
+    int* ticket = reinterpret_cast<int*>(ws + WS_TICKET);
+    if (tid == 0) {
+        long long s0 = 0, s1 = 0, s2 = 0;
+        for (int w = 0; w < nw; ++w) { s0 += s_red[w][0]; s1 += s_red[w][1]; s2 += s_red[w][2]; }
+        if (s0) atomicAdd(&acc[0], (unsigned long long)s0);
+        if (s1) atomicAdd(&acc[1], (unsigned long long)s1);
+        if (s2) atomicAdd(&acc[2], (unsigned long long)s2);
+        if (s_any_out) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_ANYHOT), 1u);
+        __threadfence();
+        s_is_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_is_last && tid == 0) {
+        __threadfence();
+        const volatile long long* av = reinterpret_cast<const volatile long long*>(acc);
+        const double s0 = (double)av[0] / FX_SCALE, s1 = (double)av[1] / FX_SCALE, s2 = (double)av[2];
+        if (a.daily_infected) a.daily_infected[t] += (float)s0;          // transition.py:235
+        if (a.sum_dne_dr) a.sum_dne_dr[t] = (float)s1;
+        if (do_prog) {
+            if (a.death_count) a.death_count[t] = (float)s2;
+            if (a.daily_deaths) a.daily_deaths[t] += (float)s2 * a.m_value[0];   // progression :52-60
+        }
+        acc[0] = 0; acc[1] = 0; acc[2] = 0;
+        *ticket = 0;
     }
 }
 
@@ -1300,14 +1522,14 @@ static int dispatch(const KModel& km, const at_seirm_launch& a, int grid, int th
     return fail("%s", "edges_per_chunk must be 512, 768 or 1024");
 }
 
-template <int RL4>
-static int launch_packed(const KModel& km, const at_seirm_launch& a, int grid, int threads, size_t smem, int bm_words, int NC, int tile_shift, cudaStream_t s) {
-    auto k = gather_packed_kernel<RL4>;
+template <int NTHREADS, int UF>
+static int launch_stream(const at_seirm_launch& a, int grid, int threads, size_t smem, int bm_words, int tile_shift, cudaStream_t s) {
+    auto k = stream_gather_kernel<NTHREADS, UF>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    AT_LAUNCH_SMEM(k, grid, threads, smem, s, km, a, bm_words, NC, tile_shift);
+    AT_LAUNCH_SMEM(k, grid, threads, smem, s, a, bm_words, tile_shift);
     e = cudaGetLastError();
-    if (e != cudaSuccess) return fail("gather_packed_kernel launch: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail("stream_gather_kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -1327,13 +1549,14 @@ int64_t at_seirm_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edge
     return ((bytes * 8) / 1024) * 1024;
 }
 
-int64_t at_seirm_packed_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edges_per_chunk, int32_t warps) {
+int64_t at_seirm_stream_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t warps) {
     if (device_props()) return 0;
-    if (warps < 1) warps = NT_MAX / 32;
-    int64_t bytes = (int64_t)g_smem_optin - (int64_t)table_smem(n_sfs, n_lam_gamma) - (int64_t)warps * packed_warp_smem_bytes(edges_per_chunk) - 2048;
+    if (warps < 1) warps = ST_NT / 32;
+    (void)n_sfs; (void)n_lam_gamma;
+    int64_t bytes = (int64_t)g_smem_optin - (int64_t)warps * ST_PEND * 8 - 16 - 16 - 1024;
     if (bytes < 4096) return 0;
     int64_t bits = ((bytes * 8) / 1024) * 1024;
-    return bits > ((int64_t)1 << AT_PACKED_SRC_BITS) ? ((int64_t)1 << AT_PACKED_SRC_BITS) : bits;
+    return bits > AT_STREAM_MAX_BLOCK_SIZE ? AT_STREAM_MAX_BLOCK_SIZE : bits;
 }
 
 int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, void* stream) {
@@ -1345,26 +1568,27 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     if (a.n_rows < 0 || (a.row_offset & 31) != 0 || (a.n_rows_pad & 255) != 0 || a.n_rows_pad < a.n_rows) return fail("%s", "bad n_rows / n_rows_pad / row_offset");
     if (!a.stage || !a.workspace || !a.sus_bitmap || !a.exp_bitmap || !a.inf_bitmap) return fail("%s", "stage / workspace / row bitmaps must not be null");
     const bool do_trans = a.flags & AT_DO_TRANSMISSION;
-    if (a.layout != AT_LAYOUT_BCSR && a.layout != AT_LAYOUT_PACKED) return fail("%s", "unknown layout");
-    const bool packed = a.layout == AT_LAYOUT_PACKED;
+    if (a.layout != AT_LAYOUT_BCSR && a.layout != AT_LAYOUT_STREAM) return fail("%s", "unknown layout");
+    const bool is_stream = a.layout == AT_LAYOUT_STREAM;
     const int epc = a.edges_per_chunk > 0 ? a.edges_per_chunk : 768;
     if (epc != 512 && epc != 768 && epc != 1024) return fail("%s", "edges_per_chunk must be 512, 768 or 1024");
     if (do_trans) {
-        if ((!packed && !a.row_start) || !a.seg_info || !a.col || !a.code_in || !a.hot_bitmap_in || !a.r_value || !a.age) return fail("%s", "transmission needs the graph, code_in, hot_bitmap_in, age, r_value");
+        if ((!is_stream && (!a.row_start || !a.seg_info)) || !a.col || !a.code_in || !a.hot_bitmap_in || !a.r_value || !a.age) return fail("%s", "transmission needs the graph, code_in, hot_bitmap_in, age, r_value");
         if (a.n_blocks < 1 || a.n_blocks > AT_MAX_BLOCKS || a.block_size < 1024 || (a.block_size & 1023)) return fail("%s", "bad n_blocks / block_size");
         if ((int64_t)a.n_blocks * a.block_size < a.n_sources) return fail("%s", "n_blocks * block_size does not cover n_sources");
-        if (!packed && a.rows_per_task != (a.n_blocks > 1 ? 256 : 32)) return fail("%s", "rows_per_task must be 32 (one block) or 256 (several blocks)");
-        if (packed) {
-            if (a.tile_rows < 32 || a.tile_rows > AT_PACKED_MAX_TILE_ROWS || (a.tile_rows & (a.tile_rows - 1)) || (a.n_rows_pad % a.tile_rows))
-                return fail("%s", "packed layout: tile_rows must be a power of two in 32..2048 dividing n_rows_pad");
-            if (a.block_size > (1 << AT_PACKED_SRC_BITS)) return fail("%s", "packed layout: block_size exceeds 2^21 sources");
-            if (a.edge_weight) return fail("%s", "packed layout: edge weights are not supported");
-            if (a.hash_words) return fail("%s", "packed layout: hash_words must be 0");
-            if (!a.lam_part || !a.dirty) return fail("%s", "packed layout needs lam_part / dirty");
+        if (!is_stream && a.rows_per_task != (a.n_blocks > 1 ? 256 : 32)) return fail("%s", "rows_per_task must be 32 (one block) or 256 (several blocks)");
+        if (is_stream) {
+            if (a.tile_rows < 32 || a.tile_rows > AT_STREAM_MAX_TILE_ROWS || (a.tile_rows & (a.tile_rows - 1)) || (a.n_rows_pad % a.tile_rows))
+                return fail("%s", "stream layout: tile_rows must be a power of two in 32..2048 dividing n_rows_pad");
+            if (a.block_size > AT_STREAM_MAX_BLOCK_SIZE) return fail("%s", "stream layout: block_size exceeds 2^21 - 1024 sources");
+            if (a.edge_weight) return fail("%s", "stream layout: edge weights are not supported");
+            if (a.hash_words) return fail("%s", "stream layout: hash_words must be 0");
+            if (!a.unit_tile || !a.block_units || !a.rec || !a.tile_rec_base || !a.tile_count) return fail("%s", "stream layout needs unit_tile, block_units, rec, tile_rec_base and tile_count");
+            if (a.lam_deg_bits < 0 || a.lam_deg_bits > 40) return fail("%s", "stream layout: lam_deg_bits out of range (0..40)");
         }
         if (a.iso_mode == AT_ISO_TENSOR && !a.isolation) return fail("%s", "iso_mode TENSOR without isolation pointer");
         if (a.u_mode == AT_U_TENSOR && !a.uniform) return fail("%s", "u_mode TENSOR without uniform pointer");
-        if (!packed && a.n_blocks > 1 && (!a.lam_part || !a.dirty)) return fail("%s", "n_blocks > 1 needs lam_part / dirty");
+        if (!is_stream && a.n_blocks > 1 && (!a.lam_part || !a.dirty)) return fail("%s", "n_blocks > 1 needs lam_part / dirty");
         if (a.flags & AT_DO_INIT) return fail("%s", "AT_DO_INIT cannot be combined with AT_DO_TRANSMISSION");
     }
     if ((a.flags & AT_DO_PROGRESSION) && (!a.next_stage_time || (a.daily_deaths && !a.m_value))) return fail("%s", "progression needs next_stage_time and m_value");
@@ -1387,7 +1611,7 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     if (warps > NT_MAX / 32) warps = NT_MAX / 32;
     int bm_words = 0;
     const bool hashed = do_trans && a.hash_words > 0;
-    if (do_trans && !packed) {
+    if (do_trans && !is_stream) {
         const int64_t bits = hashed ? (int64_t)a.hash_words * 32 : (int64_t)a.block_size;
         if (hashed && (a.n_blocks != 1 || (a.hash_words & (a.hash_words - 1)) != 0 || a.hash_words < 32)) return fail("%s", "hash_words must be a power of two >= 32 and n_blocks 1");
         while (warps > 4 && bits > at_seirm_max_block_size(model->n_sfs, model->n_lam_gamma, epc, warps)) --warps;
@@ -1407,26 +1631,35 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         if (ugrid > uuseful) ugrid = (int)uuseful;
         if (ugrid < 1) ugrid = 1;
     }
-    if (do_trans && packed) {
-        int pw = a.warps_per_cta > 0 ? a.warps_per_cta : NT_MAX / 32;
-        if (pw > NT_MAX / 32) pw = NT_MAX / 32;
-        while (pw > 4 && a.block_size > at_seirm_packed_max_block_size(model->n_sfs, model->n_lam_gamma, epc, pw)) --pw;
-        if (a.block_size > at_seirm_packed_max_block_size(model->n_sfs, model->n_lam_gamma, epc, pw))
-            return fail("%s", "packed layout: block bitmap exceeds the shared-memory capacity (at_seirm_packed_max_block_size)");
+    if (do_trans && is_stream) {
+        int pw = a.warps_per_cta > 0 ? a.warps_per_cta : ST_NT / 32;
+        if (pw > ST_NT / 32) pw = ST_NT / 32;
+        if (a.block_size > at_seirm_stream_max_block_size(model->n_sfs, model->n_lam_gamma, pw))
+            return fail("%s", "stream layout: block bitmap exceeds the shared-memory capacity (at_seirm_stream_max_block_size)");
         const int words = a.block_size / 32;
-        const size_t smem = (size_t)pw * packed_warp_smem_bytes(epc) + tables + (size_t)words * 4;
+        const size_t smem = (size_t)(words + 4) * 4 + 16 + (size_t)pw * ST_PEND * 8;
         int tile_shift = 0;
         while ((1 << tile_shift) < a.tile_rows) ++tile_shift;
-        int ggrid = grid < a.n_blocks ? a.n_blocks : grid;
+        // the more warps, the fewer registers each has for units in flight: 32 warps x 3 units, 24 x 5, <= 16 x 8 (KB per SM: 96 / 120 / 128)
         int rc;
-        switch (epc) {
-            case 512: rc = launch_packed<4>(km, al, ggrid, pw * 32, smem, words, NC, tile_shift, s); break;
-            case 768: rc = launch_packed<6>(km, al, ggrid, pw * 32, smem, words, NC, tile_shift, s); break;
-            default: rc = launch_packed<8>(km, al, ggrid, pw * 32, smem, words, NC, tile_shift, s); break;
-        }
+        if (pw > 24 && a.tasks_per_group == 2) rc = launch_stream<1024, 2>(al, grid, pw * 32, smem, words, tile_shift, s);
+        else if (pw > 24) rc = launch_stream<1024, 3>(al, grid, pw * 32, smem, words, tile_shift, s);
+        else if (pw > 16) rc = launch_stream<768, 4>(al, grid, pw * 32, smem, words, tile_shift, s);
+        else rc = launch_stream<512, 6>(al, grid, pw * 32, smem, words, tile_shift, s);
         if (rc) return rc;
         al.edges_per_chunk = 512;
-        return launch_kernel<MODE_UPDATE, 4>(km, al, ugrid, 256, smem_update, 0, NC, 8, s);
+        int tgrid = a.grid > 0 ? a.grid : g_sm_count * 4;
+        const int64_t n_tiles = a.n_rows_pad / a.tile_rows;
+        if (tgrid > n_tiles) tgrid = (int)n_tiles;
+        const size_t usmem = (size_t)model->n_sfs * NC * 8 + 2 * 256 * 4 + (size_t)a.tile_rows * 10;
+        const bool tf32 = a.timer_dtype == AT_TIMER_F32, grad = a.dne_dr != nullptr;
+        if (tf32 && grad) AT_LAUNCH_SMEM((stream_update_kernel<true, true>), tgrid, TU_THREADS, usmem, s, km, al, NC);
+        else if (tf32) AT_LAUNCH_SMEM((stream_update_kernel<true, false>), tgrid, TU_THREADS, usmem, s, km, al, NC);
+        else if (grad) AT_LAUNCH_SMEM((stream_update_kernel<false, true>), tgrid, TU_THREADS, usmem, s, km, al, NC);
+        else AT_LAUNCH_SMEM((stream_update_kernel<false, false>), tgrid, TU_THREADS, usmem, s, km, al, NC);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail("stream_update_kernel launch: %s", cudaGetErrorString(e));
+        return 0;
     }
     if (do_trans && a.n_blocks > 1) {
         const int Gg = a.tasks_per_group > 0 ? (a.tasks_per_group > MAXG ? MAXG : a.tasks_per_group) : 1;

@@ -148,14 +148,15 @@ def _ptr(t, dtype=None, name="tensor"):
 class SeirmEngine:
     def __init__(self, graph, spec: SeirmSpec, process_group=None, grid=0, code_len=None, block_size=None,
                  tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0, hashed=None, hash_words=None, hash_min_warps=20, symmetric=None, sparse_exchange=True,
-                 layout="auto", tile_rows=None, packed_warps=14):
+                 layout="auto", tile_rows=None, bank_aware=True):
         """graph: ContactGraph (plain CSR, re-blocked here) or a prebuilt BlockedGraph.  block_size: sources
         per column block (default: the largest that fits the shared-memory bitmap, i.e. as few blocks as
         possible); code_len: length of the code/bitmap arrays (multi-GPU: world_size equal slices).
-        layout: "bcsr" (row_start + col; one exact block, hashed filter or 256-row column blocks), "packed" (every entry
-        carries its row; exact bitmap per column block, gather + update kernels — the layout for source sets beyond one
-        shared-memory bitmap) or "auto" (bcsr when all sources fit one exact bitmap, else packed)."""
-        from .graph import (BlockedGraph, block_graph, block_graph_packed, choose_block_size, choose_edges_per_chunk,
+        layout: "stream" (flat per-source-block streams of self-describing entries against the block's exact bitmap,
+        fixed-point lambda sums, gather + update kernels: any number of sources), "bcsr" (row_start + col; one exact block
+        fused in one kernel, a hashed filter, or 256-row column blocks; the only layout with edge weights) or "auto"
+        (stream unless the graph has edge weights or a bcsr-only option is given)."""
+        from .graph import (BlockedGraph, block_graph, block_graph_stream, choose_block_size, choose_edges_per_chunk,
                             choose_tile_rows)
 
         _require_cuda("SeirmEngine needs the contact graph on a CUDA device; there is no CPU fallback", graph.device.type == "cuda")
@@ -184,27 +185,24 @@ class SeirmEngine:
             with torch.cuda.device(self.device):
                 return int(self.lib.at_seirm_max_block_size(len(spec.sfs), len(spec.lam_gamma), int(epc), int(warps)))
 
-        def packed_capacity(epc, warps):
+        def stream_capacity(warps):
             with torch.cuda.device(self.device):
-                return int(self.lib.at_seirm_packed_max_block_size(len(spec.sfs), len(spec.lam_gamma), int(epc), int(warps)))
+                return int(self.lib.at_seirm_stream_max_block_size(len(spec.sfs), len(spec.lam_gamma), int(warps)))
 
-        if layout not in ("auto", "bcsr", "packed"):
-            raise ValueError("layout must be 'auto', 'bcsr' or 'packed'")
-        full_src = ((n_src + 1023) // 1024) * 1024
+        if layout not in ("auto", "bcsr", "stream"):
+            raise ValueError("layout must be 'auto', 'bcsr' or 'stream'")
         if layout == "auto" and not isinstance(graph, BlockedGraph):
-            explicit_bcsr = block_size is not None or hashed or hash_words or graph.edge_weight is not None
-            layout = "bcsr" if explicit_bcsr or full_src <= capacity(edges_per_chunk or 768, 12) else "packed"
+            bcsr_only = hashed or hash_words or edges_per_chunk or graph.edge_weight is not None
+            layout = "bcsr" if bcsr_only else "stream"
         if isinstance(graph, BlockedGraph):
             self.graph = graph
-        elif layout == "packed":
-            epc = int(edges_per_chunk or 512)
+        elif layout == "stream":
             if block_size is None:
-                _, block_size = choose_block_size(n_src, packed_capacity(epc, packed_warps))
+                _, block_size = choose_block_size(n_src, stream_capacity(warps_per_cta or 0))
             nb = -(-n_src // int(block_size))
             if tile_rows is None:
-                sm = torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == "cuda" else 2
-                tile_rows = choose_tile_rows(graph.n_rows, nb, sm * int(warps_per_cta or packed_warps))
-            self.graph = block_graph_packed(graph, int(block_size), int(tile_rows), epc)
+                tile_rows = choose_tile_rows(graph.n_rows, nb)
+            self.graph = block_graph_stream(graph, int(block_size), int(tile_rows), bank_aware=bool(bank_aware))
         else:
             # one column block if the whole bitmap fits next to >= 12 warps of TMA buffers, else equal blocks
             # sized for 16 warps
@@ -232,7 +230,7 @@ class SeirmEngine:
                 else:
                     _, block_size = choose_block_size(n_src, capacity(epc, 16))
             self.graph = block_graph(graph, int(block_size), edges_per_chunk=edges_per_chunk, hash_words=hash_words)
-        cap4 = (packed_capacity if self.graph.layout == 1 else capacity)(self.graph.edges_per_chunk, 4)
+        cap4 = stream_capacity(self.warps_per_cta or 0) if self.graph.layout == 1 else capacity(self.graph.edges_per_chunk, 4)
         if (self.graph.hash_words * 32 or self.graph.block_size) > cap4:
             raise RuntimeError(f"block_size {self.graph.block_size} exceeds the shared-memory bitmap capacity")
         g = self.graph
@@ -277,8 +275,13 @@ class SeirmEngine:
         self.sus = torch.zeros(nt, dtype=torch.int32, device=dev)
         self.exp = torch.zeros(nt, dtype=torch.int32, device=dev)
         self.inf = torch.zeros(nt, dtype=torch.int32, device=dev)
-        self.lam_part = self.dirty = None
-        if g.n_blocks > 1 or g.layout == 1:
+        self.lam_part = self.dirty = self.rec = self.tile_count = None
+        if g.layout == 1:
+            # stream layout: per-tile lists of hit records (capacity = the tile's edges) and their fill counters, which are all
+            # zero between steps (the update kernel clears what the gather kernel counted)
+            self.rec = torch.empty(max(g.num_edges, 1), dtype=torch.int32, device=dev)
+            self.tile_count = torch.zeros(g.n_rows_pad // g.tile_rows, dtype=torch.int32, device=dev)
+        elif g.n_blocks > 1:
             # per-(column block, row) partial lambdas; only the rows flagged in `dirty` are ever written or read
             self.lam_part = torch.empty((g.n_blocks, g.n_rows_pad, 2), dtype=torch.float64, device=dev)
             self.dirty = torch.zeros((g.n_blocks, nt), dtype=torch.int32, device=dev)
@@ -354,6 +357,14 @@ class SeirmEngine:
         a.recovered_step = _ptr(recovered_step, torch.uint8, "recovered_step")
         a.lam_part, a.dirty = _ptr(self.lam_part), _ptr(self.dirty)
         a.layout, a.tile_rows = int(g.layout), int(g.tile_rows)
+        if g.layout == 1:
+            a.seg_info = None
+            a.unit_tile = _ptr(g.seg_info, torch.int32, "unit_tile")
+            a.block_units = _ptr(g.block_units, torch.int32, "block_units")
+            a.tile_rec_base = _ptr(g.tile_rec_base, torch.int64, "tile_rec_base")
+            a.tile_count = _ptr(self.tile_count, torch.int32, "tile_count")
+            a.rec = _ptr(self.rec, torch.int32, "rec")
+            a.lam_deg_bits = int(g.lam_deg_bits)
         a.workspace = _ptr(self.workspace, torch.float64)
         # check_range=False: the launch encodes the infectiousness of a step that is never simulated (the last step of an
         # episode), so an infection older than lam_gamma_integrals there is not an error — the reference never looks it up

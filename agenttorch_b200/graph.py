@@ -267,7 +267,7 @@ class BlockedGraph:
     block_size: int
     rows_per_task: int
     row_start: torch.Tensor      # (n_blocks, n_rows_pad) int16 holding uint16 offsets inside the segment
-    seg_info: torch.Tensor       # (n_blocks*n_gtasks, 2) int32: (first entry / 4, edges)
+    seg_info: torch.Tensor       # (n_blocks*n_gtasks, 2) int32: (first entry / 4, edges); stream layout: (units,) tile of each unit
     col: torch.Tensor            # (padded edges + TAIL_PAD,) int32
     num_edges: int
     edges_per_chunk: int = 768
@@ -275,8 +275,11 @@ class BlockedGraph:
     edge_weight: Optional[torch.Tensor] = None
     i_bar: float = 1.0
     i_bar_agent: int = -1
-    layout: int = 0              # 0 = BCSR (row_start + col), 1 = packed (every col entry carries its row; include/at_seirm.h)
-    tile_rows: int = 0           # packed layout: rows per tile
+    layout: int = 0              # 0 = BCSR (row_start + col), 1 = stream (self-describing entries; include/at_seirm.h)
+    tile_rows: int = 0           # stream layout: rows per tile
+    block_units: Optional[torch.Tensor] = None   # stream layout: (n_blocks+1,) int32 first unit of every source block
+    tile_rec_base: Optional[torch.Tensor] = None # stream layout: (n_tiles,) int64 first hit-record slot of every tile
+    lam_deg_bits: int = 0        # stream layout: bits of the largest in-degree (head room of the fixed-point sums)
 
     @property
     def device(self):
@@ -295,7 +298,9 @@ class BlockedGraph:
                             self.rows_per_task, self.row_start.to(device), self.seg_info.to(device), self.col.to(device),
                             self.num_edges, self.edges_per_chunk, self.hash_words,
                             None if self.edge_weight is None else self.edge_weight.to(device), self.i_bar, self.i_bar_agent,
-                            self.layout, self.tile_rows)
+                            self.layout, self.tile_rows,
+                            None if self.block_units is None else self.block_units.to(device),
+                            None if self.tile_rec_base is None else self.tile_rec_base.to(device), self.lam_deg_bits)
 
 
 def choose_block_size(n_sources, max_block_size):
@@ -387,31 +392,40 @@ def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = 
                         seg_info, col_out, e, epc, int(hash_words), w_out, graph.i_bar, graph.i_bar_agent)
 
 
-PACKED_SRC_BITS = 21
-PACKED_MAX_TILE_ROWS = 2048
+STREAM_UNIT = 256                       # entries per unit of the stream layout (AT_STREAM_UNIT)
+STREAM_MAX_TILE_ROWS = 2048
+STREAM_MAX_BLOCK_SIZE = (1 << 21) - 1024
 
 
-def choose_tile_rows(n_rows, n_blocks, warps_total, min_segments_per_warp=8):
-    """Rows per tile of the packed layout: as large as the 11 row bits allow, smaller when the shard has so few rows
-    that the warps of the gather grid would get fewer than `min_segments_per_warp` segments each."""
-    tile = PACKED_MAX_TILE_ROWS
-    while tile > 256 and (-(-n_rows // tile)) * n_blocks < warps_total * min_segments_per_warp:
+def choose_tile_rows(n_rows, n_blocks, avg_degree=20.0, max_padding=0.04):
+    """Rows per tile of the stream layout: every (source block, tile) run is padded to whole units of 256 entries, i.e.
+    by half a unit on average, so tiles are as large as the 11 row bits of an entry allow unless the shard is so small
+    that one tile would leave most CTAs without work."""
+    tile = STREAM_MAX_TILE_ROWS
+    while tile > 32 and n_rows < tile * 8:
         tile //= 2
     return tile
 
 
-def block_graph_packed(graph: ContactGraph, block_size: int, tile_rows: int = PACKED_MAX_TILE_ROWS,
-                       edges_per_chunk: int = 512) -> BlockedGraph:
-    """ContactGraph -> packed column-blocked layout (AT_LAYOUT_PACKED, include/at_seirm.h): segment (block, tile) holds the
-    edges of the tile's rows whose source lies in the block, sorted by row and, inside a row, in original edge order, as
-    entries (row_in_tile << 21) | block-local source id.  Replaces the (2,E) COO edge_index of the reference
-    (utils.py:129-148) for source sets that need more than one shared-memory bitmap."""
+def block_graph_stream(graph: ContactGraph, block_size: int, tile_rows: int = STREAM_MAX_TILE_ROWS,
+                       bank_aware: bool = True) -> BlockedGraph:
+    """ContactGraph -> stream layout (AT_LAYOUT_STREAM, include/at_seirm.h): for every source block ONE flat stream of
+    32-bit entries, tile after tile, every (block, tile) run padded to whole 256-entry units with entries that can never
+    hit.  An entry describes itself: (bitmap word of the block-local source << 16) | (row_in_tile << 5) | bit of the source,
+    so the stream needs no per-row metadata and puts no limit on a row's degree.  Replaces the (2,E) COO edge_index of
+    the reference (utils.py:129-148).
+
+    The order of the entries inside a run does not matter (the kernels sum in fixed point), which `bank_aware` uses: the
+    gather kernel tests the 32 entries {128 q + 4 lane + j} of a unit with ONE shared-memory load instruction, so the run
+    is arranged in such groups of 32 with lane = shared-memory bank of the entry's bitmap word (word mod 32) as long as
+    every bank still has entries — those loads are conflict-free — and the few entries of the over-full banks follow in
+    ordinary groups."""
     dev = graph.device
     if graph.edge_weight is not None:
-        raise NotImplementedError("the packed layout does not carry edge weights")
-    if block_size % 1024 or block_size > (1 << PACKED_SRC_BITS):
-        raise ValueError("block_size must be a multiple of 1024 and at most 2^21")
-    if tile_rows & (tile_rows - 1) or not 32 <= tile_rows <= PACKED_MAX_TILE_ROWS:
+        raise NotImplementedError("the stream layout does not carry edge weights")
+    if block_size % 1024 or not 1024 <= block_size <= STREAM_MAX_BLOCK_SIZE:
+        raise ValueError("block_size must be a multiple of 1024 in 1024..2^21-1024")
+    if tile_rows & (tile_rows - 1) or not 32 <= tile_rows <= STREAM_MAX_TILE_ROWS:
         raise ValueError("tile_rows must be a power of two in 32..2048")
     n_rows, e = graph.n_rows, graph.num_edges
     pad = max(tile_rows, 256)
@@ -422,34 +436,87 @@ def block_graph_packed(graph: ContactGraph, block_size: int, tile_rows: int = PA
     n_tiles = n_rows_pad // tile_rows
     shift = tile_rows.bit_length() - 1
     row_ptr = graph.row_ptr.long()
-    rows = torch.repeat_interleave(torch.arange(n_rows, device=dev), row_ptr[1:] - row_ptr[:-1])
+    deg = row_ptr[1:] - row_ptr[:-1]
+    max_deg = int(deg.max()) if n_rows else 0
+    # hit records of a tile: one slot per edge of its rows, so the list can never overflow
+    tile_edges = torch.zeros(n_tiles * tile_rows, dtype=torch.int64, device=dev)
+    tile_edges[:n_rows] = deg
+    tile_edges = tile_edges.reshape(n_tiles, tile_rows).sum(1)
+    tile_rec_base = (torch.cumsum(tile_edges, 0) - tile_edges).contiguous()
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=dev), deg)
+    del deg
     col = graph.col_idx[:e].long()
     blk = torch.div(col, block_size, rounding_mode="floor")
-    key = blk * n_rows_pad + rows                       # (block, row): a stable sort keeps the edge order inside a row
-    if nb > 1:
-        order = torch.sort(key, stable=True).indices
-        key, col, blk = key[order], col[order], blk[order]
-        del order
-    enc = (((key - blk * n_rows_pad) & (tile_rows - 1)) << PACKED_SRC_BITS) | (col - blk * block_size)
-    del col, blk, rows
+    seg = blk * n_tiles + (rows >> shift)                 # run id = block * n_tiles + tile
+    local = col - blk * block_size
+    enc = ((local >> 5) << 16) | ((rows & (tile_rows - 1)) << 5) | (local & 31)
+    bank = (local >> 5) & 31
+    del col, blk, rows, local
     n_seg = nb * n_tiles
-    seg = key >> shift                                  # = block * n_tiles + tile
-    del key
-    seg_len = torch.bincount(seg, minlength=n_seg)
-    seg_pad = ((seg_len + 3) >> 2) << 2
-    seg_base = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
-    seg_base[1:] = torch.cumsum(seg_pad, 0)
-    seg_first = torch.zeros(n_seg, dtype=torch.int64, device=dev)
-    seg_first[1:] = torch.cumsum(seg_len, 0)[:-1]
-    total = int(seg_base[-1])
-    if total // 4 >= 2**31:
-        raise ValueError("graph shard too large for int32 segment bases")
-    pos = torch.arange(e, device=dev) - seg_first[seg] + seg_base[:-1][seg]
-    del seg
-    col_out = torch.zeros(total + TAIL_PAD, dtype=torch.int32, device=dev)
+    GROUP = 32
+    GPU_ = STREAM_UNIT // GROUP                           # groups per unit (8)
+    if bank_aware and e > 0:
+        key = seg * 32 + bank                             # (run, bank) classes
+        order = torch.sort(key, stable=True).indices
+        key, enc = key[order], enc[order]
+        del order, bank
+        seg = key >> 5
+        cls = torch.bincount(key, minlength=n_seg * 32)
+        cls_start = torch.cumsum(cls, 0) - cls
+        rank = torch.arange(e, device=dev) - cls_start[key]          # rank of the entry inside its class
+        # conflict-free groups: as many as the 12th smallest class of the run has entries (below that, banks would need padding)
+        thr = torch.sort(cls.reshape(n_seg, 32), dim=1).values[:, 11].contiguous()
+        seg_len = cls.reshape(n_seg, 32).sum(1)
+        seg_first = torch.cumsum(seg_len, 0) - seg_len
+        left = rank >= thr[seg]
+        cs = torch.cumsum(left.to(torch.int64), 0)
+        cs_before = cs - left.to(torch.int64)
+        left_idx = cs - 1 - cs_before[seg_first.clamp(max=max(e - 1, 0))][seg]      # index among the run's leftover entries
+        n_left = torch.zeros(n_seg, dtype=torch.int64, device=dev)
+        n_left.scatter_add_(0, seg, left.to(torch.int64))
+        group = torch.where(left, thr[seg] + torch.div(left_idx, GROUP, rounding_mode="floor"), rank)
+        lane = torch.where(left, left_idx % GROUP, key & 31)
+        seg_groups = thr + (n_left + (GROUP - 1)) // GROUP
+        seg_groups = torch.where(seg_len > 0, seg_groups, torch.zeros_like(seg_groups))
+        del key, cls, cls_start, rank, left, cs, cs_before, left_idx, n_left
+    else:
+        del bank
+        if nb > 1:
+            order = torch.sort(seg, stable=True).indices  # rows are sorted already, so a run's tiles stay contiguous
+            seg, enc = seg[order], enc[order]
+            del order
+        seg_len = torch.bincount(seg, minlength=n_seg)
+        seg_first = torch.cumsum(seg_len, 0) - seg_len
+        idx = torch.arange(e, device=dev) - seg_first[seg]
+        group, lane = torch.div(idx, GROUP, rounding_mode="floor"), idx % GROUP
+        seg_groups = (seg_len + (GROUP - 1)) // GROUP
+        del idx
+    seg_units = (seg_groups + (GPU_ - 1)) // GPU_
+    unit_base = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
+    unit_base[1:] = torch.cumsum(seg_units, 0)
+    n_units = int(unit_base[-1])
+    if (n_units + 1) * STREAM_UNIT >= 2**32:
+        raise ValueError("graph shard too large for 32-bit stream positions")
+    # group g of a run -> unit g // 8, and inside the unit the entries {128 q + 4 lane + j}, q = (g % 8) // 4, j = g % 4:
+    # the 32 entries one shared-memory load instruction of the gather kernel tests
+    gi = group % GPU_
+    pos = (unit_base[:-1][seg] + torch.div(group, GPU_, rounding_mode="floor")) * STREAM_UNIT + (gi // 4) * 128 + lane * 4 + (gi % 4)
+    del seg, group, lane, gi
+    pad_entry = (block_size >> 5) << 16                   # word block_size/32 of the staged bitmap is always zero
+    pad_entry = pad_entry - 2**32 if pad_entry >= 2**31 else pad_entry
+    col_out = torch.full((max(n_units, 1) * STREAM_UNIT + TAIL_PAD,), pad_entry, dtype=torch.int32, device=dev)
     enc = torch.where(enc >= 2**31, enc - 2**32, enc).to(torch.int32)     # the 32-bit pattern, as int32
     col_out[pos] = enc
-    seg_info = torch.stack(((seg_base[:-1] >> 2), seg_len), dim=1).to(torch.int32).contiguous()
+    del pos, enc
+    tile_of_seg = (torch.arange(n_seg, device=dev) % n_tiles).to(torch.int32)
+    unit_tile = torch.repeat_interleave(tile_of_seg, seg_units)
+    if unit_tile.numel() == 0:
+        unit_tile = torch.zeros(1, dtype=torch.int32, device=dev)
+    block_units = unit_base[torch.arange(nb + 1, device=dev) * n_tiles].to(torch.int32).contiguous()
     row_start = torch.zeros(1, dtype=torch.int16, device=dev)            # unused in this layout
-    return BlockedGraph(n_rows, n_rows_pad, graph.n_sources, graph.row_offset, nb, block_size, tile_rows, row_start,
-                        seg_info, col_out, e, int(edges_per_chunk), 0, None, graph.i_bar, graph.i_bar_agent, 1, tile_rows)
+    g = BlockedGraph(n_rows, n_rows_pad, graph.n_sources, graph.row_offset, nb, block_size, tile_rows, row_start,
+                     unit_tile.contiguous(), col_out, e, 512, 0, None, graph.i_bar, graph.i_bar_agent, 1, tile_rows)
+    g.block_units = block_units
+    g.tile_rec_base = tile_rec_base
+    g.lam_deg_bits = max(int(max_deg).bit_length(), 1)
+    return g

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AT_SEIRM_ABI_VERSION 8
+#define AT_SEIRM_ABI_VERSION 9
 #define AT_MAX_SFS 16        /* SFSusceptibility entries (config.yaml has 9)                     */
 #define AT_MAX_SFI 8         /* SFInfector entries (config.yaml has 5)                           */
 #define AT_MAX_LAMGAMMA 84   /* lam_gamma_integrals entries; 1 + 3*K infectiousness codes fit a byte */
@@ -50,9 +50,10 @@ extern "C" {
 
 /* contact-graph layouts (at_seirm_launch.layout) */
 #define AT_LAYOUT_BCSR 0     /* row_start + seg_info + col: 32-row tasks (one column block) or 256-row tasks    */
-#define AT_LAYOUT_PACKED 1   /* seg_info + col only: every entry carries its row, (row_in_tile << 21) | source  */
-#define AT_PACKED_SRC_BITS 21
-#define AT_PACKED_MAX_TILE_ROWS 2048
+#define AT_LAYOUT_STREAM 1   /* col + unit_tile only: flat per-source-block streams of self-describing entries    */
+#define AT_STREAM_UNIT 256          /* entries per unit (1 KB): streams are padded to whole units per (block, tile)   */
+#define AT_STREAM_MAX_TILE_ROWS 2048
+#define AT_STREAM_MAX_BLOCK_SIZE ((1 << 21) - 1024)
 
 /* what one launch does */
 #define AT_DO_TRANSMISSION 1 /* substep '0' transition (NewTransmission.forward)                  */
@@ -89,15 +90,19 @@ typedef struct at_seirm_model {
  *     times 32, plus its bit — so that the shared-memory bitmap test needs no address arithmetic.
  *   Edges are used as written: directed, duplicates and self-loops kept (Q9).
  *
- * layout == AT_LAYOUT_PACKED ("PBCSR", the layout for source sets larger than one shared-memory bitmap): rows are
- *   grouped in TILES of tile_rows rows (a power of two <= 2048; n_rows_pad is a multiple of it), sources in n_blocks
- *   ranges of block_size <= 2^21 ids.  Segment s = block*n_tiles + tile holds the tile's edges whose source lies in
- *   the block, sorted by row, each row in original edge order, as 32-bit entries
- *     col[] = (row_in_tile << 21) | block-local source id,
- *   so a segment is a flat stream that needs no per-row metadata (row_start is NULL) and no limit on a row's degree.
- *   seg_info as above.  The gather kernel (one column block's EXACT hot bitmap in shared memory per CTA) leaves
- *   per-(block,row) partial lambdas in lam_part + dirty, which the update kernel folds in block order.  Edge weights are
- *   not supported in this layout (edge_weight must be NULL).
+ * layout == AT_LAYOUT_STREAM (the layout for source sets larger than one shared-memory bitmap, and the default for
+ *   unweighted graphs): rows are grouped in TILES of tile_rows rows (a power of two <= 2048; n_rows_pad is a multiple
+ *   of it), sources in n_blocks ranges of block_size <= 2^21 - 1024 ids.  For every source block the edges whose
+ *   source lies in it form ONE flat stream, tile after tile, each (block, tile) run padded to whole UNITS of
+ *   AT_STREAM_UNIT entries with entries that can never hit.  A 32-bit entry describes itself:
+ *     col[] = (bitmap word of the block-local source << 16) | (row_in_tile << 5) | (bit of the source in its word),
+ *   unit_tile[u] = tile of unit u, block_units[b] = first unit of block b (block_units[n_blocks] = all units).
+ *   The gather kernel streams the units with 128-bit loads against the block's EXACT hot bitmap in shared memory and
+ *   appends, for every hit on a susceptible row, the record (row_in_tile << 8) | source code to the row tile's record
+ *   list (rec / tile_rec_base / tile_count).  The update kernel sums a tile's records into one 64-bit FIXED-POINT
+ *   lambda per row — an integer sum, hence independent of the order in which the hits arrived (bitwise reproducible
+ *   without any floating-point atomic) — and turns it back into float64.  Edge weights are not supported
+ *   (edge_weight must be NULL).
  */
 typedef struct at_seirm_launch {
     int32_t abi_version;        /* = AT_SEIRM_ABI_VERSION */
@@ -111,7 +116,7 @@ typedef struct at_seirm_launch {
     int64_t row_offset;         /* global id of local row 0 (multiple of 32): slice of this rank in
                                    code/hot_bitmap, and the agent id fed to the counter hash */
     int32_t n_blocks, block_size;   /* block_size multiple of 1024 */
-    int32_t rows_per_task, edges_per_chunk;  /* 32 or 256 (BCSR; ignored for PACKED); TMA chunk capacity: 512, 768 or 1024 edges */
+    int32_t rows_per_task, edges_per_chunk;  /* 32 or 256 (BCSR; ignored for STREAM); TMA chunk capacity: 512, 768 or 1024 edges */
     const uint16_t* row_start;  /* [n_blocks][n_rows_pad] */
     const int32_t* seg_info;    /* [n_blocks*n_gtasks][2] = (first entry / 4, edges) */
     const int32_t* col;         /* encoded source ids, segment-padded, + >= 1024 ints of tail padding */
@@ -159,7 +164,7 @@ typedef struct at_seirm_launch {
     /* scratch for n_blocks > 1 (per-block partial lambdas), else NULL */
     double* lam_part;           /* [n_blocks][n_rows_pad][2]: (lambda, d lambda / dR) of the rows flagged in dirty */
     int32_t layout;             /* AT_LAYOUT_* */
-    int32_t tile_rows;          /* AT_LAYOUT_PACKED: rows per tile (power of two, 32..2048), else 0 */
+    int32_t tile_rows;          /* AT_LAYOUT_STREAM: rows per tile (power of two, 32..2048), else 0 */
     uint32_t* dirty;            /* [n_blocks][n_rows_pad/32]: which rows of lam_part hold a value this step */
     /* workspace: at_seirm_workspace_bytes() bytes, zeroed once by the caller, reset by every launch */
     void* workspace;
@@ -170,6 +175,14 @@ typedef struct at_seirm_launch {
     int32_t hash_words;         /* 0: exact bitmap, col holds encoded ids.  > 0 (power of two, n_blocks == 1): the
                                    shared-memory bitmap is a hashed filter of hash_words words (bit src mod 32*hash_words),
                                    col holds RAW source ids, false positives are rejected by code_in[src] == 0 */
+    /* AT_LAYOUT_STREAM only (NULL / 0 otherwise) */
+    const int32_t* unit_tile;   /* [units] tile of every unit */
+    const int32_t* block_units; /* [n_blocks + 1] first unit of every source block */
+    const int64_t* tile_rec_base; /* [tiles] first record slot of every tile (slots = edges of the tile's rows) */
+    uint32_t* tile_count;       /* [tiles] records of the tile this step, all zero between launches */
+    uint32_t* rec;              /* [edges] hit records (row_in_tile << 8) | source code, grouped by tile */
+    int32_t lam_deg_bits;       /* ceil(log2(largest in-degree + 1)): head room of the fixed-point sums */
+    int32_t _pad1;
 } at_seirm_launch;
 
 /* ---- queries (host only) ---- */
@@ -183,16 +196,17 @@ int64_t at_seirm_workspace_bytes(void);
    `warps` warps' TMA buffers of `edges_per_chunk` edges, for a model with n_sfs susceptibility classes and
    n_lam_gamma integrals (the term tables share the same shared memory) */
 int64_t at_seirm_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edges_per_chunk, int32_t warps);
-/* the same for AT_LAYOUT_PACKED (its per-warp staging area differs); never more than 2^21 */
-int64_t at_seirm_packed_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edges_per_chunk, int32_t warps);
+/* the same for AT_LAYOUT_STREAM (no staging buffers: the stream goes through registers); never more than
+   AT_STREAM_MAX_BLOCK_SIZE */
+int64_t at_seirm_stream_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t warps);
 
 /*
  * at_seirm_step — one step (or part of one, per the flags) of the agent update on `stream`.
  * Replaces NewTransmission.forward (transition.py:131-252, including the PyG gather/scatter-add and the
  * straight-through Bernoulli), SEIRMProgression.forward (seirm_progression/transition.py:90-121), and
  * produces what their autograd graph would have saved (dne_dr, death_count, recovered_step) without any
- * per-edge intermediate.  n_blocks == 1: one fused launch; n_blocks > 1: a gather launch over all column
- * blocks followed by the update launch.
+ * per-edge intermediate.  BCSR with n_blocks == 1: one fused launch; n_blocks > 1 or AT_LAYOUT_STREAM: a gather
+ * launch over all column blocks followed by the update launch.
  */
 int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, void* stream);
 

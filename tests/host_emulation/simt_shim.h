@@ -159,6 +159,8 @@ static inline float __fmul_rn(float a, float b) { volatile float r = a * b; retu
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 #define __expf(x) expf(x)          /* glibc declares its own __expf */
 static inline long long __double2ll_rn(double x) { return llrint(x); }
+static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
+static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x, 8); return r; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift)
 {
     return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (shift & 31u));

@@ -80,18 +80,21 @@ def _check(g, st, grad_r2, grad_m):
 
 
 @pytest.mark.parametrize("case,kw", [
-    ("tiny96_hard", dict()),                                         # fused kernel, exact shared-memory bitmap
-    ("tiny96_hard", dict(packed=False, tensor_noise=True)),          # float32 timers, injected uniforms
+    ("tiny96_hard", dict(layout="bcsr")),                            # fused kernel, exact shared-memory bitmap
+    ("tiny96_hard", dict(layout="bcsr", packed=False, tensor_noise=True)),   # float32 timers, injected uniforms
+    ("noiso500", dict(layout="bcsr")),
+    ("synth3k_hard", dict(layout="bcsr")),
+    ("synth3k_soft", dict(layout="bcsr", block_size=1024)),          # column blocks: gather + update kernels
+    ("synth3k_r2vec", dict(hashed=True, hash_words=32)),             # hashed filter + hot_fold_kernel
+    ("tiny96_hard", dict()),                                         # stream layout (the default): one block, one tile
     ("noiso500", dict()),
     ("synth3k_hard", dict()),
-    ("synth3k_soft", dict(block_size=1024)),                         # column blocks: gather + update kernels
-    ("synth3k_r2vec", dict(hashed=True, hash_words=32)),             # hashed filter + hot_fold_kernel
-    ("synth3k_soft", dict(layout="packed", block_size=1024, tile_rows=256)),     # packed layout: 3 column blocks, 12 tiles
-    ("synth3k_hard", dict(layout="packed", block_size=2048, tile_rows=2048)),    # segments of several TMA chunks (carry across chunks)
-    ("synth3k_r2vec", dict(layout="packed", block_size=4096, tile_rows=64, warps_per_cta=1)),   # one block, tiny tiles
-    ("tiny96_hard", dict(layout="packed", block_size=1024, tile_rows=32)),
-    ("noiso500", dict(layout="packed", block_size=1024, tile_rows=128, packed=False, tensor_noise=True)),
-    ("tiny96_hard", dict(warps_per_cta=1)),                          # a CTA smaller than the code tables (found by tools/fuzz_emulated.py)
+    ("synth3k_soft", dict(block_size=1024, tile_rows=256)),          # stream layout: 3 source blocks, 12 tiles, CTAs spanning blocks
+    ("synth3k_hard", dict(block_size=2048, tile_rows=2048, grid=5)),
+    ("synth3k_r2vec", dict(block_size=4096, tile_rows=64, warps_per_cta=1)),   # one block, tiny tiles
+    ("tiny96_hard", dict(block_size=1024, tile_rows=32, grid=1)),
+    ("noiso500", dict(block_size=1024, tile_rows=128, packed=False, tensor_noise=True)),
+    ("tiny96_hard", dict(layout="bcsr", warps_per_cta=1)),           # a CTA smaller than the code tables (found by tools/fuzz_emulated.py)
     ("noiso500", dict(warps_per_cta=1, hashed=True, hash_words=32)),
 ])
 def test_kernel_source_matches_reference_golden(engine_on_host, case, kw):

@@ -22,7 +22,8 @@ ap.add_argument("--iso", default="soft")
 ap.add_argument("--layout", default="auto")
 ap.add_argument("--tile", type=int, default=0)
 ap.add_argument("--epc", type=int, default=0)
-ap.add_argument("--pw", type=int, default=14)
+ap.add_argument("--grid", type=int, default=0)
+ap.add_argument("--bank", type=int, default=1)
 ap.add_argument("--warps", type=int, default=0)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -32,8 +33,8 @@ mi = mean_interactions_from_age(age)
 graph = synthetic_contact_graph(args.n, args.d, 99, family=args.family, device=dev, mean_interactions=mi)
 print("N", args.n, "E", graph.num_edges, "ibar", graph.i_bar, flush=True)
 eng = SeirmEngine(graph, SeirmSpec(num_steps=T), block_size=args.block or None, tasks_per_group=args.tpg, hashed=None if args.hashed < 0 else bool(args.hashed), hash_min_warps=args.hmw,
-                  layout=args.layout, tile_rows=args.tile or None, edges_per_chunk=args.epc or None, packed_warps=args.pw, warps_per_cta=args.warps)
-print('layout', eng.graph.layout, 'blocks', eng.graph.n_blocks, 'block_size', eng.graph.block_size, 'hash_words', eng.graph.hash_words, 'tile', eng.graph.tile_rows, 'epc', eng.graph.edges_per_chunk, flush=True)
+                  layout=args.layout, tile_rows=args.tile or None, edges_per_chunk=args.epc or None, warps_per_cta=args.warps, grid=args.grid, bank_aware=bool(args.bank))
+print('units', int(eng.graph.block_units[-1]) if eng.graph.block_units is not None else 0, 'layout', eng.graph.layout, 'blocks', eng.graph.n_blocks, 'block_size', eng.graph.block_size, 'hash_words', eng.graph.hash_words, 'tile', eng.graph.tile_rows, 'epc', eng.graph.edges_per_chunk, flush=True)
 r_steps = torch.full((T,), 3 * args.r2, device=dev)
 m = torch.tensor([0.12], device=dev)
 noise = NoiseSpec(seed=5, isolation=args.iso)
@@ -66,4 +67,5 @@ for rep in range(args.reps):
             gi = torch.ones(T, device=dev); gd = torch.ones(T, device=dev)
             e0.record(); gr, gm = eng.episode_backward(sv, T, gi, gd, m); e1.record(); torch.cuda.synchronize()
             print("bwd %.1f us" % (e0.elapsed_time(e1) * 1e3), gr[:4].tolist(), gm.tolist())
+        print("checksum", int((st.stage.double() * torch.arange(1, args.n + 1, device=dev).double()).sum().item()) % 1000003, int(st.next_stage_time.long().sum()), int(st.infected_time.long().sum()))
         print("stage hist", torch.bincount(st.stage.round().long().clamp(0, 3), minlength=4).tolist())
