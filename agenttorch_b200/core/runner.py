@@ -86,6 +86,16 @@ class Runner(nn.Module):
         buffers of an initial condition or a checkpoint, possibly in narrower dtypes) INTO the live state tensors, keeping their storage —
         and therefore the engine bindings and captured CUDA graphs — valid.  The cheap counterpart of
         reset_state(), which re-runs every initialiser."""
+        from .snapshot import PackedSnapshot
+
+        if isinstance(snapshot, PackedSnapshot):
+            # one pinned host buffer: one copy over PCIe, widened on the device
+            snapshot.restore_into(self.state, non_blocking=non_blocking)
+            self.state["current_step"] = 0
+            self.state["current_substep"] = "0"
+            self.state_trajectory = [[self._snapshot(self.state)]]
+            return
+
         def walk(dst, src):
             for k, v in src.items():
                 if isinstance(v, dict):

@@ -54,7 +54,9 @@
 #define WS_BPART 1024               // double[BWD_MAX_GRID][BWD_MAXT]
 #define BWD_MAX_GRID 1024
 #define BWD_MAXT 64
-#define WS_BYTES (WS_BPART + BWD_MAX_GRID * BWD_MAXT * 8)
+#define WS_FIXSHIFT (WS_BPART + BWD_MAX_GRID * BWD_MAXT * 8)      // int: binary scale of the fixed-point terms of this step (stream layout)
+#define WS_FIXTAB (WS_FIXSHIFT + 16)                             // int64[AT_MAX_SFS * 256]: the table itself, gather kernel -> update kernel
+#define WS_BYTES (WS_FIXTAB + AT_MAX_SFS * 256 * 8)
 
 static thread_local char g_err[512] = "";
 
@@ -319,6 +321,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     auto update_subtask = [&](int task, uint32_t sus_w, uint32_t exp_w, uint32_t inf_w, double lam, double lam1) {
         const int64_t row = (int64_t)task * 32 + lane;
         const bool valid = row < a.n_rows;
+        const bool task_valid = (int64_t)task * 32 < a.n_rows;     // (hot words of padding tasks belong to somebody else)
         float stage = 0.f;
         bool stage_known = false;
         if (do_init) {
@@ -335,7 +338,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             if (want_grad && do_trans && valid) a.dne_dr[row] = 0.f;
             if (do_enc) {
                 if (valid) a.code_out[a.row_offset + row] = 0;
-                if (lane == 0) a.hot_bitmap_out[(a.row_offset >> 5) + task] = 0u;
+                if (lane == 0 && task_valid) a.hot_bitmap_out[(a.row_offset >> 5) + task] = 0u;
             }
             return;
         }
@@ -379,7 +382,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             if (want_grad && do_trans && valid) a.dne_dr[row] = dne;
             if (do_enc) {
                 if (valid) a.code_out[a.row_offset + row] = 0;
-                if (lane == 0) a.hot_bitmap_out[(a.row_offset >> 5) + task] = 0u;
+                if (lane == 0 && task_valid) a.hot_bitmap_out[(a.row_offset >> 5) + task] = 0u;
             }
             return;
         }
@@ -417,7 +420,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             }
             const uint32_t hot = __ballot_sync(0xffffffffu, code != 0u);
             if (valid) a.code_out[a.row_offset + row] = (uint8_t)code;
-            if (lane == 0) {
+            if (lane == 0 && task_valid) {
                 a.hot_bitmap_out[(a.row_offset >> 5) + task] = hot;
                 if (hot != 0u) s_any_out = 1;                    // benign race: every writer stores 1
             }
@@ -791,20 +794,72 @@ __device__ __noinline__ void stream_resolve(const StreamResolveCtx& c, const uin
 }
 
 // NTHREADS: CTA size the kernel is compiled for (register budget); UF: units in flight per warp (register sets)
+// Table of the step's fixed-point lambda terms, computed ONCE per step (by the last CTA of the gather launch, for the update
+// launch that follows it in the stream): term[age][code] = f64(f32(((R*S)*A)*G)) / I_bar, the reference's message
+// (transition.py:78-83), rounded once to the 2^-shift grid, shift chosen so that in-degree * largest term < 2^62.
+// R == 0 (lambda == 0 everywhere): the terms of d lambda / dR instead, which is all the update then needs.
+__device__ void stream_build_term_table(const KModel& m, const at_seirm_launch& a, int NC, double* s_scratch /* n_sfs*NC */,
+                                        unsigned long long* s_tmax)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const float R = a.r_value[a.r_index];
+    const double ibar = (double)m.ibar;
+    char* ws = reinterpret_cast<char*>(a.workspace);
+    long long* tab = reinterpret_cast<long long*>(ws + WS_FIXTAB);
+    if (tid == 0) *s_tmax = 0ull;
+    __syncthreads();
+    double mymax = 0.0;
+    for (int i = tid; i < m.n_sfs * NC; i += nt) {
+        const int ag = i / NC, c = i % NC;
+        float av = 0.f, gv = 0.f;
+        if (c >= 1 && c <= 3 * m.n_lg) {
+            const int sidx = (c - 1) / m.n_lg, idx = (c - 1) % m.n_lg;
+            av = sidx < m.n_sfi ? m.sfi[sidx] : 0.f;
+            gv = m.lg[idx];
+        }
+        const float s = m.sfs[ag];
+        const double d = (R != 0.f) ? (double)__fmul_rn(__fmul_rn(__fmul_rn(R, s), av), gv) / ibar
+                                    : (double)__fmul_rn(__fmul_rn(s, av), gv) / ibar;
+        s_scratch[i] = d;
+        const double ad = fabs(d);
+        if (ad < 1e300 && ad > mymax) mymax = ad;
+    }
+    if (mymax > 0.0) atomicMax(s_tmax, (unsigned long long)__double_as_longlong(mymax));   // bit order == value order
+    __syncthreads();
+    int shift = 0;
+    const double tmax = __longlong_as_double((long long)*s_tmax);
+    if (tmax > 0.0) {
+        int ex = 0;
+        frexp(tmax, &ex);                                       // tmax < 2^ex
+        shift = 62 - ex - a.lam_deg_bits;
+        shift = shift > 1000 ? 1000 : (shift < -1000 ? -1000 : shift);
+    }
+    for (int i = tid; i < m.n_sfs * NC; i += nt) {
+        const double d = s_scratch[i];                          // written by this thread
+        tab[i] = (fabs(d) < 1e300) ? __double2ll_rn(ldexp(d, shift)) : 0ll;
+    }
+    if (tid == 0) *reinterpret_cast<int*>(ws + WS_FIXSHIFT) = shift;
+    __syncthreads();
+}
+
 template <int NTHREADS, int UF>
 __global__ void __launch_bounds__(NTHREADS, 1)
-stream_gather_kernel(const at_seirm_launch a, const int bm_words, const int tile_shift)
+stream_gather_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const int NC, const int tile_shift)
 {
     AT_DYNAMIC_SMEM(unsigned char, smem_raw, 128);
     const int nw = blockDim.x >> 5;
     // [hot bitmap of the current block: bm_words + 4 words, the last 4 always zero (padding entries point there)]
-    // [mbarrier 16 B][parked hits uint2 nw*ST_PEND]
+    // [mbarrier 16 B][parked hits uint2 nw*ST_PEND][scratch of the term table: 16 B + f64 n_sfs*NC]
     uint32_t* s_bm = reinterpret_cast<uint32_t*>(smem_raw);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)(bm_words + 4) * 4);
     uint2* s_pend_all = reinterpret_cast<uint2*>(s_bar + 2);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint2* s_pend = s_pend_all + warp * ST_PEND;
+    if (blockIdx.x == gridDim.x - 1) {                          // scratch: after the parked-hit lists
+        unsigned char* scratch = reinterpret_cast<unsigned char*>(s_pend_all + (size_t)nw * ST_PEND);
+        stream_build_term_table(m, a, NC, reinterpret_cast<double*>(scratch + 16), reinterpret_cast<unsigned long long*>(scratch));
+    }
     if (tid == 0) mbar_init(s_bar, 1);
     if (tid < 4) s_bm[bm_words + tid] = 0u;
     fence_mbarrier_init();
@@ -828,20 +883,24 @@ stream_gather_kernel(const at_seirm_launch a, const int bm_words, const int tile
         if (s0 >= s1) continue;
         // ---- stage the block's hot bitmap (TMA bulk copy, one mbarrier phase per block)
         __syncthreads();                                         // barrier initialised; previous block's bitmap no longer read
+        // (the last block may reach past the end of the source id space: those bitmap words are zero-filled here, not read)
+        const int valid_words = (int)min((int64_t)block_words, (a.n_sources >> 5) - (int64_t)block * block_words);
         if (tid == 0) {
-            const uint32_t bytes = (uint32_t)block_words * 4u;
+            const uint32_t bytes = (uint32_t)valid_words * 4u;
             fence_proxy_async_smem();
             mbar_expect_tx(s_bar, bytes);
             bulk_g2s(s_bm, a.hot_bitmap_in + (size_t)block * block_words, bytes, s_bar);
         }
+        for (int i = valid_words + tid; i < block_words; i += blockDim.x) s_bm[i] = 0u;
         mbar_wait(s_bar, bar_phase & 1u);
         ++bar_phase;
         uint32_t seen = 0;
         {
             const uint4* b4 = reinterpret_cast<const uint4*>(s_bm);
-            for (int i = tid; i < (block_words >> 2); i += blockDim.x) { const uint4 v = b4[i]; seen |= v.x | v.y | v.z | v.w; }
+            for (int i = tid; i < (valid_words >> 2); i += blockDim.x) { const uint4 v = b4[i]; seen |= v.x | v.y | v.z | v.w; }
         }
         if (!__syncthreads_or(seen != 0u)) continue;             // no infectious source in this block: nothing can hit
+                                                                 // (the barrier also orders the zero-fill above before the tests)
         rc.code_b = a.code_in + (size_t)block * a.block_size;
         auto resolve = [&]() { stream_resolve(rc, s_pend, count, lane); count = 0; };
         // edge test: byte offset of the bitmap word from the top 16 bits, bit index in the low 5 (the shift uses them alone)
@@ -909,26 +968,26 @@ stream_gather_kernel(const at_seirm_launch a, const int bm_words, const int tile
 //   1  sum the tile's hit records (row in tile, source code) into one 64-bit FIXED-POINT lambda per row in shared memory
 //      (integer atomics: the order of the records does not matter, the sum is bitwise reproducible; scale 2^fx_shift chosen
 //      so that in-degree * largest term < 2^62)
-//   A  compact the exposure candidates (susceptible rows with lambda != 0) of the tile and decide them densely, one
-//      candidate per thread: noise, p = 1 - exp(-lambda), stage / timer writes, d ne / dR
+//   A  the exposure candidates (rows that received a record) are decided densely, one candidate per thread, whatever
+//      their position in the tile: noise, p = 1 - exp(-lambda), stage / timer writes, d ne / dR
 //   B  32-row tasks that hold a row in E or I: progression and the code of the next step, lane <-> row
 // The per-row logic is the one of seirm_kernel's update_subtask (the generic kernel), restated for launches with
 // transmission (row bitmaps valid, no AT_DO_INIT).
 #define TU_THREADS 256
 #define TU_MAX_TASKS (AT_STREAM_MAX_TILE_ROWS / 32)
 template <bool TF32, bool GRAD>
-__global__ void __launch_bounds__(TU_THREADS, 4)
+__global__ void __launch_bounds__(TU_THREADS, 8)
 stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
 {
     AT_DYNAMIC_SMEM(unsigned char, smem_raw, 128);
-    // [s_fix i64 n_sfs*NC][s_A f32 256][s_G f32 256][s_lam i64 tile_rows][s_cand u16 tile_rows]
+    // [s_fix i64 n_sfs*NC][s_A f32 256][s_G f32 256][s_lam i64 tile_rows][s_cand u16 tile_rows][s_age u8 tile_rows]
     long long* s_fix = reinterpret_cast<long long*>(smem_raw);
     float* s_A = reinterpret_cast<float*>(s_fix + m.n_sfs * NC);
     float* s_G = s_A + 256;
     long long* s_lam = reinterpret_cast<long long*>(s_G + 256);
     uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_lam + a.tile_rows);
+    uint8_t* s_age = reinterpret_cast<uint8_t*>(s_cand + a.tile_rows);
     __shared__ long long s_red[TU_THREADS / 32][3];
-    __shared__ unsigned long long s_tmax;
     __shared__ uint32_t s_w[3][TU_MAX_TASKS], s_orig[3][TU_MAX_TASKS], s_hot[TU_MAX_TASKS];   // sus / exp / inf words of the tile
     __shared__ int s_is_last, s_any_out, s_ncand;
 
@@ -937,11 +996,10 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     const bool do_prog = (a.flags & AT_DO_PROGRESSION) != 0, do_enc = (a.flags & AT_DO_ENCODE) != 0;
     const int t = a.t;
     const float R = a.r_value[a.r_index];
-    const double ibar = (double)m.ibar;
     const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
     char* ws = reinterpret_cast<char*>(a.workspace);
 
-    if (tid == 0) { s_tmax = 0ull; s_any_out = 0; s_ncand = 0; }
+    if (tid == 0) { s_any_out = 0; s_ncand = 0; }
     for (int c = tid; c < 256; c += TU_THREADS) {
         float av = 0.f, gv = 0.f;
         if (c >= 1 && c <= 3 * m.n_lg) {
@@ -953,38 +1011,12 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
         s_G[c] = gv;
     }
     __syncthreads();
-    // R != 0: lambda terms f64(f32(((R*S)*A)*G)) / I_bar, the reference's message (transition.py:78-83), rounded once to the
-    // 2^-fx_shift grid; R == 0 (lambda == 0 everywhere): the terms of d lambda / dR instead, all the update then needs
-    double* s_Td = reinterpret_cast<double*>(s_fix);
+    // fixed-point term table of this step, built by the gather launch (stream_build_term_table)
     {
-        double mymax = 0.0;
-        for (int i = tid; i < m.n_sfs * NC; i += TU_THREADS) {
-            const int ag = i / NC, c = i % NC;
-            const float s = m.sfs[ag];
-            const float av = c < 256 ? s_A[c] : 0.f, gv = c < 256 ? s_G[c] : 0.f;
-            const double d = (R != 0.f) ? (double)__fmul_rn(__fmul_rn(__fmul_rn(R, s), av), gv) / ibar
-                                        : (double)__fmul_rn(__fmul_rn(s, av), gv) / ibar;
-            s_Td[i] = d;
-            const double ad = fabs(d);
-            if (ad < 1e300 && ad > mymax) mymax = ad;
-        }
-        if (mymax > 0.0) atomicMax(&s_tmax, (unsigned long long)__double_as_longlong(mymax));   // bit order == value order
+        const long long* tab = reinterpret_cast<const long long*>(ws + WS_FIXTAB);
+        for (int i = tid; i < m.n_sfs * NC; i += TU_THREADS) s_fix[i] = tab[i];
     }
-    __syncthreads();
-    int fx_shift = 0;
-    {
-        const double tmax = __longlong_as_double((long long)s_tmax);
-        if (tmax > 0.0) {
-            int ex = 0;
-            frexp(tmax, &ex);                                   // tmax < 2^ex
-            fx_shift = 62 - ex - a.lam_deg_bits;
-            fx_shift = fx_shift > 1000 ? 1000 : (fx_shift < -1000 ? -1000 : fx_shift);
-        }
-    }
-    for (int i = tid; i < m.n_sfs * NC; i += TU_THREADS) {
-        const double d = s_Td[i];                               // written by this thread
-        s_fix[i] = (fabs(d) < 1e300) ? __double2ll_rn(ldexp(d, fx_shift)) : 0ll;
-    }
+    const int fx_shift = *reinterpret_cast<const int*>(ws + WS_FIXSHIFT);
     __syncthreads();
     const double inv_scale = ldexp(1.0, -fx_shift);             // exact power of two
     const double inv_r = (R != 0.f) ? 1.0 / (double)R : 1.0;
@@ -1040,9 +1072,15 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
             s_w[0][tid] = sw; s_w[1][tid] = ew; s_w[2][tid] = iw;
             s_orig[0][tid] = sw; s_orig[1][tid] = ew; s_orig[2][tid] = iw;
             s_hot[tid] = 0u;
-            if (do_enc) hot_out[task] = 0u;
+            if (do_enc && task * 32 < n_rows) hot_out[task] = 0u;         // (words of padding rows belong to somebody else)
         }
-        if (nrec != 0u) for (int i = tid; i < tile_rows; i += TU_THREADS) s_lam[i] = 0ll;
+        if (nrec != 0u) {
+            for (int i = tid; i < tile_rows; i += TU_THREADS) {
+                s_lam[i] = 0ll;
+                int ag = (i < rows_here) ? load_age(a.age, row_base + i, age_f32) : 0;     // susceptibility class of the row
+                s_age[i] = (uint8_t)(ag < 0 ? 0 : (ag >= m.n_sfs ? m.n_sfs - 1 : ag));
+            }
+        }
         __syncthreads();
         if (nrec != 0u) {
             // ---- phase 1: records -> fixed-point lambda per row
@@ -1050,27 +1088,16 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
             for (uint32_t i = tid; i < nrec; i += TU_THREADS) {
                 const uint32_t rec = recs[i];
                 const int r = (int)(rec >> 8);
-                int ag = (r < rows_here) ? load_age(a.age, row_base + r, age_f32) : 0;
-                ag = ag < 0 ? 0 : (ag >= m.n_sfs ? m.n_sfs - 1 : ag);
-                const long long v = s_fix[ag * NC + (int)(rec & 255u)];
-                if (v != 0ll) atomicAdd(reinterpret_cast<unsigned long long*>(s_lam) + r, (unsigned long long)v);
-            }
-            __syncthreads();
-            if (tid == 0) a.tile_count[tile] = 0u;
-            // ---- phase A: the exposure candidates of the tile, compacted (lambda != 0, or with R == 0 d lambda / dR != 0,
-            //      <=> a non-zero fixed-point sum)
-            for (int tk = warp; tk < tpt; tk += nw) {
-                const uint32_t sw = s_w[0][tk];
-                const bool cand = ((sw >> lane) & 1u) && s_lam[tk * 32 + lane] != 0ll;
-                const uint32_t cw = __ballot_sync(0xffffffffu, cand);
-                if (cw != 0u) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_ncand, __popc(cw));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (cand) s_cand[base + __popc(cw & ((1u << lane) - 1u))] = (uint16_t)(tk * 32 + lane);
+                const long long v = s_fix[(int)s_age[r] * NC + (int)(rec & 255u)];
+                if (v != 0ll) {
+                    // ---- phase A, part 1: the row's first record makes it an exposure candidate (records exist for susceptible rows
+                    //      only, and all terms of a step have the sign of R, so the sum was zero exactly before the first one)
+                    const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(s_lam) + r, (unsigned long long)v);
+                    if (old == 0ull) s_cand[atomicAdd(&s_ncand, 1)] = (uint16_t)r;
                 }
             }
             __syncthreads();
+            if (tid == 0) a.tile_count[tile] = 0u;
             const int ncand = s_ncand;
             for (int i = tid; i < ncand; i += TU_THREADS) {
                 const int r = (int)s_cand[i];
@@ -1131,8 +1158,9 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
             bool is_e = (exp_w >> lane) & 1u, is_i = (inf_w >> lane) & 1u;
             uint32_t code = 0;
             if (is_e || is_i) {
+                const int nst = do_prog ? ld_timer(a.next_stage_time, row) : 0;     // both timers in flight together
+                const int itime = do_enc ? ld_timer(a.infected_time, row) : 0;
                 if (do_prog) {
-                    const int nst = ld_timer(a.next_stage_time, row);
                     if (nst <= t) {                              // progression (seirm_progression/transition.py:41-88)
                         if (is_i) {
                             acc_dead += 1;                      // stage * rd / INFECTED_VAR = 2/2
@@ -1145,7 +1173,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
                         is_i = was_e;
                     }
                 }
-                if (do_enc && (is_e || is_i)) code = encode(is_e ? 1 : 2, ld_timer(a.infected_time, row));
+                if (do_enc && (is_e || is_i)) code = encode(is_e ? 1 : 2, itime);
             }
             const uint32_t hot = __ballot_sync(0xffffffffu, code != 0u) | frac_hot;
             if (code != 0u) code_out[row] = (uint8_t)code;
@@ -1523,11 +1551,11 @@ static int dispatch(const KModel& km, const at_seirm_launch& a, int grid, int th
 }
 
 template <int NTHREADS, int UF>
-static int launch_stream(const at_seirm_launch& a, int grid, int threads, size_t smem, int bm_words, int tile_shift, cudaStream_t s) {
+static int launch_stream(const KModel& km, const at_seirm_launch& a, int grid, int threads, size_t smem, int bm_words, int NC, int tile_shift, cudaStream_t s) {
     auto k = stream_gather_kernel<NTHREADS, UF>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    AT_LAUNCH_SMEM(k, grid, threads, smem, s, a, bm_words, tile_shift);
+    AT_LAUNCH_SMEM(k, grid, threads, smem, s, km, a, bm_words, NC, tile_shift);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail("stream_gather_kernel launch: %s", cudaGetErrorString(e));
     return 0;
@@ -1552,8 +1580,7 @@ int64_t at_seirm_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t edge
 int64_t at_seirm_stream_max_block_size(int32_t n_sfs, int32_t n_lam_gamma, int32_t warps) {
     if (device_props()) return 0;
     if (warps < 1) warps = ST_NT / 32;
-    (void)n_sfs; (void)n_lam_gamma;
-    int64_t bytes = (int64_t)g_smem_optin - (int64_t)warps * ST_PEND * 8 - 16 - 16 - 1024;
+    int64_t bytes = (int64_t)g_smem_optin - (int64_t)warps * ST_PEND * 8 - 16 - 16 - 16 - (int64_t)n_sfs * code_count(n_lam_gamma) * 8 - 1024;
     if (bytes < 4096) return 0;
     int64_t bits = ((bytes * 8) / 1024) * 1024;
     return bits > AT_STREAM_MAX_BLOCK_SIZE ? AT_STREAM_MAX_BLOCK_SIZE : bits;
@@ -1637,21 +1664,21 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         if (a.block_size > at_seirm_stream_max_block_size(model->n_sfs, model->n_lam_gamma, pw))
             return fail("%s", "stream layout: block bitmap exceeds the shared-memory capacity (at_seirm_stream_max_block_size)");
         const int words = a.block_size / 32;
-        const size_t smem = (size_t)(words + 4) * 4 + 16 + (size_t)pw * ST_PEND * 8;
+        const size_t smem = (size_t)(words + 4) * 4 + 16 + (size_t)pw * ST_PEND * 8 + 16 + (size_t)model->n_sfs * NC * 8;
         int tile_shift = 0;
         while ((1 << tile_shift) < a.tile_rows) ++tile_shift;
         // the more warps, the fewer registers each has for units in flight: 32 warps x 3 units, 24 x 5, <= 16 x 8 (KB per SM: 96 / 120 / 128)
         int rc;
-        if (pw > 24 && a.tasks_per_group == 2) rc = launch_stream<1024, 2>(al, grid, pw * 32, smem, words, tile_shift, s);
-        else if (pw > 24) rc = launch_stream<1024, 3>(al, grid, pw * 32, smem, words, tile_shift, s);
-        else if (pw > 16) rc = launch_stream<768, 4>(al, grid, pw * 32, smem, words, tile_shift, s);
-        else rc = launch_stream<512, 6>(al, grid, pw * 32, smem, words, tile_shift, s);
+        if (pw > 24 && a.tasks_per_group == 2) rc = launch_stream<1024, 2>(km, al, grid, pw * 32, smem, words, NC, tile_shift, s);
+        else if (pw > 24) rc = launch_stream<1024, 3>(km, al, grid, pw * 32, smem, words, NC, tile_shift, s);
+        else if (pw > 16) rc = launch_stream<768, 4>(km, al, grid, pw * 32, smem, words, NC, tile_shift, s);
+        else rc = launch_stream<512, 6>(km, al, grid, pw * 32, smem, words, NC, tile_shift, s);
         if (rc) return rc;
         al.edges_per_chunk = 512;
-        int tgrid = a.grid > 0 ? a.grid : g_sm_count * 4;
+        int tgrid = a.grid > 0 ? a.grid : g_sm_count * 8;
         const int64_t n_tiles = a.n_rows_pad / a.tile_rows;
         if (tgrid > n_tiles) tgrid = (int)n_tiles;
-        const size_t usmem = (size_t)model->n_sfs * NC * 8 + 2 * 256 * 4 + (size_t)a.tile_rows * 10;
+        const size_t usmem = (size_t)model->n_sfs * NC * 8 + 2 * 256 * 4 + (size_t)a.tile_rows * 11;
         const bool tf32 = a.timer_dtype == AT_TIMER_F32, grad = a.dne_dr != nullptr;
         if (tf32 && grad) AT_LAUNCH_SMEM((stream_update_kernel<true, true>), tgrid, TU_THREADS, usmem, s, km, al, NC);
         else if (tf32) AT_LAUNCH_SMEM((stream_update_kernel<true, false>), tgrid, TU_THREADS, usmem, s, km, al, NC);

@@ -118,10 +118,16 @@ class DistributedRunner:
 
         edge_index, edge_attr = var("adjacency_matrix")
         _require_cuda(edge_index.is_cuda)
+        from .graph import ContactGraph
         from .models.covid.context import spec_from_state
 
-        graph_full = build_contact_graph(edge_index, n, edge_attr=edge_attr, mean_interactions=var("mean_interactions"),
-                                         device=edge_index.device)
+        net = get_by_path(full, re.split("/", iv["adjacency_matrix"])[:-1])
+        prebuilt = net.get("graph") if isinstance(net, dict) else None
+        if isinstance(prebuilt, ContactGraph) and prebuilt.num_edges == edge_index.shape[1] and prebuilt.row_offset == 0:
+            graph_full = prebuilt.to(edge_index.device)          # the network helper already produced the dst-sorted CSR
+        else:
+            graph_full = build_contact_graph(edge_index, n, edge_attr=edge_attr, mean_interactions=var("mean_interactions"),
+                                             device=edge_index.device)
         shard = shard_graph(graph_full, r0, r1)
         del graph_full
         self.engine = SeirmEngine(shard, spec_from_state(self.config, full, iv), process_group=self.pg,
@@ -149,6 +155,41 @@ class DistributedRunner:
 
     def reset(self):
         self.init()
+
+    def local_snapshot(self):
+        """The owned slices of the agent state and the daily series, as `restore_state` takes them back."""
+        st = self.local_state
+        agent = self.config["substeps"]["0"]["active_agents"][0]
+        return {"agents": {agent: {"disease_stage": st.stage.view(-1, 1).clone(), "next_stage_time": st.next_stage_time.view(-1, 1).clone(),
+                                   "infected_time": st.infected_time.view(-1, 1).clone()}},
+                "environment": {"daily_infected": self.state["environment"]["daily_infected"].detach().clone(),
+                                "daily_deaths": self.state["environment"]["daily_deaths"].detach().clone()}}
+
+    def restore_state(self, snapshot, non_blocking=True):
+        """Copy a saved state of THIS rank's agents (nested dict of tensors or a core.snapshot.PackedSnapshot, host or device)
+        into the live local tensors — the sharded counterpart of Runner.restore_state; the engine bindings and captured CUDA
+        graphs stay valid."""
+        from .core.snapshot import PackedSnapshot
+
+        env = self.state["environment"]
+        for k in ("daily_infected", "daily_deaths"):                  # step() replaced them by autograd outputs
+            if env[k].requires_grad or env[k].grad_fn is not None:
+                env[k] = env[k].detach().clone()
+        if isinstance(snapshot, PackedSnapshot):
+            snapshot.restore_into(self.state, non_blocking=non_blocking)
+        else:
+            def walk(dst, src):
+                for k, v in src.items():
+                    if isinstance(v, dict):
+                        walk(dst[k], v)
+                    elif torch.is_tensor(v) and torch.is_tensor(dst.get(k)):
+                        cur = dst[k]
+                        if v.dtype != cur.dtype and v.device != cur.device:
+                            cur.copy_(v.to(cur.device, non_blocking=non_blocking).reshape(cur.shape))
+                        else:
+                            cur.copy_(v.reshape(cur.shape), non_blocking=non_blocking)
+            walk(self.state, snapshot)
+        self.state["current_step"] = 0
 
     def episode_seed(self):
         self.tr.episode_index = self._episode

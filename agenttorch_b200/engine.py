@@ -198,7 +198,10 @@ class SeirmEngine:
             self.graph = graph
         elif layout == "stream":
             if block_size is None:
-                _, block_size = choose_block_size(n_src, stream_capacity(warps_per_cta or 0))
+                # the streamed units pass through L1 (whatever shared memory leaves of the SM's 256 KB), which has to hold
+                # the ~96 KB of loads in flight: measured on B200, bitmaps of <= 88 KB per block stream at 5.3 TB/s, 175 KB
+                # ones at 4.3 TB/s
+                _, block_size = choose_block_size(n_src, min(stream_capacity(warps_per_cta or 0), 88 * 1024 * 8))
             nb = -(-n_src // int(block_size))
             if tile_rows is None:
                 tile_rows = choose_tile_rows(graph.n_rows, nb)
@@ -234,7 +237,10 @@ class SeirmEngine:
         if (self.graph.hash_words * 32 or self.graph.block_size) > cap4:
             raise RuntimeError(f"block_size {self.graph.block_size} exceeds the shared-memory bitmap capacity")
         g = self.graph
-        self.n_code = max(((n_src + 1023) // 1024) * 1024, g.n_blocks * g.block_size)
+        self.n_code = ((n_src + 1023) // 1024) * 1024
+        if g.layout != 1:
+            # (the stream gather zero-fills what the last block's bitmap lacks; the older kernels read whole blocks)
+            self.n_code = max(self.n_code, g.n_blocks * g.block_size)
         dev = self.device
         # Multi-GPU: the code arrays live in symmetric memory when available, so that the per-step halo exchange is a
         # device-side barrier + peer copies over NVLink that can be captured into the episode's CUDA graph (NCCL

@@ -25,9 +25,12 @@ def test_reference_arm_prints_one_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "agent-steps/s" and line["higher_is_better"] is True
     assert line["metric"] == "agent-steps/s fwd+bwd, 8.4M-agent SEIRM" and line["n_gpus"] == 1 and line["steps"] == 1
     assert line["value"] > 0 and line["ms_per_step"] > 0 and line["vs_baseline"] is None
-    assert line["config"]["agents"] == 8_400_000 and "workload" in line["config"] and "model" not in line["config"]
+    # config.agents states the N the CPU arm really ran (a bounded sample), agents_gpu_arm the GPU arm's workload
+    assert line["config"]["agents"] == 20_000 and line["config"]["agents_gpu_arm"] == 8_400_000
+    assert "workload" in line["config"] and "model" not in line["config"]
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "N=20000" in cb["sample"]
+    # "reference": the unmodified reference package is installed (baseline/_ref, or /root/reference in the build container)
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and "N=20000" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

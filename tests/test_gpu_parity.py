@@ -17,7 +17,8 @@ def _r_steps_and_grad(r2_np, T, num_weeks=3):
     return r2, r_steps
 
 
-def _run_engine(g, *, packed, block_size=None, use_tensor_noise=False, cuda_graph=False, grid=0, tasks_per_group=0, hashed=None, hash_words=None):
+def _run_engine(g, *, packed, block_size=None, use_tensor_noise=False, cuda_graph=False, grid=0, tasks_per_group=0, hashed=None, hash_words=None,
+                layout="auto", tile_rows=None, warps_per_cta=0):
     from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
     from agenttorch_b200.graph import build_contact_graph, mean_interactions_from_age
 
@@ -29,7 +30,8 @@ def _run_engine(g, *, packed, block_size=None, use_tensor_noise=False, cuda_grap
     edges = torch.from_numpy(g["edges"].astype(np.int64)).t().contiguous()
     graph = build_contact_graph(edges, n, mean_interactions=mi).to(dev)
     spec = SeirmSpec(num_steps=T)
-    eng = SeirmEngine(graph, spec, block_size=block_size, grid=grid, tasks_per_group=tasks_per_group, hashed=hashed, hash_words=hash_words)
+    eng = SeirmEngine(graph, spec, block_size=block_size, grid=grid, tasks_per_group=tasks_per_group, hashed=hashed, hash_words=hash_words,
+                      layout=layout, tile_rows=tile_rows, warps_per_cta=warps_per_cta)
     st = SeirmState.from_initial(g["stage0"].astype(np.float32), g["age"], T, dev, packed=packed)
     if use_tensor_noise:
         U, W = make_noise(g["seed"], g["mode"], n, T, float(g["p_isolate"]))
@@ -58,12 +60,28 @@ def _check(g, st, grad_r2, grad_m):
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 @pytest.mark.parametrize("packed,block_size", [(True, None), (False, 1024), (True, 2048)])
-def test_episode_matches_reference_golden(case, packed, block_size):
-    """block_size=None: one column block, fused kernel; 1024/2048: column-blocked gather + update kernels."""
+@pytest.mark.parametrize("layout", ["stream", "bcsr"])
+def test_episode_matches_reference_golden(case, packed, block_size, layout):
+    """stream: flat per-block streams + fixed-point hit records (gather + update kernels), one or several source blocks.
+    bcsr: block_size=None one column block, fused kernel; 1024/2048: column-blocked gather + update kernels."""
     g = load_golden(case)
-    st, gr2, gm, eng = _run_engine(g, packed=packed, block_size=block_size)
+    st, gr2, gm, eng = _run_engine(g, packed=packed, block_size=block_size, layout=layout,
+                                   tile_rows=(256 if block_size == 1024 else None) if layout == "stream" else None)
+    assert eng.graph.layout == (1 if layout == "stream" else 0)
     if block_size is not None and len(g["age"]) > block_size:
         assert eng.graph.n_blocks > 1
+    _check(g, st, gr2, gm)
+
+
+@pytest.mark.parametrize("case", ["synth3k_soft", "astoria_hard", "astoria_soft"])
+@pytest.mark.parametrize("kw", [dict(warps_per_cta=24), dict(warps_per_cta=16, grid=3), dict(tile_rows=64, block_size=4096, grid=301),
+                                dict(tasks_per_group=2)])
+def test_stream_layout_kernel_variants(case, kw):
+    """the stream gather's register-budget variants (32 / 24 / 16 warps with 3 / 4 / 6 units in flight), grids that make CTAs
+    span source blocks, tiny tiles"""
+    g = load_golden(case)
+    st, gr2, gm, eng = _run_engine(g, packed=True, layout="stream", **kw)
+    assert eng.graph.layout == 1
     _check(g, st, gr2, gm)
 
 
@@ -83,8 +101,9 @@ def test_hashed_filter_mode(case, hash_words):
 @pytest.mark.parametrize("case", ["synth3k_soft", "astoria_hard"])
 def test_tensor_noise_and_cuda_graph_paths(case):
     g = load_golden(case)
-    st, gr2, gm, _ = _run_engine(g, packed=True, use_tensor_noise=True, tasks_per_group=1)
-    _check(g, st, gr2, gm)
-    st, gr2, gm, eng = _run_engine(g, packed=True, block_size=1024, cuda_graph=True, grid=7, tasks_per_group=8)
-    _check(g, st, gr2, gm)
-    assert eng.launch_count > 0
+    for layout in ("stream", "bcsr"):
+        st, gr2, gm, _ = _run_engine(g, packed=True, use_tensor_noise=True, tasks_per_group=1, layout=layout)
+        _check(g, st, gr2, gm)
+        st, gr2, gm, eng = _run_engine(g, packed=True, block_size=1024, cuda_graph=True, grid=7, tasks_per_group=8, layout=layout)
+        _check(g, st, gr2, gm)
+        assert eng.launch_count > 0

@@ -72,7 +72,8 @@ R2, M = np.array([[0.30], [0.25], [0.20]], dtype=np.float32), np.array([0.2], dt
 
 
 @pytest.mark.parametrize("mode", ["hard", "soft"])
-@pytest.mark.parametrize("kw", [dict(), dict(block_size=2048), dict(hash_words=128), dict(edges_per_chunk=512)])
+@pytest.mark.parametrize("kw", [dict(), dict(block_size=2048, tile_rows=512), dict(layout="bcsr"), dict(layout="bcsr", block_size=2048),
+                                dict(hash_words=128), dict(edges_per_chunk=512)])
 def test_tasks_larger_than_one_chunk(mode, kw):
     """average in-degree 45: a 32-row task holds ~1440 edges = 2-3 TMA chunks of 512/768 edges"""
     age, stage0, edges = _inputs(6000, 45.0, 3)
@@ -103,7 +104,9 @@ def test_100k_agents_against_the_oracle():
 def test_layouts_grids_and_reruns_are_bitwise_identical():
     age, stage0, edges = _inputs(50_000, 12.0, 8)
     base = None
-    for kw in (dict(), dict(), dict(grid=5), dict(warps_per_cta=4), dict(block_size=8192), dict(hash_words=256), dict(tasks_per_group=2)):
+    for kw in (dict(), dict(), dict(grid=5), dict(warps_per_cta=4), dict(block_size=8192), dict(warps_per_cta=24, tile_rows=256),
+               dict(bank_aware=False), dict(layout="bcsr"), dict(layout="bcsr", grid=5), dict(layout="bcsr", warps_per_cta=4),
+               dict(layout="bcsr", block_size=8192), dict(hash_words=256), dict(layout="bcsr", tasks_per_group=2)):
         st, gr2, gm, _ = _gpu_episode(age, stage0, edges, 3, "soft", R2 * 10, M, **kw)
         cur = (st.stage.cpu(), st.next_stage_time.cpu(), st.daily_infected.cpu(), st.daily_deaths.cpu())
         if base is None:
