@@ -21,7 +21,7 @@ TIMER_F32, TIMER_I16 = 0, 1
 AGE_F32, AGE_U8 = 0, 1
 ISO_TENSOR, ISO_HASH_SOFT, ISO_HASH_HARD, ISO_NONE = 0, 1, 2, 3
 U_TENSOR, U_HASH = 0, 1
-DO_TRANSMISSION, DO_PROGRESSION, DO_ENCODE, DO_INIT = 1, 2, 4, 8
+DO_TRANSMISSION, DO_PROGRESSION, DO_ENCODE, DO_INIT, DO_LOOKAHEAD = 1, 2, 4, 8, 16
 MAX_BLOCKS = 64
 LAYOUT_BCSR, LAYOUT_STREAM = 0, 1
 STREAM_UNIT, STREAM_MAX_TILE_ROWS, STREAM_MAX_BLOCK_SIZE = 256, 2048, (1 << 21) - 1024
@@ -70,7 +70,8 @@ class SeirmLaunch(ctypes.Structure):
         ("warps_per_cta", ctypes.c_int32), ("hash_words", ctypes.c_int32),
         ("unit_tile", ctypes.c_void_p), ("block_units", ctypes.c_void_p), ("tile_rec_base", ctypes.c_void_p),
         ("tile_count", ctypes.c_void_p), ("rec", ctypes.c_void_p),
-        ("lam_deg_bits", ctypes.c_int32), ("_pad1", ctypes.c_int32),
+        ("lam_deg_bits", ctypes.c_int32), ("xchg_slot", ctypes.c_int32),
+        ("reserve_sms", ctypes.c_int32), ("_pad2", ctypes.c_int32),
     ]
 
 
@@ -138,7 +139,7 @@ def lib():
         L.at_seirm_exchange_sparse.restype = ctypes.c_int
         L.at_seirm_exchange_sparse.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
                                                ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
-                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
         L.at_noise_fill.restype = ctypes.c_int
         L.at_noise_fill.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32,
                                     ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]

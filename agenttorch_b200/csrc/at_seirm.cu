@@ -47,7 +47,8 @@
 #define WS_ACC 0                    // int64[3]: sum ne, sum dne, deaths (fixed point)
 #define WS_TICKET 32                // int: CTAs finished (main kernel)
 #define WS_COUNTER 36               // int: group counter (main kernel)
-#define WS_ANYHOT 40                // uint: some agent of this rank is infectious in the step just encoded (read + reset by the exchange)
+#define WS_ANYHOT 40                // uint[3]: some agent of this rank is infectious in the step just encoded, one word per code
+                                    // buffer in flight (at_seirm_launch.xchg_slot; read + reset by the exchange)
 #define WS_GCOUNTERS 64             // int[AT_MAX_BLOCKS]: group counters of the gather kernel
 #define WS_GTICKET 384              // int
 #define WS_BTICKET 512              // int: backward kernel
@@ -156,6 +157,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     const bool do_prog = (a.flags & AT_DO_PROGRESSION) != 0;
     const bool do_enc = (a.flags & AT_DO_ENCODE) != 0;
     const bool do_init = (a.flags & AT_DO_INIT) != 0;
+    const bool lookahead = (a.flags & AT_DO_LOOKAHEAD) != 0;
     const bool want_grad = a.dne_dr != nullptr;
     const bool weighted = a.edge_weight != nullptr;
     const bool timer_f32 = a.timer_dtype == AT_TIMER_F32, age_f32 = a.age_dtype == AT_AGE_F32;
@@ -393,7 +395,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
                     acc_dead += 1;                         // stage * rd / INFECTED_VAR = 2/2
                     if (a.recovered_step) a.recovered_step[row] = (uint8_t)t;
                 }
-                if (nst == t) store_timer(a.next_stage_time, row, is_i ? m.inf_time : t + m.i2r, timer_f32);
+                if (nst == t) { nst = is_i ? m.inf_time : t + m.i2r; store_timer(a.next_stage_time, row, nst, timer_f32); }
                 stage = is_i ? 3.0f : 2.0f;
                 stage_known = true;
                 a.stage[row] = stage;
@@ -407,9 +409,15 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             uint32_t code = 0;
             // infectious = 0 < stage < 3; fractional stages (soft isolation, Q4) index SFInfector[0]
             const bool frac = stage_known && stage > 0.0f && stage < 3.0f && !(is_e || is_i);
-            if (is_e || is_i || frac) {
+            bool ce = is_e, ci = is_i;                       // classes the code is computed for
+            if (lookahead && (is_e || is_i)) {
+                // the stage after the progression of step t_encode-1 (progression :41-88: E/I rows that are due move on)
+                if (!nst_known) { nst = load_timer(a.next_stage_time, row, timer_f32); nst_known = true; }
+                if (nst <= a.t_encode - 1) { ci = ce; ce = false; }
+            }
+            if (ce || ci || frac) {
                 if (!itime_known) itime = load_timer(a.infected_time, row, timer_f32);
-                const int sidx = is_e ? 1 : (is_i ? 2 : (int)stage);
+                const int sidx = ce ? 1 : (ci ? 2 : (int)stage);
                 int idx = a.t_encode - itime - 1;
                 if (idx < 0 || idx >= m.n_lg) {
                     if (a.error_flag && sidx < m.n_sfi && m.sfi[sidx] != 0.f) *a.error_flag = 1;
@@ -707,7 +715,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             if (s0) atomicAdd(&acc[0], (unsigned long long)s0);
             if (s1) atomicAdd(&acc[1], (unsigned long long)s1);
             if (s2) atomicAdd(&acc[2], (unsigned long long)s2);
-            if (s_any_out) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_ANYHOT), 1u);
+            if (s_any_out) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_ANYHOT) + a.xchg_slot, 1u);
         }
         __threadfence();
         s_is_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
@@ -793,7 +801,6 @@ __device__ __noinline__ void stream_resolve(const StreamResolveCtx& c, const uin
     __syncwarp();
 }
 
-// NTHREADS: CTA size the kernel is compiled for (register budget); UF: units in flight per warp (register sets)
 // Table of the step's fixed-point lambda terms, computed ONCE per step (by the last CTA of the gather launch, for the update
 // launch that follows it in the stream): term[age][code] = f64(f32(((R*S)*A)*G)) / I_bar, the reference's message
 // (transition.py:78-83), rounded once to the 2^-shift grid, shift chosen so that in-degree * largest term < 2^62.
@@ -842,9 +849,11 @@ __device__ void stream_build_term_table(const KModel& m, const at_seirm_launch& 
     __syncthreads();
 }
 
-template <int NTHREADS, int UF>
-__global__ void __launch_bounds__(NTHREADS, 1)
-stream_gather_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const int NC, const int tile_shift)
+// UF: units in flight per warp (register sets).  The body is shared by the __global__ entry points below, which differ in their
+// register budget.
+template <int UF>
+__device__ __forceinline__ void
+stream_gather_body(const KModel& m, const at_seirm_launch& a, const int bm_words, const int NC, const int tile_shift)
 {
     AT_DYNAMIC_SMEM(unsigned char, smem_raw, 128);
     const int nw = blockDim.x >> 5;
@@ -960,6 +969,25 @@ stream_gather_kernel(const KModel m, const at_seirm_launch a, const int bm_words
     }
 }
 
+// NTHREADS: CTA size the entry point is compiled for (its register budget)
+template <int NTHREADS, int UF>
+__global__ void __launch_bounds__(NTHREADS, 1)
+stream_gather_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const int NC, const int tile_shift)
+{
+    stream_gather_body<UF>(m, a, bm_words, NC, tile_shift);
+}
+// The "lean" entry point: 1024 threads with at most 56 registers each, which leaves 8 K registers of every SM to a 256-thread
+// CTA of another stream — the overlapped halo exchange of the next-but-one step runs beside it instead of waiting for it.
+#ifndef AT_HOST_EMULATION
+__global__ void __maxnreg__(56)
+#else
+__global__ void
+#endif
+stream_gather_lean_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const int NC, const int tile_shift)
+{
+    stream_gather_body<2>(m, a, bm_words, NC, tile_shift);
+}
+
 // ------------------------------------------------------------------------------- stream-layout update
 // Second kernel of a stream-layout step: transmission decision + progression + encoding of the next step
 // (reference: transition.py:219-252, seirm_progression/transition.py:41-121).  A CTA takes whole row tiles and works in
@@ -994,6 +1022,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = TU_THREADS / 32;
     const bool age_f32 = a.age_dtype == AT_AGE_F32;
     const bool do_prog = (a.flags & AT_DO_PROGRESSION) != 0, do_enc = (a.flags & AT_DO_ENCODE) != 0;
+    const bool lookahead = (a.flags & AT_DO_LOOKAHEAD) != 0;
     const int t = a.t;
     const float R = a.r_value[a.r_index];
     const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
@@ -1158,7 +1187,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
             bool is_e = (exp_w >> lane) & 1u, is_i = (inf_w >> lane) & 1u;
             uint32_t code = 0;
             if (is_e || is_i) {
-                const int nst = do_prog ? ld_timer(a.next_stage_time, row) : 0;     // both timers in flight together
+                int nst = (do_prog || lookahead) ? ld_timer(a.next_stage_time, row) : 0;     // both timers in flight together
                 const int itime = do_enc ? ld_timer(a.infected_time, row) : 0;
                 if (do_prog) {
                     if (nst <= t) {                              // progression (seirm_progression/transition.py:41-88)
@@ -1166,14 +1195,16 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
                             acc_dead += 1;                      // stage * rd / INFECTED_VAR = 2/2
                             if (a.recovered_step) a.recovered_step[row] = (uint8_t)t;
                         }
-                        if (nst == t) st_timer(a.next_stage_time, row, is_i ? m.inf_time : t + m.i2r);
+                        if (nst == t) { nst = is_i ? m.inf_time : t + m.i2r; st_timer(a.next_stage_time, row, nst); }
                         a.stage[row] = is_i ? 3.0f : 2.0f;
                         const bool was_e = is_e;
                         is_e = false;
                         is_i = was_e;
                     }
                 }
-                if (do_enc && (is_e || is_i)) code = encode(is_e ? 1 : 2, itime);
+                bool ce = is_e, ci = is_i;                       // classes the code is computed for
+                if (lookahead && (is_e || is_i) && nst <= a.t_encode - 1) { ci = ce; ce = false; }   // after the progression of t_encode-1
+                if (do_enc && (ce || ci)) code = encode(ce ? 1 : 2, itime);
             }
             const uint32_t hot = __ballot_sync(0xffffffffu, code != 0u) | frac_hot;
             if (code != 0u) code_out[row] = (uint8_t)code;
@@ -1212,7 +1243,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
         if (s0) atomicAdd(&acc[0], (unsigned long long)s0);
         if (s1) atomicAdd(&acc[1], (unsigned long long)s1);
         if (s2) atomicAdd(&acc[2], (unsigned long long)s2);
-        if (s_any_out) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_ANYHOT), 1u);
+        if (s_any_out) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_ANYHOT) + a.xchg_slot, 1u);
         __threadfence();
         s_is_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
     }
@@ -1621,6 +1652,8 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     if ((a.flags & AT_DO_PROGRESSION) && (!a.next_stage_time || (a.daily_deaths && !a.m_value))) return fail("%s", "progression needs next_stage_time and m_value");
     if ((a.flags & AT_DO_ENCODE) && (!a.code_out || !a.hot_bitmap_out || !a.infected_time)) return fail("%s", "encode needs code_out, hot_bitmap_out, infected_time");
     if (a.t < 0 || a.t > 255) return fail("%s", "t out of range (0..255)");
+    if (a.xchg_slot < 0 || a.xchg_slot > 2) return fail("%s", "xchg_slot out of range (0..2)");
+    if ((a.flags & AT_DO_LOOKAHEAD) && (!(a.flags & AT_DO_ENCODE) || !a.next_stage_time)) return fail("%s", "AT_DO_LOOKAHEAD needs AT_DO_ENCODE and next_stage_time");
     if (device_props()) return fail("%s", "cannot query device");
     if (a.n_rows == 0) return 0;
 
@@ -1669,13 +1702,21 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         while ((1 << tile_shift) < a.tile_rows) ++tile_shift;
         // the more warps, the fewer registers each has for units in flight: 32 warps x 3 units, 24 x 5, <= 16 x 8 (KB per SM: 96 / 120 / 128)
         int rc;
-        if (pw > 24 && a.tasks_per_group == 2) rc = launch_stream<1024, 2>(km, al, grid, pw * 32, smem, words, NC, tile_shift, s);
+        if (a.reserve_sms > 0) {
+            // leave room for a concurrent halo exchange: the lean gather (56 registers) here, 7 instead of 8 update CTAs per SM below
+            auto k = stream_gather_lean_kernel;
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            AT_LAUNCH_SMEM(k, grid, (pw > 32 ? 32 : pw) * 32, smem, s, km, al, words, NC, tile_shift);
+            e = cudaGetLastError();
+            rc = (e != cudaSuccess) ? fail("stream_gather_lean_kernel launch: %s", cudaGetErrorString(e)) : 0;
+        } else if (pw > 24 && a.tasks_per_group == 2) rc = launch_stream<1024, 2>(km, al, grid, pw * 32, smem, words, NC, tile_shift, s);
         else if (pw > 24) rc = launch_stream<1024, 3>(km, al, grid, pw * 32, smem, words, NC, tile_shift, s);
         else if (pw > 16) rc = launch_stream<768, 4>(km, al, grid, pw * 32, smem, words, NC, tile_shift, s);
         else rc = launch_stream<512, 6>(km, al, grid, pw * 32, smem, words, NC, tile_shift, s);
         if (rc) return rc;
         al.edges_per_chunk = 512;
-        int tgrid = a.grid > 0 ? a.grid : g_sm_count * 8;
+        int tgrid = a.grid > 0 ? a.grid : g_sm_count * (a.reserve_sms > 0 ? 7 : 8);
         const int64_t n_tiles = a.n_rows_pad / a.tile_rows;
         if (tgrid > n_tiles) tgrid = (int)n_tiles;
         const size_t usmem = (size_t)model->n_sfs * NC * 8 + 2 * 256 * 4 + (size_t)a.tile_rows * 11;
@@ -1786,7 +1827,7 @@ int64_t at_seirm_exchange_bytes(int64_t n_sources) {
 
 int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* hot_filter, int32_t hash_words,
                              void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, void* step_workspace,
-                             int32_t* error_flag, void* stream) {
+                             int32_t* error_flag, int32_t max_ctas, void* stream) {
     if (!local_buf || !peer_buf || !sync_state) return fail("%s", "exchange_sparse: null buffer");
     if (n_sources <= 0 || (n_sources & 1023)) return fail("%s", "exchange_sparse: n_sources must be a positive multiple of 1024");
     if (world < 2 || world > 16 || rank < 0 || rank >= world || (n_sources % world) || ((n_sources / world) & 1023))
@@ -1808,6 +1849,7 @@ int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* ho
     // every CTA spins on the arrival flags: keep all of them co-resident (one wave)
     int64_t tiles = (n_sources / 32 + 255) / 256;
     int grid = (int)(tiles < g_sm_count * 4 ? tiles : g_sm_count * 4);
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (grid < 1) grid = 1;
     uint32_t* any_word = step_workspace ? reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(step_workspace) + WS_ANYHOT) : nullptr;
     AT_LAUNCH(exchange_sparse_kernel, grid, 256, s, local_buf, n_sources, hot_filter, hash_words, pb, world, rank, n_sources / world,

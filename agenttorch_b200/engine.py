@@ -148,7 +148,7 @@ def _ptr(t, dtype=None, name="tensor"):
 class SeirmEngine:
     def __init__(self, graph, spec: SeirmSpec, process_group=None, grid=0, code_len=None, block_size=None,
                  tasks_per_group=0, edges_per_chunk=None, warps_per_cta=0, hashed=None, hash_words=None, hash_min_warps=20, symmetric=None, sparse_exchange=True,
-                 layout="auto", tile_rows=None, bank_aware=True):
+                 layout="auto", tile_rows=None, bank_aware=True, overlap_exchange=None):
         """graph: ContactGraph (plain CSR, re-blocked here) or a prebuilt BlockedGraph.  block_size: sources
         per column block (default: the largest that fits the shared-memory bitmap, i.e. as few blocks as
         possible); code_len: length of the code/bitmap arrays (multi-GPU: world_size equal slices).
@@ -247,6 +247,24 @@ class SeirmEngine:
         # collectives could not).  symmetric=None: try, fall back to the NCCL all-gather.
         self.code_hdl = None
         self.sparse_exchange = bool(sparse_exchange)
+        # Overlapped halo exchange: lam_gamma_integrals[0] == 0 (the gamma CDF difference at day 0, utils.py:14-27) means an agent
+        # exposed at step t contributes nothing at t+1, so the infectiousness of step t+2 is known when step t ends — every
+        # E/I agent's code follows from (stage, timers) and the progression it will make at t+1.  The step kernels then encode
+        # TWO steps ahead (AT_DO_LOOKAHEAD) into a third code buffer and the exchange of step t+2 runs on a side stream while
+        # step t+1 computes.  Checked here; anything else keeps the synchronous exchange.
+        can_overlap = (process_group is not None and self.sparse_exchange and float(spec.lam_gamma[0]) == 0.0
+                       and int(spec.exposed_to_infected_time) >= 1)
+        import os
+
+        if overlap_exchange is None and os.environ.get("AGENTTORCH_B200_OVERLAP_EXCHANGE") in ("0", "1"):
+            overlap_exchange = os.environ["AGENTTORCH_B200_OVERLAP_EXCHANGE"] == "1" and can_overlap     # developer switch
+        if overlap_exchange and not can_overlap:
+            raise ValueError("overlap_exchange needs several ranks, the sparse exchange and lam_gamma_integrals[0] == 0")
+        # Measured on 2 and 4 B200s (profiles/r02_multigpu.md) the overlapped form is 4-6 % SLOWER than the synchronous exchange:
+        # the exchange is not what bounds a step there (fixed launch / prologue costs are), and the lean kernels plus the second
+        # encode launch cost more than the hidden rendezvous saves.  So it is opt-in.
+        self.overlap = False if overlap_exchange is None else bool(overlap_exchange)
+        n_buf = 3 if self.overlap else 2
         if process_group is not None and symmetric is not False:
             try:
                 import torch.distributed._symmetric_memory as symm
@@ -254,13 +272,13 @@ class SeirmEngine:
                 # one symmetric buffer per step parity: [code bytes][hot bitmap][arrival flags] (include/at_seirm.h,
                 # at_seirm_exchange_sparse); the step kernel writes this rank's slice of the first two parts
                 nbytes = int(self.lib.at_seirm_exchange_bytes(self.n_code))
-                self.xbuf = [symm.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+                self.xbuf = [symm.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(n_buf)]
                 self.code_hdl = [symm.rendezvous(c, process_group) for c in self.xbuf]
                 for c in self.xbuf:
                     c.zero_()
                 self.code = [c[: self.n_code] for c in self.xbuf]
                 self.hot = [c[self.n_code: self.n_code + self.n_code // 8 + 16].view(torch.int32) for c in self.xbuf]
-                self.xsync = [torch.zeros(32, dtype=torch.int32, device=dev) for _ in range(2)]
+                self.xsync = [torch.zeros(32, dtype=torch.int32, device=dev) for _ in range(n_buf)]
                 torch.cuda.synchronize(dev)
                 import torch.distributed as dist
 
@@ -270,6 +288,7 @@ class SeirmEngine:
                     raise
                 self.code_hdl = None
         if self.code_hdl is None:
+            self.overlap = False                                  # the overlapped exchange is the symmetric-memory kernel
             self.code = [torch.zeros(self.n_code, dtype=torch.uint8, device=dev) for _ in range(2)]
             self.hot = [torch.zeros(self.n_code // 32 + 4, dtype=torch.int32, device=dev) for _ in range(2)]
         self.cur = 0
@@ -303,12 +322,13 @@ class SeirmEngine:
         # kernels of a covid config, which read the stage array the step just updated); episodes with a hook are not captured
         # into CUDA graphs (the hook's buffers are not part of the capture key)
         self.after_step = None
+        self._side = None                    # side stream of the overlapped halo exchange
 
     # ------------------------------------------------------------------------------ raw launch
     def launch(self, state: SeirmState, *, flags, t, t_encode=None, code_in=None, code_out=None,
                noise: Optional[NoiseSpec] = None, isolation=None, uniform=None, r_value=None, r_index=0,
                m_value=None, dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None,
-               seed_ptr=None, check_range=True):
+               seed_ptr=None, check_range=True, xchg_slot=0, reserve_sms=0):
         g = self.graph
         a = nat.SeirmLaunch()
         a.abi_version = nat.ABI_VERSION
@@ -379,6 +399,8 @@ class SeirmEngine:
         a.tasks_per_group = int(self.tasks_per_group)
         a.warps_per_cta = int(self.warps_per_cta)
         a.hash_words = int(g.hash_words)
+        a.xchg_slot = int(xchg_slot)
+        a.reserve_sms = int(reserve_sms)
         rec = getattr(self, "_recording", None)
         if rec is not None:
             rec.append((a, self._kernels_of(flags)))
@@ -401,12 +423,19 @@ class SeirmEngine:
         n = self._kernels_of(nat.DO_ENCODE | nat.DO_INIT) + num_steps * self._kernels_of(full) + (1 if backward else 0)
         if self.pg is not None:
             n += num_steps + 1               # one pull / rebuild kernel per halo exchange
+            if self.overlap:
+                n += 1                       # the second encode launch (two steps are encoded before step 0)
         return n
 
     # ------------------------------------------------------------------------ halo exchange
-    def exchange(self, buf_index):
+    # the overlapped exchange runs beside the step kernels of the same rank, which are launched in their register-lean form
+    # (at_seirm_launch.reserve_sms): 8 K registers and 256 threads of every SM stay free, one exchange CTA per SM fits
+    OVERLAP_SMS = 148
+
+    def exchange(self, buf_index, slot=0, max_ctas=0):
         """Make every rank's freshly written slice of code/bitmap visible to all ranks (the per-step
-        halo exchange of boundary-agent infectiousness).  No-op on one GPU."""
+        halo exchange of boundary-agent infectiousness).  No-op on one GPU.  slot: the workspace word (at_seirm_launch.xchg_slot)
+        in which the launch that wrote the slice noted whether it holds an infectious agent."""
         if self.pg is None:
             return
         from .parallel import halo_exchange
@@ -425,8 +454,8 @@ class SeirmEngine:
                 # (P2P loads of the non-empty 32-byte code sectors only) + filter fold
                 nat.check(self.lib.at_seirm_exchange_sparse(_ptr(self.xbuf[buf_index]), int(self.n_code), _ptr(filt),
                                                             int(self.graph.hash_words), ptrs, world, rank,
-                                                            _ptr(self.xsync[buf_index]), _ptr(self.workspace),
-                                                            _ptr(self.error_flag), ctypes.c_void_p(stream)))
+                                                            _ptr(self.xsync[buf_index]), _ptr(self.workspace) + 4 * int(slot),
+                                                            _ptr(self.error_flag), int(max_ctas), ctypes.c_void_p(stream)))
             else:
                 hdl.barrier(channel=buf_index)                   # every rank has written its slice of this buffer
                 # dense: pull the peers' whole slices (P2P loads) + rebuild bitmap/filter from the codes, one kernel
@@ -484,6 +513,8 @@ class SeirmEngine:
                None if noise.isolation_tensor is None else noise.isolation_tensor.data_ptr(),
                None if noise.uniform_tensor is None else noise.uniform_tensor.data_ptr())
         sv["recovered_step"].fill_(255)
+        if self.overlap:
+            return self._issue_episode_overlapped(state, num_steps, noise, sv, want_grad, t0)
         plan = self._plans.get(key)
         if plan is not None:
             for k, (a, nk, flips) in enumerate(plan):
@@ -515,6 +546,58 @@ class SeirmEngine:
         if len(self._plans) > 8:
             self._plans.clear()
         self._plans[key] = plan
+
+    def _issue_episode_overlapped(self, state, num_steps, noise, sv, want_grad, t0=0):
+        """Episode with the halo exchange taken off the critical path: step t encodes the infectiousness of step t+2
+        (AT_DO_LOOKAHEAD) into code buffer (t+2) % 3, whose exchange runs on a side stream while step t+1 computes; step t+2
+        waits for it.  Same results as the synchronous path (tests/test_gpu_multi.py, emulated multi-rank tests)."""
+        streams = self.device.type == "cuda"                  # (the host-emulation tests run the same sequence in program order)
+        main = side = None
+        if streams:
+            main = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side
+        full = nat.DO_TRANSMISSION | nat.DO_PROGRESSION | nat.DO_ENCODE | nat.DO_LOOKAHEAD
+        # code(t0) from the initial state, exchanged on the main stream; code(t0+1) predicted, exchanged beside step t0
+        self.launch(state, flags=nat.DO_ENCODE | nat.DO_INIT, t=0, t_encode=t0, code_in=2, code_out=0, xchg_slot=0)
+        self.exchange(0, slot=0)
+        self.launch(state, flags=nat.DO_ENCODE | nat.DO_LOOKAHEAD, t=t0, t_encode=t0 + 1, code_in=2, code_out=1, xchg_slot=1)
+        done = {}
+
+        def exchange_on_side(k):
+            if not streams:
+                self.exchange(k % 3, slot=k % 3, max_ctas=self.OVERLAP_SMS)
+                return
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                self.exchange(k % 3, slot=k % 3, max_ctas=self.OVERLAP_SMS)
+                done[k] = torch.cuda.Event()
+                done[k].record(side)
+
+        if num_steps > 1:
+            exchange_on_side(1)
+        for k in range(num_steps):
+            t = t0 + k
+            if k in done:
+                main.wait_event(done.pop(k))
+            iso = noise.isolation_tensor[k] if noise.isolation == "tensor" else None
+            uni = noise.uniform_tensor[k] if noise.uniform == "tensor" else None
+            needed = k + 2 < num_steps                               # somebody will gather from code(t+2)
+            self.launch(state, flags=full, t=t, t_encode=t + 2, code_in=k % 3, code_out=(k + 2) % 3, noise=noise, isolation=iso,
+                        uniform=uni, r_value=sv["r_steps"], r_index=k, m_value=sv["m_value"],
+                        dne_dr=sv["dne_dr"][k] if want_grad else None, sum_dne_dr=sv["sum_dne_dr"], death_count=sv["death_count"],
+                        recovered_step=sv["recovered_step"], seed_ptr=self.seed_buf, check_range=needed, xchg_slot=(k + 2) % 3,
+                        reserve_sms=1)
+            if needed:
+                exchange_on_side(k + 2)
+            if self.after_step is not None:
+                self.after_step(t)
+        if streams:
+            main.wait_stream(side)
+        self.cur = 0
 
     def run_episode(self, state, r_steps, m_value, num_steps, noise: NoiseSpec, want_grad=False, cuda_graph=False):
         """Advance `state` in place through `num_steps` steps (t = 0..num_steps-1, as Runner.step does).

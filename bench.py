@@ -240,7 +240,9 @@ def ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     _native.lib()
     N, d, T = args.agents, args.degree, T_STEPS
     gI = torch.linspace(0.5, 1.5, T, device=dev)
@@ -311,8 +313,10 @@ def ours(args):
     for _ in range(args.warmup):
         episode(snap_dev, False)
     sampler = ClockSampler(local)
-    t_load = time.perf_counter()
-    while time.perf_counter() - t_load < 0.6:  # nvidia-smi needs a few periods under load before the timed regions begin
+    # nvidia-smi needs a few periods under load before the timed regions begin: ~0.6 s of episodes — the SAME number on every
+    # rank (derived from an all-reduced time), a rank-local loop "until 0.6 s have passed" would desynchronise the collectives
+    n_load = max(3, min(2000, int(600.0 / max(timed(lambda: episode(snap_dev, False), 3) / 3, 0.05))))
+    for _ in range(n_load):
         episode(snap_dev, False)
     l0 = engine.launch_count
     ms = timed(lambda: episode(snap_dev, False), args.steps)
@@ -386,7 +390,10 @@ def ours(args):
                 dist.all_reduce(times, op=dist.ReduceOp.MAX)
             times = times.tolist()
             if best is None or sum(times) < sum(best[0]):
-                best = (times, active, float(st.daily_infected.sum()))
+                di_sum = st.daily_infected.sum().reshape(1).clone()
+                if world > 1:
+                    dist.all_reduce(di_sum)
+                best = (times, active, float(di_sum))
         return best
 
     def resident_engine_episodes(isolation, k):

@@ -63,6 +63,12 @@ extern "C" {
                                 instead of reading them (first launch on a state, or after the
                                 caller edited the state)                                          */
 
+#define AT_DO_LOOKAHEAD 16   /* with AT_DO_ENCODE: `t_encode` lies one step beyond the state this launch leaves, so the
+                                code is computed for the stage every agent WILL have after the progression of step
+                                t_encode-1 (E/I agents whose next_stage_time <= t_encode-1 move on; agents exposed in
+                                between contribute lam_gamma[0]*... at t_encode, which must be 0 — the caller checks).
+                                Lets the halo exchange of step t+2 run while step t+1 computes.           */
+
 /* Model constants (simulation_metadata + environment tables of config.yaml). Host struct. */
 typedef struct at_seirm_model {
     int32_t n_sfs, n_sfi, n_lam_gamma;
@@ -182,7 +188,12 @@ typedef struct at_seirm_launch {
     uint32_t* tile_count;       /* [tiles] records of the tile this step, all zero between launches */
     uint32_t* rec;              /* [edges] hit records (row_in_tile << 8) | source code, grouped by tile */
     int32_t lam_deg_bits;       /* ceil(log2(largest in-degree + 1)): head room of the fixed-point sums */
-    int32_t _pad1;
+    int32_t xchg_slot;          /* 0..2: which "my slice holds an infectious agent" word of the workspace this launch sets
+                                   (one per code buffer in flight; at_seirm_exchange_sparse reads and clears it) */
+    int32_t reserve_sms;        /* stream layout, != 0: the step kernels leave 1/8 of every SM's registers free (lean gather entry
+                                   point, 7 instead of 8 update CTAs per SM), so that a halo exchange issued on another stream runs
+                                   beside them instead of waiting for them (they otherwise take every register of every SM) */
+    int32_t _pad2;
 } at_seirm_launch;
 
 /* ---- queries (host only) ---- */
@@ -252,13 +263,15 @@ int at_seirm_pull_codes(uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, 
  * non-zero (a slice whose owner reports no infectious agent, and of which no stale copy is held, is skipped altogether),
  * and folds the whole bitmap into hot_filter (may be NULL).  sync_state: 32 zero-initialised device words per buffer,
  * owned by this call sequence.  step_workspace: the at_seirm_launch.workspace of the step kernel that wrote this rank's
- * slice (it records there whether the slice holds any infectious agent; NULL = scan the slice).  A peer that never arrives sets *error_flag = 2 after ~20 s.
+ * slice (it records there whether the slice holds any infectious agent; NULL = scan the slice).  max_ctas: 0 = as many
+ * 256-thread CTAs as fit in one wave; > 0 caps the grid (an exchange that runs BESIDE the step kernels of the next step
+ * should only occupy the SMs those leave free, at_seirm_launch.reserve_sms).  A peer that never arrives sets *error_flag = 2 after ~20 s.
  * Replaces nothing in the reference (core/distributed_runner.py:218-228 is `pass`).
  */
 int64_t at_seirm_exchange_bytes(int64_t n_sources);
 int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* hot_filter, int32_t hash_words,
                              void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, void* step_workspace,
-                             int32_t* error_flag, void* stream);
+                             int32_t* error_flag, int32_t max_ctas, void* stream);
 
 /*
  * at_noise_fill — materialise the counter-hash noise (same values the step kernel generates in

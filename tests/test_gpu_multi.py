@@ -39,10 +39,11 @@ def _episode(rank, world, port, out_dir, cuda_graph):
     graph = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, row_begin=r0, row_end=r1)
     graph.i_bar, graph.i_bar_agent = full.i_bar, full.i_bar_agent
     dense = cuda_graph == "dense"                                  # symmetric memory, barrier + whole-slice pull
+    sync = cuda_graph == "sync"                                    # sparse exchange on the critical path (no look-ahead encoding)
     cuda_graph = bool(cuda_graph)
     eng = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=shard_code_len(N, world),
                       symmetric=None if cuda_graph else False,      # False: NCCL all-gather path
-                      sparse_exchange=not dense)
+                      sparse_exchange=not dense, overlap_exchange=bool(cuda_graph) and not (sync or dense) and world > 1)
     st = SeirmState.from_initial(stage0[r0:r1], age[r0:r1], T, dev)
     r_steps = torch.full((T,), 14.25, device=dev)
     m = torch.tensor([0.12], device=dev)
@@ -64,10 +65,11 @@ def _episode(rank, world, port, out_dir, cuda_graph):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cuda_graph", [False, True, "dense"])
+@pytest.mark.parametrize("cuda_graph", [False, True, "sync", "dense"])
 def test_two_gpus_reproduce_one_gpu(tmp_path, cuda_graph):
     """False: NCCL all-gather, issued step by step.  True: symmetric memory, one kernel per step with the rendezvous
-    inside and a bitmap-directed sparse pull, the whole episode replayed from one CUDA graph per rank.
+    inside and a bitmap-directed sparse pull, issued on a side stream for step t+2 while step t+1 computes (look-ahead
+    encoding), the whole two-stream episode replayed from one CUDA graph per rank.  "sync": the same exchange on the critical path.
     "dense": symmetric memory with a separate barrier and a whole-slice pull (the round-1 first version)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

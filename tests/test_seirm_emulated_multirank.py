@@ -112,10 +112,12 @@ def _episode(rank, world, port, out_dir, lib_path, exchange, tag):
         graph = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", row_begin=r0, row_end=r1)
         graph.i_bar, graph.i_bar_agent = full.i_bar, full.i_bar_agent
         eng = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=shard_code_len(N, world), warps_per_cta=2,
-                          symmetric=(exchange != "allgather") if world > 1 else None, sparse_exchange=exchange == "sparse",
+                          symmetric=(exchange != "allgather") if world > 1 else None, sparse_exchange=exchange.startswith("sparse"),
+                          overlap_exchange=(exchange == "sparse") if world > 1 else None,
                           hashed=True if HASHED else None, hash_words=32 if HASHED else None)
         if world > 1:
             assert (eng.code_hdl is not None) == (exchange != "allgather")
+            assert eng.overlap == (exchange == "sparse")         # lam_gamma_integrals[0] == 0: the exchange of t+2 runs beside step t+1
         st = SeirmState.from_initial(stage0[r0:r1], age[r0:r1], T, torch.device("cpu"))
         r_steps, m = torch.full((T,), R_VALUE), torch.tensor([0.12])
         sv = eng.run_episode(st, r_steps, m, T, NoiseSpec(seed=9, isolation=ISOLATION), want_grad=True, cuda_graph=False)
@@ -143,7 +145,7 @@ def single_rank(emulated_library, tmp_path_factory):
     return torch.load(os.path.join(out, "single_w1_r0.pt"))
 
 
-@pytest.mark.parametrize("exchange,world", [("allgather", 2), ("sparse", 2), ("dense", 2), ("sparse", 4)])
+@pytest.mark.parametrize("exchange,world", [("allgather", 2), ("sparse", 2), ("sparse_sync", 2), ("dense", 2), ("sparse", 4)])
 def test_sharded_engine_reproduces_single_rank(emulated_library, single_rank, tmp_path, exchange, world):
     import torch.multiprocessing as mp
 

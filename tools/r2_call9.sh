@@ -1,4 +1,4 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r9_multi_tests.log 2>&1; tail -5 gpurun_out/r9_multi_tests.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r9_bench2.json 2> gpurun_out/r9_bench2.err; tail -5 gpurun_out/r9_bench2.err; cat gpurun_out/r9_bench2.json
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r9_bench1.json 2> gpurun_out/r9_bench1.err; tail -3 gpurun_out/r9_bench1.err; cat gpurun_out/r9_bench1.json
+
+timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r9_bench2.json 2> gpurun_out/r9_bench2.err; tail -5 gpurun_out/r9_bench2.err; cat gpurun_out/r9_bench2.json
+
