@@ -23,6 +23,7 @@ ISO_TENSOR, ISO_HASH_SOFT, ISO_HASH_HARD, ISO_NONE = 0, 1, 2, 3
 U_TENSOR, U_HASH = 0, 1
 DO_TRANSMISSION, DO_PROGRESSION, DO_ENCODE, DO_INIT, DO_LOOKAHEAD = 1, 2, 4, 8, 16
 MAX_BLOCKS = 64
+MAX_LAYERS = 8
 LAYOUT_BCSR, LAYOUT_STREAM = 0, 1
 STREAM_UNIT, STREAM_MAX_TILE_ROWS, STREAM_MAX_BLOCK_SIZE = 256, 2048, (1 << 21) - 1024
 
@@ -41,7 +42,7 @@ class SeirmModel(ctypes.Structure):
         ("exposed_to_infected_time", ctypes.c_int32), ("infected_to_recovered_time", ctypes.c_int32),
         ("infinity_time", ctypes.c_int32), ("i_bar", ctypes.c_float),
         ("sfs", ctypes.c_float * MAX_SFS), ("sfi", ctypes.c_float * MAX_SFI),
-        ("lam_gamma", ctypes.c_float * MAX_LAMGAMMA),
+        ("lam_gamma", ctypes.c_float * MAX_LAMGAMMA), ("n_layers", ctypes.c_int32), ("i_bar_layers", ctypes.c_float * MAX_LAYERS),
     ]
 
 
@@ -71,7 +72,7 @@ class SeirmLaunch(ctypes.Structure):
         ("unit_tile", ctypes.c_void_p), ("block_units", ctypes.c_void_p), ("tile_rec_base", ctypes.c_void_p),
         ("tile_count", ctypes.c_void_p), ("rec", ctypes.c_void_p),
         ("lam_deg_bits", ctypes.c_int32), ("xchg_slot", ctypes.c_int32),
-        ("reserve_sms", ctypes.c_int32), ("_pad2", ctypes.c_int32),
+        ("dne_e_dr", ctypes.c_void_p), ("reserve_sms", ctypes.c_int32), ("_pad2", ctypes.c_int32),
     ]
 
 

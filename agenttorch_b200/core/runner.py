@@ -306,15 +306,21 @@ class Runner(nn.Module):
             uniform = torch.stack([as_kernel_f32(tr.exposure_uniform(t) if callable(tr.exposure_uniform)
                                                  else tr.exposure_uniform[t]).reshape(-1) for t in range(num_steps)])
         before = ctx.engine.launch_count
-        ops.bind_state(ctx.handle, tensors["disease_stage"], tensors["next_stage_time"], tensors["infected_time"],
-                       tensors["age"])
         make_hook = plan.get("after_step")
         hook = make_hook(state) if make_hook is not None else None
         ctx.engine.after_step = hook
+        # SFSusceptibility / SFInfector given as differentiable tensors (learnable tables): their gradients come from the same
+        # saved buffers as dL/dR (SeirmEngine.table_gradients)
+        tables = []
+        for name in ("SFSusceptibility", "SFInfector"):
+            tv = get_by_path(state, path(iv.get(name, "environment/" + name)))
+            tables.append(tv if torch.is_tensor(tv) and tv.requires_grad else None)
+        want_grad = want_grad or (any(tv is not None for tv in tables) and torch.is_grad_enabled())
         try:
-            new_di, new_dd, _, _ = ops.seirm_episode(
-                ctx.handle, di.reshape(-1), dd.reshape(-1), r_steps, m_value, int(num_steps), tr.episode_seed(), "soft", 0.0,
-                None, uniform, want_grad, self._use_cuda_graph and uniform is None)
+            new_di, new_dd = ops.seirm_episode_fn(
+                ctx.handle, tensors["disease_stage"], tensors["next_stage_time"], tensors["infected_time"], tensors["age"],
+                di.reshape(-1), dd.reshape(-1), r_steps, m_value, int(num_steps), tr.episode_seed(), "soft", 0.0,
+                None, uniform, want_grad, self._use_cuda_graph and uniform is None, sfs=tables[0], sfi=tables[1])
         finally:
             ctx.engine.after_step = None
         set_by_path(state, path(iv["daily_infected"]), new_di.view_as(di))

@@ -126,6 +126,8 @@ struct KModel {   // device copy of at_seirm_model (kernel parameter, by value)
     int n_sfs, n_sfi, n_lg, e2i, i2r, inf_time;
     float ibar;
     float sfs[AT_MAX_SFS], sfi[AT_MAX_SFI], lg[AT_MAX_LAMGAMMA];
+    int n_layers;                       // >= 1
+    float ibar_layers[AT_MAX_LAYERS];   // [0] == ibar for single-layer graphs
 };
 
 // per-warp shared memory: two col chunks, the hit mask and hit codes of the chunk being folded, two mbarriers
@@ -770,20 +772,20 @@ __device__ __noinline__ void stream_resolve(const StreamResolveCtx& c, const uin
 #pragma unroll
     for (int k = 0; k < ST_RK; ++k) {
         const int i = k * 32 + lane;
-        e[k] = 0u; tile[k] = -1;
+        e[k] = 0u; tile[k] = -1;                         // (layers < 128, so a valid unit_tile word is never negative)
         if (i < count) {
             const uint2 p = s_pend[i];
             e[k] = p.x;
-            tile[k] = __ldg(c.unit_tile + p.y);
+            tile[k] = __ldg(c.unit_tile + p.y);          // tile in the low 24 bits, network layer of the unit's edges above
         }
     }
 #pragma unroll
     for (int k = 0; k < ST_RK; ++k) {
         sw[k] = 0u; base[k] = 0;
         if (tile[k] >= 0) {
-            const int64_t row = ((int64_t)tile[k] << c.tile_shift) + (int64_t)((e[k] >> 5) & 0x7FFu);
+            const int64_t row = ((int64_t)(tile[k] & 0xFFFFFF) << c.tile_shift) + (int64_t)((e[k] >> 5) & 0x7FFu);
             sw[k] = (__ldg(c.sus + (row >> 5)) >> (row & 31)) & 1u;
-            base[k] = __ldg(c.tile_rec_base + tile[k]);
+            base[k] = __ldg(c.tile_rec_base + (tile[k] & 0xFFFFFF));
         }
     }
 #pragma unroll
@@ -794,8 +796,8 @@ __device__ __noinline__ void stream_resolve(const StreamResolveCtx& c, const uin
 #pragma unroll
     for (int k = 0; k < ST_RK; ++k) {
         if (cd[k] != 0u) {
-            const uint32_t slot = atomicAdd(c.tile_count + tile[k], 1u);
-            c.rec[base[k] + slot] = (((e[k] >> 5) & 0x7FFu) << 8) | cd[k];
+            const uint32_t slot = atomicAdd(c.tile_count + (tile[k] & 0xFFFFFF), 1u);
+            c.rec[base[k] + slot] = ((uint32_t)(tile[k] >> 24) << 24) | (((e[k] >> 5) & 0x7FFu) << 8) | cd[k];
         }
     }
     __syncwarp();
@@ -805,19 +807,20 @@ __device__ __noinline__ void stream_resolve(const StreamResolveCtx& c, const uin
 // launch that follows it in the stream): term[age][code] = f64(f32(((R*S)*A)*G)) / I_bar, the reference's message
 // (transition.py:78-83), rounded once to the 2^-shift grid, shift chosen so that in-degree * largest term < 2^62.
 // R == 0 (lambda == 0 everywhere): the terms of d lambda / dR instead, which is all the update then needs.
-__device__ void stream_build_term_table(const KModel& m, const at_seirm_launch& a, int NC, double* s_scratch /* n_sfs*NC */,
+__device__ void stream_build_term_table(const KModel& m, const at_seirm_launch& a, int NC, double* s_scratch /* n_layers*n_sfs*NC */,
                                         unsigned long long* s_tmax)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     const float R = a.r_value[a.r_index];
-    const double ibar = (double)m.ibar;
     char* ws = reinterpret_cast<char*>(a.workspace);
     long long* tab = reinterpret_cast<long long*>(ws + WS_FIXTAB);
     if (tid == 0) *s_tmax = 0ull;
     __syncthreads();
     double mymax = 0.0;
-    for (int i = tid; i < m.n_sfs * NC; i += nt) {
-        const int ag = i / NC, c = i % NC;
+    const int per_layer = m.n_sfs * NC, n_tab = m.n_layers * per_layer;          // table[layer][age][code]
+    for (int i = tid; i < n_tab; i += nt) {
+        const int layer = i / per_layer, ag = (i % per_layer) / NC, c = i % NC;
+        const double ibar = (double)m.ibar_layers[layer];
         float av = 0.f, gv = 0.f;
         if (c >= 1 && c <= 3 * m.n_lg) {
             const int sidx = (c - 1) / m.n_lg, idx = (c - 1) % m.n_lg;
@@ -841,7 +844,7 @@ __device__ void stream_build_term_table(const KModel& m, const at_seirm_launch& 
         shift = 62 - ex - a.lam_deg_bits;
         shift = shift > 1000 ? 1000 : (shift < -1000 ? -1000 : shift);
     }
-    for (int i = tid; i < m.n_sfs * NC; i += nt) {
+    for (int i = tid; i < n_tab; i += nt) {
         const double d = s_scratch[i];                          // written by this thread
         tab[i] = (fabs(d) < 1e300) ? __double2ll_rn(ldexp(d, shift)) : 0ll;
     }
@@ -1008,12 +1011,16 @@ __global__ void __launch_bounds__(TU_THREADS, 8)
 stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
 {
     AT_DYNAMIC_SMEM(unsigned char, smem_raw, 128);
-    // [s_fix i64 n_sfs*NC][s_A f32 256][s_G f32 256][s_lam i64 tile_rows][s_cand u16 tile_rows][s_age u8 tile_rows]
+    // [s_fix i64 n_layers*n_sfs*NC][s_A f32 256][s_G f32 256][s_lam i64 tile_rows][s_lamE i64 tile_rows, if dne_e_dr][s_cand u16 tile_rows]
+    // [s_age u8 tile_rows]
+    const int n_tab = m.n_layers * m.n_sfs * NC;
+    const bool want_e = GRAD && a.dne_e_dr != nullptr;          // split d ne / dR by the stage of the sources (for d / d SFInfector)
     long long* s_fix = reinterpret_cast<long long*>(smem_raw);
-    float* s_A = reinterpret_cast<float*>(s_fix + m.n_sfs * NC);
+    float* s_A = reinterpret_cast<float*>(s_fix + n_tab);
     float* s_G = s_A + 256;
     long long* s_lam = reinterpret_cast<long long*>(s_G + 256);
-    uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_lam + a.tile_rows);
+    long long* s_lamE = s_lam + a.tile_rows;                     // lambda from sources in stage E
+    uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_lam + (want_e ? 2 : 1) * a.tile_rows);
     uint8_t* s_age = reinterpret_cast<uint8_t*>(s_cand + a.tile_rows);
     __shared__ long long s_red[TU_THREADS / 32][3];
     __shared__ uint32_t s_w[3][TU_MAX_TASKS], s_orig[3][TU_MAX_TASKS], s_hot[TU_MAX_TASKS];   // sus / exp / inf words of the tile
@@ -1043,7 +1050,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     // fixed-point term table of this step, built by the gather launch (stream_build_term_table)
     {
         const long long* tab = reinterpret_cast<const long long*>(ws + WS_FIXTAB);
-        for (int i = tid; i < m.n_sfs * NC; i += TU_THREADS) s_fix[i] = tab[i];
+        for (int i = tid; i < n_tab; i += TU_THREADS) s_fix[i] = tab[i];
     }
     const int fx_shift = *reinterpret_cast<const int*>(ws + WS_FIXSHIFT);
     __syncthreads();
@@ -1083,9 +1090,15 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
         // ---- phase 0: outputs of rows that need nothing, bitmaps of the tile
         if (GRAD) {
             float4* d4 = reinterpret_cast<float4*>(a.dne_dr + row_base);
+            float4* e4 = want_e ? reinterpret_cast<float4*>(a.dne_e_dr + row_base) : nullptr;
             for (int i = tid; i * 4 < rows_here; i += TU_THREADS) {
-                if (i * 4 + 4 <= rows_here) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                else for (int r = i * 4; r < rows_here; ++r) a.dne_dr[row_base + r] = 0.f;
+                if (i * 4 + 4 <= rows_here) {
+                    d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (want_e) e4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else for (int r = i * 4; r < rows_here; ++r) {
+                    a.dne_dr[row_base + r] = 0.f;
+                    if (want_e) a.dne_e_dr[row_base + r] = 0.f;
+                }
             }
         }
         if (do_enc) {
@@ -1106,6 +1119,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
         if (nrec != 0u) {
             for (int i = tid; i < tile_rows; i += TU_THREADS) {
                 s_lam[i] = 0ll;
+                if (want_e) s_lamE[i] = 0ll;
                 int ag = (i < rows_here) ? load_age(a.age, row_base + i, age_f32) : 0;     // susceptibility class of the row
                 s_age[i] = (uint8_t)(ag < 0 ? 0 : (ag >= m.n_sfs ? m.n_sfs - 1 : ag));
             }
@@ -1115,10 +1129,12 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
             // ---- phase 1: records -> fixed-point lambda per row
             const uint32_t* recs = a.rec + a.tile_rec_base[tile];
             for (uint32_t i = tid; i < nrec; i += TU_THREADS) {
-                const uint32_t rec = recs[i];
-                const int r = (int)(rec >> 8);
-                const long long v = s_fix[(int)s_age[r] * NC + (int)(rec & 255u)];
+                const uint32_t rec = recs[i];                 // (layer << 24) | (row in tile << 8) | code
+                const int r = (int)((rec >> 8) & 0x7FFu), code = (int)(rec & 255u);
+                const long long v = s_fix[((int)(rec >> 24) * m.n_sfs + (int)s_age[r]) * NC + code];
                 if (v != 0ll) {
+                    // code = 1 + stage * n_lg + day: stage 1 = exposed (SFInfector[1])
+                    if (want_e && (code - 1) / m.n_lg == 1) atomicAdd(reinterpret_cast<unsigned long long*>(s_lamE) + r, (unsigned long long)v);
                     // ---- phase A, part 1: the row's first record makes it an exposure candidate (records exist for susceptible rows
                     //      only, and all terms of a step have the sign of R, so the sum was zero exactly before the first one)
                     const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(s_lam) + r, (unsigned long long)v);
@@ -1155,6 +1171,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
                     const float dne = omw * q32 * (float)lam1;
                     acc_dne += __double2ll_rn((double)dne * FX_SCALE);
                     a.dne_dr[row] = dne;
+                    if (want_e) a.dne_e_dr[row] = (float)((double)dne * ((double)s_lamE[r] / (double)s_lam[r]));
                 }
                 if (ne != 0.0f) {
                     a.stage[row] = ne;                         // 0 + ne
@@ -1661,6 +1678,11 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
     km.n_sfs = model->n_sfs; km.n_sfi = model->n_sfi; km.n_lg = model->n_lam_gamma;
     km.e2i = model->exposed_to_infected_time; km.i2r = model->infected_to_recovered_time; km.inf_time = model->infinity_time;
     km.ibar = model->i_bar;
+    km.n_layers = model->n_layers > 1 ? model->n_layers : 1;
+    if (km.n_layers > AT_MAX_LAYERS) return fail("%s", "n_layers out of range (<= 8)");
+    for (int l = 0; l < AT_MAX_LAYERS; ++l) km.ibar_layers[l] = (model->n_layers > 1 && l < model->n_layers) ? model->i_bar_layers[l] : model->i_bar;
+    if (km.n_layers > 1 && a.layout != AT_LAYOUT_STREAM && (a.flags & AT_DO_TRANSMISSION)) return fail("%s", "multi-layer contact networks need the stream layout");
+    if ((int64_t)km.n_layers * model->n_sfs * code_count(model->n_lam_gamma) > (int64_t)AT_MAX_SFS * 256) return fail("%s", "layers x susceptibility classes x codes exceed the term table (4096 entries)");
     memcpy(km.sfs, model->sfs, sizeof(km.sfs)); memcpy(km.sfi, model->sfi, sizeof(km.sfi)); memcpy(km.lg, model->lam_gamma, sizeof(km.lg));
 
     const int NC = code_count(model->n_lam_gamma);
@@ -1697,7 +1719,7 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         if (a.block_size > at_seirm_stream_max_block_size(model->n_sfs, model->n_lam_gamma, pw))
             return fail("%s", "stream layout: block bitmap exceeds the shared-memory capacity (at_seirm_stream_max_block_size)");
         const int words = a.block_size / 32;
-        const size_t smem = (size_t)(words + 4) * 4 + 16 + (size_t)pw * ST_PEND * 8 + 16 + (size_t)model->n_sfs * NC * 8;
+        const size_t smem = (size_t)(words + 4) * 4 + 16 + (size_t)pw * ST_PEND * 8 + 16 + (size_t)km.n_layers * model->n_sfs * NC * 8;
         int tile_shift = 0;
         while ((1 << tile_shift) < a.tile_rows) ++tile_shift;
         // the more warps, the fewer registers each has for units in flight: 32 warps x 3 units, 24 x 5, <= 16 x 8 (KB per SM: 96 / 120 / 128)
@@ -1719,7 +1741,7 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         int tgrid = a.grid > 0 ? a.grid : g_sm_count * (a.reserve_sms > 0 ? 7 : 8);
         const int64_t n_tiles = a.n_rows_pad / a.tile_rows;
         if (tgrid > n_tiles) tgrid = (int)n_tiles;
-        const size_t usmem = (size_t)model->n_sfs * NC * 8 + 2 * 256 * 4 + (size_t)a.tile_rows * 11;
+        const size_t usmem = (size_t)km.n_layers * model->n_sfs * NC * 8 + 2 * 256 * 4 + (size_t)a.tile_rows * (a.dne_e_dr ? 19 : 11);
         const bool tf32 = a.timer_dtype == AT_TIMER_F32, grad = a.dne_dr != nullptr;
         if (tf32 && grad) AT_LAUNCH_SMEM((stream_update_kernel<true, true>), tgrid, TU_THREADS, usmem, s, km, al, NC);
         else if (tf32) AT_LAUNCH_SMEM((stream_update_kernel<true, false>), tgrid, TU_THREADS, usmem, s, km, al, NC);

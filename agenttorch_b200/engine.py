@@ -42,8 +42,11 @@ class SeirmSpec:
         if len(self.sfs) > nat.MAX_SFS or len(self.sfi) > nat.MAX_SFI:
             raise ValueError("SFSusceptibility / SFInfector table too long")
 
-    def to_struct(self, i_bar):
+    def to_struct(self, i_bar, i_bar_layers=()):
         m = nat.SeirmModel()
+        m.n_layers = len(i_bar_layers) if len(i_bar_layers) > 1 else 0
+        for i, v in enumerate(i_bar_layers):
+            m.i_bar_layers[i] = float(v)
         m.n_sfs, m.n_sfi, m.n_lam_gamma = len(self.sfs), len(self.sfi), len(self.lam_gamma)
         m.exposed_to_infected_time = int(self.exposed_to_infected_time)
         m.infected_to_recovered_time = int(self.infected_to_recovered_time)
@@ -163,7 +166,7 @@ class SeirmEngine:
         self.lib = nat.lib()
         self.spec = spec
         self.device = graph.device
-        self.model = spec.to_struct(graph.i_bar)
+        self.model = spec.to_struct(graph.i_bar, getattr(graph, "i_bar_layers", ()))
         if float(spec.sfi[0]) != 0.0:
             raise NotImplementedError("SFInfector[0] must be 0 (agents with a fractional stage are not tracked as infectious)")
         self.pg = process_group
@@ -192,7 +195,7 @@ class SeirmEngine:
         if layout not in ("auto", "bcsr", "stream"):
             raise ValueError("layout must be 'auto', 'bcsr' or 'stream'")
         if layout == "auto" and not isinstance(graph, BlockedGraph):
-            bcsr_only = hashed or hash_words or edges_per_chunk or graph.edge_weight is not None
+            bcsr_only = (hashed or hash_words or edges_per_chunk or graph.edge_weight is not None) and graph.edge_layer is None
             layout = "bcsr" if bcsr_only else "stream"
         if isinstance(graph, BlockedGraph):
             self.graph = graph
@@ -328,7 +331,7 @@ class SeirmEngine:
     def launch(self, state: SeirmState, *, flags, t, t_encode=None, code_in=None, code_out=None,
                noise: Optional[NoiseSpec] = None, isolation=None, uniform=None, r_value=None, r_index=0,
                m_value=None, dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None,
-               seed_ptr=None, check_range=True, xchg_slot=0, reserve_sms=0):
+               seed_ptr=None, check_range=True, xchg_slot=0, reserve_sms=0, dne_e_dr=None):
         g = self.graph
         a = nat.SeirmLaunch()
         a.abi_version = nat.ABI_VERSION
@@ -378,6 +381,7 @@ class SeirmEngine:
         a.daily_infected = _ptr(state.daily_infected, torch.float32, "daily_infected")
         a.daily_deaths = _ptr(state.daily_deaths, torch.float32, "daily_deaths")
         a.dne_dr = _ptr(dne_dr, torch.float32, "dne_dr")
+        a.dne_e_dr = _ptr(dne_e_dr, torch.float32, "dne_e_dr")
         a.sum_dne_dr = _ptr(sum_dne_dr, torch.float32, "sum_dne_dr")
         a.death_count = _ptr(death_count, torch.float32, "death_count")
         a.recovered_step = _ptr(recovered_step, torch.uint8, "recovered_step")
@@ -476,17 +480,22 @@ class SeirmEngine:
         self.exchange(self.cur)
 
     def step(self, state, t, noise, r_value, r_index, m_value, *, isolation=None, uniform=None, flags=None,
-             dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None, seed_ptr=None, check_range=True):
+             dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None, seed_ptr=None, check_range=True, dne_e_dr=None):
         """One fused step: transmission + progression + encode of step t+1; flips the live buffer."""
         flags = (nat.DO_TRANSMISSION | nat.DO_PROGRESSION | nat.DO_ENCODE) if flags is None else flags
         self.launch(state, flags=flags, t=t, t_encode=t + 1, noise=noise, isolation=isolation, uniform=uniform,
                     r_value=r_value, r_index=r_index, m_value=m_value, dne_dr=dne_dr, sum_dne_dr=sum_dne_dr,
-                    death_count=death_count, recovered_step=recovered_step, seed_ptr=seed_ptr, check_range=check_range)
+                    death_count=death_count, recovered_step=recovered_step, seed_ptr=seed_ptr, check_range=check_range,
+                    dne_e_dr=dne_e_dr)
         if flags & nat.DO_ENCODE:
             self.cur = 1 - self.cur
             self.exchange(self.cur)
 
     # ------------------------------------------------------------------------------ episode
+    # gradients with respect to the SFSusceptibility / SFInfector tables (config.yaml declares them learnable-capable): the forward
+    # additionally saves, per step and agent, the part of d ne / dR that came from sources in stage E
+    want_table_grad = False
+
     def saved_buffers(self, num_steps, want_grad):
         key = (num_steps, want_grad)
         if key not in self._saved:
@@ -495,6 +504,7 @@ class SeirmEngine:
             self._saved[key] = {
                 "ld": ld,
                 "dne_dr": torch.zeros((num_steps, ld), dtype=torch.float32, device=dev) if want_grad else None,
+                "dne_e": None,
                 "recovered_step": torch.full((n,), 255, dtype=torch.uint8, device=dev),
                 "sum_dne_dr": torch.zeros(num_steps, dtype=torch.float32, device=dev),
                 "death_count": torch.zeros(num_steps, dtype=torch.float32, device=dev),
@@ -537,7 +547,8 @@ class SeirmEngine:
                 self.step(state, t, noise, sv["r_steps"], k, sv["m_value"], isolation=iso, uniform=uni,
                           dne_dr=sv["dne_dr"][k] if want_grad else None, sum_dne_dr=sv["sum_dne_dr"],
                           death_count=sv["death_count"], recovered_step=sv["recovered_step"], seed_ptr=self.seed_buf,
-                          check_range=k + 1 < num_steps)
+                          check_range=k + 1 < num_steps,
+                          dne_e_dr=sv["dne_e"][k] if (want_grad and self.want_table_grad and sv["dne_e"] is not None) else None)
                 plan.append((*self._recording[-1], True))
                 if self.after_step is not None:
                     self.after_step(t)
@@ -590,7 +601,8 @@ class SeirmEngine:
                         uniform=uni, r_value=sv["r_steps"], r_index=k, m_value=sv["m_value"],
                         dne_dr=sv["dne_dr"][k] if want_grad else None, sum_dne_dr=sv["sum_dne_dr"], death_count=sv["death_count"],
                         recovered_step=sv["recovered_step"], seed_ptr=self.seed_buf, check_range=needed, xchg_slot=(k + 2) % 3,
-                        reserve_sms=1)
+                        reserve_sms=1,
+                        dne_e_dr=sv["dne_e"][k] if (want_grad and self.want_table_grad and sv["dne_e"] is not None) else None)
             if needed:
                 exchange_on_side(k + 2)
             if self.after_step is not None:
@@ -607,6 +619,10 @@ class SeirmEngine:
         With cuda_graph=True the launch sequence is captured once per (state buffers, shape) and
         replayed; the seed, R and M are read from device memory so the graph is reusable."""
         sv = self.saved_buffers(num_steps, want_grad)
+        if want_grad and self.want_table_grad and sv["dne_e"] is None:
+            if self.graph.layout != 1:
+                raise NotImplementedError("gradients with respect to SFInfector need the stream layout")
+            sv["dne_e"] = torch.zeros_like(sv["dne_dr"])
         sv["r_steps"].copy_(r_steps.detach().reshape(-1)[:num_steps])
         sv["m_value"].copy_(m_value.detach().reshape(-1)[:1])
         self.seed_buf.fill_(_as_i64(noise.seed))
@@ -661,6 +677,52 @@ class SeirmEngine:
             dist.all_reduce(packed, group=self.pg)
             grad_r, grad_m = packed[:num_steps].clone(), packed[num_steps:].clone()
         return grad_r, grad_m
+
+    def table_gradients(self, sv, num_steps, g_daily_infected, g_daily_deaths, m_value, r_steps, age):
+        """dL/dSFSusceptibility (n_sfs,) and dL/dSFInfector (n_sfi,) of an episode, from the buffers the forward saved — no per-edge
+        intermediate, like the R / M gradients.  lambda_i is linear in S[age_i] and, source by source, in A[stage_j]
+        (transition.py:63-64,78-83), so with c_i(t) = gI[t] + gD[recovery step of i] * M / 2 (the cotangent of ne_i(t), through the
+        float stage to the deaths):
+            dL/dS[a] = sum_t R_t / S[a] * sum_{i: age_i = a} c_i(t) * dne_dr[t, i]
+            dL/dA[1] = sum_t R_t / A[1] * sum_i c_i(t) * dne_e[t, i]          (sources in stage E)
+            dL/dA[2] = sum_t R_t / A[2] * sum_i c_i(t) * (dne_dr - dne_e)[t, i]
+        dL/dA[0] (fractional-stage sources under soft isolation, whose A[0] = 0 contributes nothing to the forward) is not
+        tracked and returned as 0, like dL/dA[3:].  A composition of torch reductions over the saved (T, N) buffers: an opt-in
+        calibration path (both tables are `learnable: false` in the reference's config), not the hot path."""
+        T, n, dev = int(num_steps), self.graph.n_rows, self.device
+        if sv.get("dne_e") is None or sv.get("dne_dr") is None:
+            raise RuntimeError("run the episode with want_grad=True and engine.want_table_grad = True first")
+        gi = g_daily_infected.detach().reshape(-1)[:T].double()
+        gd = g_daily_deaths.detach().reshape(-1)[:T].double()
+        half_m = float(m_value.detach().reshape(-1)[0]) * 0.5
+        rstep = sv["recovered_step"].long()
+        c_rec = torch.where(rstep < T, gd[rstep.clamp(max=T - 1)] * half_m, torch.zeros((), dtype=torch.float64, device=dev))
+        r = r_steps.detach().reshape(-1)[:T].double()
+        age_l = age.reshape(-1).long().clamp(0, len(self.spec.sfs) - 1)
+        grad_sfs = torch.zeros(len(self.spec.sfs), dtype=torch.float64, device=dev)
+        ge = torch.zeros((), dtype=torch.float64, device=dev)
+        gi2 = torch.zeros((), dtype=torch.float64, device=dev)
+        for t in range(T):                                             # one (N,) pass per step keeps the temporaries small
+            w = (gi[t] + c_rec) * r[t]
+            d = sv["dne_dr"][t, :n].double() * w
+            e = sv["dne_e"][t, :n].double() * w
+            grad_sfs.index_add_(0, age_l, d)
+            ge += e.sum()
+            gi2 += (d - e).sum()
+        sfs = torch.tensor(self.spec.sfs, dtype=torch.float64, device=dev)
+        grad_sfs = torch.where(sfs != 0, grad_sfs / sfs, torch.zeros_like(grad_sfs))
+        grad_sfi = torch.zeros(len(self.spec.sfi), dtype=torch.float64, device=dev)
+        if len(self.spec.sfi) > 1 and self.spec.sfi[1] != 0:
+            grad_sfi[1] = ge / float(self.spec.sfi[1])
+        if len(self.spec.sfi) > 2 and self.spec.sfi[2] != 0:
+            grad_sfi[2] = gi2 / float(self.spec.sfi[2])
+        if self.pg is not None:
+            import torch.distributed as dist
+
+            packed = torch.cat([grad_sfs, grad_sfi])
+            dist.all_reduce(packed, group=self.pg)
+            grad_sfs, grad_sfi = packed[: grad_sfs.numel()], packed[grad_sfs.numel():]
+        return grad_sfs.float(), grad_sfi.float()
 
     def check_errors(self):
         code = int(self.error_flag.item())

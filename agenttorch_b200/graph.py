@@ -32,6 +32,10 @@ class ContactGraph:
     edge_weight: Optional[torch.Tensor] = None   # (E + COL_PAD,) float32 or None when all == 1
     i_bar: float = 1.0
     i_bar_agent: int = -1            # agent whose mean_interactions is I_bar (dst of original edge #c)
+    # multi-layer contact networks (per-edge network type, transition.py:71-73): layer number of every CSR edge and the I_bar
+    # of every layer (mean_interactions[dst[type]] of the layer's type); None / () when every edge has the same type
+    edge_layer: Optional[torch.Tensor] = None    # (E + COL_PAD,) uint8
+    i_bar_layers: tuple = ()
 
     @property
     def device(self):
@@ -41,7 +45,8 @@ class ContactGraph:
         return ContactGraph(self.n_rows, self.n_sources, self.row_offset, self.row_ptr.to(device),
                             self.col_idx.to(device), self.num_edges,
                             None if self.edge_weight is None else self.edge_weight.to(device),
-                            self.i_bar, self.i_bar_agent)
+                            self.i_bar, self.i_bar_agent,
+                            None if self.edge_layer is None else self.edge_layer.to(device), tuple(self.i_bar_layers))
 
     def edge_index(self):
         """COO view in CSR order: (2,E) int64 [src; dst] with global destination ids."""
@@ -79,16 +84,29 @@ def build_contact_graph(edge_index, num_agents, edge_attr=None, mean_interaction
     weight = None
     i_bar, i_bar_agent = 1.0, -1
     etype_const = 1
+    layer, i_bar_layers = None, ()
     if edge_attr is not None:
         edge_attr = torch.as_tensor(edge_attr)
-        etype = edge_attr[0].to(torch.int64)
+        etype = edge_attr[0].to(device=device, dtype=torch.int64)
         if e:
             etype_const = int(etype[0])
             if not bool((etype == etype_const).all()):
-                raise NotImplementedError("per-edge edge_type (multi-layer networks) is not supported yet")
+                # multi-layer network: the reference gathers I_bar per edge, I_bar_e = mean_interactions[dst[type_e]]
+                # (transition.py:71-73: a gather of the per-edge vector at index type_e) — one value per distinct type
+                types, layer = torch.unique(etype, return_inverse=True)
+                if types.numel() > 8:
+                    raise NotImplementedError("more than 8 distinct edge types (network layers)")
+                if int(types.min()) < 0 or int(types.max()) >= e:
+                    raise IndexError("edge_type indexes past the edge list (the reference's gather would fail)")
+                if mean_interactions is None:
+                    raise ValueError("a multi-layer contact network needs mean_interactions")
+                mi = torch.as_tensor(mean_interactions).reshape(-1).to(device)
+                i_bar_layers = tuple(float(mi[int(dst[int(k)])]) for k in types)
         w = edge_attr[1].to(device=device, dtype=torch.float32)
         if e and not bool((w == 1.0).all()):
             weight = w
+    if weight is not None and layer is not None:
+        raise NotImplementedError("edge weights on a multi-layer contact network are not supported")
     if e and mean_interactions is not None:
         if not 0 <= etype_const < e:
             raise IndexError("edge_type indexes past the edge list (the reference's gather would fail)")
@@ -101,7 +119,8 @@ def build_contact_graph(edge_index, num_agents, edge_attr=None, mean_interaction
     row_ptr = torch.zeros(num_agents + 1, dtype=torch.int64, device=device)
     row_ptr[1:] = torch.cumsum(counts, 0)
     g = ContactGraph(num_agents, num_agents, 0, row_ptr.to(torch.int32), _pad_cols(col), e,
-                     None if weight is None else _pad_cols(weight[order]), i_bar, i_bar_agent)
+                     None if weight is None else _pad_cols(weight[order]), i_bar, i_bar_agent,
+                     None if layer is None else _pad_cols(layer[order].to(torch.uint8)), i_bar_layers)
     return g
 
 
@@ -111,6 +130,8 @@ GRAPH_FILE_VERSION = 1
 def save_contact_graph(graph, path):
     """Binary CSR on disk: what `build_contact_graph` produced (sorted rows, int32 columns, I_bar), so that a population's
     edge-list CSV (`mobility_networks/0.csv`, 2.5 GB of text for 168 M edges) is parsed and sorted once."""
+    if graph.edge_layer is not None:
+        raise NotImplementedError("multi-layer contact networks are not stored in the binary graph file")
     cpu = graph.to("cpu")
     torch.save({"version": GRAPH_FILE_VERSION, "n_rows": cpu.n_rows, "n_sources": cpu.n_sources, "row_offset": cpu.row_offset,
                 "row_ptr": cpu.row_ptr, "col_idx": cpu.col_idx[: cpu.num_edges].clone(), "num_edges": cpu.num_edges,
@@ -242,8 +263,9 @@ def shard_graph(graph, row_begin, row_end):
     e0, e1 = int(rp[row_begin]), int(rp[row_end])
     col = graph.col_idx[e0:e1].clone()
     w = None if graph.edge_weight is None else _pad_cols(graph.edge_weight[e0:e1].clone())
+    lay = None if graph.edge_layer is None else _pad_cols(graph.edge_layer[e0:e1].clone())
     return ContactGraph(row_end - row_begin, graph.n_sources, row_begin, (rp[row_begin: row_end + 1] - e0).to(torch.int32),
-                        _pad_cols(col), e1 - e0, w, graph.i_bar, graph.i_bar_agent)
+                        _pad_cols(col), e1 - e0, w, graph.i_bar, graph.i_bar_agent, lay, tuple(graph.i_bar_layers))
 
 
 # --------------------------------------------------------------------------------------- BCSR
@@ -280,6 +302,7 @@ class BlockedGraph:
     block_units: Optional[torch.Tensor] = None   # stream layout: (n_blocks+1,) int32 first unit of every source block
     tile_rec_base: Optional[torch.Tensor] = None # stream layout: (n_tiles,) int64 first hit-record slot of every tile
     lam_deg_bits: int = 0        # stream layout: bits of the largest in-degree (head room of the fixed-point sums)
+    i_bar_layers: tuple = ()     # stream layout: I_bar of every network layer (multi-layer contact networks), else ()
 
     @property
     def device(self):
@@ -300,7 +323,8 @@ class BlockedGraph:
                             None if self.edge_weight is None else self.edge_weight.to(device), self.i_bar, self.i_bar_agent,
                             self.layout, self.tile_rows,
                             None if self.block_units is None else self.block_units.to(device),
-                            None if self.tile_rec_base is None else self.tile_rec_base.to(device), self.lam_deg_bits)
+                            None if self.tile_rec_base is None else self.tile_rec_base.to(device), self.lam_deg_bits,
+                            tuple(self.i_bar_layers))
 
 
 def choose_block_size(n_sources, max_block_size):
@@ -331,6 +355,8 @@ def block_graph(graph: ContactGraph, block_size: int, n_blocks: Optional[int] = 
     """ContactGraph (plain dst-sorted CSR, global source ids) -> BlockedGraph, on the graph's device.
     hash_words > 0: single block, raw source ids in `col`, hashed shared-memory filter (see include/at_seirm.h)."""
     dev = graph.device
+    if graph.edge_layer is not None:
+        raise NotImplementedError("multi-layer contact networks need the stream layout")
     n_rows, e = graph.n_rows, graph.num_edges
     n_rows_pad = -(-max(n_rows, 1) // 256) * 256
     if block_size % 1024:
@@ -447,12 +473,18 @@ def block_graph_stream(graph: ContactGraph, block_size: int, tile_rows: int = ST
     del deg
     col = graph.col_idx[:e].long()
     blk = torch.div(col, block_size, rounding_mode="floor")
-    seg = blk * n_tiles + (rows >> shift)                 # run id = block * n_tiles + tile
+    n_layers = max(len(graph.i_bar_layers), 1)
+    if graph.edge_layer is not None:
+        blk_lay = blk * n_layers + graph.edge_layer[:e].long()       # runs per (block, layer, tile): a unit has ONE layer
+    else:
+        blk_lay = blk
+    seg = blk_lay * n_tiles + (rows >> shift)             # run id = (block * n_layers + layer) * n_tiles + tile
+    del blk_lay
     local = col - blk * block_size
     enc = ((local >> 5) << 16) | ((rows & (tile_rows - 1)) << 5) | (local & 31)
     bank = (local >> 5) & 31
     del col, blk, rows, local
-    n_seg = nb * n_tiles
+    n_seg = nb * n_layers * n_tiles
     GROUP = 32
     GPU_ = STREAM_UNIT // GROUP                           # groups per unit (8)
     if bank_aware and e > 0:
@@ -508,15 +540,20 @@ def block_graph_stream(graph: ContactGraph, block_size: int, tile_rows: int = ST
     enc = torch.where(enc >= 2**31, enc - 2**32, enc).to(torch.int32)     # the 32-bit pattern, as int32
     col_out[pos] = enc
     del pos, enc
-    tile_of_seg = (torch.arange(n_seg, device=dev) % n_tiles).to(torch.int32)
+    seg_ids = torch.arange(n_seg, device=dev)
+    # tile in the low 24 bits, network layer in the top 8
+    tile_of_seg = ((seg_ids % n_tiles) | ((torch.div(seg_ids, n_tiles, rounding_mode="floor") % n_layers) << 24)).to(torch.int32)
     unit_tile = torch.repeat_interleave(tile_of_seg, seg_units)
     if unit_tile.numel() == 0:
         unit_tile = torch.zeros(1, dtype=torch.int32, device=dev)
-    block_units = unit_base[torch.arange(nb + 1, device=dev) * n_tiles].to(torch.int32).contiguous()
+    if n_tiles >= 1 << 24:
+        raise ValueError("too many row tiles for the 24-bit tile field")
+    block_units = unit_base[torch.arange(nb + 1, device=dev) * (n_layers * n_tiles)].to(torch.int32).contiguous()
     row_start = torch.zeros(1, dtype=torch.int16, device=dev)            # unused in this layout
     g = BlockedGraph(n_rows, n_rows_pad, graph.n_sources, graph.row_offset, nb, block_size, tile_rows, row_start,
                      unit_tile.contiguous(), col_out, e, 512, 0, None, graph.i_bar, graph.i_bar_agent, 1, tile_rows)
     g.block_units = block_units
     g.tile_rec_base = tile_rec_base
     g.lam_deg_bits = max(int(max_deg).bit_length(), 1)
+    g.i_bar_layers = tuple(graph.i_bar_layers)
     return g

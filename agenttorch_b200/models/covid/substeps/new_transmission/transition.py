@@ -13,6 +13,8 @@ import re
 
 import torch
 
+import torch
+
 from agenttorch_b200 import ops
 from agenttorch_b200.core.helpers import get_by_path
 from agenttorch_b200.core.substep import SubstepTransitionMessagePassing
@@ -69,6 +71,11 @@ class NewTransmission(SubstepTransitionMessagePassing):
         def var(name):
             return get_by_path(state, re.split("/", iv[name]))
 
+        for name in ("SFSusceptibility", "SFInfector"):
+            tv = get_by_path(state, re.split("/", iv.get(name, "environment/" + name)))
+            if torch.is_tensor(tv) and tv.requires_grad and torch.is_grad_enabled():
+                raise NotImplementedError(f"gradients with respect to {name} are computed by the fused episode path (Runner.step with "
+                                          "cuda_params.fused_episode), not by the per-substep operators")
         stage = as_kernel_f32(var("disease_stage"))
         nst = as_kernel_f32(var("next_stage_time"))
         itime = as_kernel_f32(var("infected_time"))

@@ -3,7 +3,7 @@
 Three operators replace the reference's ATen op chains and their autograd graph:
   seirm_transmission  — NewTransmission.forward       (new_transmission/transition.py:131-252)
   seirm_progression   — SEIRMProgression.forward      (seirm_progression/transition.py:90-121)
-  seirm_episode       — T x (transmission + progression) fused, state advanced in place, with a fused
+  seirm_episode       — T x (transmission + progression) fused, state advanced in place (declared in the schema), with a fused
                         O(N) backward (at_seirm_episode_backward) instead of a T-step autograd tape.
 An engine (graph + buffers) is addressed by an integer handle because custom ops only take tensors
 and scalars.  Every op launches CUDA kernels from libat_seirm.so; there is no CPU implementation —
@@ -149,36 +149,31 @@ seirm_progression.register_autograd(_progression_backward, setup_context=_progre
 
 
 # ----------------------------------------------------------------------------------------- episode
-_BOUND = {}
-
-
-def bind_state(handle: int, stage: Tensor, next_stage_time: Tensor, infected_time: Tensor, age: Tensor):
-    """Attach the agent-state tensors the episode operator advances IN PLACE.  They are engine-side state
-    (like an optimizer's buffers), not operator arguments: torch.library only registers autograd formulas
-    for functional operators, and the state tensors are never differentiable inputs."""
-    _BOUND[handle] = (stage.view(-1), next_stage_time.view(-1), infected_time.view(-1), age.view(-1))
-
-
-@torch.library.custom_op("agenttorch_b200::seirm_episode", mutates_args=())
-def seirm_episode(handle: int, daily_infected: Tensor, daily_deaths: Tensor, r_steps: Tensor, m_value: Tensor,
+# The episode operator MUTATES the agent-state tensors it is given (stage, timers) and says so in its schema, so the dispatcher
+# (functionalisation, torch.compile) knows.  torch.library only registers autograd formulas for functional operators, so the
+# differentiable entry point is an autograd.Function around the mutating operator (`seirm_episode_fn` below): its forward
+# calls the operator, its backward the fused backward kernel — the state tensors are never differentiable inputs.
+@torch.library.custom_op("agenttorch_b200::seirm_episode", mutates_args=("stage", "next_stage_time", "infected_time"))
+def seirm_episode(handle: int, stage: Tensor, next_stage_time: Tensor, infected_time: Tensor, age: Tensor,
+                  daily_infected: Tensor, daily_deaths: Tensor, r_steps: Tensor, m_value: Tensor,
                   num_steps: int, seed: int, iso_mode: str, p_isolate: float, isolation: Optional[Tensor],
-                  uniform: Optional[Tensor], want_grad: bool, cuda_graph: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """Advance the bound agent state through `num_steps` steps.  Returns the new (daily_infected,
-    daily_deaths) and the (T,) reductions saved for backward (sum_dne_dr, death_count); the (T,N) dne_dr and
-    recovered_step buffers stay inside the engine until the next episode."""
+                  uniform: Optional[Tensor], want_grad: bool, cuda_graph: bool, want_table_grad: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Advance the agent state IN PLACE through `num_steps` steps.  Returns the new (daily_infected, daily_deaths) and the (T,)
+    reductions saved for backward (sum_dne_dr, death_count); the (T,N) dne_dr and recovered_step buffers stay inside the engine
+    until the next episode."""
     eng = get_engine(handle)
-    stage, nst, itime, age = _BOUND[handle]
     di = daily_infected.detach().clone()
     dd = daily_deaths.detach().clone()
-    st = SeirmState(stage, nst, itime, age, di.view(-1), dd.view(-1))
+    st = SeirmState(stage.view(-1), next_stage_time.view(-1), infected_time.view(-1), age.view(-1), di.view(-1), dd.view(-1))
     noise = _noise(seed, iso_mode, p_isolate, isolation, uniform)
+    eng.want_table_grad = bool(want_table_grad)
     sv = eng.run_episode(st, r_steps, m_value, num_steps, noise, want_grad=want_grad, cuda_graph=cuda_graph)
     return di, dd, sv["sum_dne_dr"].clone(), sv["death_count"].clone()
 
 
 @seirm_episode.register_fake
-def _(handle, daily_infected, daily_deaths, r_steps, m_value, num_steps, seed, iso_mode, p_isolate, isolation,
-      uniform, want_grad, cuda_graph):
+def _(handle, stage, next_stage_time, infected_time, age, daily_infected, daily_deaths, r_steps, m_value, num_steps, seed, iso_mode,
+      p_isolate, isolation, uniform, want_grad, cuda_graph, want_table_grad):
     return (torch.empty_like(daily_infected), torch.empty_like(daily_deaths),
             daily_infected.new_empty(num_steps), daily_infected.new_empty(num_steps))
 
@@ -196,28 +191,53 @@ def _(handle, num_steps, g_daily_infected, g_daily_deaths, m_value):
     return g_daily_infected.new_empty(num_steps), g_daily_infected.new_empty(1)
 
 
-def _episode_setup(ctx, inputs, output):
-    ctx.handle, ctx.num_steps = inputs[0], inputs[5]
-    ctx.want_grad = inputs[11]
-    ctx.r_shape, ctx.m_shape = inputs[3].shape, inputs[4].shape
-    ctx.mark_non_differentiable(output[2], output[3])
-    ctx.save_for_backward(inputs[4])
+class _SeirmEpisodeFn(torch.autograd.Function):
+    """Differentiable episode: d(daily_infected, daily_deaths) / d(r_steps, M) by the fused backward kernel and, when the
+    SFSusceptibility / SFInfector tables are given as differentiable tensors, d / d(tables) from the same saved buffers
+    (SeirmEngine.table_gradients)."""
+
+    @staticmethod
+    def forward(ctx, handle, stage, next_stage_time, infected_time, age, daily_infected, daily_deaths, r_steps, m_value, sfs, sfi,
+                num_steps, seed, iso_mode, p_isolate, isolation, uniform, want_grad, cuda_graph):
+        table_grad = bool(want_grad and ((sfs is not None and sfs.requires_grad) or (sfi is not None and sfi.requires_grad)))
+        di, dd, _, _ = seirm_episode(handle, stage, next_stage_time, infected_time, age, daily_infected, daily_deaths,
+                                     r_steps.detach(), m_value.detach(), num_steps, seed, iso_mode, p_isolate, isolation, uniform,
+                                     want_grad, cuda_graph, table_grad)
+        ctx.handle, ctx.num_steps, ctx.want_grad, ctx.table_grad = handle, num_steps, want_grad, table_grad
+        ctx.r_shape, ctx.m_shape = r_steps.shape, m_value.shape
+        ctx.sfs_shape = None if sfs is None else sfs.shape
+        ctx.sfi_shape = None if sfi is None else sfi.shape
+        ctx.save_for_backward(m_value.detach(), r_steps.detach(), age)
+        return di, dd
+
+    @staticmethod
+    def backward(ctx, g_di, g_dd):
+        m_value, r_steps, age = ctx.saved_tensors
+        g_r = g_m = g_sfs = g_sfi = None
+        if ctx.want_grad and (g_di is not None or g_dd is not None):
+            T = ctx.num_steps
+            zeros = torch.zeros(T, dtype=torch.float32, device=m_value.device)
+            gi = zeros if g_di is None else g_di.reshape(-1)[:T]
+            gd = zeros if g_dd is None else g_dd.reshape(-1)[:T]
+            gr, gm = seirm_episode_backward(ctx.handle, T, gi, gd, m_value)
+            g_r = torch.zeros(ctx.r_shape, dtype=gr.dtype, device=gr.device).reshape(-1)
+            g_r[:T] = gr
+            g_r = g_r.reshape(ctx.r_shape)
+            g_m = gm.expand(m_value.numel()).reshape(ctx.m_shape).clone()
+            if ctx.table_grad:
+                eng = get_engine(ctx.handle)
+                gs, gf = eng.table_gradients(eng.saved_buffers(T, True), T, gi, gd, m_value, r_steps, age)
+                if ctx.sfs_shape is not None:
+                    g_sfs = gs.reshape(ctx.sfs_shape)
+                if ctx.sfi_shape is not None:
+                    g_sfi = gf.reshape(ctx.sfi_shape)
+        return (None, None, None, None, None, g_di, g_dd, g_r, g_m, g_sfs, g_sfi, None, None, None, None, None, None, None, None)
 
 
-def _episode_backward(ctx, g_di, g_dd, g_sum, g_cnt):
-    (m_value,) = ctx.saved_tensors
-    g_r = g_m = None
-    if ctx.want_grad and (g_di is not None or g_dd is not None):
-        T = ctx.num_steps
-        zeros = torch.zeros(T, dtype=torch.float32, device=m_value.device)
-        gi = zeros if g_di is None else g_di.reshape(-1)[:T]
-        gd = zeros if g_dd is None else g_dd.reshape(-1)[:T]
-        gr, gm = seirm_episode_backward(ctx.handle, T, gi, gd, m_value)
-        g_r = torch.zeros(ctx.r_shape, dtype=gr.dtype, device=gr.device).reshape(-1)
-        g_r[:T] = gr
-        g_r = g_r.reshape(ctx.r_shape)
-        g_m = gm.expand(m_value.numel()).reshape(ctx.m_shape).clone()
-    return (None, g_di, g_dd, g_r, g_m, None, None, None, None, None, None, None, None)
-
-
-seirm_episode.register_autograd(_episode_backward, setup_context=_episode_setup)
+def seirm_episode_fn(handle, stage, next_stage_time, infected_time, age, daily_infected, daily_deaths, r_steps, m_value,
+                     num_steps, seed, iso_mode="soft", p_isolate=0.0, isolation=None, uniform=None, want_grad=False, cuda_graph=False,
+                     sfs=None, sfi=None):
+    """The differentiable fused episode (see _SeirmEpisodeFn).  Returns (daily_infected, daily_deaths)."""
+    return _SeirmEpisodeFn.apply(handle, stage, next_stage_time, infected_time, age, daily_infected, daily_deaths, r_steps, m_value,
+                                 sfs, sfi, int(num_steps), int(seed), iso_mode, float(p_isolate), isolation, uniform, bool(want_grad),
+                                 bool(cuda_graph))

@@ -32,6 +32,7 @@ extern "C" {
 #define AT_MAX_SFI 8         /* SFInfector entries (config.yaml has 5)                           */
 #define AT_MAX_LAMGAMMA 84   /* lam_gamma_integrals entries; 1 + 3*K infectiousness codes fit a byte */
 #define AT_MAX_BLOCKS 64     /* column blocks of the contact graph                               */
+#define AT_MAX_LAYERS 8      /* network layers (distinct per-edge network types) of a multi-layer contact graph */
 
 /* dtype tags for the timer / age arrays */
 #define AT_TIMER_F32 0       /* reference layout: float32 holding integers (Q3)                  */
@@ -75,10 +76,16 @@ typedef struct at_seirm_model {
     int32_t exposed_to_infected_time;   /* EXPOSED_TO_INFECTED_TIME, transition.py:25-27      */
     int32_t infected_to_recovered_time; /* INFECTED_TO_RECOVERED_TIME, progression :31-33      */
     int32_t infinity_time;              /* num_steps_per_episode + 20, progression :28-30      */
-    float i_bar;                        /* mean_interactions[dst[edge_type]] — one scalar (Q1) */
+    float i_bar;                        /* mean_interactions[dst[edge_type]] — one scalar when every edge has the same
+                                           network type (Q1; network_from_file writes type 1 everywhere)            */
     float sfs[AT_MAX_SFS];
     float sfi[AT_MAX_SFI];
     float lam_gamma[AT_MAX_LAMGAMMA];
+    /* multi-layer contact networks (transition.py:71-73: I_bar is gathered PER EDGE by the edge's network type k,
+       I_bar_e = mean_interactions[dst[k]]): one I_bar per distinct type; n_layers <= 1 means "i_bar for every edge".
+       Layers are carried by the stream layout only (unit_tile holds the layer of each unit in its top 8 bits). */
+    int32_t n_layers;
+    float i_bar_layers[AT_MAX_LAYERS];
 } at_seirm_model;
 
 /*
@@ -102,9 +109,10 @@ typedef struct at_seirm_model {
  *   source lies in it form ONE flat stream, tile after tile, each (block, tile) run padded to whole UNITS of
  *   AT_STREAM_UNIT entries with entries that can never hit.  A 32-bit entry describes itself:
  *     col[] = (bitmap word of the block-local source << 16) | (row_in_tile << 5) | (bit of the source in its word),
- *   unit_tile[u] = tile of unit u, block_units[b] = first unit of block b (block_units[n_blocks] = all units).
+ *   unit_tile[u] = tile of unit u in its low 24 bits and the network layer of its edges in the top 8 (runs are
+ *   per (block, layer, tile)), block_units[b] = first unit of block b (block_units[n_blocks] = all units).
  *   The gather kernel streams the units with 128-bit loads against the block's EXACT hot bitmap in shared memory and
- *   appends, for every hit on a susceptible row, the record (row_in_tile << 8) | source code to the row tile's record
+ *   appends, for every hit on a susceptible row, the record (layer << 24) | (row_in_tile << 8) | source code to the row tile's record
  *   list (rec / tile_rec_base / tile_count).  The update kernel sums a tile's records into one 64-bit FIXED-POINT
  *   lambda per row — an integer sum, hence independent of the order in which the hits arrived (bitwise reproducible
  *   without any floating-point atomic) — and turns it back into float64.  Edge weights are not supported
@@ -186,10 +194,12 @@ typedef struct at_seirm_launch {
     const int32_t* block_units; /* [n_blocks + 1] first unit of every source block */
     const int64_t* tile_rec_base; /* [tiles] first record slot of every tile (slots = edges of the tile's rows) */
     uint32_t* tile_count;       /* [tiles] records of the tile this step, all zero between launches */
-    uint32_t* rec;              /* [edges] hit records (row_in_tile << 8) | source code, grouped by tile */
+    uint32_t* rec;              /* [edges] hit records (layer << 24) | (row_in_tile << 8) | source code, grouped by tile */
     int32_t lam_deg_bits;       /* ceil(log2(largest in-degree + 1)): head room of the fixed-point sums */
     int32_t xchg_slot;          /* 0..2: which "my slice holds an infectious agent" word of the workspace this launch sets
                                    (one per code buffer in flight; at_seirm_exchange_sparse reads and clears it) */
+    float* dne_e_dr;            /* n_rows or NULL (stream layout): the part of dne_dr that comes from sources in stage E
+                                   (SFInfector[1]); with dne_dr it gives d ne / d SFInfector[1], [2] — saved for backward */
     int32_t reserve_sms;        /* stream layout, != 0: the step kernels leave 1/8 of every SM's registers free (lean gather entry
                                    point, 7 instead of 8 update CTAs per SM), so that a halo exchange issued on another stream runs
                                    beside them instead of waiting for them (they otherwise take every register of every SM) */

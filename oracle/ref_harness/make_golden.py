@@ -42,12 +42,12 @@ def synthetic_population(n, avg_deg, seed, frac_e=0.02, frac_i=0.01):
     return age.astype(np.int64), stage0, edges.astype(np.int64)
 
 
-def save_case(name, age, stage0, edges, seed, mode, r2=None, m=None, store_inputs=True):
+def save_case(name, age, stage0, edges, seed, mode, r2=None, m=None, store_inputs=True, edge_type=None, table_grads=False):
     n = len(age)
     U, W = make_noise(seed, mode, n)
     gI = np.linspace(0.5, 1.5, T).astype(np.float32)
     gD = np.linspace(2.0, 1.0, T).astype(np.float32)
-    out = run_reference(age, stage0, edges, U, W, num_steps=T, r2=r2, m=m, gI=gI, gD=gD)
+    out = run_reference(age, stage0, edges, U, W, num_steps=T, r2=r2, m=m, gI=gI, gD=gD, edge_type=edge_type, table_grads=table_grads)
     payload = dict(
         seed=np.int64(seed), mode=np.array(mode), p_isolate=np.float32(0.3), num_steps=np.int64(T),
         gI=gI, gD=gD,
@@ -67,12 +67,36 @@ def save_case(name, age, stage0, edges, seed, mode, r2=None, m=None, store_input
     assert np.array_equal(payload["ref_stage_history"].astype(np.float64), out["stage_history"])
     assert np.array_equal(payload["ref_next_stage_time"].astype(np.float32), out["next_stage_time"])
     assert np.array_equal(payload["ref_infected_time"].astype(np.float32), out["infected_time"])
+    if edge_type is not None:
+        payload["edge_type"] = np.asarray(edge_type, dtype=np.int32)
+    if table_grads:
+        payload["ref_grad_SFS"] = out["grad_SFS"].astype(np.float32)
+        payload["ref_grad_SFI"] = out["grad_SFI"].astype(np.float32)
     if store_inputs:
         payload.update(age=age.astype(np.uint8), stage0=stage0.astype(np.uint8), edges=edges.astype(np.int32))
     path = os.path.join(GOLDEN, name + ".npz")
     np.savez_compressed(path, **payload)
     print(name, "N=%d E=%d" % (n, len(edges)), "%.0f KB" % (os.path.getsize(path) / 1024),
           "daily_infected[:6]=", out["daily_infected"][:6], "grad_R2=", out["grad_R2"].reshape(-1), "grad_M=", out["grad_M"])
+
+
+def layered_edge_types(age, edges, seed):
+    """Per-edge network types for a three-layer contact network: the reference gathers I_bar = mean_interactions[dst[type]]
+    (transition.py:71-73), so the three types are numbers of edges whose destinations have 2, 3 and 4 mean interactions."""
+    mi = np.where(age < 1, 2.0, np.where(age > 4, 4.0, 3.0))
+    dst = edges[:, 1]
+    ks = np.array([int(np.where(mi[dst] == v)[0][0]) for v in (2.0, 3.0, 4.0)])
+    return ks[np.random.default_rng(seed).integers(0, 3, len(edges))]
+
+
+def main_round2():
+    """Round-2 fixtures: multi-layer contact networks and the gradients w.r.t. SFSusceptibility / SFInfector."""
+    a, s, e = synthetic_population(3000, 8.0, seed=4242)
+    save_case("synth3k_layers_hard", a, s, e, seed=77, mode="hard", edge_type=layered_edge_types(a, e, 5), table_grads=True)
+    save_case("synth3k_tables_soft", a, s, e, seed=78, mode="soft", table_grads=True,
+              r2=np.array([[1.2], [0.4], [0.8]], dtype=np.float32), m=np.array([0.25], dtype=np.float32), store_inputs=False)
+    a, s, e = synthetic_population(400, 5.0, seed=9, frac_e=0.05, frac_i=0.05)
+    save_case("layers400_none", a, s, e, seed=79, mode="none", edge_type=layered_edge_types(a, e, 6), table_grads=True)
 
 
 def main():
@@ -98,4 +122,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        main_round2()
+    else:
+        main()

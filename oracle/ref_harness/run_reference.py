@@ -92,7 +92,7 @@ class _InjectedBernoulli(torch.autograd.Function):
 
 
 def run_reference(age, stage0, edges, U, W, num_steps=21, r2=None, m=None, gI=None, gD=None,
-                  num_threads=None, want_grads=True, timing=None):
+                  num_threads=None, want_grads=True, timing=None, edge_type=None, table_grads=False):
     """Run one episode of the reference on CPU with injected noise.
 
     U, W: (T, N) float32 arrays.  Returns a dict of numpy arrays: final stage /
@@ -133,6 +133,21 @@ def run_reference(age, stage0, edges, U, W, num_steps=21, r2=None, m=None, gI=No
     if m is not None:
         pg.calibrate_M = torch.tensor(np.asarray(m, dtype=np.float32), requires_grad=True)
 
+    if edge_type is not None:
+        # multi-layer contact network: the reference's loader only ever writes edge type 1 (utils.py:143), but its message
+        # function gathers I_bar per edge by that type (transition.py:71-73); give it a per-edge type vector
+        net = runner.state["network"]["agent_agent"]["infection_network"]
+        edge_index, edge_attr = net["adjacency_matrix"]
+        et = torch.from_numpy(np.asarray(edge_type)).to(edge_attr.dtype)
+        assert et.numel() == edge_attr.shape[1]
+        net["adjacency_matrix"] = (edge_index, torch.vstack((et, edge_attr[1])))
+    if table_grads:
+        # SFSusceptibility / SFInfector as differentiable leaves (config.yaml: learnable-capable environment tables)
+        env0 = runner.state["environment"]
+        env0["SFSusceptibility"] = env0["SFSusceptibility"].detach().clone().requires_grad_(True)
+        env0["SFInfector"] = env0["SFInfector"].detach().clone().requires_grad_(True)
+        leaf_sfs, leaf_sfi = env0["SFSusceptibility"], env0["SFInfector"]
+
     Ut = torch.from_numpy(np.ascontiguousarray(U)).to(torch.float64)
     Wt = torch.from_numpy(np.ascontiguousarray(W)).to(torch.float32)
     pol.behavior = lambda obs: Wt[int(runner.state["current_step"])].reshape(n, 1)
@@ -169,6 +184,9 @@ def run_reference(age, stage0, edges, U, W, num_steps=21, r2=None, m=None, gI=No
         out["loss"] = float(loss.detach())
         out["grad_R2"] = tr.calibrate_R2.grad.numpy().copy()
         out["grad_M"] = pg.calibrate_M.grad.numpy().copy()
+        if table_grads:
+            out["grad_SFS"] = leaf_sfs.grad.numpy().copy()
+            out["grad_SFI"] = leaf_sfi.grad.numpy().copy()
         if timing is not None:
             timing["backward_s"] = t3 - t2
     if timing is not None:

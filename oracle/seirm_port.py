@@ -226,8 +226,13 @@ class SeirmPort:
         return st, {"stage_history": hist, "lam": lams, "r2": r2, "m": m}
 
 
-def episode_with_grads(port, W, U, gI, gD, r2=None, m=None, num_steps=None):
-    """Forward + backward of L = sum(gI*daily_infected) + sum(gD*daily_deaths); numpy outputs."""
+def episode_with_grads(port, W, U, gI, gD, r2=None, m=None, num_steps=None, table_grads=False):
+    """Forward + backward of L = sum(gI*daily_infected) + sum(gD*daily_deaths); numpy outputs.
+    table_grads: SFSusceptibility / SFInfector as differentiable leaves too (config.yaml:206-235,268-300 declare them
+    learnable-capable; transition.py:63-64 indexes them inside the message)."""
+    if table_grads:
+        port.sfs = port.sfs.detach().clone().requires_grad_(True)
+        port.sfi = port.sfi.detach().clone().requires_grad_(True)
     r2d, md = port.default_params()
     r2 = r2d if r2 is None else torch.tensor(np.asarray(r2, dtype=np.float32), requires_grad=True)
     m = md if m is None else torch.tensor(np.asarray(m, dtype=np.float32), requires_grad=True)
@@ -236,7 +241,9 @@ def episode_with_grads(port, W, U, gI, gD, r2=None, m=None, num_steps=None):
     gD_t = torch.as_tensor(np.asarray(gD, dtype=np.float32))
     loss = (gI_t * st.daily_infected).sum() + (gD_t * st.daily_deaths).sum()
     loss.backward()
+    extra_out = {"grad_SFS": port.sfs.grad.numpy().copy(), "grad_SFI": port.sfi.grad.numpy().copy()} if table_grads else {}
     return {
+        **extra_out,
         "stage": st.stage.detach().numpy(),
         "next_stage_time": st.next_stage_time.numpy(),
         "infected_time": st.infected_time.numpy(),

@@ -9,7 +9,11 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 GOLDEN_CASES = ["astoria_hard", "astoria_soft", "synth3k_hard", "synth3k_soft", "synth3k_r2vec",
                 "tiny96_hard", "noiso500"]
-_INPUTS_FROM = {"astoria_hard": "astoria_inputs", "astoria_soft": "astoria_inputs", "synth3k_r2vec": "synth3k_hard"}
+_INPUTS_FROM = {"astoria_hard": "astoria_inputs", "astoria_soft": "astoria_inputs", "synth3k_r2vec": "synth3k_hard",
+                "synth3k_tables_soft": "synth3k_layers_hard"}
+# round-2 fixtures of the real reference: per-edge network types (multi-layer contact networks) and the gradients with respect
+# to SFSusceptibility / SFInfector (oracle/ref_harness/make_golden.py round2)
+TABLE_CASES = ["synth3k_layers_hard", "synth3k_tables_soft", "layers400_none"]
 
 
 def load_golden(name):

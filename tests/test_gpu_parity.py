@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import GOLDEN_CASES, load_golden, make_noise, rel_err
+from tests.helpers import GOLDEN_CASES, TABLE_CASES, load_golden, make_noise, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -107,3 +107,44 @@ def test_tensor_noise_and_cuda_graph_paths(case):
         st, gr2, gm, eng = _run_engine(g, packed=True, block_size=1024, cuda_graph=True, grid=7, tasks_per_group=8, layout=layout)
         _check(g, st, gr2, gm)
         assert eng.launch_count > 0
+
+
+@pytest.mark.parametrize("case", TABLE_CASES)
+@pytest.mark.parametrize("kw", [dict(), dict(block_size=1024, tile_rows=256)])
+def test_layers_and_table_gradients_match_reference_golden(case, kw):
+    """multi-layer contact networks (per-edge network type -> per-edge I_bar, transition.py:71-73) and dL/dSFSusceptibility,
+    dL/dSFInfector against the real reference (oracle/ref_harness/make_golden.py round2)"""
+    from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
+    from agenttorch_b200.graph import build_contact_graph, mean_interactions_from_age
+
+    dev = torch.device("cuda:0")
+    g = load_golden(case)
+    T, n = g["num_steps"], len(g["age"])
+    age = torch.from_numpy(g["age"].astype(np.int64))
+    edges = torch.from_numpy(g["edges"].astype(np.int64)).t().contiguous()
+    attr = None
+    if "edge_type" in g:
+        attr = torch.stack((torch.from_numpy(g["edge_type"]).float(), torch.ones(edges.shape[1])))
+    graph = build_contact_graph(edges, n, edge_attr=attr, mean_interactions=mean_interactions_from_age(age)).to(dev)
+    assert (len(graph.i_bar_layers) == 3) == ("edge_type" in g)
+    eng = SeirmEngine(graph, SeirmSpec(num_steps=T), **kw)
+    eng.want_table_grad = True
+    st = SeirmState.from_initial(g["stage0"].astype(np.float32), g["age"], T, dev)
+    noise = NoiseSpec(seed=g["seed"], isolation=g["mode"], p_isolate=float(g["p_isolate"]))
+    r2, r_steps = _r_steps_and_grad(g["r2"], T)
+    m = torch.tensor(g["m"], dtype=torch.float32, device=dev)
+    for cuda_graph in (False, True):
+        fresh = SeirmState.from_initial(g["stage0"].astype(np.float32), g["age"], T, dev)
+        for k in ("stage", "next_stage_time", "infected_time", "daily_infected", "daily_deaths"):
+            getattr(st, k).copy_(getattr(fresh, k))
+        sv = eng.run_episode(st, r_steps.detach().to(dev), m, T, noise, want_grad=True, cuda_graph=cuda_graph)
+    gI, gD = torch.from_numpy(g["gI"]).to(dev), torch.from_numpy(g["gD"]).to(dev)
+    gr, gm = eng.episode_backward(sv, T, gI, gD, m)
+    eng.check_errors()
+    r_steps.backward(gr.cpu())
+    _check(g, st, r2.grad.numpy(), gm.cpu().numpy())
+    g_sfs, g_sfi = eng.table_gradients(sv, T, gI, gD, m, r_steps.detach().to(dev), st.age)
+    assert rel_err(g["ref_grad_SFS"], g_sfs.cpu().numpy()) <= 1e-4
+    assert rel_err(g["ref_grad_SFI"][1:3], g_sfi.cpu().numpy()[1:3]) <= 1e-4      # [0]: fractional-stage sources, not tracked
+    if g["mode"] != "soft":
+        assert rel_err(g["ref_grad_SFI"], g_sfi.cpu().numpy()) <= 1e-4

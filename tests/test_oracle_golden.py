@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle.seirm_port import SeirmPort, episode_with_grads
-from tests.helpers import GOLDEN_CASES, load_golden, make_noise, rel_err
+from tests.helpers import GOLDEN_CASES, TABLE_CASES, load_golden, make_noise, rel_err
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
@@ -31,6 +31,26 @@ def test_port_matches_reference(case, faithful):
     assert rel_err(g["ref_daily_deaths"], out["daily_deaths"]) <= 1e-6
     assert rel_err(g["ref_grad_R2"], out["grad_R2"]) <= 1e-6
     assert rel_err(g["ref_grad_M"], out["grad_M"]) <= 1e-6
+
+
+@pytest.mark.parametrize("case", TABLE_CASES)
+def test_port_matches_reference_layers_and_table_gradients(case):
+    """per-edge network types (I_bar gathered per edge, transition.py:71-73) and dL/dSFSusceptibility, dL/dSFInfector"""
+    g = load_golden(case)
+    T = g["num_steps"]
+    U, W = make_noise(g["seed"], g["mode"], len(g["age"]), T, float(g["p_isolate"]))
+    port = SeirmPort(g["age"], g["stage0"], g["edges"], edge_type=g.get("edge_type"))
+    out = episode_with_grads(port, W, U, g["gI"], g["gD"], r2=g["r2"], m=g["m"], table_grads=True)
+    assert np.array_equal(out["stage"], g["ref_stage"])
+    assert np.array_equal(out["next_stage_time"], g["ref_next_stage_time"].astype(np.float32))
+    assert np.array_equal(out["infected_time"], g["ref_infected_time"].astype(np.float32))
+    assert rel_err(g["ref_daily_infected"], out["daily_infected"]) <= 1e-6
+    assert rel_err(g["ref_daily_deaths"], out["daily_deaths"]) <= 1e-6
+    for k in ("grad_R2", "grad_M", "grad_SFS", "grad_SFI"):
+        assert rel_err(g["ref_" + k], out[k]) <= 1e-6, k
+    assert np.count_nonzero(g["ref_grad_SFS"]) >= 5 and np.count_nonzero(g["ref_grad_SFI"][1:3]) == 2
+    if "edge_type" in g:
+        assert len(np.unique(g["edge_type"])) == 3
 
 
 def test_golden_covers_fractional_and_initially_infected_agents():

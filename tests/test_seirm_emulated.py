@@ -103,6 +103,48 @@ def test_kernel_source_matches_reference_golden(engine_on_host, case, kw):
     _check(g, st, grad_r2, grad_m)
 
 
+@pytest.mark.parametrize("case,kw", [
+    ("layers400_none", dict(block_size=1024, tile_rows=64)),          # three network layers, one / several source blocks
+    ("synth3k_layers_hard", dict(block_size=1024, tile_rows=256)),
+    ("synth3k_layers_hard", dict()),
+    ("synth3k_tables_soft", dict()),
+])
+def test_layers_and_table_gradients_match_reference_golden(engine_on_host, case, kw):
+    """multi-layer contact networks (per-edge network type -> per-edge I_bar, transition.py:71-73) and the gradients with respect
+    to SFSusceptibility / SFInfector, against outputs of the real reference (oracle/ref_harness/make_golden.py round2)"""
+    from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
+    from agenttorch_b200.graph import build_contact_graph, mean_interactions_from_age
+
+    g = load_golden(case)
+    T, n = g["num_steps"], len(g["age"])
+    age = torch.from_numpy(g["age"].astype(np.int64))
+    edges = torch.from_numpy(g["edges"].astype(np.int64)).t().contiguous()
+    attr = None
+    if "edge_type" in g:
+        attr = torch.stack((torch.from_numpy(g["edge_type"]).float(), torch.ones(edges.shape[1])))
+    graph = build_contact_graph(edges, n, edge_attr=attr, mean_interactions=mean_interactions_from_age(age))
+    assert (len(graph.i_bar_layers) == 3) == ("edge_type" in g)
+    eng = SeirmEngine(graph, SeirmSpec(num_steps=T), warps_per_cta=2, **kw)
+    eng.want_table_grad = True
+    st = SeirmState.from_initial(g["stage0"].astype(np.float32), g["age"], T, torch.device("cpu"))
+    noise = NoiseSpec(seed=g["seed"], isolation=g["mode"], p_isolate=float(g["p_isolate"]))
+    r2 = torch.tensor(g["r2"], dtype=torch.float32, requires_grad=True)
+    eye = torch.eye(3)
+    r_steps = torch.stack([(r2 * eye[int(t / 7)]).sum() for t in range(T)])
+    m = torch.tensor(g["m"], dtype=torch.float32)
+    sv = eng.run_episode(st, r_steps.detach(), m, T, noise, want_grad=True)
+    gI, gD = torch.from_numpy(g["gI"]), torch.from_numpy(g["gD"])
+    gr, gm = eng.episode_backward(sv, T, gI, gD, m)
+    r_steps.backward(gr)
+    _check(g, st, r2.grad.numpy(), gm.numpy())
+    g_sfs, g_sfi = eng.table_gradients(sv, T, gI, gD, m, r_steps.detach(), st.age)
+    assert rel_err(g["ref_grad_SFS"], g_sfs.numpy()) <= 1e-4
+    # SFInfector[1] (exposed) and [2] (infected) sources; [0] — fractional-stage sources under soft isolation — is not tracked
+    assert rel_err(g["ref_grad_SFI"][1:3], g_sfi.numpy()[1:3]) <= 1e-4
+    if g["mode"] != "soft":
+        assert rel_err(g["ref_grad_SFI"], g_sfi.numpy()) <= 1e-4
+
+
 def test_the_real_binding_is_restored_after_emulation():
     assert _native.LIB_PATH.endswith(os.path.join("lib", "libat_seirm.so"))
     assert engine._require_cuda.__module__ == "agenttorch_b200.engine"
@@ -180,6 +222,21 @@ def test_runner_fused_episode_path_on_host(engine_on_host, monkeypatch, tmp_path
     runner.step(g["num_steps"])
     assert runner.perf_stats["fused_episodes"] == 1
     _check_runner(g, runner, r2, m)
+
+
+def test_runner_fused_episode_learnable_tables_on_host(engine_on_host, monkeypatch, tmp_path):
+    """SFSusceptibility / SFInfector as differentiable environment tensors (learnable-capable in config.yaml): loss.backward()
+    through runner.step() fills their gradients, as in the reference (golden from the real reference)"""
+    g = load_golden("synth3k_tables_soft")
+    runner, r2, m = _runner(g, tmp_path, monkeypatch, fused=True)
+    env = runner.state["environment"]
+    env["SFSusceptibility"] = env["SFSusceptibility"].detach().clone().requires_grad_(True)
+    env["SFInfector"] = env["SFInfector"].detach().clone().requires_grad_(True)
+    runner.step(g["num_steps"])
+    assert runner.perf_stats["fused_episodes"] == 1
+    _check_runner(g, runner, r2, m)
+    assert rel_err(g["ref_grad_SFS"], env["SFSusceptibility"].grad.numpy()) <= 1e-4
+    assert rel_err(g["ref_grad_SFI"][1:3], env["SFInfector"].grad.numpy().reshape(-1)[1:3]) <= 1e-4
 
 
 # ------------------------------------------------------------------------------------------------------------------
