@@ -13,8 +13,6 @@ import re
 
 import torch
 
-import torch
-
 from agenttorch_b200 import ops
 from agenttorch_b200.core.helpers import get_by_path
 from agenttorch_b200.core.substep import SubstepTransitionMessagePassing

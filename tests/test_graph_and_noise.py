@@ -45,13 +45,17 @@ def test_csr_keeps_original_edge_order_duplicates_and_self_loops():
     assert g.col_idx.numel() >= g.num_edges + 4 and g.col_idx.data_ptr() % 16 == 0
 
 
-def test_i_bar_follows_edge_type_and_rejects_mixed_types():
+def test_i_bar_follows_edge_type_and_mixed_types_become_layers():
     ei = torch.tensor([[0, 1, 2], [1, 2, 0]])
     mi = torch.tensor([2.0, 3.0, 4.0])
     attr = torch.tensor([[2.0, 2.0, 2.0], [1.0, 1.0, 1.0]])
     assert build_contact_graph(ei, 3, edge_attr=attr, mean_interactions=mi).i_bar == 2.0     # dst[2] = 0
-    with pytest.raises(NotImplementedError):
-        build_contact_graph(ei, 3, edge_attr=torch.tensor([[1.0, 2.0, 1.0], [1.0, 1.0, 1.0]]), mean_interactions=mi)
+    # mixed types: one I_bar per distinct type k, mean_interactions[dst[k]] (the reference's per-edge gather, transition.py:71-73)
+    lay = build_contact_graph(ei, 3, edge_attr=torch.tensor([[1.0, 2.0, 1.0], [1.0, 1.0, 1.0]]), mean_interactions=mi)
+    assert lay.i_bar_layers == (4.0, 2.0)                                                     # types 1, 2 -> dst[1] = 2, dst[2] = 0
+    assert lay.edge_layer[:3].tolist() == [0, 0, 1]                                           # dst-sorted edge order: (2->0), (0->1), (1->2)
+    with pytest.raises(NotImplementedError):                                                 # layers + weights: not supported
+        build_contact_graph(ei, 3, edge_attr=torch.tensor([[1.0, 2.0, 1.0], [1.0, 0.5, 1.0]]), mean_interactions=mi)
     w = build_contact_graph(ei, 3, edge_attr=torch.tensor([[1.0, 1.0, 1.0], [1.0, 0.5, 1.0]]), mean_interactions=mi)
     assert w.edge_weight is not None and w.edge_weight[:3].tolist() == [1.0, 1.0, 0.5]       # dst-sorted order
 

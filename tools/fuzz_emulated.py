@@ -48,13 +48,14 @@ def random_case(rng):
     stage0[r < fe] = 1.0
     stage0[(r >= fe) & (r < fe + fi)] = 2.0
     weights = rng.uniform(0.1, 3.0, e).astype(np.float32) if e and rng.random() < 0.3 else None
-    layout = rng.choice(["fused", "blocked", "hashed32", "hashed64", "packed", "packed"] if weights is None else
+    layout = rng.choice(["fused", "blocked", "hashed32", "hashed64", "stream", "stream", "stream"] if weights is None else
                         ["fused", "blocked", "hashed32", "hashed64"])
-    kw = {"fused": {}, "blocked": {"block_size": 1024}, "hashed32": {"hashed": True, "hash_words": 32},
+    kw = {"fused": {"layout": "bcsr"}, "blocked": {"layout": "bcsr", "block_size": 1024}, "hashed32": {"hashed": True, "hash_words": 32},
           "hashed64": {"hashed": True, "hash_words": 64},
-          "packed": {"layout": "packed", "block_size": int(rng.choice([1024, 2048, 4096])),
-                     "tile_rows": int(rng.choice([32, 64, 256, 2048]))}}[layout]
-    if layout != "blocked" and rng.random() < 0.5:
+          "stream": {"layout": "stream", "block_size": int(rng.choice([1024, 2048, 4096])),
+                     "tile_rows": int(rng.choice([32, 64, 256, 2048])), "bank_aware": bool(rng.random() < 0.7),
+                     "grid": int(rng.choice([0, 1, 3, 5]))}}[layout]
+    if layout not in ("blocked", "stream") and rng.random() < 0.5:
         kw["edges_per_chunk"] = int(rng.choice([512, 768, 1024]))
     if rng.random() < 0.3:
         kw["tasks_per_group"] = int(rng.choice([1, 2, 8]))
