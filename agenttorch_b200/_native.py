@@ -72,7 +72,7 @@ class SeirmLaunch(ctypes.Structure):
         ("unit_tile", ctypes.c_void_p), ("block_units", ctypes.c_void_p), ("tile_rec_base", ctypes.c_void_p),
         ("tile_count", ctypes.c_void_p), ("rec", ctypes.c_void_p),
         ("lam_deg_bits", ctypes.c_int32), ("xchg_slot", ctypes.c_int32),
-        ("dne_e_dr", ctypes.c_void_p), ("reserve_sms", ctypes.c_int32), ("_pad2", ctypes.c_int32),
+        ("dne_e_dr", ctypes.c_void_p), ("over_state", ctypes.c_void_p), ("over_local", ctypes.c_int32), ("reserve_sms", ctypes.c_int32),
     ]
 
 
@@ -140,7 +140,8 @@ def lib():
         L.at_seirm_exchange_sparse.restype = ctypes.c_int
         L.at_seirm_exchange_sparse.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
                                                ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
-                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
+                                               ctypes.c_void_p]
         L.at_noise_fill.restype = ctypes.c_int
         L.at_noise_fill.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32,
                                     ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]

@@ -323,6 +323,9 @@ class Runner(nn.Module):
                 None, uniform, want_grad, self._use_cuda_graph and uniform is None, sfs=tables[0], sfi=tables[1])
         finally:
             ctx.engine.after_step = None
+        # a lam_gamma_integrals overrun (the reference raises an IndexError) or an exchange timeout flagged on the device
+        # surfaces here without a host synchronisation, i.e. on the call after the one that caused it
+        ctx.engine.poll_errors()
         set_by_path(state, path(iv["daily_infected"]), new_di.view_as(di))
         set_by_path(state, path(pv["daily_deaths"]), new_dd.reshape(1, -1))       # (1,T) like the reference (Q6)
         state["current_step"] = num_steps - 1

@@ -49,6 +49,7 @@
 #define WS_COUNTER 36               // int: group counter (main kernel)
 #define WS_ANYHOT 40                // uint[3]: some agent of this rank is infectious in the step just encoded, one word per code
                                     // buffer in flight (at_seirm_launch.xchg_slot; read + reset by the exchange)
+#define WS_HASEI 52                 // uint[3]: some agent of this rank is in E or I after the step just done (same slots as WS_ANYHOT)
 #define WS_GCOUNTERS 64             // int[AT_MAX_BLOCKS]: group counters of the gather kernel
 #define WS_GTICKET 384              // int
 #define WS_BTICKET 512              // int: backward kernel
@@ -171,8 +172,8 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
     const double ibar = (double)m.ibar;
     char* ws = reinterpret_cast<char*>(a.workspace);
 
-    __shared__ int s_any_hot, s_any_out;
-    if (tid == 0) { s_any_hot = 0; s_any_out = 0; }
+    __shared__ int s_any_hot, s_any_out, s_any_ei;
+    if (tid == 0) { s_any_hot = 0; s_any_out = 0; s_any_ei = 0; }
     // ---- tables: code -> (SFInfector[int(stage)], lam_gamma[idx]); code = 1 + sidx*K + idx
     // (strided: a CTA may have fewer than 256 threads — few warps next to a large bitmap, or warps_per_cta set by the caller)
     for (int c = tid; c < 256; c += blockDim.x) {
@@ -439,6 +440,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
         const uint32_t exp_o = __ballot_sync(0xffffffffu, is_e);
         const uint32_t inf_o = __ballot_sync(0xffffffffu, is_i);
         if (lane == 0) {
+            if ((exp_o | inf_o) != 0u) s_any_ei = 1;             // benign race: every writer stores 1
             if (do_init || sus_o != sus_w) a.sus_bitmap[task] = sus_o;
             if (do_init || exp_o != exp_w) a.exp_bitmap[task] = exp_o;
             if (do_init || inf_o != inf_w) a.inf_bitmap[task] = inf_o;
@@ -718,6 +720,7 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
             if (s1) atomicAdd(&acc[1], (unsigned long long)s1);
             if (s2) atomicAdd(&acc[2], (unsigned long long)s2);
             if (s_any_out) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_ANYHOT) + a.xchg_slot, 1u);
+            if (s_any_ei) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_HASEI) + a.xchg_slot, 1u);
         }
         __threadfence();
         s_is_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
@@ -737,6 +740,12 @@ seirm_kernel(const KModel m, const at_seirm_launch a, const int bm_words, const 
                 if (a.daily_deaths) a.daily_deaths[t] += (float)s2 * a.m_value[0];   // progression :52-60
             }
             acc[0] = 0; acc[1] = 0; acc[2] = 0;
+            if (a.over_state != nullptr && a.over_local) {
+                // one GPU: this launch knows whether anybody is left in E or I ("epidemic over" lets the next gathers return at once)
+                unsigned int* he = reinterpret_cast<unsigned int*>(ws + WS_HASEI) + a.xchg_slot;
+                *a.over_state = (*reinterpret_cast<volatile unsigned int*>(he) != 0u) ? 0 : 1;
+                *he = 0u;
+            }
         }
         *ticket = 0;
     }
@@ -868,6 +877,8 @@ stream_gather_body(const KModel& m, const at_seirm_launch& a, const int bm_words
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint2* s_pend = s_pend_all + warp * ST_PEND;
+    // the epidemic is over (nobody of any rank in E or I): no source is infectious, the update has no record to read
+    if (a.over_state != nullptr && *reinterpret_cast<const volatile int*>(a.over_state) > 0) return;
     if (blockIdx.x == gridDim.x - 1) {                          // scratch: after the parked-hit lists
         unsigned char* scratch = reinterpret_cast<unsigned char*>(s_pend_all + (size_t)nw * ST_PEND);
         stream_build_term_table(m, a, NC, reinterpret_cast<double*>(scratch + 16), reinterpret_cast<unsigned long long*>(scratch));
@@ -1024,7 +1035,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     uint8_t* s_age = reinterpret_cast<uint8_t*>(s_cand + a.tile_rows);
     __shared__ long long s_red[TU_THREADS / 32][3];
     __shared__ uint32_t s_w[3][TU_MAX_TASKS], s_orig[3][TU_MAX_TASKS], s_hot[TU_MAX_TASKS];   // sus / exp / inf words of the tile
-    __shared__ int s_is_last, s_any_out, s_ncand;
+    __shared__ int s_is_last, s_any_out, s_any_ei, s_ncand;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = TU_THREADS / 32;
     const bool age_f32 = a.age_dtype == AT_AGE_F32;
@@ -1035,7 +1046,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
     char* ws = reinterpret_cast<char*>(a.workspace);
 
-    if (tid == 0) { s_any_out = 0; s_ncand = 0; }
+    if (tid == 0) { s_any_out = 0; s_any_ei = 0; s_ncand = 0; }
     for (int c = tid; c < 256; c += TU_THREADS) {
         float av = 0.f, gv = 0.f;
         if (c >= 1 && c <= 3 * m.n_lg) {
@@ -1239,6 +1250,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
             if (s_w[0][tid] != s_orig[0][tid]) a.sus_bitmap[task] = s_w[0][tid];
             if (s_w[1][tid] != s_orig[1][tid]) a.exp_bitmap[task] = s_w[1][tid];
             if (s_w[2][tid] != s_orig[2][tid]) a.inf_bitmap[task] = s_w[2][tid];
+            if ((s_w[1][tid] | s_w[2][tid]) != 0u) s_any_ei = 1;  // benign race: every writer stores 1
         }
         __syncthreads();                                         // shared arrays are reused by the next tile
     }
@@ -1261,6 +1273,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
         if (s1) atomicAdd(&acc[1], (unsigned long long)s1);
         if (s2) atomicAdd(&acc[2], (unsigned long long)s2);
         if (s_any_out) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_ANYHOT) + a.xchg_slot, 1u);
+        if (s_any_ei) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_HASEI) + a.xchg_slot, 1u);
         __threadfence();
         s_is_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
     }
@@ -1276,6 +1289,12 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
             if (a.daily_deaths) a.daily_deaths[t] += (float)s2 * a.m_value[0];   // progression :52-60
         }
         acc[0] = 0; acc[1] = 0; acc[2] = 0;
+        if (a.over_state != nullptr && a.over_local) {
+            // one GPU: nobody left in E or I => nothing is or will become infectious; the next gathers return at once
+            unsigned int* he = reinterpret_cast<unsigned int*>(ws + WS_HASEI) + a.xchg_slot;
+            *a.over_state = (*reinterpret_cast<volatile unsigned int*>(he) != 0u) ? 0 : 1;
+            *he = 0u;
+        }
         *ticket = 0;
     }
 }
@@ -1390,12 +1409,15 @@ struct PeerBufs { uint8_t* p[16]; };
 __global__ void __launch_bounds__(256)
 exchange_sparse_kernel(uint8_t* __restrict__ local, int64_t n_sources, uint32_t* __restrict__ filter, int hash_words,
                        PeerBufs peers, int world, int rank, int64_t per, uint32_t* sync_state, uint32_t* any_word,
-                       int32_t* error_flag)
+                       int32_t* error_flag, int32_t* over_state, int over_after)
 {
     // sync_state: [0] epoch of this buffer, [1] CTA ticket, [2 + r] "my copy of rank r's slice holds non-zero data"
     __shared__ uint32_t s_epoch;
-    __shared__ int s_any[16], s_skip[16];
+    __shared__ int s_any[16], s_skip[16], s_ei[16];
     const int tid = threadIdx.x, lane = tid & 31;
+    // the epidemic has been over for as many exchanges as there are code buffers: every copy is clear, nothing can change
+    // (all ranks saw the same signals, so all of them skip the same calls)
+    if (over_state != nullptr && *reinterpret_cast<const volatile int32_t*>(over_state) >= over_after) return;
     if (tid == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(sync_state) + 1u;
     __syncthreads();
     const uint32_t epoch = s_epoch;
@@ -1405,25 +1427,28 @@ exchange_sparse_kernel(uint8_t* __restrict__ local, int64_t n_sources, uint32_t*
     if (blockIdx.x == 0) {
         // does my own slice hold any infectious agent?  (travels with the arrival signal, so that peers skip it)
         // (the step kernel leaves the answer in its workspace; without it the slice's bitmap is scanned)
-        uint32_t acc = 0;
+        uint32_t acc = 0, ei = 1u;
         if (any_word != nullptr) {
-            if (tid == 0) acc = atomicExch(any_word, 0u);
+            if (tid == 0) { acc = atomicExch(any_word, 0u); ei = atomicExch(any_word + (WS_HASEI - WS_ANYHOT) / 4, 0u); }
         } else {
             const uint4* mine4 = reinterpret_cast<const uint4*>(hot_local + rank * words_per);
             for (int64_t i = tid; i < (words_per >> 2); i += blockDim.x) { const uint4 v = mine4[i]; acc |= v.x | v.y | v.z | v.w; }
         }
         const int any_own = __syncthreads_or(acc != 0u);
+        const int ei_own = __syncthreads_or(tid == 0 && ei != 0u);
+        // arrival signal: epoch of the buffer, "somebody of mine is in E or I", "somebody of mine is infectious in this step"
+        const uint32_t sig = (epoch << 2) | ((uint32_t)(ei_own != 0) << 1) | (uint32_t)(any_own != 0);
         if (tid < world && tid != rank) {
             __threadfence_system();
-            st_release_sys(reinterpret_cast<uint32_t*>(peers.p[tid] + flag_off) + rank, (epoch << 1) | (uint32_t)(any_own != 0));
+            st_release_sys(reinterpret_cast<uint32_t*>(peers.p[tid] + flag_off) + rank, sig);
         }
-        if (tid == 0) *(reinterpret_cast<volatile uint32_t*>(local + flag_off) + rank) = (epoch << 1) | (uint32_t)(any_own != 0);
+        if (tid == 0) *(reinterpret_cast<volatile uint32_t*>(local + flag_off) + rank) = sig;
     }
     if (tid < world) {
         const uint32_t* mine = reinterpret_cast<const uint32_t*>(local + flag_off) + tid;
         const long long t0 = clock64();
         uint32_t v = ld_acquire_sys(mine);
-        while ((int32_t)((v >> 1) - epoch) < 0) {
+        while ((int32_t)(((v >> 2) - epoch) << 2) < 0) {
             if (clock64() - t0 > 40000000000ll) {            // ~20 s: a peer never arrived; report instead of hanging
                 if (error_flag) *error_flag = 2;
                 break;
@@ -1433,6 +1458,7 @@ exchange_sparse_kernel(uint8_t* __restrict__ local, int64_t n_sources, uint32_t*
         }
         // (a peer cannot be more than one use of this buffer ahead, so the low bit belongs to this epoch)
         s_any[tid] = (int)(v & 1u);
+        s_ei[tid] = (int)((v >> 1) & 1u);
         const int live = (int)reinterpret_cast<volatile uint32_t*>(sync_state)[2 + tid];
         s_skip[tid] = !(v & 1u) && (tid == rank || !live);          // nothing hot there now and nothing to clear here
     }
@@ -1479,6 +1505,11 @@ exchange_sparse_kernel(uint8_t* __restrict__ local, int64_t n_sources, uint32_t*
     __syncthreads();
     if (s_last) {
         if (tid < world) reinterpret_cast<volatile uint32_t*>(sync_state)[2 + tid] = (uint32_t)s_any[tid];
+        if (tid == 0 && over_state != nullptr) {
+            int any_ei = 0;
+            for (int r = 0; r < world; ++r) any_ei |= s_ei[r];
+            *over_state = any_ei ? 0 : *over_state + 1;
+        }
         if (tid == 0) {
             reinterpret_cast<int*>(sync_state)[1] = 0;
             __threadfence();
@@ -1564,11 +1595,12 @@ __global__ void noise_fill_kernel(float* out, int64_t n, int64_t id_offset, uint
 }
 
 // ------------------------------------------------------------------------------------------ C ABI
-static int g_sm_count = 0, g_smem_optin = 0;
+static thread_local int g_sm_count = 0, g_smem_optin = 0, g_props_dev = -1;     // properties of the CURRENT device
 static int device_props() {
-    if (g_sm_count) return 0;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    if (g_sm_count && dev == g_props_dev) return 0;
+    g_props_dev = dev;
     if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
     if (cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 1;
     return 0;
@@ -1849,7 +1881,7 @@ int64_t at_seirm_exchange_bytes(int64_t n_sources) {
 
 int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* hot_filter, int32_t hash_words,
                              void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, void* step_workspace,
-                             int32_t* error_flag, int32_t max_ctas, void* stream) {
+                             int32_t* error_flag, int32_t max_ctas, int32_t* over_state, int32_t over_after, void* stream) {
     if (!local_buf || !peer_buf || !sync_state) return fail("%s", "exchange_sparse: null buffer");
     if (n_sources <= 0 || (n_sources & 1023)) return fail("%s", "exchange_sparse: n_sources must be a positive multiple of 1024");
     if (world < 2 || world > 16 || rank < 0 || rank >= world || (n_sources % world) || ((n_sources / world) & 1023))
@@ -1875,7 +1907,7 @@ int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* ho
     if (grid < 1) grid = 1;
     uint32_t* any_word = step_workspace ? reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(step_workspace) + WS_ANYHOT) : nullptr;
     AT_LAUNCH(exchange_sparse_kernel, grid, 256, s, local_buf, n_sources, hot_filter, hash_words, pb, world, rank, n_sources / world,
-                                                sync_state, any_word, error_flag);
+                                                sync_state, any_word, error_flag, over_state, over_after < 1 ? 2 : over_after);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("exchange_sparse_kernel launch: %s", cudaGetErrorString(e));
     return 0;

@@ -209,6 +209,7 @@ class DistributedRunner:
         st.daily_deaths.zero_()
         env = self.state["environment"]
         di, dd = _EpisodeFn.apply(self, r_steps, m_value, T, want_grad)
+        self.engine.poll_errors()                 # device-side error flag of an earlier episode (no host synchronisation)
         env["daily_infected"] = env["daily_infected"].detach().reshape(-1) + di
         env["daily_deaths"] = (env["daily_deaths"].detach().reshape(-1) + dd).reshape(1, -1)         # (1,T), Q6
         self.state["current_step"] = T - 1

@@ -41,6 +41,10 @@ class SeirmSpec:
             raise ValueError(f"lam_gamma_integrals must have 1..{nat.MAX_LAMGAMMA} entries")
         if len(self.sfs) > nat.MAX_SFS or len(self.sfi) > nat.MAX_SFI:
             raise ValueError("SFSusceptibility / SFInfector table too long")
+        # limits of the kernels, refused here rather than inside a launch (README "Limits"): the step index is stored in a byte,
+        # the fused backward keeps one accumulator per step and lane
+        if self.num_steps > 255:
+            raise ValueError("episodes of more than 255 steps are not supported (recovered_step is a uint8)")
 
     def to_struct(self, i_bar, i_bar_layers=()):
         m = nat.SeirmModel()
@@ -286,9 +290,20 @@ class SeirmEngine:
                 import torch.distributed as dist
 
                 dist.barrier(group=process_group)               # nobody signals into a buffer that is still being zeroed
-            except Exception:
+            except Exception as exc:
                 if symmetric is True:
                     raise
+                import warnings
+
+                warnings.warn(f"symmetric memory unavailable on this rank ({type(exc).__name__}: {exc}); NCCL all-gather exchange")
+                self.code_hdl = None
+            # every rank must take the same exchange path: a rank that fell back alone would wait in an all-gather while the
+            # others spin in the rendezvous kernel
+            import torch.distributed as dist
+
+            ok = torch.tensor([1 if self.code_hdl is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+            if int(ok.item()) == 0:
                 self.code_hdl = None
         if self.code_hdl is None:
             self.overlap = False                                  # the overlapped exchange is the symmetric-memory kernel
@@ -326,6 +341,12 @@ class SeirmEngine:
         # into CUDA graphs (the hook's buffers are not part of the capture key)
         self.after_step = None
         self._side = None                    # side stream of the overlapped halo exchange
+        # "the epidemic is over" (no agent of any rank in E or I): device word maintained by the launches of an episode (one GPU)
+        # or by the halo exchange (several); the gather launches and, after one more round over the code buffers, the exchanges
+        # then return at once.  Only consulted inside run_episode(), which zeroes it first: between direct launches the caller may
+        # have edited the state.
+        self.over = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._use_over = False
 
     # ------------------------------------------------------------------------------ raw launch
     def launch(self, state: SeirmState, *, flags, t, t_encode=None, code_in=None, code_out=None,
@@ -405,6 +426,9 @@ class SeirmEngine:
         a.hash_words = int(g.hash_words)
         a.xchg_slot = int(xchg_slot)
         a.reserve_sms = int(reserve_sms)
+        if self._use_over:
+            a.over_state = _ptr(self.over, torch.int32)
+            a.over_local = 1 if self.pg is None else 0
         rec = getattr(self, "_recording", None)
         if rec is not None:
             rec.append((a, self._kernels_of(flags)))
@@ -459,7 +483,9 @@ class SeirmEngine:
                 nat.check(self.lib.at_seirm_exchange_sparse(_ptr(self.xbuf[buf_index]), int(self.n_code), _ptr(filt),
                                                             int(self.graph.hash_words), ptrs, world, rank,
                                                             _ptr(self.xsync[buf_index]), _ptr(self.workspace) + 4 * int(slot),
-                                                            _ptr(self.error_flag), int(max_ctas), ctypes.c_void_p(stream)))
+                                                            _ptr(self.error_flag), int(max_ctas),
+                                                            _ptr(self.over, torch.int32) if self._use_over else None,
+                                                            len(self.xbuf), ctypes.c_void_p(stream)))
             else:
                 hdl.barrier(channel=buf_index)                   # every rank has written its slice of this buffer
                 # dense: pull the peers' whole slices (P2P loads) + rebuild bitmap/filter from the codes, one kernel
@@ -523,8 +549,16 @@ class SeirmEngine:
                None if noise.isolation_tensor is None else noise.isolation_tensor.data_ptr(),
                None if noise.uniform_tensor is None else noise.uniform_tensor.data_ptr())
         sv["recovered_step"].fill_(255)
-        if self.overlap:
-            return self._issue_episode_overlapped(state, num_steps, noise, sv, want_grad, t0)
+        self.over.zero_()
+        self._use_over = self.after_step is None     # (a hook may change stages behind the step kernels' back)
+        try:
+            if self.overlap:
+                return self._issue_episode_overlapped(state, num_steps, noise, sv, want_grad, t0)
+            return self._issue_episode_sync(state, num_steps, noise, sv, want_grad, t0, key)
+        finally:
+            self._use_over = False
+
+    def _issue_episode_sync(self, state, num_steps, noise, sv, want_grad, t0, key):
         plan = self._plans.get(key)
         if plan is not None:
             for k, (a, nk, flips) in enumerate(plan):
@@ -618,6 +652,9 @@ class SeirmEngine:
         m_value: (1,) float32.  Returns the saved-for-backward buffers (views owned by the engine).
         With cuda_graph=True the launch sequence is captured once per (state buffers, shape) and
         replayed; the seed, R and M are read from device memory so the graph is reusable."""
+        if want_grad and num_steps > 64:
+            raise ValueError("gradients through episodes of more than 64 steps are not supported (the fused backward kernel keeps "
+                             "one accumulator per step and lane); run forward-only or split the episode")
         sv = self.saved_buffers(num_steps, want_grad)
         if want_grad and self.want_table_grad and sv["dne_e"] is None:
             if self.graph.layout != 1:
@@ -723,6 +760,30 @@ class SeirmEngine:
             dist.all_reduce(packed, group=self.pg)
             grad_sfs, grad_sfi = packed[: grad_sfs.numel()], packed[grad_sfs.numel():]
         return grad_sfs.float(), grad_sfi.float()
+
+    def poll_errors(self):
+        """Raise for an error flagged by an EARLIER episode without stalling the stream: the flag is copied to pinned host memory
+        asynchronously after every call and inspected on the next one (check_errors() is the synchronous form)."""
+        if self.device.type != "cuda":
+            return self.check_errors()
+        if getattr(self, "_err_host", None) is None:
+            self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._err_event = None
+        if self._err_event is not None and self._err_event.query():
+            code = int(self._err_host[0])
+            if code != 0:
+                self._err_host.zero_()
+                self.error_flag.zero_()
+                self._raise_for(code)
+        self._err_host.copy_(self.error_flag, non_blocking=True)
+        self._err_event = torch.cuda.Event()
+        self._err_event.record(torch.cuda.current_stream(self.device))
+
+    @staticmethod
+    def _raise_for(code):
+        if code == 2:
+            raise RuntimeError("halo exchange: a peer rank never arrived at the rendezvous (at_seirm_exchange_sparse timed out)")
+        raise RuntimeError("lam_gamma_integrals index out of range during the episode (SURVEY.md A.2 Q10)")
 
     def check_errors(self):
         code = int(self.error_flag.item())

@@ -371,6 +371,8 @@ def ours(args):
             ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(T)]
             ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(T)]
             flags = torch.zeros(T, dtype=torch.bool, device=dev)
+            engine.over.zero_()
+            engine._use_over = True                                  # as inside run_episode(): "epidemic over" short cuts enabled
             engine.encode(st, 0)
             barrier()
             for t in range(T):
@@ -382,6 +384,7 @@ def ours(args):
                             death_count=sv["death_count"], recovered_step=sv["recovered_step"], seed_ptr=engine.seed_buf,
                             check_range=t + 1 < T)
                 ev1[t].record()
+            engine._use_over = False
             torch.cuda.synchronize(dev)
             active = flags.tolist()
             times = torch.tensor([ev0[t].elapsed_time(ev1[t]) for t in range(T)], device=dev)

@@ -200,10 +200,14 @@ typedef struct at_seirm_launch {
                                    (one per code buffer in flight; at_seirm_exchange_sparse reads and clears it) */
     float* dne_e_dr;            /* n_rows or NULL (stream layout): the part of dne_dr that comes from sources in stage E
                                    (SFInfector[1]); with dne_dr it gives d ne / d SFInfector[1], [2] — saved for backward */
+    int32_t* over_state;        /* or NULL: device word, > 0 once NO agent of ANY rank is in E or I ("the epidemic is over": nothing
+                                   is or will become infectious; agents with a fractional stage never are).  The stream gather then
+                                   returns at once.  Zeroed by the caller before the first launch of an episode; maintained by the
+                                   launches themselves when over_local != 0 (one GPU), else by at_seirm_exchange_sparse */
+    int32_t over_local;
     int32_t reserve_sms;        /* stream layout, != 0: the step kernels leave 1/8 of every SM's registers free (lean gather entry
                                    point, 7 instead of 8 update CTAs per SM), so that a halo exchange issued on another stream runs
                                    beside them instead of waiting for them (they otherwise take every register of every SM) */
-    int32_t _pad2;
 } at_seirm_launch;
 
 /* ---- queries (host only) ---- */
@@ -275,13 +279,17 @@ int at_seirm_pull_codes(uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, 
  * owned by this call sequence.  step_workspace: the at_seirm_launch.workspace of the step kernel that wrote this rank's
  * slice (it records there whether the slice holds any infectious agent; NULL = scan the slice).  max_ctas: 0 = as many
  * 256-thread CTAs as fit in one wave; > 0 caps the grid (an exchange that runs BESIDE the step kernels of the next step
- * should only occupy the SMs those leave free, at_seirm_launch.reserve_sms).  A peer that never arrives sets *error_flag = 2 after ~20 s.
+ * should only occupy the SMs those leave free, at_seirm_launch.reserve_sms).  over_state (or NULL): the arrival signal also says
+ * whether the rank still holds an agent in E or I; an exchange in which no rank does increments *over_state, any other resets
+ * it, and once it has reached over_after (the number of code buffers in rotation: every stale copy has been cleared by then) the
+ * call returns without a rendezvous — identically on every rank, because every rank saw the same signals.  The caller zeroes
+ * it when an episode starts.  A peer that never arrives sets *error_flag = 2 after ~20 s.
  * Replaces nothing in the reference (core/distributed_runner.py:218-228 is `pass`).
  */
 int64_t at_seirm_exchange_bytes(int64_t n_sources);
 int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* hot_filter, int32_t hash_words,
                              void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, void* step_workspace,
-                             int32_t* error_flag, int32_t max_ctas, void* stream);
+                             int32_t* error_flag, int32_t max_ctas, int32_t* over_state, int32_t over_after, void* stream);
 
 /*
  * at_noise_fill — materialise the counter-hash noise (same values the step kernel generates in
