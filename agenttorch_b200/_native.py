@@ -73,6 +73,7 @@ class SeirmLaunch(ctypes.Structure):
         ("tile_count", ctypes.c_void_p), ("rec", ctypes.c_void_p),
         ("lam_deg_bits", ctypes.c_int32), ("xchg_slot", ctypes.c_int32),
         ("dne_e_dr", ctypes.c_void_p), ("over_state", ctypes.c_void_p), ("over_local", ctypes.c_int32), ("reserve_sms", ctypes.c_int32),
+        ("step_skipped", ctypes.c_void_p),
     ]
 
 
@@ -128,7 +129,7 @@ def lib():
         L.at_seirm_episode_backward.argtypes = [
             ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-            ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
+            ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
         L.at_seirm_hot_from_code.restype = ctypes.c_int
         L.at_seirm_hot_from_code.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_int32, ctypes.c_void_p]

@@ -1065,6 +1065,13 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     }
     const int fx_shift = *reinterpret_cast<const int*>(ws + WS_FIXSHIFT);
     __syncthreads();
+    // epidemic over on entry (nobody of any rank in E or I after the previous step): no record, no candidate, no progression.
+    // The (T, N) saved-for-backward rows of this step are then left untouched (step_skipped tells the backward pass) and,
+    // from the second such step on, so are the code / hot buffers (both of them are zero by then).
+    const int over_in = (a.over_state != nullptr) ? *reinterpret_cast<const volatile int*>(a.over_state) : 0;
+    const bool skip_saved = over_in >= 1 && a.step_skipped != nullptr;
+    const bool skip_codes = over_in >= 2;
+    if (blockIdx.x == 0 && tid == 0 && a.step_skipped != nullptr) a.step_skipped[t] = skip_saved ? 1 : 0;
     const double inv_scale = ldexp(1.0, -fx_shift);             // exact power of two
     const double inv_r = (R != 0.f) ? 1.0 / (double)R : 1.0;
 
@@ -1097,9 +1104,10 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
         const int row_base = tile * tile_rows;
         const int rows_here = min(tile_rows, n_rows - row_base);        // valid rows of the tile (<= 0: padding only)
-        const uint32_t nrec = a.tile_count[tile];
+        if (over_in >= 1 && skip_codes && (skip_saved || !GRAD)) break;     // nothing left to do for any tile
+        const uint32_t nrec = (over_in >= 1) ? 0u : a.tile_count[tile];
         // ---- phase 0: outputs of rows that need nothing, bitmaps of the tile
-        if (GRAD) {
+        if (GRAD && !skip_saved) {
             float4* d4 = reinterpret_cast<float4*>(a.dne_dr + row_base);
             float4* e4 = want_e ? reinterpret_cast<float4*>(a.dne_e_dr + row_base) : nullptr;
             for (int i = tid; i * 4 < rows_here; i += TU_THREADS) {
@@ -1112,7 +1120,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
                 }
             }
         }
-        if (do_enc) {
+        if (do_enc && !skip_codes) {
             uint4* c4 = reinterpret_cast<uint4*>(code_out + row_base);
             for (int i = tid; i * 16 < rows_here; i += TU_THREADS) {
                 if (i * 16 + 16 <= rows_here) c4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -1125,7 +1133,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
             s_w[0][tid] = sw; s_w[1][tid] = ew; s_w[2][tid] = iw;
             s_orig[0][tid] = sw; s_orig[1][tid] = ew; s_orig[2][tid] = iw;
             s_hot[tid] = 0u;
-            if (do_enc && task * 32 < n_rows) hot_out[task] = 0u;         // (words of padding rows belong to somebody else)
+            if (do_enc && !skip_codes && task * 32 < n_rows) hot_out[task] = 0u;     // (words of padding rows belong to somebody else)
         }
         if (nrec != 0u) {
             for (int i = tid; i < tile_rows; i += TU_THREADS) {
@@ -1292,7 +1300,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
         if (a.over_state != nullptr && a.over_local) {
             // one GPU: nobody left in E or I => nothing is or will become infectious; the next gathers return at once
             unsigned int* he = reinterpret_cast<unsigned int*>(ws + WS_HASEI) + a.xchg_slot;
-            *a.over_state = (*reinterpret_cast<volatile unsigned int*>(he) != 0u) ? 0 : 1;
+            *a.over_state = (*reinterpret_cast<volatile unsigned int*>(he) != 0u) ? 0 : over_in + 1;
             *he = 0u;
         }
         *ticket = 0;
@@ -1528,7 +1536,7 @@ __global__ void __launch_bounds__(AT_BWD_THREADS)
 seirm_episode_bwd_kernel(int T, int64_t n, int64_t ld, const float* __restrict__ dne, const uint8_t* __restrict__ rstep,
                          const float* __restrict__ sum_dne, const float* __restrict__ death_count,
                          const float* __restrict__ gI, const float* __restrict__ gD, const float* __restrict__ m_value,
-                         float* grad_r, float* grad_m, char* ws)
+                         float* grad_r, float* grad_m, char* ws, const int32_t* __restrict__ skipped)
 {
     __shared__ float s_gd[256];
     __shared__ double s_acc[AT_BWD_THREADS / 32][BWD_MAXT];
@@ -1539,6 +1547,9 @@ seirm_episode_bwd_kernel(int T, int64_t n, int64_t ld, const float* __restrict__
     if (tid < 256) s_gd[tid] = (tid < T) ? gD[tid] * half_m : 0.f;
     __syncthreads();
     double acc0 = 0.0, acc1 = 0.0;                  // steps lane and lane + 32
+    // steps the forward skipped (epidemic over: their dne rows were not written and mean zero)
+    const bool skip0 = skipped != nullptr && lane < T && skipped[lane] != 0;
+    const bool skip1 = skipped != nullptr && lane + 32 < T && skipped[lane + 32] != 0;
     const int64_t ngroups = (n + 31) >> 5;
     const int64_t wstride = (int64_t)gridDim.x * (AT_BWD_THREADS / 32);
     for (int64_t g = (int64_t)blockIdx.x * (AT_BWD_THREADS / 32) + warp; g < ngroups; g += wstride) {
@@ -1550,8 +1561,8 @@ seirm_episode_bwd_kernel(int T, int64_t n, int64_t ld, const float* __restrict__
             mask &= mask - 1u;
             const float ci = __shfl_sync(0xffffffffu, c, src);
             const int64_t agent = g * 32 + src;
-            if (lane < T) acc0 += (double)(dne[(int64_t)lane * ld + agent] * ci);
-            if (lane + 32 < T) acc1 += (double)(dne[(int64_t)(lane + 32) * ld + agent] * ci);
+            if (lane < T && !skip0) acc0 += (double)(dne[(int64_t)lane * ld + agent] * ci);
+            if (lane + 32 < T && !skip1) acc1 += (double)(dne[(int64_t)(lane + 32) * ld + agent] * ci);
         }
     }
     s_acc[warp][lane] = acc0;
@@ -1825,7 +1836,7 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
 int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, const float* dne_dr, const uint8_t* recovered_step,
                               const float* sum_dne_dr, const float* death_count, const float* g_daily_infected,
                               const float* g_daily_deaths, const float* m_value, float* grad_r, float* grad_m,
-                              void* workspace, int32_t grid, void* stream) {
+                              void* workspace, int32_t grid, const int32_t* step_skipped, void* stream) {
     if (num_steps < 1 || num_steps > BWD_MAXT) return fail("%s", "num_steps out of range (1..64)");
     if (!dne_dr || !recovered_step || !sum_dne_dr || !death_count || !g_daily_infected || !g_daily_deaths || !m_value || !grad_r || !grad_m || !workspace)
         return fail("%s", "null argument");
@@ -1836,7 +1847,7 @@ int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, con
     if (g > BWD_MAX_GRID) g = BWD_MAX_GRID;
     if (g < 1) g = 1;
     AT_LAUNCH(seirm_episode_bwd_kernel, g, AT_BWD_THREADS, (cudaStream_t)stream, num_steps, n_rows, ld, dne_dr, recovered_step, sum_dne_dr,
-        death_count, g_daily_infected, g_daily_deaths, m_value, grad_r, grad_m, (char*)workspace);
+        death_count, g_daily_infected, g_daily_deaths, m_value, grad_r, grad_m, (char*)workspace, step_skipped);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("seirm_episode_bwd_kernel launch: %s", cudaGetErrorString(e));
     return 0;

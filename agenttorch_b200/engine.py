@@ -352,7 +352,7 @@ class SeirmEngine:
     def launch(self, state: SeirmState, *, flags, t, t_encode=None, code_in=None, code_out=None,
                noise: Optional[NoiseSpec] = None, isolation=None, uniform=None, r_value=None, r_index=0,
                m_value=None, dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None,
-               seed_ptr=None, check_range=True, xchg_slot=0, reserve_sms=0, dne_e_dr=None):
+               seed_ptr=None, check_range=True, xchg_slot=0, reserve_sms=0, dne_e_dr=None, step_skipped=None):
         g = self.graph
         a = nat.SeirmLaunch()
         a.abi_version = nat.ABI_VERSION
@@ -429,6 +429,7 @@ class SeirmEngine:
         if self._use_over:
             a.over_state = _ptr(self.over, torch.int32)
             a.over_local = 1 if self.pg is None else 0
+            a.step_skipped = _ptr(step_skipped, torch.int32, "step_skipped")
         rec = getattr(self, "_recording", None)
         if rec is not None:
             rec.append((a, self._kernels_of(flags)))
@@ -506,13 +507,14 @@ class SeirmEngine:
         self.exchange(self.cur)
 
     def step(self, state, t, noise, r_value, r_index, m_value, *, isolation=None, uniform=None, flags=None,
-             dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None, seed_ptr=None, check_range=True, dne_e_dr=None):
+             dne_dr=None, sum_dne_dr=None, death_count=None, recovered_step=None, seed_ptr=None, check_range=True, dne_e_dr=None,
+             step_skipped=None):
         """One fused step: transmission + progression + encode of step t+1; flips the live buffer."""
         flags = (nat.DO_TRANSMISSION | nat.DO_PROGRESSION | nat.DO_ENCODE) if flags is None else flags
         self.launch(state, flags=flags, t=t, t_encode=t + 1, noise=noise, isolation=isolation, uniform=uniform,
                     r_value=r_value, r_index=r_index, m_value=m_value, dne_dr=dne_dr, sum_dne_dr=sum_dne_dr,
                     death_count=death_count, recovered_step=recovered_step, seed_ptr=seed_ptr, check_range=check_range,
-                    dne_e_dr=dne_e_dr)
+                    dne_e_dr=dne_e_dr, step_skipped=step_skipped)
         if flags & nat.DO_ENCODE:
             self.cur = 1 - self.cur
             self.exchange(self.cur)
@@ -531,6 +533,8 @@ class SeirmEngine:
                 "ld": ld,
                 "dne_dr": torch.zeros((num_steps, ld), dtype=torch.float32, device=dev) if want_grad else None,
                 "dne_e": None,
+                # [t] = 1: the forward found the epidemic over at step t and left dne_dr[t] / dne_e[t] untouched (they mean zero)
+                "step_skipped": torch.zeros(num_steps, dtype=torch.int32, device=dev),
                 "recovered_step": torch.full((n,), 255, dtype=torch.uint8, device=dev),
                 "sum_dne_dr": torch.zeros(num_steps, dtype=torch.float32, device=dev),
                 "death_count": torch.zeros(num_steps, dtype=torch.float32, device=dev),
@@ -550,7 +554,9 @@ class SeirmEngine:
                None if noise.uniform_tensor is None else noise.uniform_tensor.data_ptr())
         sv["recovered_step"].fill_(255)
         self.over.zero_()
-        self._use_over = self.after_step is None     # (a hook may change stages behind the step kernels' back)
+        sv["step_skipped"].zero_()
+        # (a hook may change stages behind the step kernels' back; the overlapped exchange updates the word while a step runs)
+        self._use_over = self.after_step is None and not self.overlap
         try:
             if self.overlap:
                 return self._issue_episode_overlapped(state, num_steps, noise, sv, want_grad, t0)
@@ -582,7 +588,8 @@ class SeirmEngine:
                           dne_dr=sv["dne_dr"][k] if want_grad else None, sum_dne_dr=sv["sum_dne_dr"],
                           death_count=sv["death_count"], recovered_step=sv["recovered_step"], seed_ptr=self.seed_buf,
                           check_range=k + 1 < num_steps,
-                          dne_e_dr=sv["dne_e"][k] if (want_grad and self.want_table_grad and sv["dne_e"] is not None) else None)
+                          dne_e_dr=sv["dne_e"][k] if (want_grad and self.want_table_grad and sv["dne_e"] is not None) else None,
+                          step_skipped=sv["step_skipped"])
                 plan.append((*self._recording[-1], True))
                 if self.after_step is not None:
                     self.after_step(t)
@@ -705,7 +712,7 @@ class SeirmEngine:
         nat.check(self.lib.at_seirm_episode_backward(
             int(num_steps), int(self.graph.n_rows), int(sv["ld"]), _ptr(sv["dne_dr"]), _ptr(sv["recovered_step"]),
             _ptr(sv["sum_dne_dr"]), _ptr(sv["death_count"]), _ptr(gi), _ptr(gd), _ptr(mv), _ptr(grad_r), _ptr(grad_m),
-            _ptr(self.workspace), 0, ctypes.c_void_p(stream)))
+            _ptr(self.workspace), 0, _ptr(sv["step_skipped"], torch.int32), ctypes.c_void_p(stream)))
         self.launch_count += 1
         if self.pg is not None:
             import torch.distributed as dist
@@ -739,7 +746,10 @@ class SeirmEngine:
         grad_sfs = torch.zeros(len(self.spec.sfs), dtype=torch.float64, device=dev)
         ge = torch.zeros((), dtype=torch.float64, device=dev)
         gi2 = torch.zeros((), dtype=torch.float64, device=dev)
+        skipped = sv["step_skipped"].cpu().tolist()                    # steps the forward skipped: their rows mean zero
         for t in range(T):                                             # one (N,) pass per step keeps the temporaries small
+            if skipped[t]:
+                continue
             w = (gi[t] + c_rec) * r[t]
             d = sv["dne_dr"][t, :n].double() * w
             e = sv["dne_e"][t, :n].double() * w

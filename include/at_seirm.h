@@ -205,7 +205,10 @@ typedef struct at_seirm_launch {
                                    returns at once.  Zeroed by the caller before the first launch of an episode; maintained by the
                                    launches themselves when over_local != 0 (one GPU), else by at_seirm_exchange_sparse */
     int32_t over_local;
-    int32_t reserve_sms;        /* stream layout, != 0: the step kernels leave 1/8 of every SM's registers free (lean gather entry
+    int32_t reserve_sms;
+    int32_t* step_skipped;      /* or NULL: [t] = 1 if this (stream-layout) launch found the epidemic over on entry and therefore
+                                   did NOT touch dne_dr / dne_e_dr of step t (they are all zero by meaning; the backward pass skips
+                                   the step), else 0 */        /* stream layout, != 0: the step kernels leave 1/8 of every SM's registers free (lean gather entry
                                    point, 7 instead of 8 update CTAs per SM), so that a halo exchange issued on another stream runs
                                    beside them instead of waiting for them (they otherwise take every register of every SM) */
 } at_seirm_launch;
@@ -241,14 +244,15 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
  *   grad_r[t] = g_daily_infected[t] * sum_dne_dr[t]
  *             + sum_i dne_dr[t,i] * g_daily_deaths[recovered_step[i]] * M / 2
  *   grad_m[0] = sum_t g_daily_deaths[t] * death_count[t]
- * dne_dr is (T, ld) row-major with the first n_rows entries of each row used.
+ * dne_dr is (T, ld) row-major with the first n_rows entries of each row used.  step_skipped (or NULL): steps whose dne_dr row
+ * was left untouched by the forward because the epidemic was over (at_seirm_launch.step_skipped); they count as all zero.
  */
 int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld,
                               const float* dne_dr, const uint8_t* recovered_step,
                               const float* sum_dne_dr, const float* death_count,
                               const float* g_daily_infected, const float* g_daily_deaths,
                               const float* m_value, float* grad_r, float* grad_m,
-                              void* workspace, int32_t grid, void* stream);
+                              void* workspace, int32_t grid, const int32_t* step_skipped, void* stream);
 
 /*
  * at_seirm_hot_from_code — multi-GPU helper: after the ranks' code slices have been all-gathered (the per-step halo

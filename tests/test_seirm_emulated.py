@@ -41,7 +41,7 @@ def engine_on_host(emulated_library, monkeypatch):
     monkeypatch.setattr(_native, "_lib", None)              # the next user loads the real library again
 
 
-def _episode(g, *, packed=True, tensor_noise=False, **engine_kw):
+def _episode(g, *, packed=True, tensor_noise=False, before=None, **engine_kw):
     from agenttorch_b200.engine import NoiseSpec, SeirmEngine, SeirmSpec, SeirmState
     from agenttorch_b200.graph import build_contact_graph, mean_interactions_from_age
 
@@ -62,6 +62,13 @@ def _episode(g, *, packed=True, tensor_noise=False, **engine_kw):
     eye = torch.eye(3)
     r_steps = torch.stack([(r2 * eye[int(t / 7)]).sum() for t in range(T)])
     m = torch.tensor(g["m"], dtype=torch.float32)
+    if before is not None:
+        # another episode on the SAME engine first (same population, other parameters / isolation mode): its saved-for-backward
+        # buffers, code buffers and "epidemic over" state must not leak into the episode that is checked
+        st_b = SeirmState.from_initial(before["stage0"].astype(np.float32), before["age"], T, torch.device("cpu"), packed=packed)
+        rb = torch.stack([(torch.tensor(before["r2"], dtype=torch.float32) * eye[int(t / 7)]).sum() for t in range(T)])
+        eng.run_episode(st_b, rb, torch.tensor(before["m"], dtype=torch.float32), T,
+                        NoiseSpec(seed=before["seed"], isolation=before["mode"], p_isolate=float(before["p_isolate"])), want_grad=True)
     sv = eng.run_episode(st, r_steps.detach(), m, T, noise, want_grad=True, cuda_graph=False)
     gr, gm = eng.episode_backward(sv, T, torch.from_numpy(g["gI"]), torch.from_numpy(g["gD"]), m)
     eng.check_errors()
@@ -143,6 +150,19 @@ def test_layers_and_table_gradients_match_reference_golden(engine_on_host, case,
     assert rel_err(g["ref_grad_SFI"][1:3], g_sfi.numpy()[1:3]) <= 1e-4
     if g["mode"] != "soft":
         assert rel_err(g["ref_grad_SFI"], g_sfi.numpy()) <= 1e-4
+
+
+@pytest.mark.parametrize("first,second,kw", [
+    ("synth3k_hard", "synth3k_soft", dict()),                        # a spreading epidemic, then one that is over after 9 steps
+    ("synth3k_soft", "synth3k_hard", dict(block_size=1024, tile_rows=256)),
+    ("synth3k_hard", "synth3k_soft", dict(layout="bcsr")),
+])
+def test_consecutive_episodes_do_not_leak_into_each_other(engine_on_host, first, second, kw):
+    """Once nobody is in E or I the stream layout skips the gather, the zero-fill of dne_dr and (one step later) of the code
+    buffers; whatever an EARLIER episode left in those buffers must then not show up in the results or the gradients."""
+    g = load_golden(second)
+    st, grad_r2, grad_m = _episode(g, before=load_golden(first), **kw)
+    _check(g, st, grad_r2, grad_m)
 
 
 def test_the_real_binding_is_restored_after_emulation():
