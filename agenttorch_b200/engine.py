@@ -670,7 +670,11 @@ class SeirmEngine:
         sv["r_steps"].copy_(r_steps.detach().reshape(-1)[:num_steps])
         sv["m_value"].copy_(m_value.detach().reshape(-1)[:1])
         self.seed_buf.fill_(_as_i64(noise.seed))
-        if not cuda_graph or self.after_step is not None or (self.pg is not None and self.code_hdl is None):
+        hook = self.after_step
+        if hook is not None and hasattr(hook, "prepare"):
+            hook.prepare()                   # the episode's noise seeds of the hook's launches, into the device words they read
+        capturable_hook = hook is None or hasattr(hook, "capture_key")
+        if not cuda_graph or not capturable_hook or (self.pg is not None and self.code_hdl is None):
             # (NCCL collectives are not captured: capturing them hung on this stack; without symmetric memory a
             # multi-GPU episode is issued launch by launch)
             self._issue_episode(state, num_steps, noise, sv, want_grad)
@@ -679,7 +683,8 @@ class SeirmEngine:
                state.stage.data_ptr(), state.next_stage_time.data_ptr(), state.infected_time.data_ptr(),
                state.age.data_ptr(), state.daily_infected.data_ptr(), state.daily_deaths.data_ptr(),
                None if noise.isolation_tensor is None else noise.isolation_tensor.data_ptr(),
-               None if noise.uniform_tensor is None else noise.uniform_tensor.data_ptr())
+               None if noise.uniform_tensor is None else noise.uniform_tensor.data_ptr(),
+               None if hook is None else hook.capture_key)
         entry = self._graphs.get(key)
         if entry is None:
             cur0 = self.cur

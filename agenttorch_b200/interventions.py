@@ -57,7 +57,7 @@ def _as_flag_bytes(t):
 
 
 def _quarantine(flags, t, seed, id_offset, p_start, p_break, days, infinity, stage, is_q, start_date, u_start, u_break,
-                start_action, break_action, is_q_out, start_date_out):
+                start_action, break_action, is_q_out, start_date_out, seed_ptr=None):
     n = is_q.numel()
     stage_f64 = 0
     if stage is not None:
@@ -67,7 +67,7 @@ def _quarantine(flags, t, seed, id_offset, p_start, p_break, days, infinity, sta
             stage = _f32(stage, "disease_stage")
     a = nat.QuarantineArgs(
         abi_version=nat.ABI_VERSION, flags=flags, t=int(t), stage_f64=stage_f64, n=n, id_offset=int(id_offset), seed=_u64(seed),
-        seed_ptr=None, p_start=float(p_start), p_break=float(p_break), quarantine_days=float(days), infinity_time=float(infinity),
+        seed_ptr=_ptr(seed_ptr), p_start=float(p_start), p_break=float(p_break), quarantine_days=float(days), infinity_time=float(infinity),
         stage=_ptr(stage), u_start=_ptr(u_start), u_break=_ptr(u_break), is_q_in=_ptr(is_q), start_date_in=_ptr(start_date),
         start_action=_ptr(start_action), break_action=_ptr(break_action), is_q_out=_ptr(is_q_out), start_date_out=_ptr(start_date_out))
     nat.check(nat.lib().at_iv_quarantine(a, _stream(is_q)))
@@ -109,23 +109,25 @@ def _(is_quarantined, quarantine_start_date, start_action, break_action, t, quar
 
 @torch.library.custom_op("agenttorch_b200::quarantine_step", mutates_args=("is_quarantined", "quarantine_start_date"))
 def quarantine_step(stage: Tensor, is_quarantined: Tensor, quarantine_start_date: Tensor, p_start: float, p_break: float,
-                    t: int, seed: int, id_offset: int, quarantine_days: float, infinity_time: float) -> None:
+                    t: int, seed: int, id_offset: int, quarantine_days: float, infinity_time: float, seed_ptr: Optional[Tensor] = None) -> None:
     """Policies + transition of one quarantine substep IN PLACE (float32 contiguous state), one launch, untouched 16-byte
-    groups are not written."""
+    groups are not written.  seed_ptr: one-element int64 device tensor that overrides `seed` (a captured CUDA graph is replayed
+    with another seed by rewriting it)."""
     for x in (is_quarantined, quarantine_start_date):
         _require_cuda("in-place state", x)
         if x.dtype != torch.float32 or not x.is_contiguous():
             raise RuntimeError("quarantine_step works in place on contiguous float32 CUDA tensors")
     _quarantine(nat.DECIDE | nat.APPLY, t, seed, id_offset, p_start, p_break, quarantine_days, infinity_time, stage.reshape(-1),
                 is_quarantined.view(-1), quarantine_start_date.view(-1), None, None, None, None, is_quarantined.view(-1),
-                quarantine_start_date.view(-1))
+                quarantine_start_date.view(-1), seed_ptr=seed_ptr)
 
 
-def _testing(flags, t, seed, id_offset, p_comply, inelig, delay, infinity, u_comply, is_q, accept, aw, rd, re, aw_o, rd_o, re_o):
+def _testing(flags, t, seed, id_offset, p_comply, inelig, delay, infinity, u_comply, is_q, accept, aw, rd, re, aw_o, rd_o, re_o,
+             seed_ptr=None):
     ref = is_q if is_q is not None else aw
     a = nat.TestingArgs(
         abi_version=nat.ABI_VERSION, flags=flags, t=int(t), reserved=0, n=ref.numel(), id_offset=int(id_offset), seed=_u64(seed),
-        seed_ptr=None, p_comply=float(p_comply), ineligible_days=float(inelig), result_delay_days=float(delay),
+        seed_ptr=_ptr(seed_ptr), p_comply=float(p_comply), ineligible_days=float(inelig), result_delay_days=float(delay),
         infinity_time=float(infinity), u_comply=_ptr(u_comply), is_q=_ptr(is_q), accept_action=_ptr(accept),
         awaiting_in=_ptr(aw), result_date_in=_ptr(rd), re_eligible_in=_ptr(re), awaiting_out=_ptr(aw_o), result_date_out=_ptr(rd_o),
         re_eligible_out=_ptr(re_o))
@@ -168,15 +170,15 @@ def _(awaiting_test_result, test_result_date, test_re_eligble_date, accept_actio
                          mutates_args=("awaiting_test_result", "test_result_date", "test_re_eligble_date"))
 def testing_step(is_quarantined: Tensor, awaiting_test_result: Tensor, test_result_date: Tensor, test_re_eligble_date: Tensor,
                  p_comply: float, t: int, seed: int, id_offset: int, ineligible_days: float, result_delay_days: float,
-                 infinity_time: float) -> None:
-    """Policy + transition of one testing substep IN PLACE, one launch."""
+                 infinity_time: float, seed_ptr: Optional[Tensor] = None) -> None:
+    """Policy + transition of one testing substep IN PLACE, one launch (seed_ptr: see quarantine_step)."""
     for x in (awaiting_test_result, test_result_date, test_re_eligble_date):
         _require_cuda("in-place state", x)
         if x.dtype != torch.float32 or not x.is_contiguous():
             raise RuntimeError("testing_step works in place on contiguous float32 CUDA tensors")
     aw, rd, re = awaiting_test_result.view(-1), test_result_date.view(-1), test_re_eligble_date.view(-1)
     _testing(nat.DECIDE | nat.APPLY, t, seed, id_offset, p_comply, ineligible_days, result_delay_days, infinity_time, None,
-             _f32(is_quarantined, "is_quarantined").reshape(-1), None, aw, rd, re, aw, rd, re)
+             _f32(is_quarantined, "is_quarantined").reshape(-1), None, aw, rd, re, aw, rd, re, seed_ptr=seed_ptr)
 
 
 # ------------------------------------------------------------------------------------------ SEIRMS progression

@@ -140,8 +140,14 @@ def plan_intervention_substeps(runner, extra_keys):
     if not still_fusable():
         return None
 
+    hook_cache = {}
+
     def make_hook(state):
-        calls = []
+        """hook(t): the in-place launches of step t.  hook.prepare(): once per episode, BEFORE the episode is issued or its CUDA
+        graph replayed — draws the episode's noise seeds (the policies' counters advance) and writes them to device words the
+        launches read (`seed_ptr`), so that a captured episode can be replayed with fresh noise.  hook.capture_key: everything a
+        captured launch sequence bakes in (tensor addresses, probabilities, durations)."""
+        calls, prepares, key = [], [], []
         for block in blocks:
             if block[0] == "quarantine":
                 _, obs_mod, start, brk, upd = block
@@ -150,12 +156,40 @@ def plan_intervention_substeps(runner, extra_keys):
                 is_q, date = in_place(state, tv["is_quarantined"]), in_place(state, tv["quarantine_start_date"])
                 p_start = scalar("p_start", get_by_path(state, re.split("/", iv["quarantine_start_prob"])))
                 p_break = scalar("p_break", get_by_path(state, re.split("/", iv["quarantine_break_prob"])))
+                key += ["q", stage.data_ptr(), is_q.data_ptr(), date.data_ptr(), p_start, p_break, start.id_offset,
+                        float(upd.quarantine_days), float(upd.INFINITY_TIME)]
+            else:
+                _, acc, upd = block
+                pv, tv = acc.input_variables, upd.input_variables
+                is_q = in_place(state, pv["is_quarantined"])
+                aw, rd, re_ = (in_place(state, tv[k]) for k in ("awaiting_test_result", "test_result_date", "test_re_eligble_date"))
+                p = scalar("p_comply", get_by_path(state, re.split("/", pv["test_compliance_prob"])))
+                key += ["t", is_q.data_ptr(), aw.data_ptr(), rd.data_ptr(), re_.data_ptr(), p, acc.id_offset,
+                        float(upd.test_ineligible_days), float(upd.test_result_delay_days), float(upd.INFINITY_TIME)]
+        key = tuple(key)
+        cached = hook_cache.get(key)
+        if cached is not None:
+            return cached
+        for block in blocks:
+            if block[0] == "quarantine":
+                _, obs_mod, start, brk, upd = block
+                iv, tv = obs_mod.input_variables, upd.input_variables
+                stage = get_by_path(state, re.split("/", iv["disease_stage"]))
+                is_q, date = in_place(state, tv["is_quarantined"]), in_place(state, tv["quarantine_start_date"])
+                p_start = scalar("p_start", get_by_path(state, re.split("/", iv["quarantine_start_prob"])))
+                p_break = scalar("p_break", get_by_path(state, re.split("/", iv["quarantine_break_prob"])))
+                seed_q = torch.zeros(1, dtype=torch.int64, device=is_q.device)
 
-                def run_quarantine(t, stage=stage, is_q=is_q, date=date, start=start, brk=brk, upd=upd, p_start=p_start, p_break=p_break):
-                    seed, seed_b = start.episode_seed(t), brk.episode_seed(t)
+                def prepare_quarantine(start=start, brk=brk, seed_q=seed_q):
+                    seed, seed_b = start.episode_seed(0), brk.episode_seed(0)
                     assert seed == seed_b
-                    iv_ops.quarantine_step(stage.detach(), is_q, date, p_start, p_break, t, seed, start.id_offset,
-                                           float(upd.quarantine_days), float(upd.INFINITY_TIME))
+                    seed_q.fill_(seed)
+
+                def run_quarantine(t, stage=stage, is_q=is_q, date=date, start=start, upd=upd, p_start=p_start, p_break=p_break,
+                                   seed_q=seed_q):
+                    iv_ops.quarantine_step(stage.detach(), is_q, date, p_start, p_break, t, 0, start.id_offset,
+                                           float(upd.quarantine_days), float(upd.INFINITY_TIME), seed_ptr=seed_q)
+                prepares.append(prepare_quarantine)
                 calls.append(run_quarantine)
             else:
                 _, acc, upd = block
@@ -163,16 +197,30 @@ def plan_intervention_substeps(runner, extra_keys):
                 is_q = in_place(state, pv["is_quarantined"])
                 aw, rd, re_ = (in_place(state, tv[k]) for k in ("awaiting_test_result", "test_result_date", "test_re_eligble_date"))
                 p = scalar("p_comply", get_by_path(state, re.split("/", pv["test_compliance_prob"])))
+                seed_t = torch.zeros(1, dtype=torch.int64, device=aw.device)
 
-                def run_testing(t, is_q=is_q, aw=aw, rd=rd, re_=re_, acc=acc, upd=upd, p=p):
-                    iv_ops.testing_step(is_q, aw, rd, re_, p, t, acc.episode_seed(t), acc.id_offset, float(upd.test_ineligible_days),
-                                        float(upd.test_result_delay_days), float(upd.INFINITY_TIME))
+                def prepare_testing(acc=acc, seed_t=seed_t):
+                    seed_t.fill_(acc.episode_seed(0))
+
+                def run_testing(t, is_q=is_q, aw=aw, rd=rd, re_=re_, acc=acc, upd=upd, p=p, seed_t=seed_t):
+                    iv_ops.testing_step(is_q, aw, rd, re_, p, t, 0, acc.id_offset, float(upd.test_ineligible_days),
+                                        float(upd.test_result_delay_days), float(upd.INFINITY_TIME), seed_ptr=seed_t)
+                prepares.append(prepare_testing)
                 calls.append(run_testing)
 
         def hook(t):
             for call in calls:
                 call(int(t))
+
+        def prepare():
+            for fn in prepares:
+                fn()
         hook.launches_per_step = len(calls)
+        hook.prepare = prepare
+        hook.capture_key = key
+        if len(hook_cache) > 4:
+            hook_cache.clear()
+        hook_cache[key] = hook
         return hook
 
     make_hook.still_fusable = still_fusable

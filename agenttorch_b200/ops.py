@@ -162,13 +162,20 @@ def seirm_episode(handle: int, stage: Tensor, next_stage_time: Tensor, infected_
     reductions saved for backward (sum_dne_dr, death_count); the (T,N) dne_dr and recovered_step buffers stay inside the engine
     until the next episode."""
     eng = get_engine(handle)
-    di = daily_infected.detach().clone()
-    dd = daily_deaths.detach().clone()
-    st = SeirmState(stage.view(-1), next_stage_time.view(-1), infected_time.view(-1), age.view(-1), di.view(-1), dd.view(-1))
+    # the kernels accumulate into engine-owned series buffers, so that a captured episode is found again whatever address the
+    # caller's (freshly cloned, autograd-carrying) series tensors happen to have
+    bufs = getattr(eng, "_series_bufs", None)
+    if bufs is None or bufs[0].numel() != daily_infected.numel() or bufs[1].numel() != daily_deaths.numel():
+        bufs = eng._series_bufs = (torch.zeros(daily_infected.numel(), dtype=torch.float32, device=daily_infected.device),
+                                   torch.zeros(daily_deaths.numel(), dtype=torch.float32, device=daily_deaths.device))
+    bufs[0].copy_(daily_infected.detach().reshape(-1))
+    bufs[1].copy_(daily_deaths.detach().reshape(-1))
+    st = SeirmState(stage.view(-1), next_stage_time.view(-1), infected_time.view(-1), age.view(-1), bufs[0], bufs[1])
     noise = _noise(seed, iso_mode, p_isolate, isolation, uniform)
     eng.want_table_grad = bool(want_table_grad)
     sv = eng.run_episode(st, r_steps, m_value, num_steps, noise, want_grad=want_grad, cuda_graph=cuda_graph)
-    return di, dd, sv["sum_dne_dr"].clone(), sv["death_count"].clone()
+    return (bufs[0].clone().view_as(daily_infected), bufs[1].clone().view_as(daily_deaths), sv["sum_dne_dr"].clone(),
+            sv["death_count"].clone())
 
 
 @seirm_episode.register_fake

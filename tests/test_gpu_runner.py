@@ -91,3 +91,46 @@ def test_fused_and_generic_paths_agree_and_reset_state(tmp_path):
     runner2, _, _ = _make_runner(g, tmp_path, "hash", fused=False)
     runner2.step(3)
     assert float(runner2.state["environment"]["daily_infected"].sum()) >= 0.0
+
+
+def test_fused_episode_learnable_tables(tmp_path):
+    """SFSusceptibility / SFInfector as differentiable environment tensors: loss.backward() through runner.step() fills their
+    gradients as the reference's autograd does (golden from the real reference, oracle/ref_harness/make_golden.py round2)"""
+    g = load_golden("synth3k_tables_soft")
+    runner, r2, m = _make_runner(g, tmp_path, "hash", fused=True)
+    env = runner.state["environment"]
+    env["SFSusceptibility"] = env["SFSusceptibility"].detach().clone().requires_grad_(True)
+    env["SFInfector"] = env["SFInfector"].detach().clone().requires_grad_(True)
+    runner.step(g["num_steps"])
+    assert runner.perf_stats["fused_episodes"] == 1
+    _check(g, runner, r2, m)
+    assert rel_err(g["ref_grad_SFS"], env["SFSusceptibility"].grad.cpu().numpy()) <= 1e-4
+    assert rel_err(g["ref_grad_SFI"][1:3], env["SFInfector"].grad.cpu().numpy().reshape(-1)[1:3]) <= 1e-4
+
+
+def test_repeated_fused_episodes_with_restore_state(tmp_path):
+    """the same runner, restored and stepped again with other parameters (CUDA-graph replay; the 'epidemic over' short cuts leave
+    dne_dr and the code buffers of late steps untouched): every episode must come out as on a fresh runner"""
+    from agenttorch_b200.core.snapshot import PackedSnapshot
+
+    g_soft = load_golden("synth3k_soft")
+    runner, r2, m = _make_runner(g_soft, tmp_path, "hash", fused=True)
+    cit, env = runner.state["agents"]["citizens"], runner.state["environment"]
+    snap = PackedSnapshot({"agents": {"citizens": {k: cit[k].clone() for k in ("disease_stage", "next_stage_time", "infected_time")}},
+                           "environment": {"daily_infected": env["daily_infected"].clone(), "daily_deaths": env["daily_deaths"].clone()}},
+                          compact={"disease_stage": torch.uint8, "next_stage_time": torch.int16, "infected_time": torch.int16})
+    dev = runner.initializer.device
+    for rep in range(3):
+        runner.restore_state(snap)
+        if rep == 1:                                                 # a very different episode in between: R2 x 6
+            big = torch.tensor(g_soft["r2"] * 6, dtype=torch.float32, device=dev, requires_grad=True)
+            runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": big})
+            runner.step(g_soft["num_steps"])
+            runner.state["environment"]["daily_infected"].sum().backward()
+            continue
+        r2 = torch.tensor(g_soft["r2"], dtype=torch.float32, device=dev, requires_grad=True)
+        m = torch.tensor(g_soft["m"], dtype=torch.float32, device=dev, requires_grad=True)
+        runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": r2,
+                                "initializer.transition_function.1.seirm_progression.learnable_args.M": m})
+        runner.step(g_soft["num_steps"])
+        _check(g_soft, runner, r2, m)

@@ -199,17 +199,34 @@ def test_fused_episode_with_intervention_substeps(tmp_path):
     runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": r2,
                             "initializer.transition_function.1.seirm_progression.learnable_args.M": m})
     Tn = g["num_steps"]
-    runner.step(Tn)
-    assert runner.perf_stats["fused_episodes"] == 1
     cit = runner.state["agents"]["citizens"]
-    for k in ("disease_stage", "next_stage_time", "is_quarantined", "quarantine_start_date", "awaiting_test_result",
-              "test_result_date", "test_re_eligble_date"):
-        got = cit[k].detach().cpu().numpy().reshape(-1).astype(np.float64)
-        assert np.array_equal(got, g["ref_" + k + "_history"][Tn - 1].astype(np.float64)), k
     env = runner.state["environment"]
-    di, dd = env["daily_infected"], env["daily_deaths"]
-    assert rel_err(g["ref_daily_infected"], di.detach().cpu().numpy()) <= 1e-5
-    assert rel_err(g["ref_daily_deaths"], dd.detach().cpu().numpy()) <= 1e-5
-    loss = (torch.from_numpy(g["gI"]).to(dev) * di.reshape(-1)).sum() + (torch.from_numpy(g["gD"]).to(dev) * dd.reshape(-1)).sum()
-    loss.backward()
-    assert rel_err(g["ref_grad_R2"], r2.grad.cpu().numpy()) <= 1e-4 and rel_err(g["ref_grad_M"], m.grad.cpu().numpy()) <= 1e-4
+    snapshot = {"agents": {"citizens": {k: v.detach().clone() for k, v in cit.items() if torch.is_tensor(v) and v.is_floating_point()}},
+                "environment": {k: env[k].detach().clone() for k in ("daily_infected", "daily_deaths")}}
+    from agenttorch_b200.models.covid.context import get_context
+
+    # twice: the first call captures the SEIRM launches AND the intervention launches of the episode into one CUDA graph (the
+    # hook's noise seeds live in device words), the second restores the state and replays it
+    for rep in range(2):
+        if rep:
+            runner.restore_state(snapshot)
+            r2 = torch.tensor(g["r2"], dtype=torch.float32, device=dev, requires_grad=True)
+            m = torch.tensor(g["m"], dtype=torch.float32, device=dev, requires_grad=True)
+            runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": r2,
+                                    "initializer.transition_function.1.seirm_progression.learnable_args.M": m})
+        runner.step(Tn)
+        assert runner.perf_stats["fused_episodes"] == rep + 1
+        cit = runner.state["agents"]["citizens"]
+        for k in ("disease_stage", "next_stage_time", "is_quarantined", "quarantine_start_date", "awaiting_test_result",
+                  "test_result_date", "test_re_eligble_date"):
+            got = cit[k].detach().cpu().numpy().reshape(-1).astype(np.float64)
+            assert np.array_equal(got, g["ref_" + k + "_history"][Tn - 1].astype(np.float64)), (rep, k)
+        env = runner.state["environment"]
+        di, dd = env["daily_infected"], env["daily_deaths"]
+        assert rel_err(g["ref_daily_infected"], di.detach().cpu().numpy()) <= 1e-5
+        assert rel_err(g["ref_daily_deaths"], dd.detach().cpu().numpy()) <= 1e-5
+        loss = (torch.from_numpy(g["gI"]).to(dev) * di.reshape(-1)).sum() + (torch.from_numpy(g["gD"]).to(dev) * dd.reshape(-1)).sum()
+        loss.backward()
+        assert rel_err(g["ref_grad_R2"], r2.grad.cpu().numpy()) <= 1e-4 and rel_err(g["ref_grad_M"], m.grad.cpu().numpy()) <= 1e-4
+    engine = get_context(runner.config, runner.state, tf["0"]["new_transmission"].input_variables).engine
+    assert len(engine._graphs) == 1                                  # captured once (with the hook's launches), replayed once
