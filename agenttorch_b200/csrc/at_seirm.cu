@@ -1557,12 +1557,25 @@ seirm_episode_bwd_kernel(int T, int64_t n, int64_t ld, const float* __restrict__
         const float c = (i < n) ? s_gd[rstep[i]] : 0.f;
         uint32_t mask = __ballot_sync(0xffffffffu, c != 0.f);
         while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1u;
-            const float ci = __shfl_sync(0xffffffffu, c, src);
-            const int64_t agent = g * 32 + src;
-            if (lane < T && !skip0) acc0 += (double)(dne[(int64_t)lane * ld + agent] * ci);
-            if (lane + 32 < T && !skip1) acc1 += (double)(dne[(int64_t)(lane + 32) * ld + agent] * ci);
+            // four recovered agents per round: their (independent) loads are in flight together, the adds keep agent order
+            float ci[4], v0[4], v1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ci[j] = 0.f; v0[j] = 0.f; v1[j] = 0.f;
+                if (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    ci[j] = __shfl_sync(0xffffffffu, c, src);
+                    const int64_t agent = g * 32 + src;
+                    if (lane < T && !skip0) v0[j] = dne[(int64_t)lane * ld + agent];
+                    if (lane + 32 < T && !skip1) v1[j] = dne[(int64_t)(lane + 32) * ld + agent];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc0 += (double)(v0[j] * ci[j]);
+                acc1 += (double)(v1[j] * ci[j]);
+            }
         }
     }
     s_acc[warp][lane] = acc0;

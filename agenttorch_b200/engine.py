@@ -674,7 +674,7 @@ class SeirmEngine:
         if hook is not None and hasattr(hook, "prepare"):
             hook.prepare()                   # the episode's noise seeds of the hook's launches, into the device words they read
         capturable_hook = hook is None or hasattr(hook, "capture_key")
-        if not cuda_graph or not capturable_hook or (self.pg is not None and self.code_hdl is None):
+        if not cuda_graph or not capturable_hook or self.device.type != "cuda" or (self.pg is not None and self.code_hdl is None):
             # (NCCL collectives are not captured: capturing them hung on this stack; without symmetric memory a
             # multi-GPU episode is issued launch by launch)
             self._issue_episode(state, num_steps, noise, sv, want_grad)
