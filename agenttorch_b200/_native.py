@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libat_seirm.so")
 SRC_PATH = os.path.join(_PKG, "csrc", "at_seirm.cu")
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_SFS, MAX_SFI, MAX_LAMGAMMA = 16, 8, 84
 TIMER_F32, TIMER_I16 = 0, 1
 AGE_F32, AGE_U8 = 0, 1
@@ -129,7 +129,7 @@ def lib():
         L.at_seirm_episode_backward.argtypes = [
             ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-            ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+            ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
         L.at_seirm_hot_from_code.restype = ctypes.c_int
         L.at_seirm_hot_from_code.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_int32, ctypes.c_void_p]

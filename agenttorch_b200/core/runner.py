@@ -280,8 +280,13 @@ class Runner(nn.Module):
         state = self.state
         ctx = get_context(self.config, state, iv)
 
+        split = plan.setdefault("_paths", {})             # "a/b/c" -> ["a", "b", "c"], once per plan
+
         def path(p):
-            return re.split("/", p)
+            parts = split.get(p)
+            if parts is None:
+                parts = split[p] = re.split("/", p)
+            return parts
 
         tensors = {}
         for name in ("disease_stage", "next_stage_time", "infected_time", "age"):

@@ -1006,19 +1006,26 @@ stream_gather_lean_kernel(const KModel m, const at_seirm_launch a, const int bm_
 // Second kernel of a stream-layout step: transmission decision + progression + encoding of the next step
 // (reference: transition.py:219-252, seirm_progression/transition.py:41-121).  A CTA takes whole row tiles and works in
 // phases that each touch only the rows that need them (most rows of a step need nothing but their zeroed outputs):
-//   0  zero-fill the tile's dne_dr / code_out / hot words with 128-bit stores; stage the tile's row bitmaps in shared memory
+//   0  zero-fill the tile's dne_dr / code_out / hot words with 128-bit stores; stage the tile's row bitmaps and (128-bit loads)
+//      susceptibility classes in shared memory.  The tile's record count and base were fetched one tile ahead and each
+//      thread's first two records are already in flight, so the dependent chain count -> records -> table costs no
+//      round trip of its own
 //   1  sum the tile's hit records (row in tile, source code) into one 64-bit FIXED-POINT lambda per row in shared memory
 //      (integer atomics: the order of the records does not matter, the sum is bitwise reproducible; scale 2^fx_shift chosen
 //      so that in-degree * largest term < 2^62)
 //   A  the exposure candidates (rows that received a record) are decided densely, one candidate per thread, whatever
 //      their position in the tile: noise, p = 1 - exp(-lambda), stage / timer writes, d ne / dR
-//   B  32-row tasks that hold a row in E or I: progression and the code of the next step, lane <-> row
+//   B  the tile's rows in E or I, compacted into a list (like the candidates): progression and the code of the next step,
+//      one row per thread, all timer loads of the tile in flight together
+// Measured on the 8.4 M-agent hot step (gather + update, float32 state): per-task phase B, scalar age loads, no prefetch
+// 254 us -> 201 us (profiles/r02_step_kernels_8p4M.md).
 // The per-row logic is the one of seirm_kernel's update_subtask (the generic kernel), restated for launches with
 // transmission (row bitmaps valid, no AT_DO_INIT).
 #define TU_THREADS 256
 #define TU_MAX_TASKS (AT_STREAM_MAX_TILE_ROWS / 32)
+#define TU_MIN_CTAS 6               // resident update CTAs per SM the register budget is cut for (40 registers; measured: 8 -> 6 CTAs: -5 % per hot step)
 template <bool TF32, bool GRAD>
-__global__ void __launch_bounds__(TU_THREADS, 8)
+__global__ void __launch_bounds__(TU_THREADS, TU_MIN_CTAS)
 stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
 {
     AT_DYNAMIC_SMEM(unsigned char, smem_raw, 128);
@@ -1035,7 +1042,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     uint8_t* s_age = reinterpret_cast<uint8_t*>(s_cand + a.tile_rows);
     __shared__ long long s_red[TU_THREADS / 32][3];
     __shared__ uint32_t s_w[3][TU_MAX_TASKS], s_orig[3][TU_MAX_TASKS], s_hot[TU_MAX_TASKS];   // sus / exp / inf words of the tile
-    __shared__ int s_is_last, s_any_out, s_any_ei, s_ncand;
+    __shared__ int s_is_last, s_any_out, s_any_ei, s_ncand, s_nei;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = TU_THREADS / 32;
     const bool age_f32 = a.age_dtype == AT_AGE_F32;
@@ -1046,7 +1053,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     const uint64_t seed = a.seed_ptr ? *a.seed_ptr : a.seed;
     char* ws = reinterpret_cast<char*>(a.workspace);
 
-    if (tid == 0) { s_any_out = 0; s_any_ei = 0; s_ncand = 0; }
+    if (tid == 0) { s_any_out = 0; s_any_ei = 0; s_ncand = 0; s_nei = 0; }
     for (int c = tid; c < 256; c += TU_THREADS) {
         float av = 0.f, gv = 0.f;
         if (c >= 1 && c <= 3 * m.n_lg) {
@@ -1101,11 +1108,22 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
         return code;
     };
 
+    // a tile waits for its record count, then for its records: both are fetched early (count and base one tile ahead)
+    uint32_t nrec_next = 0u;
+    int64_t base_next = 0;
+    if ((int)blockIdx.x < n_tiles && over_in < 1) { nrec_next = a.tile_count[blockIdx.x]; base_next = a.tile_rec_base[blockIdx.x]; }
     for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
         const int row_base = tile * tile_rows;
         const int rows_here = min(tile_rows, n_rows - row_base);        // valid rows of the tile (<= 0: padding only)
         if (over_in >= 1 && skip_codes && (skip_saved || !GRAD)) break;     // nothing left to do for any tile
-        const uint32_t nrec = (over_in >= 1) ? 0u : a.tile_count[tile];
+        const uint32_t nrec = nrec_next;
+        const uint32_t* recs = a.rec + base_next;
+        uint32_t rec0 = 0u, rec1 = 0u;
+        if ((uint32_t)tid < nrec) rec0 = recs[tid];
+        if ((uint32_t)tid + TU_THREADS < nrec) rec1 = recs[tid + TU_THREADS];
+        const int next_tile = tile + (int)gridDim.x;
+        nrec_next = 0u;
+        if (next_tile < n_tiles && over_in < 1) { nrec_next = a.tile_count[next_tile]; base_next = a.tile_rec_base[next_tile]; }
         // ---- phase 0: outputs of rows that need nothing, bitmaps of the tile
         if (GRAD && !skip_saved) {
             float4* d4 = reinterpret_cast<float4*>(a.dne_dr + row_base);
@@ -1136,6 +1154,29 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
             if (do_enc && !skip_codes && task * 32 < n_rows) hot_out[task] = 0u;     // (words of padding rows belong to somebody else)
         }
         if (nrec != 0u) {
+            const bool full = rows_here == tile_rows;
+            if (full && age_f32 && ((reinterpret_cast<uintptr_t>(a.age) & 15) == 0)) {
+                const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.age) + row_base);
+                uint32_t* s_age4 = reinterpret_cast<uint32_t*>(s_age);
+                const int hi = m.n_sfs - 1;
+                for (int i = tid; i * 4 < tile_rows; i += TU_THREADS) {
+                    const float4 v = a4[i];
+                    const int a0 = min(max((int)v.x, 0), hi), a1 = min(max((int)v.y, 0), hi);
+                    const int a2 = min(max((int)v.z, 0), hi), a3 = min(max((int)v.w, 0), hi);
+                    s_age4[i] = (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)a2 << 16) | ((uint32_t)a3 << 24);
+                }
+                for (int i = tid; i < tile_rows; i += TU_THREADS) { s_lam[i] = 0ll; if (want_e) s_lamE[i] = 0ll; }
+            } else if (full && !age_f32 && ((reinterpret_cast<uintptr_t>(a.age) & 15) == 0)) {
+                const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.age) + row_base);
+                uint4* s_age16 = reinterpret_cast<uint4*>(s_age);
+                const uint32_t hi4 = (uint32_t)(m.n_sfs - 1) * 0x01010101u;
+                for (int i = tid; i * 16 < tile_rows; i += TU_THREADS) {
+                    uint4 v = a4[i];
+                    v.x = __vminu4(v.x, hi4); v.y = __vminu4(v.y, hi4); v.z = __vminu4(v.z, hi4); v.w = __vminu4(v.w, hi4);
+                    s_age16[i] = v;
+                }
+                for (int i = tid; i < tile_rows; i += TU_THREADS) { s_lam[i] = 0ll; if (want_e) s_lamE[i] = 0ll; }
+            } else
             for (int i = tid; i < tile_rows; i += TU_THREADS) {
                 s_lam[i] = 0ll;
                 if (want_e) s_lamE[i] = 0ll;
@@ -1146,9 +1187,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
         __syncthreads();
         if (nrec != 0u) {
             // ---- phase 1: records -> fixed-point lambda per row
-            const uint32_t* recs = a.rec + a.tile_rec_base[tile];
-            for (uint32_t i = tid; i < nrec; i += TU_THREADS) {
-                const uint32_t rec = recs[i];                 // (layer << 24) | (row in tile << 8) | code
+            auto add_record = [&](const uint32_t rec) {       // (layer << 24) | (row in tile << 8) | code
                 const int r = (int)((rec >> 8) & 0x7FFu), code = (int)(rec & 255u);
                 const long long v = s_fix[((int)(rec >> 24) * m.n_sfs + (int)s_age[r]) * NC + code];
                 if (v != 0ll) {
@@ -1159,7 +1198,10 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
                     const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(s_lam) + r, (unsigned long long)v);
                     if (old == 0ull) s_cand[atomicAdd(&s_ncand, 1)] = (uint16_t)r;
                 }
-            }
+            };
+            if ((uint32_t)tid < nrec) add_record(rec0);
+            if ((uint32_t)tid + TU_THREADS < nrec) add_record(rec1);
+            for (uint32_t i = tid + 2 * TU_THREADS; i < nrec; i += TU_THREADS) add_record(recs[i]);
             __syncthreads();
             if (tid == 0) a.tile_count[tile] = 0u;
             const int ncand = s_ncand;
@@ -1210,48 +1252,57 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
             __syncthreads();
             if (tid == 0) s_ncand = 0;
         }
-        // ---- phase B: tasks with a row in E or I (timers written in phase A are visible: same CTA, after the barrier)
-        for (int tk = warp; tk < tpt; tk += nw) {
-            const uint32_t exp_w = s_w[1][tk], inf_w = s_w[2][tk];
-            const uint32_t frac_hot = s_hot[tk];
-            if ((exp_w | inf_w) == 0u) {
-                if (frac_hot != 0u && lane == 0) { hot_out[tile * tpt + tk] = frac_hot; s_any_out = 1; }
-                continue;
-            }
-            const int task = tile * tpt + tk;
-            const int row = task * 32 + lane;
-            bool is_e = (exp_w >> lane) & 1u, is_i = (inf_w >> lane) & 1u;
-            uint32_t code = 0;
-            if (is_e || is_i) {
-                int nst = (do_prog || lookahead) ? ld_timer(a.next_stage_time, row) : 0;     // both timers in flight together
-                const int itime = do_enc ? ld_timer(a.infected_time, row) : 0;
-                if (do_prog) {
-                    if (nst <= t) {                              // progression (seirm_progression/transition.py:41-88)
-                        if (is_i) {
-                            acc_dead += 1;                      // stage * rd / INFECTED_VAR = 2/2
-                            if (a.recovered_step) a.recovered_step[row] = (uint8_t)t;
-                        }
-                        if (nst == t) { nst = is_i ? m.inf_time : t + m.i2r; st_timer(a.next_stage_time, row, nst); }
-                        a.stage[row] = is_i ? 3.0f : 2.0f;
-                        const bool was_e = is_e;
-                        is_e = false;
-                        is_i = was_e;
-                    }
+        // ---- phase B: the tile's rows in E or I, compacted into a list so that every row has its own thread and all timer loads
+        //      of the tile are in flight together (timers written in phase A are visible: same CTA, after the barrier)
+        if (tid < tpt) {
+            const uint32_t ew = s_w[1][tid];
+            uint32_t ei = ew | s_w[2][tid];
+            if (ei != 0u) {
+                int at = atomicAdd(&s_nei, __popc(ei));
+                while (ei != 0u) {
+                    const int b = __ffs((int)ei) - 1;
+                    ei &= ei - 1u;
+                    s_cand[at++] = (uint16_t)((tid * 32 + b) | (((ew >> b) & 1u) << 15));     // row in tile (< 2048), bit 15: in E
                 }
-                bool ce = is_e, ci = is_i;                       // classes the code is computed for
-                if (lookahead && (is_e || is_i) && nst <= a.t_encode - 1) { ci = ce; ce = false; }   // after the progression of t_encode-1
-                if (do_enc && (ce || ci)) code = encode(ce ? 1 : 2, itime);
-            }
-            const uint32_t hot = __ballot_sync(0xffffffffu, code != 0u) | frac_hot;
-            if (code != 0u) code_out[row] = (uint8_t)code;
-            const uint32_t exp_o = __ballot_sync(0xffffffffu, is_e);
-            const uint32_t inf_o = __ballot_sync(0xffffffffu, is_i);
-            if (lane == 0) {
-                if (do_enc && hot != 0u) { hot_out[task] = hot; s_any_out = 1; }     // benign race: every writer stores 1
-                s_w[1][tk] = exp_o; s_w[2][tk] = inf_o;
             }
         }
         __syncthreads();
+        {
+            const int nei = s_nei;
+            for (int i = tid; i < nei; i += TU_THREADS) {
+                const int entry = (int)s_cand[i];
+                const int r = entry & 0x7FF;
+                const int row = row_base + r;
+                const uint32_t bit = 1u << (r & 31);
+                bool is_e = (entry >> 15) != 0, is_i = !is_e;
+                int nst = (do_prog || lookahead) ? ld_timer(a.next_stage_time, row) : 0;     // both timers in flight together
+                const int itime = do_enc ? ld_timer(a.infected_time, row) : 0;
+                if (do_prog && nst <= t) {                   // progression (seirm_progression/transition.py:41-88)
+                    if (is_i) {
+                        acc_dead += 1;                      // stage * rd / INFECTED_VAR = 2/2
+                        if (a.recovered_step) a.recovered_step[row] = (uint8_t)t;
+                        atomicAnd(&s_w[2][r >> 5], ~bit);                             // I -> R
+                    } else {
+                        atomicAnd(&s_w[1][r >> 5], ~bit);                             // E -> I
+                        atomicOr(&s_w[2][r >> 5], bit);
+                    }
+                    if (nst == t) { nst = is_i ? m.inf_time : t + m.i2r; st_timer(a.next_stage_time, row, nst); }
+                    a.stage[row] = is_i ? 3.0f : 2.0f;
+                    const bool was_e = is_e;
+                    is_e = false;
+                    is_i = was_e;
+                }
+                bool ce = is_e, ci = is_i;                       // classes the code is computed for
+                if (lookahead && (is_e || is_i) && nst <= a.t_encode - 1) { ci = ce; ce = false; }   // after the progression of t_encode-1
+                if (do_enc && (ce || ci)) {
+                    const uint32_t code = encode(ce ? 1 : 2, itime);
+                    if (code != 0u) { code_out[row] = (uint8_t)code; atomicOr(&s_hot[r >> 5], bit); }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_nei = 0;
+        if (tid < tpt && do_enc && s_hot[tid] != 0u) { hot_out[tile * tpt + tid] = s_hot[tid]; s_any_out = 1; }   // benign race
         // ---- the tile's bitmap words that changed; hot words of tasks without a hot row
         if (tid < tpt) {
             const int task = tile * tpt + tid;
@@ -1304,6 +1355,86 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
             *he = 0u;
         }
         *ticket = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------ initial encode
+// flags == AT_DO_ENCODE | AT_DO_INIT, the first launch of every episode: the S / E / I row bitmaps from the stage array, the
+// infectiousness code and hot bitmap of step t_encode (same results as the generic kernel's update-only pass).  One streaming
+// pass: a warp takes 128 rows per round, four independent 128-byte loads of the stage array in flight per warp; the
+// timers are read only for rows that are infectious (E, I or a fractional stage, Q4).
+template <bool TF32>
+__global__ void __launch_bounds__(256)
+init_encode_kernel(KModel m, at_seirm_launch a)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_any_out, s_any_ei;
+    if (tid == 0) { s_any_out = 0; s_any_ei = 0; }
+    __syncthreads();
+    char* ws = reinterpret_cast<char*>(a.workspace);
+    const int ntasks32 = (int)(a.n_rows_pad >> 5);
+    const int nquad = (ntasks32 + 3) >> 2;
+    for (int q = (int)blockIdx.x * 8 + warp; q < nquad; q += (int)gridDim.x * 8) {
+        float st[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t row = ((int64_t)q * 4 + j) * 32 + lane;
+            st[j] = row < a.n_rows ? a.stage[row] : 3.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int task = q * 4 + j;
+            const int64_t row = (int64_t)task * 32 + lane;
+            const bool valid = row < a.n_rows;
+            const float stage = st[j];
+            const bool is_s = stage == 0.0f, is_e = stage == 1.0f, is_i = stage == 2.0f;
+            // infectious = 0 < stage < 3; fractional stages (soft isolation, Q4) index SFInfector[0]
+            const bool frac = stage > 0.0f && stage < 3.0f && !(is_e || is_i);
+            uint32_t code = 0;
+            if (is_e || is_i || frac) {
+                const int itime = load_timer(a.infected_time, row, TF32);
+                const int sidx = is_e ? 1 : (is_i ? 2 : (int)stage);
+                int idx = a.t_encode - itime - 1;
+                if (idx < 0 || idx >= m.n_lg) {
+                    if (a.error_flag && sidx < m.n_sfi && m.sfi[sidx] != 0.f) *a.error_flag = 1;
+                    idx = idx < 0 ? 0 : m.n_lg - 1;
+                }
+                code = 1u + (uint32_t)(sidx * m.n_lg + idx);
+                const float av = sidx < m.n_sfi ? m.sfi[sidx] : 0.f;
+                if (av == 0.f || m.lg[idx] == 0.f) code = 0;            // contributes exactly 0 to every lambda
+            }
+            const uint32_t hot = __ballot_sync(0xffffffffu, code != 0u);
+            const uint32_t sus_o = __ballot_sync(0xffffffffu, is_s);
+            const uint32_t exp_o = __ballot_sync(0xffffffffu, is_e);
+            const uint32_t inf_o = __ballot_sync(0xffffffffu, is_i);
+            if (valid) a.code_out[a.row_offset + row] = (uint8_t)code;
+            if (lane == 0 && task < ntasks32) {
+                if ((int64_t)task * 32 < a.n_rows) {                    // (hot words of padding tasks belong to somebody else)
+                    a.hot_bitmap_out[(a.row_offset >> 5) + task] = hot;
+                    if (hot != 0u) s_any_out = 1;                       // benign race: every writer stores 1
+                }
+                if ((exp_o | inf_o) != 0u) s_any_ei = 1;
+                a.sus_bitmap[task] = sus_o;
+                a.exp_bitmap[task] = exp_o;
+                a.inf_bitmap[task] = inf_o;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_any_out) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_ANYHOT) + a.xchg_slot, 1u);
+        if (s_any_ei) atomicOr(reinterpret_cast<unsigned int*>(ws + WS_HASEI) + a.xchg_slot, 1u);
+        __threadfence();
+        int* ticket = reinterpret_cast<int*>(ws + WS_TICKET);
+        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            if (a.over_state != nullptr && a.over_local) {
+                unsigned int* he = reinterpret_cast<unsigned int*>(ws + WS_HASEI) + a.xchg_slot;
+                *a.over_state = (*reinterpret_cast<volatile unsigned int*>(he) != 0u) ? 0 : 1;
+                *he = 0u;
+            }
+            *ticket = 0;
+        }
     }
 }
 
@@ -1531,12 +1662,15 @@ exchange_sparse_kernel(uint8_t* __restrict__ local, int64_t n_sources, uint32_t*
 #define AT_BWD_THREADS 256
 // Agents with c_i != 0 (they recovered inside the episode) are sparse: a warp scans 32 agents at a time and, for
 // every such agent, lane t fetches dne[t, agent] — lane <-> step, so no cross-lane reduction is needed until the end.
+// An agent is an exposure candidate only up to the step of its exposure (= its infected_time), so lanes t > infected_time
+// fetch nothing and agents infected before the episode (the seeds: most of those that recover inside it) are skipped.
 // Static assignment and fixed-order folds: deterministic.
 __global__ void __launch_bounds__(AT_BWD_THREADS)
 seirm_episode_bwd_kernel(int T, int64_t n, int64_t ld, const float* __restrict__ dne, const uint8_t* __restrict__ rstep,
                          const float* __restrict__ sum_dne, const float* __restrict__ death_count,
                          const float* __restrict__ gI, const float* __restrict__ gD, const float* __restrict__ m_value,
-                         float* grad_r, float* grad_m, char* ws, const int32_t* __restrict__ skipped)
+                         float* grad_r, float* grad_m, char* ws, const int32_t* __restrict__ skipped,
+                         const void* __restrict__ itime, int itime_f32)
 {
     __shared__ float s_gd[256];
     __shared__ double s_acc[AT_BWD_THREADS / 32][BWD_MAXT];
@@ -1555,7 +1689,9 @@ seirm_episode_bwd_kernel(int T, int64_t n, int64_t ld, const float* __restrict__
     for (int64_t g = (int64_t)blockIdx.x * (AT_BWD_THREADS / 32) + warp; g < ngroups; g += wstride) {
         const int64_t i = g * 32 + lane;
         const float c = (i < n) ? s_gd[rstep[i]] : 0.f;
-        uint32_t mask = __ballot_sync(0xffffffffu, c != 0.f);
+        int last = BWD_MAXT;                        // the last step at which this agent can have been an exposure candidate
+        if (itime != nullptr && c != 0.f) last = load_timer(itime, i, itime_f32 != 0);
+        uint32_t mask = __ballot_sync(0xffffffffu, c != 0.f && last >= 0);
         while (mask) {
             // four recovered agents per round: their (independent) loads are in flight together, the adds keep agent order
             float ci[4], v0[4], v1[4];
@@ -1566,9 +1702,10 @@ seirm_episode_bwd_kernel(int T, int64_t n, int64_t ld, const float* __restrict__
                     const int src = __ffs(mask) - 1;
                     mask &= mask - 1u;
                     ci[j] = __shfl_sync(0xffffffffu, c, src);
+                    const int upto = __shfl_sync(0xffffffffu, last, src);
                     const int64_t agent = g * 32 + src;
-                    if (lane < T && !skip0) v0[j] = dne[(int64_t)lane * ld + agent];
-                    if (lane + 32 < T && !skip1) v1[j] = dne[(int64_t)(lane + 32) * ld + agent];
+                    if (lane < T && !skip0 && lane <= upto) v0[j] = dne[(int64_t)lane * ld + agent];
+                    if (lane + 32 < T && !skip1 && lane + 32 <= upto) v1[j] = dne[(int64_t)(lane + 32) * ld + agent];
                 }
             }
 #pragma unroll
@@ -1781,7 +1918,7 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         // the more warps, the fewer registers each has for units in flight: 32 warps x 3 units, 24 x 5, <= 16 x 8 (KB per SM: 96 / 120 / 128)
         int rc;
         if (a.reserve_sms > 0) {
-            // leave room for a concurrent halo exchange: the lean gather (56 registers) here, 7 instead of 8 update CTAs per SM below
+            // leave room for a concurrent halo exchange: the lean gather (56 registers) here, one update CTA per SM fewer below
             auto k = stream_gather_lean_kernel;
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1794,7 +1931,7 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         else rc = launch_stream<512, 6>(km, al, grid, pw * 32, smem, words, NC, tile_shift, s);
         if (rc) return rc;
         al.edges_per_chunk = 512;
-        int tgrid = a.grid > 0 ? a.grid : g_sm_count * (a.reserve_sms > 0 ? 7 : 8);
+        int tgrid = a.grid > 0 ? a.grid : g_sm_count * (a.reserve_sms > 0 ? TU_MIN_CTAS - 1 : TU_MIN_CTAS);
         const int64_t n_tiles = a.n_rows_pad / a.tile_rows;
         if (tgrid > n_tiles) tgrid = (int)n_tiles;
         const size_t usmem = (size_t)km.n_layers * model->n_sfs * NC * 8 + 2 * 256 * 4 + (size_t)a.tile_rows * (a.dne_e_dr ? 19 : 11);
@@ -1825,6 +1962,16 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
         if (grid < 1) grid = 1;
         if (hashed) rc = dispatch<MODE_HASHED>(km, al, grid, warps * 32, smem_gather, bm_words, NC, G, s);
         else rc = dispatch<MODE_FUSED>(km, al, grid, warps * 32, smem_gather, bm_words, NC, G, s);
+    } else if (a.flags == (AT_DO_ENCODE | AT_DO_INIT)) {
+        // the first launch of an episode: a dedicated streaming pass
+        const int64_t nquad = (ntasks32 + 3) / 4;
+        int igrid = a.grid > 0 ? a.grid : g_sm_count * 8;
+        if (igrid > (nquad + 7) / 8) igrid = (int)((nquad + 7) / 8);
+        if (igrid < 1) igrid = 1;
+        if (a.timer_dtype == AT_TIMER_F32) AT_LAUNCH(init_encode_kernel<true>, igrid, 256, s, km, al);
+        else AT_LAUNCH(init_encode_kernel<false>, igrid, 256, s, km, al);
+        cudaError_t e = cudaGetLastError();
+        rc = (e != cudaSuccess) ? fail("init_encode_kernel launch: %s", cudaGetErrorString(e)) : 0;
     } else {
         al.edges_per_chunk = 512;
         rc = launch_kernel<MODE_UPDATE, 4>(km, al, ugrid, 256, smem_update, 0, NC, 8, s);
@@ -1849,7 +1996,8 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
 int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, const float* dne_dr, const uint8_t* recovered_step,
                               const float* sum_dne_dr, const float* death_count, const float* g_daily_infected,
                               const float* g_daily_deaths, const float* m_value, float* grad_r, float* grad_m,
-                              void* workspace, int32_t grid, const int32_t* step_skipped, void* stream) {
+                              void* workspace, int32_t grid, const int32_t* step_skipped,
+                              const void* infected_time, int32_t timer_dtype, void* stream) {
     if (num_steps < 1 || num_steps > BWD_MAXT) return fail("%s", "num_steps out of range (1..64)");
     if (!dne_dr || !recovered_step || !sum_dne_dr || !death_count || !g_daily_infected || !g_daily_deaths || !m_value || !grad_r || !grad_m || !workspace)
         return fail("%s", "null argument");
@@ -1860,7 +2008,8 @@ int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, con
     if (g > BWD_MAX_GRID) g = BWD_MAX_GRID;
     if (g < 1) g = 1;
     AT_LAUNCH(seirm_episode_bwd_kernel, g, AT_BWD_THREADS, (cudaStream_t)stream, num_steps, n_rows, ld, dne_dr, recovered_step, sum_dne_dr,
-        death_count, g_daily_infected, g_daily_deaths, m_value, grad_r, grad_m, (char*)workspace, step_skipped);
+        death_count, g_daily_infected, g_daily_deaths, m_value, grad_r, grad_m, (char*)workspace, step_skipped,
+        infected_time, timer_dtype == AT_TIMER_F32 ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("seirm_episode_bwd_kernel launch: %s", cudaGetErrorString(e));
     return 0;

@@ -38,7 +38,9 @@ class _EpisodeFn(torch.autograd.Function):
         factory = getattr(runner, "_after_step_factory", None)
         eng.after_step = factory(runner.state) if factory is not None else None      # episodes with a hook are issued eagerly
         try:
-            sv = eng.run_episode(st, r_steps, m_value, num_steps, noise, want_grad=want_grad, cuda_graph=eng.code_hdl is not None)
+            # the local series are zeroed inside the episode's (captured) launch sequence
+            sv = eng.run_episode(st, r_steps, m_value, num_steps, noise, want_grad=want_grad, cuda_graph=eng.code_hdl is not None,
+                                 zero_series=runner._series)
         finally:
             eng.after_step = None
         if eng.pg is not None:
@@ -59,7 +61,8 @@ class _EpisodeFn(torch.autograd.Function):
             return None, None, None, None, None
         T = ctx.num_steps
         gr, gm = ctx.runner.engine.episode_backward(ctx.sv, T, g_di.reshape(-1)[:T].contiguous(), g_dd.reshape(-1)[:T].contiguous(), m_value)
-        return None, gr.reshape(ctx.r_shape), gm.expand(m_value.numel()).reshape(ctx.m_shape).clone(), None, None
+        g_m = gm.reshape(ctx.m_shape) if m_value.numel() == 1 else gm.expand(m_value.numel()).reshape(ctx.m_shape).clone()
+        return None, gr.reshape(ctx.r_shape), g_m, None, None
 
 
 class DistributedRunner:
@@ -134,9 +137,9 @@ class DistributedRunner:
                                   code_len=shard_code_len(n, world) if world > 1 else None)
         f32 = lambda t: t.reshape(-1)[r0:r1].to(torch.float32).clone().contiguous()          # noqa: E731
         dev = edge_index.device
+        self._series = torch.zeros((2, T), dtype=torch.float32, device=dev)      # this rank's share of the two daily series
         self.local_state = SeirmState(f32(var("disease_stage")), f32(var("next_stage_time")), f32(var("infected_time")),
-                                      f32(var("age")), torch.zeros(T, dtype=torch.float32, device=dev),
-                                      torch.zeros(T, dtype=torch.float32, device=dev))
+                                      f32(var("age")), self._series[0], self._series[1])
         # the public state holds the LOCAL slices of the agent tensors (reference: _slice_agent_tensors, :126-144)
         cit = full["agents"][self.config["substeps"]["0"]["active_agents"][0]]
         for k, v in list(cit.items()):
@@ -204,9 +207,6 @@ class DistributedRunner:
         r_steps = self.tr.r_steps(T)
         m_value = self.pg_mod.m_tensor()
         want_grad = bool(r_steps.requires_grad or m_value.requires_grad) and torch.is_grad_enabled()
-        st = self.local_state
-        st.daily_infected.zero_()
-        st.daily_deaths.zero_()
         env = self.state["environment"]
         di, dd = _EpisodeFn.apply(self, r_steps, m_value, T, want_grad)
         self.engine.poll_errors()                 # device-side error flag of an earlier episode (no host synchronisation)

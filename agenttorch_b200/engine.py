@@ -331,6 +331,7 @@ class SeirmEngine:
         self.workspace = torch.zeros(self.lib.at_seirm_workspace_bytes() // 8 + 8, dtype=torch.float64, device=dev)
         self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.seed_buf = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._seed_value = 0                 # what seed_buf holds (set_seed skips the fill when an episode repeats a seed)
         self.launch_count = 0
         self._graphs = {}
         self._saved = {}
@@ -500,6 +501,13 @@ class SeirmEngine:
         self.launch_count += 1
 
     # ----------------------------------------------------------------------------- substeps
+    def set_seed(self, seed):
+        """The noise seed the step kernels read from device memory (so that a captured episode serves any seed)."""
+        v = _as_i64(seed)
+        if v != self._seed_value:
+            self.seed_buf.fill_(v)
+            self._seed_value = v
+
     def encode(self, state, t):
         """(Re)derive the row bitmaps from `state.stage` and write the infectiousness code/bitmap of step `t`
         into the live buffer: the first launch on a state, or after the caller edited it."""
@@ -543,7 +551,7 @@ class SeirmEngine:
             }
         return self._saved[key]
 
-    def _issue_episode(self, state, num_steps, noise, sv, want_grad, t0=0):
+    def _issue_episode(self, state, num_steps, noise, sv, want_grad, t0=0, zero_series=None):
         """Issue the 1 + num_steps launches of an episode.  The filled launch structs are cached per (buffers, modes),
         so that re-issuing an episode costs one ctypes call per step (matters when the episode cannot be replayed from
         a CUDA graph, i.e. with the NCCL halo exchange between the steps)."""
@@ -555,14 +563,19 @@ class SeirmEngine:
         sv["recovered_step"].fill_(255)
         self.over.zero_()
         sv["step_skipped"].zero_()
+        if zero_series is not None:
+            zero_series.zero_()
         # (a hook may change stages behind the step kernels' back; the overlapped exchange updates the word while a step runs)
         self._use_over = self.after_step is None and not self.overlap
         try:
             if self.overlap:
-                return self._issue_episode_overlapped(state, num_steps, noise, sv, want_grad, t0)
-            return self._issue_episode_sync(state, num_steps, noise, sv, want_grad, t0, key)
+                self._issue_episode_overlapped(state, num_steps, noise, sv, want_grad, t0)
+            else:
+                self._issue_episode_sync(state, num_steps, noise, sv, want_grad, t0, key)
         finally:
             self._use_over = False
+        if want_grad and sv.get("itime_valid"):
+            sv["itime_copy"].copy_(state.infected_time)       # for the backward pass (see episode_backward_packed)
 
     def _issue_episode_sync(self, state, num_steps, noise, sv, want_grad, t0, key):
         plan = self._plans.get(key)
@@ -652,13 +665,15 @@ class SeirmEngine:
             main.wait_stream(side)
         self.cur = 0
 
-    def run_episode(self, state, r_steps, m_value, num_steps, noise: NoiseSpec, want_grad=False, cuda_graph=False):
+    def run_episode(self, state, r_steps, m_value, num_steps, noise: NoiseSpec, want_grad=False, cuda_graph=False, zero_series=None):
         """Advance `state` in place through `num_steps` steps (t = 0..num_steps-1, as Runner.step does).
 
         r_steps: (num_steps,) float32 device tensor with the per-step R (transition.py:139-143);
         m_value: (1,) float32.  Returns the saved-for-backward buffers (views owned by the engine).
         With cuda_graph=True the launch sequence is captured once per (state buffers, shape) and
-        replayed; the seed, R and M are read from device memory so the graph is reusable."""
+        replayed; the seed, R and M are read from device memory so the graph is reusable.
+        zero_series: a tensor (normally the storage behind state.daily_infected / daily_deaths) to be zeroed as part of the
+        episode's launch sequence, so that the series come out as this episode's increments without a launch of the caller's."""
         if want_grad and num_steps > 64:
             raise ValueError("gradients through episodes of more than 64 steps are not supported (the fused backward kernel keeps "
                              "one accumulator per step and lane); run forward-only or split the episode")
@@ -667,9 +682,28 @@ class SeirmEngine:
             if self.graph.layout != 1:
                 raise NotImplementedError("gradients with respect to SFInfector need the stream layout")
             sv["dne_e"] = torch.zeros_like(sv["dne_dr"])
-        sv["r_steps"].copy_(r_steps.detach().reshape(-1)[:num_steps])
-        sv["m_value"].copy_(m_value.detach().reshape(-1)[:1])
-        self.seed_buf.fill_(_as_i64(noise.seed))
+        # (every tensor method here is a dispatcher call of several microseconds on the host: the common case - float32 (T,) and
+        # (1,) device tensors - goes through unchanged)
+        if want_grad:
+            it = state.infected_time
+            pool = sv.setdefault("itime_pool", {})
+            buf = pool.get((it.dtype, it.numel()))
+            if buf is None:                        # (kept for the engine's lifetime: captured episodes hold its address)
+                buf = pool[(it.dtype, it.numel())] = torch.empty_like(it)
+            sv["itime_copy"] = buf
+            sv["itime_valid"] = self.after_step is None and it.dtype in (torch.float32, torch.int16)
+        src_r = r_steps.detach() if r_steps.requires_grad else r_steps
+        src_m = m_value.detach() if m_value.requires_grad else m_value
+        if src_r.dim() != 1 or src_r.numel() != num_steps:
+            src_r = src_r.reshape(-1)[:num_steps]
+        if src_m.dim() != 1 or src_m.numel() != 1:
+            src_m = src_m.reshape(-1)[:1]
+        if src_r.dtype == torch.float32 and src_m.dtype == torch.float32 and src_r.device == src_m.device == sv["r_steps"].device:
+            torch._foreach_copy_([sv["r_steps"], sv["m_value"]], [src_r, src_m])          # one launch
+        else:
+            sv["r_steps"].copy_(src_r)
+            sv["m_value"].copy_(src_m)
+        self.set_seed(noise.seed)
         hook = self.after_step
         if hook is not None and hasattr(hook, "prepare"):
             hook.prepare()                   # the episode's noise seeds of the hook's launches, into the device words they read
@@ -677,9 +711,9 @@ class SeirmEngine:
         if not cuda_graph or not capturable_hook or self.device.type != "cuda" or (self.pg is not None and self.code_hdl is None):
             # (NCCL collectives are not captured: capturing them hung on this stack; without symmetric memory a
             # multi-GPU episode is issued launch by launch)
-            self._issue_episode(state, num_steps, noise, sv, want_grad)
+            self._issue_episode(state, num_steps, noise, sv, want_grad, zero_series=zero_series)
             return sv
-        key = (num_steps, want_grad, noise.isolation, noise.uniform, float(noise.p_isolate),
+        key = (num_steps, want_grad, None if zero_series is None else zero_series.data_ptr(), noise.isolation, noise.uniform, float(noise.p_isolate),
                state.stage.data_ptr(), state.next_stage_time.data_ptr(), state.infected_time.data_ptr(),
                state.age.data_ptr(), state.daily_infected.data_ptr(), state.daily_deaths.data_ptr(),
                None if noise.isolation_tensor is None else noise.isolation_tensor.data_ptr(),
@@ -692,7 +726,7 @@ class SeirmEngine:
             torch.cuda.synchronize(self.device)
             # capture issues no work; the replay below is the execution
             with torch.cuda.graph(g):
-                self._issue_episode(state, num_steps, noise, sv, want_grad)
+                self._issue_episode(state, num_steps, noise, sv, want_grad, zero_series=zero_series)
             entry = (g, cur0, self.cur)
             if len(self._graphs) >= 4:               # state tensors were re-created (reset_state): drop old captures
                 self._graphs.pop(next(iter(self._graphs)))
@@ -707,25 +741,37 @@ class SeirmEngine:
 
     def episode_backward(self, sv, num_steps, g_daily_infected, g_daily_deaths, m_value):
         """grad wrt the per-step R (num_steps,) and M (1,) — at_seirm_episode_backward."""
+        packed = self.episode_backward_packed(sv, num_steps, g_daily_infected, g_daily_deaths, m_value)
+        return packed[:num_steps], packed[num_steps:]
+
+    def episode_backward_packed(self, sv, num_steps, g_daily_infected, g_daily_deaths, m_value):
+        """(num_steps + 1,): dL/d(per-step R) followed by dL/dM."""
         dev = self.device
-        grad_r = torch.empty(num_steps, dtype=torch.float32, device=dev)
-        grad_m = torch.empty(1, dtype=torch.float32, device=dev)
-        gi = g_daily_infected.detach().reshape(-1)[:num_steps].to(torch.float32).contiguous()
-        gd = g_daily_deaths.detach().reshape(-1)[:num_steps].to(torch.float32).contiguous()
-        mv = m_value.detach().reshape(-1)[:1].to(torch.float32).contiguous()
+        packed = torch.empty(num_steps + 1, dtype=torch.float32, device=dev)      # [grad_r | grad_m]: one buffer, one all-reduce
+        grad_r, grad_m = packed[:num_steps], packed[num_steps:]
+        def plain(t, n):         # float32, contiguous, exactly n elements: the usual case costs no tensor operation
+            if t.dtype == torch.float32 and t.numel() == n and t.is_contiguous() and not t.requires_grad:
+                return t
+            return t.detach().reshape(-1)[:n].to(torch.float32).contiguous()
+
+        gi, gd, mv = plain(g_daily_infected, num_steps), plain(g_daily_deaths, num_steps), plain(m_value, 1)
+        # infected_time as the episode left it (copied by the episode's own launch sequence): an agent is an exposure candidate only
+        # up to its exposure, so the kernel fetches no dne_dr entry of later steps; not with an intervention hook, which may make
+        # an agent susceptible again
+        itime = sv.get("itime_copy") if sv.get("itime_valid") else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         nat.check(self.lib.at_seirm_episode_backward(
             int(num_steps), int(self.graph.n_rows), int(sv["ld"]), _ptr(sv["dne_dr"]), _ptr(sv["recovered_step"]),
             _ptr(sv["sum_dne_dr"]), _ptr(sv["death_count"]), _ptr(gi), _ptr(gd), _ptr(mv), _ptr(grad_r), _ptr(grad_m),
-            _ptr(self.workspace), 0, _ptr(sv["step_skipped"], torch.int32), ctypes.c_void_p(stream)))
+            _ptr(self.workspace), 0, _ptr(sv["step_skipped"], torch.int32),
+            None if itime is None else ctypes.c_void_p(itime.data_ptr()), nat.TIMER_F32 if (itime is not None and itime.dtype == torch.float32) else nat.TIMER_I16,
+            ctypes.c_void_p(stream)))
         self.launch_count += 1
         if self.pg is not None:
             import torch.distributed as dist
 
-            packed = torch.cat([grad_r, grad_m])               # one small all-reduce instead of two
             dist.all_reduce(packed, group=self.pg)
-            grad_r, grad_m = packed[:num_steps].clone(), packed[num_steps:].clone()
-        return grad_r, grad_m
+        return packed
 
     def table_gradients(self, sv, num_steps, g_daily_infected, g_daily_deaths, m_value, r_steps, age):
         """dL/dSFSusceptibility (n_sfs,) and dL/dSFInfector (n_sfi,) of an episode, from the buffers the forward saved — no per-edge
@@ -791,7 +837,8 @@ class SeirmEngine:
                 self.error_flag.zero_()
                 self._raise_for(code)
         self._err_host.copy_(self.error_flag, non_blocking=True)
-        self._err_event = torch.cuda.Event()
+        if self._err_event is None:
+            self._err_event = torch.cuda.Event()
         self._err_event.record(torch.cuda.current_stream(self.device))
 
     @staticmethod

@@ -19,6 +19,27 @@ from agenttorch_b200.core.substep import SubstepTransitionMessagePassing
 from agenttorch_b200.models.covid.context import as_kernel_f32, get_context
 
 
+class _StepR(torch.autograd.Function):
+    """r_steps[t] = (R2 * one_hot[week(t)]).sum() (transition.py:136-143), evaluated once per distinct week and gathered per step.
+    All weeks in one broadcast product and one row-wise sum (bit-identical to the reference's per-step expression on this device:
+    tools/probe_host.py compares the two on random R2); the Jacobian d r_steps / d R2 is a constant `jac` of shape
+    (T, *R2.shape), so backward is one product and one sum."""
+
+    @staticmethod
+    def forward(ctx, r, eye_used, pos, jac):
+        per_week = (r.detach().unsqueeze(0) * eye_used).flatten(1).sum(1)
+        ctx.jac = jac
+        return per_week.index_select(0, pos)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        jac = ctx.jac
+        if jac is None:
+            return None, None, None, None
+        return (jac * g.reshape(-1, *([1] * (jac.dim() - 1)))).sum(0), None, None, None
+
+
 class NewTransmission(SubstepTransitionMessagePassing):
     fusable = True
 
@@ -37,6 +58,7 @@ class NewTransmission(SubstepTransitionMessagePassing):
         self.episode_index = 0
         self.advance_seed = True          # a fresh noise stream per episode, like the reference's global RNG
         self.exposure_uniform = None
+        self._r_index = {}
 
     def r_tensor(self):
         return self.calibrate_R2 if self.calibration_mode else self.learnable_args["R2"]
@@ -47,11 +69,23 @@ class NewTransmission(SubstepTransitionMessagePassing):
         return (self.r_tensor() * self._week_one_hot[int(t / 7)]).sum()
 
     def r_steps(self, num_steps):
-        """(num_steps,) per-step R: `effective_r` evaluated once per distinct week, then indexed, so the
-        values are identical to the per-step evaluation."""
-        weeks = [int(t / 7) for t in range(num_steps)]
-        per_week = {w: self.effective_r(7 * w) for w in sorted(set(weeks))}
-        return torch.stack([per_week[w] for w in weeks])
+        """(num_steps,) per-step R with the values of `effective_r(t)`; 3 launches forward, 2 backward (autograd through 21 stacked
+        scalars took ~50).  Index tensors and the constant Jacobian are cached per (num_steps, R2.shape)."""
+        r = self.r_tensor()
+        key = (int(num_steps), tuple(r.shape), r.device)
+        cached = self._r_index.get(key)
+        if cached is None:
+            eye = self._week_one_hot.to(r.device)
+            weeks = [int(t / 7) for t in range(int(num_steps))]
+            used = sorted(set(weeks))
+            pos = torch.tensor([used.index(w) for w in weeks], dtype=torch.long, device=r.device)
+            # one_hot rows of the weeks in use, shaped to broadcast against R2 exactly as `R2 * one_hot[w]` does
+            eye_used = eye[used].reshape(len(used), *([1] * max(r.dim() - 1, 0)), eye.shape[1]).contiguous()
+            full = torch.broadcast_shapes(tuple(r.shape), (eye.shape[1],))
+            jac = torch.stack([torch.broadcast_to(eye[w], full).sum_to_size(r.shape) for w in weeks]).contiguous()
+            cached = self._r_index[key] = (eye_used, pos, jac)
+        eye_used, pos, jac = cached
+        return _StepR.apply(r, eye_used, pos, jac if r.requires_grad else None)
 
     def episode_seed(self):
         """64-bit seed of this episode's noise stream, as a signed int64 (custom-op integer arguments are int64)."""

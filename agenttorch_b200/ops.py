@@ -157,45 +157,53 @@ seirm_progression.register_autograd(_progression_backward, setup_context=_progre
 def seirm_episode(handle: int, stage: Tensor, next_stage_time: Tensor, infected_time: Tensor, age: Tensor,
                   daily_infected: Tensor, daily_deaths: Tensor, r_steps: Tensor, m_value: Tensor,
                   num_steps: int, seed: int, iso_mode: str, p_isolate: float, isolation: Optional[Tensor],
-                  uniform: Optional[Tensor], want_grad: bool, cuda_graph: bool, want_table_grad: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """Advance the agent state IN PLACE through `num_steps` steps.  Returns the new (daily_infected, daily_deaths) and the (T,)
-    reductions saved for backward (sum_dne_dr, death_count); the (T,N) dne_dr and recovered_step buffers stay inside the engine
-    until the next episode."""
+                  uniform: Optional[Tensor], want_grad: bool, cuda_graph: bool, want_table_grad: bool) -> Tuple[Tensor, Tensor]:
+    """Advance the agent state IN PLACE through `num_steps` steps.  Returns the new (daily_infected, daily_deaths); everything
+    saved for backward (the (T,N) dne_dr, recovered_step, the (T,) sum_dne_dr and death_count) stays inside the engine until
+    its next episode (`SeirmEngine.saved_buffers`)."""
     eng = get_engine(handle)
-    # the kernels accumulate into engine-owned series buffers, so that a captured episode is found again whatever address the
-    # caller's (freshly cloned, autograd-carrying) series tensors happen to have
-    bufs = getattr(eng, "_series_bufs", None)
-    if bufs is None or bufs[0].numel() != daily_infected.numel() or bufs[1].numel() != daily_deaths.numel():
-        bufs = eng._series_bufs = (torch.zeros(daily_infected.numel(), dtype=torch.float32, device=daily_infected.device),
-                                   torch.zeros(daily_deaths.numel(), dtype=torch.float32, device=daily_deaths.device))
-    bufs[0].copy_(daily_infected.detach().reshape(-1))
-    bufs[1].copy_(daily_deaths.detach().reshape(-1))
-    st = SeirmState(stage.view(-1), next_stage_time.view(-1), infected_time.view(-1), age.view(-1), bufs[0], bufs[1])
+    # the kernels accumulate this episode's increments into an engine-owned (2, L) buffer that the episode's own launch sequence
+    # zeroes: a captured episode is found again whatever address the caller's (freshly cloned, autograd-carrying) series tensors
+    # have, and the host issues one launch for the two results.  The flattened state views are cached per set of state tensors
+    # (every view is a dispatcher call, and the host - not the GPU - bounds a small shard's episode).
+    n_di, n_dd = daily_infected.numel(), daily_deaths.numel()
+    ck = (stage.data_ptr(), next_stage_time.data_ptr(), infected_time.data_ptr(), age.data_ptr(), stage.numel(), stage.dtype,
+          next_stage_time.dtype, infected_time.dtype, age.dtype, n_di, n_dd)
+    cached = getattr(eng, "_op_state", None)
+    if cached is None or cached[0] != ck:
+        bufs = torch.zeros((2, max(n_di, n_dd)), dtype=torch.float32, device=daily_infected.device)
+        st = SeirmState(stage.view(-1), next_stage_time.view(-1), infected_time.view(-1), age.view(-1), bufs[0, :n_di], bufs[1, :n_dd])
+        cached = eng._op_state = (ck, st, bufs)
+    _, st, bufs = cached
     noise = _noise(seed, iso_mode, p_isolate, isolation, uniform)
     eng.want_table_grad = bool(want_table_grad)
-    sv = eng.run_episode(st, r_steps, m_value, num_steps, noise, want_grad=want_grad, cuda_graph=cuda_graph)
-    return (bufs[0].clone().view_as(daily_infected), bufs[1].clone().view_as(daily_deaths), sv["sum_dne_dr"].clone(),
-            sv["death_count"].clone())
+    eng.run_episode(st, r_steps, m_value, num_steps, noise, want_grad=want_grad, cuda_graph=cuda_graph, zero_series=bufs)
+    if (daily_infected.dtype == torch.float32 and daily_deaths.dtype == torch.float32 and daily_infected.dim() == 1
+            and daily_deaths.dim() == 1 and daily_infected.is_contiguous() and daily_deaths.is_contiguous()):
+        new_di, new_dd = torch._foreach_add([daily_infected, daily_deaths], [st.daily_infected, st.daily_deaths])
+        return new_di, new_dd
+    return ((daily_infected.reshape(-1).float() + st.daily_infected).to(daily_infected.dtype).view_as(daily_infected),
+            (daily_deaths.reshape(-1).float() + st.daily_deaths).to(daily_deaths.dtype).view_as(daily_deaths))
 
 
 @seirm_episode.register_fake
 def _(handle, stage, next_stage_time, infected_time, age, daily_infected, daily_deaths, r_steps, m_value, num_steps, seed, iso_mode,
       p_isolate, isolation, uniform, want_grad, cuda_graph, want_table_grad):
-    return (torch.empty_like(daily_infected), torch.empty_like(daily_deaths),
-            daily_infected.new_empty(num_steps), daily_infected.new_empty(num_steps))
+    return torch.empty_like(daily_infected), torch.empty_like(daily_deaths)
 
 
 @torch.library.custom_op("agenttorch_b200::seirm_episode_backward", mutates_args=())
 def seirm_episode_backward(handle: int, num_steps: int, g_daily_infected: Tensor, g_daily_deaths: Tensor,
-                           m_value: Tensor) -> Tuple[Tensor, Tensor]:
+                           m_value: Tensor) -> Tensor:
+    """(num_steps + 1,): dL/d(per-step R) followed by dL/dM (one buffer: one launch, one all-reduce on several GPUs)."""
     eng = get_engine(handle)
     sv = eng.saved_buffers(num_steps, True)
-    return eng.episode_backward(sv, num_steps, g_daily_infected, g_daily_deaths, m_value)
+    return eng.episode_backward_packed(sv, num_steps, g_daily_infected, g_daily_deaths, m_value)
 
 
 @seirm_episode_backward.register_fake
 def _(handle, num_steps, g_daily_infected, g_daily_deaths, m_value):
-    return g_daily_infected.new_empty(num_steps), g_daily_infected.new_empty(1)
+    return g_daily_infected.new_empty(num_steps + 1)
 
 
 class _SeirmEpisodeFn(torch.autograd.Function):
@@ -207,7 +215,7 @@ class _SeirmEpisodeFn(torch.autograd.Function):
     def forward(ctx, handle, stage, next_stage_time, infected_time, age, daily_infected, daily_deaths, r_steps, m_value, sfs, sfi,
                 num_steps, seed, iso_mode, p_isolate, isolation, uniform, want_grad, cuda_graph):
         table_grad = bool(want_grad and ((sfs is not None and sfs.requires_grad) or (sfi is not None and sfi.requires_grad)))
-        di, dd, _, _ = seirm_episode(handle, stage, next_stage_time, infected_time, age, daily_infected, daily_deaths,
+        di, dd = seirm_episode(handle, stage, next_stage_time, infected_time, age, daily_infected, daily_deaths,
                                      r_steps.detach(), m_value.detach(), num_steps, seed, iso_mode, p_isolate, isolation, uniform,
                                      want_grad, cuda_graph, table_grad)
         ctx.handle, ctx.num_steps, ctx.want_grad, ctx.table_grad = handle, num_steps, want_grad, table_grad
@@ -223,14 +231,18 @@ class _SeirmEpisodeFn(torch.autograd.Function):
         g_r = g_m = g_sfs = g_sfi = None
         if ctx.want_grad and (g_di is not None or g_dd is not None):
             T = ctx.num_steps
-            zeros = torch.zeros(T, dtype=torch.float32, device=m_value.device)
-            gi = zeros if g_di is None else g_di.reshape(-1)[:T]
-            gd = zeros if g_dd is None else g_dd.reshape(-1)[:T]
-            gr, gm = seirm_episode_backward(ctx.handle, T, gi, gd, m_value)
-            g_r = torch.zeros(ctx.r_shape, dtype=gr.dtype, device=gr.device).reshape(-1)
-            g_r[:T] = gr
-            g_r = g_r.reshape(ctx.r_shape)
-            g_m = gm.expand(m_value.numel()).reshape(ctx.m_shape).clone()
+            zeros = torch.zeros(T, dtype=torch.float32, device=m_value.device) if (g_di is None or g_dd is None) else None
+            gi = zeros if g_di is None else (g_di if g_di.dim() == 1 and g_di.numel() == T else g_di.reshape(-1)[:T])
+            gd = zeros if g_dd is None else (g_dd if g_dd.dim() == 1 and g_dd.numel() == T else g_dd.reshape(-1)[:T])
+            packed = seirm_episode_backward(ctx.handle, T, gi, gd, m_value)
+            gr, gm = packed[:T], packed[T:]
+            if r_steps.numel() == T:
+                g_r = gr.reshape(ctx.r_shape)
+            else:
+                g_r = torch.zeros(ctx.r_shape, dtype=gr.dtype, device=gr.device).reshape(-1)
+                g_r[:T] = gr
+                g_r = g_r.reshape(ctx.r_shape)
+            g_m = gm.reshape(ctx.m_shape) if m_value.numel() == 1 else gm.expand(m_value.numel()).reshape(ctx.m_shape).clone()
             if ctx.table_grad:
                 eng = get_engine(ctx.handle)
                 gs, gf = eng.table_gradients(eng.saved_buffers(T, True), T, gi, gd, m_value, r_steps, age)

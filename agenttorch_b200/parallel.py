@@ -48,4 +48,4 @@ def reduce_daily_series(state, group=None):
     if dist.get_world_size(group) > 1:
         dist.all_reduce(packed, group=group)
     n = di.numel()
-    return packed[:n].reshape(di.shape).clone(), packed[n:].reshape(dd.shape).clone()
+    return packed[:n].reshape(di.shape), packed[n:].reshape(dd.shape)          # views of the fresh packed tensor

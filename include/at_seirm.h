@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AT_SEIRM_ABI_VERSION 9
+#define AT_SEIRM_ABI_VERSION 10
 #define AT_MAX_SFS 16        /* SFSusceptibility entries (config.yaml has 9)                     */
 #define AT_MAX_SFI 8         /* SFInfector entries (config.yaml has 5)                           */
 #define AT_MAX_LAMGAMMA 84   /* lam_gamma_integrals entries; 1 + 3*K infectiousness codes fit a byte */
@@ -246,13 +246,18 @@ int at_seirm_step(const at_seirm_model* model, const at_seirm_launch* launch, vo
  *   grad_m[0] = sum_t g_daily_deaths[t] * death_count[t]
  * dne_dr is (T, ld) row-major with the first n_rows entries of each row used.  step_skipped (or NULL): steps whose dne_dr row
  * was left untouched by the forward because the epidemic was over (at_seirm_launch.step_skipped); they count as all zero.
+ * infected_time (or NULL; timer_dtype as in at_seirm_launch): the agents' infected_time as the episode left it.  An agent is an
+ * exposure candidate only up to the step of its (last) exposure, so dne_dr[t,i] == 0 for t > infected_time[i] and those
+ * entries are not fetched.  Pass NULL when something other than the transmission substep may have made an agent susceptible
+ * again during the episode (an intervention hook): every entry is fetched then.
  */
 int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld,
                               const float* dne_dr, const uint8_t* recovered_step,
                               const float* sum_dne_dr, const float* death_count,
                               const float* g_daily_infected, const float* g_daily_deaths,
                               const float* m_value, float* grad_r, float* grad_m,
-                              void* workspace, int32_t grid, const int32_t* step_skipped, void* stream);
+                              void* workspace, int32_t grid, const int32_t* step_skipped,
+                              const void* infected_time, int32_t timer_dtype, void* stream);
 
 /*
  * at_seirm_hot_from_code — multi-GPU helper: after the ranks' code slices have been all-gathered (the per-step halo

@@ -167,6 +167,12 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift)
 }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline unsigned __vminu4(unsigned a, unsigned b)        // per-byte unsigned minimum
+{
+    unsigned r = 0;
+    for (int k = 0; k < 32; k += 8) { unsigned x = (a >> k) & 255u, y = (b >> k) & 255u; r |= (x < y ? x : y) << k; }
+    return r;
+}
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline unsigned __brev(unsigned v)
 {

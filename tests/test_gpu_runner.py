@@ -120,8 +120,10 @@ def test_repeated_fused_episodes_with_restore_state(tmp_path):
                            "environment": {"daily_infected": env["daily_infected"].clone(), "daily_deaths": env["daily_deaths"].clone()}},
                           compact={"disease_stage": torch.uint8, "next_stage_time": torch.int16, "infected_time": torch.int16})
     dev = runner.initializer.device
-    for rep in range(3):
+    for rep in range(5):
         runner.restore_state(snap)
+        if rep >= 2:
+            snap.prefetch(dev)                                       # episodes 3.. restore from the prefetched staging buffer
         if rep == 1:                                                 # a very different episode in between: R2 x 6
             big = torch.tensor(g_soft["r2"] * 6, dtype=torch.float32, device=dev, requires_grad=True)
             runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": big})

@@ -277,3 +277,27 @@ def test_core_exports_match_the_reference_package():
     assert runner.is_vectorized and isinstance(runner, core.Runner)
     assert runner.vectorized_functions["transition"] == {"0/new_transmission": True, "1/seirm_progression": True}
     assert runner.vectorized_functions["policy"] == {"0/citizens/make_isolation_decision": True}
+
+
+def test_packed_snapshot_round_trip_on_host_tensors():
+    """PackedSnapshot: compact dtypes, one buffer, restore into live tensors (storage kept); a lossy compact dtype is refused"""
+    from agenttorch_b200.core.snapshot import PackedSnapshot
+
+    stage = torch.tensor([[0.0], [1.0], [2.0], [3.0]])
+    nst = torch.tensor([[500.0], [3.0], [5.0], [41.0]])
+    env = torch.linspace(0, 1, 21)
+    snap = PackedSnapshot({"agents": {"citizens": {"disease_stage": stage, "next_stage_time": nst}}, "environment": {"daily_infected": env}},
+                          compact={"disease_stage": torch.uint8, "next_stage_time": torch.int16}, pin=False)
+    assert snap.payload_bytes() == 4 * 1 + 4 * 2 + 21 * 4
+    live = {"agents": {"citizens": {"disease_stage": torch.zeros(4, 1), "next_stage_time": torch.zeros(4, 1)}},
+            "environment": {"daily_infected": torch.zeros(21)}}
+    keep = live["agents"]["citizens"]["disease_stage"]
+    for _ in range(3):                       # alternating staging buffers
+        keep.fill_(7.0)
+        snap.prefetch("cpu")                 # a no-op off the GPU
+        snap.restore_into(live)
+        assert live["agents"]["citizens"]["disease_stage"] is keep and torch.equal(keep, stage)
+        assert torch.equal(live["agents"]["citizens"]["next_stage_time"], nst)
+        assert torch.equal(live["environment"]["daily_infected"], env)
+    with pytest.raises(ValueError):
+        PackedSnapshot({"a": {"stage": torch.tensor([0.5, 1.0])}}, compact={"stage": torch.uint8}, pin=False)

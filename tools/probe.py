@@ -25,7 +25,13 @@ ap.add_argument("--epc", type=int, default=0)
 ap.add_argument("--grid", type=int, default=0)
 ap.add_argument("--bank", type=int, default=1)
 ap.add_argument("--warps", type=int, default=0)
+ap.add_argument("--lib", default="")          # a variant build of libat_seirm.so (kernel experiments)
+ap.add_argument("--f32", type=int, default=0)  # reference layout: float32 timers and ages (what the Runner path carries)
+ap.add_argument("--brief", type=int, default=0)
 args = ap.parse_args()
+if args.lib:
+    from agenttorch_b200 import _native
+    _native.LIB_PATH = os.path.abspath(args.lib)
 dev = torch.device("cuda:0")
 T = args.steps
 age, stage0 = synthetic_population(args.n, 1234, device=dev)
@@ -39,7 +45,7 @@ r_steps = torch.full((T,), 3 * args.r2, device=dev)
 m = torch.tensor([0.12], device=dev)
 noise = NoiseSpec(seed=5, isolation=args.iso)
 for rep in range(args.reps):
-    st = SeirmState.from_initial(stage0, age, T, dev)
+    st = SeirmState.from_initial(stage0, age, T, dev, packed=not args.f32)
     sv = eng.saved_buffers(T, bool(args.grad))
     sv["r_steps"].copy_(r_steps); sv["m_value"].copy_(m); eng.seed_buf.fill_(5)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(T + 2)]
@@ -57,7 +63,11 @@ for rep in range(args.reps):
         sus = None
         print("encode us %.1f" % times[0])
         di = st.daily_infected.tolist()
-        for t in range(T):
+        hot = [times[t + 1] for t in range(T) if times[t + 1] > 100.0]
+        print("hot steps: mean %.1f us  min %.1f  max %.1f  (n=%d)   inert mean %.1f us" % (
+            sum(hot) / max(len(hot), 1), min(hot) if hot else 0, max(hot) if hot else 0, len(hot),
+            sum(x for x in times[1:] if x <= 100.0) / max(1, T - len(hot))))
+        for t in range(T if not args.brief else 0):
             bytes_ = args.n * (4 * graph.num_edges / args.n + 41)
             print("t=%2d  %8.1f us  %6.2f TB/s(alg)  new_inf=%d" % (t, times[t + 1], bytes_ / times[t + 1] / 1e6, di[t]))
         tot = sum(times[1:])

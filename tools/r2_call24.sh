@@ -1,0 +1,1 @@
+python tools/probe_host.py --agents 1050000 > gpurun_out/r24_host_1m.log 2>&1; head -5 gpurun_out/r24_host_1m.log
