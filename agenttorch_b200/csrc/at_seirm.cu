@@ -1684,26 +1684,58 @@ seirm_episode_bwd_kernel(int T, int64_t n, int64_t ld, const float* __restrict__
     // steps the forward skipped (epidemic over: their dne rows were not written and mean zero)
     const bool skip0 = skipped != nullptr && lane < T && skipped[lane] != 0;
     const bool skip1 = skipped != nullptr && lane + 32 < T && skipped[lane + 32] != 0;
-    const int64_t ngroups = (n + 31) >> 5;
+    // scan: a warp takes 512 agents per round, lane <-> 16 consecutive agents (one 128-bit load of recovered_step); `hit` = the
+    // lane's agents with c != 0 that can have been exposure candidates inside the episode
+    const int64_t ngroups = (n + 511) >> 9;
     const int64_t wstride = (int64_t)gridDim.x * (AT_BWD_THREADS / 32);
     for (int64_t g = (int64_t)blockIdx.x * (AT_BWD_THREADS / 32) + warp; g < ngroups; g += wstride) {
-        const int64_t i = g * 32 + lane;
-        const float c = (i < n) ? s_gd[rstep[i]] : 0.f;
-        int last = BWD_MAXT;                        // the last step at which this agent can have been an exposure candidate
-        if (itime != nullptr && c != 0.f) last = load_timer(itime, i, itime_f32 != 0);
-        uint32_t mask = __ballot_sync(0xffffffffu, c != 0.f && last >= 0);
-        while (mask) {
-            // four recovered agents per round: their (independent) loads are in flight together, the adds keep agent order
+        const int64_t base = g * 512 + (int64_t)lane * 16;
+        uint32_t rs[4] = {0u, 0u, 0u, 0u};
+        if (base + 16 <= n && (reinterpret_cast<uintptr_t>(rstep) & 15) == 0) {
+            const uint4 v = *reinterpret_cast<const uint4*>(rstep + base);
+            rs[0] = v.x; rs[1] = v.y; rs[2] = v.z; rs[3] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)                                              // 255 = never recovered
+                rs[k >> 2] |= (base + k < n ? (uint32_t)rstep[base + k] : 255u) << ((k & 3) * 8);
+        }
+        // byte k of the lane's 16 (selects, so that the words stay in registers)
+        auto rbyte = [&](int k) -> uint32_t {
+            const uint32_t w = k < 8 ? (k < 4 ? rs[0] : rs[1]) : (k < 12 ? rs[2] : rs[3]);
+            return (w >> ((k & 3) * 8)) & 255u;
+        };
+        uint32_t hit = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (s_gd[(rs[k >> 2] >> ((k & 3) * 8)) & 255u] != 0.f) hit |= 1u << k;
+        if (itime != nullptr) {
+            // agents infected before the episode (the seeds) were never candidates in it
+            for (uint32_t h = hit; h != 0u; h &= h - 1u) {
+                const int k = __ffs((int)h) - 1;
+                if (load_timer(itime, base + k, itime_f32 != 0) < 0) hit &= ~(1u << k);
+            }
+        }
+        while (__any_sync(0xffffffffu, hit != 0u)) {
+            // four agents per round: their (independent) loads are in flight together, the adds keep agent order
             float ci[4], v0[4], v1[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 ci[j] = 0.f; v0[j] = 0.f; v1[j] = 0.f;
-                if (mask) {
-                    const int src = __ffs(mask) - 1;
-                    mask &= mask - 1u;
+                const uint32_t any = __ballot_sync(0xffffffffu, hit != 0u);
+                if (any) {
+                    const int src = __ffs((int)any) - 1;
+                    int k = 0, last = BWD_MAXT;
+                    float c = 0.f;
+                    if (lane == src) {
+                        k = __ffs((int)hit) - 1;
+                        hit &= hit - 1u;
+                        c = s_gd[rbyte(k)];
+                        if (itime != nullptr) last = load_timer(itime, base + k, itime_f32 != 0);
+                    }
+                    k = __shfl_sync(0xffffffffu, k, src);
                     ci[j] = __shfl_sync(0xffffffffu, c, src);
                     const int upto = __shfl_sync(0xffffffffu, last, src);
-                    const int64_t agent = g * 32 + src;
+                    const int64_t agent = g * 512 + (int64_t)src * 16 + k;
                     if (lane < T && !skip0 && lane <= upto) v0[j] = dne[(int64_t)lane * ld + agent];
                     if (lane + 32 < T && !skip1 && lane + 32 <= upto) v1[j] = dne[(int64_t)(lane + 32) * ld + agent];
                 }
@@ -2003,7 +2035,7 @@ int at_seirm_episode_backward(int32_t num_steps, int64_t n_rows, int64_t ld, con
         return fail("%s", "null argument");
     if (device_props()) return fail("%s", "cannot query device");
     int g = grid > 0 ? grid : g_sm_count * 6;
-    const int64_t tiles = (n_rows + AT_BWD_THREADS * 8 - 1) / (AT_BWD_THREADS * 8);
+    const int64_t tiles = (n_rows + AT_BWD_THREADS * 16 - 1) / (AT_BWD_THREADS * 16);       // a CTA round covers 8 warps x 512 agents
     if (g > tiles) g = (int)tiles;
     if (g > BWD_MAX_GRID) g = BWD_MAX_GRID;
     if (g < 1) g = 1;

@@ -75,7 +75,10 @@ for rep in range(args.reps):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         if args.grad:
             gi = torch.ones(T, device=dev); gd = torch.ones(T, device=dev)
-            e0.record(); gr, gm = eng.episode_backward(sv, T, gi, gd, m); e1.record(); torch.cuda.synchronize()
-            print("bwd %.1f us" % (e0.elapsed_time(e1) * 1e3), gr[:4].tolist(), gm.tolist())
+            for prune in (False, True, True):
+                # (run_episode() hands the backward pass a copy of infected_time, so that it skips dne_dr entries after an agent's exposure)
+                sv["itime_copy"], sv["itime_valid"] = st.infected_time, prune
+                e0.record(); gr, gm = eng.episode_backward(sv, T, gi, gd, m); e1.record(); torch.cuda.synchronize()
+                print("bwd (pruned by infected_time: %s) %.1f us" % (prune, e0.elapsed_time(e1) * 1e3), gr[:4].tolist(), gm.tolist())
         print("checksum", int((st.stage.double() * torch.arange(1, args.n + 1, device=dev).double()).sum().item()) % 1000003, int(st.next_stage_time.long().sum()), int(st.infected_time.long().sum()))
         print("stage hist", torch.bincount(st.stage.round().long().clamp(0, 3), minlength=4).tolist())
