@@ -1054,31 +1054,32 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     char* ws = reinterpret_cast<char*>(a.workspace);
 
     if (tid == 0) { s_any_out = 0; s_any_ei = 0; s_ncand = 0; s_nei = 0; }
-    for (int c = tid; c < 256; c += TU_THREADS) {
-        float av = 0.f, gv = 0.f;
-        if (c >= 1 && c <= 3 * m.n_lg) {
-            const int sidx = (c - 1) / m.n_lg, idx = (c - 1) % m.n_lg;
-            av = sidx < m.n_sfi ? m.sfi[sidx] : 0.f;
-            gv = m.lg[idx];
-        }
-        s_A[c] = av;
-        s_G[c] = gv;
-    }
-    __syncthreads();
-    // fixed-point term table of this step, built by the gather launch (stream_build_term_table)
-    {
-        const long long* tab = reinterpret_cast<const long long*>(ws + WS_FIXTAB);
-        for (int i = tid; i < n_tab; i += TU_THREADS) s_fix[i] = tab[i];
-    }
-    const int fx_shift = *reinterpret_cast<const int*>(ws + WS_FIXSHIFT);
-    __syncthreads();
     // epidemic over on entry (nobody of any rank in E or I after the previous step): no record, no candidate, no progression.
     // The (T, N) saved-for-backward rows of this step are then left untouched (step_skipped tells the backward pass) and,
     // from the second such step on, so are the code / hot buffers (both of them are zero by then).
     const int over_in = (a.over_state != nullptr) ? *reinterpret_cast<const volatile int*>(a.over_state) : 0;
     const bool skip_saved = over_in >= 1 && a.step_skipped != nullptr;
     const bool skip_codes = over_in >= 2;
+    const bool idle = over_in >= 1 && skip_codes && (skip_saved || !GRAD);      // nothing to do for any tile: no tables either
     if (blockIdx.x == 0 && tid == 0 && a.step_skipped != nullptr) a.step_skipped[t] = skip_saved ? 1 : 0;
+    int fx_shift = 0;
+    if (!idle) {
+        for (int c = tid; c < 256; c += TU_THREADS) {
+            float av = 0.f, gv = 0.f;
+            if (c >= 1 && c <= 3 * m.n_lg) {
+                const int sidx = (c - 1) / m.n_lg, idx = (c - 1) % m.n_lg;
+                av = sidx < m.n_sfi ? m.sfi[sidx] : 0.f;
+                gv = m.lg[idx];
+            }
+            s_A[c] = av;
+            s_G[c] = gv;
+        }
+        // fixed-point term table of this step, built by the gather launch (stream_build_term_table)
+        const long long* tab = reinterpret_cast<const long long*>(ws + WS_FIXTAB);
+        for (int i = tid; i < n_tab; i += TU_THREADS) s_fix[i] = tab[i];
+        fx_shift = *reinterpret_cast<const int*>(ws + WS_FIXSHIFT);
+    }
+    __syncthreads();
     const double inv_scale = ldexp(1.0, -fx_shift);             // exact power of two
     const double inv_r = (R != 0.f) ? 1.0 / (double)R : 1.0;
 
@@ -1115,7 +1116,7 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
         const int row_base = tile * tile_rows;
         const int rows_here = min(tile_rows, n_rows - row_base);        // valid rows of the tile (<= 0: padding only)
-        if (over_in >= 1 && skip_codes && (skip_saved || !GRAD)) break;     // nothing left to do for any tile
+        if (idle) break;
         const uint32_t nrec = nrec_next;
         const uint32_t* recs = a.rec + base_next;
         uint32_t rec0 = 0u, rec1 = 0u;

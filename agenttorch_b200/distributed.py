@@ -60,7 +60,7 @@ class _EpisodeFn(torch.autograd.Function):
         if not ctx.want_grad:
             return None, None, None, None, None
         T = ctx.num_steps
-        gr, gm = ctx.runner.engine.episode_backward(ctx.sv, T, g_di.reshape(-1)[:T].contiguous(), g_dd.reshape(-1)[:T].contiguous(), m_value)
+        gr, gm = ctx.runner.engine.episode_backward(ctx.sv, T, g_di, g_dd, m_value)     # (the engine flattens / trims if it has to)
         g_m = gm.reshape(ctx.m_shape) if m_value.numel() == 1 else gm.expand(m_value.numel()).reshape(ctx.m_shape).clone()
         return None, gr.reshape(ctx.r_shape), g_m, None, None
 
