@@ -1062,8 +1062,21 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     const bool skip_codes = over_in >= 2;
     const bool idle = over_in >= 1 && skip_codes && (skip_saved || !GRAD);      // nothing to do for any tile: no tables either
     if (blockIdx.x == 0 && tid == 0 && a.step_skipped != nullptr) a.step_skipped[t] = skip_saved ? 1 : 0;
+    if (idle) {
+        // nothing to do and nothing to publish but zeros: no tables, no tiles, no ticket (888 CTAs queueing for one atomic cost more
+        // than everything else an idle launch does).  over_state is >= 2 whichever CTA reads it when, so CTA 0 may advance it alone.
+        if (blockIdx.x == 0 && tid == 0) {
+            if (a.sum_dne_dr) a.sum_dne_dr[t] = 0.f;
+            if (do_prog && a.death_count) a.death_count[t] = 0.f;
+            if (a.over_state != nullptr && a.over_local) {
+                *a.over_state = over_in + 1;
+                reinterpret_cast<unsigned int*>(ws + WS_HASEI)[a.xchg_slot] = 0u;
+            }
+        }
+        return;
+    }
     int fx_shift = 0;
-    if (!idle) {
+    {
         for (int c = tid; c < 256; c += TU_THREADS) {
             float av = 0.f, gv = 0.f;
             if (c >= 1 && c <= 3 * m.n_lg) {
@@ -1116,7 +1129,6 @@ stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
     for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
         const int row_base = tile * tile_rows;
         const int rows_here = min(tile_rows, n_rows - row_base);        // valid rows of the tile (<= 0: padding only)
-        if (idle) break;
         const uint32_t nrec = nrec_next;
         const uint32_t* recs = a.rec + base_next;
         uint32_t rec0 = 0u, rec1 = 0u;

@@ -313,7 +313,7 @@ class SeirmEngine:
         # hashed mode on one GPU: the folded filter of each hot bitmap, produced by the launch that writes the bitmap
         self.filt = None
         if g.hash_words:
-            self.filt = [torch.zeros(g.hash_words + 4, dtype=torch.int32, device=dev) for _ in range(2)]
+            self.filt = [torch.zeros(g.hash_words + 4, dtype=torch.int32, device=dev) for _ in range(3 if self.overlap else 2)]   # one per code buffer
         nt = g.n_tasks
         self.sus = torch.zeros(nt, dtype=torch.int32, device=dev)
         self.exp = torch.zeros(nt, dtype=torch.int32, device=dev)
