@@ -142,7 +142,7 @@ def lib():
         L.at_seirm_exchange_sparse.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
                                                ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
-                                               ctypes.c_void_p]
+                                               ctypes.c_void_p, ctypes.c_void_p]
         L.at_noise_fill.restype = ctypes.c_int
         L.at_noise_fill.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32,
                                     ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]

@@ -1561,7 +1561,7 @@ struct PeerBufs { uint8_t* p[16]; };
 __global__ void __launch_bounds__(256)
 exchange_sparse_kernel(uint8_t* __restrict__ local, int64_t n_sources, uint32_t* __restrict__ filter, int hash_words,
                        PeerBufs peers, int world, int rank, int64_t per, uint32_t* sync_state, uint32_t* any_word,
-                       int32_t* error_flag, int32_t* over_state, int over_after)
+                       int32_t* error_flag, int32_t* over_state, int over_after, const uint32_t* __restrict__ halo_mask)
 {
     // sync_state: [0] epoch of this buffer, [1] CTA ticket, [2 + r] "my copy of rank r's slice holds non-zero data"
     __shared__ uint32_t s_epoch;
@@ -1623,9 +1623,16 @@ exchange_sparse_kernel(uint8_t* __restrict__ local, int64_t n_sources, uint32_t*
     for (int64_t w0 = warp_id * 32; w0 < n_words; w0 += n_warps * 32) {
         const int owner = (int)((w0 * 32) / per);             // a 1024-source tile never straddles two slices
         if (s_skip[owner]) continue;
+        // halo mask: the 32-source groups of a peer's slice that some edge of this rank's rows refers to (one bit per group, one
+        // mask word per warp round); the others are neither read nor written
+        uint32_t wanted = 0xFFFFFFFFu;
+        if (halo_mask != nullptr && owner != rank) {
+            wanted = halo_mask[w0 >> 5];
+            if (wanted == 0u) continue;
+        }
         const int64_t w = w0 + lane;
         uint32_t word = 0;
-        if (w < n_words) {
+        if (w < n_words && ((wanted >> lane) & 1u)) {
             if (owner == rank) {
                 word = hot_local[w];
             } else {
@@ -2099,7 +2106,8 @@ int64_t at_seirm_exchange_bytes(int64_t n_sources) {
 
 int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* hot_filter, int32_t hash_words,
                              void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, void* step_workspace,
-                             int32_t* error_flag, int32_t max_ctas, int32_t* over_state, int32_t over_after, void* stream) {
+                             int32_t* error_flag, int32_t max_ctas, int32_t* over_state, int32_t over_after,
+                             const uint32_t* halo_mask, void* stream) {
     if (!local_buf || !peer_buf || !sync_state) return fail("%s", "exchange_sparse: null buffer");
     if (n_sources <= 0 || (n_sources & 1023)) return fail("%s", "exchange_sparse: n_sources must be a positive multiple of 1024");
     if (world < 2 || world > 16 || rank < 0 || rank >= world || (n_sources % world) || ((n_sources / world) & 1023))
@@ -2125,7 +2133,7 @@ int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* ho
     if (grid < 1) grid = 1;
     uint32_t* any_word = step_workspace ? reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(step_workspace) + WS_ANYHOT) : nullptr;
     AT_LAUNCH(exchange_sparse_kernel, grid, 256, s, local_buf, n_sources, hot_filter, hash_words, pb, world, rank, n_sources / world,
-                                                sync_state, any_word, error_flag, over_state, over_after < 1 ? 2 : over_after);
+                                                sync_state, any_word, error_flag, over_state, over_after < 1 ? 2 : over_after, halo_mask);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("exchange_sparse_kernel launch: %s", cudaGetErrorString(e));
     return 0;

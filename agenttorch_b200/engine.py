@@ -201,6 +201,11 @@ class SeirmEngine:
         if layout == "auto" and not isinstance(graph, BlockedGraph):
             bcsr_only = (hashed or hash_words or edges_per_chunk or graph.edge_weight is not None) and graph.edge_layer is None
             layout = "bcsr" if bcsr_only else "stream"
+        # Multi-GPU: which 32-source groups (bitmap words, code sectors) do the edges of THIS rank's rows refer to?  The halo
+        # exchange pulls only those (include/at_seirm.h, halo_mask); from the plain CSR, before it is re-blocked.
+        self.halo_groups = None
+        if process_group is not None and not isinstance(graph, BlockedGraph) and graph.num_edges > 0:
+            self.halo_groups = torch.unique(graph.col_idx[: graph.num_edges].to(torch.int64) >> 5)
         if isinstance(graph, BlockedGraph):
             self.graph = graph
         elif layout == "stream":
@@ -249,6 +254,15 @@ class SeirmEngine:
             # (the stream gather zero-fills what the last block's bitmap lacks; the older kernels read whole blocks)
             self.n_code = max(self.n_code, g.n_blocks * g.block_size)
         dev = self.device
+        self.halo_mask = None
+        if self.halo_groups is not None:
+            n_mask = self.n_code // 1024
+            acc = torch.zeros(n_mask, dtype=torch.int64, device=dev)
+            grp = self.halo_groups.to(dev)
+            acc.index_add_(0, grp >> 5, torch.ones_like(grp) << (grp & 31))            # groups are unique: the sum is the OR
+            acc = torch.where(acc >= (1 << 31), acc - (1 << 32), acc)                      # as the int32 bit pattern
+            self.halo_mask = acc.to(torch.int32)
+            self.halo_fraction = float(grp.numel()) / max(self.n_code // 32, 1)            # share of the population's groups this rank pulls from
         # Multi-GPU: the code arrays live in symmetric memory when available, so that the per-step halo exchange is a
         # device-side barrier + peer copies over NVLink that can be captured into the episode's CUDA graph (NCCL
         # collectives could not).  symmetric=None: try, fall back to the NCCL all-gather.
@@ -487,7 +501,8 @@ class SeirmEngine:
                                                             _ptr(self.xsync[buf_index]), _ptr(self.workspace) + 4 * int(slot),
                                                             _ptr(self.error_flag), int(max_ctas),
                                                             _ptr(self.over, torch.int32) if self._use_over else None,
-                                                            len(self.xbuf), ctypes.c_void_p(stream)))
+                                                            len(self.xbuf), _ptr(self.halo_mask, torch.int32),
+                                                            ctypes.c_void_p(stream)))
             else:
                 hdl.barrier(channel=buf_index)                   # every rank has written its slice of this buffer
                 # dense: pull the peers' whole slices (P2P loads) + rebuild bitmap/filter from the codes, one kernel

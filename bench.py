@@ -515,6 +515,11 @@ def ours(args):
         "layout": {"name": "stream" if engine.graph.layout == 1 else "bcsr", "source_blocks": engine.graph.n_blocks,
                    "block_size": engine.graph.block_size, "tile_rows": engine.graph.tile_rows},
     }
+    if world > 1 and getattr(engine, "halo_mask", None) is not None:
+        # share of the population's 32-agent groups this rank's edges refer to (its own included): what the halo exchange may pull;
+        # 1.0 on the uniformly random graph of this workload, less on a graph with community structure (--family comm)
+        line["halo"] = {"groups_referenced_fraction_rank0": engine.halo_fraction, "exchange": "sparse pull of hot 32-byte code sectors "
+                        "inside the rank's halo mask" if engine.sparse_exchange and engine.code_hdl is not None else "whole slices"}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n_s = args.cpu_sample_agents

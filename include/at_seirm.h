@@ -293,12 +293,17 @@ int at_seirm_pull_codes(uint8_t* code, int64_t n_sources, uint32_t* hot_bitmap, 
  * it, and once it has reached over_after (the number of code buffers in rotation: every stale copy has been cleared by then) the
  * call returns without a rendezvous — identically on every rank, because every rank saw the same signals.  The caller zeroes
  * it when an episode starts.  A peer that never arrives sets *error_flag = 2 after ~20 s.
+ * halo_mask (or NULL = everything): one bit per 32-source group (= per bitmap word and 32-byte code sector), n_sources / 1024
+ * words: set iff some edge of THIS rank's rows has its source in the group.  Groups outside the mask are neither read from
+ * the peers nor written locally (their local copy stays zero), so what crosses NVLink is the infectiousness of the rank's
+ * boundary (halo) agents only — the whole population only when every group is referenced, as on a uniformly random graph.
  * Replaces nothing in the reference (core/distributed_runner.py:218-228 is `pass`).
  */
 int64_t at_seirm_exchange_bytes(int64_t n_sources);
 int at_seirm_exchange_sparse(uint8_t* local_buf, int64_t n_sources, uint32_t* hot_filter, int32_t hash_words,
                              void* const* peer_buf, int32_t world, int32_t rank, uint32_t* sync_state, void* step_workspace,
-                             int32_t* error_flag, int32_t max_ctas, int32_t* over_state, int32_t over_after, void* stream);
+                             int32_t* error_flag, int32_t max_ctas, int32_t* over_state, int32_t over_after,
+                             const uint32_t* halo_mask, void* stream);
 
 /*
  * at_noise_fill — materialise the counter-hash noise (same values the step kernel generates in

@@ -35,11 +35,15 @@ def _episode(rank, world, port, out_dir, cuda_graph):
     bounds = shard_bounds(N, world)
     r0, r1 = bounds[rank]
     age, stage0 = synthetic_population(N, SEED, device=dev)
-    full = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, mean_interactions=mean_interactions_from_age(age))
-    graph = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, row_begin=r0, row_end=r1)
+    # "comm": a graph with community structure (99.8 % of an agent's contacts inside its block of 1024 ids), exchanged like "sync":
+    # the rank's edges refer to a part of the peer's agents only, the halo mask of the exchange leaves the rest alone
+    comm = cuda_graph == "comm"
+    gkw = {"family": "comm", "block": 1024, "p_local": 0.998} if comm else {}
+    full = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, mean_interactions=mean_interactions_from_age(age), **gkw)
+    graph = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, row_begin=r0, row_end=r1, **gkw)
     graph.i_bar, graph.i_bar_agent = full.i_bar, full.i_bar_agent
     dense = cuda_graph == "dense"                                  # symmetric memory, barrier + whole-slice pull
-    sync = cuda_graph == "sync"                                    # sparse exchange on the critical path (no look-ahead encoding)
+    sync = cuda_graph in ("sync", "comm")                          # sparse exchange on the critical path (no look-ahead encoding)
     cuda_graph = bool(cuda_graph)
     eng = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=shard_code_len(N, world),
                       symmetric=None if cuda_graph else False,      # False: NCCL all-gather path
@@ -59,13 +63,22 @@ def _episode(rank, world, port, out_dir, cuda_graph):
         dist.all_reduce(di); dist.all_reduce(dd)
     gr, gm = eng.episode_backward(sv, T, torch.linspace(0.5, 1.5, T, device=dev), torch.linspace(2, 1, T, device=dev), m)
     eng.check_errors()
+    halo = None
+    if world > 1 and comm:
+        groups = torch.zeros(eng.n_code // 32, dtype=torch.bool, device=dev)
+        groups[eng.halo_groups] = True
+        outside = ~groups.repeat_interleave(32)
+        outside[r0:r1] = False                                     # the rank's own slice is not pulled
+        halo = {"fraction": eng.halo_fraction,
+                "stray": sum(int((buf[: eng.n_code][outside] != 0).sum()) for buf in eng.xbuf),
+                "pulled": sum(int((buf[: eng.n_code][~outside] != 0).sum()) for buf in eng.xbuf)}
     torch.save({"stage": st.stage.cpu(), "nst": st.next_stage_time.cpu(), "di": di.cpu(), "dd": dd.cpu(), "gr": gr.cpu(), "gm": gm.cpu(),
-                "bounds": bounds}, os.path.join(out_dir, f"w{world}_r{rank}.pt"))
+                "bounds": bounds, "halo": halo}, os.path.join(out_dir, f"w{world}_r{rank}.pt"))
     if world > 1:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cuda_graph", [False, True, "sync", "dense"])
+@pytest.mark.parametrize("cuda_graph", [False, True, "sync", "dense", "comm"])
 def test_two_gpus_reproduce_one_gpu(tmp_path, cuda_graph):
     """False: NCCL all-gather, issued step by step.  True: symmetric memory, one kernel per step with the rendezvous
     inside and a bitmap-directed sparse pull, issued on a side stream for step t+2 while step t+1 computes (look-ahead
@@ -75,7 +88,7 @@ def test_two_gpus_reproduce_one_gpu(tmp_path, cuda_graph):
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
 
-    mp.spawn(_episode, args=(1, 0, str(tmp_path), False), nprocs=1, join=True)
+    mp.spawn(_episode, args=(1, 0, str(tmp_path), "comm" if cuda_graph == "comm" else False), nprocs=1, join=True)
     mp.spawn(_episode, args=(2, _free_port(), str(tmp_path), cuda_graph), nprocs=2, join=True)
     one = torch.load(os.path.join(str(tmp_path), "w1_r0.pt"))
     parts = [torch.load(os.path.join(str(tmp_path), f"w2_r{r}.pt")) for r in range(2)]
@@ -85,6 +98,9 @@ def test_two_gpus_reproduce_one_gpu(tmp_path, cuda_graph):
     # deaths: every rank adds f32(count_r) * M, so the all-reduced series differs from f32(count) * M by f32 rounding
     np.testing.assert_allclose(parts[0]["dd"].numpy(), one["dd"].numpy(), rtol=1e-6)
     assert float(one["di"].sum()) > 1000                        # a real epidemic happened
+    if cuda_graph == "comm":
+        for p in parts:                                         # nothing outside the halo mask was ever written, something inside was
+            assert p["halo"]["stray"] == 0 and p["halo"]["pulled"] > 0 and p["halo"]["fraction"] < 0.95
     np.testing.assert_allclose(parts[0]["gr"].numpy(), one["gr"].numpy(), rtol=1e-6)
     np.testing.assert_allclose(parts[0]["gm"].numpy(), one["gm"].numpy(), rtol=1e-6)
 

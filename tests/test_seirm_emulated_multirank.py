@@ -81,6 +81,11 @@ class _SharedSymmetricMemory(types.ModuleType):
 
 def _episode(rank, world, port, out_dir, lib_path, exchange, tag):
     sys.path.insert(0, ROOT)
+    # "<exchange>+comm": a contact graph with community structure (99.5 % of an agent's contacts inside its block of 256 ids), so
+    # that a rank's edges refer to a part of the peers' agents only and the halo mask of the exchange has something to leave out
+    label = exchange
+    exchange, _, family = exchange.partition("+")
+    gkw = {"family": "comm", "block": 256, "p_local": 0.995} if family == "comm" else {}
     import torch.distributed as dist
 
     from agenttorch_b200 import _native, engine
@@ -108,8 +113,8 @@ def _episode(rank, world, port, out_dir, lib_path, exchange, tag):
         bounds = shard_bounds(N, world)
         r0, r1 = bounds[rank]
         age, stage0 = synthetic_population(N, SEED, initial_exposed=EXPOSED0, device="cpu")
-        full = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", mean_interactions=mean_interactions_from_age(age))
-        graph = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", row_begin=r0, row_end=r1)
+        full = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", mean_interactions=mean_interactions_from_age(age), **gkw)
+        graph = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", row_begin=r0, row_end=r1, **gkw)
         graph.i_bar, graph.i_bar_agent = full.i_bar, full.i_bar_agent
         eng = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=shard_code_len(N, world), warps_per_cta=2,
                           symmetric=(exchange != "allgather") if world > 1 else None, sparse_exchange=exchange.startswith("sparse"),
@@ -126,8 +131,18 @@ def _episode(rank, world, port, out_dir, lib_path, exchange, tag):
             dist.all_reduce(di); dist.all_reduce(dd)
         gr, gm = eng.episode_backward(sv, T, torch.linspace(0.5, 1.5, T), torch.linspace(2, 1, T), m)
         eng.check_errors()
-        torch.save({"stage": st.stage, "nst": st.next_stage_time, "itime": st.infected_time, "di": di, "dd": dd, "gr": gr, "gm": gm},
-                   os.path.join(out_dir, f"{exchange}_w{world}_r{rank}.pt"))
+        halo = None
+        if world > 1 and exchange.startswith("sparse"):
+            # the rank's copies of the peers' code bytes: nothing outside the halo mask may ever have been written
+            groups = torch.zeros(eng.n_code // 32, dtype=torch.bool)
+            groups[eng.halo_groups] = True
+            outside = ~groups.repeat_interleave(32)
+            outside[r0:r1] = False                                       # the rank's own slice is not pulled
+            stray = sum(int((buf[: eng.n_code][outside] != 0).sum()) for buf in eng.xbuf)
+            pulled_any = sum(int((buf[: eng.n_code][~outside] != 0).sum()) for buf in eng.xbuf)
+            halo = {"fraction": eng.halo_fraction, "stray": stray, "pulled": pulled_any}
+        torch.save({"stage": st.stage, "nst": st.next_stage_time, "itime": st.infected_time, "di": di, "dd": dd, "gr": gr, "gm": gm,
+                    "halo": halo}, os.path.join(out_dir, f"{label}_w{world}_r{rank}.pt"))
     finally:
         if world > 1:
             dist.barrier()
@@ -143,6 +158,28 @@ def single_rank(emulated_library, tmp_path_factory):
     out = str(tmp_path_factory.mktemp("single"))
     mp.spawn(_episode, args=(1, 0, out, emulated_library, "single", "single"), nprocs=1, join=True)
     return torch.load(os.path.join(out, "single_w1_r0.pt"))
+
+
+def test_halo_exchange_pulls_only_what_the_ranks_edges_refer_to(emulated_library, tmp_path):
+    """community graph, 2 and 4 emulated ranks: same trajectories as one rank, and the sparse exchange neither reads nor writes the
+    32-agent groups no edge of the rank refers to (include/at_seirm.h, halo_mask)"""
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path)
+    mp.spawn(_episode, args=(1, 0, out, emulated_library, "single+comm", "single"), nprocs=1, join=True)
+    one = torch.load(os.path.join(out, "single+comm_w1_r0.pt"))
+    assert float(one["di"].sum()) > 50                                                       # an epidemic happened
+    for exchange, world in (("sparse_sync+comm", 2), ("sparse+comm", 4)):
+        tag = f"{os.getpid()}_halo_{world}"
+        mp.spawn(_episode, args=(world, _free_port(), out, emulated_library, exchange, tag), nprocs=world, join=True)
+        parts = [torch.load(os.path.join(out, f"{exchange}_w{world}_r{r}.pt")) for r in range(world)]
+        assert torch.equal(torch.cat([p["stage"] for p in parts]), one["stage"])
+        assert torch.equal(torch.cat([p["nst"] for p in parts]), one["nst"])
+        assert torch.equal(torch.cat([p["itime"] for p in parts]), one["itime"])
+        assert torch.equal(parts[0]["di"], one["di"])
+        for p in parts:
+            assert p["halo"]["stray"] == 0 and p["halo"]["pulled"] > 0
+            assert p["halo"]["fraction"] < 0.95                          # the mask really leaves groups out
 
 
 @pytest.mark.parametrize("exchange,world", [("allgather", 2), ("sparse", 2), ("sparse_sync", 2), ("dense", 2), ("sparse", 4)])
