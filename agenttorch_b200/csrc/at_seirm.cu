@@ -1021,9 +1021,13 @@ stream_gather_lean_kernel(const KModel m, const at_seirm_launch a, const int bm_
 // 254 us -> 201 us (profiles/r02_step_kernels_8p4M.md).
 // The per-row logic is the one of seirm_kernel's update_subtask (the generic kernel), restated for launches with
 // transmission (row bitmaps valid, no AT_DO_INIT).
+#ifndef TU_THREADS
 #define TU_THREADS 256
+#endif
 #define TU_MAX_TASKS (AT_STREAM_MAX_TILE_ROWS / 32)
+#ifndef TU_MIN_CTAS
 #define TU_MIN_CTAS 6               // resident update CTAs per SM the register budget is cut for (40 registers; measured: 8 -> 6 CTAs: -5 % per hot step)
+#endif
 template <bool TF32, bool GRAD>
 __global__ void __launch_bounds__(TU_THREADS, TU_MIN_CTAS)
 stream_update_kernel(const KModel m, const at_seirm_launch a, const int NC)
