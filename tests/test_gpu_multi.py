@@ -39,11 +39,33 @@ def _episode(rank, world, port, out_dir, cuda_graph):
     # the rank's edges refer to a part of the peer's agents only, the halo mask of the exchange leaves the rest alone
     comm = cuda_graph == "comm"
     gkw = {"family": "comm", "block": 1024, "p_local": 0.998} if comm else {}
-    full = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, mean_interactions=mean_interactions_from_age(age), **gkw)
-    graph = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, row_begin=r0, row_end=r1, **gkw)
-    graph.i_bar, graph.i_bar_agent = full.i_bar, full.i_bar_agent
+    part = cuda_graph == "part"
+    if part:
+        # the community structure hidden behind RANDOM agent ids, recovered by the partitioner (agenttorch_b200/partition.py: balanced
+        # label propagation into 2 parts, relabelled part by part with the boundary agents last) — the same relabelling on one GPU
+        # and on two, so both simulate the same population; exchanged like "sync"
+        from agenttorch_b200 import partition
+        from agenttorch_b200.graph import build_contact_graph, shard_graph
+
+        hidden = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, family="comm", block=1024, p_local=0.998)
+        rp = hidden.row_ptr.long()
+        perm = torch.randperm(N, generator=torch.Generator().manual_seed(SEED + 2)).to(dev)
+        edges = torch.stack([perm[hidden.col_idx[: hidden.num_edges].long()],
+                             perm[torch.repeat_interleave(torch.arange(N, device=dev), rp[1:] - rp[:-1])]])
+        labels = partition.label_propagation_partition(edges, N, 2, rounds=15)
+        cut_before = partition.edge_cut_fraction(edges[0], edges[1], partition.label_propagation_partition(edges, N, 2, rounds=0))
+        cut_after = partition.edge_cut_fraction(edges[0], edges[1], labels)
+        edges, moved, _ = partition.reorder_population(edges, {"age": age, "stage0": stage0}, labels)
+        age, stage0 = moved["age"], moved["stage0"]
+        full = build_contact_graph(edges, N, mean_interactions=mean_interactions_from_age(age), device=dev)
+        graph = shard_graph(full, r0, r1)
+        comm = True                                                # the halo checks below apply
+    else:
+        full = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, mean_interactions=mean_interactions_from_age(age), **gkw)
+        graph = synthetic_contact_graph(N, DEG, SEED + 1, device=dev, row_begin=r0, row_end=r1, **gkw)
+        graph.i_bar, graph.i_bar_agent = full.i_bar, full.i_bar_agent
     dense = cuda_graph == "dense"                                  # symmetric memory, barrier + whole-slice pull
-    sync = cuda_graph in ("sync", "comm")                          # sparse exchange on the critical path (no look-ahead encoding)
+    sync = cuda_graph in ("sync", "comm", "part")                  # sparse exchange on the critical path (no look-ahead encoding)
     cuda_graph = bool(cuda_graph)
     eng = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=shard_code_len(N, world),
                       symmetric=None if cuda_graph else False,      # False: NCCL all-gather path
@@ -69,7 +91,7 @@ def _episode(rank, world, port, out_dir, cuda_graph):
         groups[eng.halo_groups] = True
         outside = ~groups.repeat_interleave(32)
         outside[r0:r1] = False                                     # the rank's own slice is not pulled
-        halo = {"fraction": eng.halo_fraction,
+        halo = {"fraction": eng.halo_fraction, "cut": (cut_before, cut_after) if part else None,
                 "stray": sum(int((buf[: eng.n_code][outside] != 0).sum()) for buf in eng.xbuf),
                 "pulled": sum(int((buf[: eng.n_code][~outside] != 0).sum()) for buf in eng.xbuf)}
     torch.save({"stage": st.stage.cpu(), "nst": st.next_stage_time.cpu(), "di": di.cpu(), "dd": dd.cpu(), "gr": gr.cpu(), "gm": gm.cpu(),
@@ -78,7 +100,7 @@ def _episode(rank, world, port, out_dir, cuda_graph):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cuda_graph", [False, True, "sync", "dense", "comm"])
+@pytest.mark.parametrize("cuda_graph", [False, True, "sync", "dense", "comm", "part"])
 def test_two_gpus_reproduce_one_gpu(tmp_path, cuda_graph):
     """False: NCCL all-gather, issued step by step.  True: symmetric memory, one kernel per step with the rendezvous
     inside and a bitmap-directed sparse pull, issued on a side stream for step t+2 while step t+1 computes (look-ahead
@@ -88,7 +110,7 @@ def test_two_gpus_reproduce_one_gpu(tmp_path, cuda_graph):
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
 
-    mp.spawn(_episode, args=(1, 0, str(tmp_path), "comm" if cuda_graph == "comm" else False), nprocs=1, join=True)
+    mp.spawn(_episode, args=(1, 0, str(tmp_path), cuda_graph if cuda_graph in ("comm", "part") else False), nprocs=1, join=True)
     mp.spawn(_episode, args=(2, _free_port(), str(tmp_path), cuda_graph), nprocs=2, join=True)
     one = torch.load(os.path.join(str(tmp_path), "w1_r0.pt"))
     parts = [torch.load(os.path.join(str(tmp_path), f"w2_r{r}.pt")) for r in range(2)]
@@ -98,9 +120,11 @@ def test_two_gpus_reproduce_one_gpu(tmp_path, cuda_graph):
     # deaths: every rank adds f32(count_r) * M, so the all-reduced series differs from f32(count) * M by f32 rounding
     np.testing.assert_allclose(parts[0]["dd"].numpy(), one["dd"].numpy(), rtol=1e-6)
     assert float(one["di"].sum()) > 1000                        # a real epidemic happened
-    if cuda_graph == "comm":
+    if cuda_graph in ("comm", "part"):
         for p in parts:                                         # nothing outside the halo mask was ever written, something inside was
             assert p["halo"]["stray"] == 0 and p["halo"]["pulled"] > 0 and p["halo"]["fraction"] < 0.95
+            if cuda_graph == "part":                            # random ids cut half of the edges; the partitioner finds the communities
+                assert p["halo"]["cut"][0] > 0.45 and p["halo"]["cut"][1] < 0.1
     np.testing.assert_allclose(parts[0]["gr"].numpy(), one["gr"].numpy(), rtol=1e-6)
     np.testing.assert_allclose(parts[0]["gm"].numpy(), one["gm"].numpy(), rtol=1e-6)
 

@@ -113,9 +113,27 @@ def _episode(rank, world, port, out_dir, lib_path, exchange, tag):
         bounds = shard_bounds(N, world)
         r0, r1 = bounds[rank]
         age, stage0 = synthetic_population(N, SEED, initial_exposed=EXPOSED0, device="cpu")
-        full = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", mean_interactions=mean_interactions_from_age(age), **gkw)
-        graph = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", row_begin=r0, row_end=r1, **gkw)
-        graph.i_bar, graph.i_bar_agent = full.i_bar, full.i_bar_agent
+        if family == "part":
+            # a community graph whose agents carry RANDOM ids (the structure is there, the numbering hides it), partitioned by
+            # agenttorch_b200.partition into 4 parts and relabelled part by part, boundary agents last — the same relabelling at
+            # every world size, so one rank and several ranks simulate the same population
+            from agenttorch_b200 import partition
+            from agenttorch_b200.graph import build_contact_graph, shard_graph
+
+            hidden = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", family="comm", block=256, p_local=0.995)
+            rp = hidden.row_ptr.long()
+            perm = torch.randperm(N, generator=torch.Generator().manual_seed(SEED + 2))
+            edges = torch.stack([perm[hidden.col_idx[: hidden.num_edges].long()],
+                                 perm[torch.repeat_interleave(torch.arange(N), rp[1:] - rp[:-1])]])
+            labels = partition.label_propagation_partition(edges, N, 4, rounds=15)
+            edges, moved, _ = partition.reorder_population(edges, {"age": age, "stage0": stage0}, labels)
+            age, stage0 = moved["age"], moved["stage0"]
+            full = build_contact_graph(edges, N, mean_interactions=mean_interactions_from_age(age), device="cpu")
+            graph = shard_graph(full, r0, r1)
+        else:
+            full = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", mean_interactions=mean_interactions_from_age(age), **gkw)
+            graph = synthetic_contact_graph(N, DEG, SEED + 1, device="cpu", row_begin=r0, row_end=r1, **gkw)
+            graph.i_bar, graph.i_bar_agent = full.i_bar, full.i_bar_agent
         eng = SeirmEngine(graph, SeirmSpec(num_steps=T), process_group=pg, code_len=shard_code_len(N, world), warps_per_cta=2,
                           symmetric=(exchange != "allgather") if world > 1 else None, sparse_exchange=exchange.startswith("sparse"),
                           overlap_exchange=(exchange == "sparse") if world > 1 else None,
@@ -161,15 +179,20 @@ def single_rank(emulated_library, tmp_path_factory):
 
 
 def test_halo_exchange_pulls_only_what_the_ranks_edges_refer_to(emulated_library, tmp_path):
-    """community graph, 2 and 4 emulated ranks: same trajectories as one rank, and the sparse exchange neither reads nor writes the
-    32-agent groups no edge of the rank refers to (include/at_seirm.h, halo_mask)"""
+    """community graph, 2 emulated ranks: same trajectories as one rank, and the sparse exchange neither reads nor writes the
+    32-agent groups no edge of the rank refers to (include/at_seirm.h, halo_mask).  "+part": the community structure is hidden
+    behind random agent ids and recovered by the partitioner (agenttorch_b200/partition.py) before the ranks take their ranges."""
     import torch.multiprocessing as mp
 
     out = str(tmp_path)
     mp.spawn(_episode, args=(1, 0, out, emulated_library, "single+comm", "single"), nprocs=1, join=True)
-    one = torch.load(os.path.join(out, "single+comm_w1_r0.pt"))
-    assert float(one["di"].sum()) > 50                                                       # an epidemic happened
-    for exchange, world in (("sparse_sync+comm", 2), ("sparse+comm", 4)):
+    one_comm = torch.load(os.path.join(out, "single+comm_w1_r0.pt"))
+    assert float(one_comm["di"].sum()) > 50                                                  # an epidemic happened
+    mp.spawn(_episode, args=(1, 0, out, emulated_library, "single+part", "single"), nprocs=1, join=True)
+    one_part = torch.load(os.path.join(out, "single+part_w1_r0.pt"))
+    assert float(one_part["di"].sum()) > 50
+    for exchange, world in (("sparse_sync+comm", 2), ("sparse_sync+part", 2)):
+        one = one_part if exchange.endswith("+part") else one_comm
         tag = f"{os.getpid()}_halo_{world}"
         mp.spawn(_episode, args=(world, _free_port(), out, emulated_library, exchange, tag), nprocs=world, join=True)
         parts = [torch.load(os.path.join(out, f"{exchange}_w{world}_r{r}.pt")) for r in range(world)]
