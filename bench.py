@@ -461,6 +461,21 @@ def ours(args):
     d_act = edges / N
     bytes_per_step = (N / world) * (4.0 * d_act + 41.0)
 
+    def ncu_traffic():
+        """DRAM bytes (read + written) of the two launches of one hot step, from the committed `ncu --set full` capture of this
+        build's kernels on this workload (profiles/r02b_ncu_full_summary.csv); one GPU only, None if the file is absent."""
+        path = os.path.join(ROOT, "profiles", "r02b_ncu_full_summary.csv")
+        if world != 1 or N != 8_400_000 or not os.path.exists(path):
+            return None
+        import csv
+
+        rows = {r[0]: r for r in csv.reader(open(path)) if r}
+        try:
+            cols = [i for i, h in enumerate(rows["metric"]) if "stream_gather_kernel" in h or "stream_update_kernel" in h]
+            return sum(float(rows[m][i]) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum") for i in cols) * 1e6
+        except (KeyError, ValueError, IndexError):
+            return None
+
     def roofline_of(times, active):
         act = [x for x, a in zip(times, active) if a]
         inert = [x for x, a in zip(times, active) if not a]
@@ -468,7 +483,7 @@ def ours(args):
         ach = bytes_per_step / (mean_act / 1e3) / 1e9 if act else None
         ach_all = bytes_per_step / (sum(times) / len(times) / 1e3) / 1e9
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                "traffic": None, "kernel": "stream_gather_kernel + stream_update_kernel (the two launches of one simulation step)",
+                "traffic": traffic_bytes, "kernel": "stream_gather_kernel + stream_update_kernel (the two launches of one simulation step)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_step,
                 "active_launches": len(act), "active_launch_ms": {"mean": mean_act, "min": min(act) if act else None, "max": max(act) if act else None},
                 "inert_launches": len(inert), "inert_launch_ms_mean": (sum(inert) / len(inert)) if inert else None,
@@ -481,7 +496,9 @@ def ours(args):
                         "gather reads the stream once: dram bytes = algorithmic col bytes + 3 % padding)"}
 
     times_s, active_s, _ = profile_episode("soft")
+    traffic_bytes = ncu_traffic()
     roofline = roofline_of(times_s, active_s)
+    traffic_bytes = None                      # (the capture is of the soft workload)
     hard = None
     if not args.no_hard:
         times_h, active_h, di_h = profile_episode("hard")
