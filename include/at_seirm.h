@@ -204,13 +204,13 @@ typedef struct at_seirm_launch {
                                    is or will become infectious; agents with a fractional stage never are).  The stream gather then
                                    returns at once.  Zeroed by the caller before the first launch of an episode; maintained by the
                                    launches themselves when over_local != 0 (one GPU), else by at_seirm_exchange_sparse */
-    int32_t over_local;
-    int32_t reserve_sms;
+    int32_t over_local;         /* != 0: one GPU — the update launch itself maintains *over_state (nobody in E or I after this step) */
+    int32_t reserve_sms;        /* stream layout, != 0: the step kernels leave part of every SM free (lean gather entry point with 56
+                                   registers, one update CTA per SM fewer), so that a halo exchange issued on another stream runs
+                                   beside them instead of waiting for them (they otherwise take every register of every SM) */
     int32_t* step_skipped;      /* or NULL: [t] = 1 if this (stream-layout) launch found the epidemic over on entry and therefore
                                    did NOT touch dne_dr / dne_e_dr of step t (they are all zero by meaning; the backward pass skips
-                                   the step), else 0 */        /* stream layout, != 0: the step kernels leave 1/8 of every SM's registers free (lean gather entry
-                                   point, 7 instead of 8 update CTAs per SM), so that a halo exchange issued on another stream runs
-                                   beside them instead of waiting for them (they otherwise take every register of every SM) */
+                                   the step), else 0 */
 } at_seirm_launch;
 
 /* ---- queries (host only) ---- */
