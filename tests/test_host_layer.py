@@ -232,6 +232,32 @@ def test_reference_r_quirk_q2():
     assert runner.state["agents"]["citizens"]["age"].shape == (256, 1)
 
 
+def test_r_steps_equals_the_per_step_expression_with_its_gradient():
+    """`r_steps` (one broadcast product + row sum + gather, constant Jacobian backward) against autograd through the reference's
+    per-step expression `(R2 * one_hot[week]).sum()`: values bit for bit, gradients to float32 rounding, for every R2 shape the
+    reference's broadcast accepts (Q2: a (NUM_WEEKS, 1) R2 sums all weeks)"""
+    cfg = synthetic_config(256, 3.0, device="cpu")
+    runner = Runner(cfg, covid.registry)
+    runner.init()
+    tr = runner.initializer.transition_function["0"]["new_transmission"]
+    gen = torch.Generator().manual_seed(3)
+    for shape in ((3, 1), (3,), (1, 3), (1,), ()):
+        for n_steps in (21, 10, 5):
+            base = torch.rand(shape, generator=gen) * 9 + 0.1
+            a, b = base.clone().requires_grad_(True), base.clone().requires_grad_(True)
+            weight = torch.rand(n_steps, generator=gen)
+            tr.calibrate_R2 = a
+            per_step = torch.stack([tr.effective_r(t) for t in range(n_steps)])
+            (per_step * weight).sum().backward()
+            tr.calibrate_R2 = b
+            fused = tr.r_steps(n_steps)
+            (fused * weight).sum().backward()
+            assert torch.equal(per_step, fused)
+            assert a.grad.shape == b.grad.shape and torch.allclose(a.grad, b.grad, rtol=1e-6, atol=1e-6)
+    tr.calibrate_R2 = torch.rand(3, 1)                           # no gradient requested: no graph
+    assert not tr.r_steps(21).requires_grad
+
+
 def test_models_sharing_helper_names_do_not_break_each_other(tmp_path):
     """The registry tables are class-level (registry.py:8-14) and both models register a `read_from_file`; whichever
     model builds a runner must get its own helpers, whatever the import order."""
