@@ -136,3 +136,18 @@ def test_repeated_fused_episodes_with_restore_state(tmp_path):
                                 "initializer.transition_function.1.seirm_progression.learnable_args.M": m})
         runner.step(g_soft["num_steps"])
         _check(g_soft, runner, r2, m)
+
+
+@pytest.mark.gpu
+def test_r_steps_on_the_device_equals_the_per_step_expression():
+    """the fused per-step R (one broadcast product + row sum) must reproduce the reference's per-step `(R2 * one_hot[week]).sum()`
+    bit for bit on the device too (R enters the exposure probabilities, so a different rounding would change trajectories)"""
+    dev = torch.device("cuda", 0)
+    eye = torch.eye(3, device=dev)
+    gen = torch.Generator(device="cpu").manual_seed(11)
+    for trial in range(200):
+        for shape in ((3, 1), (3,)):
+            r = (torch.rand(shape, generator=gen) * 9 + 0.1).to(dev)
+            per_week = torch.stack([(r * eye[w]).sum() for w in range(3)])
+            fused = (r.unsqueeze(0) * eye.view(3, *([1] * (r.dim() - 1)), 3)).flatten(1).sum(1)
+            assert torch.equal(per_week, fused)
