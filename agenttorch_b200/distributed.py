@@ -125,6 +125,34 @@ class DistributedRunner:
         from .models.covid.context import spec_from_state
 
         net = get_by_path(full, re.split("/", iv["adjacency_matrix"])[:-1])
+        # distributed_config["partition"] = {"parts": P, "rounds": R} (or True: P = world size): re-order the population so that
+        # the ranks' contiguous ranges are communities of the contact graph (partition.py) before anything is sliced.  The agents
+        # get NEW ids (the noise streams follow them): the same `parts` gives the same population at every world size;
+        # gather_final_state() hands the agent tensors back in the original order.
+        self._order = None
+        part_cfg = (self.distributed_config or {}).get("partition")
+        if part_cfg:
+            from . import partition
+
+            part_cfg = part_cfg if isinstance(part_cfg, dict) else {}
+            labels = partition.label_propagation_partition(edge_index, n, int(part_cfg.get("parts", world)),
+                                                           rounds=int(part_cfg.get("rounds", 10)))
+            agent_type = self.config["substeps"]["0"]["active_agents"][0]
+            per_agent = {k: v for k, v in full["agents"][agent_type].items()
+                         if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == n}
+            # (the reference keeps one per-agent tensor in the environment: mean_interactions, config.yaml:219)
+            per_env = {k: v for k, v in full["environment"].items() if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == n}
+            new_edges, moved, order = partition.reorder_population(edge_index, {**{("a", k): v for k, v in per_agent.items()},
+                                                                                **{("e", k): v for k, v in per_env.items()}}, labels)
+            for (where, k), v in moved.items():
+                (full["agents"][agent_type] if where == "a" else full["environment"])[k] = v
+            edge_index = new_edges
+            net["adjacency_matrix"] = (edge_index, edge_attr)                 # (edge order unchanged: edge_attr still applies)
+            net.pop("graph", None)                                            # a prebuilt CSR describes the old numbering
+            self._order = order
+            self.partition_report = {"parts": int(part_cfg.get("parts", world)),
+                                     "edge_cut": partition.edge_cut_fraction(edge_index[0].long(), edge_index[1].long(),
+                                                                             labels[order])}
         prebuilt = net.get("graph") if isinstance(net, dict) else None
         if isinstance(prebuilt, ContactGraph) and prebuilt.num_edges == edge_index.shape[1] and prebuilt.row_offset == 0:
             graph_full = prebuilt.to(edge_index.device)          # the network helper already produced the dst-sorted CSR
@@ -241,5 +269,11 @@ class DistributedRunner:
     def gather_final_state(self):
         self.engine.check_errors()                # e.g. a halo-exchange rendezvous that timed out (device-side flag)
         cit = self.state["agents"][self.config["substeps"]["0"]["active_agents"][0]]
-        return {k: self.gather_agent_states(v) for k, v in cit.items()
-                if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == self.agent_partition_map["local_size"]}
+        out = {k: self.gather_agent_states(v) for k, v in cit.items()
+               if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == self.agent_partition_map["local_size"]}
+        if getattr(self, "_order", None) is not None:                         # back to the population's original agent order
+            for k, v in out.items():
+                orig = torch.empty_like(v)
+                orig[self._order.to(v.device)] = v
+                out[k] = orig
+        return out

@@ -221,7 +221,7 @@ def test_sharded_engine_reproduces_single_rank(emulated_library, single_rank, tm
 # ------------------------------------------------------------------------------------------------------------------
 # envs.create(distributed=True) — the reference's multi-GPU entry point — on two emulated ranks, against the real reference's
 # golden outputs (the 2-GPU version is tests/test_gpu_multi.py::test_distributed_runner_api_matches_reference_golden).
-def _distributed_runner(rank, world, port, out_dir, lib_path, pop_dir, tag):
+def _distributed_runner(rank, world, port, out_dir, lib_path, pop_dir, tag, partition=None):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
 
@@ -261,8 +261,9 @@ def _distributed_runner(rank, world, port, out_dir, lib_path, pop_dir, tag):
     torch.distributed._symmetric_memory = symm
     try:
         g = load_golden("synth3k_soft")
-        runner = envs.create(model=covid, population=pop_dir, distributed=True, world_size=world)
-        assert runner.engine.code_hdl is not None                                # the symmetric-memory exchange is in use
+        runner = envs.create(model=covid, population=pop_dir, distributed=True, world_size=world,
+                             distributed_config=None if partition is None else {"partition": partition})
+        assert (runner.engine.code_hdl is not None) == (world > 1)               # the symmetric-memory exchange is in use
         r2 = torch.tensor(g["r2"], dtype=torch.float32, requires_grad=True)
         m = torch.tensor(g["m"], dtype=torch.float32, requires_grad=True)
         runner._set_parameters({"initializer.transition_function.0.new_transmission.learnable_args.R2": r2,
@@ -276,7 +277,9 @@ def _distributed_runner(rank, world, port, out_dir, lib_path, pop_dir, tag):
         final = runner.gather_final_state()
         assert runner.agent_partition_map["local_size"] == runner.state["agents"]["citizens"]["disease_stage"].shape[0]
         torch.save({"stage": final["disease_stage"], "nst": final["next_stage_time"], "di": env["daily_infected"].detach(),
-                    "dd": env["daily_deaths"].detach(), "gr2": r2.grad, "gm": m.grad}, os.path.join(out_dir, f"dr{rank}.pt"))
+                    "dd": env["daily_deaths"].detach(), "gr2": r2.grad, "gm": m.grad,
+                    "order": getattr(runner, "_order", None), "report": getattr(runner, "partition_report", None)},
+                   os.path.join(out_dir, f"dr{rank}.pt" if partition is None else f"dr_w{world}_{rank}.pt"))
     finally:
         dist.barrier()
         dist.destroy_process_group()
@@ -299,6 +302,36 @@ def test_distributed_runner_api_on_two_emulated_ranks(emulated_library, tmp_path
         assert tuple(o["dd"].shape) == (1, g["num_steps"])
         assert rel_err(g["ref_daily_infected"], o["di"].numpy()) <= 1e-5 and rel_err(g["ref_daily_deaths"], o["dd"].numpy()) <= 1e-5
         assert rel_err(g["ref_grad_R2"], o["gr2"].numpy()) <= 1e-4 and rel_err(g["ref_grad_M"], o["gm"].numpy()) <= 1e-4
+
+
+def test_distributed_runner_partition_option_gives_the_same_population_at_every_world_size(emulated_library, tmp_path):
+    """envs.create(distributed=True, distributed_config={"partition": {"parts": 2}}): the population is re-ordered by the contact-graph
+    partitioner before the ranks take their ranges; one rank and two ranks then simulate the same (relabelled) population, and
+    gather_final_state() returns the agents in the population's original order"""
+    import torch.multiprocessing as mp
+
+    from agenttorch_b200.populations import write_population_folder
+    from tests.helpers import load_golden
+
+    g = load_golden("synth3k_soft")
+    pop = write_population_folder(str(tmp_path / "pop"), g["age"], g["stage0"], g["edges"])
+    part = {"parts": 2, "rounds": 4}
+    for world in (1, 2):
+        mp.spawn(_distributed_runner, args=(world, _free_port(), str(tmp_path), emulated_library, pop, f"{os.getpid()}_pt{world}", part),
+                 nprocs=world, join=True)
+    one = torch.load(os.path.join(str(tmp_path), "dr_w1_0.pt"))
+    n = one["stage"].shape[0]
+    assert one["order"] is not None and not torch.equal(one["order"], torch.arange(n))     # a real relabelling happened
+    assert torch.equal(torch.sort(one["order"]).values, torch.arange(n)) and 0.0 <= one["report"]["edge_cut"] <= 1.0
+    assert float(one["di"].sum()) > 10                                                       # an epidemic happened
+    for r in range(2):
+        o = torch.load(os.path.join(str(tmp_path), f"dr_w2_{r}.pt"))
+        assert torch.equal(o["order"], one["order"])
+        assert torch.equal(o["stage"], one["stage"]) and torch.equal(o["nst"], one["nst"])  # original agent order, bit for bit
+        np.testing.assert_allclose(o["di"].numpy(), one["di"].numpy(), rtol=1e-6)
+        np.testing.assert_allclose(o["dd"].numpy(), one["dd"].numpy(), rtol=1e-6)
+        np.testing.assert_allclose(o["gr2"].numpy(), one["gr2"].numpy(), rtol=1e-5)
+        np.testing.assert_allclose(o["gm"].numpy(), one["gm"].numpy(), rtol=1e-5)
 
 
 # ------------------------------------------------------------------------------------------------------------------
